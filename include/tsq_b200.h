@@ -1,0 +1,172 @@
+/*
+ * tsq_b200.h -- C ABI of libtsqb200.so, the B200-native all-vs-all Gotoh distance-matrix
+ * backend for tweakseq.
+ *
+ * This is the boundary a tweakseq maintainer binds (INTEGRATION.md shows the stub).  It
+ * replaces, for the pairwise-distance stage only, the process boundary through which
+ * tweakseq reaches its aligner today:
+ *
+ *   tweakseq/Core/AlignmentTool.h:36-71        the wrapper interface (argv builder)
+ *   tweakseq/Core/ClustalO.cpp:48-52           makeCommand(): the clustalo argv
+ *   tweakseq/UI/SeqEditMainWin.cpp:1654-1660   QProcess::start(exec, args)  <- replaced
+ *   tweakseq/UI/SeqEditMainWin.cpp:803-812     alignmentStop(): kill()      <- cancel flag
+ *   tweakseq/UI/SeqEditMainWin.cpp:822-834     stdout/stderr -> MessageWin  <- log callback
+ *   tweakseq/UI/SeqEditMainWin.cpp:836-861     exit code / status           <- int status
+ *
+ * Conventions: plain C99 types only; every function returns an int status (0 = TSQ_OK,
+ * negative = error) unless noted; no exception or abort crosses this boundary; the caller
+ * owns inputs and the context handle, the library owns outputs (valid until the next
+ * tsq_run/tsq_compute/tsq_set_sequences/tsq_destroy on the same context).  A context is not
+ * re-entrant: use one context per thread.  There is NO CPU fallback: without an sm_100
+ * device tsq_create fails with TSQ_ERR_NO_DEVICE.
+ *
+ * Scoring spec: global alignment, end gaps penalised, affine gaps
+ * (a gap of length k costs gap_open + k*gap_extend), substitution matrix BLOSUM62 in the
+ * order and with the values of tweakseq/Core/Annotations/Consensus.cpp:34-69, or a caller
+ * supplied symmetric matrix.  distance(i,j) = 1 - S(i,j)/min(S(i,i),S(j,j)), 1 if that
+ * minimum is <= 0.  Packed upper triangle, row-major: index(i,j) = i*n - i*(i+1)/2 + (j-i-1)
+ * for i < j, over the sequences in the order they were submitted.
+ */
+#ifndef TSQ_B200_H
+#define TSQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSQ_VERSION_MAJOR 0
+#define TSQ_VERSION_MINOR 1
+
+/* status codes */
+#define TSQ_OK 0
+#define TSQ_ERR_INVALID (-1)    /* bad argument / bad parameter block */
+#define TSQ_ERR_NO_DEVICE (-2)  /* no CUDA device of compute capability 10.x */
+#define TSQ_ERR_CUDA (-3)       /* a CUDA runtime call failed; see tsq_last_error */
+#define TSQ_ERR_NOMEM (-4)      /* host or device allocation failed */
+#define TSQ_ERR_CANCELLED (-5)  /* the cancel flag was raised (SeqEditMainWin.cpp:803-812) */
+#define TSQ_ERR_STATE (-6)      /* call out of order (e.g. results before a run) */
+#define TSQ_ERR_IO (-7)         /* FASTA / distance-matrix file could not be read/written */
+#define TSQ_ERR_MATRIX (-8)     /* substitution matrix not symmetric or out of range */
+#define TSQ_ERR_RANGE (-9)      /* scores would not fit the 32-bit kernels */
+
+#define TSQ_PROTEIN 0    /* 23 symbols ARNDCQEGHILKMFPSTWYVBZX, Consensus.cpp:34-69 */
+#define TSQ_NUCLEOTIDE 1 /* 5 symbols ACGTN (U->T, other letters -> N) */
+
+/* flags */
+#define TSQ_FLAG_FORCE_S32 1u     /* never use the packed 16-bit kernel */
+#define TSQ_FLAG_NO_DISTANCES 2u  /* skip the fp64 distance pass (scores only) */
+
+typedef struct tsq_ctx tsq_ctx;
+
+typedef struct tsq_params {
+  uint32_t struct_size;  /* = sizeof(tsq_params); lets the struct grow compatibly */
+  int32_t alphabet;      /* TSQ_PROTEIN | TSQ_NUCLEOTIDE */
+  int32_t gap_open;      /* >= 0; <0 selects the default (protein 11, nucleotide 10) */
+  int32_t gap_extend;    /* >= 0; <0 selects the default (1) */
+  const int8_t *matrix;  /* nsym x nsym row-major, symmetric, or NULL = built-in */
+  int32_t device;        /* CUDA ordinal of the device this context computes on */
+  int32_t part_rank;     /* this context's share of the pair space: rank ... */
+  int32_t part_world;    /* ... of world (1 = everything).  See tsq_partition. */
+  uint32_t flags;        /* TSQ_FLAG_* */
+} tsq_params;
+
+typedef struct tsq_stats {
+  uint64_t n_sequences;
+  uint64_t n_pairs;          /* pairs this context computed (its partition) */
+  uint64_t cells;            /* sum len_i*len_j over those pairs */
+  uint64_t cells_s16;        /* of which in the packed 16-bit inter-task kernel */
+  uint64_t cells_s32;        /* of which in the 32-bit wavefront kernel */
+  double kernel_ms;          /* CUDA-event time of the last tsq_compute (device only) */
+  double upload_ms;          /* host encode/sort/pack + H2D of the last tsq_upload */
+  double download_ms;        /* D2H of the last tsq_download */
+  double gcups_kernel;       /* cells / kernel_ms */
+  uint32_t launches;         /* kernels launched by the last tsq_compute */
+  uint32_t sm_count;
+  uint32_t strip_width;      /* K of the 16-bit kernel variant used */
+  uint32_t reserved;
+} tsq_stats;
+
+/* progress in [0,1]; msg may be NULL.  Return value ignored. */
+typedef void (*tsq_progress_cb)(void *user, double fraction, const char *msg);
+/* one line of log text, no trailing newline (what MessageWin::addMessage would receive) */
+typedef void (*tsq_log_cb)(void *user, const char *line);
+
+int tsq_version(int *major, int *minor);
+/* textual version, what AlignmentTool::version() shows (ClustalO.cpp:100-111) */
+const char *tsq_version_string(void);
+/* static description of a status code */
+const char *tsq_status_string(int status);
+/* Number of usable (compute capability 10.x) devices; <0 = status code. */
+int tsq_device_count(void);
+
+void tsq_default_params(tsq_params *p);
+int tsq_create(tsq_ctx **out, const tsq_params *params);
+int tsq_destroy(tsq_ctx *ctx);
+/* Last error text of this context ("" if none).  Never NULL. */
+const char *tsq_last_error(const tsq_ctx *ctx);
+
+/*
+ * Residues as ASCII letters, one array per sequence, lengths[i] bytes each (no NUL needed).
+ * Case-insensitive; '-', '.', and whitespace are dropped (an aligned project reaches the
+ * tool with gaps still in place: Sequence.cpp:57-69); any other byte maps to X (protein)
+ * or N (nucleotide).  The library copies and encodes; the caller keeps ownership.
+ */
+int tsq_set_sequences(tsq_ctx *ctx, const char *const *residues, const uint32_t *lengths,
+                      uint32_t n);
+
+/* The three stages of a run, separately callable (bench.py times them separately). */
+int tsq_upload(tsq_ctx *ctx);   /* sort/pack on the host, H2D */
+int tsq_compute(tsq_ctx *ctx);  /* enqueue all kernels on the context's stream (async) */
+int tsq_download(tsq_ctx *ctx); /* synchronise, D2H of scores (+ distances) */
+/* Make tsq_compute enqueue on a caller-owned cudaStream_t (passed as void*); NULL = own. */
+int tsq_set_stream(tsq_ctx *ctx, void *cuda_stream);
+/* Block until everything enqueued by tsq_compute has finished. */
+int tsq_synchronize(tsq_ctx *ctx);
+
+/*
+ * upload + compute + download, blocking, cancellable between kernel launches:
+ * *cancel != 0 makes it return TSQ_ERR_CANCELLED.  cb/cancel may be NULL.
+ */
+int tsq_run(tsq_ctx *ctx, tsq_progress_cb cb, void *user, volatile int *cancel);
+
+/* Host results (after tsq_run or tsq_download). count = n*(n-1)/2. */
+int tsq_scores(tsq_ctx *ctx, const int32_t **packed_upper, uint64_t *count);
+int tsq_distances(tsq_ctx *ctx, const double **packed_upper, uint64_t *count);
+int tsq_self_scores(tsq_ctx *ctx, const int32_t **self, uint32_t *n);
+
+/*
+ * Device results (after tsq_compute): pointers into this context's device memory, packed
+ * like the host results.  For world > 1 only [*part_begin, *part_end) of the packed index
+ * space -- in the library's internal length-sorted order -- is filled on this rank; the
+ * host layer gathers the slabs (NCCL) into rank 0 and calls tsq_finalize there.
+ */
+int tsq_device_scores(tsq_ctx *ctx, void **d_sorted_scores, uint64_t *count);
+int tsq_partition(tsq_ctx *ctx, uint64_t *part_begin, uint64_t *part_end);
+/* Sorted-order slab complete on this device -> original-order scores (+distances). */
+int tsq_finalize(tsq_ctx *ctx);
+int tsq_device_results(tsq_ctx *ctx, void **d_scores, void **d_distances, uint64_t *count);
+
+int tsq_get_stats(tsq_ctx *ctx, tsq_stats *out);
+
+/*
+ * Integer-pipe issue-rate probe ("measure, don't assume"): thread-level
+ * VIADDMNMX.U16x2 / VIMNMX3.U16x2 results per clock per SM on this context's device.
+ */
+int tsq_measure_dpx_rate(tsq_ctx *ctx, double *ops_per_clk_per_sm, double *sm_mhz);
+
+/*
+ * File-level convenience for the Qt adapter: read the FASTA file tweakseq
+ * exported (Project.cpp:870-881, FASTAFile.cpp:149-171), compute, and write a square
+ * PHYLIP-style distance matrix (n, then "label d d d ..." rows) that clustalo accepts via
+ * --distmat-in.  Labels follow FASTAFile::parseComment (FASTAFile.cpp:177-187).
+ */
+int tsq_run_fasta(const char *fasta_in, const char *distmat_out, const tsq_params *params,
+                  tsq_log_cb log, void *user, volatile int *cancel);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSQ_B200_H */

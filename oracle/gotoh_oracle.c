@@ -1,0 +1,257 @@
+/*
+ * gotoh_oracle.c -- scalar CPU restatement of the all-vs-all Gotoh distance-matrix path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see gotoh_oracle.h).  PARITY UNPINNED by the reference: there is
+ * no alignment arithmetic in groundstate/tweakseq to restate; the spec
+ * implemented here is the one frozen in SURVEY.md section 8c.
+ *
+ * What follows the reference:
+ *   - matrix values + residue order      tweakseq/Core/Annotations/Consensus.cpp:34-59
+ *   - letter -> index map (J,O,U,X -> X)  tweakseq/Core/Annotations/Consensus.cpp:61-69
+ *   - non-letters are "not a residue"     tweakseq/Core/Annotations/Consensus.cpp:99-105
+ *   - 7-bit residue cells, '-' kept by the editor and therefore stripped here
+ *                                         tweakseq/Core/Sequence.cpp:57-69, Sequence.h:36-39
+ */
+#include "gotoh_oracle.h"
+
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* Rows/columns in the order A R N D C Q E G H I L K M F P S T W Y V B Z X. */
+const int8_t tsq_oracle_blosum62[23 * 23] = {
+    /* A */ 4,  -1, -2, -2, 0,  -1, -1, 0,  -2, -1, -1, -1, -1, -2, -1, 1,  0,  -3, -2, 0,  -2, -1, 0,
+    /* R */ -1, 5,  0,  -2, -3, 1,  0,  -2, 0,  -3, -2, 2,  -1, -3, -2, -1, -1, -3, -2, -3, -1, 0,  -1,
+    /* N */ -2, 0,  6,  1,  -3, 0,  0,  0,  1,  -3, -3, 0,  -2, -3, -2, 1,  0,  -4, -2, -3, 3,  0,  -1,
+    /* D */ -2, -2, 1,  6,  -3, 0,  2,  -1, -1, -3, -4, -1, -3, -3, -1, 0,  -1, -4, -3, -3, 4,  1,  -1,
+    /* C */ 0,  -3, -3, -3, 9,  -3, -4, -3, -3, -1, -1, -3, -1, -2, -3, -1, -1, -2, -2, -1, -3, -3, -2,
+    /* Q */ -1, 1,  0,  0,  -3, 5,  2,  -2, 0,  -3, -2, 1,  0,  -3, -1, 0,  -1, -2, -1, -2, 0,  3,  -1,
+    /* E */ -1, 0,  0,  2,  -4, 2,  5,  -2, 0,  -3, -3, 1,  -2, -3, -1, 0,  -1, -3, -2, -2, 1,  4,  -1,
+    /* G */ 0,  -2, 0,  -1, -3, -2, -2, 6,  -2, -4, -4, -2, -3, -3, -2, 0,  -2, -2, -3, -3, -1, -2, -1,
+    /* H */ -2, 0,  1,  -1, -3, 0,  0,  -2, 8,  -3, -3, -1, -2, -1, -2, -1, -2, -2, 2,  -3, 0,  0,  -1,
+    /* I */ -1, -3, -3, -3, -1, -3, -3, -4, -3, 4,  2,  -3, 1,  0,  -3, -2, -1, -3, -1, 3,  -3, -3, -1,
+    /* L */ -1, -2, -3, -4, -1, -2, -3, -4, -3, 2,  4,  -2, 2,  0,  -3, -2, -1, -2, -1, 1,  -4, -3, -1,
+    /* K */ -1, 2,  0,  -1, -3, 1,  1,  -2, -1, -3, -2, 5,  -1, -3, -1, 0,  -1, -3, -2, -2, 0,  1,  -1,
+    /* M */ -1, -1, -2, -3, -1, 0,  -2, -3, -2, 1,  2,  -1, 5,  0,  -2, -1, -1, -1, -1, 1,  -3, -1, -1,
+    /* F */ -2, -3, -3, -3, -2, -3, -3, -3, -1, 0,  0,  -3, 0,  6,  -4, -2, -2, 1,  3,  -1, -3, -3, -1,
+    /* P */ -1, -2, -2, -1, -3, -1, -1, -2, -2, -3, -3, -1, -2, -4, 7,  -1, -1, -4, -3, -2, -2, -1, -2,
+    /* S */ 1,  -1, 1,  0,  -1, 0,  0,  0,  -1, -2, -2, 0,  -1, -2, -1, 4,  1,  -3, -2, -2, 0,  0,  0,
+    /* T */ 0,  -1, 0,  -1, -1, -1, -1, -2, -2, -1, -1, -1, -1, -2, -1, 1,  5,  -2, -2, 0,  -1, -1, 0,
+    /* W */ -3, -3, -4, -4, -2, -2, -3, -2, -2, -3, -2, -3, -1, 1,  -4, -3, -2, 11, 2,  -3, -4, -3, -2,
+    /* Y */ -2, -2, -2, -3, -2, -1, -2, -3, 2,  -1, -1, -2, -1, 3,  -3, -2, -2, 2,  7,  -1, -3, -2, -1,
+    /* V */ 0,  -3, -3, -3, -1, -2, -2, -3, -3, 3,  1,  -2, 1,  -1, -2, -2, 0,  -3, -1, 4,  -3, -2, -1,
+    /* B */ -2, -1, 3,  4,  -3, 0,  1,  -1, 0,  -3, -4, 0,  -3, -3, -2, 0,  -1, -4, -3, -3, 4,  1,  -1,
+    /* Z */ -1, 0,  0,  1,  -3, 3,  4,  -2, 0,  -3, -3, 1,  -1, -3, -1, 0,  -1, -3, -2, -2, 1,  4,  -1,
+    /* X */ 0,  -1, -1, -1, -2, -1, -1, -1, -1, -1, -1, -1, -1, -1, -2, 0,  0,  -2, -1, -1, -1, -1, -1,
+};
+
+/* A C G T N.  The reference has no nucleotide matrix (Core/DNA.h is colours only); these
+ * EDNAFULL-style values are build-defined and this table is authoritative. */
+const int8_t tsq_oracle_dna[5 * 5] = {
+    /* A */ 5,  -4, -4, -4, -2,
+    /* C */ -4, 5,  -4, -4, -2,
+    /* G */ -4, -4, 5,  -4, -2,
+    /* T */ -4, -4, -4, 5,  -2,
+    /* N */ -2, -2, -2, -2, -1,
+};
+
+/* 'A'..'Z' -> row of tsq_oracle_blosum62 (Consensus.cpp:61-69). */
+static const uint8_t protein_index[26] = {
+    /* A */ 0,  /* B */ 20, /* C */ 4,  /* D */ 3,  /* E */ 6,  /* F */ 13, /* G */ 7,
+    /* H */ 8,  /* I */ 9,  /* J */ 22, /* K */ 11, /* L */ 10, /* M */ 12, /* N */ 2,
+    /* O */ 22, /* P */ 14, /* Q */ 5,  /* R */ 1,  /* S */ 15, /* T */ 16, /* U */ 22,
+    /* V */ 19, /* W */ 17, /* X */ 22, /* Y */ 18, /* Z */ 21,
+};
+
+int tsq_oracle_nsym(int alphabet) { return alphabet == TSQ_ORACLE_NUCLEOTIDE ? 5 : 23; }
+
+const int8_t *tsq_oracle_matrix(int alphabet) {
+  return alphabet == TSQ_ORACLE_NUCLEOTIDE ? tsq_oracle_dna : tsq_oracle_blosum62;
+}
+
+static int is_gap_or_space(unsigned char c) {
+  return c == '-' || c == '.' || c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' ||
+         c == '\f';
+}
+
+size_t tsq_oracle_encode(int alphabet, const char *in, size_t n, uint8_t *out) {
+  size_t k = 0;
+  for (size_t i = 0; i < n; i++) {
+    unsigned char c = (unsigned char)in[i];
+    if (is_gap_or_space(c)) continue;
+    if (c >= 'a' && c <= 'z') c = (unsigned char)(c - 'a' + 'A');
+    if (alphabet == TSQ_ORACLE_NUCLEOTIDE) {
+      uint8_t v = 4;
+      if (c == 'A') v = 0;
+      else if (c == 'C') v = 1;
+      else if (c == 'G') v = 2;
+      else if (c == 'T' || c == 'U') v = 3;
+      out[k++] = v;
+    } else {
+      out[k++] = (c >= 'A' && c <= 'Z') ? protein_index[c - 'A'] : 22;
+    }
+  }
+  return k;
+}
+
+static inline int32_t max2(int32_t a, int32_t b) { return a > b ? a : b; }
+
+int32_t tsq_oracle_gotoh(const uint8_t *a, int m, const uint8_t *b, int n, const int8_t *mat,
+                         int nsym, int go, int ge) {
+  if (m == 0 && n == 0) return 0;
+  if (m == 0) return -(go + n * ge);
+  if (n == 0) return -(go + m * ge);
+  const int32_t NEG = INT32_MIN / 2;
+  const int32_t goe = go + ge;
+  int32_t stackbuf[2 * 1025];
+  int32_t *H = stackbuf;
+  if (n > 1024) {
+    H = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)(n + 1));
+    if (!H) return INT32_MIN;
+  }
+  int32_t *F = H + (n + 1);
+  H[0] = 0;
+  for (int j = 1; j <= n; j++) {
+    H[j] = -(go + j * ge);
+    F[j] = NEG;
+  }
+  for (int i = 1; i <= m; i++) {
+    const int8_t *srow = mat + (size_t)a[i - 1] * nsym;
+    int32_t diag = H[0];
+    int32_t left = -(go + i * ge); /* H[i][0] */
+    int32_t E = NEG;               /* E[i][0] */
+    H[0] = left;
+    for (int j = 1; j <= n; j++) {
+      E = max2(E - ge, left - goe);
+      int32_t f = max2(F[j] - ge, H[j] - goe);
+      int32_t h = diag + srow[b[j - 1]];
+      h = max2(h, max2(E, f));
+      diag = H[j];
+      H[j] = h;
+      F[j] = f;
+      left = h;
+    }
+  }
+  int32_t r = H[n];
+  if (H != stackbuf) free(H);
+  return r;
+}
+
+int32_t tsq_oracle_self_score(const uint8_t *a, int m, const int8_t *mat, int nsym) {
+  int32_t s = 0;
+  for (int k = 0; k < m; k++) s += mat[(size_t)a[k] * nsym + a[k]];
+  return s;
+}
+
+double tsq_oracle_distance(int32_t s_ij, int32_t s_ii, int32_t s_jj) {
+  int32_t mn = s_ii < s_jj ? s_ii : s_jj;
+  if (mn <= 0) return 1.0;
+  double q = (double)s_ij / (double)mn;
+  return 1.0 - q;
+}
+
+uint64_t tsq_oracle_pair_index(uint64_t i, uint64_t j, uint64_t n) {
+  return i * n - i * (i + 1) / 2 + (j - i - 1);
+}
+
+/* ---- multithreaded drivers (also the CPU baseline timed by bench.py) ---- */
+
+typedef struct {
+  const uint8_t *seqs;
+  const uint64_t *offs;
+  const uint32_t *lens;
+  uint32_t n;
+  const int8_t *mat;
+  int nsym, go, ge;
+  uint64_t begin, end;
+  const uint32_t *pi, *pj; /* explicit list, or NULL for the packed range */
+  int32_t *out;
+  uint64_t next; /* atomic chunk cursor */
+  uint64_t cells; /* atomic */
+} job_t;
+
+#define CHUNK 64
+
+static void unpack_pair(uint64_t p, uint64_t n, uint32_t *pi, uint32_t *pj) {
+  /* invert p = i*n - i(i+1)/2 + (j-i-1) by walking rows from a float guess */
+  double nn = (double)n;
+  double disc = (2.0 * nn - 1.0) * (2.0 * nn - 1.0) - 8.0 * (double)p;
+  uint64_t i = 0;
+  if (disc > 0) {
+    double r = ((2.0 * nn - 1.0) - __builtin_sqrt(disc)) / 2.0;
+    if (r > 0) i = (uint64_t)r;
+  }
+  if (i >= n - 1) i = n - 2;
+  while (i > 0 && tsq_oracle_pair_index(i, i + 1, n) > p) i--;
+  while (i + 2 < n && tsq_oracle_pair_index(i + 1, i + 2, n) <= p) i++;
+  uint64_t j = p - tsq_oracle_pair_index(i, i + 1, n) + i + 1;
+  *pi = (uint32_t)i;
+  *pj = (uint32_t)j;
+}
+
+static void *worker(void *arg) {
+  job_t *jb = (job_t *)arg;
+  uint64_t cells = 0;
+  for (;;) {
+    uint64_t s = __atomic_fetch_add(&jb->next, CHUNK, __ATOMIC_RELAXED);
+    if (s >= jb->end) break;
+    uint64_t e = s + CHUNK < jb->end ? s + CHUNK : jb->end;
+    uint32_t i = 0, j = 0;
+    if (!jb->pi) unpack_pair(s, jb->n, &i, &j);
+    for (uint64_t p = s; p < e; p++) {
+      if (jb->pi) {
+        i = jb->pi[p];
+        j = jb->pj[p];
+      }
+      jb->out[p - jb->begin] =
+          tsq_oracle_gotoh(jb->seqs + jb->offs[i], (int)jb->lens[i], jb->seqs + jb->offs[j],
+                           (int)jb->lens[j], jb->mat, jb->nsym, jb->go, jb->ge);
+      cells += (uint64_t)jb->lens[i] * jb->lens[j];
+      if (!jb->pi) {
+        if (++j >= jb->n) {
+          i++;
+          j = i + 1;
+        }
+      }
+    }
+  }
+  __atomic_fetch_add(&jb->cells, cells, __ATOMIC_RELAXED);
+  return NULL;
+}
+
+static uint64_t run_job(job_t *jb, int nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  pthread_t th[256];
+  int started = 0;
+  for (int t = 1; t < nthreads; t++)
+    if (pthread_create(&th[started], NULL, worker, jb) == 0) started++;
+  worker(jb);
+  for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+  return jb->cells;
+}
+
+uint64_t tsq_oracle_all_pairs(const uint8_t *seqs, const uint64_t *offs, const uint32_t *lens,
+                              uint32_t n, const int8_t *mat, int nsym, int go, int ge,
+                              uint64_t pair_begin, uint64_t pair_end, int32_t *out,
+                              int nthreads) {
+  if (n < 2 || pair_end <= pair_begin) return 0;
+  job_t jb;
+  memset(&jb, 0, sizeof jb);
+  jb.seqs = seqs; jb.offs = offs; jb.lens = lens; jb.n = n;
+  jb.mat = mat; jb.nsym = nsym; jb.go = go; jb.ge = ge;
+  jb.begin = pair_begin; jb.end = pair_end; jb.out = out; jb.next = pair_begin;
+  return run_job(&jb, nthreads);
+}
+
+uint64_t tsq_oracle_pair_list(const uint8_t *seqs, const uint64_t *offs, const uint32_t *lens,
+                              const int8_t *mat, int nsym, int go, int ge, const uint32_t *pi,
+                              const uint32_t *pj, uint64_t npairs, int32_t *out, int nthreads) {
+  if (npairs == 0) return 0;
+  job_t jb;
+  memset(&jb, 0, sizeof jb);
+  jb.seqs = seqs; jb.offs = offs; jb.lens = lens; jb.n = 0;
+  jb.mat = mat; jb.nsym = nsym; jb.go = go; jb.ge = ge;
+  jb.begin = 0; jb.end = npairs; jb.pi = pi; jb.pj = pj; jb.out = out; jb.next = 0;
+  return run_job(&jb, nthreads);
+}

@@ -1,0 +1,72 @@
+/*
+ * gotoh_oracle.h -- CPU oracle for the all-vs-all Gotoh distance-matrix path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under tweakseq_b200/ or host/ may include, link or
+ * call this.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs use it, and there only as the checker / the timed CPU baseline.
+ *
+ * PARITY UNPINNED: the reference (groundstate/tweakseq) ships no alignment arithmetic and no
+ * test vectors for this path; it shells out to an external clustalo
+ * binary (tweakseq/Core/ClustalO.cpp:48-52, tweakseq/UI/SeqEditMainWin.cpp:1654-1660) that is
+ * neither vendored nor pinned.  The oracle therefore restates the frozen spec of SURVEY.md
+ * section 8c; what it takes from the reference is the substitution matrix and letter map
+ * (tweakseq/Core/Annotations/Consensus.cpp:34-69) and the residue-cell filtering rule
+ * (tweakseq/Core/Sequence.cpp:57-69).  It is pinned against hand-derived known answers and
+ * an independent numpy formulation in tests/.
+ */
+#ifndef TSQ_GOTOH_ORACLE_H
+#define TSQ_GOTOH_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSQ_ORACLE_PROTEIN 0
+#define TSQ_ORACLE_NUCLEOTIDE 1
+
+/* 23x23, order ARNDCQEGHILKMFPSTWYVBZX (Consensus.cpp:34-59). */
+extern const int8_t tsq_oracle_blosum62[23 * 23];
+/* 5x5, order ACGTN: match +5, mismatch -4, N vs ACGT -2, N vs N -1. */
+extern const int8_t tsq_oracle_dna[5 * 5];
+
+/* Number of symbols of an alphabet (23 or 5). */
+int tsq_oracle_nsym(int alphabet);
+/* Built-in matrix of an alphabet. */
+const int8_t *tsq_oracle_matrix(int alphabet);
+
+/* ASCII -> symbol indices; returns the encoded length (gaps '-', '.', whitespace removed). */
+size_t tsq_oracle_encode(int alphabet, const char *in, size_t n, uint8_t *out);
+
+/* Global affine-gap (Gotoh) score H[m][n]; a gap of length k costs go + k*ge. */
+int32_t tsq_oracle_gotoh(const uint8_t *a, int m, const uint8_t *b, int n,
+                         const int8_t *mat, int nsym, int go, int ge);
+
+/* Sum of mat[a_k][a_k]. */
+int32_t tsq_oracle_self_score(const uint8_t *a, int m, const int8_t *mat, int nsym);
+
+/* d = 1 - s_ij / min(s_ii, s_jj); 1.0 if that minimum is <= 0. */
+double tsq_oracle_distance(int32_t s_ij, int32_t s_ii, int32_t s_jj);
+
+/* Packed upper-triangle index of (i,j), i<j, over n sequences. */
+uint64_t tsq_oracle_pair_index(uint64_t i, uint64_t j, uint64_t n);
+
+/*
+ * Scores of the packed pairs [pair_begin, pair_end) into out[0 .. pair_end-pair_begin),
+ * using nthreads POSIX threads.  seqs = concatenated encoded residues, offs[i] = start of
+ * sequence i, lens[i] = its length.  Returns the number of DP cells evaluated.
+ */
+uint64_t tsq_oracle_all_pairs(const uint8_t *seqs, const uint64_t *offs, const uint32_t *lens,
+                              uint32_t n, const int8_t *mat, int nsym, int go, int ge,
+                              uint64_t pair_begin, uint64_t pair_end, int32_t *out,
+                              int nthreads);
+
+/* Scores of an explicit list of pairs (pi[k], pj[k]); same conventions. */
+uint64_t tsq_oracle_pair_list(const uint8_t *seqs, const uint64_t *offs, const uint32_t *lens,
+                              const int8_t *mat, int nsym, int go, int ge, const uint32_t *pi,
+                              const uint32_t *pj, uint64_t npairs, int32_t *out, int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

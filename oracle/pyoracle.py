@@ -1,0 +1,154 @@
+"""ctypes binding of the CPU oracle (oracle/gotoh_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (tweakseq_b200/) never imports it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libtsq_oracle.so")
+
+PROTEIN, NUCLEOTIDE = 0, 1
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "gotoh_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libtsq_oracle.so"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        u8p, u32p, u64p, i32p, i8p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint32, C.c_uint64, C.c_int32, C.c_int8))
+        L.tsq_oracle_nsym.restype = C.c_int
+        L.tsq_oracle_matrix.restype = i8p
+        L.tsq_oracle_encode.restype = C.c_size_t
+        L.tsq_oracle_encode.argtypes = [C.c_int, C.c_char_p, C.c_size_t, u8p]
+        L.tsq_oracle_gotoh.restype = C.c_int32
+        L.tsq_oracle_gotoh.argtypes = [u8p, C.c_int, u8p, C.c_int, i8p, C.c_int, C.c_int, C.c_int]
+        L.tsq_oracle_self_score.restype = C.c_int32
+        L.tsq_oracle_self_score.argtypes = [u8p, C.c_int, i8p, C.c_int]
+        L.tsq_oracle_distance.restype = C.c_double
+        L.tsq_oracle_distance.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        L.tsq_oracle_pair_index.restype = C.c_uint64
+        L.tsq_oracle_pair_index.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+        L.tsq_oracle_all_pairs.restype = C.c_uint64
+        L.tsq_oracle_all_pairs.argtypes = [u8p, u64p, u32p, C.c_uint32, i8p, C.c_int, C.c_int, C.c_int,
+                                           C.c_uint64, C.c_uint64, i32p, C.c_int]
+        L.tsq_oracle_pair_list.restype = C.c_uint64
+        L.tsq_oracle_pair_list.argtypes = [u8p, u64p, u32p, i8p, C.c_int, C.c_int, C.c_int, u32p, u32p,
+                                           C.c_uint64, i32p, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def nsym(alphabet: int) -> int:
+    return lib().tsq_oracle_nsym(alphabet)
+
+
+def matrix(alphabet: int) -> np.ndarray:
+    n = nsym(alphabet)
+    lib().tsq_oracle_matrix.argtypes = [C.c_int]
+    ptr = lib().tsq_oracle_matrix(alphabet)
+    return np.ctypeslib.as_array(ptr, shape=(n * n,)).reshape(n, n).copy()
+
+
+def encode(seq: str | bytes, alphabet: int = PROTEIN) -> np.ndarray:
+    raw = seq.encode("latin-1", "replace") if isinstance(seq, str) else bytes(seq)
+    out = np.empty(max(len(raw), 1), dtype=np.uint8)
+    k = lib().tsq_oracle_encode(alphabet, raw, len(raw), _p(out, C.c_uint8))
+    return out[:k].copy()
+
+
+def gotoh(a: np.ndarray, b: np.ndarray, mat: np.ndarray, go: int, ge: int) -> int:
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    m8 = np.ascontiguousarray(mat, dtype=np.int8)
+    return int(lib().tsq_oracle_gotoh(_p(a, C.c_uint8), len(a), _p(b, C.c_uint8), len(b), _p(m8, C.c_int8),
+                                      m8.shape[0], go, ge))
+
+
+def score_str(a: str, b: str, alphabet: int = PROTEIN, go: int | None = None, ge: int = 1) -> int:
+    if go is None:
+        go = 11 if alphabet == PROTEIN else 10
+    return gotoh(encode(a, alphabet), encode(b, alphabet), matrix(alphabet), go, ge)
+
+
+def self_score(a: np.ndarray, mat: np.ndarray) -> int:
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    m8 = np.ascontiguousarray(mat, dtype=np.int8)
+    return int(lib().tsq_oracle_self_score(_p(a, C.c_uint8), len(a), _p(m8, C.c_int8), m8.shape[0]))
+
+
+def distance(sij: int, sii: int, sjj: int) -> float:
+    return float(lib().tsq_oracle_distance(sij, sii, sjj))
+
+
+def pair_index(i: int, j: int, n: int) -> int:
+    return int(lib().tsq_oracle_pair_index(i, j, n))
+
+
+def _pack(encoded: list[np.ndarray]):
+    lens = np.array([len(s) for s in encoded], dtype=np.uint32)
+    offs = np.zeros(len(encoded), dtype=np.uint64)
+    if len(encoded) > 1:
+        offs[1:] = np.cumsum(lens[:-1], dtype=np.uint64)
+    flat = np.concatenate(encoded).astype(np.uint8) if lens.sum() else np.zeros(1, np.uint8)
+    return np.ascontiguousarray(flat), offs, lens
+
+
+def all_pairs(encoded: list[np.ndarray], mat: np.ndarray, go: int, ge: int, nthreads: int = 1,
+              pair_begin: int = 0, pair_end: int | None = None):
+    """Scores of packed pairs [pair_begin, pair_end); returns (int32 array, cells)."""
+    n = len(encoded)
+    total = n * (n - 1) // 2
+    if pair_end is None:
+        pair_end = total
+    flat, offs, lens = _pack(encoded)
+    out = np.zeros(max(pair_end - pair_begin, 0), dtype=np.int32)
+    m8 = np.ascontiguousarray(mat, dtype=np.int8)
+    cells = lib().tsq_oracle_all_pairs(_p(flat, C.c_uint8), _p(offs, C.c_uint64), _p(lens, C.c_uint32), n,
+                                       _p(m8, C.c_int8), m8.shape[0], go, ge, pair_begin, pair_end,
+                                       _p(out, C.c_int32), nthreads)
+    return out, int(cells)
+
+
+def pair_list(encoded: list[np.ndarray], pi: np.ndarray, pj: np.ndarray, mat: np.ndarray, go: int, ge: int,
+              nthreads: int = 1):
+    flat, offs, lens = _pack(encoded)
+    pi = np.ascontiguousarray(pi, dtype=np.uint32)
+    pj = np.ascontiguousarray(pj, dtype=np.uint32)
+    out = np.zeros(len(pi), dtype=np.int32)
+    m8 = np.ascontiguousarray(mat, dtype=np.int8)
+    cells = lib().tsq_oracle_pair_list(_p(flat, C.c_uint8), _p(offs, C.c_uint64), _p(lens, C.c_uint32),
+                                       _p(m8, C.c_int8), m8.shape[0], go, ge, _p(pi, C.c_uint32),
+                                       _p(pj, C.c_uint32), len(pi), _p(out, C.c_int32), nthreads)
+    return out, int(cells)
+
+
+def distances(scores: np.ndarray, selfs: np.ndarray) -> np.ndarray:
+    """Packed fp64 distances from packed int32 scores and per-sequence self scores."""
+    n = len(selfs)
+    iu, ju = np.triu_indices(n, 1)
+    mn = np.minimum(selfs[iu], selfs[ju]).astype(np.int64)
+    d = np.ones(len(scores), dtype=np.float64)
+    ok = mn > 0
+    q = scores[ok].astype(np.float64) / mn[ok].astype(np.float64)
+    d[ok] = 1.0 - q
+    return d

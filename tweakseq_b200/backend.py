@@ -1,0 +1,146 @@
+"""Host-side mirror of tweakseq's alignment-tool wrapper interface for the in-process backend.
+
+``AlignmentTool`` restates tweakseq/Core/AlignmentTool.h:36-71 without Qt (same method names,
+argument meaning and defaults: AlignmentTool.cpp:43-63), extended with the two members an
+in-process backend needs: ``inProcess()`` and ``run()``.
+``B200Gotoh`` is the new tool, shaped like tweakseq/Core/ClustalO.cpp:48-111: same settings
+element (``<alignment_tool><name/><path/><preferred/>`` -- ClustalO.cpp:54-61), same
+break-on-name-mismatch parse (ClustalO.cpp:63-86).  The C++ twin a maintainer would compile
+into tweakseq is host/B200Gotoh.{h,cpp}.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import xml.etree.ElementTree as ET
+
+import numpy as np
+
+from . import capi
+from .fasta import filter_cells, read_fasta
+
+
+class AlignmentTool:
+    """Qt-free restatement of tweakseq/Core/AlignmentTool.h:36-71."""
+
+    def __init__(self):
+        self.name_ = ""
+        self.version_ = ""
+        self.executable_ = ""
+        self.preferred_ = False   # AlignmentTool.cpp:59-63
+        self.usesStdOut_ = False
+
+    def name(self): return self.name_
+    def version(self): return self.version_
+    def executable(self): return self.executable_
+    def setExecutable(self, e): self.executable_ = e
+    def setPreferred(self, pref): self.preferred_ = bool(pref)
+    def preferred(self): return self.preferred_
+    def usesStdOut(self): return self.usesStdOut_
+
+    # virtuals; the base class versions are no-ops (AlignmentTool.cpp:43-53)
+    def makeCommand(self, fin, fout):
+        """Returns (exec, arglist); the reference fills two out-parameters."""
+        return "", []
+
+    def writeSettings(self, parent: ET.Element): pass
+    def readSettings(self, doc: ET.Element): pass
+
+    # extension for in-process tools
+    def inProcess(self): return False
+
+    def run(self, fin, fout, log=None, cancel=None):
+        raise NotImplementedError
+
+
+class B200Gotoh(AlignmentTool):
+    """The in-process tool: all-vs-all Gotoh scores + guide-tree distances on a B200."""
+
+    def __init__(self):
+        super().__init__()
+        self.name_ = "b200gotoh"
+        self.executable_ = capi.library_path()   # "path" = the shared library (ClustalO.cpp:96)
+        self.alphabet = capi.PROTEIN
+        self.gap_open = -1
+        self.gap_extend = -1
+        self.device = 0
+        self.last_stats: dict = {}
+
+    def inProcess(self): return True
+
+    def makeCommand(self, fin, fout):
+        # What startAlignment() would exec for an external tool (ClustalO.cpp:48-52).  For the
+        # in-process tool this is informational: clustalo can consume the matrix we wrote.
+        return "", ["--in-process", "-i", fin, "--distmat-out", fout]
+
+    def writeSettings(self, parent: ET.Element):
+        e = ET.SubElement(parent, "alignment_tool")           # ClustalO.cpp:54-61
+        ET.SubElement(e, "name").text = self.name()
+        ET.SubElement(e, "path").text = self.executable()
+        ET.SubElement(e, "preferred").text = "yes" if self.preferred() else "no"
+        ET.SubElement(e, "gap_open").text = str(self.gap_open)
+        ET.SubElement(e, "gap_extend").text = str(self.gap_extend)
+        ET.SubElement(e, "device").text = str(self.device)
+
+    def readSettings(self, doc: ET.Element):
+        for node in doc.iter("alignment_tool"):                # ClustalO.cpp:63-86
+            for elem in list(node):
+                if elem.tag == "name" and (elem.text or "") != self.name_:
+                    break
+                if elem.tag == "path":
+                    self.executable_ = elem.text or ""
+                if elem.tag == "preferred":
+                    self.setPreferred((elem.text or "") == "yes")
+                if elem.tag == "gap_open":
+                    self.gap_open = int(elem.text)
+                if elem.tag == "gap_extend":
+                    self.gap_extend = int(elem.text)
+                if elem.tag == "device":
+                    self.device = int(elem.text)
+        self.getVersion()
+
+    def getVersion(self):
+        # ClustalO.cpp:100-111 runs `clustalo --version`; here the library reports it.
+        try:
+            self.version_ = capi.load_library().tsq_version_string().decode()
+        except capi.TsqError:
+            self.version_ = ""
+        return self.version_
+
+    # ---- the in-process path -------------------------------------------------------------
+    def run(self, fin, fout, log=None, cancel: C.c_int | None = None) -> int:
+        """FASTA file in (what Project::exportFASTA wrote), distance matrix file out.
+
+        Returns the exit status startAlignment()/alignmentFinished() would see (0 = success:
+        SeqEditMainWin.cpp:836-861)."""
+        return capi.run_fasta(fin, fout, log=log, cancel=cancel, alphabet=self.alphabet,
+                              gap_open=self.gap_open, gap_extend=self.gap_extend, device=self.device)
+
+    def distance_matrix(self, residues, labels=None, progress=None, cancel=None, flags: int = 0):
+        """Scores and distances for in-memory residues (what Sequence::filter(true) returns).
+
+        Returns (scores int32 packed, distances float64 packed)."""
+        with capi.Context(alphabet=self.alphabet, gap_open=self.gap_open, gap_extend=self.gap_extend,
+                          device=self.device, flags=flags) as ctx:
+            ctx.set_sequences(residues)
+            ctx.run(progress=progress, cancel=cancel)
+            self.last_stats = ctx.stats()
+            d = None if flags & capi.FLAG_NO_DISTANCES else ctx.distances()
+            return ctx.scores(), d
+
+    def distance_matrix_from_cells(self, cell_rows, applyExclusions=True, **kw):
+        """Rows of 16-bit residue cells with tweakseq's flag bits (Sequence.h:36-39)."""
+        return self.distance_matrix([filter_cells(r, applyExclusions) for r in cell_rows], **kw)
+
+    def distance_matrix_from_fasta(self, path, **kw):
+        labels, seqs, _ = read_fasta(path)
+        s, d = self.distance_matrix(seqs, **kw)
+        return labels, s, d
+
+
+def square(packed: np.ndarray, n: int, diag=0):
+    """Packed upper triangle -> full symmetric n x n matrix."""
+    m = np.full((n, n), diag, dtype=packed.dtype)
+    iu = np.triu_indices(n, 1)
+    m[iu] = packed
+    m[(iu[1], iu[0])] = packed
+    return m

@@ -1,0 +1,256 @@
+"""ctypes binding of libtsqb200.so (include/tsq_b200.h) -- no compute happens in Python.
+
+Fails loudly (``TsqError``) when the CUDA library is missing: there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+PROTEIN, NUCLEOTIDE = 0, 1
+FLAG_FORCE_S32, FLAG_NO_DISTANCES = 1, 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libtsqb200.so")
+
+STATUS = {0: "TSQ_OK", -1: "TSQ_ERR_INVALID", -2: "TSQ_ERR_NO_DEVICE", -3: "TSQ_ERR_CUDA",
+          -4: "TSQ_ERR_NOMEM", -5: "TSQ_ERR_CANCELLED", -6: "TSQ_ERR_STATE", -7: "TSQ_ERR_IO",
+          -8: "TSQ_ERR_MATRIX", -9: "TSQ_ERR_RANGE"}
+
+
+class TsqError(RuntimeError):
+    def __init__(self, status: int, message: str = ""):
+        self.status = status
+        super().__init__(f"{STATUS.get(status, status)}: {message}" if message else STATUS.get(status, str(status)))
+
+
+class Params(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("alphabet", C.c_int32), ("gap_open", C.c_int32),
+                ("gap_extend", C.c_int32), ("matrix", C.POINTER(C.c_int8)), ("device", C.c_int32),
+                ("part_rank", C.c_int32), ("part_world", C.c_int32), ("flags", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_sequences", C.c_uint64), ("n_pairs", C.c_uint64), ("cells", C.c_uint64),
+                ("cells_s16", C.c_uint64), ("cells_s32", C.c_uint64), ("kernel_ms", C.c_double),
+                ("upload_ms", C.c_double), ("download_ms", C.c_double), ("gcups_kernel", C.c_double),
+                ("launches", C.c_uint32), ("sm_count", C.c_uint32), ("strip_width", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+PROGRESS_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_double, C.c_char_p)
+LOG_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p)
+
+# every symbol include/tsq_b200.h declares (tests check the library exports each one)
+SYMBOLS = ["tsq_version", "tsq_version_string", "tsq_status_string", "tsq_device_count", "tsq_default_params",
+           "tsq_create", "tsq_destroy", "tsq_last_error", "tsq_set_sequences", "tsq_upload", "tsq_compute",
+           "tsq_download", "tsq_set_stream", "tsq_synchronize", "tsq_run", "tsq_scores", "tsq_distances",
+           "tsq_self_scores", "tsq_device_scores", "tsq_partition", "tsq_finalize", "tsq_device_results",
+           "tsq_get_stats", "tsq_measure_dpx_rate", "tsq_run_fasta"]
+
+_lib = None
+
+
+def library_path() -> str:
+    return _SO
+
+
+def build_library(force: bool = False) -> str:
+    """Compile csrc/ into libtsqb200.so with nvcc (sm_100a).  Used by __graft_entry__.build()."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc")] + (["-B"] if force else [])
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    return _SO
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise TsqError(-2, f"{_SO} is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                           "there is no CPU fallback")
+    L = C.CDLL(_SO)
+    vp, i32p, u64p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)
+    L.tsq_version.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.tsq_version_string.restype = C.c_char_p
+    L.tsq_status_string.restype = C.c_char_p
+    L.tsq_status_string.argtypes = [C.c_int]
+    L.tsq_default_params.argtypes = [C.POINTER(Params)]
+    L.tsq_default_params.restype = None
+    L.tsq_create.argtypes = [C.POINTER(vp), C.POINTER(Params)]
+    L.tsq_destroy.argtypes = [vp]
+    L.tsq_last_error.argtypes = [vp]
+    L.tsq_last_error.restype = C.c_char_p
+    L.tsq_set_sequences.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), C.c_uint32]
+    for f in ("tsq_upload", "tsq_compute", "tsq_download", "tsq_synchronize", "tsq_finalize"):
+        getattr(L, f).argtypes = [vp]
+    L.tsq_set_stream.argtypes = [vp, vp]
+    L.tsq_run.argtypes = [vp, PROGRESS_CB, vp, C.POINTER(C.c_int)]
+    L.tsq_scores.argtypes = [vp, C.POINTER(i32p), u64p]
+    L.tsq_distances.argtypes = [vp, C.POINTER(C.POINTER(C.c_double)), u64p]
+    L.tsq_self_scores.argtypes = [vp, C.POINTER(i32p), C.POINTER(C.c_uint32)]
+    L.tsq_device_scores.argtypes = [vp, C.POINTER(vp), u64p]
+    L.tsq_partition.argtypes = [vp, u64p, u64p]
+    L.tsq_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), u64p]
+    L.tsq_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.tsq_measure_dpx_rate.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.tsq_run_fasta.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(Params), LOG_CB, vp, C.POINTER(C.c_int)]
+    _lib = L
+    return L
+
+
+def pair_index(i: int, j: int, n: int) -> int:
+    """Packed upper-triangle index of (i, j), i < j (include/tsq_b200.h)."""
+    return i * n - i * (i + 1) // 2 + (j - i - 1)
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ holder so torch/cupy can wrap library-owned memory."""
+
+    def __init__(self, ptr: int, count: int, typestr: str, owner):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False),
+                                         "version": 3, "strides": None}
+        self._owner = owner
+
+
+class Context:
+    """One tsq_ctx.  Methods mirror the C ABI one to one."""
+
+    def __init__(self, alphabet: int = PROTEIN, gap_open: int = -1, gap_extend: int = -1,
+                 matrix: np.ndarray | None = None, device: int = 0, part_rank: int = 0,
+                 part_world: int = 1, flags: int = 0):
+        self._L = load_library()
+        p = Params()
+        self._L.tsq_default_params(C.byref(p))
+        p.alphabet, p.gap_open, p.gap_extend = alphabet, gap_open, gap_extend
+        p.device, p.part_rank, p.part_world, p.flags = device, part_rank, part_world, flags
+        self._matrix = None
+        if matrix is not None:
+            self._matrix = np.ascontiguousarray(matrix, dtype=np.int8)
+            p.matrix = self._matrix.ctypes.data_as(C.POINTER(C.c_int8))
+        self._h = C.c_void_p()
+        rc = self._L.tsq_create(C.byref(self._h), C.byref(p))
+        if rc != 0:
+            self._h = None
+            raise TsqError(rc, self._L.tsq_status_string(rc).decode())
+        self.n = 0
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.tsq_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise TsqError(rc, self._L.tsq_last_error(self._h).decode())
+
+    def set_sequences(self, seqs):
+        raw = [s.encode("latin-1", "replace") if isinstance(s, str) else bytes(s) for s in seqs]
+        n = len(raw)
+        arr = (C.c_char_p * max(n, 1))(*raw) if n else (C.c_char_p * 1)()
+        lens = (C.c_uint32 * max(n, 1))(*[len(r) for r in raw]) if n else (C.c_uint32 * 1)()
+        self._keep = (raw, arr, lens)
+        self._ck(self._L.tsq_set_sequences(self._h, arr, lens, n))
+        self.n = n
+
+    def upload(self):
+        self._ck(self._L.tsq_upload(self._h))
+
+    def compute(self):
+        self._ck(self._L.tsq_compute(self._h))
+
+    def finalize(self):
+        self._ck(self._L.tsq_finalize(self._h))
+
+    def download(self):
+        self._ck(self._L.tsq_download(self._h))
+
+    def synchronize(self):
+        self._ck(self._L.tsq_synchronize(self._h))
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._ck(self._L.tsq_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def run(self, progress=None, cancel: C.c_int | None = None):
+        cb = PROGRESS_CB(lambda u, f, m: progress(f, m.decode() if m else "")) if progress else PROGRESS_CB(0)
+        self._ck(self._L.tsq_run(self._h, cb, None, C.byref(cancel) if cancel is not None else None))
+
+    @property
+    def npairs(self) -> int:
+        return self.n * (self.n - 1) // 2 if self.n >= 2 else 0
+
+    def scores(self) -> np.ndarray:
+        p, cnt = C.POINTER(C.c_int32)(), C.c_uint64()
+        self._ck(self._L.tsq_scores(self._h, C.byref(p), C.byref(cnt)))
+        if cnt.value == 0:
+            return np.zeros(0, np.int32)
+        return np.ctypeslib.as_array(p, shape=(cnt.value,)).copy()
+
+    def distances(self) -> np.ndarray:
+        p, cnt = C.POINTER(C.c_double)(), C.c_uint64()
+        self._ck(self._L.tsq_distances(self._h, C.byref(p), C.byref(cnt)))
+        if cnt.value == 0:
+            return np.zeros(0, np.float64)
+        return np.ctypeslib.as_array(p, shape=(cnt.value,)).copy()
+
+    def self_scores(self) -> np.ndarray:
+        p, n = C.POINTER(C.c_int32)(), C.c_uint32()
+        self._ck(self._L.tsq_self_scores(self._h, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, np.int32)
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+
+    def partition(self) -> tuple[int, int]:
+        b, e = C.c_uint64(), C.c_uint64()
+        self._ck(self._L.tsq_partition(self._h, C.byref(b), C.byref(e)))
+        return b.value, e.value
+
+    def device_scores(self) -> _DevArray:
+        """Sorted-order packed int32 score buffer on the device (for the NCCL gather)."""
+        d, cnt = C.c_void_p(), C.c_uint64()
+        self._ck(self._L.tsq_device_scores(self._h, C.byref(d), C.byref(cnt)))
+        return _DevArray(d.value or 0, cnt.value, "<i4", self)
+
+    def device_results(self):
+        ds, dd, cnt = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._ck(self._L.tsq_device_results(self._h, C.byref(ds), C.byref(dd), C.byref(cnt)))
+        s = _DevArray(ds.value or 0, cnt.value, "<i4", self)
+        d = _DevArray(dd.value, cnt.value, "<f8", self) if dd.value else None
+        return s, d
+
+    def stats(self) -> dict:
+        st = Stats()
+        self._ck(self._L.tsq_get_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def measure_dpx_rate(self) -> tuple[float, float]:
+        ops, mhz = C.c_double(), C.c_double()
+        self._ck(self._L.tsq_measure_dpx_rate(self._h, C.byref(ops), C.byref(mhz)))
+        return ops.value, mhz.value
+
+
+def run_fasta(fasta_in: str, distmat_out: str, log=None, cancel: C.c_int | None = None, **kw) -> int:
+    """tsq_run_fasta(): FASTA file in, PHYLIP-style distance matrix out.  Returns the status."""
+    L = load_library()
+    p = Params()
+    L.tsq_default_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    cb = LOG_CB(lambda u, m: log(m.decode())) if log else LOG_CB(0)
+    return L.tsq_run_fasta(fasta_in.encode(), distmat_out.encode(), C.byref(p), cb, None,
+                           C.byref(cancel) if cancel is not None else None)

@@ -1,0 +1,215 @@
+// gotoh16.cuh -- regime 1: inter-task packed 16-bit Gotoh kernel for sm_100a.
+//
+// One warp = one task = (a PAIR of query sequences A1,A2) x (32 subject sequences, one per
+// lane).  The two queries ride in the two 16-bit halves of every 32-bit DP word, so each
+// DPX instruction (VIMNMX3.U16x2 / VIADDMNMX.U16x2) advances two alignments.
+//
+// The DP is strip-mined: a lane keeps K columns of H and F in registers and walks down all
+// rows of its subject; the right-hand boundary column (H, E) of the strip goes to a per-lane
+// L2-resident scratch column and is read back, one row ahead, by the next strip.  Lanes never
+// exchange data, so the row loop has no barrier and no shuffle.
+//
+// Scores come from a per-warp, per-strip "query-pair profile" in shared memory:
+//   prof[b][c] = S'(A1[j0+c], b) | S'(A2[j0+c], b) << 16          (b = subject letter)
+// with row stride == 1 (mod 32): all lanes read the same column c of different rows b, so
+// the bank is (b + c) mod 32 -- distinct letters hit distinct banks, equal letters broadcast.
+// One conflict-free LDS.32 per packed cell, no ALU work for the lookup.
+//
+// Arithmetic (exactness argument in DESIGN.md section 4):
+//   * values are stored biased and skewed:  v~(i,j) = v(i,j) + delta*(i+j) + BIAS, as
+//     unsigned 16-bit.  delta = ceil(-min(S)/2) makes every substitution score S' = S+2*delta
+//     non-negative, so "H_diag + S" and "H - (go+ge)" are plain 32-bit adds of two packed
+//     halves with no carry between halves -> they run on the FMA pipe (IMAD.IADD), leaving
+//     3 DPX instructions per packed cell on the ALU pipe:
+//         t  = hd + S'                      (FMA pipe)
+//         h  = vimax3(t, E, F)              (ALU, DPX)
+//         hg = h - goe'                     (FMA pipe)
+//         E  = viaddmax(E, -ge', hg)        (ALU, DPX)
+//         F  = viaddmax(F, -ge', hg)        (ALU, DPX)
+//     with ge' = ge - delta, goe' = go + ge - delta.
+//   * -inf is never needed: E(i,0) and F(0,j) only ever feed max(x - ge, H - go - ge), which
+//     equals H - go - ge for any x <= H - go, so the boundary E/F are seeded with H - goe'.
+//
+// Spec: SURVEY.md section 8c (frozen oracle spec).  Matrix/alphabet:
+// tweakseq/Core/Annotations/Consensus.cpp:34-69.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace tsq {
+
+struct G16Params {
+  const uint32_t* dbw;         // subject residues, 32-way interleaved, 4 letters per word
+  const uint32_t* goff;        // word offset of each group of 32 sorted sequences
+  const uint8_t* lin;          // residues, linear, sorted order
+  const uint32_t* loff;        // start of each sorted sequence in lin
+  const uint32_t* lens;        // sorted lengths
+  const unsigned long long* task_prefix;  // [nq+1] cumulative chunk counts, per query pair
+  unsigned long long* counter; // dynamic task cursor
+  uint2* bnd;                  // strip boundary scratch: [warp slot][row][lane] (H, E)
+  const uint32_t* sbias;       // (nsym+1) x nsym biased scores S' (row nsym = padding = 0)
+  int32_t* out;                // scores, packed upper triangle in sorted order
+  unsigned long long ntasks;
+  uint32_t bnd_rows;           // rows per warp slot in bnd
+  uint32_t n_total;            // N of the triangle
+  uint32_t lo, hi;             // the packed-16 eligible sorted range [lo, hi)
+  uint32_t q_begin, q_end;     // query pairs of this launch (rows lo+2q, lo+2q+1)
+  uint32_t nsym;
+  uint32_t bias;               // BIAS
+  int32_t delta;               // skew per anti-diagonal
+  int32_t go;                  // gap open
+  int32_t gep;                 // ge' = ge - delta
+  uint32_t negge2;             // (-ge' mod 2^16) in both halves
+  uint32_t goe2;               // goe' * 0x10001 (mod 2^32)
+};
+
+__device__ __forceinline__ unsigned long long tri_index(unsigned long long i, unsigned long long j,
+                                                        unsigned long long n) {
+  return i * n - i * (i + 1) / 2 + (j - i - 1);
+}
+
+template <int K>
+struct G16Cfg {
+  static constexpr int STRIDE = ((K + 31) & ~31) + 1;  // == 1 (mod 32)
+};
+
+template <int K, int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) gotoh16_kernel(const __grid_constant__ G16Params p) {
+  constexpr int STRIDE = G16Cfg<K>::STRIDE;
+  extern __shared__ uint32_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const uint32_t nsym = p.nsym;
+  const uint32_t sbsz = (nsym + 1) * nsym;
+  uint32_t* sb = smem;
+  uint32_t* prof = smem + ((sbsz + 31) & ~31u) + wib * (nsym * STRIDE);
+  for (uint32_t i = threadIdx.x; i < sbsz; i += TPB) sb[i] = p.sbias[i];
+  __syncthreads();
+
+  const uint32_t gw = blockIdx.x * (TPB / 32) + wib;
+  uint2* const bnd = p.bnd + (size_t)gw * p.bnd_rows * 32 + lane;
+  const uint32_t negge2 = p.negge2;
+  const uint32_t goe2 = p.goe2;
+  const int32_t gep = p.gep;
+
+  for (;;) {
+    unsigned long long task = 0;
+    if (lane == 0) task = atomicAdd(p.counter, 1ULL);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= p.ntasks) break;
+
+    // task -> (query pair q, subject chunk); big tasks (long queries, long subjects) first
+    uint32_t r;
+    {
+      uint32_t a = 0, b = p.q_end - p.q_begin;
+      while (b - a > 1) {
+        const uint32_t m = (a + b) >> 1;
+        if (p.task_prefix[m] <= task) a = m; else b = m;
+      }
+      r = a;
+    }
+    const uint32_t q = p.q_end - 1 - r;
+    const unsigned long long pr = p.task_prefix[r];
+    const uint32_t nch = (uint32_t)(p.task_prefix[r + 1] - pr);
+    const uint32_t chunk = nch - 1 - (uint32_t)(task - pr);
+    const uint32_t A1 = p.lo + 2 * q, A2 = A1 + 1;
+    const uint32_t L1 = p.lens[A1], L2 = p.lens[A2];
+    const uint8_t* q1 = p.lin + p.loff[A1];
+    const uint8_t* q2 = p.lin + p.loff[A2];
+    const uint32_t j = A1 + 1 + chunk * 32 + lane;
+    const bool valid = j < p.hi;
+    const uint32_t Ls = valid ? p.lens[j] : 0u;
+    const uint32_t* dbp = p.dbw + (valid ? (p.goff[j >> 5] + (j & 31)) : 0u);
+    const uint32_t nstrips = (L2 + K - 1) / K;  // L1 <= L2 (sorted ascending)
+    uint32_t res1 = 0, res2 = 0;
+
+    for (uint32_t s = 0; s < nstrips; ++s) {
+      const uint32_t j0 = s * K;
+      // ---- profile of columns [j0, j0+K) for this query pair --------------------------
+      __syncwarp();
+      for (int c = lane; c < K; c += 32) {
+        const uint32_t col = j0 + c;
+        const uint32_t a1 = col < L1 ? q1[col] : nsym;
+        const uint32_t a2 = col < L2 ? q2[col] : nsym;
+        const uint32_t* r1 = sb + a1 * nsym;
+        const uint32_t* r2 = sb + a2 * nsym;
+        for (uint32_t b = 0; b < nsym; ++b) prof[b * STRIDE + c] = r1[b] | (r2[b] << 16);
+      }
+      __syncwarp();
+
+      // ---- row 0 of the strip ---------------------------------------------------------
+      uint32_t H[K], F[K];
+      const int32_t h0 = (int32_t)p.bias - p.go - (int32_t)(j0 + 1) * gep;
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        const uint32_t v = (uint32_t)(h0 - c * gep) * 0x10001u;  // H~(0, j0+c+1), both halves
+        H[c] = v;
+        F[c] = v - goe2;                                         // F~(1, j0+c+1)
+      }
+      uint32_t hdiag = (j0 == 0) ? p.bias * 0x10001u
+                                 : (uint32_t)((int32_t)p.bias - p.go - (int32_t)j0 * gep) * 0x10001u;
+      const int32_t hl0 = (int32_t)p.bias - p.go;  // H~(i,0) = hl0 - i*ge'
+      const bool first = (s == 0);
+      const bool last = (s + 1 == nstrips);
+
+      uint32_t w = 0;
+      uint32_t wn = valid ? __ldg(dbp) : 0u;
+      uint2 bn = make_uint2(0u, 0u);
+      if (!first && Ls > 0) bn = bnd[32];
+
+      for (uint32_t i = 1; i <= Ls; ++i) {
+        if (((i - 1) & 3u) == 0u) {
+          w = wn;
+          wn = __ldg(dbp + (((i - 1) >> 2) + 1) * 32);
+        }
+        const uint32_t b = w & 0xffu;
+        w >>= 8;
+        const uint32_t* prow = prof + b * STRIDE;
+        uint32_t Hl, E;
+        if (first) {
+          Hl = (uint32_t)(hl0 - (int32_t)i * gep) * 0x10001u;
+          E = Hl - goe2;
+        } else {
+          Hl = bn.x;
+          E = bn.y;
+          bn = bnd[(size_t)(i + 1) * 32];
+        }
+        uint32_t hd = hdiag;
+        hdiag = Hl;
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          const uint32_t t = hd + prow[c];
+          hd = H[c];
+          const uint32_t h = __vimax3_u16x2(t, E, F[c]);
+          H[c] = h;
+          const uint32_t hg = h - goe2;
+          E = __viaddmax_u16x2(E, negge2, hg);
+          F[c] = __viaddmax_u16x2(F[c], negge2, hg);
+        }
+        if (!last) bnd[(size_t)i * 32] = make_uint2(H[K - 1], E);
+      }
+
+      // ---- pick H(Ls, L1) / H(Ls, L2) if the query ends inside this strip --------------
+      if (L1 > j0 && L1 <= j0 + K) {
+        const int c1 = (int)(L1 - 1 - j0);
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+          if (c == c1) res1 = H[c] & 0xffffu;
+      }
+      if (L2 > j0 && L2 <= j0 + K) {
+        const int c2 = (int)(L2 - 1 - j0);
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+          if (c == c2) res2 = H[c] >> 16;
+      }
+    }
+
+    if (valid) {
+      const int32_t base = -(int32_t)p.bias - p.delta * (int32_t)Ls;
+      p.out[tri_index(A1, j, p.n_total)] = (int32_t)res1 + base - p.delta * (int32_t)L1;
+      if (j > A2) p.out[tri_index(A2, j, p.n_total)] = (int32_t)res2 + base - p.delta * (int32_t)L2;
+    }
+  }
+}
+
+}  // namespace tsq

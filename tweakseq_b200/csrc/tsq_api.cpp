@@ -1,0 +1,900 @@
+// tsq_api.cpp -- the C ABI of libtsqb200.so (include/tsq_b200.h): context, host-side
+// encode / length sort / packing, work partitioning, kernel orchestration, result access.
+//
+// Replaces the process boundary tweakseq/UI/SeqEditMainWin.cpp:1654-1660 for the pairwise
+// distance stage; matrix and alphabet from tweakseq/Core/Annotations/Consensus.cpp:34-69.
+// No CPU compute path exists here: every score comes out of the sm_100a kernels.
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/tsq_b200.h"
+#include "tsq_device.h"
+
+namespace {
+
+// Rows/columns A R N D C Q E G H I L K M F P S T W Y V B Z X
+// (values and order: tweakseq/Core/Annotations/Consensus.cpp:34-59).
+const int8_t kBlosum62[23 * 23] = {
+     4,-1,-2,-2, 0,-1,-1, 0,-2,-1,-1,-1,-1,-2,-1, 1, 0,-3,-2, 0,-2,-1, 0,
+    -1, 5, 0,-2,-3, 1, 0,-2, 0,-3,-2, 2,-1,-3,-2,-1,-1,-3,-2,-3,-1, 0,-1,
+    -2, 0, 6, 1,-3, 0, 0, 0, 1,-3,-3, 0,-2,-3,-2, 1, 0,-4,-2,-3, 3, 0,-1,
+    -2,-2, 1, 6,-3, 0, 2,-1,-1,-3,-4,-1,-3,-3,-1, 0,-1,-4,-3,-3, 4, 1,-1,
+     0,-3,-3,-3, 9,-3,-4,-3,-3,-1,-1,-3,-1,-2,-3,-1,-1,-2,-2,-1,-3,-3,-2,
+    -1, 1, 0, 0,-3, 5, 2,-2, 0,-3,-2, 1, 0,-3,-1, 0,-1,-2,-1,-2, 0, 3,-1,
+    -1, 0, 0, 2,-4, 2, 5,-2, 0,-3,-3, 1,-2,-3,-1, 0,-1,-3,-2,-2, 1, 4,-1,
+     0,-2, 0,-1,-3,-2,-2, 6,-2,-4,-4,-2,-3,-3,-2, 0,-2,-2,-3,-3,-1,-2,-1,
+    -2, 0, 1,-1,-3, 0, 0,-2, 8,-3,-3,-1,-2,-1,-2,-1,-2,-2, 2,-3, 0, 0,-1,
+    -1,-3,-3,-3,-1,-3,-3,-4,-3, 4, 2,-3, 1, 0,-3,-2,-1,-3,-1, 3,-3,-3,-1,
+    -1,-2,-3,-4,-1,-2,-3,-4,-3, 2, 4,-2, 2, 0,-3,-2,-1,-2,-1, 1,-4,-3,-1,
+    -1, 2, 0,-1,-3, 1, 1,-2,-1,-3,-2, 5,-1,-3,-1, 0,-1,-3,-2,-2, 0, 1,-1,
+    -1,-1,-2,-3,-1, 0,-2,-3,-2, 1, 2,-1, 5, 0,-2,-1,-1,-1,-1, 1,-3,-1,-1,
+    -2,-3,-3,-3,-2,-3,-3,-3,-1, 0, 0,-3, 0, 6,-4,-2,-2, 1, 3,-1,-3,-3,-1,
+    -1,-2,-2,-1,-3,-1,-1,-2,-2,-3,-3,-1,-2,-4, 7,-1,-1,-4,-3,-2,-2,-1,-2,
+     1,-1, 1, 0,-1, 0, 0, 0,-1,-2,-2, 0,-1,-2,-1, 4, 1,-3,-2,-2, 0, 0, 0,
+     0,-1, 0,-1,-1,-1,-1,-2,-2,-1,-1,-1,-1,-2,-1, 1, 5,-2,-2, 0,-1,-1, 0,
+    -3,-3,-4,-4,-2,-2,-3,-2,-2,-3,-2,-3,-1, 1,-4,-3,-2,11, 2,-3,-4,-3,-2,
+    -2,-2,-2,-3,-2,-1,-2,-3, 2,-1,-1,-2,-1, 3,-3,-2,-2, 2, 7,-1,-3,-2,-1,
+     0,-3,-3,-3,-1,-2,-2,-3,-3, 3, 1,-2, 1,-1,-2,-2, 0,-3,-1, 4,-3,-2,-1,
+    -2,-1, 3, 4,-3, 0, 1,-1, 0,-3,-4, 0,-3,-3,-2, 0,-1,-4,-3,-3, 4, 1,-1,
+    -1, 0, 0, 1,-3, 3, 4,-2, 0,-3,-3, 1,-1,-3,-1, 0,-1,-3,-2,-2, 1, 4,-1,
+     0,-1,-1,-1,-2,-1,-1,-1,-1,-1,-1,-1,-1,-1,-2, 0, 0,-2,-1,-1,-1,-1,-1,
+};
+// 'A'..'Z' -> matrix row (Consensus.cpp:61-69; J, O, U, X -> X)
+const uint8_t kProteinIndex[26] = {0,  20, 4,  3,  6,  13, 7,  8,  9,  22, 11, 10, 12,
+                                   2,  22, 14, 5,  1,  15, 16, 22, 19, 17, 22, 18, 21};
+// A C G T N (the reference has no nucleotide matrix)
+const int8_t kDna[5 * 5] = {5, -4, -4, -4, -2, -4, 5, -4, -4, -2, -4, -4, 5,
+                            -4, -2, -4, -4, -4, 5, -2, -2, -2, -2, -2, -1};
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+template <typename T>
+struct PinnedBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct tsq_ctx {
+  tsq_params prm{};
+  int nsym = 23;
+  std::vector<int8_t> matrix;  // nsym x nsym
+  int go = 11, ge = 1;
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+
+  // packed-16 arithmetic constants
+  int smin = 0, smax = 0, delta = 0;
+  uint32_t max_len16 = 0;  // longest sequence the packed kernel may see
+
+  // host copies (sorted order unless noted)
+  uint32_t n = 0;
+  std::vector<std::vector<uint8_t>> enc;  // submitted order
+  std::vector<uint32_t> perm;             // sorted -> submitted
+  std::vector<uint32_t> lens;             // sorted
+  std::vector<uint32_t> loff;             // sorted
+  std::vector<uint8_t> lin;               // sorted, concatenated
+  std::vector<uint32_t> dbw, goff;        // interleaved words / group offsets
+  std::vector<int32_t> self_sorted, self_orig;
+  bool identity = true;
+  uint32_t lo = 0, hi = 0;  // sorted range eligible for the packed 16-bit kernel
+  uint32_t row_a = 0, row_b = 0;  // this partition's sorted rows
+  uint64_t part_begin = 0, part_end = 0;
+  std::vector<unsigned long long> task_prefix;
+  uint32_t q_begin = 0, q_end = 0;
+  int K = 0;
+  uint64_t cells16 = 0, cells32 = 0, pairs_part = 0;
+
+  // device
+  DevBuf<uint32_t> d_dbw, d_goff, d_loff, d_lens, d_perm, d_sbias;
+  DevBuf<uint8_t> d_lin;
+  DevBuf<int32_t> d_self, d_sorted, d_scores;
+  DevBuf<double> d_dist;
+  DevBuf<unsigned long long> d_prefix, d_counter;
+  DevBuf<uint2> d_bnd;
+  // host results
+  PinnedBuf<int32_t> h_scores;
+  PinnedBuf<double> h_dist;
+
+  bool have_seqs = false, uploaded = false, computed = false, finalized = false, downloaded = false;
+  tsq_stats st{};
+};
+
+namespace {
+
+int fail(tsq_ctx* c, int code, const char* fmt, ...) {
+  if (c) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    c->err = buf;
+  }
+  return code;
+}
+
+#define TSQ_CUDA(c, call)                                                                  \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      return fail((c), e_ == cudaErrorMemoryAllocation ? TSQ_ERR_NOMEM : TSQ_ERR_CUDA,     \
+                  "%s failed: %s", #call, cudaGetErrorString(e_));                         \
+    }                                                                                      \
+  } while (0)
+
+inline uint64_t tri(uint64_t i, uint64_t j, uint64_t n) { return i * n - i * (i + 1) / 2 + (j - i - 1); }
+
+bool is_gap_or_space(unsigned char c) {
+  return c == '-' || c == '.' || c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f';
+}
+
+void encode_into(int alphabet, const char* s, size_t len, std::vector<uint8_t>& out) {
+  out.clear();
+  out.reserve(len);
+  for (size_t i = 0; i < len; i++) {
+    unsigned char c = (unsigned char)s[i];
+    if (is_gap_or_space(c)) continue;
+    if (c >= 'a' && c <= 'z') c = (unsigned char)(c - 'a' + 'A');
+    if (alphabet == TSQ_NUCLEOTIDE) {
+      uint8_t v = 4;
+      if (c == 'A') v = 0;
+      else if (c == 'C') v = 1;
+      else if (c == 'G') v = 2;
+      else if (c == 'T' || c == 'U') v = 3;
+      out.push_back(v);
+    } else {
+      out.push_back((c >= 'A' && c <= 'Z') ? kProteinIndex[c - 'A'] : (uint8_t)22);
+    }
+  }
+}
+
+// Packed-16 range analysis.  Values live as v + delta*(i+j) + BIAS in
+// an unsigned 16-bit half; this returns BIAS and the largest padded length that stays inside
+// [0, 65535] for every intermediate of the recurrence.
+uint32_t bias_for(const tsq_ctx* c, uint32_t lpad) {
+  const int gep = c->ge - c->delta;
+  const long long b = 3LL * c->go + 2LL * c->ge + (long long)std::max(0, gep) * 2LL * (lpad + 1) + c->delta + 16;
+  return (uint32_t)b;
+}
+bool fits16(const tsq_ctx* c, uint32_t lpad) {
+  const long long hi = (long long)bias_for(c, lpad) + (long long)std::max(c->smax, 0) * lpad +
+                       2LL * c->delta * (lpad + 1) + 16;
+  return hi <= 65535;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tsq_version(int* major, int* minor) {
+  if (major) *major = TSQ_VERSION_MAJOR;
+  if (minor) *minor = TSQ_VERSION_MINOR;
+  return TSQ_OK;
+}
+
+const char* tsq_version_string(void) { return "tsq-b200 0.1 (sm_100a Gotoh all-vs-all)"; }
+
+const char* tsq_status_string(int s) {
+  switch (s) {
+    case TSQ_OK: return "ok";
+    case TSQ_ERR_INVALID: return "invalid argument";
+    case TSQ_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+    case TSQ_ERR_CUDA: return "CUDA error";
+    case TSQ_ERR_NOMEM: return "out of memory";
+    case TSQ_ERR_CANCELLED: return "cancelled";
+    case TSQ_ERR_STATE: return "call out of order";
+    case TSQ_ERR_IO: return "I/O error";
+    case TSQ_ERR_MATRIX: return "bad substitution matrix";
+    case TSQ_ERR_RANGE: return "score range exceeded";
+    default: return "unknown status";
+  }
+}
+
+int tsq_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int d = 0; d < n; d++) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ok++;
+  }
+  return ok;
+}
+
+void tsq_default_params(tsq_params* p) {
+  if (!p) return;
+  memset(p, 0, sizeof *p);
+  p->struct_size = (uint32_t)sizeof(tsq_params);
+  p->alphabet = TSQ_PROTEIN;
+  p->gap_open = -1;
+  p->gap_extend = -1;
+  p->matrix = nullptr;
+  p->device = 0;
+  p->part_rank = 0;
+  p->part_world = 1;
+  p->flags = 0;
+}
+
+int tsq_create(tsq_ctx** out, const tsq_params* params) {
+  if (!out) return TSQ_ERR_INVALID;
+  *out = nullptr;
+  tsq_params p;
+  tsq_default_params(&p);
+  if (params) {
+    if (params->struct_size < 8 || params->struct_size > sizeof(tsq_params)) return TSQ_ERR_INVALID;
+    memcpy(&p, params, params->struct_size);
+    p.struct_size = (uint32_t)sizeof(tsq_params);
+  }
+  if (p.alphabet != TSQ_PROTEIN && p.alphabet != TSQ_NUCLEOTIDE) return TSQ_ERR_INVALID;
+  if (p.part_world < 1) p.part_world = 1;
+  if (p.part_rank < 0 || p.part_rank >= p.part_world) return TSQ_ERR_INVALID;
+  const int nsym = p.alphabet == TSQ_NUCLEOTIDE ? 5 : 23;
+  const int8_t* m = p.matrix ? p.matrix : (p.alphabet == TSQ_NUCLEOTIDE ? kDna : kBlosum62);
+  for (int a = 0; a < nsym; a++)
+    for (int b = 0; b < nsym; b++)
+      if (m[a * nsym + b] != m[b * nsym + a]) return TSQ_ERR_MATRIX;
+  const int go = p.gap_open < 0 ? (p.alphabet == TSQ_NUCLEOTIDE ? 10 : 11) : p.gap_open;
+  const int ge = p.gap_extend < 0 ? 1 : p.gap_extend;
+  if (go > 4096 || ge > 1024) return TSQ_ERR_INVALID;
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return TSQ_ERR_NO_DEVICE;
+  }
+  if (p.device < 0 || p.device >= ndev) return TSQ_ERR_NO_DEVICE;
+  int major = 0, sms = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, p.device) != cudaSuccess || major != 10)
+    return TSQ_ERR_NO_DEVICE;  // sm_100a SASS only: nothing else can run these kernels
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p.device);
+
+  tsq_ctx* c = new (std::nothrow) tsq_ctx();
+  if (!c) return TSQ_ERR_NOMEM;
+  c->prm = p;
+  c->nsym = nsym;
+  c->matrix.assign(m, m + nsym * nsym);
+  c->prm.matrix = nullptr;
+  c->go = go;
+  c->ge = ge;
+  c->device = p.device;
+  c->sm_count = sms;
+  c->smin = *std::min_element(c->matrix.begin(), c->matrix.end());
+  c->smax = *std::max_element(c->matrix.begin(), c->matrix.end());
+  c->delta = c->smin < 0 ? (-c->smin + 1) / 2 : 0;
+  // largest sequence length the packed kernel can take (binary search on the range bound)
+  {
+    uint32_t a = 0, b = 60000;
+    while (b - a > 1) {
+      const uint32_t mid = (a + b) / 2;
+      if (fits16(c, mid + 64)) a = mid; else b = mid;
+    }
+    c->max_len16 = (p.flags & TSQ_FLAG_FORCE_S32) ? 0 : a;
+  }
+  if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+    cudaGetLastError();
+    delete c;
+    return TSQ_ERR_CUDA;
+  }
+  c->stream = c->own_stream;
+  *out = c;
+  return TSQ_OK;
+}
+
+int tsq_destroy(tsq_ctx* c) {
+  if (!c) return TSQ_OK;
+  cudaSetDevice(c->device);
+  if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+  c->d_dbw.release(); c->d_goff.release(); c->d_loff.release(); c->d_lens.release();
+  c->d_perm.release(); c->d_sbias.release(); c->d_lin.release(); c->d_self.release();
+  c->d_sorted.release(); c->d_scores.release(); c->d_dist.release(); c->d_prefix.release();
+  c->d_counter.release(); c->d_bnd.release(); c->h_scores.release(); c->h_dist.release();
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+  return TSQ_OK;
+}
+
+const char* tsq_last_error(const tsq_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int tsq_set_stream(tsq_ctx* c, void* s) {
+  if (!c) return TSQ_ERR_INVALID;
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return TSQ_OK;
+}
+
+int tsq_set_sequences(tsq_ctx* c, const char* const* residues, const uint32_t* lengths, uint32_t n) {
+  if (!c) return TSQ_ERR_INVALID;
+  if (n > 0 && (!residues || !lengths)) return fail(c, TSQ_ERR_INVALID, "null sequence arrays");
+  c->enc.assign(n, {});
+  for (uint32_t i = 0; i < n; i++) {
+    if (lengths[i] > 0 && !residues[i]) return fail(c, TSQ_ERR_INVALID, "sequence %u is null", i);
+    encode_into(c->prm.alphabet, residues[i], lengths[i], c->enc[i]);
+  }
+  c->n = n;
+  c->have_seqs = true;
+  c->uploaded = c->computed = c->finalized = c->downloaded = false;
+  c->err.clear();
+  return TSQ_OK;
+}
+
+int tsq_upload(tsq_ctx* c) {
+  if (!c) return TSQ_ERR_INVALID;
+  if (!c->have_seqs) return fail(c, TSQ_ERR_STATE, "tsq_upload before tsq_set_sequences");
+  const double t0 = now_ms();
+  TSQ_CUDA(c, cudaSetDevice(c->device));
+  const uint32_t n = c->n;
+  const uint64_t npairs = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
+
+  // ---- stable length sort ---------------------------------------------------------------
+  c->perm.resize(n);
+  std::iota(c->perm.begin(), c->perm.end(), 0u);
+  std::stable_sort(c->perm.begin(), c->perm.end(),
+                   [&](uint32_t a, uint32_t b) { return c->enc[a].size() < c->enc[b].size(); });
+  c->lens.resize(n);
+  c->loff.resize(n + 1);
+  uint64_t total = 0;
+  c->identity = true;
+  for (uint32_t i = 0; i < n; i++) {
+    const size_t l = c->enc[c->perm[i]].size();
+    if (l > 0x7fffffffu) return fail(c, TSQ_ERR_RANGE, "sequence too long");
+    c->lens[i] = (uint32_t)l;
+    c->loff[i] = (uint32_t)total;
+    total += l;
+    if (c->perm[i] != i) c->identity = false;
+  }
+  if (total > 0xfffffff0ull) return fail(c, TSQ_ERR_RANGE, "more than 4 Gi residues");
+  c->loff[n] = (uint32_t)total;
+  c->lin.resize(total + 16);
+  c->self_sorted.resize(n);
+  c->self_orig.resize(n);
+  for (uint32_t i = 0; i < n; i++) {
+    const std::vector<uint8_t>& e = c->enc[c->perm[i]];
+    if (!e.empty()) memcpy(&c->lin[c->loff[i]], e.data(), e.size());
+    int64_t s = 0;
+    for (uint8_t a : e) s += c->matrix[a * c->nsym + a];
+    c->self_sorted[i] = (int32_t)s;
+    c->self_orig[c->perm[i]] = (int32_t)s;
+  }
+  // ---- regimes --------------------------------------------------------------------------
+  uint32_t lo = 0;
+  while (lo < n && c->lens[lo] == 0) lo++;
+  uint32_t hi = lo;
+  while (hi < n && c->lens[hi] <= c->max_len16) hi++;
+  if (c->identity && lo > 0) c->identity = false;  // empties are filled in by finalize
+  c->lo = lo;
+  c->hi = hi;
+  if (hi < n) return fail(c, TSQ_ERR_RANGE, "sequence of length %u needs the 32-bit wavefront kernel (not built yet)", c->lens[n - 1]);
+
+  // ---- 32-way interleaved subject database (4 residues per word) ---------------------------
+  const uint32_t ngroups = (n + 31) / 32;
+  c->goff.assign(ngroups + 1, 0);
+  uint64_t words = 0;
+  for (uint32_t g = 0; g < ngroups; g++) {
+    c->goff[g] = (uint32_t)words;
+    const uint32_t last = std::min(n, (g + 1) * 32) - 1;
+    const uint32_t rows4 = (c->lens[last] + 3) / 4 + 1;  // +1: the kernel prefetches one word ahead
+    words += (uint64_t)rows4 * 32;
+    if (words > 0xfffffff0ull) return fail(c, TSQ_ERR_RANGE, "interleaved database too large");
+  }
+  c->goff[ngroups] = (uint32_t)words;
+  c->dbw.assign(words, 0);
+  for (uint32_t i = 0; i < n; i++) {
+    const uint8_t* s = &c->lin[c->loff[i]];
+    uint32_t* base = &c->dbw[c->goff[i >> 5] + (i & 31)];
+    const uint32_t l = c->lens[i];
+    for (uint32_t r = 0; r < l; r += 4) {
+      uint32_t w = 0;
+      for (uint32_t k = 0; k < 4 && r + k < l; k++) w |= (uint32_t)s[r + k] << (8 * k);
+      base[(size_t)(r >> 2) * 32] = w;
+    }
+  }
+
+  // ---- partition of the sorted rows across ranks (contiguous, balanced by DP cells) ---------
+  // suffix sums of lengths give the cells of each row: len_i * sum_{j>i} len_j
+  std::vector<double> rowcost(n, 0.0);
+  {
+    uint64_t suffix = 0;
+    for (uint32_t i = n; i-- > 0;) {
+      rowcost[i] = (double)c->lens[i] * (double)suffix;
+      suffix += c->lens[i];
+    }
+  }
+  const int world = c->prm.part_world, rank = c->prm.part_rank;
+  auto boundary = [&](int r) -> uint32_t {  // first row of rank r
+    if (r <= 0) return 0;
+    if (r >= world) return n;
+    double tot = 0;
+    for (uint32_t i = 0; i < n; i++) tot += rowcost[i];
+    const double target = tot * r / world;
+    double acc = 0;
+    uint32_t i = 0;
+    while (i < n && acc + rowcost[i] <= target) acc += rowcost[i++];
+    // rows of the packed kernel come in pairs (lo+2q, lo+2q+1): cut on a pair boundary
+    if (i > lo && i < hi && ((i - lo) & 1u)) i++;
+    return std::min(i, n);
+  };
+  c->row_a = boundary(rank);
+  c->row_b = boundary(rank + 1);
+  c->part_begin = (n >= 2 && c->row_a + 1 < n) ? tri(c->row_a, c->row_a + 1, n) : npairs;
+  c->part_end = (n >= 2 && c->row_b + 1 < n) ? tri(c->row_b, c->row_b + 1, n) : npairs;
+  if (c->part_begin > c->part_end) c->part_begin = c->part_end;
+
+  // ---- tasks of the packed kernel: query pairs q in [q_begin, q_end) ------------------------
+  const uint32_t nq_all = (hi - lo) / 2;
+  auto row_to_q = [&](uint32_t row) -> uint32_t {
+    if (row <= lo) return 0;
+    return std::min(nq_all, (row - lo + 1) / 2);
+  };
+  c->q_begin = row_to_q(c->row_a);
+  c->q_end = row_to_q(c->row_b);
+  if (c->q_end < c->q_begin) c->q_end = c->q_begin;
+  const uint32_t nq = c->q_end - c->q_begin;
+  c->task_prefix.assign((size_t)nq + 1, 0);
+  c->cells16 = 0;
+  c->pairs_part = 0;
+  {
+    std::vector<uint64_t> suffix(n + 1, 0);
+    for (uint32_t i = n; i-- > 0;) suffix[i] = suffix[i + 1] + c->lens[i];
+    for (uint32_t r = 0; r < nq; r++) {
+      const uint32_t q = c->q_end - 1 - r;
+      const uint32_t a1 = lo + 2 * q;
+      const uint32_t nsub = hi - a1 - 1;
+      c->task_prefix[r + 1] = c->task_prefix[r] + (nsub + 31) / 32;
+      c->cells16 += (uint64_t)c->lens[a1] * (suffix[a1 + 1] - suffix[hi]) +
+                    (uint64_t)c->lens[a1 + 1] * (suffix[a1 + 2] - suffix[hi]);
+      c->pairs_part += (uint64_t)(hi - a1 - 1) + (hi - a1 - 2);
+    }
+  }
+  c->cells32 = 0;
+
+  // ---- strip width: least padded columns over the instantiated variants ---------------------
+  {
+    uint64_t best = ~0ull;
+    int bestK = tsq::kStripWidths[0];
+    for (int v = 0; v < tsq::kNumStripWidths; v++) {
+      const int K = tsq::kStripWidths[v];
+      uint64_t padded = 0;
+      for (uint32_t r = 0; r < nq; r++) {
+        const uint32_t q = c->q_end - 1 - r;
+        const uint32_t l2 = c->lens[lo + 2 * q + 1];
+        const uint64_t cols = (uint64_t)((l2 + K - 1) / K) * K + 2;  // +2: per-strip overhead proxy
+        padded += cols * (c->task_prefix[r + 1] - c->task_prefix[r]);
+      }
+      if (padded < best || (padded == best && K > bestK)) {
+        best = padded;
+        bestK = K;
+      }
+    }
+    c->K = bestK;
+  }
+
+  // ---- biased score table -----------------------------------------------------------------
+  const uint32_t nsym = (uint32_t)c->nsym;
+  std::vector<uint32_t> sbias((size_t)(nsym + 1) * nsym, 0);
+  for (uint32_t a = 0; a < nsym; a++)
+    for (uint32_t b = 0; b < nsym; b++) sbias[a * nsym + b] = (uint32_t)(c->matrix[a * nsym + b] + 2 * c->delta);
+
+  // ---- H2D ----------------------------------------------------------------------------------
+  cudaStream_t s = c->stream;
+  TSQ_CUDA(c, c->d_dbw.reserve(c->dbw.size()));
+  TSQ_CUDA(c, c->d_goff.reserve(c->goff.size()));
+  TSQ_CUDA(c, c->d_lin.reserve(c->lin.size()));
+  TSQ_CUDA(c, c->d_loff.reserve(c->loff.size()));
+  TSQ_CUDA(c, c->d_lens.reserve(n + 1));
+  TSQ_CUDA(c, c->d_perm.reserve(n + 1));
+  TSQ_CUDA(c, c->d_self.reserve(n + 1));
+  TSQ_CUDA(c, c->d_sbias.reserve(sbias.size()));
+  TSQ_CUDA(c, c->d_prefix.reserve(c->task_prefix.size()));
+  TSQ_CUDA(c, c->d_counter.reserve(4));
+  TSQ_CUDA(c, c->d_sorted.reserve(npairs));
+  if (!c->dbw.empty()) TSQ_CUDA(c, cudaMemcpyAsync(c->d_dbw.p, c->dbw.data(), c->dbw.size() * 4, cudaMemcpyHostToDevice, s));
+  TSQ_CUDA(c, cudaMemcpyAsync(c->d_goff.p, c->goff.data(), c->goff.size() * 4, cudaMemcpyHostToDevice, s));
+  TSQ_CUDA(c, cudaMemcpyAsync(c->d_lin.p, c->lin.data(), c->lin.size(), cudaMemcpyHostToDevice, s));
+  TSQ_CUDA(c, cudaMemcpyAsync(c->d_loff.p, c->loff.data(), c->loff.size() * 4, cudaMemcpyHostToDevice, s));
+  if (n) {
+    TSQ_CUDA(c, cudaMemcpyAsync(c->d_lens.p, c->lens.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    TSQ_CUDA(c, cudaMemcpyAsync(c->d_perm.p, c->perm.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    TSQ_CUDA(c, cudaMemcpyAsync(c->d_self.p, c->self_sorted.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  }
+  TSQ_CUDA(c, cudaMemcpyAsync(c->d_sbias.p, sbias.data(), sbias.size() * 4, cudaMemcpyHostToDevice, s));
+  TSQ_CUDA(c, cudaMemcpyAsync(c->d_prefix.p, c->task_prefix.data(), c->task_prefix.size() * 8, cudaMemcpyHostToDevice, s));
+  TSQ_CUDA(c, cudaStreamSynchronize(s));
+  c->uploaded = true;
+  c->computed = c->finalized = c->downloaded = false;
+  c->st.upload_ms = now_ms() - t0;
+  return TSQ_OK;
+}
+
+int tsq_compute(tsq_ctx* c) {
+  if (!c) return TSQ_ERR_INVALID;
+  if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "tsq_compute before tsq_upload");
+  TSQ_CUDA(c, cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  uint32_t launches = 0;
+  TSQ_CUDA(c, cudaEventRecord(c->ev0, s));
+  const uint32_t nq = c->q_end - c->q_begin;
+  const unsigned long long ntasks = c->task_prefix.empty() ? 0 : c->task_prefix[nq];
+  if (ntasks > 0) {
+    tsq::G16Launch v;
+    if (!tsq::g16_variant(c->K, (uint32_t)c->nsym, &v)) return fail(c, TSQ_ERR_INVALID, "no kernel variant K=%d", c->K);
+    const int warps_per_cta = v.tpb / 32;
+    int grid = c->sm_count * v.ctas_sm;
+    const unsigned long long need = (ntasks + warps_per_cta - 1) / warps_per_cta;
+    if ((unsigned long long)grid > need) grid = (int)need;
+    const uint32_t maxlen = c->hi > c->lo ? c->lens[c->hi - 1] : 0;
+    const uint32_t bnd_rows = maxlen + 4;
+    TSQ_CUDA(c, c->d_bnd.reserve((size_t)grid * warps_per_cta * bnd_rows * 32));
+    TSQ_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), s));
+    const uint32_t lpad = ((maxlen + c->K - 1) / c->K) * c->K;
+    tsq::G16Params p{};
+    p.dbw = c->d_dbw.p;
+    p.goff = c->d_goff.p;
+    p.lin = c->d_lin.p;
+    p.loff = c->d_loff.p;
+    p.lens = c->d_lens.p;
+    p.task_prefix = c->d_prefix.p;
+    p.counter = c->d_counter.p;
+    p.bnd = c->d_bnd.p;
+    p.sbias = c->d_sbias.p;
+    p.out = c->d_sorted.p;
+    p.ntasks = ntasks;
+    p.bnd_rows = bnd_rows;
+    p.n_total = c->n;
+    p.lo = c->lo;
+    p.hi = c->hi;
+    p.q_begin = c->q_begin;
+    p.q_end = c->q_end;
+    p.nsym = (uint32_t)c->nsym;
+    p.bias = bias_for(c, lpad);
+    p.delta = c->delta;
+    p.go = c->go;
+    p.gep = c->ge - c->delta;
+    p.negge2 = ((uint32_t)(-(c->ge - c->delta)) & 0xffffu) * 0x10001u;
+    p.goe2 = (uint32_t)(c->go + c->ge - c->delta) * 0x10001u;
+    if (!fits16(c, lpad)) return fail(c, TSQ_ERR_RANGE, "internal: padded length %u outside the 16-bit bound", lpad);
+    TSQ_CUDA(c, tsq::g16_launch(c->K, grid, p, s));
+    launches++;
+  }
+  TSQ_CUDA(c, cudaEventRecord(c->ev1, s));
+  c->st.launches = launches;
+  c->computed = true;
+  c->finalized = c->downloaded = false;
+  return TSQ_OK;
+}
+
+int tsq_finalize(tsq_ctx* c) {
+  if (!c) return TSQ_ERR_INVALID;
+  if (!c->computed) return fail(c, TSQ_ERR_STATE, "tsq_finalize before tsq_compute");
+  TSQ_CUDA(c, cudaSetDevice(c->device));
+  const uint32_t n = c->n;
+  const uint64_t npairs = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
+  const bool want_dist = !(c->prm.flags & TSQ_FLAG_NO_DISTANCES);
+  if (npairs > 0 && (want_dist || !c->identity)) {
+    tsq::FinalizeParams f{};
+    f.sorted = c->d_sorted.p;
+    f.lens = c->d_lens.p;
+    f.perm = c->d_perm.p;
+    f.self = c->d_self.p;
+    if (c->identity) {
+      f.out_scores = c->d_sorted.p;
+    } else {
+      TSQ_CUDA(c, c->d_scores.reserve(npairs));
+      f.out_scores = c->d_scores.p;
+    }
+    f.out_dist = nullptr;
+    if (want_dist) {
+      TSQ_CUDA(c, c->d_dist.reserve(npairs));
+      f.out_dist = c->d_dist.p;
+    }
+    f.n = n;
+    f.go = c->go;
+    f.ge = c->ge;
+    f.identity = c->identity ? 1u : 0u;
+    TSQ_CUDA(c, tsq::finalize_launch(f, c->stream));
+    c->st.launches++;
+  }
+  c->finalized = true;
+  return TSQ_OK;
+}
+
+int tsq_synchronize(tsq_ctx* c) {
+  if (!c) return TSQ_ERR_INVALID;
+  TSQ_CUDA(c, cudaSetDevice(c->device));
+  TSQ_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->computed) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->st.kernel_ms = ms;
+    else cudaGetLastError();
+  }
+  return TSQ_OK;
+}
+
+int tsq_download(tsq_ctx* c) {
+  if (!c) return TSQ_ERR_INVALID;
+  if (!c->computed) return fail(c, TSQ_ERR_STATE, "tsq_download before tsq_compute");
+  if (!c->finalized) {
+    if (c->prm.part_world > 1 && c->prm.part_rank != 0) {
+      // non-root ranks only hold a slab; nothing to assemble here
+    } else {
+      int rc = tsq_finalize(c);
+      if (rc != TSQ_OK) return rc;
+    }
+  }
+  const double t0 = now_ms();
+  const uint32_t n = c->n;
+  const uint64_t npairs = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
+  const bool want_dist = !(c->prm.flags & TSQ_FLAG_NO_DISTANCES);
+  cudaStream_t s = c->stream;
+  if (npairs > 0 && c->finalized) {
+    TSQ_CUDA(c, c->h_scores.reserve(npairs));
+    const int32_t* src = c->identity ? c->d_sorted.p : c->d_scores.p;
+    TSQ_CUDA(c, cudaMemcpyAsync(c->h_scores.p, src, npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (want_dist) {
+      TSQ_CUDA(c, c->h_dist.reserve(npairs));
+      TSQ_CUDA(c, cudaMemcpyAsync(c->h_dist.p, c->d_dist.p, npairs * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+  }
+  int rc = tsq_synchronize(c);
+  if (rc != TSQ_OK) return rc;
+  c->downloaded = c->finalized;
+  c->st.download_ms = now_ms() - t0;
+  return TSQ_OK;
+}
+
+int tsq_run(tsq_ctx* c, tsq_progress_cb cb, void* user, volatile int* cancel) {
+  if (!c) return TSQ_ERR_INVALID;
+  auto cancelled = [&]() { return cancel && *cancel != 0; };
+  if (cancelled()) return fail(c, TSQ_ERR_CANCELLED, "cancelled");
+  if (cb) cb(user, 0.0, "packing sequences");
+  int rc = tsq_upload(c);
+  if (rc != TSQ_OK) return rc;
+  if (cancelled()) return fail(c, TSQ_ERR_CANCELLED, "cancelled");
+  if (cb) cb(user, 0.05, "computing pairwise scores");
+  rc = tsq_compute(c);
+  if (rc != TSQ_OK) return rc;
+  // poll the stream so that "Stop" (SeqEditMainWin.cpp:803-812) is honoured while kernels run
+  for (;;) {
+    cudaError_t q = cudaStreamQuery(c->stream);
+    if (q == cudaSuccess) break;
+    if (q != cudaErrorNotReady) return fail(c, TSQ_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(q));
+    if (cancelled()) {
+      cudaStreamSynchronize(c->stream);
+      return fail(c, TSQ_ERR_CANCELLED, "cancelled");
+    }
+    struct timespec ts = {0, 200000};
+    nanosleep(&ts, nullptr);
+  }
+  if (cb) cb(user, 0.9, "collecting results");
+  rc = tsq_download(c);
+  if (rc != TSQ_OK) return rc;
+  if (cb) cb(user, 1.0, "done");
+  return TSQ_OK;
+}
+
+int tsq_scores(tsq_ctx* c, const int32_t** out, uint64_t* count) {
+  if (!c || !out) return TSQ_ERR_INVALID;
+  if (!c->downloaded) return fail(c, TSQ_ERR_STATE, "no results: call tsq_run or tsq_download first");
+  *out = c->h_scores.p;
+  if (count) *count = c->n < 2 ? 0 : (uint64_t)c->n * (c->n - 1) / 2;
+  return TSQ_OK;
+}
+
+int tsq_distances(tsq_ctx* c, const double** out, uint64_t* count) {
+  if (!c || !out) return TSQ_ERR_INVALID;
+  if (!c->downloaded) return fail(c, TSQ_ERR_STATE, "no results: call tsq_run or tsq_download first");
+  if (c->prm.flags & TSQ_FLAG_NO_DISTANCES) return fail(c, TSQ_ERR_STATE, "distances disabled by TSQ_FLAG_NO_DISTANCES");
+  *out = c->h_dist.p;
+  if (count) *count = c->n < 2 ? 0 : (uint64_t)c->n * (c->n - 1) / 2;
+  return TSQ_OK;
+}
+
+int tsq_self_scores(tsq_ctx* c, const int32_t** self, uint32_t* n) {
+  if (!c || !self) return TSQ_ERR_INVALID;
+  if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "no sequences uploaded");
+  *self = c->self_orig.data();
+  if (n) *n = c->n;
+  return TSQ_OK;
+}
+
+int tsq_device_scores(tsq_ctx* c, void** d, uint64_t* count) {
+  if (!c || !d) return TSQ_ERR_INVALID;
+  if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "tsq_device_scores before tsq_upload");
+  *d = c->d_sorted.p;
+  if (count) *count = c->n < 2 ? 0 : (uint64_t)c->n * (c->n - 1) / 2;
+  return TSQ_OK;
+}
+
+int tsq_partition(tsq_ctx* c, uint64_t* b, uint64_t* e) {
+  if (!c) return TSQ_ERR_INVALID;
+  if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "tsq_partition before tsq_upload");
+  if (b) *b = c->part_begin;
+  if (e) *e = c->part_end;
+  return TSQ_OK;
+}
+
+int tsq_device_results(tsq_ctx* c, void** d_scores, void** d_dist, uint64_t* count) {
+  if (!c) return TSQ_ERR_INVALID;
+  if (!c->finalized) return fail(c, TSQ_ERR_STATE, "tsq_device_results before tsq_finalize");
+  if (d_scores) *d_scores = c->identity ? (void*)c->d_sorted.p : (void*)c->d_scores.p;
+  if (d_dist) *d_dist = (c->prm.flags & TSQ_FLAG_NO_DISTANCES) ? nullptr : (void*)c->d_dist.p;
+  if (count) *count = c->n < 2 ? 0 : (uint64_t)c->n * (c->n - 1) / 2;
+  return TSQ_OK;
+}
+
+int tsq_get_stats(tsq_ctx* c, tsq_stats* out) {
+  if (!c || !out) return TSQ_ERR_INVALID;
+  c->st.n_sequences = c->n;
+  c->st.n_pairs = c->pairs_part;
+  c->st.cells_s16 = c->cells16;
+  c->st.cells_s32 = c->cells32;
+  c->st.cells = c->cells16 + c->cells32;
+  c->st.gcups_kernel = c->st.kernel_ms > 0 ? (double)c->st.cells / (c->st.kernel_ms * 1e6) : 0.0;
+  c->st.sm_count = (uint32_t)c->sm_count;
+  c->st.strip_width = (uint32_t)c->K;
+  *out = c->st;
+  return TSQ_OK;
+}
+
+int tsq_measure_dpx_rate(tsq_ctx* c, double* ops, double* mhz) {
+  if (!c) return TSQ_ERR_INVALID;
+  TSQ_CUDA(c, cudaSetDevice(c->device));
+  TSQ_CUDA(c, tsq::dpx_probe(c->sm_count, ops, mhz, c->stream));
+  return TSQ_OK;
+}
+
+// ---- file-level convenience -------------------------------------------------------------------
+// FASTA reading follows tweakseq/Core/FASTAFile.cpp:71-147 (state machine: '>' or ';' starts a
+// record, further ';' lines directly after a header are skipped, blank lines ignored, lines
+// trimmed) and the label rule of parseComment (:177-187: header[1 .. first space)).
+int tsq_run_fasta(const char* fin, const char* fout, const tsq_params* params, tsq_log_cb log, void* user,
+                  volatile int* cancel) {
+  if (!fin || !fout) return TSQ_ERR_INVALID;
+  auto say = [&](const std::string& s) { if (log) log(user, s.c_str()); };
+  std::ifstream in(fin);
+  if (!in) {
+    say(std::string("cannot open ") + fin);
+    return TSQ_ERR_IO;
+  }
+  std::vector<std::string> labels, seqs;
+  std::string line;
+  int state = 0;  // 0 seeking header, 1 just read header, 2 reading residues
+  auto trim = [](std::string& s) {
+    size_t a = 0, b = s.size();
+    while (a < b && isspace((unsigned char)s[a])) a++;
+    while (b > a && isspace((unsigned char)s[b - 1])) b--;
+    s = s.substr(a, b - a);
+  };
+  auto label_of = [](const std::string& h) {
+    const size_t sp = h.find(' ', 1);
+    return sp == std::string::npos ? h.substr(1) : h.substr(1, sp - 1);
+  };
+  while (std::getline(in, line)) {
+    trim(line);
+    if (line.empty()) continue;
+    const char f = line[0];
+    const bool hdr = (f == '>' || f == ';');
+    if (state == 0) {
+      if (hdr) { labels.push_back(label_of(line)); seqs.emplace_back(); state = 1; }
+    } else if (state == 1) {
+      if (f == ';') continue;
+      if (f == '>') { labels.push_back(label_of(line)); seqs.emplace_back(); continue; }
+      seqs.back() += line;
+      state = 2;
+    } else {
+      if (hdr) { labels.push_back(label_of(line)); seqs.emplace_back(); state = 1; }
+      else seqs.back() += line;
+    }
+  }
+  char msg[256];
+  snprintf(msg, sizeof msg, "tsq-b200: read %zu sequences from %s", seqs.size(), fin);
+  say(msg);
+  tsq_ctx* c = nullptr;
+  int rc = tsq_create(&c, params);
+  if (rc != TSQ_OK) {
+    say(std::string("tsq_create failed: ") + tsq_status_string(rc));
+    return rc;
+  }
+  std::vector<const char*> ptrs(seqs.size());
+  std::vector<uint32_t> lens(seqs.size());
+  for (size_t i = 0; i < seqs.size(); i++) {
+    ptrs[i] = seqs[i].data();
+    lens[i] = (uint32_t)seqs[i].size();
+  }
+  rc = tsq_set_sequences(c, ptrs.data(), lens.data(), (uint32_t)seqs.size());
+  if (rc == TSQ_OK) rc = tsq_run(c, nullptr, nullptr, cancel);
+  if (rc != TSQ_OK) {
+    say(std::string("tsq-b200: ") + tsq_last_error(c));
+    tsq_destroy(c);
+    return rc;
+  }
+  const double* d = nullptr;
+  uint64_t cnt = 0;
+  rc = tsq_distances(c, &d, &cnt);
+  if (rc == TSQ_OK) {
+    FILE* fo = fopen(fout, "w");
+    if (!fo) {
+      say(std::string("cannot write ") + fout);
+      rc = TSQ_ERR_IO;
+    } else {
+      const uint64_t n = seqs.size();
+      fprintf(fo, "%llu\n", (unsigned long long)n);
+      for (uint64_t i = 0; i < n; i++) {
+        fprintf(fo, "%s", labels[i].c_str());
+        for (uint64_t j = 0; j < n; j++) {
+          double v = 0.0;
+          if (i != j) v = d[i < j ? tri(i, j, n) : tri(j, i, n)];
+          fprintf(fo, " %.6f", v);
+        }
+        fputc('\n', fo);
+      }
+      fclose(fo);
+      tsq_stats st;
+      tsq_get_stats(c, &st);
+      snprintf(msg, sizeof msg, "tsq-b200: %llu pairs, %.3e cells, kernel %.3f ms (%.1f GCUPS), wrote %s",
+               (unsigned long long)cnt, (double)st.cells, st.kernel_ms, st.gcups_kernel, fout);
+      say(msg);
+    }
+  }
+  tsq_destroy(c);
+  return rc;
+}
+
+}  // extern "C"

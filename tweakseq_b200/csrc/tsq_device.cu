@@ -1,0 +1,165 @@
+// tsq_device.cu -- kernel instantiations and launchers (sm_100a only).
+#include "tsq_device.h"
+
+#include <cstdio>
+
+namespace tsq {
+
+// ---- packed 16-bit inter-task kernel variants -------------------------------------------
+// (K, threads per CTA, CTAs per SM).  Register budget = 65536 / (tpb * ctas_sm).
+#define TSQ_G16_VARIANTS(X) \
+  X(32, 128, 4)             \
+  X(40, 128, 3)             \
+  X(50, 128, 3)             \
+  X(60, 128, 2)
+
+const int kStripWidths[kNumStripWidths] = {32, 40, 50, 60};
+
+bool g16_variant(int K, uint32_t nsym, G16Launch* out) {
+#define X(KK, TT, MM)                                                                     \
+  if (K == KK) {                                                                          \
+    if (out) {                                                                            \
+      out->K = KK;                                                                        \
+      out->tpb = TT;                                                                      \
+      out->ctas_sm = MM;                                                                  \
+      const size_t sbsz = ((size_t)(nsym + 1) * nsym + 31) & ~(size_t)31;                 \
+      out->smem = (sbsz + (size_t)(TT / 32) * nsym * G16Cfg<KK>::STRIDE) * sizeof(uint32_t); \
+    }                                                                                     \
+    return true;                                                                          \
+  }
+  TSQ_G16_VARIANTS(X)
+#undef X
+  return false;
+}
+
+cudaError_t g16_launch(int K, int grid, const G16Params& p, cudaStream_t stream) {
+  G16Launch v;
+  if (!g16_variant(K, p.nsym, &v)) return cudaErrorInvalidValue;
+#define X(KK, TT, MM)                                                                          \
+  if (K == KK) {                                                                               \
+    auto kern = gotoh16_kernel<KK, TT, MM>;                                                    \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                         (int)v.smem);                                         \
+    if (e != cudaSuccess) return e;                                                            \
+    kern<<<grid, TT, v.smem, stream>>>(p);                                                     \
+    return cudaGetLastError();                                                                 \
+  }
+  TSQ_G16_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
+// ---- finalize: empties, un-sort, fp64 distances -----------------------------------------
+// One CTA per sorted row i; threads stride over j > i.  Distances follow the oracle's
+// tsq_oracle_distance(): two separately rounded IEEE operations (div, sub), no contraction.
+__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeParams p) {
+  const unsigned long long n = p.n;
+  for (unsigned long long i = blockIdx.x; i + 1 < n; i += gridDim.x) {
+    const uint32_t li = p.lens[i];
+    const uint32_t oi = p.identity ? (uint32_t)i : p.perm[i];
+    const int32_t si = p.self[i];
+    const unsigned long long rowbase = tri_index(i, i + 1, n);
+    for (unsigned long long j = i + 1 + threadIdx.x; j < n; j += blockDim.x) {
+      const unsigned long long sidx = rowbase + (j - i - 1);
+      int32_t s;
+      if (li == 0) {
+        const uint32_t lj = p.lens[j];
+        s = lj == 0 ? 0 : -(p.go + (int32_t)lj * p.ge);
+      } else {
+        s = p.sorted[sidx];
+      }
+      unsigned long long oidx = sidx;
+      if (!p.identity) {
+        const uint32_t oj = p.perm[j];
+        const unsigned long long a = oi < oj ? oi : oj, b = oi < oj ? oj : oi;
+        oidx = tri_index(a, b, n);
+      }
+      if (p.out_scores != p.sorted || li == 0) p.out_scores[oidx] = s;
+      if (p.out_dist) {
+        const int32_t sj = p.self[j];
+        const int32_t mn = si < sj ? si : sj;
+        double d = 1.0;
+        if (mn > 0) d = __dsub_rn(1.0, __ddiv_rn((double)s, (double)mn));
+        p.out_dist[oidx] = d;
+      }
+    }
+  }
+}
+
+cudaError_t finalize_launch(const FinalizeParams& p, cudaStream_t stream) {
+  if (p.n < 2) return cudaSuccess;
+  unsigned int grid = p.n - 1;
+  if (grid > 148u * 64u) grid = 148u * 64u;
+  finalize_kernel<<<grid, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// ---- DPX issue-rate probe -----------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1) dpx_probe_kernel(uint32_t* out, uint32_t k1, uint32_t k2,
+                                                            long long* cyc) {
+  constexpr int NCH = 8, ITER = 2048;
+  uint32_t a[NCH], b[NCH];
+#pragma unroll
+  for (int i = 0; i < NCH; i++) {
+    a[i] = threadIdx.x * 7 + i + k1;
+    b[i] = threadIdx.x * 3 + i * 5 + k2;
+  }
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < ITER; it++) {
+#pragma unroll
+    for (int i = 0; i < NCH; i++) {
+      a[i] = __viaddmax_u16x2(a[i], k1, b[i]);
+      b[i] = __vimax3_u16x2(b[i], k2, a[i]);
+    }
+  }
+  const long long t1 = clock64();
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < NCH; i++) r ^= a[i] ^ b[i];
+  if (r == 0x12345678u) out[threadIdx.x] = r;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+cudaError_t dpx_probe(int sms, double* ops_per_clk_per_sm, double* sm_mhz, cudaStream_t stream) {
+  uint32_t* d_out = nullptr;
+  long long* d_cyc = nullptr;
+  cudaError_t e;
+  if ((e = cudaMalloc(&d_out, 1024 * sizeof(uint32_t))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&d_cyc, sizeof(long long) * sms)) != cudaSuccess) {
+    cudaFree(d_out);
+    return e;
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  dpx_probe_kernel<<<sms, 1024, 0, stream>>>(d_out, 3, 5, d_cyc);  // warm-up
+  cudaEventRecord(e0, stream);
+  dpx_probe_kernel<<<sms, 1024, 0, stream>>>(d_out, 3, 5, d_cyc);
+  cudaEventRecord(e1, stream);
+  e = cudaStreamSynchronize(stream);
+  if (e == cudaSuccess) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    long long* h = new long long[sms];
+    e = cudaMemcpy(h, d_cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
+    double avg = 0;
+    long long mx = 0;
+    for (int i = 0; i < sms; i++) {
+      avg += (double)h[i];
+      if (h[i] > mx) mx = h[i];
+    }
+    avg /= sms;
+    delete[] h;
+    const double ops = 1024.0 * 8 * 2048 * 2;
+    if (ops_per_clk_per_sm) *ops_per_clk_per_sm = ops / avg;
+    if (sm_mhz) *sm_mhz = ms > 0 ? (double)mx / (ms * 1e3) : 0.0;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  cudaFree(d_cyc);
+  return e;
+}
+
+}  // namespace tsq

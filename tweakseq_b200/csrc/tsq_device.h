@@ -1,0 +1,42 @@
+// tsq_device.h -- host-callable launchers of the sm_100a kernels (internal, C++).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "gotoh16.cuh"
+
+namespace tsq {
+
+// Strip widths the packed 16-bit kernel is instantiated for.
+constexpr int kNumStripWidths = 4;
+extern const int kStripWidths[kNumStripWidths];
+
+struct G16Launch {
+  int K;         // strip width
+  int tpb;       // threads per CTA
+  int ctas_sm;   // resident CTAs per SM the variant is compiled for
+  size_t smem;   // dynamic shared memory per CTA for a given nsym
+};
+
+// Static description of the variant with strip width K (nullptr-safe: returns false).
+bool g16_variant(int K, uint32_t nsym, G16Launch* out);
+// Launch the packed 16-bit kernel: grid CTAs of the variant's size on `stream`.
+cudaError_t g16_launch(int K, int grid, const G16Params& p, cudaStream_t stream);
+
+struct FinalizeParams {
+  const int32_t* sorted;      // packed triangle, sorted order
+  const uint32_t* lens;       // sorted lengths
+  const uint32_t* perm;       // sorted index -> original index
+  const int32_t* self;        // self scores, sorted order
+  int32_t* out_scores;        // packed triangle, original order (may alias sorted if identity)
+  double* out_dist;           // packed triangle, original order, or nullptr
+  uint32_t n;
+  int32_t go, ge;
+  uint32_t identity;          // perm is the identity and there are no empty sequences
+};
+cudaError_t finalize_launch(const FinalizeParams& p, cudaStream_t stream);
+
+// DPX issue-rate probe: thread-level VIADDMNMX.U16x2 + VIMNMX3.U16x2 results / clk / SM.
+cudaError_t dpx_probe(int device_sms, double* ops_per_clk_per_sm, double* sm_mhz, cudaStream_t stream);
+
+}  // namespace tsq
