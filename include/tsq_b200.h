@@ -87,6 +87,8 @@ typedef struct tsq_stats {
   uint32_t sm_count;
   uint32_t strip_width;      /* K of the 16-bit kernel variant used */
   uint32_t reserved;
+  uint64_t h2d_bytes;        /* bytes the last tsq_upload copied host -> device */
+  uint64_t d2h_bytes;        /* bytes the last tsq_download copied device -> host */
 } tsq_stats;
 
 /* progress in [0,1]; msg may be NULL.  Return value ignored. */
@@ -148,6 +150,14 @@ int tsq_partition(tsq_ctx *ctx, uint64_t *part_begin, uint64_t *part_end);
 /* Sorted-order slab complete on this device -> original-order scores (+distances). */
 int tsq_finalize(tsq_ctx *ctx);
 int tsq_device_results(tsq_ctx *ctx, void **d_scores, void **d_distances, uint64_t *count);
+
+/*
+ * Host-only planning (no device needed): the packed-index slab [begins[r], ends[r]) -- in the
+ * library's length-sorted order -- that rank r of `world` computes for sequences of the given
+ * encoded lengths.  Same arithmetic tsq_upload uses; lets the host layer size its gather.
+ */
+int tsq_plan_partition(const tsq_params *params, const uint32_t *lengths, uint32_t n,
+                       int32_t world, uint64_t *begins, uint64_t *ends);
 
 int tsq_get_stats(tsq_ctx *ctx, tsq_stats *out);
 

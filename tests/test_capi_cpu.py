@@ -1,0 +1,82 @@
+"""CPU-side checks of the C ABI: the library builds, loads, exports every symbol the header
+declares, and fails loudly (no fallback) without a B200.  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+import tweakseq_b200 as t
+from tweakseq_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "tsq_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tsq_[a-z0-9_]+)\s*\(", src)) - {"tsq_progress_cb", "tsq_log_cb"})
+
+
+def test_library_exports_every_declared_symbol():
+    L = t.load_library()
+    syms = _header_symbols()
+    assert len(syms) >= 25
+    assert sorted(capi.SYMBOLS) == syms
+    for s in syms:
+        assert hasattr(L, s), s
+
+
+def test_version_and_status_strings():
+    L = t.load_library()
+    ma, mi = C.c_int(), C.c_int()
+    assert L.tsq_version(C.byref(ma), C.byref(mi)) == 0
+    assert (ma.value, mi.value) == (0, 1)
+    assert b"sm_100a" in L.tsq_version_string()
+    assert L.tsq_status_string(0) == b"ok"
+    assert L.tsq_status_string(-2) == b"no sm_100 CUDA device"
+
+
+def test_default_params():
+    p = capi.Params()
+    t.load_library().tsq_default_params(C.byref(p))
+    assert p.struct_size == C.sizeof(capi.Params)
+    assert (p.alphabet, p.gap_open, p.gap_extend, p.part_rank, p.part_world, p.flags) == (0, -1, -1, 0, 1, 0)
+
+
+def test_parameter_validation_happens_before_device_probe():
+    L = t.load_library()
+    h = C.c_void_p()
+    p = capi.Params()
+    L.tsq_default_params(C.byref(p))
+    p.alphabet = 7
+    assert L.tsq_create(C.byref(h), C.byref(p)) == -1
+    L.tsq_default_params(C.byref(p))
+    p.part_rank, p.part_world = 3, 2
+    assert L.tsq_create(C.byref(h), C.byref(p)) == -1
+    L.tsq_default_params(C.byref(p))
+    m = np.zeros((23, 23), dtype=np.int8)
+    m[0, 1] = 3                      # asymmetric
+    p.matrix = m.ctypes.data_as(C.POINTER(C.c_int8))
+    assert L.tsq_create(C.byref(h), C.byref(p)) == -8
+    assert L.tsq_create(None, None) == -1
+
+
+def test_no_cpu_fallback_without_a_device():
+    if t.load_library().tsq_device_count() > 0:
+        return                       # on the GPU box the gpu-marked tests cover creation
+    try:
+        t.Context()
+    except t.TsqError as e:
+        assert e.status == -2
+    else:
+        raise AssertionError("tsq_create must fail without an sm_100 device")
+
+
+def test_null_context_calls_are_errors_not_crashes():
+    L = t.load_library()
+    for f in ("tsq_upload", "tsq_compute", "tsq_download", "tsq_synchronize", "tsq_finalize"):
+        assert getattr(L, f)(None) == -1
+    assert L.tsq_destroy(None) == 0
+    assert L.tsq_last_error(None) == b"null context"
+    assert L.tsq_run_fasta(None, None, None, capi.LOG_CB(0), None, None) == -1

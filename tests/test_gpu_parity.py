@@ -1,0 +1,268 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs, against the committed golden vectors, and -- at BASELINE.json's full sizes --
+through size-independent properties.  Bit-exact: integer scores identical, fp64 distances
+identical bit for bit."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import tweakseq_b200 as t
+from tweakseq_b200 import capi, synth
+from tweakseq_b200.fasta import read_distmat, write_fasta
+from oracle import pyoracle as o
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+AA = "ARNDCQEGHILKMFPSTWYVBZX"
+NT = os.cpu_count() or 1
+
+
+def gpu_run(seqs, **kw):
+    with t.Context(**kw) as ctx:
+        ctx.set_sequences(seqs)
+        ctx.run()
+        d = None if kw.get("flags", 0) & t.FLAG_NO_DISTANCES else ctx.distances()
+        return ctx.scores(), d, ctx.self_scores(), ctx.stats()
+
+
+def oracle_run(seqs, alphabet=0, go=None, ge=1):
+    go = (11 if alphabet == 0 else 10) if go is None else go
+    enc = [o.encode(s, alphabet) for s in seqs]
+    mat = o.matrix(alphabet)
+    s, cells = o.all_pairs(enc, mat, go, ge, nthreads=NT)
+    selfs = np.array([o.self_score(e, mat) for e in enc], dtype=np.int32)
+    return s, o.distances(s, selfs), selfs, cells
+
+
+def assert_same(seqs, alphabet=0, go=None, ge=1, **kw):
+    s, d, selfs, st = gpu_run(seqs, alphabet=alphabet, gap_open=-1 if go is None else go, gap_extend=ge, **kw)
+    rs, rd, rselfs, cells = oracle_run(seqs, alphabet, go, ge)
+    assert (s == rs).all(), np.nonzero(s != rs)[0][:10]
+    assert (selfs == rselfs).all()
+    assert d.tobytes() == rd.tobytes()
+    return st, cells
+
+
+def ragged(rng, n, lo, hi, letters=AA):
+    return ["".join(rng.choice(list(letters), int(l))) for l in rng.integers(lo, hi, n)]
+
+
+def test_device_is_b200_class():
+    assert t.load_library().tsq_device_count() >= 1
+
+
+def test_golden_allpairs():
+    g = json.load(open(os.path.join(HERE, "golden", "allpairs_small.json")))
+    s, d, selfs, _ = gpu_run(g["seqs"], gap_open=g["go"], gap_extend=g["ge"])
+    assert s.tolist() == g["scores"]
+    assert selfs.tolist() == g["self"]
+    assert [float(x).hex() for x in d] == g["distances_hex"]
+
+
+def test_golden_pairs_each_as_a_two_sequence_job():
+    pairs = json.load(open(os.path.join(HERE, "golden", "pairs.json")))
+    for p in pairs:
+        s, _, _, _ = gpu_run([p["a"], p["b"]], alphabet=p["alphabet"], gap_open=p["go"], gap_extend=p["ge"])
+        assert int(s[0]) == p["score"], p
+
+
+@pytest.mark.parametrize("go,ge", [(None, 1), (5, 2), (0, 0), (0, 3), (30, 0), (1, 7)])
+def test_ragged_protein_all_gap_models(go, ge):
+    rng = np.random.default_rng(31)
+    seqs = ragged(rng, 77, 0, 140)
+    seqs[4] = ""; seqs[40] = ""; seqs[9] = "acdefg-hik.lmn pq"; seqs[11] = "W"; seqs[12] = "*1?JOU"
+    assert_same(seqs, 0, go, ge)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 64, 65, 129])
+def test_group_and_chunk_edges(n):
+    rng = np.random.default_rng(n)
+    seqs = ragged(rng, n, 1, 90)
+    if n == 1:
+        s, d, selfs, _ = gpu_run(seqs)
+        assert len(s) == 0 and len(d) == 0 and len(selfs) == 1
+    else:
+        assert_same(seqs)
+
+
+def test_zero_sequences_and_all_empty():
+    s, d, selfs, _ = gpu_run([])
+    assert len(s) == 0 and len(selfs) == 0
+    s, d, _, _ = gpu_run(["", "--", " "])
+    assert s.tolist() == [0, 0, 0] and d.tolist() == [1.0, 1.0, 1.0]
+
+
+@pytest.mark.parametrize("lens", [(49, 50, 51), (59, 60, 61, 120, 121), (1, 299, 300, 301), (31, 32, 33, 64)])
+def test_strip_width_boundaries(lens):
+    rng = np.random.default_rng(sum(lens))
+    seqs = []
+    for l in lens:
+        seqs += ragged(rng, 9, l, l + 1, AA[:20])
+    assert_same(seqs)
+
+
+def test_config1_full():
+    _, seqs = synth.config(1)
+    st, cells = assert_same(seqs)
+    assert st["cells"] == cells == synth.total_cells(seqs)
+    fam = synth.protein(100, (200, 400, 300, 30), 1, family=True)
+    assert_same(fam)
+
+
+def test_config2_full_1000x300():
+    _, seqs = synth.config(2)
+    st, cells = assert_same(seqs)
+    assert st["n_pairs"] == 499500 and st["cells"] == cells == 44955000000
+
+
+def test_longer_proteins_and_mixed_lengths():
+    rng = np.random.default_rng(77)
+    seqs = ragged(rng, 40, 600, 1500, AA[:20]) + ragged(rng, 30, 1, 50, AA[:20])
+    assert_same(seqs)
+
+
+def test_nucleotide_short_reads():
+    rng = np.random.default_rng(78)
+    seqs = ragged(rng, 50, 0, 400, "ACGTN") + ["acgu-nn", "RYKM"]
+    assert_same(seqs, alphabet=1)
+    assert_same(seqs, alphabet=1, go=4, ge=4)
+
+
+def test_custom_symmetric_matrix():
+    rng = np.random.default_rng(79)
+    m = rng.integers(-7, 9, (23, 23))
+    m = np.triu(m) + np.triu(m, 1).T
+    seqs = ragged(rng, 45, 1, 120)
+    with t.Context(matrix=m.astype(np.int8), gap_open=6, gap_extend=2) as ctx:
+        ctx.set_sequences(seqs)
+        ctx.run()
+        s = ctx.scores()
+    enc = [o.encode(x) for x in seqs]
+    ref, _ = o.all_pairs(enc, m.astype(np.int8), 6, 2, nthreads=NT)
+    assert (s == ref).all()
+
+
+def test_input_order_does_not_change_scores():
+    rng = np.random.default_rng(80)
+    seqs = ragged(rng, 60, 5, 200)
+    s1, d1, _, _ = gpu_run(seqs)
+    perm = rng.permutation(len(seqs))
+    s2, d2, _, _ = gpu_run([seqs[k] for k in perm])
+    n = len(seqs)
+    for a in range(n):
+        for b in range(a + 1, n):
+            i, j = sorted((int(perm[a]), int(perm[b])))
+            assert s2[t.pair_index(a, b, n)] == s1[t.pair_index(i, j, n)]
+            assert d2[t.pair_index(a, b, n)] == d1[t.pair_index(i, j, n)]
+
+
+def test_properties_identical_and_gapped_sequences():
+    rng = np.random.default_rng(81)
+    base = ragged(rng, 20, 50, 300, AA[:20])
+    gapped = [s[:10] + "-" * 3 + s[10:] + ".." for s in base]
+    s, d, selfs, _ = gpu_run(base + base + gapped)
+    n = 60
+    for k in range(20):
+        assert s[t.pair_index(k, k + 20, n)] == selfs[k]          # S(x, x) = sum of diagonal
+        assert d[t.pair_index(k, k + 20, n)] == 0.0
+        assert s[t.pair_index(k, k + 40, n)] == selfs[k]          # gaps are stripped before DP
+    s2, _, _, _ = gpu_run(base + base + gapped)                    # idempotent
+    assert (s == s2).all()
+
+
+def test_staged_api_and_repeat_compute_is_stable():
+    _, seqs = synth.config(2, 0.2)
+    with t.Context() as ctx:
+        ctx.set_sequences(seqs)
+        ctx.upload()
+        ctx.compute(); ctx.download()
+        a = ctx.scores()
+        ctx.compute(); ctx.compute(); ctx.download()
+        b = ctx.scores()
+        st = ctx.stats()
+    assert (a == b).all() and st["kernel_ms"] > 0 and st["launches"] >= 1
+
+
+def test_partition_slabs_tile_the_matrix():
+    rng = np.random.default_rng(82)
+    seqs = ragged(rng, 150, 30, 260, AA[:20])
+    full, _, _, _ = gpu_run(seqs, flags=t.FLAG_NO_DISTANCES)
+    import torch
+    world = 3
+    bufs, ranges = [], []
+    ctxs = []
+    for r in range(world):
+        ctx = t.Context(part_rank=r, part_world=world, flags=t.FLAG_NO_DISTANCES)
+        ctx.set_sequences(seqs); ctx.upload(); ctx.compute(); ctx.synchronize()
+        ranges.append(ctx.partition())
+        bufs.append(torch.as_tensor(ctx.device_scores(), device="cuda"))
+        ctxs.append(ctx)
+    assert ranges == capi.plan_partition([len(s) for s in seqs], world)
+    assert ranges[0][0] == 0 and ranges[-1][1] == len(full)
+    root = bufs[0]
+    for r in range(1, world):
+        b, e = ranges[r]
+        root[b:e] = bufs[r][b:e]                       # what the NCCL gather does across ranks
+    ctxs[0].finalize(); ctxs[0].download()
+    assert (ctxs[0].scores() == full).all()
+    for c in ctxs:
+        c.close()
+
+
+def test_run_fasta_writes_clustalo_distmat(tmp_path):
+    rng = np.random.default_rng(83)
+    seqs = ragged(rng, 12, 20, 90, AA[:20])
+    labels = [f"seq{k}" for k in range(12)]
+    fin, fout = str(tmp_path / "in.fa"), str(tmp_path / "out.mat")
+    write_fasta(fin, labels, seqs, [f">{l} some description" for l in labels])
+    log = []
+    tool = t.B200Gotoh()
+    assert tool.run(fin, fout, log=log.append) == 0
+    lab, rows = read_distmat(fout)
+    assert lab == labels and len(rows) == 12 and any("GCUPS" in m for m in log)
+    _, rd, _, _ = oracle_run(seqs)
+    for i in range(12):
+        assert rows[i][i] == 0.0
+        for j in range(i + 1, 12):
+            assert abs(rows[i][j] - rd[t.pair_index(i, j, 12)]) < 5e-7 and rows[j][i] == rows[i][j]
+    assert tool.run(str(tmp_path / "missing.fa"), fout) == -7
+
+
+def test_cancel_and_state_errors():
+    with t.Context() as ctx:
+        with pytest.raises(t.TsqError) as e:
+            ctx.upload()
+        assert e.value.status == -6
+        ctx.set_sequences(["ACD", "ACE"])
+        flag = C.c_int(1)
+        with pytest.raises(t.TsqError) as e:
+            ctx.run(cancel=flag)
+        assert e.value.status == -5
+        with pytest.raises(t.TsqError):
+            ctx.scores()
+        ctx.run()
+        assert ctx.scores().tolist() == [o.score_str("ACD", "ACE")]
+
+
+def test_backend_object_and_progress_callback():
+    tool = t.B200Gotoh()
+    seen = []
+    _, seqs = synth.config(1)
+    s, d = tool.distance_matrix(seqs[:30], progress=lambda f, m: seen.append(f))
+    rs, rd, _, _ = oracle_run(seqs[:30])
+    assert (s == rs).all() and d.tobytes() == rd.tobytes()
+    assert seen[0] == 0.0 and seen[-1] == 1.0 and tool.last_stats["cells"] > 0
+    cells = [[ord(c) for c in q] for q in seqs[:5]]
+    cells[0][3] |= 0x80            # an excluded residue cell (Sequence.h:36)
+    s2, _ = tool.distance_matrix_from_cells(cells)
+    rs2, _, _, _ = oracle_run([seqs[0][:3] + seqs[0][4:]] + seqs[1:5])
+    assert (s2 == rs2).all()
+
+
+def test_dpx_probe_reports_the_alu_rate():
+    with t.Context() as ctx:
+        ops, mhz = ctx.measure_dpx_rate()
+    assert 50 < ops < 80 and 1000 < mhz < 2200

@@ -38,7 +38,7 @@ class Stats(C.Structure):
                 ("cells_s16", C.c_uint64), ("cells_s32", C.c_uint64), ("kernel_ms", C.c_double),
                 ("upload_ms", C.c_double), ("download_ms", C.c_double), ("gcups_kernel", C.c_double),
                 ("launches", C.c_uint32), ("sm_count", C.c_uint32), ("strip_width", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("reserved", C.c_uint32), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -52,7 +52,7 @@ SYMBOLS = ["tsq_version", "tsq_version_string", "tsq_status_string", "tsq_device
            "tsq_create", "tsq_destroy", "tsq_last_error", "tsq_set_sequences", "tsq_upload", "tsq_compute",
            "tsq_download", "tsq_set_stream", "tsq_synchronize", "tsq_run", "tsq_scores", "tsq_distances",
            "tsq_self_scores", "tsq_device_scores", "tsq_partition", "tsq_finalize", "tsq_device_results",
-           "tsq_get_stats", "tsq_measure_dpx_rate", "tsq_run_fasta"]
+           "tsq_get_stats", "tsq_measure_dpx_rate", "tsq_run_fasta", "tsq_plan_partition"]
 
 _lib = None
 
@@ -99,6 +99,7 @@ def load_library():
     L.tsq_partition.argtypes = [vp, u64p, u64p]
     L.tsq_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), u64p]
     L.tsq_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.tsq_plan_partition.argtypes = [C.POINTER(Params), C.POINTER(C.c_uint32), C.c_uint32, C.c_int32, u64p, u64p]
     L.tsq_measure_dpx_rate.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.tsq_run_fasta.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(Params), LOG_CB, vp, C.POINTER(C.c_int)]
     _lib = L
@@ -108,6 +109,22 @@ def load_library():
 def pair_index(i: int, j: int, n: int) -> int:
     """Packed upper-triangle index of (i, j), i < j (include/tsq_b200.h)."""
     return i * n - i * (i + 1) // 2 + (j - i - 1)
+
+
+def plan_partition(lengths, world: int, **kw) -> list[tuple[int, int]]:
+    """tsq_plan_partition(): per-rank [begin, end) slabs of the sorted packed index space (host only)."""
+    L = load_library()
+    p = Params()
+    L.tsq_default_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    lens = np.ascontiguousarray(lengths, dtype=np.uint32)
+    b = (C.c_uint64 * world)()
+    e = (C.c_uint64 * world)()
+    rc = L.tsq_plan_partition(C.byref(p), lens.ctypes.data_as(C.POINTER(C.c_uint32)), len(lens), world, b, e)
+    if rc != 0:
+        raise TsqError(rc, "tsq_plan_partition")
+    return [(int(b[r]), int(e[r])) for r in range(world)]
 
 
 class _DevArray:

@@ -124,8 +124,11 @@ struct tsq_ctx {
   std::vector<uint32_t> perm;             // sorted -> submitted
   std::vector<uint32_t> lens;             // sorted
   std::vector<uint32_t> loff;             // sorted
-  std::vector<uint8_t> lin;               // sorted, concatenated
-  std::vector<uint32_t> dbw, goff;        // interleaved words / group offsets
+  PinnedBuf<uint8_t> lin;                 // sorted, concatenated (pinned staging)
+  size_t lin_size = 0;
+  PinnedBuf<uint32_t> dbw;                // interleaved words (pinned staging)
+  size_t dbw_size = 0;
+  std::vector<uint32_t> goff;             // group offsets
   std::vector<int32_t> self_sorted, self_orig;
   bool identity = true;
   uint32_t lo = 0, hi = 0;  // sorted range eligible for the packed 16-bit kernel
@@ -212,6 +215,42 @@ bool fits16(const tsq_ctx* c, uint32_t lpad) {
   const long long hi = (long long)bias_for(c, lpad) + (long long)std::max(c->smax, 0) * lpad +
                        2LL * c->delta * (lpad + 1) + 16;
   return hi <= 65535;
+}
+
+// Largest sequence length the packed kernel can take (binary search on the range bound).
+uint32_t max_len16_of(const tsq_ctx* c) {
+  uint32_t a = 0, b = 60000;
+  while (b - a > 1) {
+    const uint32_t mid = (a + b) / 2;
+    if (fits16(c, mid + 64)) a = mid; else b = mid;
+  }
+  return a;
+}
+
+// Contiguous partition of the sorted rows over `world` ranks, balanced by weighted DP cells
+// (cells of the 32-bit kernel count twice: one alignment per DPX lane instead of two).  Rows
+// of the packed kernel come in pairs (lo+2q, lo+2q+1), so cuts inside [lo, hi) fall on pair
+// boundaries.  first_row has world+1 entries.
+void plan_rows(const std::vector<uint32_t>& lens, uint32_t lo, uint32_t hi, int world,
+               std::vector<uint32_t>& first_row) {
+  const uint32_t n = (uint32_t)lens.size();
+  std::vector<double> rowcost(n, 0.0);
+  double s16 = 0, s32 = 0, tot = 0;  // suffix sums of lengths below / at-or-above hi
+  for (uint32_t i = n; i-- > 0;) {
+    rowcost[i] = (double)lens[i] * (i < hi ? s16 + 2.0 * s32 : 2.0 * s32);
+    tot += rowcost[i];
+    if (i < hi) s16 += lens[i]; else s32 += lens[i];
+  }
+  first_row.assign((size_t)world + 1, n);
+  first_row[0] = 0;
+  double acc = 0;
+  uint32_t i = 0;
+  for (int r = 1; r < world; r++) {
+    const double target = tot * r / world;
+    while (i < n && acc + rowcost[i] <= target) acc += rowcost[i++];
+    if (i > lo && i < hi && ((i - lo) & 1u)) acc += rowcost[i++];
+    first_row[(size_t)r] = std::min(i, n);
+  }
 }
 
 }  // namespace
@@ -317,15 +356,7 @@ int tsq_create(tsq_ctx** out, const tsq_params* params) {
   c->smin = *std::min_element(c->matrix.begin(), c->matrix.end());
   c->smax = *std::max_element(c->matrix.begin(), c->matrix.end());
   c->delta = c->smin < 0 ? (-c->smin + 1) / 2 : 0;
-  // largest sequence length the packed kernel can take (binary search on the range bound)
-  {
-    uint32_t a = 0, b = 60000;
-    while (b - a > 1) {
-      const uint32_t mid = (a + b) / 2;
-      if (fits16(c, mid + 64)) a = mid; else b = mid;
-    }
-    c->max_len16 = (p.flags & TSQ_FLAG_FORCE_S32) ? 0 : a;
-  }
+  c->max_len16 = (p.flags & TSQ_FLAG_FORCE_S32) ? 0 : max_len16_of(c);
   if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
     cudaGetLastError();
@@ -345,6 +376,7 @@ int tsq_destroy(tsq_ctx* c) {
   c->d_perm.release(); c->d_sbias.release(); c->d_lin.release(); c->d_self.release();
   c->d_sorted.release(); c->d_scores.release(); c->d_dist.release(); c->d_prefix.release();
   c->d_counter.release(); c->d_bnd.release(); c->h_scores.release(); c->h_dist.release();
+  c->lin.release(); c->dbw.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -402,12 +434,14 @@ int tsq_upload(tsq_ctx* c) {
   }
   if (total > 0xfffffff0ull) return fail(c, TSQ_ERR_RANGE, "more than 4 Gi residues");
   c->loff[n] = (uint32_t)total;
-  c->lin.resize(total + 16);
+  TSQ_CUDA(c, c->lin.reserve(total + 16));
+  c->lin_size = total + 16;
+  memset(c->lin.p + total, 0, 16);
   c->self_sorted.resize(n);
   c->self_orig.resize(n);
   for (uint32_t i = 0; i < n; i++) {
     const std::vector<uint8_t>& e = c->enc[c->perm[i]];
-    if (!e.empty()) memcpy(&c->lin[c->loff[i]], e.data(), e.size());
+    if (!e.empty()) memcpy(c->lin.p + c->loff[i], e.data(), e.size());
     int64_t s = 0;
     for (uint8_t a : e) s += c->matrix[a * c->nsym + a];
     c->self_sorted[i] = (int32_t)s;
@@ -435,10 +469,12 @@ int tsq_upload(tsq_ctx* c) {
     if (words > 0xfffffff0ull) return fail(c, TSQ_ERR_RANGE, "interleaved database too large");
   }
   c->goff[ngroups] = (uint32_t)words;
-  c->dbw.assign(words, 0);
+  TSQ_CUDA(c, c->dbw.reserve(words));
+  c->dbw_size = words;
+  memset(c->dbw.p, 0, words * sizeof(uint32_t));
   for (uint32_t i = 0; i < n; i++) {
-    const uint8_t* s = &c->lin[c->loff[i]];
-    uint32_t* base = &c->dbw[c->goff[i >> 5] + (i & 31)];
+    const uint8_t* s = c->lin.p + c->loff[i];
+    uint32_t* base = c->dbw.p + c->goff[i >> 5] + (i & 31);
     const uint32_t l = c->lens[i];
     for (uint32_t r = 0; r < l; r += 4) {
       uint32_t w = 0;
@@ -448,29 +484,10 @@ int tsq_upload(tsq_ctx* c) {
   }
 
   // ---- partition of the sorted rows across ranks (contiguous, balanced by DP cells) ---------
-  // suffix sums of lengths give the cells of each row: len_i * sum_{j>i} len_j
-  std::vector<double> rowcost(n, 0.0);
-  {
-    uint64_t suffix = 0;
-    for (uint32_t i = n; i-- > 0;) {
-      rowcost[i] = (double)c->lens[i] * (double)suffix;
-      suffix += c->lens[i];
-    }
-  }
   const int world = c->prm.part_world, rank = c->prm.part_rank;
-  auto boundary = [&](int r) -> uint32_t {  // first row of rank r
-    if (r <= 0) return 0;
-    if (r >= world) return n;
-    double tot = 0;
-    for (uint32_t i = 0; i < n; i++) tot += rowcost[i];
-    const double target = tot * r / world;
-    double acc = 0;
-    uint32_t i = 0;
-    while (i < n && acc + rowcost[i] <= target) acc += rowcost[i++];
-    // rows of the packed kernel come in pairs (lo+2q, lo+2q+1): cut on a pair boundary
-    if (i > lo && i < hi && ((i - lo) & 1u)) i++;
-    return std::min(i, n);
-  };
+  std::vector<uint32_t> first_row;
+  plan_rows(c->lens, lo, hi, world, first_row);
+  auto boundary = [&](int r) -> uint32_t { return first_row[(size_t)r]; };
   c->row_a = boundary(rank);
   c->row_b = boundary(rank + 1);
   c->part_begin = (n >= 2 && c->row_a + 1 < n) ? tri(c->row_a, c->row_a + 1, n) : npairs;
@@ -534,9 +551,9 @@ int tsq_upload(tsq_ctx* c) {
 
   // ---- H2D ----------------------------------------------------------------------------------
   cudaStream_t s = c->stream;
-  TSQ_CUDA(c, c->d_dbw.reserve(c->dbw.size()));
+  TSQ_CUDA(c, c->d_dbw.reserve(c->dbw_size));
   TSQ_CUDA(c, c->d_goff.reserve(c->goff.size()));
-  TSQ_CUDA(c, c->d_lin.reserve(c->lin.size()));
+  TSQ_CUDA(c, c->d_lin.reserve(c->lin_size));
   TSQ_CUDA(c, c->d_loff.reserve(c->loff.size()));
   TSQ_CUDA(c, c->d_lens.reserve(n + 1));
   TSQ_CUDA(c, c->d_perm.reserve(n + 1));
@@ -545,9 +562,9 @@ int tsq_upload(tsq_ctx* c) {
   TSQ_CUDA(c, c->d_prefix.reserve(c->task_prefix.size()));
   TSQ_CUDA(c, c->d_counter.reserve(4));
   TSQ_CUDA(c, c->d_sorted.reserve(npairs));
-  if (!c->dbw.empty()) TSQ_CUDA(c, cudaMemcpyAsync(c->d_dbw.p, c->dbw.data(), c->dbw.size() * 4, cudaMemcpyHostToDevice, s));
+  if (c->dbw_size) TSQ_CUDA(c, cudaMemcpyAsync(c->d_dbw.p, c->dbw.p, c->dbw_size * 4, cudaMemcpyHostToDevice, s));
   TSQ_CUDA(c, cudaMemcpyAsync(c->d_goff.p, c->goff.data(), c->goff.size() * 4, cudaMemcpyHostToDevice, s));
-  TSQ_CUDA(c, cudaMemcpyAsync(c->d_lin.p, c->lin.data(), c->lin.size(), cudaMemcpyHostToDevice, s));
+  TSQ_CUDA(c, cudaMemcpyAsync(c->d_lin.p, c->lin.p, c->lin_size, cudaMemcpyHostToDevice, s));
   TSQ_CUDA(c, cudaMemcpyAsync(c->d_loff.p, c->loff.data(), c->loff.size() * 4, cudaMemcpyHostToDevice, s));
   if (n) {
     TSQ_CUDA(c, cudaMemcpyAsync(c->d_lens.p, c->lens.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
@@ -560,6 +577,8 @@ int tsq_upload(tsq_ctx* c) {
   c->uploaded = true;
   c->computed = c->finalized = c->downloaded = false;
   c->st.upload_ms = now_ms() - t0;
+  c->st.h2d_bytes = c->dbw_size * 4 + c->lin_size + c->goff.size() * 4 + c->loff.size() * 4 + (uint64_t)n * 12 +
+                    sbias.size() * 4 + c->task_prefix.size() * 8;
   return TSQ_OK;
 }
 
@@ -696,6 +715,7 @@ int tsq_download(tsq_ctx* c) {
   if (rc != TSQ_OK) return rc;
   c->downloaded = c->finalized;
   c->st.download_ms = now_ms() - t0;
+  c->st.d2h_bytes = (npairs > 0 && c->finalized) ? npairs * (want_dist ? 12ull : 4ull) : 0ull;
   return TSQ_OK;
 }
 
@@ -776,6 +796,42 @@ int tsq_device_results(tsq_ctx* c, void** d_scores, void** d_dist, uint64_t* cou
   if (d_scores) *d_scores = c->identity ? (void*)c->d_sorted.p : (void*)c->d_scores.p;
   if (d_dist) *d_dist = (c->prm.flags & TSQ_FLAG_NO_DISTANCES) ? nullptr : (void*)c->d_dist.p;
   if (count) *count = c->n < 2 ? 0 : (uint64_t)c->n * (c->n - 1) / 2;
+  return TSQ_OK;
+}
+
+int tsq_plan_partition(const tsq_params* params, const uint32_t* lengths, uint32_t n, int32_t world,
+                       uint64_t* begins, uint64_t* ends) {
+  if (world < 1 || (n > 0 && !lengths) || !begins || !ends) return TSQ_ERR_INVALID;
+  tsq_ctx tmp;
+  tsq_params p;
+  tsq_default_params(&p);
+  if (params) {
+    if (params->struct_size < 8 || params->struct_size > sizeof(tsq_params)) return TSQ_ERR_INVALID;
+    memcpy(&p, params, params->struct_size);
+  }
+  const int nsym = p.alphabet == TSQ_NUCLEOTIDE ? 5 : 23;
+  const int8_t* m = p.matrix ? p.matrix : (p.alphabet == TSQ_NUCLEOTIDE ? kDna : kBlosum62);
+  tmp.go = p.gap_open < 0 ? (p.alphabet == TSQ_NUCLEOTIDE ? 10 : 11) : p.gap_open;
+  tmp.ge = p.gap_extend < 0 ? 1 : p.gap_extend;
+  tmp.smin = *std::min_element(m, m + nsym * nsym);
+  tmp.smax = *std::max_element(m, m + nsym * nsym);
+  tmp.delta = tmp.smin < 0 ? (-tmp.smin + 1) / 2 : 0;
+  const uint32_t max16 = (p.flags & TSQ_FLAG_FORCE_S32) ? 0 : max_len16_of(&tmp);
+  std::vector<uint32_t> lens(lengths, lengths + n);
+  std::stable_sort(lens.begin(), lens.end());
+  uint32_t lo = 0;
+  while (lo < n && lens[lo] == 0) lo++;
+  uint32_t hi = lo;
+  while (hi < n && lens[hi] <= max16) hi++;
+  std::vector<uint32_t> first_row;
+  plan_rows(lens, lo, hi, world, first_row);
+  const uint64_t npairs = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
+  auto start_of = [&](uint32_t row) -> uint64_t { return (n >= 2 && row + 1 < n) ? tri(row, row + 1, n) : npairs; };
+  for (int r = 0; r < world; r++) {
+    begins[r] = start_of(first_row[(size_t)r]);
+    ends[r] = start_of(first_row[(size_t)r + 1]);
+    if (begins[r] > ends[r]) begins[r] = ends[r];
+  }
   return TSQ_OK;
 }
 
