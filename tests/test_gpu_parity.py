@@ -266,3 +266,15 @@ def test_dpx_probe_reports_the_alu_rate():
     with t.Context() as ctx:
         ops, mhz = ctx.measure_dpx_rate()
     assert 50 < ops < 80 and 1000 < mhz < 2200
+
+
+@pytest.mark.parametrize("K", [32, 36, 40, 44, 48, 50, 52, 56])
+def test_every_strip_width_variant(K, monkeypatch):
+    """Each instantiated kernel variant (strip width K), odd and even row counts, both gap-model
+    specialisations (immediate -ge' for the defaults, runtime for the rest)."""
+    monkeypatch.setenv("TSQ_FORCE_K", str(K))
+    rng = np.random.default_rng(K)
+    seqs = ragged(rng, 70, 1, 3 * K + 7, AA[:20]) + ragged(rng, 6, K, K + 1) + ragged(rng, 6, 2 * K - 1, 2 * K)
+    st, _ = assert_same(seqs)
+    assert st["strip_width"] == K
+    assert_same(seqs, 0, 7, 3)

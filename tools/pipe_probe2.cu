@@ -1,0 +1,83 @@
+// pipe_probe2.cu -- which operand forms let the Gotoh cell mix (3 DPX + 2 adds + 1 LDS) issue fastest.
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+constexpr int NCH = 8, ITER = 4096;
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d; asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+__device__ __forceinline__ uint32_t opaque(uint32_t a) { uint32_t d; asm volatile("mov.u32 %0, %1;" : "=r"(d) : "r"(a)); return d; }
+
+template <int V>
+__global__ void __launch_bounds__(1024, 1) probe(uint32_t* out, const uint32_t k1, const uint32_t k2, uint32_t one, long long* cyc, int nw) {
+  __shared__ uint32_t sm[2048];
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) sm[i] = i & 15;
+  __syncthreads();
+  uint32_t a[NCH], b[NCH], h[NCH];
+#pragma unroll
+  for (int i = 0; i < NCH; i++) { a[i] = 0x40004000u + threadIdx.x * 7 + i; b[i] = 0x40004000u + threadIdx.x * 3 + i * 5; h[i] = 0x40004000u + i; }
+  const uint32_t* sp = sm + (threadIdx.x & 31);
+  const uint32_t goe_r = opaque(k1);      // vector-register copy of a parameter
+  const uint32_t nge_r = opaque(k2);
+  long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < ITER; it++) {
+    const uint32_t* row = sp + (it & 7) * 64;
+#pragma unroll
+    for (int i = 0; i < NCH; i++) {
+      uint32_t s = row[i * 33];
+      uint32_t t = h[i] + s;
+      uint32_t hh, hg;
+      if (V == 0) {        // all register operands, forced IMAD for hg
+        hh = __vimax3_u16x2(t, a[i], b[i]); hg = imad(hh, one, goe_r);
+        a[i] = __viaddmax_u16x2(a[i], nge_r, hg); b[i] = __viaddmax_u16x2(b[i], nge_r, hg);
+      } else if (V == 1) { // immediates for -ge', hg = hh - imm
+        hh = __vimax3_u16x2(t, a[i], b[i]); hg = hh - 0x000a000au;
+        a[i] = __viaddmax_u16x2(a[i], 0x00010001u, hg); b[i] = __viaddmax_u16x2(b[i], 0x00010001u, hg);
+      } else if (V == 2) { // immediates for -ge', hg = hh - vector register
+        hh = __vimax3_u16x2(t, a[i], b[i]); hg = hh - goe_r;
+        a[i] = __viaddmax_u16x2(a[i], 0x00010001u, hg); b[i] = __viaddmax_u16x2(b[i], 0x00010001u, hg);
+      } else if (V == 3) { // immediates for -ge', hg via forced IMAD
+        hh = __vimax3_u16x2(t, a[i], b[i]); hg = imad(hh, one, goe_r);
+        a[i] = __viaddmax_u16x2(a[i], 0x00010001u, hg); b[i] = __viaddmax_u16x2(b[i], 0x00010001u, hg);
+      } else if (V == 4) { // register -ge' (param), hg = hh - param (uniform)
+        hh = __vimax3_u16x2(t, a[i], b[i]); hg = hh - k1;
+        a[i] = __viaddmax_u16x2(a[i], k2, hg); b[i] = __viaddmax_u16x2(b[i], k2, hg);
+      } else {             // 5: no LDS, immediates, hg = hh - vector register
+        t = h[i] + k2;
+        hh = __vimax3_u16x2(t, a[i], b[i]); hg = hh - goe_r;
+        a[i] = __viaddmax_u16x2(a[i], 0x00010001u, hg); b[i] = __viaddmax_u16x2(b[i], 0x00010001u, hg);
+      }
+      h[i] = hh;
+    }
+  }
+  long long t1 = clock64();
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < NCH; i++) r ^= a[i] ^ b[i] ^ h[i];
+  if (r == 0x12345678u) out[threadIdx.x] = r;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+template <int V> void run(const char* name, int threads, int nsm, uint32_t* out, long long* dcyc) {
+  probe<V><<<nsm, threads>>>(out, 0x000a000a, 0x00010001, 1, dcyc, 0);
+  cudaDeviceSynchronize();
+  probe<V><<<nsm, threads>>>(out, 0x000a000a, 0x00010001, 1, dcyc, 0);
+  cudaDeviceSynchronize();
+  static long long h[1024];
+  cudaMemcpy(h, dcyc, sizeof(long long) * nsm, cudaMemcpyDeviceToHost);
+  double avg = 0; for (int i = 0; i < nsm; i++) avg += h[i]; avg /= nsm;
+  printf("{\"variant\": \"%s\", \"threads_per_sm\": %d, \"packed_cells_per_clk_per_sm\": %.2f}\n", name, threads, (double)threads * NCH * ITER / avg);
+}
+int main() {
+  cudaDeviceProp p; cudaGetDeviceProperties(&p, 0); int nsm = p.multiProcessorCount;
+  uint32_t* out; long long* dcyc; cudaMalloc(&out, 4096 * 4); cudaMalloc(&dcyc, 1024 * 8);
+  for (int threads : {1024, 512, 384, 256}) {
+    run<0>("V0 regs + forced IMAD", threads, nsm, out, dcyc);
+    run<1>("V1 imm ge, hg=h-imm", threads, nsm, out, dcyc);
+    run<2>("V2 imm ge, hg=h-vreg", threads, nsm, out, dcyc);
+    run<3>("V3 imm ge, forced IMAD", threads, nsm, out, dcyc);
+    run<4>("V4 param ge, hg=h-param", threads, nsm, out, dcyc);
+    run<5>("V5 no LDS, imm ge, hg=h-vreg", threads, nsm, out, dcyc);
+  }
+  return 0;
+}

@@ -19,11 +19,11 @@
 //   * values are stored biased and skewed:  v~(i,j) = v(i,j) + delta*(i+j) + BIAS, as
 //     unsigned 16-bit.  delta = ceil(-min(S)/2) makes every substitution score S' = S+2*delta
 //     non-negative, so "H_diag + S" and "H - (go+ge)" are plain 32-bit adds of two packed
-//     halves with no carry between halves -> they run on the FMA pipe (IMAD.IADD), leaving
-//     3 DPX instructions per packed cell on the ALU pipe:
-//         t  = hd + S'                      (FMA pipe)
+//     halves with no carry between halves -> ptxas is free to place them on either integer
+//     pipe (IMAD.IADD / VIADD), leaving 3 DPX instructions per packed cell:
+//         t  = hd + S'                      (plain add)
 //         h  = vimax3(t, E, F)              (ALU, DPX)
-//         hg = h - goe'                     (FMA pipe)
+//         hg = h - goe'                     (plain add)
 //         E  = viaddmax(E, -ge', hg)        (ALU, DPX)
 //         F  = viaddmax(F, -ge', hg)        (ALU, DPX)
 //     with ge' = ge - delta, goe' = go + ge - delta.
@@ -73,7 +73,9 @@ struct G16Cfg {
   static constexpr int STRIDE = ((K + 31) & ~31) + 1;  // == 1 (mod 32)
 };
 
-template <int K, int TPB, int MINB>
+// NGE != 0: -ge' (both halves) is the compile-time constant NGE, so the two VIADDMNMX of a cell
+// take it as an immediate (one register read less each); NGE == 0: taken from the parameters.
+template <int K, int TPB, int MINB, uint32_t NGE>
 __global__ void __launch_bounds__(TPB, MINB) gotoh16_kernel(const __grid_constant__ G16Params p) {
   constexpr int STRIDE = G16Cfg<K>::STRIDE;
   extern __shared__ uint32_t smem[];
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(TPB, MINB) gotoh16_kernel(const __grid_constan
 
   const uint32_t gw = blockIdx.x * (TPB / 32) + wib;
   uint2* const bnd = p.bnd + (size_t)gw * p.bnd_rows * 32 + lane;
-  const uint32_t negge2 = p.negge2;
+  const uint32_t nge = NGE ? NGE : p.negge2;
   const uint32_t goe2 = p.goe2;
   const int32_t gep = p.gep;
 
@@ -152,41 +154,104 @@ __global__ void __launch_bounds__(TPB, MINB) gotoh16_kernel(const __grid_constan
       const bool first = (s == 0);
       const bool last = (s + 1 == nstrips);
 
-      uint32_t w = 0;
+      // subject letters: one 32-bit word (4 residues) per lane per 4 rows, fetched a word ahead
+      uint32_t w = 0, nread = 0;
       uint32_t wn = valid ? __ldg(dbp) : 0u;
-      uint2 bn = make_uint2(0u, 0u);
-      if (!first && Ls > 0) bn = bnd[32];
-
-      for (uint32_t i = 1; i <= Ls; ++i) {
-        if (((i - 1) & 3u) == 0u) {
+      auto next_letter = [&]() -> uint32_t {
+        if ((nread & 3u) == 0u) {
           w = wn;
-          wn = __ldg(dbp + (((i - 1) >> 2) + 1) * 32);
+          wn = __ldg(dbp + ((nread >> 2) + 1) * 32);
         }
         const uint32_t b = w & 0xffu;
         w >>= 8;
-        const uint32_t* prow = prof + b * STRIDE;
-        uint32_t Hl, E;
-        if (first) {
-          Hl = (uint32_t)(hl0 - (int32_t)i * gep) * 0x10001u;
-          E = Hl - goe2;
-        } else {
-          Hl = bn.x;
-          E = bn.y;
-          bn = bnd[(size_t)(i + 1) * 32];
-        }
-        uint32_t hd = hdiag;
-        hdiag = Hl;
+        ++nread;
+        return b;
+      };
+      // left boundary (H~(i, j0), E entering column j0+1) of row i
+      auto left_formula = [&](uint32_t i) -> uint2 {
+        const uint32_t hl = (uint32_t)(hl0 - (int32_t)i * gep) * 0x10001u;
+        return make_uint2(hl, hl - goe2);
+      };
+
+      uint32_t i = 1;
+      // ---- odd row count: row 1 alone, so that the main loop can take rows two at a time ----
+      if (Ls & 1u) {
+        const uint32_t* prow = prof + next_letter() * STRIDE;
+        const uint2 lb = first ? left_formula(1) : bnd[32];
+        uint32_t E = lb.y;
+        uint32_t t = hdiag + prow[0];
+        hdiag = lb.x;
 #pragma unroll
         for (int c = 0; c < K; ++c) {
-          const uint32_t t = hd + prow[c];
-          hd = H[c];
+          uint32_t tn = 0;
+          if (c + 1 < K) tn = H[c] + prow[c + 1];
           const uint32_t h = __vimax3_u16x2(t, E, F[c]);
           H[c] = h;
           const uint32_t hg = h - goe2;
-          E = __viaddmax_u16x2(E, negge2, hg);
-          F[c] = __viaddmax_u16x2(F[c], negge2, hg);
+          E = __viaddmax_u16x2(E, nge, hg);
+          F[c] = __viaddmax_u16x2(F[c], nge, hg);
+          t = tn;
         }
-        if (!last) bnd[(size_t)i * 32] = make_uint2(H[K - 1], E);
+        if (!last) bnd[32] = make_uint2(H[K - 1], E);
+        i = 2;
+      }
+
+      // ---- main loop: rows i (A) and i+1 (B) together, B one column behind A --------------------
+      // Two independent E chains per lane double the instruction-level parallelism: the
+      // 3-instruction dependent chain of one cell (VIMNMX3 -> add -> VIADDMNMX, ~14 clk) is
+      // overlapped with the other row's.  t = H_diag + S' is formed one column ahead, from the
+      // old H value before the cell overwrites it, so no register copy carries the diagonal.
+      uint2 na = make_uint2(0u, 0u), nb = make_uint2(0u, 0u);
+      if (!first && i < Ls) {
+        na = bnd[(size_t)i * 32];
+        nb = bnd[(size_t)(i + 1) * 32];
+      }
+      for (; i < Ls; i += 2) {
+        const uint32_t* prow_a = prof + next_letter() * STRIDE;
+        const uint32_t* prow_b = prof + next_letter() * STRIDE;
+        uint2 la, lb;
+        if (first) {
+          la = left_formula(i);
+          lb = left_formula(i + 1);
+        } else {
+          la = na;
+          lb = nb;
+          na = bnd[(size_t)(i + 2) * 32];   // rows of the next iteration (scratch has slack rows)
+          nb = bnd[(size_t)(i + 3) * 32];
+        }
+        uint32_t Ea = la.y, Eb = lb.y;
+        uint32_t ta = hdiag + prow_a[0];      // diag of A(0) = H(i-1, j0)
+        uint32_t tb = la.x + prow_b[0];       // diag of B(0) = H(i,   j0)
+        hdiag = lb.x;                         // H(i+1, j0) for the next pair
+        uint32_t ha_last = 0;
+#pragma unroll
+        for (int c = 0; c <= K; ++c) {
+          if (c < K) {  // cell A(c) of row i
+            uint32_t tn = 0;
+            if (c + 1 < K) tn = H[c] + prow_a[c + 1];
+            const uint32_t h = __vimax3_u16x2(ta, Ea, F[c]);
+            H[c] = h;
+            const uint32_t hg = h - goe2;
+            Ea = __viaddmax_u16x2(Ea, nge, hg);
+            F[c] = __viaddmax_u16x2(F[c], nge, hg);
+            ta = tn;
+            if (c == K - 1) ha_last = h;
+          }
+          if (c >= 1) {  // cell B(c-1) of row i+1
+            uint32_t tn = 0;
+            if (c < K) tn = H[c - 1] + prow_b[c];   // H(i, c-1), before B overwrites it
+            const uint32_t h = __vimax3_u16x2(tb, Eb, F[c - 1]);
+            H[c - 1] = h;
+            const uint32_t hg = h - goe2;
+            Eb = __viaddmax_u16x2(Eb, nge, hg);
+            F[c - 1] = __viaddmax_u16x2(F[c - 1], nge, hg);
+            tb = tn;
+          }
+        }
+        if (!last) {
+          bnd[(size_t)i * 32] = make_uint2(ha_last, Ea);
+          bnd[(size_t)(i + 1) * 32] = make_uint2(H[K - 1], Eb);
+        }
       }
 
       // ---- pick H(Ls, L1) / H(Ls, L2) if the query ends inside this strip --------------

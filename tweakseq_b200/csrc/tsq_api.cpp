@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <fstream>
 #include <numeric>
 #include <string>
@@ -522,25 +523,30 @@ int tsq_upload(tsq_ctx* c) {
   }
   c->cells32 = 0;
 
-  // ---- strip width: least padded columns over the instantiated variants ---------------------
+  // ---- strip width: least estimated work over the instantiated variants -----------------------
+  // A strip of K columns costs about K + 2.5 cell-times per row (the row's letter fetch, boundary
+  // load/store and loop control are worth ~2.5 cells: profiles/ r01 sweep), padding included.
   {
-    uint64_t best = ~0ull;
+    double best = 1e300;
     int bestK = tsq::kStripWidths[0];
     for (int v = 0; v < tsq::kNumStripWidths; v++) {
       const int K = tsq::kStripWidths[v];
-      uint64_t padded = 0;
+      double work = 0;
       for (uint32_t r = 0; r < nq; r++) {
         const uint32_t q = c->q_end - 1 - r;
         const uint32_t l2 = c->lens[lo + 2 * q + 1];
-        const uint64_t cols = (uint64_t)((l2 + K - 1) / K) * K + 2;  // +2: per-strip overhead proxy
-        padded += cols * (c->task_prefix[r + 1] - c->task_prefix[r]);
+        work += (double)((l2 + K - 1) / K) * (K + 2.5) * (double)(c->task_prefix[r + 1] - c->task_prefix[r]);
       }
-      if (padded < best || (padded == best && K > bestK)) {
-        best = padded;
+      if (work < best * 0.999 || (work <= best * 1.001 && K > bestK)) {
+        if (work < best) best = work;
         bestK = K;
       }
     }
     c->K = bestK;
+    if (const char* fk = getenv("TSQ_FORCE_K")) {  // developer override for tuning runs
+      tsq::G16Launch v;
+      if (tsq::g16_variant(atoi(fk), (uint32_t)c->nsym, &v)) c->K = atoi(fk);
+    }
   }
 
   // ---- biased score table -----------------------------------------------------------------
@@ -599,7 +605,7 @@ int tsq_compute(tsq_ctx* c) {
     const unsigned long long need = (ntasks + warps_per_cta - 1) / warps_per_cta;
     if ((unsigned long long)grid > need) grid = (int)need;
     const uint32_t maxlen = c->hi > c->lo ? c->lens[c->hi - 1] : 0;
-    const uint32_t bnd_rows = maxlen + 4;
+    const uint32_t bnd_rows = maxlen + 8;  // the row loop prefetches up to 3 rows past the end
     TSQ_CUDA(c, c->d_bnd.reserve((size_t)grid * warps_per_cta * bnd_rows * 32));
     TSQ_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), s));
     const uint32_t lpad = ((maxlen + c->K - 1) / c->K) * c->K;

@@ -9,11 +9,15 @@ namespace tsq {
 // (K, threads per CTA, CTAs per SM).  Register budget = 65536 / (tpb * ctas_sm).
 #define TSQ_G16_VARIANTS(X) \
   X(32, 128, 4)             \
+  X(36, 128, 3)             \
   X(40, 128, 3)             \
+  X(44, 128, 3)             \
+  X(48, 128, 3)             \
   X(50, 128, 3)             \
-  X(60, 128, 2)
+  X(52, 128, 3)             \
+  X(56, 128, 3)
 
-const int kStripWidths[kNumStripWidths] = {32, 40, 50, 60};
+const int kStripWidths[kNumStripWidths] = {32, 36, 40, 44, 48, 50, 52, 56};
 
 bool g16_variant(int K, uint32_t nsym, G16Launch* out) {
 #define X(KK, TT, MM)                                                                     \
@@ -37,7 +41,10 @@ cudaError_t g16_launch(int K, int grid, const G16Params& p, cudaStream_t stream)
   if (!g16_variant(K, p.nsym, &v)) return cudaErrorInvalidValue;
 #define X(KK, TT, MM)                                                                          \
   if (K == KK) {                                                                               \
-    auto kern = gotoh16_kernel<KK, TT, MM>;                                                    \
+    /* -ge' == +1 in both halves (ge = 1, delta = 2: the protein and nucleotide defaults) gets */ \
+    /* the immediate-operand specialisation; every other gap model the generic kernel.        */ \
+    auto kern = p.negge2 == 0x00010001u ? gotoh16_kernel<KK, TT, MM, 0x00010001u>              \
+                                        : gotoh16_kernel<KK, TT, MM, 0u>;                      \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                          (int)v.smem);                                         \
     if (e != cudaSuccess) return e;                                                            \

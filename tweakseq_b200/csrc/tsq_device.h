@@ -8,7 +8,7 @@
 namespace tsq {
 
 // Strip widths the packed 16-bit kernel is instantiated for.
-constexpr int kNumStripWidths = 4;
+constexpr int kNumStripWidths = 8;
 extern const int kStripWidths[kNumStripWidths];
 
 struct G16Launch {
