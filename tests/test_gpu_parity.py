@@ -278,3 +278,56 @@ def test_every_strip_width_variant(K, monkeypatch):
     st, _ = assert_same(seqs)
     assert st["strip_width"] == K
     assert_same(seqs, 0, 7, 3)
+
+
+# ---- regime 2: the 32-bit anti-diagonal wavefront kernel -------------------------------------
+def test_force_s32_protein_ragged_matches_oracle():
+    rng = np.random.default_rng(90)
+    seqs = ragged(rng, 48, 0, 420) + ["W", "AC", "ACD"]
+    st, cells = assert_same(seqs, flags=t.FLAG_FORCE_S32)
+    assert st["cells_s32"] == cells and st["cells_s16"] == 0
+    assert_same(seqs, 0, 3, 2, flags=t.FLAG_FORCE_S32)
+
+
+def test_force_s32_nucleotide_ragged_matches_oracle():
+    rng = np.random.default_rng(91)
+    seqs = ragged(rng, 40, 1, 2600, "ACGT") + ragged(rng, 6, 1020, 1030, "ACGTN") + ["A", "ACGTACGT"]
+    assert_same(seqs, alphabet=1, flags=t.FLAG_FORCE_S32)
+    assert_same(seqs[:20], alphabet=1, go=0, ge=2, flags=t.FLAG_FORCE_S32)
+
+
+def test_long_nucleotide_sequences_use_both_kernels():
+    rng = np.random.default_rng(92)
+    seqs = (ragged(rng, 24, 10, 400, "ACGT") + ragged(rng, 5, 7300, 9500, "ACGT") + ragged(rng, 2, 12000, 12600, "ACGT")
+            + [""])
+    fam = synth.nucleotide(3, 8000, 9000, 4, family=True)
+    st, cells = assert_same(seqs + fam, alphabet=1)
+    assert st["cells_s16"] > 0 and st["cells_s32"] > 0 and st["cells_s16"] + st["cells_s32"] == cells
+
+
+def test_long_protein_beyond_the_16_bit_range():
+    rng = np.random.default_rng(93)
+    seqs = ragged(rng, 10, 50, 300, AA[:20]) + ragged(rng, 2, 4700, 5200, AA[:20])
+    st, _ = assert_same(seqs)
+    assert st["cells_s32"] > 0
+
+
+def test_partition_slabs_with_wavefront_rows():
+    rng = np.random.default_rng(94)
+    seqs = ragged(rng, 30, 20, 200, "ACGT") + ragged(rng, 6, 7300, 8000, "ACGT")
+    full, _, _, _ = gpu_run(seqs, alphabet=1, flags=t.FLAG_NO_DISTANCES)
+    import torch
+    world, ctxs, bufs, ranges = 2, [], [], []
+    for r in range(world):
+        ctx = t.Context(alphabet=1, part_rank=r, part_world=world, flags=t.FLAG_NO_DISTANCES)
+        ctx.set_sequences(seqs); ctx.upload(); ctx.compute(); ctx.synchronize()
+        ranges.append(ctx.partition()); bufs.append(torch.as_tensor(ctx.device_scores(), device="cuda")); ctxs.append(ctx)
+    assert ranges == capi.plan_partition([len(s) for s in seqs], world, alphabet=1)
+    b, e = ranges[1]
+    bufs[0][b:e] = bufs[1][b:e]
+    ctxs[0].finalize(); ctxs[0].download()
+    assert (ctxs[0].scores() == full).all()
+    rs, _, _, _ = oracle_run(seqs, 1)
+    assert (full == rs).all()
+    for c in ctxs:
+        c.close()

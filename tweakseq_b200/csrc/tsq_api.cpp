@@ -136,6 +136,7 @@ struct tsq_ctx {
   uint32_t row_a = 0, row_b = 0;  // this partition's sorted rows
   uint64_t part_begin = 0, part_end = 0;
   std::vector<unsigned long long> task_prefix;
+  std::vector<uint2> pairs32;             // tasks of the 32-bit wavefront kernel (sorted indices)
   uint32_t q_begin = 0, q_end = 0;
   int K = 0;
   uint64_t cells16 = 0, cells32 = 0, pairs_part = 0;
@@ -147,6 +148,9 @@ struct tsq_ctx {
   DevBuf<double> d_dist;
   DevBuf<unsigned long long> d_prefix, d_counter;
   DevBuf<uint2> d_bnd;
+  DevBuf<uint2> d_pairs32;
+  DevBuf<int2> d_bnd32;
+  DevBuf<int32_t> d_smat;
   // host results
   PinnedBuf<int32_t> h_scores;
   PinnedBuf<double> h_dist;
@@ -377,7 +381,7 @@ int tsq_destroy(tsq_ctx* c) {
   c->d_perm.release(); c->d_sbias.release(); c->d_lin.release(); c->d_self.release();
   c->d_sorted.release(); c->d_scores.release(); c->d_dist.release(); c->d_prefix.release();
   c->d_counter.release(); c->d_bnd.release(); c->h_scores.release(); c->h_dist.release();
-  c->lin.release(); c->dbw.release();
+  c->lin.release(); c->dbw.release(); c->d_pairs32.release(); c->d_bnd32.release(); c->d_smat.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -456,7 +460,11 @@ int tsq_upload(tsq_ctx* c) {
   if (c->identity && lo > 0) c->identity = false;  // empties are filled in by finalize
   c->lo = lo;
   c->hi = hi;
-  if (hi < n) return fail(c, TSQ_ERR_RANGE, "sequence of length %u needs the 32-bit wavefront kernel (not built yet)", c->lens[n - 1]);
+  if (n > 0) {  // 32-bit range: |H| <= (m+n) * max|score or ge| + 2*go must stay far inside int32
+    const int64_t unit = std::max<int64_t>(std::max(std::abs(c->smin), std::abs(c->smax)), c->ge);
+    if (2 * (int64_t)c->lens[n - 1] * unit + 2 * (int64_t)c->go >= (1ll << 30))
+      return fail(c, TSQ_ERR_RANGE, "sequence of length %u: scores would not fit 32 bits", c->lens[n - 1]);
+  }
 
   // ---- 32-way interleaved subject database (4 residues per word) ---------------------------
   const uint32_t ngroups = (n + 31) / 32;
@@ -521,7 +529,20 @@ int tsq_upload(tsq_ctx* c) {
       c->pairs_part += (uint64_t)(hi - a1 - 1) + (hi - a1 - 2);
     }
   }
+  // ---- tasks of the 32-bit wavefront kernel: every pair with a sequence beyond the packed range,
+  //      restricted to this rank's rows, biggest pairs first -------------------------------------
   c->cells32 = 0;
+  c->pairs32.clear();
+  if (hi < n) {
+    const uint32_t ra = std::max(c->row_a, lo);
+    for (uint32_t i = c->row_b; i-- > ra;) {
+      for (uint32_t j = n; j-- > std::max(i + 1, hi);) {
+        c->pairs32.push_back(make_uint2(i, j));
+        c->cells32 += (uint64_t)c->lens[i] * c->lens[j];
+      }
+    }
+    c->pairs_part += c->pairs32.size();
+  }
 
   // ---- strip width: least estimated work over the instantiated variants -----------------------
   // A strip of K columns costs about K + 2.5 cell-times per row (the row's letter fetch, boundary
@@ -579,6 +600,16 @@ int tsq_upload(tsq_ctx* c) {
   }
   TSQ_CUDA(c, cudaMemcpyAsync(c->d_sbias.p, sbias.data(), sbias.size() * 4, cudaMemcpyHostToDevice, s));
   TSQ_CUDA(c, cudaMemcpyAsync(c->d_prefix.p, c->task_prefix.data(), c->task_prefix.size() * 8, cudaMemcpyHostToDevice, s));
+  if (!c->pairs32.empty()) {
+    std::vector<int32_t> smat((size_t)(nsym + 1) * nsym, 0);
+    for (uint32_t a = 0; a < nsym; a++)
+      for (uint32_t b = 0; b < nsym; b++) smat[a * nsym + b] = c->matrix[a * nsym + b];
+    TSQ_CUDA(c, c->d_smat.reserve(smat.size()));
+    TSQ_CUDA(c, c->d_pairs32.reserve(c->pairs32.size()));
+    TSQ_CUDA(c, cudaMemcpyAsync(c->d_smat.p, smat.data(), smat.size() * 4, cudaMemcpyHostToDevice, s));
+    TSQ_CUDA(c, cudaMemcpyAsync(c->d_pairs32.p, c->pairs32.data(), c->pairs32.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
+    TSQ_CUDA(c, cudaStreamSynchronize(s));  // smat is a local
+  }
   TSQ_CUDA(c, cudaStreamSynchronize(s));
   c->uploaded = true;
   c->computed = c->finalized = c->downloaded = false;
@@ -636,6 +667,34 @@ int tsq_compute(tsq_ctx* c) {
     p.goe2 = (uint32_t)(c->go + c->ge - c->delta) * 0x10001u;
     if (!fits16(c, lpad)) return fail(c, TSQ_ERR_RANGE, "internal: padded length %u outside the 16-bit bound", lpad);
     TSQ_CUDA(c, tsq::g16_launch(c->K, grid, p, s));
+    launches++;
+  }
+  if (!c->pairs32.empty()) {
+    tsq::W32Launch v;
+    if (!tsq::w32_variant((uint32_t)c->nsym, &v)) return fail(c, TSQ_ERR_INVALID, "no wavefront kernel variant");
+    const int warps_per_cta = v.tpb / 32;
+    int grid = c->sm_count * v.ctas_sm;
+    const unsigned long long need = (c->pairs32.size() + warps_per_cta - 1) / warps_per_cta;
+    if ((unsigned long long)grid > need) grid = (int)need;
+    const uint32_t bnd_rows = c->lens[c->n - 1] + 8;
+    TSQ_CUDA(c, c->d_bnd32.reserve((size_t)grid * warps_per_cta * bnd_rows));
+    TSQ_CUDA(c, cudaMemsetAsync(c->d_counter.p + 1, 0, sizeof(unsigned long long), s));
+    tsq::W32Params w{};
+    w.lin = c->d_lin.p;
+    w.loff = c->d_loff.p;
+    w.lens = c->d_lens.p;
+    w.pairs = c->d_pairs32.p;
+    w.counter = c->d_counter.p + 1;
+    w.bnd = c->d_bnd32.p;
+    w.smat = c->d_smat.p;
+    w.out = c->d_sorted.p;
+    w.ntasks = c->pairs32.size();
+    w.bnd_rows = bnd_rows;
+    w.n_total = c->n;
+    w.nsym = (uint32_t)c->nsym;
+    w.go = c->go;
+    w.ge = c->ge;
+    TSQ_CUDA(c, tsq::w32_launch(grid, w, s));
     launches++;
   }
   TSQ_CUDA(c, cudaEventRecord(c->ev1, s));

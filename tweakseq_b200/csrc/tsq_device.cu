@@ -56,6 +56,39 @@ cudaError_t g16_launch(int K, int grid, const G16Params& p, cudaStream_t stream)
   return cudaErrorInvalidValue;
 }
 
+// ---- 32-bit wavefront kernel ----------------------------------------------------------------
+// nucleotides (5 symbols): 32 columns per lane, 1024 per pass, 20 KB of profile per warp;
+// proteins (23 symbols): 8 columns per lane, 256 per pass, 23.5 KB of profile per warp.
+bool w32_variant(uint32_t nsym, W32Launch* out) {
+  if (nsym == 0 || nsym > 24) return false;
+  W32Launch v;
+  v.KW = nsym <= 8 ? 32 : 8;
+  v.tpb = 128;
+  v.ctas_sm = 2;
+  const size_t sbsz = ((size_t)(nsym + 1) * nsym + 31) & ~(size_t)31;
+  v.smem = (sbsz + (size_t)(v.tpb / 32) * nsym * 32 * v.KW) * sizeof(int32_t);
+  if (out) *out = v;
+  return true;
+}
+
+cudaError_t w32_launch(int grid, const W32Params& p, cudaStream_t stream) {
+  W32Launch v;
+  if (!w32_variant(p.nsym, &v)) return cudaErrorInvalidValue;
+  cudaError_t e;
+  if (v.KW == 32) {
+    auto kern = wave32_kernel<32, 128, 2>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, v.tpb, v.smem, stream>>>(p);
+  } else {
+    auto kern = wave32_kernel<8, 128, 2>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, v.tpb, v.smem, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
 // ---- finalize: empties, un-sort, fp64 distances -----------------------------------------
 // One CTA per sorted row i; threads stride over j > i.  Distances follow the oracle's
 // tsq_oracle_distance(): two separately rounded IEEE operations (div, sub), no contraction.

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "gotoh16.cuh"
+#include "wave32.cuh"
 
 namespace tsq {
 
@@ -22,6 +23,15 @@ struct G16Launch {
 bool g16_variant(int K, uint32_t nsym, G16Launch* out);
 // Launch the packed 16-bit kernel: grid CTAs of the variant's size on `stream`.
 cudaError_t g16_launch(int K, int grid, const G16Params& p, cudaStream_t stream);
+
+// 32-bit wavefront kernel: columns per lane (KW) is chosen from the alphabet size so that the
+// per-warp profile fits shared memory; *warps_per_cta / *ctas_sm describe the launch shape.
+struct W32Launch {
+  int KW, tpb, ctas_sm;
+  size_t smem;
+};
+bool w32_variant(uint32_t nsym, W32Launch* out);
+cudaError_t w32_launch(int grid, const W32Params& p, cudaStream_t stream);
 
 struct FinalizeParams {
   const int32_t* sorted;      // packed triangle, sorted order
