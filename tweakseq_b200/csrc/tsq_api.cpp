@@ -694,6 +694,7 @@ int tsq_compute(tsq_ctx* c) {
     w.nsym = (uint32_t)c->nsym;
     w.go = c->go;
     w.ge = c->ge;
+    w.one = 1;
     TSQ_CUDA(c, tsq::w32_launch(grid, w, s));
     launches++;
   }

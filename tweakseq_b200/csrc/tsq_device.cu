@@ -2,6 +2,7 @@
 #include "tsq_device.h"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace tsq {
 
@@ -57,14 +58,31 @@ cudaError_t g16_launch(int K, int grid, const G16Params& p, cudaStream_t stream)
 }
 
 // ---- 32-bit wavefront kernel ----------------------------------------------------------------
-// nucleotides (5 symbols): 32 columns per lane, 1024 per pass, 20 KB of profile per warp;
-// proteins (23 symbols): 8 columns per lane, 256 per pass, 23.5 KB of profile per warp.
+// nucleotides (5 symbols): 24 columns per lane, 768 per pass, 15 KB of profile per warp, 12 warps/SM;
+// proteins (23 symbols): 8 columns per lane, 256 per pass, 23.5 KB of profile per warp, 8 warps/SM.
+#define TSQ_W32_VARIANTS(X) \
+  X(32, 128, 2)             \
+  X(24, 128, 3)             \
+  X(16, 128, 4)             \
+  X(16, 128, 3)             \
+  X(8, 128, 4)              \
+  X(8, 128, 2)
+
 bool w32_variant(uint32_t nsym, W32Launch* out) {
   if (nsym == 0 || nsym > 24) return false;
   W32Launch v;
-  v.KW = nsym <= 8 ? 32 : 8;
+  // r01 sweep on 150 x 10-30 kb (profiles/): KW,CTAs = 24,3 -> 3728 GCUPS; 32,2 -> 3425; 16,4 -> 3267
+  v.KW = nsym <= 8 ? 24 : 8;
   v.tpb = 128;
-  v.ctas_sm = 2;
+  v.ctas_sm = nsym <= 8 ? 3 : 2;
+  if (const char* e = getenv("TSQ_FORCE_KW")) {  // developer override for tuning runs: "KW,ctas"
+    int kw = 0, ct = 0;
+    if (sscanf(e, "%d,%d", &kw, &ct) == 2) {
+#define X(KK, TT, MM) if (kw == KK && ct == MM) { v.KW = KK; v.ctas_sm = MM; }
+      TSQ_W32_VARIANTS(X)
+#undef X
+    }
+  }
   const size_t sbsz = ((size_t)(nsym + 1) * nsym + 31) & ~(size_t)31;
   v.smem = (sbsz + (size_t)(v.tpb / 32) * nsym * 32 * v.KW) * sizeof(int32_t);
   if (out) *out = v;
@@ -74,19 +92,18 @@ bool w32_variant(uint32_t nsym, W32Launch* out) {
 cudaError_t w32_launch(int grid, const W32Params& p, cudaStream_t stream) {
   W32Launch v;
   if (!w32_variant(p.nsym, &v)) return cudaErrorInvalidValue;
-  cudaError_t e;
-  if (v.KW == 32) {
-    auto kern = wave32_kernel<32, 128, 2>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, v.tpb, v.smem, stream>>>(p);
-  } else {
-    auto kern = wave32_kernel<8, 128, 2>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, v.tpb, v.smem, stream>>>(p);
+#define X(KK, TT, MM)                                                                        \
+  if (v.KW == KK && v.ctas_sm == MM) {                                                       \
+    auto kern = wave32_kernel<KK, TT, MM>;                                                   \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                         (int)v.smem);                                       \
+    if (e != cudaSuccess) return e;                                                          \
+    kern<<<grid, TT, v.smem, stream>>>(p);                                                   \
+    return cudaGetLastError();                                                               \
   }
-  return cudaGetLastError();
+  TSQ_W32_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
 }
 
 // ---- finalize: empties, un-sort, fp64 distances -----------------------------------------

@@ -40,7 +40,17 @@ struct W32Params {
   uint32_t n_total;
   uint32_t nsym;
   int32_t go, ge;
+  int32_t one;                 // 1, opaque to the compiler (see add_fma_pipe)
 };
+
+// a*one + b with `one` an opaque 1: forces IMAD (FMA pipe) for the diagonal add.  Left to itself
+// ptxas fuses that add into the DPX instruction (VIADDMNMX + VIMNMX instead of VIMNMX3), which
+// puts five ALU-pipe instructions in a cell; this way it is four (r01 profile: ALU pipe 73 %).
+__device__ __forceinline__ int32_t add_fma_pipe(int32_t a, int32_t one, int32_t b) {
+  int32_t d;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+  return d;
+}
 
 template <int KW, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) wave32_kernel(const __grid_constant__ W32Params p) {
@@ -58,6 +68,7 @@ __global__ void __launch_bounds__(TPB, MINB) wave32_kernel(const __grid_constant
   const uint32_t gw = blockIdx.x * (TPB / 32) + wib;
   int2* const bnd = p.bnd + (size_t)gw * p.bnd_rows;
   const int32_t go = p.go, ge = p.ge, goe = p.go + p.ge, nge = -p.ge;
+  const int32_t one = p.one;
 
   for (;;) {
     unsigned long long task = 0;
@@ -78,12 +89,11 @@ __global__ void __launch_bounds__(TPB, MINB) wave32_kernel(const __grid_constant
       const bool firstp = (pass == 0), lastp = (pass + 1 == npass);
       // ---- profile of this pass: prof[b][c][l] = S(A[pcol0 + l*KW + c], b) -------------------
       __syncwarp();
-      for (int idx = lane; idx < PW; idx += 32) {
-        const uint32_t col = pcol0 + idx;
+      for (int c2 = 0; c2 < KW; ++c2) {  // lane l fills its own columns: stores hit bank l
+        const uint32_t col = pcol0 + lane * KW + c2;
         const uint32_t a = col < n ? qa[col] : nsym;
-        const int l2 = idx / KW, c2 = idx % KW;
         const int32_t* srow = sm + a * nsym;
-        for (uint32_t b = 0; b < nsym; ++b) prof[b * PW + c2 * 32 + l2] = srow[b];
+        for (uint32_t b = 0; b < nsym; ++b) prof[b * PW + c2 * 32 + lane] = srow[b];
       }
       __syncwarp();
       const int32_t* myprof = prof + lane;
@@ -147,12 +157,12 @@ __global__ void __launch_bounds__(TPB, MINB) wave32_kernel(const __grid_constant
           if (ra == m) {
             // ---- last row of an odd-length subject: a single row ------------------------------
             int32_t E = iEa;
-            int32_t t = hdiag + prow_a[0];
+            int32_t t = add_fma_pipe(hdiag, one, prow_a[0]);
             hdiag = iHa;
 #pragma unroll
             for (int c = 0; c < KW; ++c) {
               int32_t tn = 0;
-              if (c + 1 < KW) tn = H[c] + prow_a[(c + 1) * 32];
+              if (c + 1 < KW) tn = add_fma_pipe(H[c], one, prow_a[(c + 1) * 32]);
               const int32_t h = __vimax3_s32(t, E, F[c]);
               H[c] = h;
               const int32_t hg = h - goe;
@@ -167,15 +177,15 @@ __global__ void __launch_bounds__(TPB, MINB) wave32_kernel(const __grid_constant
             // ---- rows ra (A) and ra+1 (B), B one column behind A --------------------------------
             const int32_t* prow_b = myprof + ((let >> 8) & 0xffu) * PW;
             int32_t Ea = iEa, Eb = iEb;
-            int32_t ta = hdiag + prow_a[0];
-            int32_t tb = iHa + prow_b[0];
+            int32_t ta = add_fma_pipe(hdiag, one, prow_a[0]);
+            int32_t tb = add_fma_pipe(iHa, one, prow_b[0]);
             hdiag = iHb;
             int32_t ha_last = 0;
 #pragma unroll
             for (int c = 0; c <= KW; ++c) {
               if (c < KW) {
                 int32_t tn = 0;
-                if (c + 1 < KW) tn = H[c] + prow_a[(c + 1) * 32];
+                if (c + 1 < KW) tn = add_fma_pipe(H[c], one, prow_a[(c + 1) * 32]);
                 const int32_t h = __vimax3_s32(ta, Ea, F[c]);
                 H[c] = h;
                 const int32_t hg = h - goe;
@@ -186,7 +196,7 @@ __global__ void __launch_bounds__(TPB, MINB) wave32_kernel(const __grid_constant
               }
               if (c >= 1) {
                 int32_t tn = 0;
-                if (c < KW) tn = H[c - 1] + prow_b[c * 32];
+                if (c < KW) tn = add_fma_pipe(H[c - 1], one, prow_b[c * 32]);
                 const int32_t h = __vimax3_s32(tb, Eb, F[c - 1]);
                 H[c - 1] = h;
                 const int32_t hg = h - goe;
