@@ -283,6 +283,13 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        traffic = None
+        try:   # dram bytes of one launch of this kernel on this workload, from the committed ncu capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["gotoh16_kernel"]
+            if args.workload == "c2" and world == 1:
+                traffic = tr["dram_bytes_per_launch"]
+        except Exception:
+            pass
         lens_bytes = sum(len(s) for s in seqs)
         hbm_alg = (lens_bytes + 4 * st["n_pairs"]) / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0
         line = {
@@ -298,7 +305,10 @@ def main():
                     "ms_per_step": 1e3 * e2e_t / e2e_steps, "steps": e2e_steps, "launches_per_step": int(e2e_launches)},
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": {"bound": "dpx-alu", "kernel": "gotoh16_kernel", "achieved": achieved, "peak": peak, "unit": UNIT,
-                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "traffic_note": "dram read+write bytes of one launch (ncu --set full, profiles/ncu_gotoh16_c2_r01.txt): the "
+                                         "strip-boundary scratch column, not input re-reads; algorithmic bytes are len_i+len_j in, 4 B out per pair",
+                         "algorithmic_bytes": lens_bytes + 4 * st["n_pairs"],
                          "peak_how": f"{sms} SMs x {dpx_ops:.1f} DPX lane-results/clk/SM (measured live) x {sm_mhz} MHz "
                                      "(median under load) / 2.5 instr per cell (5 integer lane-ops, 16x2 packing: SURVEY 8d)",
                          "kernel_ms": kernel_ms, "kernel_cells": kernel_cells,

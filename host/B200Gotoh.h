@@ -1,0 +1,42 @@
+// B200Gotoh.h -- the in-process alignment tool: all-vs-all Gotoh distance matrix on a B200.
+//
+// Shaped like tweakseq/Core/ClustalO.{h,cpp} (name/path/preferred settings element, version
+// probe, makeCommand), but run() calls libtsqb200.so through the C ABI (include/tsq_b200.h)
+// instead of handing an argv to QProcess (SeqEditMainWin.cpp:1654-1660).
+#ifndef TSQ_HOST_B200GOTOH_H
+#define TSQ_HOST_B200GOTOH_H
+
+#include "AlignmentTool.h"
+
+namespace tsqhost {
+
+class B200Gotoh : public AlignmentTool {
+ public:
+  B200Gotoh();
+  ~B200Gotoh() override;
+
+  void makeCommand(std::string& fin, std::string& fout, std::string& exec,
+                   std::vector<std::string>& arglist) override;
+  void writeSettings(SettingsDocument& doc) override;
+  void readSettings(SettingsDocument& doc) override;
+  bool inProcess() override { return true; }
+  int run(const std::string& fin, const std::string& fout, const LogSink& log, CancelFlag* cancel) override;
+
+  // In-memory path: residues exactly as Sequence::filter(true) returns them
+  // (Sequence.cpp:57-69).  Packed upper-triangle results, submitted order.
+  int distanceMatrix(const std::vector<std::string>& residues, std::vector<int>& scores,
+                     std::vector<double>& distances, std::string* error = nullptr);
+
+  int gapOpen = -1, gapExtend = -1, device = 0;  // <0: library defaults (11/1 protein)
+  bool nucleotide = false;
+
+ private:
+  void init();
+  void getVersion();
+};
+
+// Sequence::filter for 16-bit residue cells carrying tweakseq's flag bits (Sequence.h:36-39).
+std::string filterCells(const std::vector<unsigned short>& cells, bool applyExclusions);
+
+}  // namespace tsqhost
+#endif
