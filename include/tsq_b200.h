@@ -119,6 +119,9 @@ const char *tsq_last_error(const tsq_ctx *ctx);
 int tsq_set_sequences(tsq_ctx *ctx, const char *const *residues, const uint32_t *lengths,
                       uint32_t n);
 
+/* Same, from ONE contiguous host buffer: sequence i is residues[offsets[i] .. offsets[i+1]). */
+int tsq_set_sequences_flat(tsq_ctx *ctx, const char *residues, const uint64_t *offsets, uint32_t n);
+
 /* The three stages of a run, separately callable (bench.py times them separately). */
 int tsq_upload(tsq_ctx *ctx);   /* sort/pack on the host, H2D */
 int tsq_compute(tsq_ctx *ctx);  /* enqueue all kernels on the context's stream (async) */

@@ -331,3 +331,15 @@ def test_partition_slabs_with_wavefront_rows():
     assert (full == rs).all()
     for c in ctxs:
         c.close()
+
+
+def test_flat_input_form_equals_pointer_form():
+    rng = np.random.default_rng(95)
+    seqs = ragged(rng, 40, 0, 150) + ["ac-d e", ""]
+    a, _, _, _ = gpu_run(seqs)
+    buf, offs = capi.flatten(seqs)
+    with t.Context() as ctx:
+        ctx.set_sequences_flat(buf, offs)
+        ctx.run()
+        b = ctx.scores()
+    assert (a == b).all()

@@ -49,7 +49,7 @@ LOG_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p)
 
 # every symbol include/tsq_b200.h declares (tests check the library exports each one)
 SYMBOLS = ["tsq_version", "tsq_version_string", "tsq_status_string", "tsq_device_count", "tsq_default_params",
-           "tsq_create", "tsq_destroy", "tsq_last_error", "tsq_set_sequences", "tsq_upload", "tsq_compute",
+           "tsq_create", "tsq_destroy", "tsq_last_error", "tsq_set_sequences", "tsq_set_sequences_flat", "tsq_upload", "tsq_compute",
            "tsq_download", "tsq_set_stream", "tsq_synchronize", "tsq_run", "tsq_scores", "tsq_distances",
            "tsq_self_scores", "tsq_device_scores", "tsq_partition", "tsq_finalize", "tsq_device_results",
            "tsq_get_stats", "tsq_measure_dpx_rate", "tsq_run_fasta", "tsq_plan_partition"]
@@ -88,6 +88,7 @@ def load_library():
     L.tsq_last_error.argtypes = [vp]
     L.tsq_last_error.restype = C.c_char_p
     L.tsq_set_sequences.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), C.c_uint32]
+    L.tsq_set_sequences_flat.argtypes = [vp, C.c_char_p, u64p, C.c_uint32]
     for f in ("tsq_upload", "tsq_compute", "tsq_download", "tsq_synchronize", "tsq_finalize"):
         getattr(L, f).argtypes = [vp]
     L.tsq_set_stream.argtypes = [vp, vp]
@@ -109,6 +110,15 @@ def load_library():
 def pair_index(i: int, j: int, n: int) -> int:
     """Packed upper-triangle index of (i, j), i < j (include/tsq_b200.h)."""
     return i * n - i * (i + 1) // 2 + (j - i - 1)
+
+
+def flatten(seqs):
+    """list of str/bytes -> (contiguous bytes, uint64 offsets[n+1]) for set_sequences_flat."""
+    raw = [s.encode("latin-1", "replace") if isinstance(s, str) else bytes(s) for s in seqs]
+    offs = np.zeros(len(raw) + 1, dtype=np.uint64)
+    if raw:
+        offs[1:] = np.cumsum([len(r) for r in raw], dtype=np.uint64)
+    return b"".join(raw), offs
 
 
 def plan_partition(lengths, world: int, **kw) -> list[tuple[int, int]]:
@@ -177,12 +187,21 @@ class Context:
             raise TsqError(rc, self._L.tsq_last_error(self._h).decode())
 
     def set_sequences(self, seqs):
+        """Per-sequence pointer form of the ABI (tsq_set_sequences)."""
         raw = [s.encode("latin-1", "replace") if isinstance(s, str) else bytes(s) for s in seqs]
         n = len(raw)
         arr = (C.c_char_p * max(n, 1))(*raw) if n else (C.c_char_p * 1)()
         lens = (C.c_uint32 * max(n, 1))(*[len(r) for r in raw]) if n else (C.c_uint32 * 1)()
         self._keep = (raw, arr, lens)
         self._ck(self._L.tsq_set_sequences(self._h, arr, lens, n))
+        self.n = n
+
+    def set_sequences_flat(self, buf: bytes, offsets: np.ndarray):
+        """One contiguous host buffer + n+1 offsets (tsq_set_sequences_flat)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        self._keep = (buf, offsets)
+        self._ck(self._L.tsq_set_sequences_flat(self._h, buf, offsets.ctypes.data_as(C.POINTER(C.c_uint64)), n))
         self.n = n
 
     def upload(self):

@@ -188,24 +188,31 @@ bool is_gap_or_space(unsigned char c) {
   return c == '-' || c == '.' || c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f';
 }
 
-void encode_into(int alphabet, const char* s, size_t len, std::vector<uint8_t>& out) {
-  out.clear();
-  out.reserve(len);
-  for (size_t i = 0; i < len; i++) {
-    unsigned char c = (unsigned char)s[i];
-    if (is_gap_or_space(c)) continue;
-    if (c >= 'a' && c <= 'z') c = (unsigned char)(c - 'a' + 'A');
-    if (alphabet == TSQ_NUCLEOTIDE) {
-      uint8_t v = 4;
-      if (c == 'A') v = 0;
-      else if (c == 'C') v = 1;
-      else if (c == 'G') v = 2;
-      else if (c == 'T' || c == 'U') v = 3;
-      out.push_back(v);
-    } else {
-      out.push_back((c >= 'A' && c <= 'Z') ? kProteinIndex[c - 'A'] : (uint8_t)22);
+// 256-entry byte -> symbol tables (0xff = dropped: '-', '.', whitespace).  Letter map of
+// tweakseq/Core/Annotations/Consensus.cpp:61-69; anything that is not a letter -> X / N.
+struct EncodeLut {
+  uint8_t prot[256], nuc[256];
+  EncodeLut() {
+    for (int c = 0; c < 256; c++) {
+      int u = (c >= 'a' && c <= 'z') ? c - 'a' + 'A' : c;
+      prot[c] = (u >= 'A' && u <= 'Z') ? kProteinIndex[u - 'A'] : (uint8_t)22;
+      nuc[c] = u == 'A' ? 0 : u == 'C' ? 1 : u == 'G' ? 2 : (u == 'T' || u == 'U') ? 3 : 4;
+      if (is_gap_or_space((unsigned char)c)) prot[c] = nuc[c] = 0xff;
     }
   }
+};
+const EncodeLut kLut;
+
+void encode_into(int alphabet, const char* s, size_t len, std::vector<uint8_t>& out) {
+  const uint8_t* lut = alphabet == TSQ_NUCLEOTIDE ? kLut.nuc : kLut.prot;
+  out.resize(len);
+  size_t k = 0;
+  for (size_t i = 0; i < len; i++) {
+    const uint8_t v = lut[(unsigned char)s[i]];
+    out[k] = v;
+    k += (v != 0xff);
+  }
+  out.resize(k);
 }
 
 // Packed-16 range analysis.  Values live as v + delta*(i+j) + BIAS in
@@ -400,10 +407,25 @@ int tsq_set_stream(tsq_ctx* c, void* s) {
 int tsq_set_sequences(tsq_ctx* c, const char* const* residues, const uint32_t* lengths, uint32_t n) {
   if (!c) return TSQ_ERR_INVALID;
   if (n > 0 && (!residues || !lengths)) return fail(c, TSQ_ERR_INVALID, "null sequence arrays");
-  c->enc.assign(n, {});
+  c->enc.resize(n);
   for (uint32_t i = 0; i < n; i++) {
     if (lengths[i] > 0 && !residues[i]) return fail(c, TSQ_ERR_INVALID, "sequence %u is null", i);
     encode_into(c->prm.alphabet, residues[i], lengths[i], c->enc[i]);
+  }
+  c->n = n;
+  c->have_seqs = true;
+  c->uploaded = c->computed = c->finalized = c->downloaded = false;
+  c->err.clear();
+  return TSQ_OK;
+}
+
+int tsq_set_sequences_flat(tsq_ctx* c, const char* residues, const uint64_t* offsets, uint32_t n) {
+  if (!c) return TSQ_ERR_INVALID;
+  if (n > 0 && (!residues || !offsets)) return fail(c, TSQ_ERR_INVALID, "null sequence buffer");
+  c->enc.resize(n);
+  for (uint32_t i = 0; i < n; i++) {
+    if (offsets[i + 1] < offsets[i]) return fail(c, TSQ_ERR_INVALID, "offsets not ascending at %u", i);
+    encode_into(c->prm.alphabet, residues + offsets[i], (size_t)(offsets[i + 1] - offsets[i]), c->enc[i]);
   }
   c->n = n;
   c->have_seqs = true;
@@ -635,6 +657,9 @@ int tsq_compute(tsq_ctx* c) {
     int grid = c->sm_count * v.ctas_sm;
     const unsigned long long need = (ntasks + warps_per_cta - 1) / warps_per_cta;
     if ((unsigned long long)grid > need) grid = (int)need;
+    // (r01: shrinking the grid so that every warp runs a whole number of tasks was measured and is
+    //  slower -- 7.8 vs 8.2 TCUPS on C2: warps of a partly filled last wave speed up on their own.)
+    if (const char* eg = getenv("TSQ_GRID")) grid = std::max(1, atoi(eg));
     const uint32_t maxlen = c->hi > c->lo ? c->lens[c->hi - 1] : 0;
     const uint32_t bnd_rows = maxlen + 8;  // the row loop prefetches up to 3 rows past the end
     TSQ_CUDA(c, c->d_bnd.reserve((size_t)grid * warps_per_cta * bnd_rows * 32));
