@@ -167,10 +167,10 @@ typedef struct {
   const uint32_t *pi, *pj; /* explicit list, or NULL for the packed range */
   int32_t *out;
   uint64_t next; /* atomic chunk cursor */
+  uint64_t chunk; /* pairs handed out per fetch */
   uint64_t cells; /* atomic */
 } job_t;
 
-#define CHUNK 64
 
 static void unpack_pair(uint64_t p, uint64_t n, uint32_t *pi, uint32_t *pj) {
   /* invert p = i*n - i(i+1)/2 + (j-i-1) by walking rows from a float guess */
@@ -193,9 +193,9 @@ static void *worker(void *arg) {
   job_t *jb = (job_t *)arg;
   uint64_t cells = 0;
   for (;;) {
-    uint64_t s = __atomic_fetch_add(&jb->next, CHUNK, __ATOMIC_RELAXED);
+    uint64_t s = __atomic_fetch_add(&jb->next, jb->chunk, __ATOMIC_RELAXED);
     if (s >= jb->end) break;
-    uint64_t e = s + CHUNK < jb->end ? s + CHUNK : jb->end;
+    uint64_t e = s + jb->chunk < jb->end ? s + jb->chunk : jb->end;
     uint32_t i = 0, j = 0;
     if (!jb->pi) unpack_pair(s, jb->n, &i, &j);
     for (uint64_t p = s; p < e; p++) {
@@ -222,6 +222,9 @@ static void *worker(void *arg) {
 static uint64_t run_job(job_t *jb, int nthreads) {
   if (nthreads < 1) nthreads = 1;
   if (nthreads > 256) nthreads = 256;
+  /* small jobs of long pairs: hand out single pairs so that every thread gets work */
+  uint64_t per = (jb->end - jb->begin) / ((uint64_t)nthreads * 4);
+  jb->chunk = per < 1 ? 1 : (per > 64 ? 64 : per);
   pthread_t th[256];
   int started = 0;
   for (int t = 1; t < nthreads; t++)

@@ -343,3 +343,68 @@ def test_flat_input_form_equals_pointer_form():
         ctx.run()
         b = ctx.scores()
     assert (a == b).all()
+
+
+# ---- BASELINE.json's sizes: sampled oracle comparison + size-independent properties ------------------
+def _sampled_check(seqs, alphabet, nsample, seed, go=None, ge=1, flags=0):
+    n = len(seqs)
+    with t.Context(alphabet=alphabet, flags=flags | t.FLAG_NO_DISTANCES) as ctx:
+        buf, offs = capi.flatten(seqs)
+        ctx.set_sequences_flat(buf, offs)
+        ctx.run()
+        s = ctx.scores()
+        st = ctx.stats()
+    assert st["cells"] == synth.total_cells(seqs)
+    rng = np.random.default_rng(seed)
+    pi = rng.integers(0, n - 1, nsample)
+    pj = rng.integers(1, n, nsample)
+    keep = pi < pj
+    pi, pj = pi[keep], pj[keep]
+    # plus the complete first and last rows of the triangle
+    pi = np.concatenate([pi, np.zeros(n - 1, dtype=pi.dtype), np.arange(0, n - 1)])
+    pj = np.concatenate([pj, np.arange(1, n), np.full(n - 1, n - 1)])
+    enc = [o.encode(x, alphabet) for x in seqs]
+    g = (11 if alphabet == 0 else 10) if go is None else go
+    ref, _ = o.pair_list(enc, pi, pj, o.matrix(alphabet), g, ge, nthreads=NT)
+    idx = pi.astype(np.int64) * n - pi.astype(np.int64) * (pi.astype(np.int64) + 1) // 2 + (pj.astype(np.int64) - pi - 1)
+    assert (s[idx] == ref).all()
+    return s, st
+
+
+def test_config3_full_size_sampled_and_properties():
+    """10,000 x 400 aa (49,995,000 pairs, 8.0e12 cells): >= 2e4 sampled pairs + first/last rows vs
+    the oracle; planted duplicates must score their self score (S(x,x) = sum of the diagonal)."""
+    _, seqs = synth.config(3)
+    seqs[9999] = seqs[0]
+    seqs[5000] = seqs[17]
+    s, st = _sampled_check(seqs, 0, 30000, 3)
+    n = len(seqs)
+    mat = o.matrix(0)
+    assert s[t.pair_index(0, 9999, n)] == o.self_score(o.encode(seqs[0]), mat)
+    assert s[t.pair_index(17, 5000, n)] == o.self_score(o.encode(seqs[17]), mat)
+    assert st["n_pairs"] == 49995000 and st["cells_s32"] == 0
+
+
+def test_config5_scaled_twin_sampled():
+    """configs[4] scaled to 20,000 x 150 aa (2.0e8 pairs, 4.5e12 cells), sampled."""
+    _, seqs = synth.config(5, 0.2)
+    _sampled_check(seqs, 0, 60000, 5)
+
+
+def test_config4_scaled_twin_wavefront_sampled():
+    """configs[3] scaled to 20 x 10-30 kb nucleotide genomes: the 32-bit wavefront kernel."""
+    _, seqs = synth.config(4, 0.04)
+    n = len(seqs)
+    with t.Context(alphabet=1, flags=t.FLAG_NO_DISTANCES) as ctx:
+        ctx.set_sequences(seqs)
+        ctx.run()
+        s, st = ctx.scores(), ctx.stats()
+    assert st["cells_s32"] == synth.total_cells(seqs) and st["cells_s16"] == 0
+    rng = np.random.default_rng(4)
+    sel = rng.choice(n * (n - 1) // 2, 40, replace=False)
+    iu, ju = np.triu_indices(n, 1)
+    enc = [o.encode(x, 1) for x in seqs]
+    ref, _ = o.pair_list(enc, iu[sel], ju[sel], o.matrix(1), 10, 1, nthreads=NT)
+    assert (s[sel] == ref).all()
+    fam = synth.nucleotide(6, 10000, 12000, 4, family=True)     # related genomes: long diagonal runs
+    assert_same(fam, alphabet=1)
