@@ -39,7 +39,8 @@
 namespace tsq {
 
 struct G16Params {
-  const uint32_t* dbw;         // subject residues, 32-way interleaved, 4 letters per word
+  const uint32_t* dbw;         // subject residues, 32-way interleaved, 2 rows per word as 16-bit
+                               // profile-row byte offsets (letter * STRIDE * 4), see the row loop
   const uint32_t* goff;        // word offset of each group of 32 sorted sequences
   const uint8_t* lin;          // residues, linear, sorted order
   const uint32_t* loff;        // start of each sorted sequence in lin
@@ -151,33 +152,37 @@ __global__ void __launch_bounds__(TPB, MINB) gotoh16_kernel(const __grid_constan
       uint32_t hdiag = (j0 == 0) ? p.bias * 0x10001u
                                  : (uint32_t)((int32_t)p.bias - p.go - (int32_t)j0 * gep) * 0x10001u;
       const int32_t hl0 = (int32_t)p.bias - p.go;  // H~(i,0) = hl0 - i*ge'
-      const bool first = (s == 0);
       const bool last = (s + 1 == nstrips);
 
-      // subject letters: one 32-bit word (4 residues) per lane per 4 rows, fetched a word ahead
-      uint32_t w = 0, nread = 0;
-      uint32_t wn = valid ? __ldg(dbp) : 0u;
-      auto next_letter = [&]() -> uint32_t {
-        if ((nread & 3u) == 0u) {
-          w = wn;
-          wn = __ldg(dbp + ((nread >> 2) + 1) * 32);
+      // subject letters: the database stores, per residue, the BYTE OFFSET of its profile row
+      // (letter * STRIDE * 4) as 16 bits, two rows per 32-bit word, right-aligned to an even
+      // count (a pad entry leads an odd-length sequence): one word = one row pair, fetched two
+      // pairs ahead (w1 next, w2 in flight).
+      const char* const profb = reinterpret_cast<const char*>(prof);
+      uint32_t widx = 2;
+      uint32_t w1 = valid ? __ldg(dbp) : 0u;
+      uint32_t w2 = valid ? __ldg(dbp + 32) : 0u;
+      auto next_word = [&]() -> uint32_t {
+        const uint32_t w = w1;
+        w1 = w2;
+        w2 = __ldg(dbp + (size_t)widx * 32);
+        ++widx;
+        return w;
+      };
+      // Strip 0 has no strip to its left: its boundary column (H~(i,0), E entering column 1) is
+      // a formula.  Writing it into the scratch column first keeps the row loop free of a
+      // first-strip case (a dozen predicated instructions per row pair otherwise).
+      if (s == 0) {
+        for (uint32_t r = 1; r <= Ls; ++r) {
+          const uint32_t hl = (uint32_t)(hl0 - (int32_t)r * gep) * 0x10001u;
+          bnd[(size_t)r * 32] = make_uint2(hl, hl - goe2);
         }
-        const uint32_t b = w & 0xffu;
-        w >>= 8;
-        ++nread;
-        return b;
-      };
-      // left boundary (H~(i, j0), E entering column j0+1) of row i
-      auto left_formula = [&](uint32_t i) -> uint2 {
-        const uint32_t hl = (uint32_t)(hl0 - (int32_t)i * gep) * 0x10001u;
-        return make_uint2(hl, hl - goe2);
-      };
-
+      }
       uint32_t i = 1;
       // ---- odd row count: row 1 alone, so that the main loop can take rows two at a time ----
       if (Ls & 1u) {
-        const uint32_t* prow = prof + next_letter() * STRIDE;
-        const uint2 lb = first ? left_formula(1) : bnd[32];
+        const uint32_t* prow = reinterpret_cast<const uint32_t*>(profb + (next_word() >> 16));
+        const uint2 lb = bnd[32];
         uint32_t E = lb.y;
         uint32_t t = hdiag + prow[0];
         hdiag = lb.x;
@@ -202,23 +207,17 @@ __global__ void __launch_bounds__(TPB, MINB) gotoh16_kernel(const __grid_constan
       // overlapped with the other row's.  t = H_diag + S' is formed one column ahead, from the
       // old H value before the cell overwrites it, so no register copy carries the diagonal.
       uint2 na = make_uint2(0u, 0u), nb = make_uint2(0u, 0u);
-      if (!first && i < Ls) {
+      if (i < Ls) {
         na = bnd[(size_t)i * 32];
         nb = bnd[(size_t)(i + 1) * 32];
       }
       for (; i < Ls; i += 2) {
-        const uint32_t* prow_a = prof + next_letter() * STRIDE;
-        const uint32_t* prow_b = prof + next_letter() * STRIDE;
-        uint2 la, lb;
-        if (first) {
-          la = left_formula(i);
-          lb = left_formula(i + 1);
-        } else {
-          la = na;
-          lb = nb;
-          na = bnd[(size_t)(i + 2) * 32];   // rows of the next iteration (scratch has slack rows)
-          nb = bnd[(size_t)(i + 3) * 32];
-        }
+        const uint32_t wab = next_word();
+        const uint32_t* prow_a = reinterpret_cast<const uint32_t*>(profb + (wab & 0xffffu));
+        const uint32_t* prow_b = reinterpret_cast<const uint32_t*>(profb + (wab >> 16));
+        const uint2 la = na, lb = nb;
+        na = bnd[(size_t)(i + 2) * 32];   // rows of the next iteration (scratch has slack rows)
+        nb = bnd[(size_t)(i + 3) * 32];
         uint32_t Ea = la.y, Eb = lb.y;
         uint32_t ta = hdiag + prow_a[0];      // diag of A(0) = H(i-1, j0)
         uint32_t tb = la.x + prow_b[0];       // diag of B(0) = H(i,   j0)

@@ -488,32 +488,6 @@ int tsq_upload(tsq_ctx* c) {
       return fail(c, TSQ_ERR_RANGE, "sequence of length %u: scores would not fit 32 bits", c->lens[n - 1]);
   }
 
-  // ---- 32-way interleaved subject database (4 residues per word) ---------------------------
-  const uint32_t ngroups = (n + 31) / 32;
-  c->goff.assign(ngroups + 1, 0);
-  uint64_t words = 0;
-  for (uint32_t g = 0; g < ngroups; g++) {
-    c->goff[g] = (uint32_t)words;
-    const uint32_t last = std::min(n, (g + 1) * 32) - 1;
-    const uint32_t rows4 = (c->lens[last] + 3) / 4 + 1;  // +1: the kernel prefetches one word ahead
-    words += (uint64_t)rows4 * 32;
-    if (words > 0xfffffff0ull) return fail(c, TSQ_ERR_RANGE, "interleaved database too large");
-  }
-  c->goff[ngroups] = (uint32_t)words;
-  TSQ_CUDA(c, c->dbw.reserve(words));
-  c->dbw_size = words;
-  memset(c->dbw.p, 0, words * sizeof(uint32_t));
-  for (uint32_t i = 0; i < n; i++) {
-    const uint8_t* s = c->lin.p + c->loff[i];
-    uint32_t* base = c->dbw.p + c->goff[i >> 5] + (i & 31);
-    const uint32_t l = c->lens[i];
-    for (uint32_t r = 0; r < l; r += 4) {
-      uint32_t w = 0;
-      for (uint32_t k = 0; k < 4 && r + k < l; k++) w |= (uint32_t)s[r + k] << (8 * k);
-      base[(size_t)(r >> 2) * 32] = w;
-    }
-  }
-
   // ---- partition of the sorted rows across ranks (contiguous, balanced by DP cells) ---------
   const int world = c->prm.part_world, rank = c->prm.part_rank;
   std::vector<uint32_t> first_row;
@@ -589,6 +563,41 @@ int tsq_upload(tsq_ctx* c) {
     if (const char* fk = getenv("TSQ_FORCE_K")) {  // developer override for tuning runs
       tsq::G16Launch v;
       if (tsq::g16_variant(atoi(fk), (uint32_t)c->nsym, &v)) c->K = atoi(fk);
+    }
+  }
+
+  // ---- 32-way interleaved subject database of the packed kernel ----------------------------------
+  // Per residue the 16-bit byte offset of its profile row (letter * STRIDE(K) * 4), two rows per
+  // 32-bit word, right-aligned to an even row count (a pad entry leads an odd-length sequence),
+  // so one coalesced 128-byte load per warp feeds one row pair of all 32 lanes.
+  {
+    tsq::G16Launch kv;
+    if (!tsq::g16_variant(c->K, (uint32_t)c->nsym, &kv)) return fail(c, TSQ_ERR_INVALID, "no kernel variant K=%d", c->K);
+    const uint32_t scale = (uint32_t)kv.stride * 4u;
+    const uint32_t ngroups = (n + 31) / 32;
+    c->goff.assign(ngroups + 1, 0);
+    uint64_t words = 0;
+    for (uint32_t g = 0; g < ngroups; g++) {
+      c->goff[g] = (uint32_t)words;
+      const uint32_t last = std::min(n, (g + 1) * 32) - 1;
+      const uint32_t len16 = std::min(c->lens[last], c->max_len16);  // longer ones never enter this kernel
+      const uint32_t rows2 = (len16 + 1) / 2 + 3;                    // +3: two-word prefetch slack
+      words += (uint64_t)rows2 * 32;
+      if (words > 0xfffffff0ull) return fail(c, TSQ_ERR_RANGE, "interleaved database too large");
+    }
+    c->goff[ngroups] = (uint32_t)words;
+    TSQ_CUDA(c, c->dbw.reserve(words));
+    c->dbw_size = words;
+    memset(c->dbw.p, 0, words * sizeof(uint32_t));
+    for (uint32_t i = lo; i < hi; i++) {
+      const uint8_t* sq = c->lin.p + c->loff[i];
+      uint32_t* base = c->dbw.p + c->goff[i >> 5] + (i & 31);
+      const uint32_t l = c->lens[i];
+      const uint32_t odd = l & 1u;
+      for (uint32_t r = 0; r < l; r++) {
+        const uint32_t slot = r + odd;  // position in the right-aligned 16-bit stream
+        base[(size_t)(slot >> 1) * 32] |= ((uint32_t)sq[r] * scale) << (16 * (slot & 1u));
+      }
     }
   }
 

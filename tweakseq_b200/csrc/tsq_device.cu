@@ -25,6 +25,7 @@ bool g16_variant(int K, uint32_t nsym, G16Launch* out) {
   if (K == KK) {                                                                          \
     if (out) {                                                                            \
       out->K = KK;                                                                        \
+      out->stride = G16Cfg<KK>::STRIDE;                                                   \
       out->tpb = TT;                                                                      \
       out->ctas_sm = MM;                                                                  \
       const size_t sbsz = ((size_t)(nsym + 1) * nsym + 31) & ~(size_t)31;                 \

@@ -14,6 +14,7 @@ extern const int kStripWidths[kNumStripWidths];
 
 struct G16Launch {
   int K;         // strip width
+  int stride;    // profile row stride in words (== 1 mod 32): the database pre-scales letters by it
   int tpb;       // threads per CTA
   int ctas_sm;   // resident CTAs per SM the variant is compiled for
   size_t smem;   // dynamic shared memory per CTA for a given nsym
