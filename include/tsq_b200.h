@@ -58,6 +58,7 @@ extern "C" {
 /* flags */
 #define TSQ_FLAG_FORCE_S32 1u     /* never use the packed 16-bit kernel */
 #define TSQ_FLAG_NO_DISTANCES 2u  /* skip the fp64 distance pass (scores only) */
+#define TSQ_FLAG_NO_WAVE16 4u     /* long sequences: 32-bit wavefront kernel only, not the packed one */
 
 typedef struct tsq_ctx tsq_ctx;
 

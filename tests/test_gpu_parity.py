@@ -280,36 +280,63 @@ def test_every_strip_width_variant(K, monkeypatch):
     assert_same(seqs, 0, 7, 3)
 
 
-# ---- regime 2: the 32-bit anti-diagonal wavefront kernel -------------------------------------
-def test_force_s32_protein_ragged_matches_oracle():
+# ---- regime 2: the anti-diagonal wavefront kernels (packed wave16, and 32-bit wave32) ----------------
+WAVE = [pytest.param(0, id="wave16"), pytest.param(4, id="wave32")]   # 4 = TSQ_FLAG_NO_WAVE16
+
+
+@pytest.mark.parametrize("wf", WAVE)
+def test_force_wavefront_protein_ragged_matches_oracle(wf):
     rng = np.random.default_rng(90)
     seqs = ragged(rng, 48, 0, 420) + ["W", "AC", "ACD"]
-    st, cells = assert_same(seqs, flags=t.FLAG_FORCE_S32)
+    st, cells = assert_same(seqs, flags=t.FLAG_FORCE_S32 | wf)
     assert st["cells_s32"] == cells and st["cells_s16"] == 0
-    assert_same(seqs, 0, 3, 2, flags=t.FLAG_FORCE_S32)
+    assert_same(seqs, 0, 3, 2, flags=t.FLAG_FORCE_S32 | wf)
 
 
-def test_force_s32_nucleotide_ragged_matches_oracle():
+@pytest.mark.parametrize("wf", WAVE)
+def test_force_wavefront_nucleotide_ragged_matches_oracle(wf):
     rng = np.random.default_rng(91)
     seqs = ragged(rng, 40, 1, 2600, "ACGT") + ragged(rng, 6, 1020, 1030, "ACGTN") + ["A", "ACGTACGT"]
-    assert_same(seqs, alphabet=1, flags=t.FLAG_FORCE_S32)
-    assert_same(seqs[:20], alphabet=1, go=0, ge=2, flags=t.FLAG_FORCE_S32)
+    assert_same(seqs, alphabet=1, flags=t.FLAG_FORCE_S32 | wf)
+    assert_same(seqs[:20], alphabet=1, go=0, ge=2, flags=t.FLAG_FORCE_S32 | wf)
 
 
-def test_long_nucleotide_sequences_use_both_kernels():
+@pytest.mark.parametrize("wf", WAVE)
+def test_long_nucleotide_sequences_use_both_regimes(wf):
     rng = np.random.default_rng(92)
     seqs = (ragged(rng, 24, 10, 400, "ACGT") + ragged(rng, 5, 7300, 9500, "ACGT") + ragged(rng, 2, 12000, 12600, "ACGT")
             + [""])
     fam = synth.nucleotide(3, 8000, 9000, 4, family=True)
-    st, cells = assert_same(seqs + fam, alphabet=1)
+    st, cells = assert_same(seqs + fam, alphabet=1, flags=wf)
     assert st["cells_s16"] > 0 and st["cells_s32"] > 0 and st["cells_s16"] + st["cells_s32"] == cells
 
 
-def test_long_protein_beyond_the_16_bit_range():
+@pytest.mark.parametrize("wf", WAVE)
+def test_long_protein_beyond_the_16_bit_range(wf):
     rng = np.random.default_rng(93)
     seqs = ragged(rng, 10, 50, 300, AA[:20]) + ragged(rng, 2, 4700, 5200, AA[:20])
-    st, _ = assert_same(seqs)
+    st, _ = assert_same(seqs, flags=wf)
     assert st["cells_s32"] > 0
+
+
+def test_wave16_extreme_scores_walk_the_base():
+    """Identical / poly-W long sequences drive H far from 0 (up to +11 per cell) and unrelated ones far
+    below: the moving base of the packed wavefront kernel has to follow both."""
+    rng = np.random.default_rng(96)
+    w = "W" * 6000
+    c = "C" * 5500
+    r1 = "".join(rng.choice(list(AA[:20]), 5200))
+    seqs = [w, w[:5900], c, r1, r1[:2000] + r1[2100:], "ACDEFGHIKL" * 480, "A" * 30]
+    assert_same(seqs)
+    g1 = "".join(rng.choice(list("ACGT"), 16000))
+    nts = ["A" * 15000, "A" * 14000 + "C" * 900, g1, g1[:9000] + g1[9500:], "ACGT" * 2500, "T" * 8000, "ACGTN"]
+    assert_same(nts, alphabet=1)
+
+
+def test_large_gap_penalties_fall_back_to_the_32_bit_wavefront():
+    rng = np.random.default_rng(97)
+    seqs = ragged(rng, 12, 100, 900, "ACGT")
+    assert_same(seqs, alphabet=1, go=120, ge=9, flags=t.FLAG_FORCE_S32)   # window too wide for wave16
 
 
 def test_partition_slabs_with_wavefront_rows():
@@ -408,3 +435,4 @@ def test_config4_scaled_twin_wavefront_sampled():
     assert (s[sel] == ref).all()
     fam = synth.nucleotide(6, 10000, 12000, 4, family=True)     # related genomes: long diagonal runs
     assert_same(fam, alphabet=1)
+    assert_same(fam, alphabet=1, flags=t.FLAG_NO_WAVE16)

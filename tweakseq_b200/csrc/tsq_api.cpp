@@ -137,6 +137,8 @@ struct tsq_ctx {
   uint64_t part_begin = 0, part_end = 0;
   std::vector<unsigned long long> task_prefix;
   std::vector<uint2> pairs32;             // tasks of the 32-bit wavefront kernel (sorted indices)
+  std::vector<uint4> tasks16w;            // tasks of the packed wavefront kernel (i1, i2, j, 0)
+  bool use_w16 = false;
   uint32_t q_begin = 0, q_end = 0;
   int K = 0;
   uint64_t cells16 = 0, cells32 = 0, pairs_part = 0;
@@ -149,6 +151,8 @@ struct tsq_ctx {
   DevBuf<unsigned long long> d_prefix, d_counter;
   DevBuf<uint2> d_bnd;
   DevBuf<uint2> d_pairs32;
+  DevBuf<uint4> d_tasks16w;
+  DevBuf<int4> d_bnd16w;
   DevBuf<int2> d_bnd32;
   DevBuf<int32_t> d_smat;
   // host results
@@ -388,7 +392,7 @@ int tsq_destroy(tsq_ctx* c) {
   c->d_perm.release(); c->d_sbias.release(); c->d_lin.release(); c->d_self.release();
   c->d_sorted.release(); c->d_scores.release(); c->d_dist.release(); c->d_prefix.release();
   c->d_counter.release(); c->d_bnd.release(); c->h_scores.release(); c->h_dist.release();
-  c->lin.release(); c->dbw.release(); c->d_pairs32.release(); c->d_bnd32.release(); c->d_smat.release();
+  c->lin.release(); c->dbw.release(); c->d_pairs32.release(); c->d_tasks16w.release(); c->d_bnd16w.release(); c->d_bnd32.release(); c->d_smat.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -529,17 +533,43 @@ int tsq_upload(tsq_ctx* c) {
   //      restricted to this rank's rows, biggest pairs first -------------------------------------
   c->cells32 = 0;
   c->pairs32.clear();
+  c->tasks16w.clear();
+  {
+    // the packed wavefront kernel is exact while the cells a warp holds span < 2^15 score units
+    const long long lip = std::max(std::abs(c->smax), std::abs(c->smin)) + c->go + c->ge + 2 * c->delta;
+    c->use_w16 = !(c->prm.flags & TSQ_FLAG_NO_WAVE16) && tsq::w16_window((uint32_t)c->nsym, lip) <= 30000;
+  }
   if (hi < n) {
     const uint32_t ra = std::max(c->row_a, lo);
-    for (uint32_t i = c->row_b; i-- > ra;) {
-      for (uint32_t j = n; j-- > std::max(i + 1, hi);) {
-        c->pairs32.push_back(make_uint2(i, j));
-        c->cells32 += (uint64_t)c->lens[i] * c->lens[j];
+    if (c->use_w16) {
+      // (query pair, subject): subject j long, queries i < j of this rank's rows, two at a time
+      for (uint32_t j = n; j-- > hi;) {
+        const uint32_t top = std::min(c->row_b, j);  // queries in [ra, top)
+        uint32_t i = top;
+        while (i > ra) {
+          if (i - ra >= 2) {
+            c->tasks16w.push_back(make_uint4(i - 2, i - 1, j, 0));
+            c->cells32 += ((uint64_t)c->lens[i - 2] + c->lens[i - 1]) * c->lens[j];
+            c->pairs_part += 2;
+            i -= 2;
+          } else {
+            c->tasks16w.push_back(make_uint4(i - 1, i - 1, j, 0));
+            c->cells32 += (uint64_t)c->lens[i - 1] * c->lens[j];
+            c->pairs_part += 1;
+            i -= 1;
+          }
+        }
       }
+    } else {
+      for (uint32_t i = c->row_b; i-- > ra;) {
+        for (uint32_t j = n; j-- > std::max(i + 1, hi);) {
+          c->pairs32.push_back(make_uint2(i, j));
+          c->cells32 += (uint64_t)c->lens[i] * c->lens[j];
+        }
+      }
+      c->pairs_part += c->pairs32.size();
     }
-    c->pairs_part += c->pairs32.size();
   }
-
   // ---- strip width: least estimated work over the instantiated variants -----------------------
   // A strip of K columns costs about K + 2.5 cell-times per row (the row's letter fetch, boundary
   // load/store and loop control are worth ~2.5 cells: profiles/ r01 sweep), padding included.
@@ -631,6 +661,10 @@ int tsq_upload(tsq_ctx* c) {
   }
   TSQ_CUDA(c, cudaMemcpyAsync(c->d_sbias.p, sbias.data(), sbias.size() * 4, cudaMemcpyHostToDevice, s));
   TSQ_CUDA(c, cudaMemcpyAsync(c->d_prefix.p, c->task_prefix.data(), c->task_prefix.size() * 8, cudaMemcpyHostToDevice, s));
+  if (!c->tasks16w.empty()) {
+    TSQ_CUDA(c, c->d_tasks16w.reserve(c->tasks16w.size()));
+    TSQ_CUDA(c, cudaMemcpyAsync(c->d_tasks16w.p, c->tasks16w.data(), c->tasks16w.size() * sizeof(uint4), cudaMemcpyHostToDevice, s));
+  }
   if (!c->pairs32.empty()) {
     std::vector<int32_t> smat((size_t)(nsym + 1) * nsym, 0);
     for (uint32_t a = 0; a < nsym; a++)
@@ -701,6 +735,37 @@ int tsq_compute(tsq_ctx* c) {
     p.goe2 = (uint32_t)(c->go + c->ge - c->delta) * 0x10001u;
     if (!fits16(c, lpad)) return fail(c, TSQ_ERR_RANGE, "internal: padded length %u outside the 16-bit bound", lpad);
     TSQ_CUDA(c, tsq::g16_launch(c->K, grid, p, s));
+    launches++;
+  }
+  if (!c->tasks16w.empty()) {
+    tsq::W32Launch v;
+    if (!tsq::w16_variant((uint32_t)c->nsym, &v)) return fail(c, TSQ_ERR_INVALID, "no packed wavefront kernel variant");
+    const int warps_per_cta = v.tpb / 32;
+    int grid = c->sm_count * v.ctas_sm;
+    const unsigned long long need = (c->tasks16w.size() + warps_per_cta - 1) / warps_per_cta;
+    if ((unsigned long long)grid > need) grid = (int)need;
+    const uint32_t bnd_rows = c->lens[c->n - 1] + 8;
+    TSQ_CUDA(c, c->d_bnd16w.reserve((size_t)grid * warps_per_cta * bnd_rows));
+    TSQ_CUDA(c, cudaMemsetAsync(c->d_counter.p + 2, 0, sizeof(unsigned long long), s));
+    tsq::W16Params w{};
+    w.lin = c->d_lin.p;
+    w.loff = c->d_loff.p;
+    w.lens = c->d_lens.p;
+    w.tasks = c->d_tasks16w.p;
+    w.counter = c->d_counter.p + 2;
+    w.bnd = c->d_bnd16w.p;
+    w.sbias = c->d_sbias.p;
+    w.out = c->d_sorted.p;
+    w.ntasks = c->tasks16w.size();
+    w.bnd_rows = bnd_rows;
+    w.n_total = c->n;
+    w.nsym = (uint32_t)c->nsym;
+    w.delta = c->delta;
+    w.go = c->go;
+    w.gep = c->ge - c->delta;
+    w.goep = c->go + c->ge - c->delta;
+    w.negge2 = ((uint32_t)(-(c->ge - c->delta)) & 0xffffu) * 0x10001u;
+    TSQ_CUDA(c, tsq::w16_launch(grid, w, s));
     launches++;
   }
   if (!c->pairs32.empty()) {

@@ -107,6 +107,57 @@ cudaError_t w32_launch(int grid, const W32Params& p, cudaStream_t stream) {
   return cudaErrorInvalidValue;
 }
 
+// ---- packed wavefront kernel -------------------------------------------------------------------
+#define TSQ_W16_VARIANTS(X) \
+  X(32, 128, 2)             \
+  X(24, 128, 3)             \
+  X(16, 128, 3)             \
+  X(8, 128, 2)
+
+bool w16_variant(uint32_t nsym, W32Launch* out) {
+  if (nsym == 0 || nsym > 24) return false;
+  W32Launch v;
+  v.KW = nsym <= 8 ? 24 : 8;
+  v.tpb = 128;
+  v.ctas_sm = nsym <= 8 ? 3 : 2;
+  if (const char* e = getenv("TSQ_FORCE_KW16")) {  // developer override for tuning runs: "KW,ctas"
+    int kw = 0, ct = 0;
+    if (sscanf(e, "%d,%d", &kw, &ct) == 2) {
+#define X(KK, TT, MM) if (kw == KK && ct == MM) { v.KW = KK; v.ctas_sm = MM; }
+      TSQ_W16_VARIANTS(X)
+#undef X
+    }
+  }
+  const size_t sbsz = ((size_t)(nsym + 1) * nsym + 31) & ~(size_t)31;
+  v.smem = (sbsz + (size_t)(v.tpb / 32) * nsym * 32 * v.KW) * sizeof(uint32_t);
+  if (out) *out = v;
+  return true;
+}
+
+long long w16_window(uint32_t nsym, long long lipschitz) {
+  W32Launch v;
+  if (!w16_variant(nsym, &v)) return 1ll << 40;
+  return (32ll * v.KW + 2 * 31 + 2 * 32 + 16) * lipschitz;  // RB = 32 steps between re-centrings
+}
+
+cudaError_t w16_launch(int grid, const W16Params& p, cudaStream_t stream) {
+  W32Launch v;
+  if (!w16_variant(p.nsym, &v)) return cudaErrorInvalidValue;
+#define X(KK, TT, MM)                                                                        \
+  if (v.KW == KK && v.ctas_sm == MM) {                                                       \
+    auto kern = p.negge2 == 0x00010001u ? wave16_kernel<KK, TT, MM, 0x00010001u>             \
+                                        : wave16_kernel<KK, TT, MM, 0u>;                     \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                         (int)v.smem);                                       \
+    if (e != cudaSuccess) return e;                                                          \
+    kern<<<grid, TT, v.smem, stream>>>(p);                                                   \
+    return cudaGetLastError();                                                               \
+  }
+  TSQ_W16_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
 // ---- finalize: empties, un-sort, fp64 distances -----------------------------------------
 // One CTA per sorted row i; threads stride over j > i.  Distances follow the oracle's
 // tsq_oracle_distance(): two separately rounded IEEE operations (div, sub), no contraction.

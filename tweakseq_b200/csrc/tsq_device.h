@@ -5,6 +5,7 @@
 
 #include "gotoh16.cuh"
 #include "wave32.cuh"
+#include "wave16.cuh"
 
 namespace tsq {
 
@@ -33,6 +34,12 @@ struct W32Launch {
 };
 bool w32_variant(uint32_t nsym, W32Launch* out);
 cudaError_t w32_launch(int grid, const W32Params& p, cudaStream_t stream);
+
+// Packed wavefront kernel (wave16.cuh).  w16_window() is the span D (in score units) of the cells a
+// warp holds at one time for a per-step Lipschitz bound L; the kernel is exact while D <= 30000.
+bool w16_variant(uint32_t nsym, W32Launch* out);
+long long w16_window(uint32_t nsym, long long lipschitz);
+cudaError_t w16_launch(int grid, const W16Params& p, cudaStream_t stream);
 
 struct FinalizeParams {
   const int32_t* sorted;      // packed triangle, sorted order

@@ -1,0 +1,281 @@
+// wave16.cuh -- regime 2, packed: intra-task anti-diagonal wavefront Gotoh kernel with two
+// alignments per 32-bit word (u16x2 DPX) and a moving base, sm_100a.
+//
+// Same wavefront as wave32.cuh (one warp per task, lane l owns KW adjacent columns, two rows per
+// lane per step, right edges handed to lane l+1 by warp shuffle), but a task is TWO queries
+// (A1, A2, along the columns, one per 16-bit half) against one long subject (along the rows), so
+// every DPX instruction advances two alignments -- what the packed inter-task kernel
+// (gotoh16.cuh) does for sequences short enough to fit 16 bits outright.
+//
+// Long sequences do not fit 16 bits (|H| reaches 10^5), but the CELLS A WARP HOLDS AT ONE TIME do:
+// by the Lipschitz property of alignment matrices (|H(i,j)-H(i,j-1)|, |H(i,j)-H(i-1,j)| <=
+// max S + go + ge), everything in flight -- 32*KW columns by ~62+2R rows -- lies within a window
+// D = (32*KW + 2*31 + 2*R + 16) * L of one reference cell, and E, F lie within go+ge of an H.
+// The kernel therefore stores v - base(half) in unsigned 16 bits, where base is a warp-uniform
+// 32-bit number per half that is re-centred every R steps on a reference cell (lane 16's first
+// column): all live registers are shifted by the same packed constant, base absorbs the shift.
+// max() and +constant commute with a uniform shift, so the arithmetic is exactly the 32-bit
+// recurrence as long as nothing leaves [0, 65535]; the host only selects this kernel when
+// D <= 30000 (tsq_api.cpp: wave16_ok) and falls back to wave32 otherwise.  Values that cross a
+// pass boundary (lane 31 -> memory -> lane 0 of the next pass) and the final scores are
+// converted to absolute 32-bit numbers.  As in gotoh16.cuh the stored value is skewed by
+// delta*(i+j) so that substitution scores are non-negative and the two plain adds of a cell
+// cannot carry between the halves; the skew is just part of what base tracks.
+//
+// Spec: SURVEY.md section 8c.  Exactness is tested bit for bit against the oracle and against
+// wave32 (tests/test_gpu_parity.py).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "gotoh16.cuh"
+
+namespace tsq {
+
+struct W16Params {
+  const uint8_t* lin;          // residues, linear, sorted order
+  const uint32_t* loff;        // start of each sorted sequence
+  const uint32_t* lens;        // sorted lengths
+  const uint4* tasks;          // (i1, i2, j, 0): queries i1 <= i2 (i2 == i1: single), subject j
+  unsigned long long* counter; // dynamic task cursor
+  int4* bnd;                   // pass boundary scratch: [warp slot][row] (H_lo, H_hi, E_lo, E_hi) absolute
+  const uint32_t* sbias;       // (nsym+1) x nsym biased scores S' = S + 2*delta (row nsym = 0)
+  int32_t* out;                // scores, packed upper triangle in sorted order
+  unsigned long long ntasks;
+  uint32_t bnd_rows;
+  uint32_t n_total;
+  uint32_t nsym;
+  int32_t delta;               // skew per anti-diagonal
+  int32_t go;                  // gap open
+  int32_t gep;                 // ge' = ge - delta
+  int32_t goep;                // goe' = go + ge - delta
+  uint32_t negge2;             // (-ge' mod 2^16) in both halves
+};
+
+__device__ __forceinline__ uint32_t pack_rel(int32_t a, int32_t base_lo, int32_t base_hi) {
+  return ((uint32_t)(a - base_lo) & 0xffffu) | ((uint32_t)(a - base_hi) << 16);
+}
+
+template <int KW, int TPB, int MINB, uint32_t NGE>
+__global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant__ W16Params p) {
+  constexpr int PW = 32 * KW;        // columns per pass
+  constexpr uint32_t RB = 32;        // re-centre the base every RB steps (2*RB rows)
+  constexpr int32_t CENTER = 32768;
+  extern __shared__ uint32_t smem16[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const uint32_t nsym = p.nsym;
+  const uint32_t sbsz = (nsym + 1) * nsym;
+  uint32_t* sb = smem16;
+  uint32_t* prof = smem16 + ((sbsz + 31) & ~31u) + (size_t)wib * nsym * PW;
+  for (uint32_t i = threadIdx.x; i < sbsz; i += TPB) sb[i] = p.sbias[i];
+  __syncthreads();
+
+  const uint32_t gw = blockIdx.x * (TPB / 32) + wib;
+  int4* const bnd = p.bnd + (size_t)gw * p.bnd_rows;
+  const uint32_t nge = NGE ? NGE : p.negge2;
+  const int32_t go = p.go, gep = p.gep, goep = p.goep;
+  const uint32_t goe2 = (uint32_t)goep * 0x10001u;
+
+  for (;;) {
+    unsigned long long task = 0;
+    if (lane == 0) task = atomicAdd(p.counter, 1ULL);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= p.ntasks) break;
+    const uint4 tk = p.tasks[task];
+    const uint32_t n1 = p.lens[tk.x], n2 = p.lens[tk.y], m = p.lens[tk.z];  // n1 <= n2
+    const uint8_t* q1 = p.lin + p.loff[tk.x];
+    const uint8_t* q2 = p.lin + p.loff[tk.y];
+    const uint8_t* sq = p.lin + p.loff[tk.z];
+    const uint32_t npass = (n2 + PW - 1) / PW;
+    const uint32_t pass1 = (n1 - 1) / PW;   // pass in which query 1 ends
+    const uint32_t npairs_rows = (m + 1) / 2;
+    int32_t res_lo = 0, res_hi = 0;
+
+    for (uint32_t pass = 0; pass < npass; ++pass) {
+      const uint32_t pcol0 = pass * PW;
+      const bool firstp = (pass == 0), lastp = (pass + 1 == npass);
+      // ---- packed profile of this pass: prof[b][c][l] = S'(A1[col],b) | S'(A2[col],b) << 16 ------
+      __syncwarp();
+      for (int c2 = 0; c2 < KW; ++c2) {
+        const uint32_t col = pcol0 + lane * KW + c2;
+        const uint32_t a1 = col < n1 ? q1[col] : nsym;
+        const uint32_t a2 = col < n2 ? q2[col] : nsym;
+        const uint32_t* r1 = sb + a1 * nsym;
+        const uint32_t* r2 = sb + a2 * nsym;
+        for (uint32_t b = 0; b < nsym; ++b) prof[b * PW + c2 * 32 + lane] = r1[b] | (r2[b] << 16);
+      }
+      __syncwarp();
+      const uint32_t* myprof = prof + lane;
+
+      // ---- row 0 of this lane's column block; absolute skewed A(0,j) = -go - j*ge' ----------------
+      const int32_t col0 = (int32_t)(pcol0 + lane * KW);
+      int32_t base_lo = (-go - (int32_t)(pcol0 + PW / 2) * gep) - CENTER;
+      int32_t base_hi = base_lo;
+      uint32_t H[KW], F[KW];
+#pragma unroll
+      for (int c = 0; c < KW; ++c) {
+        H[c] = pack_rel(-go - (col0 + c + 1) * gep, base_lo, base_hi);
+        F[c] = H[c] - goe2;
+      }
+      uint32_t hdiag = pack_rel(col0 == 0 ? 0 : -go - col0 * gep, base_lo, base_hi);
+
+      uint32_t oHa = 0, oEa = 0, oHb = 0, oEb = 0, olet = 0;  // handed to the right neighbour
+      int4 nba = make_int4(0, 0, 0, 0), nbb = make_int4(0, 0, 0, 0);
+      uint32_t nlet = 0;
+      if (lane == 0) {
+        nlet = (uint32_t)sq[0] | ((m > 1 ? (uint32_t)sq[1] : 0u) << 8);
+        if (!firstp) {
+          nba = bnd[1];
+          nbb = bnd[2];
+        }
+      }
+      const uint32_t nsteps = npairs_rows + 31;
+      for (uint32_t s = 0; s < nsteps; ++s) {
+        uint32_t iHa = __shfl_up_sync(0xffffffffu, oHa, 1);
+        uint32_t iEa = __shfl_up_sync(0xffffffffu, oEa, 1);
+        uint32_t iHb = __shfl_up_sync(0xffffffffu, oHb, 1);
+        uint32_t iEb = __shfl_up_sync(0xffffffffu, oEb, 1);
+        uint32_t let = __shfl_up_sync(0xffffffffu, olet, 1);
+        if (lane == 0) {
+          const uint32_t ra = 2 * s + 1;
+          let = nlet;
+          if (firstp) {  // A(i,0) = -go - i*ge'; E entering column 1 = A(i,0) - goe'
+            const int32_t a = -go - (int32_t)ra * gep;
+            iHa = pack_rel(a, base_lo, base_hi);
+            iEa = iHa - goe2;
+            iHb = pack_rel(a - gep, base_lo, base_hi);
+            iEb = iHb - goe2;
+          } else {
+            iHa = ((uint32_t)(nba.x - base_lo) & 0xffffu) | ((uint32_t)(nba.y - base_hi) << 16);
+            iEa = ((uint32_t)(nba.z - base_lo) & 0xffffu) | ((uint32_t)(nba.w - base_hi) << 16);
+            iHb = ((uint32_t)(nbb.x - base_lo) & 0xffffu) | ((uint32_t)(nbb.y - base_hi) << 16);
+            iEb = ((uint32_t)(nbb.z - base_lo) & 0xffffu) | ((uint32_t)(nbb.w - base_hi) << 16);
+          }
+          if (s + 1 < npairs_rows) {
+            const uint32_t r2 = ra + 2;
+            nlet = (uint32_t)sq[r2 - 1] | ((r2 < m ? (uint32_t)sq[r2] : 0u) << 8);
+            if (!firstp) {
+              nba = bnd[r2];
+              nbb = bnd[r2 + 1];
+            }
+          }
+        }
+        const int32_t ps = (int32_t)s - lane;
+        const bool active = ps >= 0 && (uint32_t)ps < npairs_rows;
+        olet = let;
+        if (active) {
+          const uint32_t ra = 2 * (uint32_t)ps + 1;
+          const uint32_t* prow_a = myprof + (let & 0xffu) * PW;
+          if (ra == m) {
+            // ---- last row of an odd-length subject ------------------------------------------------
+            uint32_t E = iEa;
+            uint32_t t = hdiag + prow_a[0];
+            hdiag = iHa;
+#pragma unroll
+            for (int c = 0; c < KW; ++c) {
+              uint32_t tn = 0;
+              if (c + 1 < KW) tn = H[c] + prow_a[(c + 1) * 32];
+              const uint32_t h = __vimax3_u16x2(t, E, F[c]);
+              H[c] = h;
+              const uint32_t hg = h - goe2;
+              E = __viaddmax_u16x2(E, nge, hg);
+              F[c] = __viaddmax_u16x2(F[c], nge, hg);
+              t = tn;
+            }
+            oHa = H[KW - 1];
+            oEa = E;
+            if (lane == 31 && !lastp)
+              bnd[ra] = make_int4((int32_t)(oHa & 0xffffu) + base_lo, (int32_t)(oHa >> 16) + base_hi,
+                                  (int32_t)(oEa & 0xffffu) + base_lo, (int32_t)(oEa >> 16) + base_hi);
+          } else {
+            // ---- rows ra (A) and ra+1 (B), B one column behind A ------------------------------------
+            const uint32_t* prow_b = myprof + ((let >> 8) & 0xffu) * PW;
+            uint32_t Ea = iEa, Eb = iEb;
+            uint32_t ta = hdiag + prow_a[0];
+            uint32_t tb = iHa + prow_b[0];
+            hdiag = iHb;
+            uint32_t ha_last = 0;
+#pragma unroll
+            for (int c = 0; c <= KW; ++c) {
+              if (c < KW) {
+                uint32_t tn = 0;
+                if (c + 1 < KW) tn = H[c] + prow_a[(c + 1) * 32];
+                const uint32_t h = __vimax3_u16x2(ta, Ea, F[c]);
+                H[c] = h;
+                const uint32_t hg = h - goe2;
+                Ea = __viaddmax_u16x2(Ea, nge, hg);
+                F[c] = __viaddmax_u16x2(F[c], nge, hg);
+                ta = tn;
+                if (c == KW - 1) ha_last = h;
+              }
+              if (c >= 1) {
+                uint32_t tn = 0;
+                if (c < KW) tn = H[c - 1] + prow_b[c * 32];
+                const uint32_t h = __vimax3_u16x2(tb, Eb, F[c - 1]);
+                H[c - 1] = h;
+                const uint32_t hg = h - goe2;
+                Eb = __viaddmax_u16x2(Eb, nge, hg);
+                F[c - 1] = __viaddmax_u16x2(F[c - 1], nge, hg);
+                tb = tn;
+              }
+            }
+            oHa = ha_last; oEa = Ea; oHb = H[KW - 1]; oEb = Eb;
+            if (lane == 31 && !lastp) {
+              bnd[ra] = make_int4((int32_t)(oHa & 0xffffu) + base_lo, (int32_t)(oHa >> 16) + base_hi,
+                                  (int32_t)(oEa & 0xffffu) + base_lo, (int32_t)(oEa >> 16) + base_hi);
+              bnd[ra + 1] = make_int4((int32_t)(oHb & 0xffffu) + base_lo, (int32_t)(oHb >> 16) + base_hi,
+                                      (int32_t)(oEb & 0xffffu) + base_lo, (int32_t)(oEb >> 16) + base_hi);
+            }
+          }
+          // ---- the lane's last row pair: H(m, n) of a query that ends in this block, as absolute ------
+          if ((uint32_t)ps + 1 == npairs_rows) {
+            if (pass == pass1) {
+              const int32_t c1 = (int32_t)n1 - 1 - col0;
+              if (c1 >= 0 && c1 < KW) {
+#pragma unroll
+                for (int c = 0; c < KW; ++c)
+                  if (c == c1) res_lo = (int32_t)(H[c] & 0xffffu) + base_lo;
+              }
+            }
+            if (lastp) {
+              const int32_t c2 = (int32_t)n2 - 1 - col0;
+              if (c2 >= 0 && c2 < KW) {
+#pragma unroll
+                for (int c = 0; c < KW; ++c)
+                  if (c == c2) res_hi = (int32_t)(H[c] >> 16) + base_hi;
+              }
+            }
+          }
+        }
+        // ---- re-centre the base on lane 16's first column (all lanes, uniform) ----------------------
+        if ((s & (RB - 1)) == RB - 1 && s < npairs_rows) {
+          const uint32_t ref = __shfl_sync(0xffffffffu, H[0], 16);
+          const int32_t sh_lo = (int32_t)(ref & 0xffffu) - CENTER;
+          const int32_t sh_hi = (int32_t)(ref >> 16) - CENTER;
+          const uint32_t shift2 = (uint32_t)(sh_hi * 65536 + sh_lo);
+#pragma unroll
+          for (int c = 0; c < KW; ++c) {
+            H[c] -= shift2;
+            F[c] -= shift2;
+          }
+          hdiag -= shift2;
+          oHa -= shift2; oEa -= shift2; oHb -= shift2; oEb -= shift2;
+          base_lo += sh_lo;
+          base_hi += sh_hi;
+        }
+      }
+      __syncwarp();
+    }
+    // results live in the lanes that own column n1 / n2
+    const int own1 = (int)(((n1 - 1) % PW) / KW), own2 = (int)(((n2 - 1) % PW) / KW);
+    res_lo = __shfl_sync(0xffffffffu, res_lo, own1);
+    res_hi = __shfl_sync(0xffffffffu, res_hi, own2);
+    if (lane == 0) {
+      p.out[tri_index(tk.x, tk.z, p.n_total)] = res_lo - p.delta * (int32_t)(m + n1);
+      if (tk.y != tk.x) p.out[tri_index(tk.y, tk.z, p.n_total)] = res_hi - p.delta * (int32_t)(m + n2);
+    }
+  }
+}
+
+}  // namespace tsq
