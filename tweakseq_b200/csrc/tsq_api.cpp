@@ -233,6 +233,14 @@ bool fits16(const tsq_ctx* c, uint32_t lpad) {
   return hi <= 65535;
 }
 
+// The packed wavefront kernel (wave16.cuh) is exact while the cells a warp holds at one time span
+// less than 2^15 score units: window = cells in flight x per-step Lipschitz bound of the skewed DP.
+bool wave16_ok(const tsq_ctx* c, int nsym, uint32_t flags) {
+  if (flags & TSQ_FLAG_NO_WAVE16) return false;
+  const long long lip = std::max(std::abs(c->smax), std::abs(c->smin)) + c->go + c->ge + 2 * c->delta;
+  return tsq::w16_window((uint32_t)nsym, lip) <= 30000;
+}
+
 // Largest sequence length the packed kernel can take (binary search on the range bound).
 uint32_t max_len16_of(const tsq_ctx* c) {
   uint32_t a = 0, b = 60000;
@@ -244,16 +252,17 @@ uint32_t max_len16_of(const tsq_ctx* c) {
 }
 
 // Contiguous partition of the sorted rows over `world` ranks, balanced by weighted DP cells
-// (cells of the 32-bit kernel count twice: one alignment per DPX lane instead of two).  Rows
+// (regime-2 cells weigh w2: 1.5 for the packed wavefront kernel, 2.4 for the 32-bit one --
+// measured 9.2 : 6.1 : 3.7 TCUPS).  Rows
 // of the packed kernel come in pairs (lo+2q, lo+2q+1), so cuts inside [lo, hi) fall on pair
 // boundaries.  first_row has world+1 entries.
 void plan_rows(const std::vector<uint32_t>& lens, uint32_t lo, uint32_t hi, int world,
-               std::vector<uint32_t>& first_row) {
+               std::vector<uint32_t>& first_row, double w2 = 1.5) {
   const uint32_t n = (uint32_t)lens.size();
   std::vector<double> rowcost(n, 0.0);
   double s16 = 0, s32 = 0, tot = 0;  // suffix sums of lengths below / at-or-above hi
   for (uint32_t i = n; i-- > 0;) {
-    rowcost[i] = (double)lens[i] * (i < hi ? s16 + 2.0 * s32 : 2.0 * s32);
+    rowcost[i] = (double)lens[i] * (i < hi ? s16 + w2 * s32 : w2 * s32);
     tot += rowcost[i];
     if (i < hi) s16 += lens[i]; else s32 += lens[i];
   }
@@ -460,14 +469,14 @@ int tsq_upload(tsq_ctx* c) {
     if (l > 0x7fffffffu) return fail(c, TSQ_ERR_RANGE, "sequence too long");
     c->lens[i] = (uint32_t)l;
     c->loff[i] = (uint32_t)total;
-    total += l;
+    total += (l + 15) & ~(size_t)15;   // 16-byte aligned starts: TMA bulk copies read tiles from here
     if (c->perm[i] != i) c->identity = false;
   }
   if (total > 0xfffffff0ull) return fail(c, TSQ_ERR_RANGE, "more than 4 Gi residues");
   c->loff[n] = (uint32_t)total;
-  TSQ_CUDA(c, c->lin.reserve(total + 16));
-  c->lin_size = total + 16;
-  memset(c->lin.p + total, 0, 16);
+  TSQ_CUDA(c, c->lin.reserve(total + 2048));   // slack: the last TMA tile of a subject may run past its end
+  c->lin_size = total + 2048;
+  memset(c->lin.p, 0, c->lin_size);
   c->self_sorted.resize(n);
   c->self_orig.resize(n);
   for (uint32_t i = 0; i < n; i++) {
@@ -495,7 +504,8 @@ int tsq_upload(tsq_ctx* c) {
   // ---- partition of the sorted rows across ranks (contiguous, balanced by DP cells) ---------
   const int world = c->prm.part_world, rank = c->prm.part_rank;
   std::vector<uint32_t> first_row;
-  plan_rows(c->lens, lo, hi, world, first_row);
+  c->use_w16 = wave16_ok(c, c->nsym, c->prm.flags);
+  plan_rows(c->lens, lo, hi, world, first_row, c->use_w16 ? 1.5 : 2.4);
   auto boundary = [&](int r) -> uint32_t { return first_row[(size_t)r]; };
   c->row_a = boundary(rank);
   c->row_b = boundary(rank + 1);
@@ -534,11 +544,6 @@ int tsq_upload(tsq_ctx* c) {
   c->cells32 = 0;
   c->pairs32.clear();
   c->tasks16w.clear();
-  {
-    // the packed wavefront kernel is exact while the cells a warp holds span < 2^15 score units
-    const long long lip = std::max(std::abs(c->smax), std::abs(c->smin)) + c->go + c->ge + 2 * c->delta;
-    c->use_w16 = !(c->prm.flags & TSQ_FLAG_NO_WAVE16) && tsq::w16_window((uint32_t)c->nsym, lip) <= 30000;
-  }
   if (hi < n) {
     const uint32_t ra = std::max(c->row_a, lo);
     if (c->use_w16) {
@@ -648,7 +653,7 @@ int tsq_upload(tsq_ctx* c) {
   TSQ_CUDA(c, c->d_self.reserve(n + 1));
   TSQ_CUDA(c, c->d_sbias.reserve(sbias.size()));
   TSQ_CUDA(c, c->d_prefix.reserve(c->task_prefix.size()));
-  TSQ_CUDA(c, c->d_counter.reserve(4));
+  TSQ_CUDA(c, c->d_counter.reserve(16));
   TSQ_CUDA(c, c->d_sorted.reserve(npairs));
   if (c->dbw_size) TSQ_CUDA(c, cudaMemcpyAsync(c->d_dbw.p, c->dbw.p, c->dbw_size * 4, cudaMemcpyHostToDevice, s));
   TSQ_CUDA(c, cudaMemcpyAsync(c->d_goff.p, c->goff.data(), c->goff.size() * 4, cudaMemcpyHostToDevice, s));
@@ -746,7 +751,7 @@ int tsq_compute(tsq_ctx* c) {
     if ((unsigned long long)grid > need) grid = (int)need;
     const uint32_t bnd_rows = c->lens[c->n - 1] + 8;
     TSQ_CUDA(c, c->d_bnd16w.reserve((size_t)grid * warps_per_cta * bnd_rows));
-    TSQ_CUDA(c, cudaMemsetAsync(c->d_counter.p + 2, 0, sizeof(unsigned long long), s));
+    TSQ_CUDA(c, cudaMemsetAsync(c->d_counter.p + 2, 0, 12 * sizeof(unsigned long long), s));
     tsq::W16Params w{};
     w.lin = c->d_lin.p;
     w.loff = c->d_loff.p;
@@ -989,7 +994,7 @@ int tsq_plan_partition(const tsq_params* params, const uint32_t* lengths, uint32
   uint32_t hi = lo;
   while (hi < n && lens[hi] <= max16) hi++;
   std::vector<uint32_t> first_row;
-  plan_rows(lens, lo, hi, world, first_row);
+  plan_rows(lens, lo, hi, world, first_row, wave16_ok(&tmp, nsym, p.flags) ? 1.5 : 2.4);
   const uint64_t npairs = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
   auto start_of = [&](uint32_t row) -> uint64_t { return (n >= 2 && row + 1 < n) ? tri(row, row + 1, n) : npairs; };
   for (int r = 0; r < world; r++) {

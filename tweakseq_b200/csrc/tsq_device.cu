@@ -129,7 +129,8 @@ bool w16_variant(uint32_t nsym, W32Launch* out) {
     }
   }
   const size_t sbsz = ((size_t)(nsym + 1) * nsym + 31) & ~(size_t)31;
-  v.smem = (sbsz + (size_t)(v.tpb / 32) * nsym * 32 * v.KW) * sizeof(uint32_t);
+  v.smem = (sbsz + (size_t)(v.tpb / 32) * nsym * 32 * v.KW) * sizeof(uint32_t) +
+           (size_t)(v.tpb / 32) * (2 * 1024 + 16);  // + two 1 KB TMA subject tiles and 2 mbarriers per warp
   if (out) *out = v;
   return true;
 }

@@ -22,6 +22,10 @@
 // delta*(i+j) so that substitution scores are non-negative and the two plain adds of a cell
 // cannot carry between the halves; the skew is just part of what base tracks.
 //
+// The subject sequence is streamed through shared memory in 1 KB tiles by TMA bulk copies
+// (cp.async.bulk + mbarrier, tma_stage.cuh) into a two-slot ring per warp; every lane reads its own
+// two letters per step from the ring, so no letter travels by shuffle.
+//
 // Spec: SURVEY.md section 8c.  Exactness is tested bit for bit against the oracle and against
 // wave32 (tests/test_gpu_parity.py).
 #pragma once
@@ -29,6 +33,7 @@
 #include <cuda_runtime.h>
 
 #include "gotoh16.cuh"
+#include "tma_stage.cuh"
 
 namespace tsq {
 
@@ -61,6 +66,7 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
   constexpr int PW = 32 * KW;        // columns per pass
   constexpr uint32_t RB = 32;        // re-centre the base every RB steps (2*RB rows)
   constexpr int32_t CENTER = 32768;
+  constexpr uint32_t TILE = 1024;    // subject bytes per TMA tile (two tiles per warp)
   extern __shared__ uint32_t smem16[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -68,6 +74,16 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
   const uint32_t sbsz = (nsym + 1) * nsym;
   uint32_t* sb = smem16;
   uint32_t* prof = smem16 + ((sbsz + 31) & ~31u) + (size_t)wib * nsym * PW;
+  // after the profiles: per warp two 1 KB subject tiles and their two mbarriers
+  uint8_t* const tile_base = reinterpret_cast<uint8_t*>(smem16 + ((sbsz + 31) & ~31u) + (size_t)(TPB / 32) * nsym * PW);
+  uint8_t* const stile = tile_base + (size_t)wib * (2 * TILE + 16);
+  uint64_t* const tbar = reinterpret_cast<uint64_t*>(stile + 2 * TILE);
+  uint32_t tph0 = 0, tph1 = 0;       // phase parity of the two tile barriers (warp-uniform)
+  if (lane == 0) {
+    mbar_init(&tbar[0], 1);
+    mbar_init(&tbar[1], 1);
+    fence_mbar_init();
+  }
   for (uint32_t i = threadIdx.x; i < sbsz; i += TPB) sb[i] = p.sbias[i];
   __syncthreads();
 
@@ -120,26 +136,63 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
       }
       uint32_t hdiag = pack_rel(col0 == 0 ? 0 : -go - col0 * gep, base_lo, base_hi);
 
-      uint32_t oHa = 0, oEa = 0, oHb = 0, oEb = 0, olet = 0;  // handed to the right neighbour
+      uint32_t oHa = 0, oEa = 0, oHb = 0, oEb = 0;  // handed to the right neighbour
       int4 nba = make_int4(0, 0, 0, 0), nbb = make_int4(0, 0, 0, 0);
-      uint32_t nlet = 0;
+      // ---- subject tiles: 2 x 1 KB ring in shared memory, filled by TMA bulk copies ----------------
+      // Tile k covers rows [1024k, 1024k+1024) and lives in ring slot k & 1.  All tile bookkeeping is
+      // WARP-UNIFORM (it depends on the step counter only): every lane polls the mbarrier, one
+      // elected lane issues the copies.  (A wait loop inside a one-lane branch makes ptxas treat the
+      // warp as possibly divergent at the shuffles below and route them through the slow
+      // WARPSYNC.COLLECTIVE path: measured 1.8x slower.)  Every lane then reads its own two letters
+      // per step straight from the ring: lane l, step s -> bytes 2(s-l), 2(s-l)+1.
+      const uint32_t ntiles = (m + TILE - 1) / TILE;
       if (lane == 0) {
-        nlet = (uint32_t)sq[0] | ((m > 1 ? (uint32_t)sq[1] : 0u) << 8);
+        fence_proxy_async_smem();
+        mbar_arrive_expect_tx(&tbar[0], TILE);
+        bulk_copy_g2s(stile, sq, TILE, &tbar[0]);
+        if (ntiles > 1) {
+          mbar_arrive_expect_tx(&tbar[1], TILE);
+          bulk_copy_g2s(stile + TILE, sq + TILE, TILE, &tbar[1]);
+        }
         if (!firstp) {
           nba = bnd[1];
           nbb = bnd[2];
         }
       }
+      mbar_wait_warp(&tbar[0], tph0);
+      tph0 ^= 1u;
+      // letters of this lane's step 0 (lanes > 0 start later and re-read in time)
+      uint32_t nlet = *reinterpret_cast<const uint16_t*>(stile + ((0u - 2u * (uint32_t)lane) & (2 * TILE - 1)));
       const uint32_t nsteps = npairs_rows + 31;
       for (uint32_t s = 0; s < nsteps; ++s) {
         uint32_t iHa = __shfl_up_sync(0xffffffffu, oHa, 1);
         uint32_t iEa = __shfl_up_sync(0xffffffffu, oEa, 1);
         uint32_t iHb = __shfl_up_sync(0xffffffffu, oHb, 1);
         uint32_t iEb = __shfl_up_sync(0xffffffffu, oEb, 1);
-        uint32_t let = __shfl_up_sync(0xffffffffu, olet, 1);
+        const uint32_t let = nlet;
+        // ---- tile ring upkeep for the next step (uniform) ------------------------------------------
+        {
+          const uint32_t s1 = s + 1;                 // lane 0 reads bytes 2*s1, 2*s1+1 next step
+          if ((s1 & (TILE / 2 - 1)) == 0) {          // lane 0 enters tile s1 / 512
+            const uint32_t tix = s1 / (TILE / 2);
+            if (tix < ntiles) {
+              if (tix & 1u) { mbar_wait_warp(&tbar[1], tph1); tph1 ^= 1u; }
+              else          { mbar_wait_warp(&tbar[0], tph0); tph0 ^= 1u; }
+            }
+          }
+          if ((s & (TILE / 2 - 1)) == 32 && s >= TILE / 2) {   // lane 31 has left tile tix-1: refill its slot
+            const uint32_t tix = s / (TILE / 2);
+            if (tix + 1 < ntiles && lane == 0) {
+              fence_proxy_async_smem();
+              uint64_t* br = &tbar[(tix + 1) & 1u];
+              mbar_arrive_expect_tx(br, TILE);
+              bulk_copy_g2s(stile + ((tix + 1) & 1u) * TILE, sq + (size_t)(tix + 1) * TILE, TILE, br);
+            }
+          }
+          nlet = *reinterpret_cast<const uint16_t*>(stile + ((2u * (s1 - (uint32_t)lane)) & (2 * TILE - 1)));
+        }
         if (lane == 0) {
           const uint32_t ra = 2 * s + 1;
-          let = nlet;
           if (firstp) {  // A(i,0) = -go - i*ge'; E entering column 1 = A(i,0) - goe'
             const int32_t a = -go - (int32_t)ra * gep;
             iHa = pack_rel(a, base_lo, base_hi);
@@ -151,19 +204,14 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
             iEa = ((uint32_t)(nba.z - base_lo) & 0xffffu) | ((uint32_t)(nba.w - base_hi) << 16);
             iHb = ((uint32_t)(nbb.x - base_lo) & 0xffffu) | ((uint32_t)(nbb.y - base_hi) << 16);
             iEb = ((uint32_t)(nbb.z - base_lo) & 0xffffu) | ((uint32_t)(nbb.w - base_hi) << 16);
-          }
-          if (s + 1 < npairs_rows) {
-            const uint32_t r2 = ra + 2;
-            nlet = (uint32_t)sq[r2 - 1] | ((r2 < m ? (uint32_t)sq[r2] : 0u) << 8);
-            if (!firstp) {
-              nba = bnd[r2];
-              nbb = bnd[r2 + 1];
+            if (s + 1 < npairs_rows) {
+              nba = bnd[ra + 2];
+              nbb = bnd[ra + 3];
             }
           }
         }
         const int32_t ps = (int32_t)s - lane;
         const bool active = ps >= 0 && (uint32_t)ps < npairs_rows;
-        olet = let;
         if (active) {
           const uint32_t ra = 2 * (uint32_t)ps + 1;
           const uint32_t* prow_a = myprof + (let & 0xffu) * PW;
