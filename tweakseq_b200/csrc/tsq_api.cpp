@@ -152,7 +152,7 @@ struct tsq_ctx {
   DevBuf<uint2> d_bnd;
   DevBuf<uint2> d_pairs32;
   DevBuf<uint4> d_tasks16w;
-  DevBuf<int4> d_bnd16w;
+  DevBuf<uint2> d_bnd16w;
   DevBuf<int2> d_bnd32;
   DevBuf<int32_t> d_smat;
   // host results
@@ -750,7 +750,7 @@ int tsq_compute(tsq_ctx* c) {
     const unsigned long long need = (c->tasks16w.size() + warps_per_cta - 1) / warps_per_cta;
     if ((unsigned long long)grid > need) grid = (int)need;
     const uint32_t bnd_rows = c->lens[c->n - 1] + 8;
-    TSQ_CUDA(c, c->d_bnd16w.reserve((size_t)grid * warps_per_cta * bnd_rows));
+    TSQ_CUDA(c, c->d_bnd16w.reserve((size_t)grid * warps_per_cta * ((size_t)bnd_rows + bnd_rows / 4 + 16)));
     TSQ_CUDA(c, cudaMemsetAsync(c->d_counter.p + 2, 0, 12 * sizeof(unsigned long long), s));
     tsq::W16Params w{};
     w.lin = c->d_lin.p;

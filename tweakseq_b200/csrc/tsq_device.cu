@@ -138,7 +138,7 @@ bool w16_variant(uint32_t nsym, W32Launch* out) {
 long long w16_window(uint32_t nsym, long long lipschitz) {
   W32Launch v;
   if (!w16_variant(nsym, &v)) return 1ll << 40;
-  return (32ll * v.KW + 2 * 31 + 2 * 32 + 16) * lipschitz;  // RB = 32 steps between re-centrings
+  return (32ll * v.KW + 4 * 31 + 4 * 16 + 16) * lipschitz;  // 4 rows per step, RB = 16 steps between re-centrings
 }
 
 cudaError_t w16_launch(int grid, const W16Params& p, cudaStream_t stream) {

@@ -1,24 +1,25 @@
 // wave16.cuh -- regime 2, packed: intra-task anti-diagonal wavefront Gotoh kernel with two
 // alignments per 32-bit word (u16x2 DPX) and a moving base, sm_100a.
 //
-// Same wavefront as wave32.cuh (one warp per task, lane l owns KW adjacent columns, two rows per
-// lane per step, right edges handed to lane l+1 by warp shuffle), but a task is TWO queries
+// Same wavefront as wave32.cuh (one warp per task, lane l owns KW adjacent columns, right edges
+// handed to lane l+1 by warp shuffle; here FOUR rows -- two interleaved row pairs -- per lane per
+// step, which halves the per-step hand-off overhead per cell), but a task is TWO queries
 // (A1, A2, along the columns, one per 16-bit half) against one long subject (along the rows), so
 // every DPX instruction advances two alignments -- what the packed inter-task kernel
 // (gotoh16.cuh) does for sequences short enough to fit 16 bits outright.
 //
 // Long sequences do not fit 16 bits (|H| reaches 10^5), but the CELLS A WARP HOLDS AT ONE TIME do:
 // by the Lipschitz property of alignment matrices (|H(i,j)-H(i,j-1)|, |H(i,j)-H(i-1,j)| <=
-// max S + go + ge), everything in flight -- 32*KW columns by ~62+2R rows -- lies within a window
-// D = (32*KW + 2*31 + 2*R + 16) * L of one reference cell, and E, F lie within go+ge of an H.
+// max S + go + ge), everything in flight -- 32*KW columns by ~124+4R rows -- lies within a window
+// D = (32*KW + 4*31 + 4*R + 16) * L of one reference cell, and E, F lie within go+ge of an H.
 // The kernel therefore stores v - base(half) in unsigned 16 bits, where base is a warp-uniform
 // 32-bit number per half that is re-centred every R steps on a reference cell (lane 16's first
 // column): all live registers are shifted by the same packed constant, base absorbs the shift.
 // max() and +constant commute with a uniform shift, so the arithmetic is exactly the 32-bit
 // recurrence as long as nothing leaves [0, 65535]; the host only selects this kernel when
 // D <= 30000 (tsq_api.cpp: wave16_ok) and falls back to wave32 otherwise.  Values that cross a
-// pass boundary (lane 31 -> memory -> lane 0 of the next pass) and the final scores are
-// converted to absolute 32-bit numbers.  As in gotoh16.cuh the stored value is skewed by
+// pass boundary (lane 31 -> memory -> lane 0 of the next pass) are stored relative together with the
+// base in force (one base pair per step) and re-based on load; final scores are made absolute.  As in gotoh16.cuh the stored value is skewed by
 // delta*(i+j) so that substitution scores are non-negative and the two plain adds of a cell
 // cannot carry between the halves; the skew is just part of what base tracks.
 //
@@ -43,7 +44,8 @@ struct W16Params {
   const uint32_t* lens;        // sorted lengths
   const uint4* tasks;          // (i1, i2, j, 0): queries i1 <= i2 (i2 == i1: single), subject j
   unsigned long long* counter; // dynamic task cursor
-  int4* bnd;                   // pass boundary scratch: [warp slot][row] (H_lo, H_hi, E_lo, E_hi) absolute
+  uint2* bnd;                  // pass boundary scratch per warp slot: [bnd_rows] rows of (H, E) packed
+                               // relative, then [bnd_rows/4 + 16] (base_lo, base_hi) per step
   const uint32_t* sbias;       // (nsym+1) x nsym biased scores S' = S + 2*delta (row nsym = 0)
   int32_t* out;                // scores, packed upper triangle in sorted order
   unsigned long long ntasks;
@@ -64,9 +66,10 @@ __device__ __forceinline__ uint32_t pack_rel(int32_t a, int32_t base_lo, int32_t
 template <int KW, int TPB, int MINB, uint32_t NGE>
 __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant__ W16Params p) {
   constexpr int PW = 32 * KW;        // columns per pass
-  constexpr uint32_t RB = 32;        // re-centre the base every RB steps (2*RB rows)
+  constexpr uint32_t RB = 16;        // re-centre the base every RB steps (4*RB rows)
   constexpr int32_t CENTER = 32768;
   constexpr uint32_t TILE = 1024;    // subject bytes per TMA tile (two tiles per warp)
+  constexpr uint32_t TSTEPS = TILE / 4;  // steps of lane 0 per tile (4 rows per step)
   extern __shared__ uint32_t smem16[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -88,10 +91,13 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
   __syncthreads();
 
   const uint32_t gw = blockIdx.x * (TPB / 32) + wib;
-  int4* const bnd = p.bnd + (size_t)gw * p.bnd_rows;
+  const size_t slot = (size_t)p.bnd_rows + p.bnd_rows / 4 + 16;
+  uint2* const brow = p.bnd + (size_t)gw * slot;                               // (H, E) per row
+  int2* const bbase = reinterpret_cast<int2*>(brow + p.bnd_rows);              // (base_lo, base_hi) per step
   const uint32_t nge = NGE ? NGE : p.negge2;
   const int32_t go = p.go, gep = p.gep, goep = p.goep;
   const uint32_t goe2 = (uint32_t)goep * 0x10001u;
+  const uint32_t gep2 = (uint32_t)gep * 0x10001u;
 
   for (;;) {
     unsigned long long task = 0;
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
     const uint8_t* sq = p.lin + p.loff[tk.z];
     const uint32_t npass = (n2 + PW - 1) / PW;
     const uint32_t pass1 = (n1 - 1) / PW;   // pass in which query 1 ends
-    const uint32_t npairs_rows = (m + 1) / 2;
+    const uint32_t nquads = (m + 3) / 4;    // steps per lane: four rows each
     int32_t res_lo = 0, res_hi = 0;
 
     for (uint32_t pass = 0; pass < npass; ++pass) {
@@ -135,16 +141,19 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
         F[c] = H[c] - goe2;
       }
       uint32_t hdiag = pack_rel(col0 == 0 ? 0 : -go - col0 * gep, base_lo, base_hi);
+      // first pass: column 0 of the matrix, A(r,0) = -go - r*ge', kept packed and relative for row 4s+1
+      uint32_t colH = pack_rel(-go - gep, base_lo, base_hi);
 
-      uint32_t oHa = 0, oEa = 0, oHb = 0, oEb = 0;  // handed to the right neighbour
-      int4 nba = make_int4(0, 0, 0, 0), nbb = make_int4(0, 0, 0, 0);
+      uint32_t oH[2][2] = {{0u, 0u}, {0u, 0u}}, oE[2][2] = {{0u, 0u}, {0u, 0u}};  // to the right neighbour
+      uint2 nb[4] = {make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u)};
+      int2 nbase = make_int2(0, 0);
       // ---- subject tiles: 2 x 1 KB ring in shared memory, filled by TMA bulk copies ----------------
       // Tile k covers rows [1024k, 1024k+1024) and lives in ring slot k & 1.  All tile bookkeeping is
       // WARP-UNIFORM (it depends on the step counter only): every lane polls the mbarrier, one
       // elected lane issues the copies.  (A wait loop inside a one-lane branch makes ptxas treat the
       // warp as possibly divergent at the shuffles below and route them through the slow
-      // WARPSYNC.COLLECTIVE path: measured 1.8x slower.)  Every lane then reads its own two letters
-      // per step straight from the ring: lane l, step s -> bytes 2(s-l), 2(s-l)+1.
+      // WARPSYNC.COLLECTIVE path: measured 1.8x slower.)  Every lane then reads its own four letters
+      // per step straight from the ring: lane l, step s -> bytes 4(s-l) .. 4(s-l)+3.
       const uint32_t ntiles = (m + TILE - 1) / TILE;
       if (lane == 0) {
         fence_proxy_async_smem();
@@ -155,33 +164,29 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
           bulk_copy_g2s(stile + TILE, sq + TILE, TILE, &tbar[1]);
         }
         if (!firstp) {
-          nba = bnd[1];
-          nbb = bnd[2];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) nb[k] = brow[1 + k];
+          nbase = bbase[0];
         }
       }
       mbar_wait_warp(&tbar[0], tph0);
       tph0 ^= 1u;
-      // letters of this lane's step 0 (lanes > 0 start later and re-read in time)
-      uint32_t nlet = *reinterpret_cast<const uint16_t*>(stile + ((0u - 2u * (uint32_t)lane) & (2 * TILE - 1)));
-      const uint32_t nsteps = npairs_rows + 31;
+      uint32_t nlet = *reinterpret_cast<const uint32_t*>(stile + ((0u - 4u * (uint32_t)lane) & (2 * TILE - 1)));
+      const uint32_t nsteps = nquads + 31;
       for (uint32_t s = 0; s < nsteps; ++s) {
-        uint32_t iHa = __shfl_up_sync(0xffffffffu, oHa, 1);
-        uint32_t iEa = __shfl_up_sync(0xffffffffu, oEa, 1);
-        uint32_t iHb = __shfl_up_sync(0xffffffffu, oHb, 1);
-        uint32_t iEb = __shfl_up_sync(0xffffffffu, oEb, 1);
-        const uint32_t let = nlet;
+        const uint32_t let4 = nlet;
         // ---- tile ring upkeep for the next step (uniform) ------------------------------------------
         {
-          const uint32_t s1 = s + 1;                 // lane 0 reads bytes 2*s1, 2*s1+1 next step
-          if ((s1 & (TILE / 2 - 1)) == 0) {          // lane 0 enters tile s1 / 512
-            const uint32_t tix = s1 / (TILE / 2);
+          const uint32_t s1 = s + 1;                 // lane 0 reads bytes 4*s1 .. 4*s1+3 next step
+          if ((s1 & (TSTEPS - 1)) == 0) {            // lane 0 enters tile s1 / TSTEPS
+            const uint32_t tix = s1 / TSTEPS;
             if (tix < ntiles) {
               if (tix & 1u) { mbar_wait_warp(&tbar[1], tph1); tph1 ^= 1u; }
               else          { mbar_wait_warp(&tbar[0], tph0); tph0 ^= 1u; }
             }
           }
-          if ((s & (TILE / 2 - 1)) == 32 && s >= TILE / 2) {   // lane 31 has left tile tix-1: refill its slot
-            const uint32_t tix = s / (TILE / 2);
+          if ((s & (TSTEPS - 1)) == 32 && s >= TSTEPS) {   // lane 31 has left tile tix-1: refill its slot
+            const uint32_t tix = s / TSTEPS;
             if (tix + 1 < ntiles && lane == 0) {
               fence_proxy_async_smem();
               uint64_t* br = &tbar[(tix + 1) & 1u];
@@ -189,115 +194,125 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
               bulk_copy_g2s(stile + ((tix + 1) & 1u) * TILE, sq + (size_t)(tix + 1) * TILE, TILE, br);
             }
           }
-          nlet = *reinterpret_cast<const uint16_t*>(stile + ((2u * (s1 - (uint32_t)lane)) & (2 * TILE - 1)));
+          nlet = *reinterpret_cast<const uint32_t*>(stile + ((4u * (s1 - (uint32_t)lane)) & (2 * TILE - 1)));
         }
-        if (lane == 0) {
-          const uint32_t ra = 2 * s + 1;
-          if (firstp) {  // A(i,0) = -go - i*ge'; E entering column 1 = A(i,0) - goe'
-            const int32_t a = -go - (int32_t)ra * gep;
-            iHa = pack_rel(a, base_lo, base_hi);
-            iEa = iHa - goe2;
-            iHb = pack_rel(a - gep, base_lo, base_hi);
-            iEb = iHb - goe2;
-          } else {
-            iHa = ((uint32_t)(nba.x - base_lo) & 0xffffu) | ((uint32_t)(nba.y - base_hi) << 16);
-            iEa = ((uint32_t)(nba.z - base_lo) & 0xffffu) | ((uint32_t)(nba.w - base_hi) << 16);
-            iHb = ((uint32_t)(nbb.x - base_lo) & 0xffffu) | ((uint32_t)(nbb.y - base_hi) << 16);
-            iEb = ((uint32_t)(nbb.z - base_lo) & 0xffffu) | ((uint32_t)(nbb.w - base_hi) << 16);
-            if (s + 1 < npairs_rows) {
-              nba = bnd[ra + 2];
-              nbb = bnd[ra + 3];
-            }
+        // ---- lane 0's left boundary of this step's four rows (computed by all lanes, uniform code) ----
+        uint32_t lH[4], lE[4];
+        if (firstp) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            lH[k] = colH - (uint32_t)k * gep2;
+            lE[k] = lH[k] - goe2;
+          }
+          colH -= 4u * gep2;
+        } else {
+          const uint32_t d2 = (uint32_t)((nbase.y - base_hi) * 65536 + (nbase.x - base_lo));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            lH[k] = nb[k].x + d2;
+            lE[k] = nb[k].y + d2;
+          }
+          if (lane == 0 && s + 1 < nquads) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) nb[k] = brow[4 * (s + 1) + 1 + k];
+            nbase = bbase[s + 1];
           }
         }
         const int32_t ps = (int32_t)s - lane;
-        const bool active = ps >= 0 && (uint32_t)ps < npairs_rows;
-        if (active) {
-          const uint32_t ra = 2 * (uint32_t)ps + 1;
-          const uint32_t* prow_a = myprof + (let & 0xffu) * PW;
-          if (ra == m) {
-            // ---- last row of an odd-length subject ------------------------------------------------
-            uint32_t E = iEa;
-            uint32_t t = hdiag + prow_a[0];
-            hdiag = iHa;
+        const bool lane_on = ps >= 0 && (uint32_t)ps < nquads;
 #pragma unroll
-            for (int c = 0; c < KW; ++c) {
-              uint32_t tn = 0;
-              if (c + 1 < KW) tn = H[c] + prow_a[(c + 1) * 32];
-              const uint32_t h = __vimax3_u16x2(t, E, F[c]);
-              H[c] = h;
-              const uint32_t hg = h - goe2;
-              E = __viaddmax_u16x2(E, nge, hg);
-              F[c] = __viaddmax_u16x2(F[c], nge, hg);
-              t = tn;
-            }
-            oHa = H[KW - 1];
-            oEa = E;
-            if (lane == 31 && !lastp)
-              bnd[ra] = make_int4((int32_t)(oHa & 0xffffu) + base_lo, (int32_t)(oHa >> 16) + base_hi,
-                                  (int32_t)(oEa & 0xffffu) + base_lo, (int32_t)(oEa >> 16) + base_hi);
-          } else {
-            // ---- rows ra (A) and ra+1 (B), B one column behind A ------------------------------------
-            const uint32_t* prow_b = myprof + ((let >> 8) & 0xffu) * PW;
-            uint32_t Ea = iEa, Eb = iEb;
-            uint32_t ta = hdiag + prow_a[0];
-            uint32_t tb = iHa + prow_b[0];
-            hdiag = iHb;
-            uint32_t ha_last = 0;
+        for (int q = 0; q < 2; ++q) {
+          uint32_t iHa = __shfl_up_sync(0xffffffffu, oH[q][0], 1);
+          uint32_t iEa = __shfl_up_sync(0xffffffffu, oE[q][0], 1);
+          uint32_t iHb = __shfl_up_sync(0xffffffffu, oH[q][1], 1);
+          uint32_t iEb = __shfl_up_sync(0xffffffffu, oE[q][1], 1);
+          if (lane == 0) {
+            iHa = lH[2 * q]; iEa = lE[2 * q]; iHb = lH[2 * q + 1]; iEb = lE[2 * q + 1];
+          }
+          const uint32_t ra = 4 * (uint32_t)ps + 2 * q + 1;
+          if (lane_on && ra <= m) {
+            const uint32_t* prow_a = myprof + ((let4 >> (16 * q)) & 0xffu) * PW;
+            if (ra == m) {
+              // ---- last row of an odd-length subject ----------------------------------------------
+              uint32_t E = iEa;
+              uint32_t t = hdiag + prow_a[0];
+              hdiag = iHa;
 #pragma unroll
-            for (int c = 0; c <= KW; ++c) {
-              if (c < KW) {
+              for (int c = 0; c < KW; ++c) {
                 uint32_t tn = 0;
                 if (c + 1 < KW) tn = H[c] + prow_a[(c + 1) * 32];
-                const uint32_t h = __vimax3_u16x2(ta, Ea, F[c]);
+                const uint32_t h = __vimax3_u16x2(t, E, F[c]);
                 H[c] = h;
                 const uint32_t hg = h - goe2;
-                Ea = __viaddmax_u16x2(Ea, nge, hg);
+                E = __viaddmax_u16x2(E, nge, hg);
                 F[c] = __viaddmax_u16x2(F[c], nge, hg);
-                ta = tn;
-                if (c == KW - 1) ha_last = h;
+                t = tn;
               }
-              if (c >= 1) {
-                uint32_t tn = 0;
-                if (c < KW) tn = H[c - 1] + prow_b[c * 32];
-                const uint32_t h = __vimax3_u16x2(tb, Eb, F[c - 1]);
-                H[c - 1] = h;
-                const uint32_t hg = h - goe2;
-                Eb = __viaddmax_u16x2(Eb, nge, hg);
-                F[c - 1] = __viaddmax_u16x2(F[c - 1], nge, hg);
-                tb = tn;
-              }
-            }
-            oHa = ha_last; oEa = Ea; oHb = H[KW - 1]; oEb = Eb;
-            if (lane == 31 && !lastp) {
-              bnd[ra] = make_int4((int32_t)(oHa & 0xffffu) + base_lo, (int32_t)(oHa >> 16) + base_hi,
-                                  (int32_t)(oEa & 0xffffu) + base_lo, (int32_t)(oEa >> 16) + base_hi);
-              bnd[ra + 1] = make_int4((int32_t)(oHb & 0xffffu) + base_lo, (int32_t)(oHb >> 16) + base_hi,
-                                      (int32_t)(oEb & 0xffffu) + base_lo, (int32_t)(oEb >> 16) + base_hi);
-            }
-          }
-          // ---- the lane's last row pair: H(m, n) of a query that ends in this block, as absolute ------
-          if ((uint32_t)ps + 1 == npairs_rows) {
-            if (pass == pass1) {
-              const int32_t c1 = (int32_t)n1 - 1 - col0;
-              if (c1 >= 0 && c1 < KW) {
+              oH[q][0] = H[KW - 1];
+              oE[q][0] = E;
+              if (lane == 31 && !lastp) brow[ra] = make_uint2(oH[q][0], oE[q][0]);
+            } else {
+              // ---- rows ra (A) and ra+1 (B), B one column behind A ----------------------------------
+              const uint32_t* prow_b = myprof + ((let4 >> (16 * q + 8)) & 0xffu) * PW;
+              uint32_t Ea = iEa, Eb = iEb;
+              uint32_t ta = hdiag + prow_a[0];
+              uint32_t tb = iHa + prow_b[0];
+              hdiag = iHb;
+              uint32_t ha_last = 0;
 #pragma unroll
-                for (int c = 0; c < KW; ++c)
-                  if (c == c1) res_lo = (int32_t)(H[c] & 0xffffu) + base_lo;
+              for (int c = 0; c <= KW; ++c) {
+                if (c < KW) {
+                  uint32_t tn = 0;
+                  if (c + 1 < KW) tn = H[c] + prow_a[(c + 1) * 32];
+                  const uint32_t h = __vimax3_u16x2(ta, Ea, F[c]);
+                  H[c] = h;
+                  const uint32_t hg = h - goe2;
+                  Ea = __viaddmax_u16x2(Ea, nge, hg);
+                  F[c] = __viaddmax_u16x2(F[c], nge, hg);
+                  ta = tn;
+                  if (c == KW - 1) ha_last = h;
+                }
+                if (c >= 1) {
+                  uint32_t tn = 0;
+                  if (c < KW) tn = H[c - 1] + prow_b[c * 32];
+                  const uint32_t h = __vimax3_u16x2(tb, Eb, F[c - 1]);
+                  H[c - 1] = h;
+                  const uint32_t hg = h - goe2;
+                  Eb = __viaddmax_u16x2(Eb, nge, hg);
+                  F[c - 1] = __viaddmax_u16x2(F[c - 1], nge, hg);
+                  tb = tn;
+                }
+              }
+              oH[q][0] = ha_last; oE[q][0] = Ea; oH[q][1] = H[KW - 1]; oE[q][1] = Eb;
+              if (lane == 31 && !lastp) {
+                brow[ra] = make_uint2(oH[q][0], oE[q][0]);
+                brow[ra + 1] = make_uint2(oH[q][1], oE[q][1]);
               }
             }
-            if (lastp) {
-              const int32_t c2 = (int32_t)n2 - 1 - col0;
-              if (c2 >= 0 && c2 < KW) {
+            // ---- the subject's last row: H(m, n) of a query that ends in this block, made absolute ----
+            if (ra + 1 >= m) {
+              if (pass == pass1) {
+                const int32_t c1 = (int32_t)n1 - 1 - col0;
+                if (c1 >= 0 && c1 < KW) {
 #pragma unroll
-                for (int c = 0; c < KW; ++c)
-                  if (c == c2) res_hi = (int32_t)(H[c] >> 16) + base_hi;
+                  for (int c = 0; c < KW; ++c)
+                    if (c == c1) res_lo = (int32_t)(H[c] & 0xffffu) + base_lo;
+                }
+              }
+              if (lastp) {
+                const int32_t c2 = (int32_t)n2 - 1 - col0;
+                if (c2 >= 0 && c2 < KW) {
+#pragma unroll
+                  for (int c = 0; c < KW; ++c)
+                    if (c == c2) res_hi = (int32_t)(H[c] >> 16) + base_hi;
+                }
               }
             }
           }
         }
+        if (lane == 31 && !lastp && lane_on) bbase[ps] = make_int2(base_lo, base_hi);
         // ---- re-centre the base on lane 16's first column (all lanes, uniform) ----------------------
-        if ((s & (RB - 1)) == RB - 1 && s < npairs_rows) {
+        if ((s & (RB - 1)) == RB - 1 && s < nquads) {
           const uint32_t ref = __shfl_sync(0xffffffffu, H[0], 16);
           const int32_t sh_lo = (int32_t)(ref & 0xffffu) - CENTER;
           const int32_t sh_hi = (int32_t)(ref >> 16) - CENTER;
@@ -308,7 +323,11 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
             F[c] -= shift2;
           }
           hdiag -= shift2;
-          oHa -= shift2; oEa -= shift2; oHb -= shift2; oEb -= shift2;
+          colH -= shift2;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            oH[q][0] -= shift2; oE[q][0] -= shift2; oH[q][1] -= shift2; oE[q][1] -= shift2;
+          }
           base_lo += sh_lo;
           base_hi += sh_hi;
         }
