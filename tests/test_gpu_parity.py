@@ -436,3 +436,39 @@ def test_config4_scaled_twin_wavefront_sampled():
     fam = synth.nucleotide(6, 10000, 12000, 4, family=True)     # related genomes: long diagonal runs
     assert_same(fam, alphabet=1)
     assert_same(fam, alphabet=1, flags=t.FLAG_NO_WAVE16)
+
+
+def test_cancel_while_the_kernels_run_stops_early():
+    """'Stop' (SeqEditMainWin.cpp:803-812): the cancel flag is polled by the host while the stream runs
+    and by every warp at each task fetch, so a long job drains within one task instead of finishing."""
+    import threading, time
+    _, seqs = synth.config(3, 0.8)            # 8,000 x 400 aa: ~0.6 s of kernel time
+    flag = C.c_int(0)
+    out = {}
+    with t.Context(flags=t.FLAG_NO_DISTANCES) as ctx:
+        ctx.set_sequences(seqs)
+        ctx.upload()
+        ctx.compute(); ctx.synchronize()
+        full_ms = ctx.stats()["kernel_ms"]
+
+        def work():
+            t0 = time.perf_counter()
+            try:
+                ctx.run(cancel=flag)
+                out["status"] = 0
+            except t.TsqError as e:
+                out["status"] = e.status
+            out["s"] = time.perf_counter() - t0
+
+        th = threading.Thread(target=work)
+        th.start()
+        time.sleep(0.15)
+        flag.value = 1
+        th.join(timeout=60)
+        assert out["status"] == -5
+        assert out["s"] < 0.15 + 0.6 * full_ms / 1e3, (out, full_ms)
+        with pytest.raises(t.TsqError):
+            ctx.scores()
+        flag.value = 0
+        ctx.run(cancel=flag)                      # the context is reusable after a cancel
+        assert len(ctx.scores()) == len(seqs) * (len(seqs) - 1) // 2

@@ -47,6 +47,7 @@ struct G16Params {
   const uint32_t* lens;        // sorted lengths
   const unsigned long long* task_prefix;  // [nq+1] cumulative chunk counts, per query pair
   unsigned long long* counter; // dynamic task cursor
+  const int* cancel;           // host-mapped flag: != 0 makes every warp stop fetching tasks
   uint2* bnd;                  // strip boundary scratch: [warp slot][row][lane] (H, E)
   const uint32_t* sbias;       // (nsym+1) x nsym biased scores S' (row nsym = padding = 0)
   int32_t* out;                // scores, packed upper triangle in sorted order
@@ -97,7 +98,10 @@ __global__ void __launch_bounds__(TPB, MINB) gotoh16_kernel(const __grid_constan
 
   for (;;) {
     unsigned long long task = 0;
-    if (lane == 0) task = atomicAdd(p.counter, 1ULL);
+    if (lane == 0) {
+      task = atomicAdd(p.counter, 1ULL);
+      if (*reinterpret_cast<const volatile int*>(p.cancel) != 0) task = ~0ULL;   // "Stop" pressed
+    }
     task = __shfl_sync(0xffffffffu, task, 0);
     if (task >= p.ntasks) break;
 

@@ -159,6 +159,9 @@ struct tsq_ctx {
   PinnedBuf<int32_t> h_scores;
   PinnedBuf<double> h_dist;
 
+  int* h_cancel = nullptr;   // pinned, device-mapped: set by tsq_run when the caller's flag goes up
+  int* d_cancel = nullptr;
+
   bool have_seqs = false, uploaded = false, computed = false, finalized = false, downloaded = false;
   tsq_stats st{};
 };
@@ -388,6 +391,13 @@ int tsq_create(tsq_ctx** out, const tsq_params* params) {
     delete c;
     return TSQ_ERR_CUDA;
   }
+  if (cudaHostAlloc((void**)&c->h_cancel, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&c->d_cancel, c->h_cancel, 0) != cudaSuccess) {
+    cudaGetLastError();
+    tsq_destroy(c);
+    return TSQ_ERR_CUDA;
+  }
+  *c->h_cancel = 0;
   c->stream = c->own_stream;
   *out = c;
   return TSQ_OK;
@@ -402,6 +412,7 @@ int tsq_destroy(tsq_ctx* c) {
   c->d_sorted.release(); c->d_scores.release(); c->d_dist.release(); c->d_prefix.release();
   c->d_counter.release(); c->d_bnd.release(); c->h_scores.release(); c->h_dist.release();
   c->lin.release(); c->dbw.release(); c->d_pairs32.release(); c->d_tasks16w.release(); c->d_bnd16w.release(); c->d_bnd32.release(); c->d_smat.release();
+  if (c->h_cancel) cudaFreeHost(c->h_cancel);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -692,6 +703,7 @@ int tsq_upload(tsq_ctx* c) {
 int tsq_compute(tsq_ctx* c) {
   if (!c) return TSQ_ERR_INVALID;
   if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "tsq_compute before tsq_upload");
+  *c->h_cancel = 0;
   TSQ_CUDA(c, cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   uint32_t launches = 0;
@@ -721,6 +733,7 @@ int tsq_compute(tsq_ctx* c) {
     p.lens = c->d_lens.p;
     p.task_prefix = c->d_prefix.p;
     p.counter = c->d_counter.p;
+    p.cancel = c->d_cancel;
     p.bnd = c->d_bnd.p;
     p.sbias = c->d_sbias.p;
     p.out = c->d_sorted.p;
@@ -758,6 +771,7 @@ int tsq_compute(tsq_ctx* c) {
     w.lens = c->d_lens.p;
     w.tasks = c->d_tasks16w.p;
     w.counter = c->d_counter.p + 2;
+    w.cancel = c->d_cancel;
     w.bnd = c->d_bnd16w.p;
     w.sbias = c->d_sbias.p;
     w.out = c->d_sorted.p;
@@ -789,6 +803,7 @@ int tsq_compute(tsq_ctx* c) {
     w.lens = c->d_lens.p;
     w.pairs = c->d_pairs32.p;
     w.counter = c->d_counter.p + 1;
+    w.cancel = c->d_cancel;
     w.bnd = c->d_bnd32.p;
     w.smat = c->d_smat.p;
     w.out = c->d_sorted.p;
@@ -906,7 +921,9 @@ int tsq_run(tsq_ctx* c, tsq_progress_cb cb, void* user, volatile int* cancel) {
     if (q == cudaSuccess) break;
     if (q != cudaErrorNotReady) return fail(c, TSQ_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(q));
     if (cancelled()) {
+      *c->h_cancel = 1;  // the kernels poll this at every task fetch and drain within one task
       cudaStreamSynchronize(c->stream);
+      c->computed = false;
       return fail(c, TSQ_ERR_CANCELLED, "cancelled");
     }
     struct timespec ts = {0, 200000};

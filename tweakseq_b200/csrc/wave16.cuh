@@ -44,6 +44,7 @@ struct W16Params {
   const uint32_t* lens;        // sorted lengths
   const uint4* tasks;          // (i1, i2, j, 0): queries i1 <= i2 (i2 == i1: single), subject j
   unsigned long long* counter; // dynamic task cursor
+  const int* cancel;           // host-mapped flag: != 0 makes every warp stop fetching tasks
   uint2* bnd;                  // pass boundary scratch per warp slot: [bnd_rows] rows of (H, E) packed
                                // relative, then [bnd_rows/4 + 16] (base_lo, base_hi) per step
   const uint32_t* sbias;       // (nsym+1) x nsym biased scores S' = S + 2*delta (row nsym = 0)
@@ -101,7 +102,10 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
 
   for (;;) {
     unsigned long long task = 0;
-    if (lane == 0) task = atomicAdd(p.counter, 1ULL);
+    if (lane == 0) {
+      task = atomicAdd(p.counter, 1ULL);
+      if (*reinterpret_cast<const volatile int*>(p.cancel) != 0) task = ~0ULL;   // "Stop" pressed
+    }
     task = __shfl_sync(0xffffffffu, task, 0);
     if (task >= p.ntasks) break;
     const uint4 tk = p.tasks[task];

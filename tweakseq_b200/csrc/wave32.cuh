@@ -32,6 +32,7 @@ struct W32Params {
   const uint32_t* lens;        // sorted lengths
   const uint2* pairs;          // tasks: (i, j) sorted indices, i < j, biggest first
   unsigned long long* counter; // dynamic task cursor
+  const int* cancel;           // host-mapped flag: != 0 makes every warp stop fetching tasks
   int2* bnd;                   // pass boundary scratch: [warp slot][row] (H, E)
   const int32_t* smat;         // (nsym+1) x nsym scores (row nsym = padding = 0)
   int32_t* out;                // scores, packed upper triangle in sorted order
@@ -72,7 +73,10 @@ __global__ void __launch_bounds__(TPB, MINB) wave32_kernel(const __grid_constant
 
   for (;;) {
     unsigned long long task = 0;
-    if (lane == 0) task = atomicAdd(p.counter, 1ULL);
+    if (lane == 0) {
+      task = atomicAdd(p.counter, 1ULL);
+      if (*reinterpret_cast<const volatile int*>(p.cancel) != 0) task = ~0ULL;   // "Stop" pressed
+    }
     task = __shfl_sync(0xffffffffu, task, 0);
     if (task >= p.ntasks) break;
     const uint2 pr = p.pairs[task];
