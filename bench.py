@@ -317,9 +317,23 @@ def main():
                          "hbm_algorithmic_gbs": hbm_alg, "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},
             "wall_s_timed_region": t_wall,
         }
+        if world == 1:
+            # the "next" row: UPGMA guide tree of the same matrix, device time
+            try:
+                run.ctx.guide_tree()
+                line["guide_tree"] = {"algorithm": "UPGMA", "n": len(seqs), "gpu_ms": run.ctx.stats()["tree_ms"]}
+            except Exception as e:   # never let the extra row break the contract line
+                line["guide_tree"] = {"error": str(e)}
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             g, sample = cpu_oracle_gcups(seqs, 10.0, threads)
+            if "gpu_ms" in line.get("guide_tree", {}):
+                from oracle import pyoracle as o
+                d = run.ctx.distances()
+                t0 = time.perf_counter()
+                o.upgma(d, len(seqs))
+                line["guide_tree"]["cpu_oracle_ms"] = 1e3 * (time.perf_counter() - t0)
+                line["guide_tree"]["cpu_oracle"] = "naive O(n^3) restatement, 1 thread"
             line["cpu_baseline"] = {"value": g, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                                     "clustalo": shutil.which("clustalo") or "ClustalO not available in image"}
         print(json.dumps(line), flush=True)

@@ -90,6 +90,7 @@ typedef struct tsq_stats {
   uint32_t reserved;
   uint64_t h2d_bytes;        /* bytes the last tsq_upload copied host -> device */
   uint64_t d2h_bytes;        /* bytes the last tsq_download copied device -> host */
+  double tree_ms;            /* CUDA-event time of the last tsq_guide_tree (device only) */
 } tsq_stats;
 
 /* progress in [0,1]; msg may be NULL.  Return value ignored. */
@@ -154,6 +155,22 @@ int tsq_partition(tsq_ctx *ctx, uint64_t *part_begin, uint64_t *part_end);
 /* Sorted-order slab complete on this device -> original-order scores (+distances). */
 int tsq_finalize(tsq_ctx *ctx);
 int tsq_device_results(tsq_ctx *ctx, void **d_scores, void **d_distances, uint64_t *count);
+
+/*
+ * Guide tree (UPGMA, average linkage) from the distance matrix of the last run -- the next
+ * consumer of the matrix (what clustalo builds from --distmat-in).
+ * n-1 merges in order; node ids: leaves 0..n-1 (submitted order), the node made by merge t is
+ * n+t; height = half the distance of the merged clusters.  Ties: smallest first slot, then
+ * smallest second slot; the merged cluster keeps the first slot.  Computed on the device.
+ */
+typedef struct tsq_merge {
+  uint32_t left, right;
+  double height;
+} tsq_merge;
+int tsq_guide_tree(tsq_ctx *ctx, const tsq_merge **merges, uint32_t *count);
+/* Newick text of that tree ("(a:0.1,(b:0.05,c:0.05):0.05);"), branch lengths %.6f, to a file
+ * (clustalo --guidetree-in).  labels[i] names leaf i; NULL = "s<i>". */
+int tsq_write_newick(tsq_ctx *ctx, const char *const *labels, const char *path);
 
 /*
  * Host-only planning (no device needed): the packed-index slab [begins[r], ends[r]) -- in the

@@ -258,3 +258,47 @@ uint64_t tsq_oracle_pair_list(const uint8_t *seqs, const uint64_t *offs, const u
   jb.begin = 0; jb.end = npairs; jb.pi = pi; jb.pj = pj; jb.out = out; jb.next = 0;
   return run_job(&jb, nthreads);
 }
+
+/* ---- UPGMA guide tree, naive O(n^3) ---- */
+void tsq_oracle_upgma(const double *packed, uint32_t n, uint32_t *left, uint32_t *right, double *height) {
+  if (n < 2) return;
+  double *D = (double *)malloc(sizeof(double) * (size_t)n * n);
+  uint32_t *size = (uint32_t *)malloc(sizeof(uint32_t) * n), *node = (uint32_t *)malloc(sizeof(uint32_t) * n);
+  unsigned char *act = (unsigned char *)malloc(n);
+  for (uint32_t i = 0; i < n; i++) {
+    size[i] = 1; node[i] = i; act[i] = 1;
+    for (uint32_t j = i + 1; j < n; j++) {
+      double v = packed[tsq_oracle_pair_index(i, j, n)];
+      D[(size_t)i * n + j] = v;
+      D[(size_t)j * n + i] = v;
+    }
+  }
+  for (uint32_t t = 0; t + 1 < n; t++) {
+    int found = 0;
+    uint32_t a = 0, b = 0;
+    double best = 0;
+    for (uint32_t i = 0; i < n; i++) {
+      if (!act[i]) continue;
+      for (uint32_t j = i + 1; j < n; j++) {
+        if (!act[j]) continue;
+        double v = D[(size_t)i * n + j];
+        if (!found || v < best) { found = 1; best = v; a = i; b = j; }   /* scan order = tie order */
+      }
+    }
+    left[t] = node[a]; right[t] = node[b];
+    volatile double half = best * 0.5;
+    height[t] = half;
+    double da = (double)size[a], db = (double)size[b], ds = (double)(size[a] + size[b]);
+    for (uint32_t k = 0; k < n; k++) {
+      if (!act[k] || k == a || k == b) continue;
+      volatile double x = da * D[(size_t)a * n + k];
+      volatile double y = db * D[(size_t)b * n + k];
+      volatile double sum = x + y;
+      double nd = sum / ds;
+      D[(size_t)a * n + k] = nd;
+      D[(size_t)k * n + a] = nd;
+    }
+    act[b] = 0; size[a] += size[b]; node[a] = n + t;
+  }
+  free(D); free(size); free(node); free(act);
+}

@@ -66,6 +66,15 @@ uint64_t tsq_oracle_pair_list(const uint8_t *seqs, const uint64_t *offs, const u
                               const int8_t *mat, int nsym, int go, int ge, const uint32_t *pi,
                               const uint32_t *pj, uint64_t npairs, int32_t *out, int nthreads);
 
+/*
+ * UPGMA guide tree of a packed fp64 distance matrix (spec in
+ * tweakseq_b200/csrc/upgma.cuh): naive O(n^3) restatement.  Step t merges the active slot pair
+ * (a < b) of smallest distance (ties: smallest a, then smallest b), the merged cluster keeps slot a,
+ * d(a,k) <- (|a| d(a,k) + |b| d(b,k)) / (|a|+|b|) with four separately rounded operations;
+ * left[t], right[t] = node ids merged (leaves 0..n-1, node of step t = n+t), height[t] = d(a,b)/2.
+ */
+void tsq_oracle_upgma(const double *packed, uint32_t n, uint32_t *left, uint32_t *right, double *height);
+
 #ifdef __cplusplus
 }
 #endif

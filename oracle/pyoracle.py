@@ -50,6 +50,8 @@ def lib():
         L.tsq_oracle_pair_list.restype = C.c_uint64
         L.tsq_oracle_pair_list.argtypes = [u8p, u64p, u32p, i8p, C.c_int, C.c_int, C.c_int, u32p, u32p,
                                            C.c_uint64, i32p, C.c_int]
+        L.tsq_oracle_upgma.restype = None
+        L.tsq_oracle_upgma.argtypes = [C.POINTER(C.c_double), C.c_uint32, u32p, u32p, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -152,3 +154,34 @@ def distances(scores: np.ndarray, selfs: np.ndarray) -> np.ndarray:
     q = scores[ok].astype(np.float64) / mn[ok].astype(np.float64)
     d[ok] = 1.0 - q
     return d
+
+
+def upgma(packed: np.ndarray, n: int):
+    """UPGMA merges (left, right, height) of a packed fp64 distance matrix (oracle, O(n^3))."""
+    d = np.ascontiguousarray(packed, dtype=np.float64)
+    left = np.zeros(max(n - 1, 0), dtype=np.uint32)
+    right = np.zeros(max(n - 1, 0), dtype=np.uint32)
+    height = np.zeros(max(n - 1, 0), dtype=np.float64)
+    if n >= 2:
+        lib().tsq_oracle_upgma(_p(d, C.c_double), n, _p(left, C.c_uint32), _p(right, C.c_uint32), _p(height, C.c_double))
+    return left, right, height
+
+
+def newick(left, right, height, labels) -> str:
+    """Newick text from UPGMA merges, same format as tsq_write_newick (branch lengths %.6f)."""
+    n = len(labels)
+    if n == 0:
+        return ";"
+    if n == 1:
+        return labels[0] + ";"
+    hs = lambda i: 0.0 if i < n else float(height[i - n])
+
+    def rec(i, ph):
+        if i < n:
+            return "%s:%.6f" % (labels[i], ph - 0.0)
+        l, r = int(left[i - n]), int(right[i - n])
+        inner = "(" + rec(l, hs(i)) + "," + rec(r, hs(i)) + ")"
+        return inner if ph < 0 else inner + ":%.6f" % (ph - hs(i))
+    import sys
+    sys.setrecursionlimit(max(10000, 4 * n))
+    return rec(2 * n - 2, -1.0) + ";"

@@ -33,12 +33,16 @@ class Params(C.Structure):
                 ("part_rank", C.c_int32), ("part_world", C.c_int32), ("flags", C.c_uint32)]
 
 
+class Merge(C.Structure):
+    _fields_ = [("left", C.c_uint32), ("right", C.c_uint32), ("height", C.c_double)]
+
+
 class Stats(C.Structure):
     _fields_ = [("n_sequences", C.c_uint64), ("n_pairs", C.c_uint64), ("cells", C.c_uint64),
                 ("cells_s16", C.c_uint64), ("cells_s32", C.c_uint64), ("kernel_ms", C.c_double),
                 ("upload_ms", C.c_double), ("download_ms", C.c_double), ("gcups_kernel", C.c_double),
                 ("launches", C.c_uint32), ("sm_count", C.c_uint32), ("strip_width", C.c_uint32),
-                ("reserved", C.c_uint32), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("reserved", C.c_uint32), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("tree_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -52,7 +56,8 @@ SYMBOLS = ["tsq_version", "tsq_version_string", "tsq_status_string", "tsq_device
            "tsq_create", "tsq_destroy", "tsq_last_error", "tsq_set_sequences", "tsq_set_sequences_flat", "tsq_upload", "tsq_compute",
            "tsq_download", "tsq_set_stream", "tsq_synchronize", "tsq_run", "tsq_scores", "tsq_distances",
            "tsq_self_scores", "tsq_device_scores", "tsq_partition", "tsq_finalize", "tsq_device_results",
-           "tsq_get_stats", "tsq_measure_dpx_rate", "tsq_run_fasta", "tsq_plan_partition"]
+           "tsq_get_stats", "tsq_measure_dpx_rate", "tsq_run_fasta", "tsq_plan_partition", "tsq_guide_tree",
+           "tsq_write_newick"]
 
 _lib = None
 
@@ -100,6 +105,8 @@ def load_library():
     L.tsq_partition.argtypes = [vp, u64p, u64p]
     L.tsq_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), u64p]
     L.tsq_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.tsq_guide_tree.argtypes = [vp, C.POINTER(C.POINTER(Merge)), C.POINTER(C.c_uint32)]
+    L.tsq_write_newick.argtypes = [vp, C.POINTER(C.c_char_p), C.c_char_p]
     L.tsq_plan_partition.argtypes = [C.POINTER(Params), C.POINTER(C.c_uint32), C.c_uint32, C.c_int32, u64p, u64p]
     L.tsq_measure_dpx_rate.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.tsq_run_fasta.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(Params), LOG_CB, vp, C.POINTER(C.c_int)]
@@ -268,6 +275,23 @@ class Context:
         s = _DevArray(ds.value or 0, cnt.value, "<i4", self)
         d = _DevArray(dd.value, cnt.value, "<f8", self) if dd.value else None
         return s, d
+
+    def guide_tree(self):
+        """UPGMA merges of the last run: (left[n-1], right[n-1], height[n-1]) numpy arrays."""
+        p, cnt = C.POINTER(Merge)(), C.c_uint32()
+        self._ck(self._L.tsq_guide_tree(self._h, C.byref(p), C.byref(cnt)))
+        k = cnt.value
+        left = np.array([p[i].left for i in range(k)], dtype=np.uint32)
+        right = np.array([p[i].right for i in range(k)], dtype=np.uint32)
+        height = np.array([p[i].height for i in range(k)], dtype=np.float64)
+        return left, right, height
+
+    def write_newick(self, path: str, labels=None):
+        arr = None
+        if labels is not None:
+            raw = [l.encode() for l in labels]
+            arr = (C.c_char_p * len(raw))(*raw)
+        self._ck(self._L.tsq_write_newick(self._h, arr, path.encode()))
 
     def stats(self) -> dict:
         st = Stats()

@@ -150,6 +150,12 @@ struct tsq_ctx {
   DevBuf<double> d_dist;
   DevBuf<unsigned long long> d_prefix, d_counter;
   DevBuf<uint2> d_bnd;
+  DevBuf<double> d_treeD, d_treemin, d_treeh;
+  DevBuf<uint32_t> d_treeu;               // rowarg, active, csize, node, rescan
+  DevBuf<tsq_merge> d_merges;
+  std::vector<tsq_merge> merges;
+  bool have_tree = false;
+  double tree_ms = 0;
   DevBuf<uint2> d_pairs32;
   DevBuf<uint4> d_tasks16w;
   DevBuf<uint2> d_bnd16w;
@@ -411,7 +417,8 @@ int tsq_destroy(tsq_ctx* c) {
   c->d_perm.release(); c->d_sbias.release(); c->d_lin.release(); c->d_self.release();
   c->d_sorted.release(); c->d_scores.release(); c->d_dist.release(); c->d_prefix.release();
   c->d_counter.release(); c->d_bnd.release(); c->h_scores.release(); c->h_dist.release();
-  c->lin.release(); c->dbw.release(); c->d_pairs32.release(); c->d_tasks16w.release(); c->d_bnd16w.release(); c->d_bnd32.release(); c->d_smat.release();
+  c->lin.release(); c->dbw.release(); c->d_treeD.release(); c->d_treemin.release(); c->d_treeh.release(); c->d_treeu.release(); c->d_merges.release();
+  c->d_pairs32.release(); c->d_tasks16w.release(); c->d_bnd16w.release(); c->d_bnd32.release(); c->d_smat.release();
   if (c->h_cancel) cudaFreeHost(c->h_cancel);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -856,6 +863,7 @@ int tsq_finalize(tsq_ctx* c) {
     c->st.launches++;
   }
   c->finalized = true;
+  c->have_tree = false;
   return TSQ_OK;
 }
 
@@ -986,6 +994,105 @@ int tsq_device_results(tsq_ctx* c, void** d_scores, void** d_dist, uint64_t* cou
   return TSQ_OK;
 }
 
+int tsq_guide_tree(tsq_ctx* c, const tsq_merge** merges, uint32_t* count) {
+  if (!c) return TSQ_ERR_INVALID;
+  if (!c->finalized) return fail(c, TSQ_ERR_STATE, "tsq_guide_tree before tsq_run / tsq_finalize");
+  if (c->prm.flags & TSQ_FLAG_NO_DISTANCES) return fail(c, TSQ_ERR_STATE, "guide tree needs distances (TSQ_FLAG_NO_DISTANCES set)");
+  const uint32_t n = c->n;
+  if (!c->have_tree) {
+    c->merges.assign(n >= 2 ? n - 1 : 0, tsq_merge{0, 0, 0.0});
+    if (n >= 2) {
+      TSQ_CUDA(c, cudaSetDevice(c->device));
+      TSQ_CUDA(c, c->d_treeD.reserve((size_t)n * n));
+      TSQ_CUDA(c, c->d_treemin.reserve(n));
+      TSQ_CUDA(c, c->d_treeh.reserve(n));
+      TSQ_CUDA(c, c->d_treeu.reserve((size_t)5 * n + 8));
+      TSQ_CUDA(c, c->d_merges.reserve(n - 1));
+      tsq::UpgmaParams u{};
+      u.dist = c->d_dist.p;
+      u.D = c->d_treeD.p;
+      u.rowmin = c->d_treemin.p;
+      u.nheight = c->d_treeh.p;
+      u.rowarg = c->d_treeu.p;
+      u.active = c->d_treeu.p + n;
+      u.csize = c->d_treeu.p + 2 * (size_t)n;
+      u.node = c->d_treeu.p + 3 * (size_t)n;
+      u.rescan = c->d_treeu.p + 4 * (size_t)n;
+      u.merges = c->d_merges.p;
+      u.n = n;
+      cudaEvent_t t0, t1;
+      TSQ_CUDA(c, cudaEventCreate(&t0));
+      TSQ_CUDA(c, cudaEventCreate(&t1));
+      TSQ_CUDA(c, cudaEventRecord(t0, c->stream));
+      TSQ_CUDA(c, tsq::upgma_launch(u, c->stream));
+      TSQ_CUDA(c, cudaEventRecord(t1, c->stream));
+      TSQ_CUDA(c, cudaMemcpyAsync(c->merges.data(), c->d_merges.p, (size_t)(n - 1) * sizeof(tsq_merge), cudaMemcpyDeviceToHost, c->stream));
+      TSQ_CUDA(c, cudaStreamSynchronize(c->stream));
+      float ms = 0;
+      cudaEventElapsedTime(&ms, t0, t1);
+      c->tree_ms = ms;
+      cudaEventDestroy(t0);
+      cudaEventDestroy(t1);
+      c->st.launches += 2;
+    }
+    c->have_tree = true;
+  }
+  if (merges) *merges = c->merges.data();
+  if (count) *count = (uint32_t)c->merges.size();
+  return TSQ_OK;
+}
+
+int tsq_write_newick(tsq_ctx* c, const char* const* labels, const char* path) {
+  if (!c || !path) return TSQ_ERR_INVALID;
+  const tsq_merge* mg = nullptr;
+  uint32_t cnt = 0;
+  int rc = tsq_guide_tree(c, &mg, &cnt);
+  if (rc != TSQ_OK) return rc;
+  const uint32_t n = c->n;
+  FILE* f = fopen(path, "w");
+  if (!f) return fail(c, TSQ_ERR_IO, "cannot write %s", path);
+  auto leaf_name = [&](uint32_t i) -> std::string {
+    if (labels && labels[i]) return labels[i];
+    return "s" + std::to_string(i);
+  };
+  if (n == 0) {
+    fputs(";\n", f);
+  } else if (n == 1) {
+    fprintf(f, "%s;\n", leaf_name(0).c_str());
+  } else {
+    // iterative post-order writer (trees of 10^5 leaves can be a caterpillar: no recursion)
+    auto height_of = [&](uint32_t id) -> double { return id < n ? 0.0 : mg[id - n].height; };
+    struct Frame { uint32_t id; int state; double parent_h; };
+    std::vector<Frame> st;
+    st.push_back({n + cnt - 1, 0, -1.0});
+    while (!st.empty()) {
+      Frame& fr = st.back();
+      if (fr.id < n) {
+        fprintf(f, "%s:%.6f", leaf_name(fr.id).c_str(), fr.parent_h - 0.0);
+        st.pop_back();
+        continue;
+      }
+      const tsq_merge& m = mg[fr.id - n];
+      if (fr.state == 0) {
+        fputc('(', f);
+        fr.state = 1;
+        st.push_back({m.left, 0, m.height});
+      } else if (fr.state == 1) {
+        fputc(',', f);
+        fr.state = 2;
+        st.push_back({m.right, 0, m.height});
+      } else {
+        if (fr.parent_h < 0) fputs(")", f);
+        else fprintf(f, "):%.6f", fr.parent_h - height_of(fr.id));
+        st.pop_back();
+      }
+    }
+    fputs(";\n", f);
+  }
+  fclose(f);
+  return TSQ_OK;
+}
+
 int tsq_plan_partition(const tsq_params* params, const uint32_t* lengths, uint32_t n, int32_t world,
                        uint64_t* begins, uint64_t* ends) {
   if (world < 1 || (n > 0 && !lengths) || !begins || !ends) return TSQ_ERR_INVALID;
@@ -1032,6 +1139,7 @@ int tsq_get_stats(tsq_ctx* c, tsq_stats* out) {
   c->st.gcups_kernel = c->st.kernel_ms > 0 ? (double)c->st.cells / (c->st.kernel_ms * 1e6) : 0.0;
   c->st.sm_count = (uint32_t)c->sm_count;
   c->st.strip_width = (uint32_t)c->K;
+  c->st.tree_ms = c->tree_ms;
   *out = c->st;
   return TSQ_OK;
 }
@@ -1129,6 +1237,12 @@ int tsq_run_fasta(const char* fin, const char* fout, const tsq_params* params, t
         fputc('\n', fo);
       }
       fclose(fo);
+      {  // guide tree for clustalo --guidetree-in, next to the matrix
+        std::vector<const char*> lab(labels.size());
+        for (size_t i = 0; i < labels.size(); i++) lab[i] = labels[i].c_str();
+        const std::string tree = std::string(fout) + ".dnd";
+        if (tsq_write_newick(c, lab.data(), tree.c_str()) == TSQ_OK) say("tsq-b200: wrote guide tree " + tree);
+      }
       tsq_stats st;
       tsq_get_stats(c, &st);
       snprintf(msg, sizeof msg, "tsq-b200: %llu pairs, %.3e cells, kernel %.3f ms (%.1f GCUPS), wrote %s",

@@ -1,4 +1,5 @@
 // tsq_device.cu -- kernel instantiations and launchers (sm_100a only).
+#define TSQ_DEVICE_IMPL 1
 #include "tsq_device.h"
 
 #include <cstdio>
@@ -157,6 +158,17 @@ cudaError_t w16_launch(int grid, const W16Params& p, cudaStream_t stream) {
   TSQ_W16_VARIANTS(X)
 #undef X
   return cudaErrorInvalidValue;
+}
+
+// ---- UPGMA guide tree -----------------------------------------------------------------------------
+cudaError_t upgma_launch(const UpgmaParams& p, cudaStream_t stream) {
+  if (p.n < 2) return cudaSuccess;
+  unsigned int grid = p.n < 148u * 16u ? p.n : 148u * 16u;
+  upgma_init_kernel<<<grid, 256, 0, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  upgma_merge_kernel<<<1, UPGMA_THREADS, 0, stream>>>(p);
+  return cudaGetLastError();
 }
 
 // ---- finalize: empties, un-sort, fp64 distances -----------------------------------------

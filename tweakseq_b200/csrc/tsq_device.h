@@ -6,6 +6,7 @@
 #include "gotoh16.cuh"
 #include "wave32.cuh"
 #include "wave16.cuh"
+#include "upgma.cuh"
 
 namespace tsq {
 
@@ -40,6 +41,9 @@ cudaError_t w32_launch(int grid, const W32Params& p, cudaStream_t stream);
 bool w16_variant(uint32_t nsym, W32Launch* out);
 long long w16_window(uint32_t nsym, long long lipschitz);
 cudaError_t w16_launch(int grid, const W16Params& p, cudaStream_t stream);
+
+// UPGMA guide tree: init (one CTA per row) + one persistent CTA for the n-1 merges.
+cudaError_t upgma_launch(const UpgmaParams& p, cudaStream_t stream);
 
 struct FinalizeParams {
   const int32_t* sorted;      // packed triangle, sorted order

@@ -1,0 +1,211 @@
+// upgma.cuh -- guide tree from the distance matrix: UPGMA, sm_100a.
+//
+// The next consumer of the distance matrix: what clustalo builds from --distmat-in before its
+// progressive alignment.  Spec (build-defined, restated by oracle/gotoh_oracle.c:tsq_oracle_upgma):
+//   * clusters live in slots 0..n-1; every step merges the active pair (a < b) with the smallest
+//     distance, ties broken by smallest a, then smallest b; the merged cluster keeps slot a;
+//   * d(a,k) <- (|a|*d(a,k) + |b|*d(b,k)) / (|a|+|b|), four separately rounded fp64 operations;
+//   * node ids: leaves 0..n-1, the node created by step t is n+t; its height is d(a,b)/2.
+//
+// Device layout: a full symmetric n x n fp64 matrix (rows contiguous) plus, per row i, the minimum
+// over active j > i and its argument.  One persistent CTA runs the n-1 sequential steps; each step
+// is a block-wide lexicographic arg-min over the row minima, an O(n) row update, and a re-scan of
+// the few rows whose cached minimum pointed at a or b.  The work per step is O(n) + re-scans, the
+// whole tree O(n^2) instead of the naive O(n^3).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/tsq_b200.h"
+
+namespace tsq {
+
+struct UpgmaParams {
+  const double* dist;   // packed upper triangle, submitted order
+  double* D;            // n x n workspace
+  double* rowmin;       // [n]
+  uint32_t* rowarg;     // [n]
+  uint32_t* active;     // [n] 1 = slot in use
+  uint32_t* csize;      // [n] leaves under the slot
+  uint32_t* node;       // [n] node id currently held by the slot
+  double* nheight;      // [n] height of that node
+  tsq_merge* merges;    // [n-1] output
+  uint32_t* rescan;     // [n+1] rows to re-scan in the current step
+  uint32_t n;
+};
+
+#ifdef TSQ_DEVICE_IMPL  // kernel definitions: only tsq_device.cu instantiates them
+
+__device__ __forceinline__ bool upgma_less(double va, uint32_t ia, uint32_t ja, double vb, uint32_t ib, uint32_t jb) {
+  if (va != vb) return va < vb;
+  if (ia != ib) return ia < ib;
+  return ja < jb;
+}
+
+// fill the square matrix and the initial row minima; one CTA per row
+__global__ void __launch_bounds__(256) upgma_init_kernel(const __grid_constant__ UpgmaParams p) {
+  const unsigned long long n = p.n;
+  __shared__ double sv[256];
+  __shared__ uint32_t sj[256];
+  for (unsigned long long i = blockIdx.x; i < n; i += gridDim.x) {
+    double best = __longlong_as_double(0x7ff0000000000000ll);  // +inf
+    uint32_t bj = 0xffffffffu;
+    for (unsigned long long j = threadIdx.x; j < n; j += blockDim.x) {
+      double v;
+      if (j == i) v = __longlong_as_double(0x7ff0000000000000ll);
+      else {
+        const unsigned long long a = i < j ? i : j, b = i < j ? j : i;
+        v = p.dist[a * n - a * (a + 1) / 2 + (b - a - 1)];
+      }
+      p.D[i * n + j] = v;
+      if (j > i && (v < best || (v == best && (uint32_t)j < bj))) { best = v; bj = (uint32_t)j; }
+    }
+    sv[threadIdx.x] = best;
+    sj[threadIdx.x] = bj;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (threadIdx.x < s) {
+        const double v2 = sv[threadIdx.x + s];
+        const uint32_t j2 = sj[threadIdx.x + s];
+        if (v2 < sv[threadIdx.x] || (v2 == sv[threadIdx.x] && j2 < sj[threadIdx.x])) { sv[threadIdx.x] = v2; sj[threadIdx.x] = j2; }
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      p.rowmin[i] = sv[0];
+      p.rowarg[i] = sj[0];
+      p.active[i] = 1;
+      p.csize[i] = 1;
+      p.node[i] = (uint32_t)i;
+      p.nheight[i] = 0.0;
+    }
+    __syncthreads();
+  }
+}
+
+constexpr int UPGMA_THREADS = 1024;
+
+// block-wide lexicographic arg-min of (v, i, j); result valid in every thread
+__device__ __forceinline__ void upgma_block_argmin(double& v, uint32_t& i, uint32_t& j, double* sv, uint32_t* si,
+                                                   uint32_t* sj) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+    const uint32_t i2 = __shfl_xor_sync(0xffffffffu, i, o);
+    const uint32_t j2 = __shfl_xor_sync(0xffffffffu, j, o);
+    if (upgma_less(v2, i2, j2, v, i, j)) { v = v2; i = i2; j = j2; }
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) { sv[w] = v; si[w] = i; sj[w] = j; }
+  __syncthreads();
+  if (w == 0) {
+    v = sv[l]; i = si[l]; j = sj[l];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+      const uint32_t i2 = __shfl_xor_sync(0xffffffffu, i, o);
+      const uint32_t j2 = __shfl_xor_sync(0xffffffffu, j, o);
+      if (upgma_less(v2, i2, j2, v, i, j)) { v = v2; i = i2; j = j2; }
+    }
+    if (l == 0) { sv[0] = v; si[0] = i; sj[0] = j; }
+  }
+  __syncthreads();
+  v = sv[0]; i = si[0]; j = sj[0];
+}
+
+__global__ void __launch_bounds__(UPGMA_THREADS, 1) upgma_merge_kernel(const __grid_constant__ UpgmaParams p) {
+  const uint32_t n = p.n;
+  const double INF = __longlong_as_double(0x7ff0000000000000ll);
+  __shared__ double sv[32];
+  __shared__ uint32_t si[32], sj[32];
+  __shared__ uint32_t nrescan;
+  uint32_t* const rescan = p.rescan;
+  const uint32_t tid = threadIdx.x;
+
+  for (uint32_t step = 0; step + 1 < n; ++step) {
+    // ---- 1. the closest active pair --------------------------------------------------------------
+    double v = INF;
+    uint32_t a = 0xffffffffu, b = 0xffffffffu;
+    for (uint32_t i = tid; i < n; i += UPGMA_THREADS) {
+      if (p.active[i]) {
+        const double rv = p.rowmin[i];
+        const uint32_t rj = p.rowarg[i];
+        if (rj != 0xffffffffu && upgma_less(rv, i, rj, v, a, b)) { v = rv; a = i; b = rj; }
+      }
+    }
+    upgma_block_argmin(v, a, b, sv, si, sj);
+    // ---- 2. record the merge ----------------------------------------------------------------------
+    const uint32_t sa = p.csize[a], sb = p.csize[b];
+    if (tid == 0) {
+      tsq_merge mg;
+      mg.left = p.node[a];
+      mg.right = p.node[b];
+      mg.height = __dmul_rn(v, 0.5);
+      p.merges[step] = mg;
+      nrescan = 0;
+    }
+    __syncthreads();
+    // ---- 3. new distances of slot a; slot b retires ------------------------------------------------
+    const double da = (double)sa, db = (double)sb, dsum = (double)(sa + sb);
+    double* Da = p.D + (size_t)a * n;
+    const double* Db = p.D + (size_t)b * n;
+    for (uint32_t k = tid; k < n; k += UPGMA_THREADS) {
+      if (k == a || k == b || !p.active[k]) continue;
+      const double nd = __ddiv_rn(__dadd_rn(__dmul_rn(da, Da[k]), __dmul_rn(db, Db[k])), dsum);
+      Da[k] = nd;
+      p.D[(size_t)k * n + a] = nd;
+      if (k < a) {
+        // entry (k,a) of row k changed, entry (k,b) disappears
+        const uint32_t rk = p.rowarg[k];
+        if (rk == a || rk == b) {
+          const uint32_t pos = atomicAdd(&nrescan, 1u);
+          rescan[pos] = k;
+        } else if (nd < p.rowmin[k] || (nd == p.rowmin[k] && a < rk)) {
+          p.rowmin[k] = nd;
+          p.rowarg[k] = a;
+        }
+      } else if (k < b) {
+        // a < k < b: row k loses entry (k,b); entry (a,k) belongs to row a (re-scanned below)
+        if (p.rowarg[k] == b) {
+          const uint32_t pos = atomicAdd(&nrescan, 1u);
+          rescan[pos] = k;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      p.active[b] = 0;
+      p.csize[a] = sa + sb;
+      p.node[a] = n + step;
+      p.nheight[a] = __dmul_rn(v, 0.5);
+      rescan[nrescan] = a;   // row a always
+      nrescan = nrescan + 1;
+    }
+    __syncthreads();
+    // ---- 4. re-scan the rows whose cached minimum is stale -----------------------------------------
+    const uint32_t nr = nrescan;
+    for (uint32_t r = 0; r < nr; ++r) {
+      const uint32_t row = rescan[r];
+      const double* Dr = p.D + (size_t)row * n;
+      double bv = INF;
+      uint32_t bi = row, bj = 0xffffffffu;
+      for (uint32_t j = row + 1 + tid; j < n; j += UPGMA_THREADS) {
+        if (p.active[j]) {
+          const double x = Dr[j];
+          if (x < bv || (x == bv && j < bj)) { bv = x; bj = j; }
+        }
+      }
+      upgma_block_argmin(bv, bi, bj, sv, si, sj);
+      if (tid == 0) {
+        p.rowmin[row] = bv;
+        p.rowarg[row] = bj;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+#endif  // TSQ_DEVICE_IMPL
+
+}  // namespace tsq
