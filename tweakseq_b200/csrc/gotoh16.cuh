@@ -47,7 +47,7 @@ struct G16Params {
   const uint32_t* lens;        // sorted lengths
   const unsigned long long* task_prefix;  // [nq+1] cumulative chunk counts, per query pair
   unsigned long long* counter; // dynamic task cursor
-  const int* cancel;           // host-mapped flag: != 0 makes every warp stop fetching tasks
+  const int* cancel;           // device flag (set by a side-stream copy): != 0 stops task fetching
   uint2* bnd;                  // strip boundary scratch: [warp slot][row][lane] (H, E)
   const uint32_t* sbias;       // (nsym+1) x nsym biased scores S' (row nsym = padding = 0)
   int32_t* out;                // scores, packed upper triangle in sorted order

@@ -165,8 +165,12 @@ struct tsq_ctx {
   PinnedBuf<int32_t> h_scores;
   PinnedBuf<double> h_dist;
 
-  int* h_cancel = nullptr;   // pinned, device-mapped: set by tsq_run when the caller's flag goes up
+  // Cancel flag the kernels poll at every task fetch.  It lives in DEVICE memory and is written by a
+  // copy on a side stream while the kernels run (polling a host-mapped flag cost ~0.5 ms per read on
+  // this platform: C2 went from 5.3 to 8.1 ms).
   int* d_cancel = nullptr;
+  int* h_one = nullptr;      // pinned source of that copy
+  cudaStream_t cancel_stream = nullptr;
 
   bool have_seqs = false, uploaded = false, computed = false, finalized = false, downloaded = false;
   tsq_stats st{};
@@ -397,13 +401,14 @@ int tsq_create(tsq_ctx** out, const tsq_params* params) {
     delete c;
     return TSQ_ERR_CUDA;
   }
-  if (cudaHostAlloc((void**)&c->h_cancel, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
-      cudaHostGetDevicePointer((void**)&c->d_cancel, c->h_cancel, 0) != cudaSuccess) {
+  if (cudaMalloc((void**)&c->d_cancel, sizeof(int)) != cudaSuccess || cudaMemset(c->d_cancel, 0, sizeof(int)) != cudaSuccess ||
+      cudaMallocHost((void**)&c->h_one, sizeof(int)) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->cancel_stream, cudaStreamNonBlocking) != cudaSuccess) {
     cudaGetLastError();
     tsq_destroy(c);
     return TSQ_ERR_CUDA;
   }
-  *c->h_cancel = 0;
+  *c->h_one = 1;
   c->stream = c->own_stream;
   *out = c;
   return TSQ_OK;
@@ -419,7 +424,9 @@ int tsq_destroy(tsq_ctx* c) {
   c->d_counter.release(); c->d_bnd.release(); c->h_scores.release(); c->h_dist.release();
   c->lin.release(); c->dbw.release(); c->d_treeD.release(); c->d_treemin.release(); c->d_treeh.release(); c->d_treeu.release(); c->d_merges.release();
   c->d_pairs32.release(); c->d_tasks16w.release(); c->d_bnd16w.release(); c->d_bnd32.release(); c->d_smat.release();
-  if (c->h_cancel) cudaFreeHost(c->h_cancel);
+  if (c->d_cancel) cudaFree(c->d_cancel);
+  if (c->h_one) cudaFreeHost(c->h_one);
+  if (c->cancel_stream) cudaStreamDestroy(c->cancel_stream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -710,10 +717,10 @@ int tsq_upload(tsq_ctx* c) {
 int tsq_compute(tsq_ctx* c) {
   if (!c) return TSQ_ERR_INVALID;
   if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "tsq_compute before tsq_upload");
-  *c->h_cancel = 0;
   TSQ_CUDA(c, cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   uint32_t launches = 0;
+  TSQ_CUDA(c, cudaMemsetAsync(c->d_cancel, 0, sizeof(int), s));
   TSQ_CUDA(c, cudaEventRecord(c->ev0, s));
   const uint32_t nq = c->q_end - c->q_begin;
   const unsigned long long ntasks = c->task_prefix.empty() ? 0 : c->task_prefix[nq];
@@ -929,7 +936,9 @@ int tsq_run(tsq_ctx* c, tsq_progress_cb cb, void* user, volatile int* cancel) {
     if (q == cudaSuccess) break;
     if (q != cudaErrorNotReady) return fail(c, TSQ_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(q));
     if (cancelled()) {
-      *c->h_cancel = 1;  // the kernels poll this at every task fetch and drain within one task
+      // the kernels poll the flag at every task fetch and drain within one task
+      cudaMemcpyAsync(c->d_cancel, c->h_one, sizeof(int), cudaMemcpyHostToDevice, c->cancel_stream);
+      cudaStreamSynchronize(c->cancel_stream);
       cudaStreamSynchronize(c->stream);
       c->computed = false;
       return fail(c, TSQ_ERR_CANCELLED, "cancelled");

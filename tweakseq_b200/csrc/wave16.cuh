@@ -44,7 +44,7 @@ struct W16Params {
   const uint32_t* lens;        // sorted lengths
   const uint4* tasks;          // (i1, i2, j, 0): queries i1 <= i2 (i2 == i1: single), subject j
   unsigned long long* counter; // dynamic task cursor
-  const int* cancel;           // host-mapped flag: != 0 makes every warp stop fetching tasks
+  const int* cancel;           // device flag (set by a side-stream copy): != 0 stops task fetching
   uint2* bnd;                  // pass boundary scratch per warp slot: [bnd_rows] rows of (H, E) packed
                                // relative, then [bnd_rows/4 + 16] (base_lo, base_hi) per step
   const uint32_t* sbias;       // (nsym+1) x nsym biased scores S' = S + 2*delta (row nsym = 0)

@@ -32,7 +32,7 @@ struct W32Params {
   const uint32_t* lens;        // sorted lengths
   const uint2* pairs;          // tasks: (i, j) sorted indices, i < j, biggest first
   unsigned long long* counter; // dynamic task cursor
-  const int* cancel;           // host-mapped flag: != 0 makes every warp stop fetching tasks
+  const int* cancel;           // device flag (set by a side-stream copy): != 0 stops task fetching
   int2* bnd;                   // pass boundary scratch: [warp slot][row] (H, E)
   const int32_t* smat;         // (nsym+1) x nsym scores (row nsym = padding = 0)
   int32_t* out;                // scores, packed upper triangle in sorted order
