@@ -167,7 +167,14 @@ cudaError_t upgma_launch(const UpgmaParams& p, cudaStream_t stream) {
   upgma_init_kernel<<<grid, 256, 0, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  upgma_merge_kernel<<<1, UPGMA_THREADS, 0, stream>>>(p);
+  if (p.n <= UPGMA_SMEM_N) {
+    const size_t smem = (size_t)p.n * (sizeof(double) + sizeof(uint32_t) + 1) + 16;
+    e = cudaFuncSetAttribute(upgma_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    upgma_merge_kernel<true><<<1, UPGMA_THREADS, smem, stream>>>(p);
+  } else {
+    upgma_merge_kernel<false><<<1, UPGMA_THREADS, 0, stream>>>(p);
+  }
   return cudaGetLastError();
 }
 

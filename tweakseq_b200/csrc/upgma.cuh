@@ -114,23 +114,41 @@ __device__ __forceinline__ void upgma_block_argmin(double& v, uint32_t& i, uint3
   v = sv[0]; i = si[0]; j = sj[0];
 }
 
+// SMEM: row minima, their arguments and the active flags live in shared memory (n <= UPGMA_SMEM_N);
+// every step then touches global memory only for the two matrix rows it combines and for re-scans.
+constexpr uint32_t UPGMA_SMEM_N = 12288;   // 12288 * (8 + 4 + 1) B = 156 KB
+
+template <bool SMEM>
 __global__ void __launch_bounds__(UPGMA_THREADS, 1) upgma_merge_kernel(const __grid_constant__ UpgmaParams p) {
   const uint32_t n = p.n;
   const double INF = __longlong_as_double(0x7ff0000000000000ll);
   __shared__ double sv[32];
   __shared__ uint32_t si[32], sj[32];
   __shared__ uint32_t nrescan;
+  extern __shared__ double upgma_dyn[];
+  double* rowmin = SMEM ? upgma_dyn : p.rowmin;
+  uint32_t* rowarg = SMEM ? reinterpret_cast<uint32_t*>(upgma_dyn + n) : p.rowarg;
+  uint8_t* act8 = reinterpret_cast<uint8_t*>(rowarg + n);   // SMEM only
   uint32_t* const rescan = p.rescan;
   const uint32_t tid = threadIdx.x;
+  if (SMEM) {
+    for (uint32_t i = tid; i < n; i += UPGMA_THREADS) {
+      rowmin[i] = p.rowmin[i];
+      rowarg[i] = p.rowarg[i];
+      act8[i] = 1;
+    }
+    __syncthreads();
+  }
+  auto is_active = [&](uint32_t i) -> bool { return SMEM ? act8[i] != 0 : p.active[i] != 0; };
 
   for (uint32_t step = 0; step + 1 < n; ++step) {
     // ---- 1. the closest active pair --------------------------------------------------------------
     double v = INF;
     uint32_t a = 0xffffffffu, b = 0xffffffffu;
     for (uint32_t i = tid; i < n; i += UPGMA_THREADS) {
-      if (p.active[i]) {
-        const double rv = p.rowmin[i];
-        const uint32_t rj = p.rowarg[i];
+      if (is_active(i)) {
+        const double rv = rowmin[i];
+        const uint32_t rj = rowarg[i];
         if (rj != 0xffffffffu && upgma_less(rv, i, rj, v, a, b)) { v = rv; a = i; b = rj; }
       }
     }
@@ -151,23 +169,23 @@ __global__ void __launch_bounds__(UPGMA_THREADS, 1) upgma_merge_kernel(const __g
     double* Da = p.D + (size_t)a * n;
     const double* Db = p.D + (size_t)b * n;
     for (uint32_t k = tid; k < n; k += UPGMA_THREADS) {
-      if (k == a || k == b || !p.active[k]) continue;
+      if (k == a || k == b || !is_active(k)) continue;
       const double nd = __ddiv_rn(__dadd_rn(__dmul_rn(da, Da[k]), __dmul_rn(db, Db[k])), dsum);
       Da[k] = nd;
       p.D[(size_t)k * n + a] = nd;
       if (k < a) {
         // entry (k,a) of row k changed, entry (k,b) disappears
-        const uint32_t rk = p.rowarg[k];
+        const uint32_t rk = rowarg[k];
         if (rk == a || rk == b) {
           const uint32_t pos = atomicAdd(&nrescan, 1u);
           rescan[pos] = k;
-        } else if (nd < p.rowmin[k] || (nd == p.rowmin[k] && a < rk)) {
-          p.rowmin[k] = nd;
-          p.rowarg[k] = a;
+        } else if (nd < rowmin[k] || (nd == rowmin[k] && a < rk)) {
+          rowmin[k] = nd;
+          rowarg[k] = a;
         }
       } else if (k < b) {
         // a < k < b: row k loses entry (k,b); entry (a,k) belongs to row a (re-scanned below)
-        if (p.rowarg[k] == b) {
+        if (rowarg[k] == b) {
           const uint32_t pos = atomicAdd(&nrescan, 1u);
           rescan[pos] = k;
         }
@@ -175,10 +193,9 @@ __global__ void __launch_bounds__(UPGMA_THREADS, 1) upgma_merge_kernel(const __g
     }
     __syncthreads();
     if (tid == 0) {
-      p.active[b] = 0;
+      if (SMEM) act8[b] = 0; else p.active[b] = 0;
       p.csize[a] = sa + sb;
       p.node[a] = n + step;
-      p.nheight[a] = __dmul_rn(v, 0.5);
       rescan[nrescan] = a;   // row a always
       nrescan = nrescan + 1;
     }
@@ -191,15 +208,15 @@ __global__ void __launch_bounds__(UPGMA_THREADS, 1) upgma_merge_kernel(const __g
       double bv = INF;
       uint32_t bi = row, bj = 0xffffffffu;
       for (uint32_t j = row + 1 + tid; j < n; j += UPGMA_THREADS) {
-        if (p.active[j]) {
+        if (is_active(j)) {
           const double x = Dr[j];
           if (x < bv || (x == bv && j < bj)) { bv = x; bj = j; }
         }
       }
       upgma_block_argmin(bv, bi, bj, sv, si, sj);
       if (tid == 0) {
-        p.rowmin[row] = bv;
-        p.rowarg[row] = bj;
+        rowmin[row] = bv;
+        rowarg[row] = bj;
       }
     }
     __syncthreads();
