@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- GCUPS of the all-vs-all Gotoh distance-matrix path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3|c5|c5s]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3|c4|c5|c5s]
 
 A step = one all-vs-all pass over one batch of synthetic sequences.
 N = 1: BASELINE.json configs[1] (1,000 protein seqs x 300 aa, 499,500 pairs, 4.4955e10 cells).
@@ -52,6 +52,9 @@ def workload(name: str, n_gpus: int):
     elif name == "c5":
         seqs = synth.protein(100000, 150, 5)
         label = "configs[4]: 100,000 protein seqs x 150 aa all-vs-all (4,999,950,000 pairs; strong scaling across ranks; scores only)"
+    elif name == "c4":
+        seqs = synth.nucleotide(500, 10000, 30000, 4)
+        label = "configs[3]: 500 nucleotide seqs x 10-30 kb all-vs-all (124,750 pairs; packed wavefront kernel)"
     elif name == "c5s":
         seqs = synth.protein(20000, 150, 5)
         label = "configs[4] scaled twin: 20,000 protein seqs x 150 aa all-vs-all"
@@ -198,10 +201,11 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    strong = args.workload in ("c3", "c5")
+    strong = args.workload in ("c3", "c4", "c5")
     seqs, label = workload(args.workload, world)
     flags = t.FLAG_NO_DISTANCES if args.workload == "c5" else 0   # 40 GB of fp64 distances: scores only
-    run = ShardedRun(seqs, flags=flags, device=local)
+    alphabet = 1 if args.workload == "c4" else 0
+    run = ShardedRun(seqs, alphabet=alphabet, flags=flags, device=local)
     run.upload()
     from tweakseq_b200 import synth
     cells_total = synth.total_cells(seqs)
@@ -305,17 +309,19 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u16x2", "data": "synthetic",
             "config": {"workload": label, "n_sequences": len(seqs), "pairs": len(seqs) * (len(seqs) - 1) // 2,
-                       "cells": cells_total, "gap_open": 11, "gap_extend": 1, "matrix": "BLOSUM62 (Consensus.cpp:34-59)",
+                       "cells": cells_total, "gap_open": 10 if alphabet else 11, "gap_extend": 1,
+                       "matrix": "ACGTN +5/-4 (SURVEY 8c)" if alphabet else "BLOSUM62 (Consensus.cpp:34-59)",
                        "strip_width": st["strip_width"], "l2": "flushed between timed steps (256 MiB fill)",
                        "seed": 20261017 + 2},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_t / e2e_steps, "steps": e2e_steps, "launches_per_step": int(e2e_launches)},
             "gpu_launches": int(launches_per_step * args.steps),
-            "roofline": {"bound": "dpx-alu", "kernel": "gotoh16_kernel", "achieved": achieved, "peak": peak, "unit": UNIT,
+            "roofline": {"bound": "dpx-alu", "kernel": "wave16_kernel" if kst["cells_s32"] > kst["cells_s16"] else "gotoh16_kernel", "achieved": achieved, "peak": peak, "unit": UNIT,
                          "frac": achieved / peak if peak else None, "traffic": traffic,
-                         "traffic_note": "dram read+write bytes of one launch (ncu --set full, profiles/ncu_gotoh16_c2_r01.txt): the "
-                                         "strip-boundary scratch column, not input re-reads; algorithmic bytes are len_i+len_j in, 4 B out per pair",
+                         "traffic_note": ("dram read+write bytes of one launch (ncu --set full, profiles/ncu_gotoh16_c2_r01.txt): the "
+                                          "strip-boundary scratch column, not input re-reads; algorithmic bytes are len_i+len_j in, "
+                                          "4 B out per pair") if traffic else "no ncu capture of this workload (profiles/ncu_traffic.json)",
                          "algorithmic_bytes": lens_bytes + 4 * st["n_pairs"],
                          "peak_how": f"{sms} SMs x {dpx_ops:.1f} DPX lane-results/clk/SM (measured live) x {sm_mhz} MHz "
                                      "(median under load) / 2.5 instr per cell (5 integer lane-ops, 16x2 packing: SURVEY 8d)",
@@ -323,14 +329,14 @@ def main():
                          "hbm_algorithmic_gbs": hbm_alg, "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},
             "wall_s_timed_region": t_wall,
         }
-        if world == 1:
+        if world == 1 and args.workload == "c2":
             # the "next" row: UPGMA guide tree of the same matrix, device time
             try:
                 run.ctx.guide_tree()
                 line["guide_tree"] = {"algorithm": "UPGMA", "n": len(seqs), "gpu_ms": run.ctx.stats()["tree_ms"]}
             except Exception as e:   # never let the extra row break the contract line
                 line["guide_tree"] = {"error": str(e)}
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and alphabet == 0:
             threads = os.cpu_count() or 1
             g, sample = cpu_oracle_gcups(seqs, 10.0, threads)
             if "gpu_ms" in line.get("guide_tree", {}):
