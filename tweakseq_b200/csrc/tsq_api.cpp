@@ -293,6 +293,390 @@ void plan_rows(const std::vector<uint32_t>& lens, uint32_t lo, uint32_t hi, int 
 
 }  // namespace
 
+namespace {
+
+// ---- tsq_upload, step 1: stable length sort, linear residue buffer, self scores, regime bounds ----
+int host_sort_and_pack(tsq_ctx* c) {
+  const uint32_t n = c->n;
+  // ---- stable length sort ---------------------------------------------------------------
+  c->perm.resize(n);
+  std::iota(c->perm.begin(), c->perm.end(), 0u);
+  std::stable_sort(c->perm.begin(), c->perm.end(),
+                   [&](uint32_t a, uint32_t b) { return c->enc[a].size() < c->enc[b].size(); });
+  c->lens.resize(n);
+  c->loff.resize(n + 1);
+  uint64_t total = 0;
+  c->identity = true;
+  for (uint32_t i = 0; i < n; i++) {
+    const size_t l = c->enc[c->perm[i]].size();
+    if (l > 0x7fffffffu) return fail(c, TSQ_ERR_RANGE, "sequence too long");
+    c->lens[i] = (uint32_t)l;
+    c->loff[i] = (uint32_t)total;
+    total += (l + 15) & ~(size_t)15;   // 16-byte aligned starts: TMA bulk copies read tiles from here
+    if (c->perm[i] != i) c->identity = false;
+  }
+  if (total > 0xfffffff0ull) return fail(c, TSQ_ERR_RANGE, "more than 4 Gi residues");
+  c->loff[n] = (uint32_t)total;
+  TSQ_CUDA(c, c->lin.reserve(total + 2048));   // slack: the last TMA tile of a subject may run past its end
+  c->lin_size = total + 2048;
+  memset(c->lin.p, 0, c->lin_size);
+  c->self_sorted.resize(n);
+  c->self_orig.resize(n);
+  for (uint32_t i = 0; i < n; i++) {
+    const std::vector<uint8_t>& e = c->enc[c->perm[i]];
+    if (!e.empty()) memcpy(c->lin.p + c->loff[i], e.data(), e.size());
+    int64_t s = 0;
+    for (uint8_t a : e) s += c->matrix[a * c->nsym + a];
+    c->self_sorted[i] = (int32_t)s;
+    c->self_orig[c->perm[i]] = (int32_t)s;
+  }
+  // ---- regimes --------------------------------------------------------------------------
+  uint32_t lo = 0;
+  while (lo < n && c->lens[lo] == 0) lo++;
+  uint32_t hi = lo;
+  while (hi < n && c->lens[hi] <= c->max_len16) hi++;
+  if (c->identity && lo > 0) c->identity = false;  // empties are filled in by finalize
+  c->lo = lo;
+  c->hi = hi;
+  if (n > 0) {  // 32-bit range: |H| <= (m+n) * max|score or ge| + 2*go must stay far inside int32
+    const int64_t unit = std::max<int64_t>(std::max(std::abs(c->smin), std::abs(c->smax)), c->ge);
+    if (2 * (int64_t)c->lens[n - 1] * unit + 2 * (int64_t)c->go >= (1ll << 30))
+      return fail(c, TSQ_ERR_RANGE, "sequence of length %u: scores would not fit 32 bits", c->lens[n - 1]);
+  }
+
+  return TSQ_OK;
+}
+
+// ---- tsq_upload, step 2: this rank's rows, task lists of the three kernels, strip width ------------
+int host_plan_work(tsq_ctx* c) {
+  const uint32_t n = c->n, lo = c->lo, hi = c->hi;
+  const uint64_t npairs = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
+  // ---- partition of the sorted rows across ranks (contiguous, balanced by DP cells) ---------
+  const int world = c->prm.part_world, rank = c->prm.part_rank;
+  std::vector<uint32_t> first_row;
+  c->use_w16 = wave16_ok(c, c->nsym, c->prm.flags);
+  plan_rows(c->lens, lo, hi, world, first_row, c->use_w16 ? 1.5 : 2.4);
+  auto boundary = [&](int r) -> uint32_t { return first_row[(size_t)r]; };
+  c->row_a = boundary(rank);
+  c->row_b = boundary(rank + 1);
+  c->part_begin = (n >= 2 && c->row_a + 1 < n) ? tri(c->row_a, c->row_a + 1, n) : npairs;
+  c->part_end = (n >= 2 && c->row_b + 1 < n) ? tri(c->row_b, c->row_b + 1, n) : npairs;
+  if (c->part_begin > c->part_end) c->part_begin = c->part_end;
+
+  // ---- tasks of the packed kernel: query pairs q in [q_begin, q_end) ------------------------
+  const uint32_t nq_all = (hi - lo) / 2;
+  auto row_to_q = [&](uint32_t row) -> uint32_t {
+    if (row <= lo) return 0;
+    return std::min(nq_all, (row - lo + 1) / 2);
+  };
+  c->q_begin = row_to_q(c->row_a);
+  c->q_end = row_to_q(c->row_b);
+  if (c->q_end < c->q_begin) c->q_end = c->q_begin;
+  const uint32_t nq = c->q_end - c->q_begin;
+  c->task_prefix.assign((size_t)nq + 1, 0);
+  c->cells16 = 0;
+  c->pairs_part = 0;
+  {
+    std::vector<uint64_t> suffix(n + 1, 0);
+    for (uint32_t i = n; i-- > 0;) suffix[i] = suffix[i + 1] + c->lens[i];
+    for (uint32_t r = 0; r < nq; r++) {
+      const uint32_t q = c->q_end - 1 - r;
+      const uint32_t a1 = lo + 2 * q;
+      const uint32_t nsub = hi - a1 - 1;
+      c->task_prefix[r + 1] = c->task_prefix[r] + (nsub + 31) / 32;
+      c->cells16 += (uint64_t)c->lens[a1] * (suffix[a1 + 1] - suffix[hi]) +
+                    (uint64_t)c->lens[a1 + 1] * (suffix[a1 + 2] - suffix[hi]);
+      c->pairs_part += (uint64_t)(hi - a1 - 1) + (hi - a1 - 2);
+    }
+  }
+  // ---- tasks of the 32-bit wavefront kernel: every pair with a sequence beyond the packed range,
+  //      restricted to this rank's rows, biggest pairs first -------------------------------------
+  c->cells32 = 0;
+  c->pairs32.clear();
+  c->tasks16w.clear();
+  if (hi < n) {
+    const uint32_t ra = std::max(c->row_a, lo);
+    if (c->use_w16) {
+      // (query pair, subject): subject j long, queries i < j of this rank's rows, two at a time
+      for (uint32_t j = n; j-- > hi;) {
+        const uint32_t top = std::min(c->row_b, j);  // queries in [ra, top)
+        uint32_t i = top;
+        while (i > ra) {
+          if (i - ra >= 2) {
+            c->tasks16w.push_back(make_uint4(i - 2, i - 1, j, 0));
+            c->cells32 += ((uint64_t)c->lens[i - 2] + c->lens[i - 1]) * c->lens[j];
+            c->pairs_part += 2;
+            i -= 2;
+          } else {
+            c->tasks16w.push_back(make_uint4(i - 1, i - 1, j, 0));
+            c->cells32 += (uint64_t)c->lens[i - 1] * c->lens[j];
+            c->pairs_part += 1;
+            i -= 1;
+          }
+        }
+      }
+    } else {
+      for (uint32_t i = c->row_b; i-- > ra;) {
+        for (uint32_t j = n; j-- > std::max(i + 1, hi);) {
+          c->pairs32.push_back(make_uint2(i, j));
+          c->cells32 += (uint64_t)c->lens[i] * c->lens[j];
+        }
+      }
+      c->pairs_part += c->pairs32.size();
+    }
+  }
+  // ---- strip width: least estimated work over the instantiated variants -----------------------
+  // A strip of K columns costs about K + 2.5 cell-times per row (the row's letter fetch, boundary
+  // load/store and loop control are worth ~2.5 cells: profiles/ r01 sweep), padding included.
+  {
+    double best = 1e300;
+    int bestK = tsq::kStripWidths[0];
+    for (int v = 0; v < tsq::kNumStripWidths; v++) {
+      const int K = tsq::kStripWidths[v];
+      double work = 0;
+      for (uint32_t r = 0; r < nq; r++) {
+        const uint32_t q = c->q_end - 1 - r;
+        const uint32_t l2 = c->lens[lo + 2 * q + 1];
+        work += (double)((l2 + K - 1) / K) * (K + 2.5) * (double)(c->task_prefix[r + 1] - c->task_prefix[r]);
+      }
+      if (work < best * 0.999 || (work <= best * 1.001 && K > bestK)) {
+        if (work < best) best = work;
+        bestK = K;
+      }
+    }
+    c->K = bestK;
+    if (const char* fk = getenv("TSQ_FORCE_K")) {  // developer override for tuning runs
+      tsq::G16Launch v;
+      if (tsq::g16_variant(atoi(fk), (uint32_t)c->nsym, &v)) c->K = atoi(fk);
+    }
+  }
+
+  return TSQ_OK;
+}
+
+// ---- tsq_upload, step 3: interleaved subject database of the packed kernel ---------------------------
+int host_build_subject_db(tsq_ctx* c) {
+  const uint32_t n = c->n, lo = c->lo, hi = c->hi;
+  // ---- 32-way interleaved subject database of the packed kernel ----------------------------------
+  // Per residue the 16-bit byte offset of its profile row (letter * STRIDE(K) * 4), two rows per
+  // 32-bit word, right-aligned to an even row count (a pad entry leads an odd-length sequence),
+  // so one coalesced 128-byte load per warp feeds one row pair of all 32 lanes.
+  {
+    tsq::G16Launch kv;
+    if (!tsq::g16_variant(c->K, (uint32_t)c->nsym, &kv)) return fail(c, TSQ_ERR_INVALID, "no kernel variant K=%d", c->K);
+    const uint32_t scale = (uint32_t)kv.stride * 4u;
+    const uint32_t ngroups = (n + 31) / 32;
+    c->goff.assign(ngroups + 1, 0);
+    uint64_t words = 0;
+    for (uint32_t g = 0; g < ngroups; g++) {
+      c->goff[g] = (uint32_t)words;
+      const uint32_t last = std::min(n, (g + 1) * 32) - 1;
+      const uint32_t len16 = std::min(c->lens[last], c->max_len16);  // longer ones never enter this kernel
+      const uint32_t rows2 = (len16 + 1) / 2 + 3;                    // +3: two-word prefetch slack
+      words += (uint64_t)rows2 * 32;
+      if (words > 0xfffffff0ull) return fail(c, TSQ_ERR_RANGE, "interleaved database too large");
+    }
+    c->goff[ngroups] = (uint32_t)words;
+    TSQ_CUDA(c, c->dbw.reserve(words));
+    c->dbw_size = words;
+    memset(c->dbw.p, 0, words * sizeof(uint32_t));
+    for (uint32_t i = lo; i < hi; i++) {
+      const uint8_t* sq = c->lin.p + c->loff[i];
+      uint32_t* base = c->dbw.p + c->goff[i >> 5] + (i & 31);
+      const uint32_t l = c->lens[i];
+      const uint32_t odd = l & 1u;
+      for (uint32_t r = 0; r < l; r++) {
+        const uint32_t slot = r + odd;  // position in the right-aligned 16-bit stream
+        base[(size_t)(slot >> 1) * 32] |= ((uint32_t)sq[r] * scale) << (16 * (slot & 1u));
+      }
+    }
+  }
+
+  return TSQ_OK;
+}
+
+// ---- tsq_upload, step 4: device buffers and host -> device copies --------------------------------------
+int device_upload(tsq_ctx* c) {
+  const uint32_t n = c->n;
+  const uint64_t npairs = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
+  // ---- biased score table -----------------------------------------------------------------
+  const uint32_t nsym = (uint32_t)c->nsym;
+  std::vector<uint32_t> sbias((size_t)(nsym + 1) * nsym, 0);
+  for (uint32_t a = 0; a < nsym; a++)
+    for (uint32_t b = 0; b < nsym; b++) sbias[a * nsym + b] = (uint32_t)(c->matrix[a * nsym + b] + 2 * c->delta);
+
+  // ---- H2D ----------------------------------------------------------------------------------
+  cudaStream_t s = c->stream;
+  TSQ_CUDA(c, c->d_dbw.reserve(c->dbw_size));
+  TSQ_CUDA(c, c->d_goff.reserve(c->goff.size()));
+  TSQ_CUDA(c, c->d_lin.reserve(c->lin_size));
+  TSQ_CUDA(c, c->d_loff.reserve(c->loff.size()));
+  TSQ_CUDA(c, c->d_lens.reserve(n + 1));
+  TSQ_CUDA(c, c->d_perm.reserve(n + 1));
+  TSQ_CUDA(c, c->d_self.reserve(n + 1));
+  TSQ_CUDA(c, c->d_sbias.reserve(sbias.size()));
+  TSQ_CUDA(c, c->d_prefix.reserve(c->task_prefix.size()));
+  TSQ_CUDA(c, c->d_counter.reserve(16));
+  TSQ_CUDA(c, c->d_sorted.reserve(npairs));
+  if (c->dbw_size) TSQ_CUDA(c, cudaMemcpyAsync(c->d_dbw.p, c->dbw.p, c->dbw_size * 4, cudaMemcpyHostToDevice, s));
+  TSQ_CUDA(c, cudaMemcpyAsync(c->d_goff.p, c->goff.data(), c->goff.size() * 4, cudaMemcpyHostToDevice, s));
+  TSQ_CUDA(c, cudaMemcpyAsync(c->d_lin.p, c->lin.p, c->lin_size, cudaMemcpyHostToDevice, s));
+  TSQ_CUDA(c, cudaMemcpyAsync(c->d_loff.p, c->loff.data(), c->loff.size() * 4, cudaMemcpyHostToDevice, s));
+  if (n) {
+    TSQ_CUDA(c, cudaMemcpyAsync(c->d_lens.p, c->lens.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    TSQ_CUDA(c, cudaMemcpyAsync(c->d_perm.p, c->perm.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    TSQ_CUDA(c, cudaMemcpyAsync(c->d_self.p, c->self_sorted.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  }
+  TSQ_CUDA(c, cudaMemcpyAsync(c->d_sbias.p, sbias.data(), sbias.size() * 4, cudaMemcpyHostToDevice, s));
+  TSQ_CUDA(c, cudaMemcpyAsync(c->d_prefix.p, c->task_prefix.data(), c->task_prefix.size() * 8, cudaMemcpyHostToDevice, s));
+  if (!c->tasks16w.empty()) {
+    TSQ_CUDA(c, c->d_tasks16w.reserve(c->tasks16w.size()));
+    TSQ_CUDA(c, cudaMemcpyAsync(c->d_tasks16w.p, c->tasks16w.data(), c->tasks16w.size() * sizeof(uint4), cudaMemcpyHostToDevice, s));
+  }
+  if (!c->pairs32.empty()) {
+    std::vector<int32_t> smat((size_t)(nsym + 1) * nsym, 0);
+    for (uint32_t a = 0; a < nsym; a++)
+      for (uint32_t b = 0; b < nsym; b++) smat[a * nsym + b] = c->matrix[a * nsym + b];
+    TSQ_CUDA(c, c->d_smat.reserve(smat.size()));
+    TSQ_CUDA(c, c->d_pairs32.reserve(c->pairs32.size()));
+    TSQ_CUDA(c, cudaMemcpyAsync(c->d_smat.p, smat.data(), smat.size() * 4, cudaMemcpyHostToDevice, s));
+    TSQ_CUDA(c, cudaMemcpyAsync(c->d_pairs32.p, c->pairs32.data(), c->pairs32.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
+    TSQ_CUDA(c, cudaStreamSynchronize(s));  // smat is a local
+  }
+  TSQ_CUDA(c, cudaStreamSynchronize(s));
+  c->st.h2d_bytes = c->dbw_size * 4 + c->lin_size + c->goff.size() * 4 + c->loff.size() * 4 + (uint64_t)n * 12 +
+                    sbias.size() * 4 + c->task_prefix.size() * 8;
+  return TSQ_OK;
+}
+
+}  // namespace
+
+namespace {
+
+// ---- tsq_compute: the three score kernels, each enqueued on stream s when it has tasks ---------------
+int enqueue_gotoh16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
+  const uint32_t nq = c->q_end - c->q_begin;
+  const unsigned long long ntasks = c->task_prefix.empty() ? 0 : c->task_prefix[nq];
+  if (ntasks > 0) {
+    tsq::G16Launch v;
+    if (!tsq::g16_variant(c->K, (uint32_t)c->nsym, &v)) return fail(c, TSQ_ERR_INVALID, "no kernel variant K=%d", c->K);
+    const int warps_per_cta = v.tpb / 32;
+    int grid = c->sm_count * v.ctas_sm;
+    const unsigned long long need = (ntasks + warps_per_cta - 1) / warps_per_cta;
+    if ((unsigned long long)grid > need) grid = (int)need;
+    // (r01: shrinking the grid so that every warp runs a whole number of tasks was measured and is
+    //  slower -- 7.8 vs 8.2 TCUPS on C2: warps of a partly filled last wave speed up on their own.)
+    if (const char* eg = getenv("TSQ_GRID")) grid = std::max(1, atoi(eg));
+    const uint32_t maxlen = c->hi > c->lo ? c->lens[c->hi - 1] : 0;
+    const uint32_t bnd_rows = maxlen + 8;  // the row loop prefetches up to 3 rows past the end
+    TSQ_CUDA(c, c->d_bnd.reserve((size_t)grid * warps_per_cta * bnd_rows * 32));
+    TSQ_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), s));
+    const uint32_t lpad = ((maxlen + c->K - 1) / c->K) * c->K;
+    tsq::G16Params p{};
+    p.dbw = c->d_dbw.p;
+    p.goff = c->d_goff.p;
+    p.lin = c->d_lin.p;
+    p.loff = c->d_loff.p;
+    p.lens = c->d_lens.p;
+    p.task_prefix = c->d_prefix.p;
+    p.counter = c->d_counter.p;
+    p.cancel = c->d_cancel;
+    p.bnd = c->d_bnd.p;
+    p.sbias = c->d_sbias.p;
+    p.out = c->d_sorted.p;
+    p.ntasks = ntasks;
+    p.bnd_rows = bnd_rows;
+    p.n_total = c->n;
+    p.lo = c->lo;
+    p.hi = c->hi;
+    p.q_begin = c->q_begin;
+    p.q_end = c->q_end;
+    p.nsym = (uint32_t)c->nsym;
+    p.bias = bias_for(c, lpad);
+    p.delta = c->delta;
+    p.go = c->go;
+    p.gep = c->ge - c->delta;
+    p.negge2 = ((uint32_t)(-(c->ge - c->delta)) & 0xffffu) * 0x10001u;
+    p.goe2 = (uint32_t)(c->go + c->ge - c->delta) * 0x10001u;
+    if (!fits16(c, lpad)) return fail(c, TSQ_ERR_RANGE, "internal: padded length %u outside the 16-bit bound", lpad);
+    TSQ_CUDA(c, tsq::g16_launch(c->K, grid, p, s));
+    launches++;
+  }
+  return TSQ_OK;
+}
+
+int enqueue_wave16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
+  if (!c->tasks16w.empty()) {
+    tsq::W32Launch v;
+    if (!tsq::w16_variant((uint32_t)c->nsym, &v)) return fail(c, TSQ_ERR_INVALID, "no packed wavefront kernel variant");
+    const int warps_per_cta = v.tpb / 32;
+    int grid = c->sm_count * v.ctas_sm;
+    const unsigned long long need = (c->tasks16w.size() + warps_per_cta - 1) / warps_per_cta;
+    if ((unsigned long long)grid > need) grid = (int)need;
+    const uint32_t bnd_rows = c->lens[c->n - 1] + 8;
+    TSQ_CUDA(c, c->d_bnd16w.reserve((size_t)grid * warps_per_cta * ((size_t)bnd_rows + bnd_rows / 4 + 16)));
+    TSQ_CUDA(c, cudaMemsetAsync(c->d_counter.p + 2, 0, 12 * sizeof(unsigned long long), s));
+    tsq::W16Params w{};
+    w.lin = c->d_lin.p;
+    w.loff = c->d_loff.p;
+    w.lens = c->d_lens.p;
+    w.tasks = c->d_tasks16w.p;
+    w.counter = c->d_counter.p + 2;
+    w.cancel = c->d_cancel;
+    w.bnd = c->d_bnd16w.p;
+    w.sbias = c->d_sbias.p;
+    w.out = c->d_sorted.p;
+    w.ntasks = c->tasks16w.size();
+    w.bnd_rows = bnd_rows;
+    w.n_total = c->n;
+    w.nsym = (uint32_t)c->nsym;
+    w.delta = c->delta;
+    w.go = c->go;
+    w.gep = c->ge - c->delta;
+    w.goep = c->go + c->ge - c->delta;
+    w.negge2 = ((uint32_t)(-(c->ge - c->delta)) & 0xffffu) * 0x10001u;
+    TSQ_CUDA(c, tsq::w16_launch(grid, w, s));
+    launches++;
+  }
+  return TSQ_OK;
+}
+
+int enqueue_wave32(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
+  if (!c->pairs32.empty()) {
+    tsq::W32Launch v;
+    if (!tsq::w32_variant((uint32_t)c->nsym, &v)) return fail(c, TSQ_ERR_INVALID, "no wavefront kernel variant");
+    const int warps_per_cta = v.tpb / 32;
+    int grid = c->sm_count * v.ctas_sm;
+    const unsigned long long need = (c->pairs32.size() + warps_per_cta - 1) / warps_per_cta;
+    if ((unsigned long long)grid > need) grid = (int)need;
+    const uint32_t bnd_rows = c->lens[c->n - 1] + 8;
+    TSQ_CUDA(c, c->d_bnd32.reserve((size_t)grid * warps_per_cta * bnd_rows));
+    TSQ_CUDA(c, cudaMemsetAsync(c->d_counter.p + 1, 0, sizeof(unsigned long long), s));
+    tsq::W32Params w{};
+    w.lin = c->d_lin.p;
+    w.loff = c->d_loff.p;
+    w.lens = c->d_lens.p;
+    w.pairs = c->d_pairs32.p;
+    w.counter = c->d_counter.p + 1;
+    w.cancel = c->d_cancel;
+    w.bnd = c->d_bnd32.p;
+    w.smat = c->d_smat.p;
+    w.out = c->d_sorted.p;
+    w.ntasks = c->pairs32.size();
+    w.bnd_rows = bnd_rows;
+    w.n_total = c->n;
+    w.nsym = (uint32_t)c->nsym;
+    w.go = c->go;
+    w.ge = c->ge;
+    w.one = 1;
+    TSQ_CUDA(c, tsq::w32_launch(grid, w, s));
+    launches++;
+  }
+  return TSQ_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int tsq_version(int* major, int* minor) {
@@ -477,240 +861,14 @@ int tsq_upload(tsq_ctx* c) {
   if (!c->have_seqs) return fail(c, TSQ_ERR_STATE, "tsq_upload before tsq_set_sequences");
   const double t0 = now_ms();
   TSQ_CUDA(c, cudaSetDevice(c->device));
-  const uint32_t n = c->n;
-  const uint64_t npairs = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
-
-  // ---- stable length sort ---------------------------------------------------------------
-  c->perm.resize(n);
-  std::iota(c->perm.begin(), c->perm.end(), 0u);
-  std::stable_sort(c->perm.begin(), c->perm.end(),
-                   [&](uint32_t a, uint32_t b) { return c->enc[a].size() < c->enc[b].size(); });
-  c->lens.resize(n);
-  c->loff.resize(n + 1);
-  uint64_t total = 0;
-  c->identity = true;
-  for (uint32_t i = 0; i < n; i++) {
-    const size_t l = c->enc[c->perm[i]].size();
-    if (l > 0x7fffffffu) return fail(c, TSQ_ERR_RANGE, "sequence too long");
-    c->lens[i] = (uint32_t)l;
-    c->loff[i] = (uint32_t)total;
-    total += (l + 15) & ~(size_t)15;   // 16-byte aligned starts: TMA bulk copies read tiles from here
-    if (c->perm[i] != i) c->identity = false;
-  }
-  if (total > 0xfffffff0ull) return fail(c, TSQ_ERR_RANGE, "more than 4 Gi residues");
-  c->loff[n] = (uint32_t)total;
-  TSQ_CUDA(c, c->lin.reserve(total + 2048));   // slack: the last TMA tile of a subject may run past its end
-  c->lin_size = total + 2048;
-  memset(c->lin.p, 0, c->lin_size);
-  c->self_sorted.resize(n);
-  c->self_orig.resize(n);
-  for (uint32_t i = 0; i < n; i++) {
-    const std::vector<uint8_t>& e = c->enc[c->perm[i]];
-    if (!e.empty()) memcpy(c->lin.p + c->loff[i], e.data(), e.size());
-    int64_t s = 0;
-    for (uint8_t a : e) s += c->matrix[a * c->nsym + a];
-    c->self_sorted[i] = (int32_t)s;
-    c->self_orig[c->perm[i]] = (int32_t)s;
-  }
-  // ---- regimes --------------------------------------------------------------------------
-  uint32_t lo = 0;
-  while (lo < n && c->lens[lo] == 0) lo++;
-  uint32_t hi = lo;
-  while (hi < n && c->lens[hi] <= c->max_len16) hi++;
-  if (c->identity && lo > 0) c->identity = false;  // empties are filled in by finalize
-  c->lo = lo;
-  c->hi = hi;
-  if (n > 0) {  // 32-bit range: |H| <= (m+n) * max|score or ge| + 2*go must stay far inside int32
-    const int64_t unit = std::max<int64_t>(std::max(std::abs(c->smin), std::abs(c->smax)), c->ge);
-    if (2 * (int64_t)c->lens[n - 1] * unit + 2 * (int64_t)c->go >= (1ll << 30))
-      return fail(c, TSQ_ERR_RANGE, "sequence of length %u: scores would not fit 32 bits", c->lens[n - 1]);
-  }
-
-  // ---- partition of the sorted rows across ranks (contiguous, balanced by DP cells) ---------
-  const int world = c->prm.part_world, rank = c->prm.part_rank;
-  std::vector<uint32_t> first_row;
-  c->use_w16 = wave16_ok(c, c->nsym, c->prm.flags);
-  plan_rows(c->lens, lo, hi, world, first_row, c->use_w16 ? 1.5 : 2.4);
-  auto boundary = [&](int r) -> uint32_t { return first_row[(size_t)r]; };
-  c->row_a = boundary(rank);
-  c->row_b = boundary(rank + 1);
-  c->part_begin = (n >= 2 && c->row_a + 1 < n) ? tri(c->row_a, c->row_a + 1, n) : npairs;
-  c->part_end = (n >= 2 && c->row_b + 1 < n) ? tri(c->row_b, c->row_b + 1, n) : npairs;
-  if (c->part_begin > c->part_end) c->part_begin = c->part_end;
-
-  // ---- tasks of the packed kernel: query pairs q in [q_begin, q_end) ------------------------
-  const uint32_t nq_all = (hi - lo) / 2;
-  auto row_to_q = [&](uint32_t row) -> uint32_t {
-    if (row <= lo) return 0;
-    return std::min(nq_all, (row - lo + 1) / 2);
-  };
-  c->q_begin = row_to_q(c->row_a);
-  c->q_end = row_to_q(c->row_b);
-  if (c->q_end < c->q_begin) c->q_end = c->q_begin;
-  const uint32_t nq = c->q_end - c->q_begin;
-  c->task_prefix.assign((size_t)nq + 1, 0);
-  c->cells16 = 0;
-  c->pairs_part = 0;
-  {
-    std::vector<uint64_t> suffix(n + 1, 0);
-    for (uint32_t i = n; i-- > 0;) suffix[i] = suffix[i + 1] + c->lens[i];
-    for (uint32_t r = 0; r < nq; r++) {
-      const uint32_t q = c->q_end - 1 - r;
-      const uint32_t a1 = lo + 2 * q;
-      const uint32_t nsub = hi - a1 - 1;
-      c->task_prefix[r + 1] = c->task_prefix[r] + (nsub + 31) / 32;
-      c->cells16 += (uint64_t)c->lens[a1] * (suffix[a1 + 1] - suffix[hi]) +
-                    (uint64_t)c->lens[a1 + 1] * (suffix[a1 + 2] - suffix[hi]);
-      c->pairs_part += (uint64_t)(hi - a1 - 1) + (hi - a1 - 2);
-    }
-  }
-  // ---- tasks of the 32-bit wavefront kernel: every pair with a sequence beyond the packed range,
-  //      restricted to this rank's rows, biggest pairs first -------------------------------------
-  c->cells32 = 0;
-  c->pairs32.clear();
-  c->tasks16w.clear();
-  if (hi < n) {
-    const uint32_t ra = std::max(c->row_a, lo);
-    if (c->use_w16) {
-      // (query pair, subject): subject j long, queries i < j of this rank's rows, two at a time
-      for (uint32_t j = n; j-- > hi;) {
-        const uint32_t top = std::min(c->row_b, j);  // queries in [ra, top)
-        uint32_t i = top;
-        while (i > ra) {
-          if (i - ra >= 2) {
-            c->tasks16w.push_back(make_uint4(i - 2, i - 1, j, 0));
-            c->cells32 += ((uint64_t)c->lens[i - 2] + c->lens[i - 1]) * c->lens[j];
-            c->pairs_part += 2;
-            i -= 2;
-          } else {
-            c->tasks16w.push_back(make_uint4(i - 1, i - 1, j, 0));
-            c->cells32 += (uint64_t)c->lens[i - 1] * c->lens[j];
-            c->pairs_part += 1;
-            i -= 1;
-          }
-        }
-      }
-    } else {
-      for (uint32_t i = c->row_b; i-- > ra;) {
-        for (uint32_t j = n; j-- > std::max(i + 1, hi);) {
-          c->pairs32.push_back(make_uint2(i, j));
-          c->cells32 += (uint64_t)c->lens[i] * c->lens[j];
-        }
-      }
-      c->pairs_part += c->pairs32.size();
-    }
-  }
-  // ---- strip width: least estimated work over the instantiated variants -----------------------
-  // A strip of K columns costs about K + 2.5 cell-times per row (the row's letter fetch, boundary
-  // load/store and loop control are worth ~2.5 cells: profiles/ r01 sweep), padding included.
-  {
-    double best = 1e300;
-    int bestK = tsq::kStripWidths[0];
-    for (int v = 0; v < tsq::kNumStripWidths; v++) {
-      const int K = tsq::kStripWidths[v];
-      double work = 0;
-      for (uint32_t r = 0; r < nq; r++) {
-        const uint32_t q = c->q_end - 1 - r;
-        const uint32_t l2 = c->lens[lo + 2 * q + 1];
-        work += (double)((l2 + K - 1) / K) * (K + 2.5) * (double)(c->task_prefix[r + 1] - c->task_prefix[r]);
-      }
-      if (work < best * 0.999 || (work <= best * 1.001 && K > bestK)) {
-        if (work < best) best = work;
-        bestK = K;
-      }
-    }
-    c->K = bestK;
-    if (const char* fk = getenv("TSQ_FORCE_K")) {  // developer override for tuning runs
-      tsq::G16Launch v;
-      if (tsq::g16_variant(atoi(fk), (uint32_t)c->nsym, &v)) c->K = atoi(fk);
-    }
-  }
-
-  // ---- 32-way interleaved subject database of the packed kernel ----------------------------------
-  // Per residue the 16-bit byte offset of its profile row (letter * STRIDE(K) * 4), two rows per
-  // 32-bit word, right-aligned to an even row count (a pad entry leads an odd-length sequence),
-  // so one coalesced 128-byte load per warp feeds one row pair of all 32 lanes.
-  {
-    tsq::G16Launch kv;
-    if (!tsq::g16_variant(c->K, (uint32_t)c->nsym, &kv)) return fail(c, TSQ_ERR_INVALID, "no kernel variant K=%d", c->K);
-    const uint32_t scale = (uint32_t)kv.stride * 4u;
-    const uint32_t ngroups = (n + 31) / 32;
-    c->goff.assign(ngroups + 1, 0);
-    uint64_t words = 0;
-    for (uint32_t g = 0; g < ngroups; g++) {
-      c->goff[g] = (uint32_t)words;
-      const uint32_t last = std::min(n, (g + 1) * 32) - 1;
-      const uint32_t len16 = std::min(c->lens[last], c->max_len16);  // longer ones never enter this kernel
-      const uint32_t rows2 = (len16 + 1) / 2 + 3;                    // +3: two-word prefetch slack
-      words += (uint64_t)rows2 * 32;
-      if (words > 0xfffffff0ull) return fail(c, TSQ_ERR_RANGE, "interleaved database too large");
-    }
-    c->goff[ngroups] = (uint32_t)words;
-    TSQ_CUDA(c, c->dbw.reserve(words));
-    c->dbw_size = words;
-    memset(c->dbw.p, 0, words * sizeof(uint32_t));
-    for (uint32_t i = lo; i < hi; i++) {
-      const uint8_t* sq = c->lin.p + c->loff[i];
-      uint32_t* base = c->dbw.p + c->goff[i >> 5] + (i & 31);
-      const uint32_t l = c->lens[i];
-      const uint32_t odd = l & 1u;
-      for (uint32_t r = 0; r < l; r++) {
-        const uint32_t slot = r + odd;  // position in the right-aligned 16-bit stream
-        base[(size_t)(slot >> 1) * 32] |= ((uint32_t)sq[r] * scale) << (16 * (slot & 1u));
-      }
-    }
-  }
-
-  // ---- biased score table -----------------------------------------------------------------
-  const uint32_t nsym = (uint32_t)c->nsym;
-  std::vector<uint32_t> sbias((size_t)(nsym + 1) * nsym, 0);
-  for (uint32_t a = 0; a < nsym; a++)
-    for (uint32_t b = 0; b < nsym; b++) sbias[a * nsym + b] = (uint32_t)(c->matrix[a * nsym + b] + 2 * c->delta);
-
-  // ---- H2D ----------------------------------------------------------------------------------
-  cudaStream_t s = c->stream;
-  TSQ_CUDA(c, c->d_dbw.reserve(c->dbw_size));
-  TSQ_CUDA(c, c->d_goff.reserve(c->goff.size()));
-  TSQ_CUDA(c, c->d_lin.reserve(c->lin_size));
-  TSQ_CUDA(c, c->d_loff.reserve(c->loff.size()));
-  TSQ_CUDA(c, c->d_lens.reserve(n + 1));
-  TSQ_CUDA(c, c->d_perm.reserve(n + 1));
-  TSQ_CUDA(c, c->d_self.reserve(n + 1));
-  TSQ_CUDA(c, c->d_sbias.reserve(sbias.size()));
-  TSQ_CUDA(c, c->d_prefix.reserve(c->task_prefix.size()));
-  TSQ_CUDA(c, c->d_counter.reserve(16));
-  TSQ_CUDA(c, c->d_sorted.reserve(npairs));
-  if (c->dbw_size) TSQ_CUDA(c, cudaMemcpyAsync(c->d_dbw.p, c->dbw.p, c->dbw_size * 4, cudaMemcpyHostToDevice, s));
-  TSQ_CUDA(c, cudaMemcpyAsync(c->d_goff.p, c->goff.data(), c->goff.size() * 4, cudaMemcpyHostToDevice, s));
-  TSQ_CUDA(c, cudaMemcpyAsync(c->d_lin.p, c->lin.p, c->lin_size, cudaMemcpyHostToDevice, s));
-  TSQ_CUDA(c, cudaMemcpyAsync(c->d_loff.p, c->loff.data(), c->loff.size() * 4, cudaMemcpyHostToDevice, s));
-  if (n) {
-    TSQ_CUDA(c, cudaMemcpyAsync(c->d_lens.p, c->lens.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    TSQ_CUDA(c, cudaMemcpyAsync(c->d_perm.p, c->perm.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    TSQ_CUDA(c, cudaMemcpyAsync(c->d_self.p, c->self_sorted.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
-  }
-  TSQ_CUDA(c, cudaMemcpyAsync(c->d_sbias.p, sbias.data(), sbias.size() * 4, cudaMemcpyHostToDevice, s));
-  TSQ_CUDA(c, cudaMemcpyAsync(c->d_prefix.p, c->task_prefix.data(), c->task_prefix.size() * 8, cudaMemcpyHostToDevice, s));
-  if (!c->tasks16w.empty()) {
-    TSQ_CUDA(c, c->d_tasks16w.reserve(c->tasks16w.size()));
-    TSQ_CUDA(c, cudaMemcpyAsync(c->d_tasks16w.p, c->tasks16w.data(), c->tasks16w.size() * sizeof(uint4), cudaMemcpyHostToDevice, s));
-  }
-  if (!c->pairs32.empty()) {
-    std::vector<int32_t> smat((size_t)(nsym + 1) * nsym, 0);
-    for (uint32_t a = 0; a < nsym; a++)
-      for (uint32_t b = 0; b < nsym; b++) smat[a * nsym + b] = c->matrix[a * nsym + b];
-    TSQ_CUDA(c, c->d_smat.reserve(smat.size()));
-    TSQ_CUDA(c, c->d_pairs32.reserve(c->pairs32.size()));
-    TSQ_CUDA(c, cudaMemcpyAsync(c->d_smat.p, smat.data(), smat.size() * 4, cudaMemcpyHostToDevice, s));
-    TSQ_CUDA(c, cudaMemcpyAsync(c->d_pairs32.p, c->pairs32.data(), c->pairs32.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
-    TSQ_CUDA(c, cudaStreamSynchronize(s));  // smat is a local
-  }
-  TSQ_CUDA(c, cudaStreamSynchronize(s));
+  int rc = host_sort_and_pack(c);
+  if (rc == TSQ_OK) rc = host_plan_work(c);
+  if (rc == TSQ_OK) rc = host_build_subject_db(c);
+  if (rc == TSQ_OK) rc = device_upload(c);
+  if (rc != TSQ_OK) return rc;
   c->uploaded = true;
   c->computed = c->finalized = c->downloaded = false;
   c->st.upload_ms = now_ms() - t0;
-  c->st.h2d_bytes = c->dbw_size * 4 + c->lin_size + c->goff.size() * 4 + c->loff.size() * 4 + (uint64_t)n * 12 +
-                    sbias.size() * 4 + c->task_prefix.size() * 8;
   return TSQ_OK;
 }
 
@@ -722,115 +880,10 @@ int tsq_compute(tsq_ctx* c) {
   uint32_t launches = 0;
   TSQ_CUDA(c, cudaMemsetAsync(c->d_cancel, 0, sizeof(int), s));
   TSQ_CUDA(c, cudaEventRecord(c->ev0, s));
-  const uint32_t nq = c->q_end - c->q_begin;
-  const unsigned long long ntasks = c->task_prefix.empty() ? 0 : c->task_prefix[nq];
-  if (ntasks > 0) {
-    tsq::G16Launch v;
-    if (!tsq::g16_variant(c->K, (uint32_t)c->nsym, &v)) return fail(c, TSQ_ERR_INVALID, "no kernel variant K=%d", c->K);
-    const int warps_per_cta = v.tpb / 32;
-    int grid = c->sm_count * v.ctas_sm;
-    const unsigned long long need = (ntasks + warps_per_cta - 1) / warps_per_cta;
-    if ((unsigned long long)grid > need) grid = (int)need;
-    // (r01: shrinking the grid so that every warp runs a whole number of tasks was measured and is
-    //  slower -- 7.8 vs 8.2 TCUPS on C2: warps of a partly filled last wave speed up on their own.)
-    if (const char* eg = getenv("TSQ_GRID")) grid = std::max(1, atoi(eg));
-    const uint32_t maxlen = c->hi > c->lo ? c->lens[c->hi - 1] : 0;
-    const uint32_t bnd_rows = maxlen + 8;  // the row loop prefetches up to 3 rows past the end
-    TSQ_CUDA(c, c->d_bnd.reserve((size_t)grid * warps_per_cta * bnd_rows * 32));
-    TSQ_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), s));
-    const uint32_t lpad = ((maxlen + c->K - 1) / c->K) * c->K;
-    tsq::G16Params p{};
-    p.dbw = c->d_dbw.p;
-    p.goff = c->d_goff.p;
-    p.lin = c->d_lin.p;
-    p.loff = c->d_loff.p;
-    p.lens = c->d_lens.p;
-    p.task_prefix = c->d_prefix.p;
-    p.counter = c->d_counter.p;
-    p.cancel = c->d_cancel;
-    p.bnd = c->d_bnd.p;
-    p.sbias = c->d_sbias.p;
-    p.out = c->d_sorted.p;
-    p.ntasks = ntasks;
-    p.bnd_rows = bnd_rows;
-    p.n_total = c->n;
-    p.lo = c->lo;
-    p.hi = c->hi;
-    p.q_begin = c->q_begin;
-    p.q_end = c->q_end;
-    p.nsym = (uint32_t)c->nsym;
-    p.bias = bias_for(c, lpad);
-    p.delta = c->delta;
-    p.go = c->go;
-    p.gep = c->ge - c->delta;
-    p.negge2 = ((uint32_t)(-(c->ge - c->delta)) & 0xffffu) * 0x10001u;
-    p.goe2 = (uint32_t)(c->go + c->ge - c->delta) * 0x10001u;
-    if (!fits16(c, lpad)) return fail(c, TSQ_ERR_RANGE, "internal: padded length %u outside the 16-bit bound", lpad);
-    TSQ_CUDA(c, tsq::g16_launch(c->K, grid, p, s));
-    launches++;
-  }
-  if (!c->tasks16w.empty()) {
-    tsq::W32Launch v;
-    if (!tsq::w16_variant((uint32_t)c->nsym, &v)) return fail(c, TSQ_ERR_INVALID, "no packed wavefront kernel variant");
-    const int warps_per_cta = v.tpb / 32;
-    int grid = c->sm_count * v.ctas_sm;
-    const unsigned long long need = (c->tasks16w.size() + warps_per_cta - 1) / warps_per_cta;
-    if ((unsigned long long)grid > need) grid = (int)need;
-    const uint32_t bnd_rows = c->lens[c->n - 1] + 8;
-    TSQ_CUDA(c, c->d_bnd16w.reserve((size_t)grid * warps_per_cta * ((size_t)bnd_rows + bnd_rows / 4 + 16)));
-    TSQ_CUDA(c, cudaMemsetAsync(c->d_counter.p + 2, 0, 12 * sizeof(unsigned long long), s));
-    tsq::W16Params w{};
-    w.lin = c->d_lin.p;
-    w.loff = c->d_loff.p;
-    w.lens = c->d_lens.p;
-    w.tasks = c->d_tasks16w.p;
-    w.counter = c->d_counter.p + 2;
-    w.cancel = c->d_cancel;
-    w.bnd = c->d_bnd16w.p;
-    w.sbias = c->d_sbias.p;
-    w.out = c->d_sorted.p;
-    w.ntasks = c->tasks16w.size();
-    w.bnd_rows = bnd_rows;
-    w.n_total = c->n;
-    w.nsym = (uint32_t)c->nsym;
-    w.delta = c->delta;
-    w.go = c->go;
-    w.gep = c->ge - c->delta;
-    w.goep = c->go + c->ge - c->delta;
-    w.negge2 = ((uint32_t)(-(c->ge - c->delta)) & 0xffffu) * 0x10001u;
-    TSQ_CUDA(c, tsq::w16_launch(grid, w, s));
-    launches++;
-  }
-  if (!c->pairs32.empty()) {
-    tsq::W32Launch v;
-    if (!tsq::w32_variant((uint32_t)c->nsym, &v)) return fail(c, TSQ_ERR_INVALID, "no wavefront kernel variant");
-    const int warps_per_cta = v.tpb / 32;
-    int grid = c->sm_count * v.ctas_sm;
-    const unsigned long long need = (c->pairs32.size() + warps_per_cta - 1) / warps_per_cta;
-    if ((unsigned long long)grid > need) grid = (int)need;
-    const uint32_t bnd_rows = c->lens[c->n - 1] + 8;
-    TSQ_CUDA(c, c->d_bnd32.reserve((size_t)grid * warps_per_cta * bnd_rows));
-    TSQ_CUDA(c, cudaMemsetAsync(c->d_counter.p + 1, 0, sizeof(unsigned long long), s));
-    tsq::W32Params w{};
-    w.lin = c->d_lin.p;
-    w.loff = c->d_loff.p;
-    w.lens = c->d_lens.p;
-    w.pairs = c->d_pairs32.p;
-    w.counter = c->d_counter.p + 1;
-    w.cancel = c->d_cancel;
-    w.bnd = c->d_bnd32.p;
-    w.smat = c->d_smat.p;
-    w.out = c->d_sorted.p;
-    w.ntasks = c->pairs32.size();
-    w.bnd_rows = bnd_rows;
-    w.n_total = c->n;
-    w.nsym = (uint32_t)c->nsym;
-    w.go = c->go;
-    w.ge = c->ge;
-    w.one = 1;
-    TSQ_CUDA(c, tsq::w32_launch(grid, w, s));
-    launches++;
-  }
+  int rc = enqueue_gotoh16(c, s, launches);                 // regime 1: packed inter-task kernel
+  if (rc == TSQ_OK) rc = enqueue_wave16(c, s, launches);    // regime 2: packed wavefront kernel
+  if (rc == TSQ_OK) rc = enqueue_wave32(c, s, launches);    // regime 2 fallback: 32-bit wavefront kernel
+  if (rc != TSQ_OK) return rc;
   TSQ_CUDA(c, cudaEventRecord(c->ev1, s));
   c->st.launches = launches;
   c->computed = true;
