@@ -268,7 +268,7 @@ def test_dpx_probe_reports_the_alu_rate():
     assert 50 < ops < 80 and 1000 < mhz < 2200
 
 
-@pytest.mark.parametrize("K", [32, 36, 40, 44, 48, 50, 52, 56])
+@pytest.mark.parametrize("K", [30, 32, 36, 40, 44, 48, 50, 52, 56])
 def test_every_strip_width_variant(K, monkeypatch):
     """Each instantiated kernel variant (strip width K), odd and even row counts, both gap-model
     specialisations (immediate -ge' for the defaults, runtime for the rest)."""

@@ -439,6 +439,7 @@ int host_plan_work(tsq_ctx* c) {
         const uint32_t l2 = c->lens[lo + 2 * q + 1];
         work += (double)((l2 + K - 1) / K) * (K + 2.5) * (double)(c->task_prefix[r + 1] - c->task_prefix[r]);
       }
+      if (K <= 32) work *= 1.05;  // the 16-warp variants run ~4-5 % slower per cell (r01 sweep)
       if (work < best * 0.999 || (work <= best * 1.001 && K > bestK)) {
         if (work < best) best = work;
         bestK = K;

@@ -10,6 +10,7 @@ namespace tsq {
 // ---- packed 16-bit inter-task kernel variants -------------------------------------------
 // (K, threads per CTA, CTAs per SM).  Register budget = 65536 / (tpb * ctas_sm).
 #define TSQ_G16_VARIANTS(X) \
+  X(30, 128, 4)             \
   X(32, 128, 4)             \
   X(36, 128, 3)             \
   X(40, 128, 3)             \
@@ -19,7 +20,7 @@ namespace tsq {
   X(52, 128, 3)             \
   X(56, 128, 3)
 
-const int kStripWidths[kNumStripWidths] = {32, 36, 40, 44, 48, 50, 52, 56};
+const int kStripWidths[kNumStripWidths] = {30, 32, 36, 40, 44, 48, 50, 52, 56};
 
 bool g16_variant(int K, uint32_t nsym, G16Launch* out) {
 #define X(KK, TT, MM)                                                                     \

@@ -11,7 +11,7 @@
 namespace tsq {
 
 // Strip widths the packed 16-bit kernel is instantiated for.
-constexpr int kNumStripWidths = 8;
+constexpr int kNumStripWidths = 9;
 extern const int kStripWidths[kNumStripWidths];
 
 struct G16Launch {
