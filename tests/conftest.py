@@ -8,6 +8,16 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def pytest_sessionstart(session):
+    """Build what the tests load if it is not there yet (fresh clone): the CUDA library (nvcc
+    cross-compiles sm_100a without a GPU), the oracle and the C++ adapter."""
+    so = os.path.join(ROOT, "tweakseq_b200", "libtsqb200.so")
+    oracle_so = os.path.join(ROOT, "oracle", "libtsq_oracle.so")
+    if not (os.path.exists(so) and os.path.exists(oracle_so)):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run under gpurun); everything else runs on CPU")
 
