@@ -282,7 +282,7 @@ def main():
             e2e_t += dt
             s2 = run.ctx.stats()
             h2d, d2h = s2["h2d_bytes"], s2["d2h_bytes"]
-            e2e_launches = s2["launches"]
+            e2e_launches = s2["launches"] + s2["upload_launches"]
     e2e_value = cells_total / (e2e_t / e2e_steps) / 1e9
 
     if rank == 0:

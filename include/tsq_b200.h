@@ -87,7 +87,7 @@ typedef struct tsq_stats {
   uint32_t launches;         /* kernels launched by the last tsq_compute */
   uint32_t sm_count;
   uint32_t strip_width;      /* K of the 16-bit kernel variant used */
-  uint32_t reserved;
+  uint32_t upload_launches;  /* kernels launched by the last tsq_upload (subject database build) */
   uint64_t h2d_bytes;        /* bytes the last tsq_upload copied host -> device */
   uint64_t d2h_bytes;        /* bytes the last tsq_download copied device -> host */
   double tree_ms;            /* CUDA-event time of the last tsq_guide_tree (device only) */

@@ -127,8 +127,8 @@ struct tsq_ctx {
   std::vector<uint32_t> loff;             // sorted
   PinnedBuf<uint8_t> lin;                 // sorted, concatenated (pinned staging)
   size_t lin_size = 0;
-  PinnedBuf<uint32_t> dbw;                // interleaved words (pinned staging)
-  size_t dbw_size = 0;
+  size_t dbw_size = 0;                    // interleaved subject database: words (built on the device)
+  uint32_t db_scale = 0;                  // letter -> profile-row byte offset factor (STRIDE(K) * 4)
   std::vector<uint32_t> goff;             // group offsets
   std::vector<int32_t> self_sorted, self_orig;
   bool identity = true;
@@ -455,9 +455,9 @@ int host_plan_work(tsq_ctx* c) {
   return TSQ_OK;
 }
 
-// ---- tsq_upload, step 3: interleaved subject database of the packed kernel ---------------------------
+// ---- tsq_upload, step 3: layout (group offsets) of the interleaved subject database -------------------
 int host_build_subject_db(tsq_ctx* c) {
-  const uint32_t n = c->n, lo = c->lo, hi = c->hi;
+  const uint32_t n = c->n;
   // ---- 32-way interleaved subject database of the packed kernel ----------------------------------
   // Per residue the 16-bit byte offset of its profile row (letter * STRIDE(K) * 4), two rows per
   // 32-bit word, right-aligned to an even row count (a pad entry leads an odd-length sequence),
@@ -478,19 +478,8 @@ int host_build_subject_db(tsq_ctx* c) {
       if (words > 0xfffffff0ull) return fail(c, TSQ_ERR_RANGE, "interleaved database too large");
     }
     c->goff[ngroups] = (uint32_t)words;
-    TSQ_CUDA(c, c->dbw.reserve(words));
-    c->dbw_size = words;
-    memset(c->dbw.p, 0, words * sizeof(uint32_t));
-    for (uint32_t i = lo; i < hi; i++) {
-      const uint8_t* sq = c->lin.p + c->loff[i];
-      uint32_t* base = c->dbw.p + c->goff[i >> 5] + (i & 31);
-      const uint32_t l = c->lens[i];
-      const uint32_t odd = l & 1u;
-      for (uint32_t r = 0; r < l; r++) {
-        const uint32_t slot = r + odd;  // position in the right-aligned 16-bit stream
-        base[(size_t)(slot >> 1) * 32] |= ((uint32_t)sq[r] * scale) << (16 * (slot & 1u));
-      }
-    }
+    c->dbw_size = words;   // the words themselves are written on the device (subject_db_launch)
+    c->db_scale = scale;
   }
 
   return TSQ_OK;
@@ -519,7 +508,6 @@ int device_upload(tsq_ctx* c) {
   TSQ_CUDA(c, c->d_prefix.reserve(c->task_prefix.size()));
   TSQ_CUDA(c, c->d_counter.reserve(16));
   TSQ_CUDA(c, c->d_sorted.reserve(npairs));
-  if (c->dbw_size) TSQ_CUDA(c, cudaMemcpyAsync(c->d_dbw.p, c->dbw.p, c->dbw_size * 4, cudaMemcpyHostToDevice, s));
   TSQ_CUDA(c, cudaMemcpyAsync(c->d_goff.p, c->goff.data(), c->goff.size() * 4, cudaMemcpyHostToDevice, s));
   TSQ_CUDA(c, cudaMemcpyAsync(c->d_lin.p, c->lin.p, c->lin_size, cudaMemcpyHostToDevice, s));
   TSQ_CUDA(c, cudaMemcpyAsync(c->d_loff.p, c->loff.data(), c->loff.size() * 4, cudaMemcpyHostToDevice, s));
@@ -530,6 +518,11 @@ int device_upload(tsq_ctx* c) {
   }
   TSQ_CUDA(c, cudaMemcpyAsync(c->d_sbias.p, sbias.data(), sbias.size() * 4, cudaMemcpyHostToDevice, s));
   TSQ_CUDA(c, cudaMemcpyAsync(c->d_prefix.p, c->task_prefix.data(), c->task_prefix.size() * 8, cudaMemcpyHostToDevice, s));
+  c->st.upload_launches = 0;
+  if (c->dbw_size && c->hi > c->lo) c->st.upload_launches = 1;
+  if (c->dbw_size && c->hi > c->lo)
+    TSQ_CUDA(c, tsq::subject_db_launch(c->d_lin.p, c->d_loff.p, c->d_lens.p, c->d_goff.p, c->d_dbw.p, c->n, c->lo, c->hi,
+                                       c->db_scale, s));
   if (!c->tasks16w.empty()) {
     TSQ_CUDA(c, c->d_tasks16w.reserve(c->tasks16w.size()));
     TSQ_CUDA(c, cudaMemcpyAsync(c->d_tasks16w.p, c->tasks16w.data(), c->tasks16w.size() * sizeof(uint4), cudaMemcpyHostToDevice, s));
@@ -545,7 +538,7 @@ int device_upload(tsq_ctx* c) {
     TSQ_CUDA(c, cudaStreamSynchronize(s));  // smat is a local
   }
   TSQ_CUDA(c, cudaStreamSynchronize(s));
-  c->st.h2d_bytes = c->dbw_size * 4 + c->lin_size + c->goff.size() * 4 + c->loff.size() * 4 + (uint64_t)n * 12 +
+  c->st.h2d_bytes = c->lin_size + c->goff.size() * 4 + c->loff.size() * 4 + (uint64_t)n * 12 +
                     sbias.size() * 4 + c->task_prefix.size() * 8;
   return TSQ_OK;
 }
@@ -807,7 +800,7 @@ int tsq_destroy(tsq_ctx* c) {
   c->d_perm.release(); c->d_sbias.release(); c->d_lin.release(); c->d_self.release();
   c->d_sorted.release(); c->d_scores.release(); c->d_dist.release(); c->d_prefix.release();
   c->d_counter.release(); c->d_bnd.release(); c->h_scores.release(); c->h_dist.release();
-  c->lin.release(); c->dbw.release(); c->d_treeD.release(); c->d_treemin.release(); c->d_treeh.release(); c->d_treeu.release(); c->d_merges.release();
+  c->lin.release(); c->d_treeD.release(); c->d_treemin.release(); c->d_treeh.release(); c->d_treeu.release(); c->d_merges.release();
   c->d_pairs32.release(); c->d_tasks16w.release(); c->d_bnd16w.release(); c->d_bnd32.release(); c->d_smat.release();
   if (c->d_cancel) cudaFree(c->d_cancel);
   if (c->h_one) cudaFreeHost(c->h_one);

@@ -161,6 +161,39 @@ cudaError_t w16_launch(int grid, const W16Params& p, cudaStream_t stream) {
   return cudaErrorInvalidValue;
 }
 
+// ---- interleaved subject database ---------------------------------------------------------------
+__global__ void __launch_bounds__(256) subject_db_kernel(const uint8_t* __restrict__ lin, const uint32_t* __restrict__ loff,
+                                                         const uint32_t* __restrict__ lens, const uint32_t* __restrict__ goff,
+                                                         uint32_t* __restrict__ dbw, uint32_t n, uint32_t lo, uint32_t hi,
+                                                         uint32_t scale) {
+  const uint32_t g = blockIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t i = g * 32 + lane;                       // this thread's sequence
+  const uint32_t words = goff[g + 1] - goff[g];
+  const uint32_t rows2 = words / 32;
+  const bool in = i < n && i >= lo && i < hi;
+  const uint32_t l = in ? lens[i] : 0u;
+  const uint32_t odd = l & 1u;
+  const uint8_t* sq = lin + (in ? loff[i] : 0u);
+  uint32_t* out = dbw + goff[g] + lane;
+  for (uint32_t r2 = threadIdx.x >> 5; r2 < rows2; r2 += blockDim.x >> 5) {
+    // slots 2*r2 and 2*r2+1 of the right-aligned stream hold residues slot - odd
+    const int32_t ra = (int32_t)(2 * r2) - (int32_t)odd, rb = ra + 1;
+    uint32_t w = 0;
+    if (ra >= 0 && (uint32_t)ra < l) w = (uint32_t)sq[ra] * scale;
+    if (rb >= 0 && (uint32_t)rb < l) w |= ((uint32_t)sq[rb] * scale) << 16;
+    out[(size_t)r2 * 32] = w;
+  }
+}
+
+cudaError_t subject_db_launch(const uint8_t* lin, const uint32_t* loff, const uint32_t* lens, const uint32_t* goff,
+                              uint32_t* dbw, uint32_t n, uint32_t lo, uint32_t hi, uint32_t scale, cudaStream_t stream) {
+  const uint32_t ngroups = (n + 31) / 32;
+  if (ngroups == 0) return cudaSuccess;
+  subject_db_kernel<<<ngroups, 256, 0, stream>>>(lin, loff, lens, goff, dbw, n, lo, hi, scale);
+  return cudaGetLastError();
+}
+
 // ---- UPGMA guide tree -----------------------------------------------------------------------------
 cudaError_t upgma_launch(const UpgmaParams& p, cudaStream_t stream) {
   if (p.n < 2) return cudaSuccess;

@@ -45,6 +45,12 @@ cudaError_t w16_launch(int grid, const W16Params& p, cudaStream_t stream);
 // UPGMA guide tree: init (one CTA per row) + one persistent CTA for the n-1 merges.
 cudaError_t upgma_launch(const UpgmaParams& p, cudaStream_t stream);
 
+// Builds the 32-way interleaved subject database of the packed kernel from the linear residues:
+// per residue the 16-bit byte offset of its profile row, two rows per word, right-aligned to an
+// even row count (gotoh16.cuh).  One CTA per group of 32 sequences; every word of the group is written.
+cudaError_t subject_db_launch(const uint8_t* lin, const uint32_t* loff, const uint32_t* lens, const uint32_t* goff,
+                              uint32_t* dbw, uint32_t n, uint32_t lo, uint32_t hi, uint32_t scale, cudaStream_t stream);
+
 struct FinalizeParams {
   const int32_t* sorted;      // packed triangle, sorted order
   const uint32_t* lens;       // sorted lengths
