@@ -99,3 +99,16 @@ def test_run_fasta_writes_the_guide_tree_next_to_the_matrix(tmp_path):
     assert t.B200Gotoh().run(fin, fout) == 0
     txt = open(fout + ".dnd").read().strip()
     assert txt.endswith(";") and txt.count("(") == 24 and all(f"{l}:" in txt for l in labels)
+
+
+@pytest.mark.gpu
+def test_newick_labels_are_sanitised(tmp_path):
+    import tweakseq_b200 as t
+    with t.Context() as ctx:
+        ctx.set_sequences(["ACDEFGHIK", "ACDEFGHIR", "WWWWWWW"])
+        ctx.run()
+        path = str(tmp_path / "t.dnd")
+        ctx.write_newick(path, ["sp|P1|A:1", "b (x)", "c;d,e"])
+    txt = open(path).read().strip()
+    assert "sp|P1|A_1:" in txt and "b__x_:" in txt and "c_d_e:" in txt
+    assert txt.count("(") == 2 and txt.count(")") == 2 and txt.endswith(";") and txt.count(";") == 1

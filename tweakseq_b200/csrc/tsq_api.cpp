@@ -1108,8 +1108,11 @@ int tsq_write_newick(tsq_ctx* c, const char* const* labels, const char* path) {
   FILE* f = fopen(path, "w");
   if (!f) return fail(c, TSQ_ERR_IO, "cannot write %s", path);
   auto leaf_name = [&](uint32_t i) -> std::string {
-    if (labels && labels[i]) return labels[i];
-    return "s" + std::to_string(i);
+    if (!(labels && labels[i])) return "s" + std::to_string(i);
+    std::string name = labels[i];   // Newick structure characters inside a label would break the tree
+    for (char& ch : name)
+      if (strchr("():;,[]'\" \t", ch)) ch = '_';
+    return name.empty() ? "s" + std::to_string(i) : name;
   };
   if (n == 0) {
     fputs(";\n", f);
