@@ -472,3 +472,20 @@ def test_cancel_while_the_kernels_run_stops_early():
         flag.value = 0
         ctx.run(cancel=flag)                      # the context is reusable after a cancel
         assert len(ctx.scores()) == len(seqs) * (len(seqs) - 1) // 2
+
+
+def test_randomised_gap_models_all_three_kernels_agree():
+    """Random gap penalties and ragged lengths: the packed inter-task kernel, the packed wavefront
+    kernel and the 32-bit wavefront kernel must all reproduce the oracle."""
+    rng = np.random.default_rng(2026)
+    for trial in range(14):
+        alphabet = int(rng.integers(0, 2))
+        letters = "ACGTN" if alphabet else AA
+        go, ge = int(rng.integers(0, 21)), int(rng.integers(0, 6))
+        n = int(rng.integers(3, 40))
+        hi = 1500 if alphabet else 600
+        seqs = ragged(rng, n, 0, hi, letters)
+        rs, _, _, _ = oracle_run(seqs, alphabet, go, ge)
+        for flags in (0, t.FLAG_FORCE_S32, t.FLAG_FORCE_S32 | t.FLAG_NO_WAVE16):
+            s, _, _, _ = gpu_run(seqs, alphabet=alphabet, gap_open=go, gap_extend=ge, flags=flags | t.FLAG_NO_DISTANCES)
+            assert (s == rs).all(), (trial, alphabet, go, ge, flags, np.nonzero(s != rs)[0][:5])
