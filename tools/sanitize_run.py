@@ -1,0 +1,24 @@
+"""Small jobs through every kernel, for compute-sanitizer (memcheck / racecheck / initcheck)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import tweakseq_b200 as t
+from tweakseq_b200 import synth
+from oracle import pyoracle as o
+
+def job(seqs, alphabet=0, flags=0, tree=False):
+    with t.Context(alphabet=alphabet, flags=flags) as ctx:
+        ctx.set_sequences(seqs); ctx.run()
+        s = ctx.scores()
+        if tree: ctx.guide_tree()
+    enc = [o.encode(x, alphabet) for x in seqs]
+    ref, _ = o.all_pairs(enc, o.matrix(alphabet), 11 if alphabet == 0 else 10, 1, nthreads=4)
+    assert (s == ref).all()
+
+rng = np.random.default_rng(0)
+prot = ["".join(rng.choice(list("ARNDCQEGHILKMFPSTWYV"), int(l))) for l in rng.integers(0, 130, 70)]
+job(prot, tree=True)                                            # gotoh16 + finalize + subject_db + upgma
+nt = ["".join(rng.choice(list("ACGT"), int(l))) for l in rng.integers(1, 1300, 12)]
+job(nt, alphabet=1, flags=t.FLAG_FORCE_S32)                      # wave16 (TMA ring)
+job(nt[:8], alphabet=1, flags=t.FLAG_FORCE_S32 | t.FLAG_NO_WAVE16)  # wave32
+print("sanitize_run ok")

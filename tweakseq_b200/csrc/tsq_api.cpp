@@ -74,6 +74,13 @@ struct DevBuf {
     if (e == cudaSuccess) cap = n;
     return e;
   }
+  // scratch that kernels read a few slack rows beyond what they wrote (prefetch): zero it once
+  cudaError_t reserve_zeroed(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    cudaError_t e = reserve(n);
+    if (e == cudaSuccess) e = cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T));
+    return e;
+  }
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
@@ -563,7 +570,7 @@ int enqueue_gotoh16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
     if (const char* eg = getenv("TSQ_GRID")) grid = std::max(1, atoi(eg));
     const uint32_t maxlen = c->hi > c->lo ? c->lens[c->hi - 1] : 0;
     const uint32_t bnd_rows = maxlen + 8;  // the row loop prefetches up to 3 rows past the end
-    TSQ_CUDA(c, c->d_bnd.reserve((size_t)grid * warps_per_cta * bnd_rows * 32));
+    TSQ_CUDA(c, c->d_bnd.reserve_zeroed((size_t)grid * warps_per_cta * bnd_rows * 32));
     TSQ_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), s));
     const uint32_t lpad = ((maxlen + c->K - 1) / c->K) * c->K;
     tsq::G16Params p{};
@@ -608,7 +615,7 @@ int enqueue_wave16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
     const unsigned long long need = (c->tasks16w.size() + warps_per_cta - 1) / warps_per_cta;
     if ((unsigned long long)grid > need) grid = (int)need;
     const uint32_t bnd_rows = c->lens[c->n - 1] + 8;
-    TSQ_CUDA(c, c->d_bnd16w.reserve((size_t)grid * warps_per_cta * ((size_t)bnd_rows + bnd_rows / 4 + 16)));
+    TSQ_CUDA(c, c->d_bnd16w.reserve_zeroed((size_t)grid * warps_per_cta * ((size_t)bnd_rows + bnd_rows / 4 + 16)));
     TSQ_CUDA(c, cudaMemsetAsync(c->d_counter.p + 2, 0, 12 * sizeof(unsigned long long), s));
     tsq::W16Params w{};
     w.lin = c->d_lin.p;
@@ -644,7 +651,7 @@ int enqueue_wave32(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
     const unsigned long long need = (c->pairs32.size() + warps_per_cta - 1) / warps_per_cta;
     if ((unsigned long long)grid > need) grid = (int)need;
     const uint32_t bnd_rows = c->lens[c->n - 1] + 8;
-    TSQ_CUDA(c, c->d_bnd32.reserve((size_t)grid * warps_per_cta * bnd_rows));
+    TSQ_CUDA(c, c->d_bnd32.reserve_zeroed((size_t)grid * warps_per_cta * bnd_rows));
     TSQ_CUDA(c, cudaMemsetAsync(c->d_counter.p + 1, 0, sizeof(unsigned long long), s));
     tsq::W32Params w{};
     w.lin = c->d_lin.p;

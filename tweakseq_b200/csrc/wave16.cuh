@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
       }
       mbar_wait_warp(&tbar[0], tph0);
       tph0 ^= 1u;
-      uint32_t nlet = *reinterpret_cast<const uint32_t*>(stile + ((0u - 4u * (uint32_t)lane) & (2 * TILE - 1)));
+      uint32_t nlet = lane == 0 ? *reinterpret_cast<const uint32_t*>(stile) : 0u;
       const uint32_t nsteps = nquads + 31;
       for (uint32_t s = 0; s < nsteps; ++s) {
         const uint32_t let4 = nlet;
@@ -198,7 +198,10 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
               bulk_copy_g2s(stile + ((tix + 1) & 1u) * TILE, sq + (size_t)(tix + 1) * TILE, TILE, br);
             }
           }
-          nlet = *reinterpret_cast<const uint32_t*>(stile + ((4u * (s1 - (uint32_t)lane)) & (2 * TILE - 1)));
+          // lanes that have not started yet must not touch the ring: their wrapped offsets can fall
+          // into a slot a TMA copy is still writing (racecheck), and they need no letters anyway
+          if (s1 >= (uint32_t)lane)
+            nlet = *reinterpret_cast<const uint32_t*>(stile + ((4u * (s1 - (uint32_t)lane)) & (2 * TILE - 1)));
         }
         // ---- lane 0's left boundary of this step's four rows (computed by all lanes, uniform code) ----
         uint32_t lH[4], lE[4];
