@@ -59,6 +59,10 @@ extern "C" {
 #define TSQ_FLAG_FORCE_S32 1u     /* never use the packed 16-bit kernel */
 #define TSQ_FLAG_NO_DISTANCES 2u  /* skip the fp64 distance pass (scores only) */
 #define TSQ_FLAG_NO_WAVE16 4u     /* long sequences: 32-bit wavefront kernel only, not the packed one */
+#define TSQ_FLAG_IDENTITY 8u      /* identity-aware scoring: among the optimal alignments of a
+                                     pair take the one with most identical residue pairs, report that count
+                                     (tsq_identities) and make the distance 1 - identities/min(len_i, len_j),
+                                     the ClustalW pairwise distance.  Scores are unchanged. */
 
 typedef struct tsq_ctx tsq_ctx;
 
@@ -143,6 +147,8 @@ int tsq_run(tsq_ctx *ctx, tsq_progress_cb cb, void *user, volatile int *cancel);
 int tsq_scores(tsq_ctx *ctx, const int32_t **packed_upper, uint64_t *count);
 int tsq_distances(tsq_ctx *ctx, const double **packed_upper, uint64_t *count);
 int tsq_self_scores(tsq_ctx *ctx, const int32_t **self, uint32_t *n);
+/* TSQ_FLAG_IDENTITY only: identical residue pairs on the chosen optimal alignment, per pair. */
+int tsq_identities(tsq_ctx *ctx, const int32_t **packed_upper, uint64_t *count);
 
 /*
  * Device results (after tsq_compute): pointers into this context's device memory, packed

@@ -302,3 +302,40 @@ void tsq_oracle_upgma(const double *packed, uint32_t n, uint32_t *left, uint32_t
   }
   free(D); free(size); free(node); free(act);
 }
+
+/* ---- identity-aware score ---- */
+void tsq_oracle_gotoh_id(const uint8_t *a, int m, const uint8_t *b, int n, const int8_t *mat, int nsym,
+                         int go, int ge, int32_t *score, int32_t *identities) {
+  *identities = 0;
+  if (m == 0 || n == 0) {
+    *score = tsq_oracle_gotoh(a, m, b, n, mat, nsym, go, ge);
+    return;
+  }
+  const int64_t M = (int64_t)1 << 32;
+  const int64_t NEG = INT64_MIN / 4;
+  const int64_t gok = go * M, gek = ge * M, goek = gok + gek;
+  int64_t *H = (int64_t *)malloc(sizeof(int64_t) * 2 * (size_t)(n + 1));
+  int64_t *F = H + (n + 1);
+  H[0] = 0;
+  for (int j = 1; j <= n; j++) { H[j] = -(gok + j * gek); F[j] = NEG; }
+  for (int i = 1; i <= m; i++) {
+    const int8_t *srow = mat + (size_t)a[i - 1] * nsym;
+    int64_t diag = H[0], left = -(gok + i * gek), E = NEG;
+    H[0] = left;
+    for (int j = 1; j <= n; j++) {
+      int64_t e1 = E - gek, e2 = left - goek;
+      E = e1 > e2 ? e1 : e2;
+      int64_t f1 = F[j] - gek, f2 = H[j] - goek;
+      int64_t f = f1 > f2 ? f1 : f2;
+      int64_t h = diag + srow[b[j - 1]] * M + (a[i - 1] == b[j - 1] ? 1 : 0);
+      if (E > h) h = E;
+      if (f > h) h = f;
+      diag = H[j]; H[j] = h; F[j] = f; left = h;
+    }
+  }
+  int64_t key = H[n];
+  int64_t sc = key >> 32;          /* floor division by 2^32 */
+  *score = (int32_t)sc;
+  *identities = (int32_t)(key - sc * M);
+  free(H);
+}

@@ -67,6 +67,15 @@ uint64_t tsq_oracle_pair_list(const uint8_t *seqs, const uint64_t *offs, const u
                               const uint32_t *pj, uint64_t npairs, int32_t *out, int nthreads);
 
 /*
+ * Identity-aware score: the Gotoh score of tsq_oracle_gotoh() and, among all
+ * alignments that reach it, the largest number of columns pairing identical symbols.  Restated as
+ * one DP over 64-bit keys  score * 2^32 + identities  (every substitution score and gap penalty
+ * scaled by 2^32, +1 for identical symbols).  Either length 0: score as tsq_oracle_gotoh, 0 identities.
+ */
+void tsq_oracle_gotoh_id(const uint8_t *a, int m, const uint8_t *b, int n, const int8_t *mat, int nsym,
+                         int go, int ge, int32_t *score, int32_t *identities);
+
+/*
  * UPGMA guide tree of a packed fp64 distance matrix (spec in
  * tweakseq_b200/csrc/upgma.cuh): naive O(n^3) restatement.  Step t merges the active slot pair
  * (a < b) of smallest distance (ties: smallest a, then smallest b), the merged cluster keeps slot a,

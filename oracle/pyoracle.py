@@ -50,6 +50,8 @@ def lib():
         L.tsq_oracle_pair_list.restype = C.c_uint64
         L.tsq_oracle_pair_list.argtypes = [u8p, u64p, u32p, i8p, C.c_int, C.c_int, C.c_int, u32p, u32p,
                                            C.c_uint64, i32p, C.c_int]
+        L.tsq_oracle_gotoh_id.restype = None
+        L.tsq_oracle_gotoh_id.argtypes = [u8p, C.c_int, u8p, C.c_int, i8p, C.c_int, C.c_int, C.c_int, i32p, i32p]
         L.tsq_oracle_upgma.restype = None
         L.tsq_oracle_upgma.argtypes = [C.POINTER(C.c_double), C.c_uint32, u32p, u32p, C.POINTER(C.c_double)]
         _lib = L
@@ -185,3 +187,26 @@ def newick(left, right, height, labels) -> str:
     import sys
     sys.setrecursionlimit(max(10000, 4 * n))
     return rec(2 * n - 2, -1.0) + ";"
+
+
+def gotoh_id(a: np.ndarray, b: np.ndarray, mat: np.ndarray, go: int, ge: int):
+    """(score, identities): the Gotoh score and the most identities among the optimal alignments."""
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    m8 = np.ascontiguousarray(mat, dtype=np.int8)
+    sc, nid = C.c_int32(), C.c_int32()
+    lib().tsq_oracle_gotoh_id(_p(a, C.c_uint8), len(a), _p(b, C.c_uint8), len(b), _p(m8, C.c_int8), m8.shape[0], go, ge,
+                              C.byref(sc), C.byref(nid))
+    return sc.value, nid.value
+
+
+def all_pairs_id(encoded, mat, go, ge):
+    """Packed (scores, identities, clustalw distances) by the identity-aware oracle (single thread)."""
+    n = len(encoded)
+    sc, nid, d = [], [], []
+    for i in range(n):
+        for j in range(i + 1, n):
+            s, k = gotoh_id(encoded[i], encoded[j], mat, go, ge)
+            ml = min(len(encoded[i]), len(encoded[j]))
+            sc.append(s); nid.append(k); d.append(1.0 - k / ml if ml > 0 else 1.0)
+    return np.array(sc, np.int32), np.array(nid, np.int32), np.array(d, np.float64)

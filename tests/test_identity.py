@@ -1,0 +1,105 @@
+"""identity-aware scoring.  CPU leg pins the oracle's rule (best score first, then
+most identities) against a brute-force enumeration of every alignment of tiny sequences; the gpu leg
+checks the CUDA path (32-bit inter-task kernel and 32-bit wavefront kernel) against the oracle."""
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as o
+
+MAT = o.matrix(0)
+
+
+def brute_force(a, b, mat, go, ge):
+    """Best (score, identities) over ALL global alignments, lexicographic."""
+    best = None
+    m, n = len(a), len(b)
+
+    def rec(i, j, score, nid, state):       # state: 0 none/diag, 1 gap in a (consuming b), 2 gap in b
+        nonlocal best
+        if i == m and j == n:
+            cand = (score, nid)
+            if best is None or cand > best:
+                best = cand
+            return
+        if i < m and j < n:
+            rec(i + 1, j + 1, score + int(mat[a[i]][b[j]]), nid + (a[i] == b[j]), 0)
+        if j < n:
+            rec(i, j + 1, score - ge - (go if state != 1 else 0), nid, 1)
+        if i < m:
+            rec(i + 1, j, score - ge - (go if state != 2 else 0), nid, 2)
+    rec(0, 0, 0, 0, 0)
+    return best
+
+
+def test_identity_oracle_matches_brute_force_on_tiny_inputs():
+    rng = np.random.default_rng(8)
+    for _ in range(250):
+        a = rng.integers(0, 6, rng.integers(1, 6)).tolist()      # small alphabet: many ties and identities
+        b = rng.integers(0, 6, rng.integers(1, 6)).tolist()
+        go, ge = int(rng.integers(0, 4)), int(rng.integers(0, 3))
+        s, k = o.gotoh_id(np.array(a), np.array(b), MAT, go, ge)
+        assert (s, k) == brute_force(a, b, MAT.tolist(), go, ge), (a, b, go, ge)
+        assert s == o.gotoh(np.array(a, np.uint8), np.array(b, np.uint8), MAT, go, ge)     # the score itself is unchanged
+
+
+def test_identity_oracle_edge_cases():
+    assert o.gotoh_id(o.encode("ACDEF"), o.encode("ACDEF"), MAT, 11, 1) == (o.score_str("ACDEF", "ACDEF"), 5)
+    assert o.gotoh_id(o.encode(""), o.encode("ACD"), MAT, 11, 1) == (-14, 0)
+    assert o.gotoh_id(o.encode("WWWW"), o.encode("WWCWW"), MAT, 11, 1)[1] == 4
+    # co-optimal alignments with different identity counts: go = ge = 0 makes many paths tie
+    s, k = o.gotoh_id(o.encode("AXA"), o.encode("AA"), MAT, 0, 0)
+    assert (s, k) == (8, 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags_extra", [0, 1], ids=["gotoh32", "wave32"])      # 1 = TSQ_FLAG_FORCE_S32
+def test_gpu_identity_mode_matches_oracle(flags_extra):
+    import tweakseq_b200 as t
+    from tweakseq_b200 import synth
+    rng = np.random.default_rng(70 + flags_extra)
+    fam = synth.protein(18, (60, 200, 120, 40), 1, family=True)
+    rag = ["".join(rng.choice(list("ARNDCQEGHILKMFPSTWYVBZX"), int(l))) for l in rng.integers(0, 180, 30)]
+    seqs = fam + rag + ["", "A", "acdefg"]
+    for go, ge in ((11, 1), (0, 0), (4, 3)):
+        with t.Context(gap_open=go, gap_extend=ge, flags=t.FLAG_IDENTITY | flags_extra) as ctx:
+            ctx.set_sequences(seqs)
+            ctx.run()
+            s, k, d, st = ctx.scores(), ctx.identities(), ctx.distances(), ctx.stats()
+        enc = [o.encode(x) for x in seqs]
+        rs, rk, rd = o.all_pairs_id(enc, MAT, go, ge)
+        assert (s == rs).all() and (k == rk).all()
+        assert d.tobytes() == rd.tobytes()
+        assert st["cells_s16"] == 0 and st["cells_s32"] > 0
+        plain, _ = o.all_pairs(enc, MAT, go, ge, nthreads=4)
+        assert (s == plain).all()              # identity mode never changes the scores
+
+
+@pytest.mark.gpu
+def test_gpu_identity_mode_nucleotide_and_long():
+    import tweakseq_b200 as t
+    rng = np.random.default_rng(72)
+    base = "".join(rng.choice(list("ACGT"), 9000))
+    seqs = [base, base[:4000] + base[4100:], "".join(rng.choice(list("ACGT"), 8500)), "ACGT" * 50, "ACGTN"]
+    with t.Context(alphabet=1, flags=t.FLAG_IDENTITY) as ctx:      # 9 kb > 8192: wavefront path with wide keys
+        ctx.set_sequences(seqs)
+        ctx.run()
+        s, k = ctx.scores(), ctx.identities()
+    enc = [o.encode(x, 1) for x in seqs]
+    rs, rk, _ = o.all_pairs_id(enc, o.matrix(1), 10, 1)
+    assert (s == rs).all() and (k == rk).all()
+
+
+@pytest.mark.gpu
+def test_wide_gap_penalties_use_the_32_bit_inter_task_kernel():
+    import tweakseq_b200 as t
+    rng = np.random.default_rng(73)
+    seqs = ["".join(rng.choice(list("ARNDCQEGHILKMFPSTWYV"), int(l))) for l in rng.integers(1, 150, 60)]
+    with t.Context(gap_open=4000, gap_extend=900) as ctx:           # no room for 16 bits, sequences short
+        ctx.set_sequences(seqs)
+        ctx.run()
+        s, st = ctx.scores(), ctx.stats()
+    enc = [o.encode(x) for x in seqs]
+    ref, cells = o.all_pairs(enc, MAT, 4000, 900, nthreads=4)
+    assert (s == ref).all() and st["cells_s32"] == cells and st["cells_s16"] == 0

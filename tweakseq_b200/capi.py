@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 PROTEIN, NUCLEOTIDE = 0, 1
-FLAG_FORCE_S32, FLAG_NO_DISTANCES, FLAG_NO_WAVE16 = 1, 2, 4
+FLAG_FORCE_S32, FLAG_NO_DISTANCES, FLAG_NO_WAVE16, FLAG_IDENTITY = 1, 2, 4, 8
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libtsqb200.so")
@@ -55,7 +55,7 @@ LOG_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p)
 SYMBOLS = ["tsq_version", "tsq_version_string", "tsq_status_string", "tsq_device_count", "tsq_default_params",
            "tsq_create", "tsq_destroy", "tsq_last_error", "tsq_set_sequences", "tsq_set_sequences_flat", "tsq_upload", "tsq_compute",
            "tsq_download", "tsq_set_stream", "tsq_synchronize", "tsq_run", "tsq_scores", "tsq_distances",
-           "tsq_self_scores", "tsq_device_scores", "tsq_partition", "tsq_finalize", "tsq_device_results",
+           "tsq_self_scores", "tsq_identities", "tsq_device_scores", "tsq_partition", "tsq_finalize", "tsq_device_results",
            "tsq_get_stats", "tsq_measure_dpx_rate", "tsq_run_fasta", "tsq_plan_partition", "tsq_guide_tree",
            "tsq_write_newick"]
 
@@ -101,6 +101,7 @@ def load_library():
     L.tsq_scores.argtypes = [vp, C.POINTER(i32p), u64p]
     L.tsq_distances.argtypes = [vp, C.POINTER(C.POINTER(C.c_double)), u64p]
     L.tsq_self_scores.argtypes = [vp, C.POINTER(i32p), C.POINTER(C.c_uint32)]
+    L.tsq_identities.argtypes = [vp, C.POINTER(i32p), u64p]
     L.tsq_device_scores.argtypes = [vp, C.POINTER(vp), u64p]
     L.tsq_partition.argtypes = [vp, u64p, u64p]
     L.tsq_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), u64p]
@@ -249,6 +250,14 @@ class Context:
         self._ck(self._L.tsq_distances(self._h, C.byref(p), C.byref(cnt)))
         if cnt.value == 0:
             return np.zeros(0, np.float64)
+        return np.ctypeslib.as_array(p, shape=(cnt.value,)).copy()
+
+    def identities(self) -> np.ndarray:
+        """FLAG_IDENTITY: identical residue pairs on the chosen optimal alignment, packed like scores()."""
+        p, cnt = C.POINTER(C.c_int32)(), C.c_uint64()
+        self._ck(self._L.tsq_identities(self._h, C.byref(p), C.byref(cnt)))
+        if cnt.value == 0:
+            return np.zeros(0, np.int32)
         return np.ctypeslib.as_array(p, shape=(cnt.value,)).copy()
 
     def self_scores(self) -> np.ndarray:

@@ -146,6 +146,11 @@ struct tsq_ctx {
   std::vector<uint2> pairs32;             // tasks of the 32-bit wavefront kernel (sorted indices)
   std::vector<uint4> tasks16w;            // tasks of the packed wavefront kernel (i1, i2, j, 0)
   bool use_w16 = false;
+  uint32_t inter_max = 0;                 // longest sequence the inter-task kernel of this job takes
+  bool use_g32 = false;                   // [lo, hi) runs on the 32-bit inter-task kernel instead of the packed one
+  uint32_t idshift = 0;                   // identity mode: keys are score * 2^idshift + identities
+  int go_k = 0, ge_k = 0;                 // gap penalties in key units (scaled by 2^idshift in identity mode)
+  std::vector<int32_t> smat_k;            // (nsym+1) x nsym score table in key units
   uint32_t q_begin = 0, q_end = 0;
   int K = 0;
   uint64_t cells16 = 0, cells32 = 0, pairs_part = 0;
@@ -153,7 +158,7 @@ struct tsq_ctx {
   // device
   DevBuf<uint32_t> d_dbw, d_goff, d_loff, d_lens, d_perm, d_sbias;
   DevBuf<uint8_t> d_lin;
-  DevBuf<int32_t> d_self, d_sorted, d_scores;
+  DevBuf<int32_t> d_self, d_sorted, d_scores, d_nid;
   DevBuf<double> d_dist;
   DevBuf<unsigned long long> d_prefix, d_counter;
   DevBuf<uint2> d_bnd;
@@ -169,7 +174,7 @@ struct tsq_ctx {
   DevBuf<int2> d_bnd32;
   DevBuf<int32_t> d_smat;
   // host results
-  PinnedBuf<int32_t> h_scores;
+  PinnedBuf<int32_t> h_scores, h_nid;
   PinnedBuf<double> h_dist;
 
   // Cancel flag the kernels poll at every task fetch.  It lives in DEVICE memory and is written by a
@@ -340,17 +345,46 @@ int host_sort_and_pack(tsq_ctx* c) {
   // ---- regimes --------------------------------------------------------------------------
   uint32_t lo = 0;
   while (lo < n && c->lens[lo] == 0) lo++;
+  // Which inter-task kernel takes the short sequences [lo, hi): the packed 16-bit one when the
+  // score range admits it; the 32-bit one (gotoh32.cuh) in identity mode (keys are wide) or when the
+  // gap/score parameters leave the packed kernel no usable range.  Longer sequences: wavefront.
+  const bool idmode = (c->prm.flags & TSQ_FLAG_IDENTITY) != 0;
+  const uint32_t kMaxLen32 = 8192;
+  c->use_g32 = idmode || (c->max_len16 < 64 && !(c->prm.flags & TSQ_FLAG_FORCE_S32));
+  const uint32_t inter_max = c->use_g32 ? ((c->prm.flags & TSQ_FLAG_FORCE_S32) ? 0u : kMaxLen32) : c->max_len16;
+  c->inter_max = inter_max;
   uint32_t hi = lo;
-  while (hi < n && c->lens[hi] <= c->max_len16) hi++;
+  while (hi < n && c->lens[hi] <= inter_max) hi++;
+  // key units: identity mode scales scores and penalties by M = 2^idshift > longest sequence
+  c->idshift = 0;
+  if (idmode) {
+    uint32_t sh = 1;
+    while ((1u << sh) <= (n ? c->lens[n - 1] : 0u)) sh++;
+    c->idshift = sh;
+  }
+  {
+    const int64_t M = 1ll << c->idshift;
+    const uint32_t nsym = (uint32_t)c->nsym;
+    c->go_k = (int)(c->go * M);
+    c->ge_k = (int)(c->ge * M);
+    c->smat_k.assign((size_t)(nsym + 1) * nsym, 0);
+    for (uint32_t a = 0; a < nsym; a++)
+      for (uint32_t b = 0; b < nsym; b++)
+        c->smat_k[a * nsym + b] = (int32_t)(c->matrix[a * nsym + b] * M + ((idmode && a == b) ? 1 : 0));
+    if (n > 0) {
+      // 32-bit range of the keys: H <= max(S) * L from above; from below H >= the all-gap path
+      // -(2 go + 2 L ge), E and F one more gap opening below that, t = H + S one min(S) below.
+      const int64_t L = c->lens[n - 1];
+      const int64_t bound = std::max<int64_t>((int64_t)std::max(c->smax, 0) * L, 3ll * c->go + (2 * L + 2) * c->ge) +
+                            std::abs(c->smin) + 2;
+      if (bound * M >= (1ll << 31) - (1ll << 20))
+        return fail(c, TSQ_ERR_RANGE, "sequence of length %u: %s would not fit 32 bits", c->lens[n - 1],
+                    idmode ? "identity-aware keys" : "scores");
+    }
+  }
   if (c->identity && lo > 0) c->identity = false;  // empties are filled in by finalize
   c->lo = lo;
   c->hi = hi;
-  if (n > 0) {  // 32-bit range: |H| <= (m+n) * max|score or ge| + 2*go must stay far inside int32
-    const int64_t unit = std::max<int64_t>(std::max(std::abs(c->smin), std::abs(c->smax)), c->ge);
-    if (2 * (int64_t)c->lens[n - 1] * unit + 2 * (int64_t)c->go >= (1ll << 30))
-      return fail(c, TSQ_ERR_RANGE, "sequence of length %u: scores would not fit 32 bits", c->lens[n - 1]);
-  }
-
   return TSQ_OK;
 }
 
@@ -361,7 +395,7 @@ int host_plan_work(tsq_ctx* c) {
   // ---- partition of the sorted rows across ranks (contiguous, balanced by DP cells) ---------
   const int world = c->prm.part_world, rank = c->prm.part_rank;
   std::vector<uint32_t> first_row;
-  c->use_w16 = wave16_ok(c, c->nsym, c->prm.flags);
+  c->use_w16 = wave16_ok(c, c->nsym, c->prm.flags) && c->idshift == 0;   // identity keys are too wide to pack
   plan_rows(c->lens, lo, hi, world, first_row, c->use_w16 ? 1.5 : 2.4);
   auto boundary = [&](int r) -> uint32_t { return first_row[(size_t)r]; };
   c->row_a = boundary(rank);
@@ -370,11 +404,13 @@ int host_plan_work(tsq_ctx* c) {
   c->part_end = (n >= 2 && c->row_b + 1 < n) ? tri(c->row_b, c->row_b + 1, n) : npairs;
   if (c->part_begin > c->part_end) c->part_begin = c->part_end;
 
-  // ---- tasks of the packed kernel: query pairs q in [q_begin, q_end) ------------------------
-  const uint32_t nq_all = (hi - lo) / 2;
+  // ---- tasks of the inter-task kernel over [lo, hi) ------------------------------------------------
+  // packed kernel: one task row per query PAIR (rows lo+2q, lo+2q+1); 32-bit kernel: per query (lo+q)
+  const uint32_t per = c->use_g32 ? 1u : 2u;
+  const uint32_t nq_all = c->use_g32 ? (hi > lo ? hi - lo - 1 : 0u) : (hi - lo) / 2;
   auto row_to_q = [&](uint32_t row) -> uint32_t {
     if (row <= lo) return 0;
-    return std::min(nq_all, (row - lo + 1) / 2);
+    return std::min(nq_all, (row - lo + per - 1) / per);
   };
   c->q_begin = row_to_q(c->row_a);
   c->q_end = row_to_q(c->row_b);
@@ -382,23 +418,28 @@ int host_plan_work(tsq_ctx* c) {
   const uint32_t nq = c->q_end - c->q_begin;
   c->task_prefix.assign((size_t)nq + 1, 0);
   c->cells16 = 0;
+  c->cells32 = 0;
   c->pairs_part = 0;
   {
     std::vector<uint64_t> suffix(n + 1, 0);
     for (uint32_t i = n; i-- > 0;) suffix[i] = suffix[i + 1] + c->lens[i];
     for (uint32_t r = 0; r < nq; r++) {
       const uint32_t q = c->q_end - 1 - r;
-      const uint32_t a1 = lo + 2 * q;
+      const uint32_t a1 = lo + per * q;
       const uint32_t nsub = hi - a1 - 1;
       c->task_prefix[r + 1] = c->task_prefix[r] + (nsub + 31) / 32;
-      c->cells16 += (uint64_t)c->lens[a1] * (suffix[a1 + 1] - suffix[hi]) +
-                    (uint64_t)c->lens[a1 + 1] * (suffix[a1 + 2] - suffix[hi]);
-      c->pairs_part += (uint64_t)(hi - a1 - 1) + (hi - a1 - 2);
+      if (c->use_g32) {
+        c->cells32 += (uint64_t)c->lens[a1] * (suffix[a1 + 1] - suffix[hi]);
+        c->pairs_part += (uint64_t)(hi - a1 - 1);
+      } else {
+        c->cells16 += (uint64_t)c->lens[a1] * (suffix[a1 + 1] - suffix[hi]) +
+                      (uint64_t)c->lens[a1 + 1] * (suffix[a1 + 2] - suffix[hi]);
+        c->pairs_part += (uint64_t)(hi - a1 - 1) + (hi - a1 - 2);
+      }
     }
   }
   // ---- tasks of the 32-bit wavefront kernel: every pair with a sequence beyond the packed range,
   //      restricted to this rank's rows, biggest pairs first -------------------------------------
-  c->cells32 = 0;
   c->pairs32.clear();
   c->tasks16w.clear();
   if (hi < n) {
@@ -443,7 +484,7 @@ int host_plan_work(tsq_ctx* c) {
       double work = 0;
       for (uint32_t r = 0; r < nq; r++) {
         const uint32_t q = c->q_end - 1 - r;
-        const uint32_t l2 = c->lens[lo + 2 * q + 1];
+        const uint32_t l2 = c->lens[c->use_g32 ? lo + q : lo + 2 * q + 1];
         work += (double)((l2 + K - 1) / K) * (K + 2.5) * (double)(c->task_prefix[r + 1] - c->task_prefix[r]);
       }
       if (K <= 32) work *= 1.05;  // the 16-warp variants run ~4-5 % slower per cell (r01 sweep)
@@ -479,7 +520,7 @@ int host_build_subject_db(tsq_ctx* c) {
     for (uint32_t g = 0; g < ngroups; g++) {
       c->goff[g] = (uint32_t)words;
       const uint32_t last = std::min(n, (g + 1) * 32) - 1;
-      const uint32_t len16 = std::min(c->lens[last], c->max_len16);  // longer ones never enter this kernel
+      const uint32_t len16 = std::min(c->lens[last], c->inter_max);  // longer ones never enter this kernel
       const uint32_t rows2 = (len16 + 1) / 2 + 3;                    // +3: two-word prefetch slack
       words += (uint64_t)rows2 * 32;
       if (words > 0xfffffff0ull) return fail(c, TSQ_ERR_RANGE, "interleaved database too large");
@@ -534,15 +575,13 @@ int device_upload(tsq_ctx* c) {
     TSQ_CUDA(c, c->d_tasks16w.reserve(c->tasks16w.size()));
     TSQ_CUDA(c, cudaMemcpyAsync(c->d_tasks16w.p, c->tasks16w.data(), c->tasks16w.size() * sizeof(uint4), cudaMemcpyHostToDevice, s));
   }
-  if (!c->pairs32.empty()) {
-    std::vector<int32_t> smat((size_t)(nsym + 1) * nsym, 0);
-    for (uint32_t a = 0; a < nsym; a++)
-      for (uint32_t b = 0; b < nsym; b++) smat[a * nsym + b] = c->matrix[a * nsym + b];
+  if (!c->pairs32.empty() || c->use_g32) {
+    const std::vector<int32_t>& smat = c->smat_k;   // key units (= plain scores unless identity mode)
     TSQ_CUDA(c, c->d_smat.reserve(smat.size()));
-    TSQ_CUDA(c, c->d_pairs32.reserve(c->pairs32.size()));
+    TSQ_CUDA(c, c->d_pairs32.reserve(c->pairs32.size() + 1));
     TSQ_CUDA(c, cudaMemcpyAsync(c->d_smat.p, smat.data(), smat.size() * 4, cudaMemcpyHostToDevice, s));
-    TSQ_CUDA(c, cudaMemcpyAsync(c->d_pairs32.p, c->pairs32.data(), c->pairs32.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
-    TSQ_CUDA(c, cudaStreamSynchronize(s));  // smat is a local
+    if (!c->pairs32.empty())
+      TSQ_CUDA(c, cudaMemcpyAsync(c->d_pairs32.p, c->pairs32.data(), c->pairs32.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
   }
   TSQ_CUDA(c, cudaStreamSynchronize(s));
   c->st.h2d_bytes = c->lin_size + c->goff.size() * 4 + c->loff.size() * 4 + (uint64_t)n * 12 +
@@ -572,6 +611,33 @@ int enqueue_gotoh16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
     const uint32_t bnd_rows = maxlen + 8;  // the row loop prefetches up to 3 rows past the end
     TSQ_CUDA(c, c->d_bnd.reserve_zeroed((size_t)grid * warps_per_cta * bnd_rows * 32));
     TSQ_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), s));
+    if (c->use_g32) {   // 32-bit inter-task kernel (identity mode, or parameters too wide for 16 bits)
+      tsq::G32Params g{};
+      g.dbw = c->d_dbw.p;
+      g.goff = c->d_goff.p;
+      g.lin = c->d_lin.p;
+      g.loff = c->d_loff.p;
+      g.lens = c->d_lens.p;
+      g.task_prefix = c->d_prefix.p;
+      g.counter = c->d_counter.p;
+      g.cancel = c->d_cancel;
+      g.bnd = reinterpret_cast<int2*>(c->d_bnd.p);
+      g.smat = c->d_smat.p;
+      g.out = c->d_sorted.p;
+      g.ntasks = ntasks;
+      g.bnd_rows = bnd_rows;
+      g.n_total = c->n;
+      g.lo = c->lo;
+      g.hi = c->hi;
+      g.q_begin = c->q_begin;
+      g.q_end = c->q_end;
+      g.nsym = (uint32_t)c->nsym;
+      g.go = c->go_k;
+      g.ge = c->ge_k;
+      TSQ_CUDA(c, tsq::g32_launch(c->K, grid, g, s));
+      launches++;
+      return TSQ_OK;
+    }
     const uint32_t lpad = ((maxlen + c->K - 1) / c->K) * c->K;
     tsq::G16Params p{};
     p.dbw = c->d_dbw.p;
@@ -667,8 +733,8 @@ int enqueue_wave32(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
     w.bnd_rows = bnd_rows;
     w.n_total = c->n;
     w.nsym = (uint32_t)c->nsym;
-    w.go = c->go;
-    w.ge = c->ge;
+    w.go = c->go_k;
+    w.ge = c->ge_k;
     w.one = 1;
     TSQ_CUDA(c, tsq::w32_launch(grid, w, s));
     launches++;
@@ -805,7 +871,7 @@ int tsq_destroy(tsq_ctx* c) {
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
   c->d_dbw.release(); c->d_goff.release(); c->d_loff.release(); c->d_lens.release();
   c->d_perm.release(); c->d_sbias.release(); c->d_lin.release(); c->d_self.release();
-  c->d_sorted.release(); c->d_scores.release(); c->d_dist.release(); c->d_prefix.release();
+  c->d_sorted.release(); c->d_scores.release(); c->d_nid.release(); c->h_nid.release(); c->d_dist.release(); c->d_prefix.release();
   c->d_counter.release(); c->d_bnd.release(); c->h_scores.release(); c->h_dist.release();
   c->lin.release(); c->d_treeD.release(); c->d_treemin.release(); c->d_treeh.release(); c->d_treeu.release(); c->d_merges.release();
   c->d_pairs32.release(); c->d_tasks16w.release(); c->d_bnd16w.release(); c->d_bnd32.release(); c->d_smat.release();
@@ -899,17 +965,24 @@ int tsq_finalize(tsq_ctx* c) {
   const uint32_t n = c->n;
   const uint64_t npairs = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
   const bool want_dist = !(c->prm.flags & TSQ_FLAG_NO_DISTANCES);
-  if (npairs > 0 && (want_dist || !c->identity)) {
+  if (npairs > 0 && (want_dist || !c->identity || c->idshift)) {
     tsq::FinalizeParams f{};
     f.sorted = c->d_sorted.p;
     f.lens = c->d_lens.p;
     f.perm = c->d_perm.p;
     f.self = c->d_self.p;
-    if (c->identity) {
+    const bool inplace = c->identity && c->idshift == 0;   // identity keys are decoded into a separate buffer
+    if (inplace) {
       f.out_scores = c->d_sorted.p;
     } else {
       TSQ_CUDA(c, c->d_scores.reserve(npairs));
       f.out_scores = c->d_scores.p;
+    }
+    f.idshift = c->idshift;
+    f.out_nid = nullptr;
+    if (c->idshift) {
+      TSQ_CUDA(c, c->d_nid.reserve(npairs));
+      f.out_nid = c->d_nid.p;
     }
     f.out_dist = nullptr;
     if (want_dist) {
@@ -958,8 +1031,12 @@ int tsq_download(tsq_ctx* c) {
   cudaStream_t s = c->stream;
   if (npairs > 0 && c->finalized) {
     TSQ_CUDA(c, c->h_scores.reserve(npairs));
-    const int32_t* src = c->identity ? c->d_sorted.p : c->d_scores.p;
+    const int32_t* src = (c->identity && c->idshift == 0) ? c->d_sorted.p : c->d_scores.p;
     TSQ_CUDA(c, cudaMemcpyAsync(c->h_scores.p, src, npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (c->idshift) {
+      TSQ_CUDA(c, c->h_nid.reserve(npairs));
+      TSQ_CUDA(c, cudaMemcpyAsync(c->h_nid.p, c->d_nid.p, npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
     if (want_dist) {
       TSQ_CUDA(c, c->h_dist.reserve(npairs));
       TSQ_CUDA(c, cudaMemcpyAsync(c->h_dist.p, c->d_dist.p, npairs * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1024,6 +1101,15 @@ int tsq_distances(tsq_ctx* c, const double** out, uint64_t* count) {
   return TSQ_OK;
 }
 
+int tsq_identities(tsq_ctx* c, const int32_t** out, uint64_t* count) {
+  if (!c || !out) return TSQ_ERR_INVALID;
+  if (!(c->prm.flags & TSQ_FLAG_IDENTITY)) return fail(c, TSQ_ERR_STATE, "identities need TSQ_FLAG_IDENTITY");
+  if (!c->downloaded) return fail(c, TSQ_ERR_STATE, "no results: call tsq_run or tsq_download first");
+  *out = c->h_nid.p;
+  if (count) *count = c->n < 2 ? 0 : (uint64_t)c->n * (c->n - 1) / 2;
+  return TSQ_OK;
+}
+
 int tsq_self_scores(tsq_ctx* c, const int32_t** self, uint32_t* n) {
   if (!c || !self) return TSQ_ERR_INVALID;
   if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "no sequences uploaded");
@@ -1051,7 +1137,7 @@ int tsq_partition(tsq_ctx* c, uint64_t* b, uint64_t* e) {
 int tsq_device_results(tsq_ctx* c, void** d_scores, void** d_dist, uint64_t* count) {
   if (!c) return TSQ_ERR_INVALID;
   if (!c->finalized) return fail(c, TSQ_ERR_STATE, "tsq_device_results before tsq_finalize");
-  if (d_scores) *d_scores = c->identity ? (void*)c->d_sorted.p : (void*)c->d_scores.p;
+  if (d_scores) *d_scores = (c->identity && c->idshift == 0) ? (void*)c->d_sorted.p : (void*)c->d_scores.p;
   if (d_dist) *d_dist = (c->prm.flags & TSQ_FLAG_NO_DISTANCES) ? nullptr : (void*)c->d_dist.p;
   if (count) *count = c->n < 2 ? 0 : (uint64_t)c->n * (c->n - 1) / 2;
   return TSQ_OK;

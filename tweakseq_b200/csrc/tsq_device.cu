@@ -60,6 +60,23 @@ cudaError_t g16_launch(int K, int grid, const G16Params& p, cudaStream_t stream)
   return cudaErrorInvalidValue;
 }
 
+cudaError_t g32_launch(int K, int grid, const G32Params& p, cudaStream_t stream) {
+  G16Launch v;
+  if (!g16_variant(K, p.nsym, &v)) return cudaErrorInvalidValue;
+#define X(KK, TT, MM)                                                                          \
+  if (K == KK) {                                                                               \
+    auto kern = gotoh32_kernel<KK, TT, MM>;                                                    \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                         (int)v.smem);                                         \
+    if (e != cudaSuccess) return e;                                                            \
+    kern<<<grid, TT, v.smem, stream>>>(p);                                                     \
+    return cudaGetLastError();                                                                 \
+  }
+  TSQ_G16_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
 // ---- 32-bit wavefront kernel ----------------------------------------------------------------
 // nucleotides (5 symbols): 24 columns per lane, 768 per pass, 15 KB of profile per warp, 12 warps/SM;
 // proteins (23 symbols): 8 columns per lane, 256 per pass, 23.5 KB of profile per warp, 8 warps/SM.
@@ -231,18 +248,30 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
       } else {
         s = p.sorted[sidx];
       }
+      int32_t nid = 0;
+      if (p.idshift && li != 0) {   // key = score * 2^idshift + identities, identities < 2^idshift
+        nid = s & (int32_t)((1u << p.idshift) - 1u);
+        s >>= p.idshift;            // arithmetic shift = floor division: exact for negative scores
+      }
       unsigned long long oidx = sidx;
       if (!p.identity) {
         const uint32_t oj = p.perm[j];
         const unsigned long long a = oi < oj ? oi : oj, b = oi < oj ? oj : oi;
         oidx = tri_index(a, b, n);
       }
-      if (p.out_scores != p.sorted || li == 0) p.out_scores[oidx] = s;
+      if (p.out_scores != p.sorted || li == 0 || p.idshift) p.out_scores[oidx] = s;
+      if (p.out_nid) p.out_nid[oidx] = nid;
       if (p.out_dist) {
         const int32_t sj = p.self[j];
         const int32_t mn = si < sj ? si : sj;
         double d = 1.0;
-        if (mn > 0) d = __dsub_rn(1.0, __ddiv_rn((double)s, (double)mn));
+        if (p.idshift) {            // ClustalW pairwise distance: 1 - identities / shorter length
+          const uint32_t lj = p.lens[j];
+          const uint32_t ml = li < lj ? li : lj;
+          if (ml > 0) d = __dsub_rn(1.0, __ddiv_rn((double)nid, (double)ml));
+        } else if (mn > 0) {
+          d = __dsub_rn(1.0, __ddiv_rn((double)s, (double)mn));
+        }
         p.out_dist[oidx] = d;
       }
     }

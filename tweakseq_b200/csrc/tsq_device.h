@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "gotoh16.cuh"
+#include "gotoh32.cuh"
 #include "wave32.cuh"
 #include "wave16.cuh"
 #include "upgma.cuh"
@@ -26,6 +27,9 @@ struct G16Launch {
 bool g16_variant(int K, uint32_t nsym, G16Launch* out);
 // Launch the packed 16-bit kernel: grid CTAs of the variant's size on `stream`.
 cudaError_t g16_launch(int K, int grid, const G16Params& p, cudaStream_t stream);
+
+// 32-bit inter-task kernel (gotoh32.cuh): same strip widths / launch shapes as the packed one.
+cudaError_t g32_launch(int K, int grid, const G32Params& p, cudaStream_t stream);
 
 // 32-bit wavefront kernel: columns per lane (KW) is chosen from the alphabet size so that the
 // per-warp profile fits shared memory; *warps_per_cta / *ctas_sm describe the launch shape.
@@ -61,6 +65,8 @@ struct FinalizeParams {
   uint32_t n;
   int32_t go, ge;
   uint32_t identity;          // perm is the identity and there are no empty sequences
+  uint32_t idshift;           // identity mode: sorted[] holds score * 2^idshift + identities; 0 = off
+  int32_t* out_nid;           // identity mode: identities, packed triangle, original order
 };
 cudaError_t finalize_launch(const FinalizeParams& p, cudaStream_t stream);
 
