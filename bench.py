@@ -336,6 +336,19 @@ def main():
                 line["guide_tree"] = {"algorithm": "UPGMA", "n": len(seqs), "gpu_ms": run.ctx.stats()["tree_ms"]}
             except Exception as e:   # never let the extra row break the contract line
                 line["guide_tree"] = {"error": str(e)}
+        if world == 1 and args.workload == "c2":
+            # the other "next" row: identity-aware scoring, 32-bit inter-task kernel
+            try:
+                with t.Context(flags=t.FLAG_IDENTITY | t.FLAG_NO_DISTANCES, device=local) as ictx:
+                    ictx.set_sequences_flat(host_buf, host_offs)
+                    ictx.upload()
+                    for _ in range(3):
+                        ictx.compute(); ictx.synchronize()
+                    ist = ictx.stats()
+                line["identity_mode"] = {"kernel": "gotoh32_kernel", "kernel_ms": ist["kernel_ms"], "gcups": ist["gcups_kernel"],
+                                         "dtype": "int32 keys = score * 2^k + identities"}
+            except Exception as e:
+                line["identity_mode"] = {"error": str(e)}
         if world == 1 and not args.no_cpu and alphabet == 0:
             threads = os.cpu_count() or 1
             g, sample = cpu_oracle_gcups(seqs, 10.0, threads)
