@@ -179,6 +179,19 @@ int tsq_guide_tree(tsq_ctx *ctx, const tsq_merge **merges, uint32_t *count);
 int tsq_write_newick(tsq_ctx *ctx, const char *const *labels, const char *path);
 
 /*
+ * Consensus annotation of an alignment: what Consensus::calculate
+ * (tweakseq/Core/Annotations/Consensus.cpp:80-161) computes on the GUI thread in O(cols * rows^2),
+ * here per column from a histogram of residue classes in O(rows + 24^2).  rows[r] has ncols
+ * characters (what `residues[c].unicode() & 0xff` yields: only 'A'..'Z' are residues, everything
+ * else -- gaps, lower case -- is the "not a residue" class 99 of Consensus.cpp:99-105).  out
+ * receives ncols characters: the residue of the first row with the best BLOSUM62-weighted sum
+ * against all other rows if its count of positively scoring partners reaches `plurality`, else
+ * '?'.  plurality < 0 selects the reference's default, nrows / 2 (Consensus.cpp:164-175).
+ */
+int tsq_consensus(tsq_ctx *ctx, const char *const *rows, uint32_t nrows, uint32_t ncols,
+                  double plurality, char *out);
+
+/*
  * Host-only planning (no device needed): the packed-index slab [begins[r], ends[r]) -- in the
  * library's length-sorted order -- that rank r of `world` computes for sequences of the given
  * encoded lengths.  Same arithmetic tsq_upload uses; lets the host layer size its gather.

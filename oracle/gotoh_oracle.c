@@ -339,3 +339,42 @@ void tsq_oracle_gotoh_id(const uint8_t *a, int m, const uint8_t *b, int n, const
   *identities = (int32_t)(key - sc * M);
   free(H);
 }
+
+/* ---- consensus annotation: Consensus.cpp:80-161 restated ---- */
+void tsq_oracle_consensus(const char *const *rows, uint32_t nrows, uint32_t ncols, double plurality, char *out) {
+  if (nrows == 0) { for (uint32_t c = 0; c < ncols; c++) out[c] = '?'; return; }
+  double *scores = (double *)malloc(sizeof(double) * nrows);
+  unsigned char *rindex = (unsigned char *)malloc((size_t)nrows * ncols);
+  for (uint32_t s = 0; s < nrows; s++)                       /* :95-106 */
+    for (uint32_t c = 0; c < ncols; c++) {
+      int idx = (int)(unsigned char)rows[s][c] - 65;
+      rindex[(size_t)s * ncols + c] = (idx < 0 || idx > 25) ? 99 : protein_index[idx];
+    }
+  for (uint32_t c = 0; c < ncols; c++) {                     /* :108-152 */
+    double hiScore = 0.0, riMatches = 0;
+    uint32_t riHiScore = 0;
+    for (uint32_t ri = 0; ri < nrows; ri++) {
+      scores[ri] = 0.0;
+      double matches = 0.0;
+      for (uint32_t rj = 0; rj < nrows; rj++) {
+        if (ri == rj) continue;
+        double weight = 1.0;
+        int resi = rindex[(size_t)ri * ncols + c], resj = rindex[(size_t)rj * ncols + c];
+        if (resi == 99 && resj == 99) {
+          scores[ri] += weight;
+          if (weight > 0) matches += weight;
+        } else if (resi == 99 || resj == 99) {
+          scores[ri] += -4 * weight;
+        } else {
+          double tmp = tsq_oracle_blosum62[resi * 23 + resj] * weight;
+          scores[ri] += tmp;
+          if (tmp > 0) matches += weight;
+        }
+      }
+      if (ri == 0) { hiScore = scores[ri]; riHiScore = ri; riMatches = matches; }
+      else if (scores[ri] > hiScore) { hiScore = scores[ri]; riHiScore = ri; riMatches = matches; }
+    }
+    out[c] = riMatches >= plurality ? rows[riHiScore][c] : '?';
+  }
+  free(scores); free(rindex);
+}

@@ -76,6 +76,13 @@ void tsq_oracle_gotoh_id(const uint8_t *a, int m, const uint8_t *b, int n, const
                          int go, int ge, int32_t *score, int32_t *identities);
 
 /*
+ * Consensus annotation: line-by-line restatement of Consensus::calculate,
+ * tweakseq/Core/Annotations/Consensus.cpp:80-161, doubles and all: rows[r] has ncols characters
+ * (already `& 0xff`), out gets ncols characters, '?' where the winner's matches < plurality.
+ */
+void tsq_oracle_consensus(const char *const *rows, uint32_t nrows, uint32_t ncols, double plurality, char *out);
+
+/*
  * UPGMA guide tree of a packed fp64 distance matrix (spec in
  * tweakseq_b200/csrc/upgma.cuh): naive O(n^3) restatement.  Step t merges the active slot pair
  * (a < b) of smallest distance (ties: smallest a, then smallest b), the merged cluster keeps slot a,

@@ -52,6 +52,8 @@ def lib():
                                            C.c_uint64, i32p, C.c_int]
         L.tsq_oracle_gotoh_id.restype = None
         L.tsq_oracle_gotoh_id.argtypes = [u8p, C.c_int, u8p, C.c_int, i8p, C.c_int, C.c_int, C.c_int, i32p, i32p]
+        L.tsq_oracle_consensus.restype = None
+        L.tsq_oracle_consensus.argtypes = [C.POINTER(C.c_char_p), C.c_uint32, C.c_uint32, C.c_double, C.c_char_p]
         L.tsq_oracle_upgma.restype = None
         L.tsq_oracle_upgma.argtypes = [C.POINTER(C.c_double), C.c_uint32, u32p, u32p, C.POINTER(C.c_double)]
         _lib = L
@@ -210,3 +212,13 @@ def all_pairs_id(encoded, mat, go, ge):
             ml = min(len(encoded[i]), len(encoded[j]))
             sc.append(s); nid.append(k); d.append(1.0 - k / ml if ml > 0 else 1.0)
     return np.array(sc, np.int32), np.array(nid, np.int32), np.array(d, np.float64)
+
+
+def consensus(rows, plurality: float | None = None) -> str:
+    """Consensus::calculate restated (oracle, O(cols * rows^2)); plurality defaults to rows/2."""
+    raw = [r.encode("latin-1", "replace") if isinstance(r, str) else bytes(r) for r in rows]
+    ncols = len(raw[0]) if raw else 0
+    arr = (C.c_char_p * max(len(raw), 1))(*raw) if raw else (C.c_char_p * 1)()
+    out = C.create_string_buffer(ncols + 1)
+    lib().tsq_oracle_consensus(arr, len(raw), ncols, len(raw) / 2.0 if plurality is None else plurality, out)
+    return out.raw[:ncols].decode("latin-1")

@@ -57,7 +57,7 @@ SYMBOLS = ["tsq_version", "tsq_version_string", "tsq_status_string", "tsq_device
            "tsq_download", "tsq_set_stream", "tsq_synchronize", "tsq_run", "tsq_scores", "tsq_distances",
            "tsq_self_scores", "tsq_identities", "tsq_device_scores", "tsq_partition", "tsq_finalize", "tsq_device_results",
            "tsq_get_stats", "tsq_measure_dpx_rate", "tsq_run_fasta", "tsq_plan_partition", "tsq_guide_tree",
-           "tsq_write_newick"]
+           "tsq_write_newick", "tsq_consensus"]
 
 _lib = None
 
@@ -108,6 +108,7 @@ def load_library():
     L.tsq_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.tsq_guide_tree.argtypes = [vp, C.POINTER(C.POINTER(Merge)), C.POINTER(C.c_uint32)]
     L.tsq_write_newick.argtypes = [vp, C.POINTER(C.c_char_p), C.c_char_p]
+    L.tsq_consensus.argtypes = [vp, C.POINTER(C.c_char_p), C.c_uint32, C.c_uint32, C.c_double, C.c_char_p]
     L.tsq_plan_partition.argtypes = [C.POINTER(Params), C.POINTER(C.c_uint32), C.c_uint32, C.c_int32, u64p, u64p]
     L.tsq_measure_dpx_rate.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.tsq_run_fasta.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(Params), LOG_CB, vp, C.POINTER(C.c_int)]
@@ -301,6 +302,17 @@ class Context:
             raw = [l.encode() for l in labels]
             arr = (C.c_char_p * len(raw))(*raw)
         self._ck(self._L.tsq_write_newick(self._h, arr, path.encode()))
+
+    def consensus(self, rows, plurality: float = -1.0) -> str:
+        """Consensus annotation of equal-length aligned rows (Consensus.cpp:80-161); '?' = no plurality."""
+        raw = [r.encode("latin-1", "replace") if isinstance(r, str) else bytes(r) for r in rows]
+        ncols = len(raw[0]) if raw else 0
+        if any(len(r) != ncols for r in raw):
+            raise ValueError("alignment rows differ in length")
+        arr = (C.c_char_p * max(len(raw), 1))(*raw) if raw else (C.c_char_p * 1)()
+        out = C.create_string_buffer(ncols + 1)
+        self._ck(self._L.tsq_consensus(self._h, arr, len(raw), ncols, plurality, out))
+        return out.raw[:ncols].decode("latin-1")
 
     def stats(self) -> dict:
         st = Stats()

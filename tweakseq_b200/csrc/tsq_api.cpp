@@ -1245,6 +1245,48 @@ int tsq_write_newick(tsq_ctx* c, const char* const* labels, const char* path) {
   return TSQ_OK;
 }
 
+int tsq_consensus(tsq_ctx* c, const char* const* rows, uint32_t nrows, uint32_t ncols, double plurality, char* out) {
+  if (!c) return TSQ_ERR_INVALID;
+  if ((nrows > 0 && !rows) || (ncols > 0 && !out)) return fail(c, TSQ_ERR_INVALID, "null alignment / output");
+  if (ncols == 0) return TSQ_OK;
+  if (nrows == 0) {
+    memset(out, '?', ncols);
+    return TSQ_OK;
+  }
+  if (plurality < 0) plurality = (double)nrows / 2.0;   // Consensus.cpp:164-175
+  TSQ_CUDA(c, cudaSetDevice(c->device));
+  const size_t cells = (size_t)nrows * ncols;
+  PinnedBuf<uint8_t> h;
+  DevBuf<uint8_t> d_aln, d_out, d_tab;
+  int rc = TSQ_OK;
+  cudaError_t e = h.reserve(cells + ncols);
+  if (e == cudaSuccess) e = d_aln.reserve(cells);
+  if (e == cudaSuccess) e = d_out.reserve(ncols);
+  if (e == cudaSuccess) e = d_tab.reserve(23 * 23 + 32);
+  if (e == cudaSuccess) {
+    for (uint32_t r = 0; r < nrows; r++) {
+      if (!rows[r]) { rc = fail(c, TSQ_ERR_INVALID, "alignment row %u is null", r); break; }
+      memcpy(h.p + (size_t)r * ncols, rows[r], ncols);
+    }
+  }
+  if (e == cudaSuccess && rc == TSQ_OK) {
+    cudaStream_t s = c->stream;
+    e = cudaMemcpyAsync(d_aln.p, h.p, cells, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tab.p, kBlosum62, 23 * 23, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tab.p + 23 * 23, kProteinIndex, 26, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess)
+      e = tsq::consensus_launch(d_aln.p, nrows, ncols, plurality, reinterpret_cast<const int8_t*>(d_tab.p), d_tab.p + 23 * 23,
+                                d_out.p, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h.p + cells, d_out.p, ncols, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) memcpy(out, h.p + cells, ncols);
+  }
+  h.release(); d_aln.release(); d_out.release(); d_tab.release();
+  if (rc != TSQ_OK) return rc;
+  if (e != cudaSuccess) return fail(c, e == cudaErrorMemoryAllocation ? TSQ_ERR_NOMEM : TSQ_ERR_CUDA, "tsq_consensus: %s", cudaGetErrorString(e));
+  return TSQ_OK;
+}
+
 int tsq_plan_partition(const tsq_params* params, const uint32_t* lengths, uint32_t n, int32_t world,
                        uint64_t* begins, uint64_t* ends) {
   if (world < 1 || (n > 0 && !lengths) || !begins || !ends) return TSQ_ERR_INVALID;

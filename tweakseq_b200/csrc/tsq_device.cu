@@ -211,6 +211,75 @@ cudaError_t subject_db_launch(const uint8_t* lin, const uint32_t* loff, const ui
   return cudaGetLastError();
 }
 
+// ---- consensus annotation (Consensus.cpp:80-161) ---------------------------------------
+// One CTA per tile of 32 columns.  Pass 1: the 8 warps stream the rows (a warp reads 32 adjacent
+// columns of one row: coalesced) into per-column class histograms and first-occurrence rows in shared
+// memory.  Pass 2: one thread per column scores every class present against the histogram.
+// All weights are 1.0 in the reference, so its double-precision sums are exact integers and integer
+// arithmetic here reproduces them bit for bit; ties go to the smallest row, as its strict '>' does.
+constexpr int CONS_CLASSES = 24;   // 0..22 = BLOSUM62 rows, 23 = "not a residue" (99 in the reference)
+
+__global__ void __launch_bounds__(256) consensus_kernel(const uint8_t* __restrict__ aln, uint32_t nrows, uint32_t ncols,
+                                                        double plurality, const int8_t* __restrict__ blosum,
+                                                        const uint8_t* __restrict__ letter_map, uint8_t* __restrict__ out) {
+  __shared__ uint32_t hist[32][CONS_CLASSES + 1];
+  __shared__ uint32_t first[32][CONS_CLASSES + 1];
+  __shared__ int8_t sB[23 * 23];
+  __shared__ uint8_t smap[26];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t i = threadIdx.x; i < 23 * 23; i += blockDim.x) sB[i] = blosum[i];
+  if (threadIdx.x < 26) smap[threadIdx.x] = letter_map[threadIdx.x];
+  for (uint32_t i = threadIdx.x; i < 32 * (CONS_CLASSES + 1); i += blockDim.x) {
+    (&hist[0][0])[i] = 0;
+    (&first[0][0])[i] = 0xffffffffu;
+  }
+  __syncthreads();
+  const uint32_t col = blockIdx.x * 32 + lane;
+  if (col < ncols) {
+    for (uint32_t r = warp; r < nrows; r += blockDim.x >> 5) {
+      const int idx = (int)aln[(size_t)r * ncols + col] - 65;           // Consensus.cpp:99-105
+      const uint32_t cls = (idx < 0 || idx > 25) ? 23u : (uint32_t)smap[idx];
+      atomicAdd(&hist[lane][cls], 1u);
+      atomicMin(&first[lane][cls], r);
+    }
+  }
+  __syncthreads();
+  if (warp == 0 && col < ncols) {
+    long long best = 0, best_matches = 0;
+    uint32_t best_row = 0xffffffffu;
+    for (int a = 0; a < CONS_CLASSES; a++) {
+      if (hist[lane][a] == 0) continue;
+      long long score = 0, matches = 0;
+      for (int b = 0; b < CONS_CLASSES; b++) {
+        const long long cnt = (long long)hist[lane][b] - (a == b ? 1 : 0);   // every other row
+        if (cnt <= 0) continue;
+        if (a == 23 && b == 23) { score += cnt; matches += cnt; }             // :118-122
+        else if (a == 23 || b == 23) score += -4 * cnt;                       // :123-124
+        else {
+          const int t = sB[a * 23 + b];                                       // :125-130
+          score += t * cnt;
+          if (t > 0) matches += cnt;
+        }
+      }
+      const uint32_t fr = first[lane][a];
+      // first row wins ties (strict '>' at :138), and row 0 seeds the maximum (:133-137)
+      if (best_row == 0xffffffffu || score > best || (score == best && fr < best_row)) {
+        best = score; best_matches = matches; best_row = fr;
+      }
+    }
+    uint8_t ch = '?';
+    if (best_row != 0xffffffffu && (double)best_matches >= plurality) ch = aln[(size_t)best_row * ncols + col];
+    out[col] = ch;
+  }
+}
+
+cudaError_t consensus_launch(const uint8_t* aln, uint32_t nrows, uint32_t ncols, double plurality, const int8_t* blosum,
+                             const uint8_t* letter_map, uint8_t* out, cudaStream_t stream) {
+  if (ncols == 0) return cudaSuccess;
+  consensus_kernel<<<(ncols + 31) / 32, 256, 0, stream>>>(aln, nrows, ncols, plurality, blosum, letter_map, out);
+  return cudaGetLastError();
+}
+
 // ---- UPGMA guide tree -----------------------------------------------------------------------------
 cudaError_t upgma_launch(const UpgmaParams& p, cudaStream_t stream) {
   if (p.n < 2) return cudaSuccess;

@@ -55,6 +55,11 @@ cudaError_t upgma_launch(const UpgmaParams& p, cudaStream_t stream);
 cudaError_t subject_db_launch(const uint8_t* lin, const uint32_t* loff, const uint32_t* lens, const uint32_t* goff,
                               uint32_t* dbw, uint32_t n, uint32_t lo, uint32_t hi, uint32_t scale, cudaStream_t stream);
 
+// Consensus annotation: aln = nrows x ncols characters, row-major; out = ncols chars.
+cudaError_t consensus_launch(const uint8_t* aln, uint32_t nrows, uint32_t ncols, double plurality,
+                             const int8_t* blosum /*23x23*/, const uint8_t* letter_map /*26*/, uint8_t* out,
+                             cudaStream_t stream);
+
 struct FinalizeParams {
   const int32_t* sorted;      // packed triangle, sorted order
   const uint32_t* lens;       // sorted lengths
