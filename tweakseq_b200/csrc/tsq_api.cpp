@@ -634,6 +634,7 @@ int enqueue_gotoh16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
       g.nsym = (uint32_t)c->nsym;
       g.go = c->go_k;
       g.ge = c->ge_k;
+      g.one = 1;
       TSQ_CUDA(c, tsq::g32_launch(c->K, grid, g, s));
       launches++;
       return TSQ_OK;
