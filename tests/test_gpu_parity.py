@@ -489,3 +489,20 @@ def test_randomised_gap_models_all_three_kernels_agree():
         for flags in (0, t.FLAG_FORCE_S32, t.FLAG_FORCE_S32 | t.FLAG_NO_WAVE16):
             s, _, _, _ = gpu_run(seqs, alphabet=alphabet, gap_open=go, gap_extend=ge, flags=flags | t.FLAG_NO_DISTANCES)
             assert (s == rs).all(), (trial, alphabet, go, ge, flags, np.nonzero(s != rs)[0][:5])
+
+
+@pytest.mark.parametrize("flags,alphabet", [(8, 0), (1, 1), (8 | 1, 0), (4, 1)])
+def test_host_planner_matches_the_context_in_every_mode(flags, alphabet):
+    """tsq_plan_partition (host only) and tsq_upload must cut the rows identically whatever kernels the
+    flags select (identity keys, forced wavefront, no packed wavefront)."""
+    rng = np.random.default_rng(flags * 10 + alphabet)
+    letters = "ACGT" if alphabet else AA[:20]
+    seqs = ragged(rng, 90, 0, 300, letters) + ragged(rng, 3, 7400 if alphabet else 4600, 7600 if alphabet else 4700, letters)
+    planned = capi.plan_partition([len(s) for s in seqs], 3, alphabet=alphabet, flags=flags)
+    got = []
+    for r in range(3):
+        with t.Context(alphabet=alphabet, part_rank=r, part_world=3, flags=flags | t.FLAG_NO_DISTANCES) as ctx:
+            ctx.set_sequences(seqs)
+            ctx.upload()
+            got.append(ctx.partition())
+    assert got == planned

@@ -266,6 +266,18 @@ bool wave16_ok(const tsq_ctx* c, int nsym, uint32_t flags) {
   return tsq::w16_window((uint32_t)nsym, lip) <= 30000;
 }
 
+// Which inter-task kernel takes the short sequences, and up to which length: the packed 16-bit one
+// when the score range admits it; the 32-bit one (gotoh32.cuh) in identity mode (keys are wide) or when
+// the gap/score parameters leave the packed kernel no usable range.  Longer sequences: wavefront.
+constexpr uint32_t kMaxLen32 = 8192;
+uint32_t inter_task_limit(uint32_t max_len16, uint32_t flags, bool* use_g32) {
+  const bool idmode = (flags & TSQ_FLAG_IDENTITY) != 0;
+  const bool force_wave = (flags & TSQ_FLAG_FORCE_S32) != 0;
+  const bool g32 = idmode || (max_len16 < 64 && !force_wave);
+  if (use_g32) *use_g32 = g32;
+  return g32 ? (force_wave ? 0u : kMaxLen32) : max_len16;
+}
+
 // Largest sequence length the packed kernel can take (binary search on the range bound).
 uint32_t max_len16_of(const tsq_ctx* c) {
   uint32_t a = 0, b = 60000;
@@ -345,13 +357,8 @@ int host_sort_and_pack(tsq_ctx* c) {
   // ---- regimes --------------------------------------------------------------------------
   uint32_t lo = 0;
   while (lo < n && c->lens[lo] == 0) lo++;
-  // Which inter-task kernel takes the short sequences [lo, hi): the packed 16-bit one when the
-  // score range admits it; the 32-bit one (gotoh32.cuh) in identity mode (keys are wide) or when the
-  // gap/score parameters leave the packed kernel no usable range.  Longer sequences: wavefront.
   const bool idmode = (c->prm.flags & TSQ_FLAG_IDENTITY) != 0;
-  const uint32_t kMaxLen32 = 8192;
-  c->use_g32 = idmode || (c->max_len16 < 64 && !(c->prm.flags & TSQ_FLAG_FORCE_S32));
-  const uint32_t inter_max = c->use_g32 ? ((c->prm.flags & TSQ_FLAG_FORCE_S32) ? 0u : kMaxLen32) : c->max_len16;
+  const uint32_t inter_max = inter_task_limit(c->max_len16, c->prm.flags, &c->use_g32);
   c->inter_max = inter_max;
   uint32_t hi = lo;
   while (hi < n && c->lens[hi] <= inter_max) hi++;
@@ -1311,9 +1318,11 @@ int tsq_plan_partition(const tsq_params* params, const uint32_t* lengths, uint32
   uint32_t lo = 0;
   while (lo < n && lens[lo] == 0) lo++;
   uint32_t hi = lo;
-  while (hi < n && lens[hi] <= max16) hi++;
+  const uint32_t inter_max = inter_task_limit(max16, p.flags, nullptr);
+  while (hi < n && lens[hi] <= inter_max) hi++;
   std::vector<uint32_t> first_row;
-  plan_rows(lens, lo, hi, world, first_row, wave16_ok(&tmp, nsym, p.flags) ? 1.5 : 2.4);
+  const bool w16 = wave16_ok(&tmp, nsym, p.flags) && !(p.flags & TSQ_FLAG_IDENTITY);
+  plan_rows(lens, lo, hi, world, first_row, w16 ? 1.5 : 2.4);
   const uint64_t npairs = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
   auto start_of = [&](uint32_t row) -> uint64_t { return (n >= 2 && row + 1 < n) ? tri(row, row + 1, n) : npairs; };
   for (int r = 0; r < world; r++) {
