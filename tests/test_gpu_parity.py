@@ -506,3 +506,19 @@ def test_host_planner_matches_the_context_in_every_mode(flags, alphabet):
             ctx.upload()
             got.append(ctx.partition())
     assert got == planned
+
+
+def test_backend_object_identity_tree_and_consensus(tmp_path):
+    tool = t.B200Gotoh()
+    _, seqs = synth.config(1, 0.25)
+    tool.identity = True
+    s, d = tool.distance_matrix(seqs)
+    enc = [o.encode(x) for x in seqs]
+    rs, rk, rd = o.all_pairs_id(enc, o.matrix(0), 11, 1)
+    assert (s == rs).all() and d.tobytes() == rd.tobytes()
+    l, r, h = tool.guide_tree(seqs, labels=[f"s{k}" for k in range(len(seqs))], newick_path=str(tmp_path / "g.dnd"))
+    ol, orr, oh = o.upgma(rd, len(seqs))
+    assert (l == ol).all() and (r == orr).all() and h.tobytes() == oh.tobytes()
+    assert open(tmp_path / "g.dnd").read().strip().endswith(";")
+    rows = [x[:200].ljust(200, "-") for x in seqs]
+    assert tool.consensus(rows) == o.consensus(rows)

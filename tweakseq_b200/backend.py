@@ -63,6 +63,7 @@ class B200Gotoh(AlignmentTool):
         self.gap_open = -1
         self.gap_extend = -1
         self.device = 0
+        self.identity = False      # ClustalW-style identity distance instead of the score distance
         self.last_stats: dict = {}
 
     def inProcess(self): return True
@@ -113,12 +114,15 @@ class B200Gotoh(AlignmentTool):
         Returns the exit status startAlignment()/alignmentFinished() would see (0 = success:
         SeqEditMainWin.cpp:836-861)."""
         return capi.run_fasta(fin, fout, log=log, cancel=cancel, alphabet=self.alphabet,
-                              gap_open=self.gap_open, gap_extend=self.gap_extend, device=self.device)
+                              gap_open=self.gap_open, gap_extend=self.gap_extend, device=self.device,
+                              flags=capi.FLAG_IDENTITY if self.identity else 0)
 
     def distance_matrix(self, residues, labels=None, progress=None, cancel=None, flags: int = 0):
         """Scores and distances for in-memory residues (what Sequence::filter(true) returns).
 
         Returns (scores int32 packed, distances float64 packed)."""
+        if self.identity:
+            flags |= capi.FLAG_IDENTITY
         with capi.Context(alphabet=self.alphabet, gap_open=self.gap_open, gap_extend=self.gap_extend,
                           device=self.device, flags=flags) as ctx:
             ctx.set_sequences(residues)
@@ -126,6 +130,24 @@ class B200Gotoh(AlignmentTool):
             self.last_stats = ctx.stats()
             d = None if flags & capi.FLAG_NO_DISTANCES else ctx.distances()
             return ctx.scores(), d
+
+    def guide_tree(self, residues, labels=None, newick_path=None):
+        """Distances + UPGMA guide tree.  Returns (left, right, height) merge arrays and
+        writes Newick to newick_path if given (what clustalo takes as --guidetree-in)."""
+        with capi.Context(alphabet=self.alphabet, gap_open=self.gap_open, gap_extend=self.gap_extend,
+                          device=self.device, flags=capi.FLAG_IDENTITY if self.identity else 0) as ctx:
+            ctx.set_sequences(residues)
+            ctx.run()
+            tree = ctx.guide_tree()
+            if newick_path:
+                ctx.write_newick(newick_path, labels)
+            self.last_stats = ctx.stats()
+            return tree
+
+    def consensus(self, aligned_rows, plurality: float = -1.0) -> str:
+        """Consensus annotation of an alignment: Consensus::calculate (Consensus.cpp:80-161) on the GPU."""
+        with capi.Context(device=self.device) as ctx:
+            return ctx.consensus(aligned_rows, plurality)
 
     def distance_matrix_from_cells(self, cell_rows, applyExclusions=True, **kw):
         """Rows of 16-bit residue cells with tweakseq's flag bits (Sequence.h:36-39)."""
