@@ -125,6 +125,8 @@ __global__ void __launch_bounds__(UPGMA_THREADS, 1) upgma_merge_kernel(const __g
   __shared__ double sv[32];
   __shared__ uint32_t si[32], sj[32];
   __shared__ uint32_t nrescan;
+  __shared__ double pv[32][32];       // re-scan partials: [row in batch][warp]
+  __shared__ uint32_t pj[32][32];
   extern __shared__ double upgma_dyn[];
   double* rowmin = SMEM ? upgma_dyn : p.rowmin;
   uint32_t* rowarg = SMEM ? reinterpret_cast<uint32_t*>(upgma_dyn + n) : p.rowarg;
@@ -201,25 +203,51 @@ __global__ void __launch_bounds__(UPGMA_THREADS, 1) upgma_merge_kernel(const __g
     }
     __syncthreads();
     // ---- 4. re-scan the rows whose cached minimum is stale -----------------------------------------
+    // Batched: every warp reduces its slice of each stale row with shuffles and parks the partial
+    // result in shared memory; after ONE barrier, warp r finishes row r.  (A block-wide reduction per
+    // row cost three barriers each and made the barriers the kernel's top stall.)
     const uint32_t nr = nrescan;
-    for (uint32_t r = 0; r < nr; ++r) {
-      const uint32_t row = rescan[r];
-      const double* Dr = p.D + (size_t)row * n;
-      double bv = INF;
-      uint32_t bi = row, bj = 0xffffffffu;
-      for (uint32_t j = row + 1 + tid; j < n; j += UPGMA_THREADS) {
-        if (is_active(j)) {
-          const double x = Dr[j];
-          if (x < bv || (x == bv && j < bj)) { bv = x; bj = j; }
+    for (uint32_t r0 = 0; r0 < nr; r0 += 32) {
+      const uint32_t nb = nr - r0 < 32u ? nr - r0 : 32u;
+#pragma unroll 4
+      for (uint32_t r = 0; r < nb; ++r) {
+        const uint32_t row = rescan[r0 + r];
+        const double* Dr = p.D + (size_t)row * n;
+        double bv = INF;
+        uint32_t bj = 0xffffffffu;
+        for (uint32_t j = row + 1 + tid; j < n; j += UPGMA_THREADS) {
+          if (is_active(j)) {
+            const double x = Dr[j];
+            if (x < bv || (x == bv && j < bj)) { bv = x; bj = j; }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+          const uint32_t j2 = __shfl_xor_sync(0xffffffffu, bj, o);
+          if (v2 < bv || (v2 == bv && j2 < bj)) { bv = v2; bj = j2; }
+        }
+        if ((tid & 31) == 0) { pv[r][tid >> 5] = bv; pj[r][tid >> 5] = bj; }
+      }
+      __syncthreads();
+      if ((tid >> 5) < nb) {
+        const uint32_t r = tid >> 5;
+        double bv = pv[r][tid & 31];
+        uint32_t bj = pj[r][tid & 31];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+          const uint32_t j2 = __shfl_xor_sync(0xffffffffu, bj, o);
+          if (v2 < bv || (v2 == bv && j2 < bj)) { bv = v2; bj = j2; }
+        }
+        if ((tid & 31) == 0) {
+          const uint32_t row = rescan[r0 + r];
+          rowmin[row] = bv;
+          rowarg[row] = bj;
         }
       }
-      upgma_block_argmin(bv, bi, bj, sv, si, sj);
-      if (tid == 0) {
-        rowmin[row] = bv;
-        rowarg[row] = bj;
-      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
