@@ -59,6 +59,7 @@ static void fill(tsq_params& p, const B200Gotoh& t) {
   p.gap_open = t.gapOpen;
   p.gap_extend = t.gapExtend;
   p.device = t.device;
+  if (t.identityDistance) p.flags |= TSQ_FLAG_IDENTITY;
 }
 
 int B200Gotoh::run(const std::string& fin, const std::string& fout, const LogSink& log, CancelFlag* cancel) {
@@ -101,6 +102,62 @@ int B200Gotoh::distanceMatrix(const std::vector<std::string>& residues, std::vec
   } else if (error) {
     *error = tsq_last_error(c);
   }
+  tsq_destroy(c);
+  return rc;
+}
+
+namespace {
+int load(tsq_ctx* c, const std::vector<std::string>& residues) {
+  std::vector<const char*> ptr(residues.size());
+  std::vector<uint32_t> len(residues.size());
+  for (size_t i = 0; i < residues.size(); i++) {
+    ptr[i] = residues[i].data();
+    len[i] = (uint32_t)residues[i].size();
+  }
+  return tsq_set_sequences(c, ptr.data(), len.data(), (uint32_t)residues.size());
+}
+}  // namespace
+
+int B200Gotoh::guideTree(const std::vector<std::string>& residues, const std::vector<std::string>& labels,
+                         const std::string& newickPath, std::string* error) {
+  tsq_params p;
+  fill(p, *this);
+  tsq_ctx* c = nullptr;
+  int rc = tsq_create(&c, &p);
+  if (rc != TSQ_OK) {
+    if (error) *error = tsq_status_string(rc);
+    return rc;
+  }
+  rc = load(c, residues);
+  if (rc == TSQ_OK) rc = tsq_run(c, nullptr, nullptr, nullptr);
+  if (rc == TSQ_OK) {
+    std::vector<const char*> lab(labels.size());
+    for (size_t i = 0; i < labels.size(); i++) lab[i] = labels[i].c_str();
+    rc = tsq_write_newick(c, labels.size() == residues.size() ? lab.data() : nullptr, newickPath.c_str());
+  }
+  if (rc != TSQ_OK && error) *error = tsq_last_error(c);
+  tsq_destroy(c);
+  return rc;
+}
+
+int B200Gotoh::consensus(const std::vector<std::string>& rows, double plurality, std::string& out, std::string* error) {
+  tsq_params p;
+  fill(p, *this);
+  tsq_ctx* c = nullptr;
+  int rc = tsq_create(&c, &p);
+  if (rc != TSQ_OK) {
+    if (error) *error = tsq_status_string(rc);
+    return rc;
+  }
+  const uint32_t ncols = rows.empty() ? 0u : (uint32_t)rows[0].size();
+  std::vector<const char*> ptr(rows.size());
+  for (size_t i = 0; i < rows.size(); i++) {
+    if (rows[i].size() != ncols) rc = TSQ_ERR_INVALID;
+    ptr[i] = rows[i].data();
+  }
+  out.assign(ncols, '?');
+  if (rc == TSQ_OK) rc = tsq_consensus(c, ptr.data(), (uint32_t)rows.size(), ncols, plurality, ncols ? &out[0] : nullptr);
+  if (rc != TSQ_OK && error) *error = rc == TSQ_ERR_INVALID ? "alignment rows differ in length" : tsq_last_error(c);
   tsq_destroy(c);
   return rc;
 }

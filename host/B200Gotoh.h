@@ -27,8 +27,16 @@ class B200Gotoh : public AlignmentTool {
   int distanceMatrix(const std::vector<std::string>& residues, std::vector<int>& scores,
                      std::vector<double>& distances, std::string* error = nullptr);
 
+  // Guide tree of the same job: Newick text for clustalo --guidetree-in.
+  int guideTree(const std::vector<std::string>& residues, const std::vector<std::string>& labels,
+                const std::string& newickPath, std::string* error = nullptr);
+  // Consensus annotation of an alignment: Consensus::calculate (Consensus.cpp:80-161) on the GPU.
+  int consensus(const std::vector<std::string>& alignedRows, double plurality, std::string& out,
+                std::string* error = nullptr);
+
   int gapOpen = -1, gapExtend = -1, device = 0;  // <0: library defaults (11/1 protein)
   bool nucleotide = false;
+  bool identityDistance = false;                 // ClustalW-style 1 - identities/min(len)
 
  private:
   void init();

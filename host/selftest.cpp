@@ -48,6 +48,15 @@ int main(int argc, char** argv) {
   std::string err;
   CHECK(g.distanceMatrix({"WWWW", "WWWW", "ACDEFG"}, s, d, &err) == TSQ_OK);
   CHECK(s.size() == 3 && s[0] == 44 && d[0] == 0.0);
+  {
+    std::string cons;
+    CHECK(g.consensus({"AWC-a", "AWC-A", "AYD-A", "RWC-x"}, -1.0, cons, &err) == TSQ_OK);
+    CHECK(cons == "AWC-?");
+    g.identityDistance = true;
+    CHECK(g.distanceMatrix({"WWWW", "WWCWW", "ACDEFG"}, s, d, &err) == TSQ_OK);
+    CHECK(d[0] == 0.0);   // 4 identities over the shorter length 4
+    g.identityDistance = false;
+  }
   if (argc >= 3) {
     int rc = g.run(argv[1], argv[2], [](const std::string& l) { printf("[log] %s\n", l.c_str()); }, nullptr);
     CHECK(rc == 0);
