@@ -5,9 +5,10 @@
 // DPX instruction (VIMNMX3.U16x2 / VIADDMNMX.U16x2) advances two alignments.
 //
 // The DP is strip-mined: a lane keeps K columns of H and F in registers and walks down all
-// rows of its subject; the right-hand boundary column (H, E) of the strip goes to a per-lane
-// L2-resident scratch column and is read back, one row ahead, by the next strip.  Lanes never
-// exchange data, so the row loop has no barrier and no shuffle.
+// rows of its subject, two rows at a time (row i+1 one column behind row i: two independent
+// dependency chains per lane); the right-hand boundary column (H, E) of the strip goes to a
+// per-lane scratch column in global memory and is read back, two rows ahead of use, by the next
+// strip.  Lanes never exchange data, so the row loop has no barrier and no shuffle.
 //
 // Scores come from a per-warp, per-strip "query-pair profile" in shared memory:
 //   prof[b][c] = S'(A1[j0+c], b) | S'(A2[j0+c], b) << 16          (b = subject letter)
