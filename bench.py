@@ -325,6 +325,13 @@ def main():
                          "algorithmic_bytes": lens_bytes + 4 * st["n_pairs"],
                          "peak_how": f"{sms} SMs x {dpx_ops:.1f} DPX lane-results/clk/SM (measured live) x {sm_mhz} MHz "
                                      "(median under load) / 2.5 instr per cell (5 integer lane-ops, 16x2 packing: SURVEY 8d)",
+                         "frac_note": "the SURVEY 8d denominator puts all 5 lane-ops per cell on the DPX (ALU-pipe) rate; ptxas places "
+                                      "the two adds on the FMA pipe (IMAD.IADD / VIADD), so frac can pass 1; frac_mix is against the "
+                                      "measured issue ceiling of the kernel's own instruction mix (3 DPX + 2 adds + 1 LDS)",
+                         "peak_mix": sms * 16.6 * 2 * sm_mhz * 1e6 / 1e9,
+                         "frac_mix": achieved / (sms * 16.6 * 2 * sm_mhz * 1e6 / 1e9) if sm_mhz else None,
+                         "peak_mix_how": "16.4-16.8 packed cells/clk/SM issued by the inner loop's instruction mix in isolation "
+                                         "(tools/pipe_probe2.cu, profiles/pipe_probe2_r01.jsonl), x2 cells, x SMs x MHz",
                          "kernel_ms": kernel_ms, "kernel_cells": kernel_cells,
                          "hbm_algorithmic_gbs": hbm_alg, "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},
             "wall_s_timed_region": t_wall,
