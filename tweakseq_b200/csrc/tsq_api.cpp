@@ -119,7 +119,8 @@ struct tsq_ctx {
   int sm_count = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;    // around the score kernels of tsq_compute
+  cudaEvent_t tev0 = nullptr, tev1 = nullptr;  // around the guide-tree kernels
   std::string err;
 
   // packed-16 arithmetic constants
@@ -138,7 +139,7 @@ struct tsq_ctx {
   uint32_t db_scale = 0;                  // letter -> profile-row byte offset factor (STRIDE(K) * 4)
   std::vector<uint32_t> goff;             // group offsets
   std::vector<int32_t> self_sorted, self_orig;
-  bool identity = true;
+  bool perm_identity = true;             // the length sort left the submitted order unchanged (and no empties)
   uint32_t lo = 0, hi = 0;  // sorted range eligible for the packed 16-bit kernel
   uint32_t row_a = 0, row_b = 0;  // this partition's sorted rows
   uint64_t part_begin = 0, part_end = 0;
@@ -330,14 +331,14 @@ int host_sort_and_pack(tsq_ctx* c) {
   c->lens.resize(n);
   c->loff.resize(n + 1);
   uint64_t total = 0;
-  c->identity = true;
+  c->perm_identity = true;
   for (uint32_t i = 0; i < n; i++) {
     const size_t l = c->enc[c->perm[i]].size();
     if (l > 0x7fffffffu) return fail(c, TSQ_ERR_RANGE, "sequence too long");
     c->lens[i] = (uint32_t)l;
     c->loff[i] = (uint32_t)total;
     total += (l + 15) & ~(size_t)15;   // 16-byte aligned starts: TMA bulk copies read tiles from here
-    if (c->perm[i] != i) c->identity = false;
+    if (c->perm[i] != i) c->perm_identity = false;
   }
   if (total > 0xfffffff0ull) return fail(c, TSQ_ERR_RANGE, "more than 4 Gi residues");
   c->loff[n] = (uint32_t)total;
@@ -389,7 +390,7 @@ int host_sort_and_pack(tsq_ctx* c) {
                     idmode ? "identity-aware keys" : "scores");
     }
   }
-  if (c->identity && lo > 0) c->identity = false;  // empties are filled in by finalize
+  if (c->perm_identity && lo > 0) c->perm_identity = false;  // empties are filled in by finalize
   c->lo = lo;
   c->hi = hi;
   return TSQ_OK;
@@ -855,9 +856,10 @@ int tsq_create(tsq_ctx** out, const tsq_params* params) {
   c->delta = c->smin < 0 ? (-c->smin + 1) / 2 : 0;
   c->max_len16 = (p.flags & TSQ_FLAG_FORCE_S32) ? 0 : max_len16_of(c);
   if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+      cudaEventCreate(&c->tev0) != cudaSuccess || cudaEventCreate(&c->tev1) != cudaSuccess) {
     cudaGetLastError();
-    delete c;
+    tsq_destroy(c);
     return TSQ_ERR_CUDA;
   }
   if (cudaMalloc((void**)&c->d_cancel, sizeof(int)) != cudaSuccess || cudaMemset(c->d_cancel, 0, sizeof(int)) != cudaSuccess ||
@@ -888,6 +890,8 @@ int tsq_destroy(tsq_ctx* c) {
   if (c->cancel_stream) cudaStreamDestroy(c->cancel_stream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->tev0) cudaEventDestroy(c->tev0);
+  if (c->tev1) cudaEventDestroy(c->tev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return TSQ_OK;
@@ -904,6 +908,9 @@ int tsq_set_stream(tsq_ctx* c, void* s) {
 int tsq_set_sequences(tsq_ctx* c, const char* const* residues, const uint32_t* lengths, uint32_t n) {
   if (!c) return TSQ_ERR_INVALID;
   if (n > 0 && (!residues || !lengths)) return fail(c, TSQ_ERR_INVALID, "null sequence arrays");
+  // a failed call leaves the context without sequences rather than with half of the new set
+  c->have_seqs = c->uploaded = c->computed = c->finalized = c->downloaded = false;
+  c->n = 0;
   c->enc.resize(n);
   for (uint32_t i = 0; i < n; i++) {
     if (lengths[i] > 0 && !residues[i]) return fail(c, TSQ_ERR_INVALID, "sequence %u is null", i);
@@ -919,6 +926,8 @@ int tsq_set_sequences(tsq_ctx* c, const char* const* residues, const uint32_t* l
 int tsq_set_sequences_flat(tsq_ctx* c, const char* residues, const uint64_t* offsets, uint32_t n) {
   if (!c) return TSQ_ERR_INVALID;
   if (n > 0 && (!residues || !offsets)) return fail(c, TSQ_ERR_INVALID, "null sequence buffer");
+  c->have_seqs = c->uploaded = c->computed = c->finalized = c->downloaded = false;
+  c->n = 0;
   c->enc.resize(n);
   for (uint32_t i = 0; i < n; i++) {
     if (offsets[i + 1] < offsets[i]) return fail(c, TSQ_ERR_INVALID, "offsets not ascending at %u", i);
@@ -973,13 +982,13 @@ int tsq_finalize(tsq_ctx* c) {
   const uint32_t n = c->n;
   const uint64_t npairs = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
   const bool want_dist = !(c->prm.flags & TSQ_FLAG_NO_DISTANCES);
-  if (npairs > 0 && (want_dist || !c->identity || c->idshift)) {
+  if (npairs > 0 && (want_dist || !c->perm_identity || c->idshift)) {
     tsq::FinalizeParams f{};
     f.sorted = c->d_sorted.p;
     f.lens = c->d_lens.p;
     f.perm = c->d_perm.p;
     f.self = c->d_self.p;
-    const bool inplace = c->identity && c->idshift == 0;   // identity keys are decoded into a separate buffer
+    const bool inplace = c->perm_identity && c->idshift == 0;   // identity keys are decoded into a separate buffer
     if (inplace) {
       f.out_scores = c->d_sorted.p;
     } else {
@@ -1000,7 +1009,7 @@ int tsq_finalize(tsq_ctx* c) {
     f.n = n;
     f.go = c->go;
     f.ge = c->ge;
-    f.identity = c->identity ? 1u : 0u;
+    f.perm_identity = c->perm_identity ? 1u : 0u;
     TSQ_CUDA(c, tsq::finalize_launch(f, c->stream));
     c->st.launches++;
   }
@@ -1039,7 +1048,7 @@ int tsq_download(tsq_ctx* c) {
   cudaStream_t s = c->stream;
   if (npairs > 0 && c->finalized) {
     TSQ_CUDA(c, c->h_scores.reserve(npairs));
-    const int32_t* src = (c->identity && c->idshift == 0) ? c->d_sorted.p : c->d_scores.p;
+    const int32_t* src = (c->perm_identity && c->idshift == 0) ? c->d_sorted.p : c->d_scores.p;
     TSQ_CUDA(c, cudaMemcpyAsync(c->h_scores.p, src, npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     if (c->idshift) {
       TSQ_CUDA(c, c->h_nid.reserve(npairs));
@@ -1145,7 +1154,7 @@ int tsq_partition(tsq_ctx* c, uint64_t* b, uint64_t* e) {
 int tsq_device_results(tsq_ctx* c, void** d_scores, void** d_dist, uint64_t* count) {
   if (!c) return TSQ_ERR_INVALID;
   if (!c->finalized) return fail(c, TSQ_ERR_STATE, "tsq_device_results before tsq_finalize");
-  if (d_scores) *d_scores = (c->identity && c->idshift == 0) ? (void*)c->d_sorted.p : (void*)c->d_scores.p;
+  if (d_scores) *d_scores = (c->perm_identity && c->idshift == 0) ? (void*)c->d_sorted.p : (void*)c->d_scores.p;
   if (d_dist) *d_dist = (c->prm.flags & TSQ_FLAG_NO_DISTANCES) ? nullptr : (void*)c->d_dist.p;
   if (count) *count = c->n < 2 ? 0 : (uint64_t)c->n * (c->n - 1) / 2;
   return TSQ_OK;
@@ -1177,19 +1186,14 @@ int tsq_guide_tree(tsq_ctx* c, const tsq_merge** merges, uint32_t* count) {
       u.rescan = c->d_treeu.p + 4 * (size_t)n;
       u.merges = c->d_merges.p;
       u.n = n;
-      cudaEvent_t t0, t1;
-      TSQ_CUDA(c, cudaEventCreate(&t0));
-      TSQ_CUDA(c, cudaEventCreate(&t1));
-      TSQ_CUDA(c, cudaEventRecord(t0, c->stream));
+      TSQ_CUDA(c, cudaEventRecord(c->tev0, c->stream));
       TSQ_CUDA(c, tsq::upgma_launch(u, c->stream));
-      TSQ_CUDA(c, cudaEventRecord(t1, c->stream));
+      TSQ_CUDA(c, cudaEventRecord(c->tev1, c->stream));
       TSQ_CUDA(c, cudaMemcpyAsync(c->merges.data(), c->d_merges.p, (size_t)(n - 1) * sizeof(tsq_merge), cudaMemcpyDeviceToHost, c->stream));
       TSQ_CUDA(c, cudaStreamSynchronize(c->stream));
       float ms = 0;
-      cudaEventElapsedTime(&ms, t0, t1);
+      if (cudaEventElapsedTime(&ms, c->tev0, c->tev1) != cudaSuccess) cudaGetLastError();
       c->tree_ms = ms;
-      cudaEventDestroy(t0);
-      cudaEventDestroy(t1);
       c->st.launches += 2;
     }
     c->have_tree = true;
@@ -1228,7 +1232,7 @@ int tsq_write_newick(tsq_ctx* c, const char* const* labels, const char* path) {
     while (!st.empty()) {
       Frame& fr = st.back();
       if (fr.id < n) {
-        fprintf(f, "%s:%.6f", leaf_name(fr.id).c_str(), fr.parent_h - 0.0);
+        fprintf(f, "%s:%.6f", leaf_name(fr.id).c_str(), fr.parent_h);   // leaves sit at height 0
         st.pop_back();
         continue;
       }

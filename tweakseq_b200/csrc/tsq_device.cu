@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   const unsigned long long n = p.n;
   for (unsigned long long i = blockIdx.x; i + 1 < n; i += gridDim.x) {
     const uint32_t li = p.lens[i];
-    const uint32_t oi = p.identity ? (uint32_t)i : p.perm[i];
+    const uint32_t oi = p.perm_identity ? (uint32_t)i : p.perm[i];
     const int32_t si = p.self[i];
     const unsigned long long rowbase = tri_index(i, i + 1, n);
     for (unsigned long long j = i + 1 + threadIdx.x; j < n; j += blockDim.x) {
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
         s >>= p.idshift;            // arithmetic shift = floor division: exact for negative scores
       }
       unsigned long long oidx = sidx;
-      if (!p.identity) {
+      if (!p.perm_identity) {
         const uint32_t oj = p.perm[j];
         const unsigned long long a = oi < oj ? oi : oj, b = oi < oj ? oj : oi;
         oidx = tri_index(a, b, n);

@@ -65,11 +65,11 @@ struct FinalizeParams {
   const uint32_t* lens;       // sorted lengths
   const uint32_t* perm;       // sorted index -> original index
   const int32_t* self;        // self scores, sorted order
-  int32_t* out_scores;        // packed triangle, original order (may alias sorted if identity)
+  int32_t* out_scores;        // packed triangle, original order (may alias sorted if perm_identity)
   double* out_dist;           // packed triangle, original order, or nullptr
   uint32_t n;
   int32_t go, ge;
-  uint32_t identity;          // perm is the identity and there are no empty sequences
+  uint32_t perm_identity;        // perm is the identity and there are no empty sequences
   uint32_t idshift;           // identity mode: sorted[] holds score * 2^idshift + identities; 0 = off
   int32_t* out_nid;           // identity mode: identities, packed triangle, original order
 };
