@@ -108,6 +108,12 @@ struct PinnedBuf {
   }
 };
 
+// A typed pointer into tsq_ctx::d_blob (one allocation, one host -> device copy per upload).
+template <typename T>
+struct DevView {
+  T* p = nullptr;
+};
+
 }  // namespace
 
 struct tsq_ctx {
@@ -133,12 +139,17 @@ struct tsq_ctx {
   std::vector<uint32_t> perm;             // sorted -> submitted
   std::vector<uint32_t> lens;             // sorted
   std::vector<uint32_t> loff;             // sorted
-  PinnedBuf<uint8_t> lin;                 // sorted, concatenated (pinned staging)
-  size_t lin_size = 0;
+  // Pinned staging blob, copied to d_blob by ONE cudaMemcpyAsync: the sorted, concatenated residues
+  // (16-byte aligned starts) first, then the small tables (group/sequence offsets, lengths,
+  // permutation, self scores, biased score table, task prefix), each 16-byte aligned.
+  PinnedBuf<uint8_t> h_blob;
+  size_t lin_size = 0;                    // residue part of the blob
+  size_t blob_size = 0;                   // bytes in use
+  std::vector<int32_t> self_input;        // self scores, submitted order (computed while encoding)
+  int32_t diag_by_byte[256] = {};         // input byte -> S(x, x) of its symbol (0 for dropped bytes)
   size_t dbw_size = 0;                    // interleaved subject database: words (built on the device)
   uint32_t db_scale = 0;                  // letter -> profile-row byte offset factor (STRIDE(K) * 4)
   std::vector<uint32_t> goff;             // group offsets
-  std::vector<int32_t> self_sorted, self_orig;
   bool perm_identity = true;             // the length sort left the submitted order unchanged (and no empties)
   uint32_t lo = 0, hi = 0;  // sorted range eligible for the packed 16-bit kernel
   uint32_t row_a = 0, row_b = 0;  // this partition's sorted rows
@@ -157,11 +168,15 @@ struct tsq_ctx {
   uint64_t cells16 = 0, cells32 = 0, pairs_part = 0;
 
   // device
-  DevBuf<uint32_t> d_dbw, d_goff, d_loff, d_lens, d_perm, d_sbias;
-  DevBuf<uint8_t> d_lin;
-  DevBuf<int32_t> d_self, d_sorted, d_scores, d_nid;
+  DevBuf<uint8_t> d_blob;
+  DevView<uint8_t> d_lin;                                   // views into d_blob
+  DevView<uint32_t> d_goff, d_loff, d_lens, d_perm, d_sbias;
+  DevView<int32_t> d_self;
+  DevView<unsigned long long> d_prefix;
+  DevBuf<uint32_t> d_dbw;
+  DevBuf<int32_t> d_sorted, d_scores, d_nid;
   DevBuf<double> d_dist;
-  DevBuf<unsigned long long> d_prefix, d_counter;
+  DevBuf<unsigned long long> d_counter;
   DevBuf<uint2> d_bnd;
   DevBuf<double> d_treeD, d_treemin, d_treeh;
   DevBuf<uint32_t> d_treeu;               // rowarg, active, csize, node, rescan
@@ -233,16 +248,21 @@ struct EncodeLut {
 };
 const EncodeLut kLut;
 
-void encode_into(int alphabet, const char* s, size_t len, std::vector<uint8_t>& out) {
+// Encodes one sequence (dropping gap / whitespace bytes) and returns its self score sum S(x, x).
+int64_t encode_into(int alphabet, const int32_t* diag_by_byte, const char* s, size_t len, std::vector<uint8_t>& out) {
   const uint8_t* lut = alphabet == TSQ_NUCLEOTIDE ? kLut.nuc : kLut.prot;
   out.resize(len);
   size_t k = 0;
+  int64_t self = 0;
   for (size_t i = 0; i < len; i++) {
-    const uint8_t v = lut[(unsigned char)s[i]];
+    const unsigned char ch = (unsigned char)s[i];
+    const uint8_t v = lut[ch];
     out[k] = v;
     k += (v != 0xff);
+    self += diag_by_byte[ch];
   }
   out.resize(k);
+  return self;
 }
 
 // Packed-16 range analysis.  Values live as v + delta*(i+j) + BIAS in
@@ -342,19 +362,22 @@ int host_sort_and_pack(tsq_ctx* c) {
   }
   if (total > 0xfffffff0ull) return fail(c, TSQ_ERR_RANGE, "more than 4 Gi residues");
   c->loff[n] = (uint32_t)total;
-  TSQ_CUDA(c, c->lin.reserve(total + 2048));   // slack: the last TMA tile of a subject may run past its end
-  c->lin_size = total + 2048;
-  memset(c->lin.p, 0, c->lin_size);
-  c->self_sorted.resize(n);
-  c->self_orig.resize(n);
+  c->lin_size = total + 2048;   // slack: the last TMA tile of a subject may run past its end
+  {
+    // upper bound of the whole staging blob (tables are laid out in device_upload)
+    const size_t ngroups = ((size_t)n + 31) / 32;
+    const size_t tables = (ngroups + 1) * 4 + ((size_t)n + 1) * 4 * 4 + (size_t)(c->nsym + 1) * c->nsym * 4 +
+                          ((size_t)n + 2) * 8 + 8 * 16;
+    TSQ_CUDA(c, c->h_blob.reserve(c->lin_size + tables));
+  }
+  uint8_t* const lin = c->h_blob.p;
   for (uint32_t i = 0; i < n; i++) {
     const std::vector<uint8_t>& e = c->enc[c->perm[i]];
-    if (!e.empty()) memcpy(c->lin.p + c->loff[i], e.data(), e.size());
-    int64_t s = 0;
-    for (uint8_t a : e) s += c->matrix[a * c->nsym + a];
-    c->self_sorted[i] = (int32_t)s;
-    c->self_orig[c->perm[i]] = (int32_t)s;
+    if (!e.empty()) memcpy(lin + c->loff[i], e.data(), e.size());
+    const size_t end = (size_t)c->loff[i] + e.size();
+    memset(lin + end, 0, (size_t)c->loff[i + 1] - end);   // the pad up to the next 16-byte aligned start
   }
+  memset(lin + total, 0, 2048);
   // ---- regimes --------------------------------------------------------------------------
   uint32_t lo = 0;
   while (lo < n && c->lens[lo] == 0) lo++;
@@ -545,35 +568,53 @@ int host_build_subject_db(tsq_ctx* c) {
 int device_upload(tsq_ctx* c) {
   const uint32_t n = c->n;
   const uint64_t npairs = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
-  // ---- biased score table -----------------------------------------------------------------
   const uint32_t nsym = (uint32_t)c->nsym;
-  std::vector<uint32_t> sbias((size_t)(nsym + 1) * nsym, 0);
-  for (uint32_t a = 0; a < nsym; a++)
-    for (uint32_t b = 0; b < nsym; b++) sbias[a * nsym + b] = (uint32_t)(c->matrix[a * nsym + b] + 2 * c->delta);
+  // ---- lay the small tables out behind the residues in the pinned blob -----------------------------
+  size_t off = c->lin_size;
+  auto carve = [&](size_t bytes) -> size_t {
+    off = (off + 15) & ~(size_t)15;
+    const size_t at = off;
+    off += bytes;
+    return at;
+  };
+  const size_t o_goff = carve(c->goff.size() * 4), o_loff = carve(c->loff.size() * 4), o_lens = carve(((size_t)n + 1) * 4),
+               o_perm = carve(((size_t)n + 1) * 4), o_self = carve(((size_t)n + 1) * 4),
+               o_sbias = carve((size_t)(nsym + 1) * nsym * 4), o_prefix = carve(c->task_prefix.size() * 8);
+  c->blob_size = off;
+  if (off > c->h_blob.cap) return fail(c, TSQ_ERR_INVALID, "internal: staging blob bound too small");
+  uint8_t* const hb = c->h_blob.p;
+  memcpy(hb + o_goff, c->goff.data(), c->goff.size() * 4);
+  memcpy(hb + o_loff, c->loff.data(), c->loff.size() * 4);
+  if (n) {
+    memcpy(hb + o_lens, c->lens.data(), (size_t)n * 4);
+    memcpy(hb + o_perm, c->perm.data(), (size_t)n * 4);
+    int32_t* self_sorted = reinterpret_cast<int32_t*>(hb + o_self);
+    for (uint32_t i = 0; i < n; i++) self_sorted[i] = c->self_input[c->perm[i]];
+  }
+  {  // biased score table of the packed kernels: S + 2 delta >= 0, one extra all-zero row
+    uint32_t* sbias = reinterpret_cast<uint32_t*>(hb + o_sbias);
+    memset(sbias, 0, (size_t)(nsym + 1) * nsym * 4);
+    for (uint32_t a = 0; a < nsym; a++)
+      for (uint32_t b = 0; b < nsym; b++) sbias[a * nsym + b] = (uint32_t)(c->matrix[a * nsym + b] + 2 * c->delta);
+  }
+  memcpy(hb + o_prefix, c->task_prefix.data(), c->task_prefix.size() * 8);
 
-  // ---- H2D ----------------------------------------------------------------------------------
+  // ---- H2D: one copy ------------------------------------------------------------------------------
   cudaStream_t s = c->stream;
+  TSQ_CUDA(c, c->d_blob.reserve(c->h_blob.cap));
+  uint8_t* const db = c->d_blob.p;
+  c->d_lin.p = db;
+  c->d_goff.p = reinterpret_cast<uint32_t*>(db + o_goff);
+  c->d_loff.p = reinterpret_cast<uint32_t*>(db + o_loff);
+  c->d_lens.p = reinterpret_cast<uint32_t*>(db + o_lens);
+  c->d_perm.p = reinterpret_cast<uint32_t*>(db + o_perm);
+  c->d_self.p = reinterpret_cast<int32_t*>(db + o_self);
+  c->d_sbias.p = reinterpret_cast<uint32_t*>(db + o_sbias);
+  c->d_prefix.p = reinterpret_cast<unsigned long long*>(db + o_prefix);
   TSQ_CUDA(c, c->d_dbw.reserve(c->dbw_size));
-  TSQ_CUDA(c, c->d_goff.reserve(c->goff.size()));
-  TSQ_CUDA(c, c->d_lin.reserve(c->lin_size));
-  TSQ_CUDA(c, c->d_loff.reserve(c->loff.size()));
-  TSQ_CUDA(c, c->d_lens.reserve(n + 1));
-  TSQ_CUDA(c, c->d_perm.reserve(n + 1));
-  TSQ_CUDA(c, c->d_self.reserve(n + 1));
-  TSQ_CUDA(c, c->d_sbias.reserve(sbias.size()));
-  TSQ_CUDA(c, c->d_prefix.reserve(c->task_prefix.size()));
   TSQ_CUDA(c, c->d_counter.reserve(16));
   TSQ_CUDA(c, c->d_sorted.reserve(npairs));
-  TSQ_CUDA(c, cudaMemcpyAsync(c->d_goff.p, c->goff.data(), c->goff.size() * 4, cudaMemcpyHostToDevice, s));
-  TSQ_CUDA(c, cudaMemcpyAsync(c->d_lin.p, c->lin.p, c->lin_size, cudaMemcpyHostToDevice, s));
-  TSQ_CUDA(c, cudaMemcpyAsync(c->d_loff.p, c->loff.data(), c->loff.size() * 4, cudaMemcpyHostToDevice, s));
-  if (n) {
-    TSQ_CUDA(c, cudaMemcpyAsync(c->d_lens.p, c->lens.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    TSQ_CUDA(c, cudaMemcpyAsync(c->d_perm.p, c->perm.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    TSQ_CUDA(c, cudaMemcpyAsync(c->d_self.p, c->self_sorted.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
-  }
-  TSQ_CUDA(c, cudaMemcpyAsync(c->d_sbias.p, sbias.data(), sbias.size() * 4, cudaMemcpyHostToDevice, s));
-  TSQ_CUDA(c, cudaMemcpyAsync(c->d_prefix.p, c->task_prefix.data(), c->task_prefix.size() * 8, cudaMemcpyHostToDevice, s));
+  TSQ_CUDA(c, cudaMemcpyAsync(db, hb, c->blob_size, cudaMemcpyHostToDevice, s));
   c->st.upload_launches = 0;
   if (c->dbw_size && c->hi > c->lo) c->st.upload_launches = 1;
   if (c->dbw_size && c->hi > c->lo)
@@ -592,8 +633,8 @@ int device_upload(tsq_ctx* c) {
       TSQ_CUDA(c, cudaMemcpyAsync(c->d_pairs32.p, c->pairs32.data(), c->pairs32.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
   }
   TSQ_CUDA(c, cudaStreamSynchronize(s));
-  c->st.h2d_bytes = c->lin_size + c->goff.size() * 4 + c->loff.size() * 4 + (uint64_t)n * 12 +
-                    sbias.size() * 4 + c->task_prefix.size() * 8;
+  c->st.h2d_bytes = c->blob_size + c->tasks16w.size() * sizeof(uint4) + c->pairs32.size() * sizeof(uint2) +
+                    ((!c->pairs32.empty() || c->use_g32) ? c->smat_k.size() * 4 : 0);
   return TSQ_OK;
 }
 
@@ -854,6 +895,10 @@ int tsq_create(tsq_ctx** out, const tsq_params* params) {
   c->smin = *std::min_element(c->matrix.begin(), c->matrix.end());
   c->smax = *std::max_element(c->matrix.begin(), c->matrix.end());
   c->delta = c->smin < 0 ? (-c->smin + 1) / 2 : 0;
+  {
+    const uint8_t* lut = p.alphabet == TSQ_NUCLEOTIDE ? kLut.nuc : kLut.prot;
+    for (int b = 0; b < 256; b++) c->diag_by_byte[b] = lut[b] == 0xff ? 0 : c->matrix[lut[b] * (nsym + 1)];
+  }
   c->max_len16 = (p.flags & TSQ_FLAG_FORCE_S32) ? 0 : max_len16_of(c);
   if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
@@ -879,11 +924,10 @@ int tsq_destroy(tsq_ctx* c) {
   if (!c) return TSQ_OK;
   cudaSetDevice(c->device);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-  c->d_dbw.release(); c->d_goff.release(); c->d_loff.release(); c->d_lens.release();
-  c->d_perm.release(); c->d_sbias.release(); c->d_lin.release(); c->d_self.release();
-  c->d_sorted.release(); c->d_scores.release(); c->d_nid.release(); c->h_nid.release(); c->d_dist.release(); c->d_prefix.release();
+  c->d_dbw.release(); c->d_blob.release(); c->h_blob.release();
+  c->d_sorted.release(); c->d_scores.release(); c->d_nid.release(); c->h_nid.release(); c->d_dist.release();
   c->d_counter.release(); c->d_bnd.release(); c->h_scores.release(); c->h_dist.release();
-  c->lin.release(); c->d_treeD.release(); c->d_treemin.release(); c->d_treeh.release(); c->d_treeu.release(); c->d_merges.release();
+  c->d_treeD.release(); c->d_treemin.release(); c->d_treeh.release(); c->d_treeu.release(); c->d_merges.release();
   c->d_pairs32.release(); c->d_tasks16w.release(); c->d_bnd16w.release(); c->d_bnd32.release(); c->d_smat.release();
   if (c->d_cancel) cudaFree(c->d_cancel);
   if (c->h_one) cudaFreeHost(c->h_one);
@@ -912,9 +956,10 @@ int tsq_set_sequences(tsq_ctx* c, const char* const* residues, const uint32_t* l
   c->have_seqs = c->uploaded = c->computed = c->finalized = c->downloaded = false;
   c->n = 0;
   c->enc.resize(n);
+  c->self_input.resize(n);
   for (uint32_t i = 0; i < n; i++) {
     if (lengths[i] > 0 && !residues[i]) return fail(c, TSQ_ERR_INVALID, "sequence %u is null", i);
-    encode_into(c->prm.alphabet, residues[i], lengths[i], c->enc[i]);
+    c->self_input[i] = (int32_t)encode_into(c->prm.alphabet, c->diag_by_byte, residues[i], lengths[i], c->enc[i]);
   }
   c->n = n;
   c->have_seqs = true;
@@ -929,9 +974,11 @@ int tsq_set_sequences_flat(tsq_ctx* c, const char* residues, const uint64_t* off
   c->have_seqs = c->uploaded = c->computed = c->finalized = c->downloaded = false;
   c->n = 0;
   c->enc.resize(n);
+  c->self_input.resize(n);
   for (uint32_t i = 0; i < n; i++) {
     if (offsets[i + 1] < offsets[i]) return fail(c, TSQ_ERR_INVALID, "offsets not ascending at %u", i);
-    encode_into(c->prm.alphabet, residues + offsets[i], (size_t)(offsets[i + 1] - offsets[i]), c->enc[i]);
+    c->self_input[i] = (int32_t)encode_into(c->prm.alphabet, c->diag_by_byte, residues + offsets[i],
+                                            (size_t)(offsets[i + 1] - offsets[i]), c->enc[i]);
   }
   c->n = n;
   c->have_seqs = true;
@@ -1130,7 +1177,7 @@ int tsq_identities(tsq_ctx* c, const int32_t** out, uint64_t* count) {
 int tsq_self_scores(tsq_ctx* c, const int32_t** self, uint32_t* n) {
   if (!c || !self) return TSQ_ERR_INVALID;
   if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "no sequences uploaded");
-  *self = c->self_orig.data();
+  *self = c->self_input.data();
   if (n) *n = c->n;
   return TSQ_OK;
 }
