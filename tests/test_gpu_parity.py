@@ -301,6 +301,28 @@ def test_force_wavefront_nucleotide_ragged_matches_oracle(wf):
     assert_same(seqs[:20], alphabet=1, go=0, ge=2, flags=t.FLAG_FORCE_S32 | wf)
 
 
+@pytest.mark.parametrize("kw,ctas", [(32, 2), (24, 3), (16, 3), (8, 2)])
+def test_every_packed_wavefront_variant(kw, ctas, monkeypatch):
+    """Each instantiated wave16 variant (columns per lane, CTAs per SM): sequences shorter than, equal to
+    and several times one pass of 32*kw columns; default and runtime gap-model specialisations."""
+    monkeypatch.setenv("TSQ_FORCE_KW16", f"{kw},{ctas}")
+    rng = np.random.default_rng(kw)
+    seqs = (ragged(rng, 14, 1, 3 * 32 * kw + 50, "ACGT") + ragged(rng, 3, 32 * kw - 1, 32 * kw + 2, "ACGTN") +
+            ragged(rng, 2, 1023, 1026, "ACGT"))
+    st, cells = assert_same(seqs, alphabet=1, flags=t.FLAG_FORCE_S32)
+    assert st["cells_s32"] == cells
+    assert_same(seqs[:12], alphabet=1, go=4, ge=2, flags=t.FLAG_FORCE_S32)
+
+
+@pytest.mark.parametrize("kw,ctas", [(32, 2), (24, 3), (16, 4), (16, 3), (8, 4), (8, 2)])
+def test_every_32_bit_wavefront_variant(kw, ctas, monkeypatch):
+    monkeypatch.setenv("TSQ_FORCE_KW", f"{kw},{ctas}")
+    rng = np.random.default_rng(100 + kw + ctas)
+    seqs = ragged(rng, 12, 1, 3 * 32 * kw + 50, "ACGT") + ragged(rng, 3, 32 * kw - 1, 32 * kw + 2, "ACGTN")
+    st, cells = assert_same(seqs, alphabet=1, flags=t.FLAG_FORCE_S32 | t.FLAG_NO_WAVE16)
+    assert st["cells_s32"] == cells
+
+
 @pytest.mark.parametrize("wf", WAVE)
 def test_long_nucleotide_sequences_use_both_regimes(wf):
     rng = np.random.default_rng(92)

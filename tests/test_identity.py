@@ -103,3 +103,22 @@ def test_wide_gap_penalties_use_the_32_bit_inter_task_kernel():
     enc = [o.encode(x) for x in seqs]
     ref, cells = o.all_pairs(enc, MAT, 4000, 900, nthreads=4)
     assert (s == ref).all() and st["cells_s32"] == cells and st["cells_s16"] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K", [30, 32, 36, 40, 44, 48, 50, 52, 56])
+def test_every_strip_width_of_the_32_bit_inter_task_kernel(K, monkeypatch):
+    """gotoh32_kernel is instantiated for the same strip widths as the packed kernel; identity mode
+    routes every short sequence through it."""
+    import tweakseq_b200 as t
+    monkeypatch.setenv("TSQ_FORCE_K", str(K))
+    rng = np.random.default_rng(500 + K)
+    lens = list(rng.integers(1, 3 * K + 7, 40)) + [K - 1, K, K + 1, 2 * K, 2 * K + 1]
+    seqs = ["".join(rng.choice(list("ARNDCQEGHILKMFPSTWYV"), int(l))) for l in lens]
+    with t.Context(flags=t.FLAG_IDENTITY) as ctx:
+        ctx.set_sequences(seqs)
+        ctx.run()
+        s, k, st = ctx.scores(), ctx.identities(), ctx.stats()
+    assert st["strip_width"] == K and st["cells_s16"] == 0
+    rs, rk, _ = o.all_pairs_id([o.encode(x) for x in seqs], MAT, 11, 1)
+    assert (s == rs).all() and (k == rk).all()
