@@ -140,6 +140,36 @@ int B200Gotoh::guideTree(const std::vector<std::string>& residues, const std::ve
   return rc;
 }
 
+int B200Gotoh::pairwiseAlignment(const std::string& a, const std::string& b, std::string& rowA, std::string& rowB, int& score,
+                                 std::string* error) {
+  tsq_params p;
+  fill(p, *this);
+  tsq_ctx* c = nullptr;
+  int rc = tsq_create(&c, &p);
+  if (rc != TSQ_OK) {
+    if (error) *error = tsq_status_string(rc);
+    return rc;
+  }
+  const char* ptr[2] = {a.data(), b.data()};
+  const uint32_t len[2] = {(uint32_t)a.size(), (uint32_t)b.size()};
+  const uint32_t cap = len[0] + len[1] + 1;
+  std::vector<char> ra(cap), rb(cap);
+  uint32_t cols = 0;
+  int32_t sc = 0;
+  rc = tsq_set_sequences(c, ptr, len, 2);
+  if (rc == TSQ_OK) rc = tsq_upload(c);
+  if (rc == TSQ_OK) rc = tsq_align_pair(c, 0, 1, ra.data(), rb.data(), cap, &cols, &sc);
+  if (rc == TSQ_OK) {
+    rowA.assign(ra.data(), cols);
+    rowB.assign(rb.data(), cols);
+    score = sc;
+  } else if (error) {
+    *error = tsq_last_error(c);
+  }
+  tsq_destroy(c);
+  return rc;
+}
+
 int B200Gotoh::consensus(const std::vector<std::string>& rows, double plurality, std::string& out, std::string* error) {
   tsq_params p;
   fill(p, *this);

@@ -30,6 +30,9 @@ class B200Gotoh : public AlignmentTool {
   // Guide tree of the same job: Newick text for clustalo --guidetree-in.
   int guideTree(const std::vector<std::string>& residues, const std::vector<std::string>& labels,
                 const std::string& newickPath, std::string* error = nullptr);
+  // One optimal global alignment of two sequences with its path: two gapped rows.
+  int pairwiseAlignment(const std::string& a, const std::string& b, std::string& rowA, std::string& rowB, int& score,
+                        std::string* error = nullptr);
   // Consensus annotation of an alignment: Consensus::calculate (Consensus.cpp:80-161) on the GPU.
   int consensus(const std::vector<std::string>& alignedRows, double plurality, std::string& out,
                 std::string* error = nullptr);

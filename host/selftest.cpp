@@ -52,6 +52,10 @@ int main(int argc, char** argv) {
     std::string cons;
     CHECK(g.consensus({"AWC-a", "AWC-A", "AYD-A", "RWC-x"}, -1.0, cons, &err) == TSQ_OK);
     CHECK(cons == "AWC-?");
+    std::string ra, rb;
+    int sc = 0;
+    CHECK(g.pairwiseAlignment("WWCWW", "WWWW", ra, rb, sc, &err) == TSQ_OK);
+    CHECK(ra == "WWCWW" && rb.size() == 5 && sc == 44 - 12);   // one gap of length 1 against C
     g.identityDistance = true;
     CHECK(g.distanceMatrix({"WWWW", "WWCWW", "ACDEFG"}, s, d, &err) == TSQ_OK);
     CHECK(d[0] == 0.0);   // 4 identities over the shorter length 4

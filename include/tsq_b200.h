@@ -179,6 +179,22 @@ int tsq_guide_tree(tsq_ctx *ctx, const tsq_merge **merges, uint32_t *count);
 int tsq_write_newick(tsq_ctx *ctx, const char *const *labels, const char *path);
 
 /*
+ * One optimal global alignment of sequences i and j (submitted order) WITH its path -- the
+ * "emit pairwise alignments" half of SURVEY.md section 8f-2; what a user would otherwise get by
+ * running the external aligner on two sequences (tweakseq/Core/ClustalO.cpp:48-52 argv on a
+ * two-record FASTA).  Needs tsq_upload (or tsq_run) to have happened.  row_i / row_j receive the
+ * two gapped rows: canonical upper-case symbols (ARNDCQEGHILKMFPSTWYVBZX or ACGTN; the input's
+ * own spelling of a residue is not kept) and '-', NUL-terminated; capacity must be at least
+ * len_i + len_j + 1 (lengths after gap stripping).  *columns = alignment length, *score = its
+ * Gotoh score, equal to the matrix entry S(i, j).  Among equally good alignments the path is
+ * fixed by rule (diagonal before gap-in-row-i before gap-in-row-j; a gap run is opened rather
+ * than extended on a tie), the same rule the CPU oracle applies.  It is one optimal alignment: its
+ * identity count can be below the maximum TSQ_FLAG_IDENTITY reports over all optimal alignments.
+ */
+int tsq_align_pair(tsq_ctx *ctx, uint32_t i, uint32_t j, char *row_i, char *row_j, uint32_t capacity,
+                   uint32_t *columns, int32_t *score);
+
+/*
  * Consensus annotation of an alignment: what Consensus::calculate
  * (tweakseq/Core/Annotations/Consensus.cpp:80-161) computes on the GUI thread in O(cols * rows^2),
  * here per column from a histogram of residue classes in O(rows + 24^2).  rows[r] has ncols

@@ -340,6 +340,64 @@ void tsq_oracle_gotoh_id(const uint8_t *a, int m, const uint8_t *b, int n, const
   free(H);
 }
 
+/* ---- one optimal alignment with its path ("emitting pairwise alignments") ----
+ * Full H, E, F matrices, row by row; the walk back from (m, n) re-derives every decision from the
+ * stored values.  Tie rules (build-defined, shared with the CUDA kernel): H prefers the diagonal,
+ * then E (gap in a), then F (gap in b); a gap run that can equally be opened or extended was opened.
+ * out_a / out_b: m + n + 1 bytes each, symbols or 0xff for a gap, written first column first.
+ * Returns the number of columns; *score = H(m, n). */
+uint32_t tsq_oracle_traceback(const uint8_t *a, int m, const uint8_t *b, int n, const int8_t *mat, int nsym,
+                              int go, int ge, uint8_t *out_a, uint8_t *out_b, int32_t *score) {
+  const int32_t NEG = -(1 << 29);
+  const int goe = go + ge;
+  const size_t ld = (size_t)n + 1, cells = ((size_t)m + 1) * ld;
+  int32_t *H = (int32_t *)malloc(sizeof(int32_t) * 3 * cells);
+  int32_t *E = H + cells, *F = E + cells;
+  H[0] = 0; E[0] = NEG; F[0] = NEG;
+  for (int j = 1; j <= n; j++) { H[j] = E[j] = -go - j * ge; F[j] = NEG; }
+  for (int i = 1; i <= m; i++) {
+    int32_t *h = H + (size_t)i * ld, *e = E + (size_t)i * ld, *f = F + (size_t)i * ld;
+    const int32_t *hu = h - ld, *fu = f - ld;
+    const int8_t *srow = mat + (size_t)a[i - 1] * nsym;
+    h[0] = f[0] = -go - i * ge; e[0] = NEG;
+    for (int j = 1; j <= n; j++) {
+      int32_t e1 = e[j - 1] - ge, e2 = h[j - 1] - goe;
+      int32_t f1 = fu[j] - ge, f2 = hu[j] - goe;
+      int32_t dg = hu[j - 1] + srow[b[j - 1]];
+      e[j] = e2 >= e1 ? e2 : e1;
+      f[j] = f2 >= f1 ? f2 : f1;
+      int32_t best = dg;
+      if (e[j] > best) best = e[j];
+      if (f[j] > best) best = f[j];
+      h[j] = best;
+    }
+  }
+  *score = H[(size_t)m * ld + n];
+  uint8_t *ra = (uint8_t *)malloc(2 * ((size_t)m + n) + 2), *rb = ra + (size_t)m + n + 1;
+  uint32_t k = 0;
+  int i = m, j = n, state = 0;
+  while (i > 0 || j > 0) {
+    if (i == 0) { ra[k] = 0xff; rb[k] = b[j - 1]; j--; k++; continue; }
+    if (j == 0) { ra[k] = a[i - 1]; rb[k] = 0xff; i--; k++; continue; }
+    const size_t at = (size_t)i * ld + j;
+    if (state == 0) {
+      if (H[at] == H[at - ld - 1] + mat[(size_t)a[i - 1] * nsym + b[j - 1]]) { ra[k] = a[i - 1]; rb[k] = b[j - 1]; i--; j--; k++; }
+      else state = (H[at] == E[at]) ? 1 : 2;
+    } else if (state == 1) {
+      ra[k] = 0xff; rb[k] = b[j - 1]; k++;
+      if (E[at] == H[at - 1] - goe) state = 0;
+      j--;
+    } else {
+      ra[k] = a[i - 1]; rb[k] = 0xff; k++;
+      if (F[at] == H[at - ld] - goe) state = 0;
+      i--;
+    }
+  }
+  for (uint32_t c = 0; c < k; c++) { out_a[c] = ra[k - 1 - c]; out_b[c] = rb[k - 1 - c]; }
+  free(ra); free(H);
+  return k;
+}
+
 /* ---- consensus annotation: Consensus.cpp:80-161 restated ---- */
 void tsq_oracle_consensus(const char *const *rows, uint32_t nrows, uint32_t ncols, double plurality, char *out) {
   if (nrows == 0) { for (uint32_t c = 0; c < ncols; c++) out[c] = '?'; return; }

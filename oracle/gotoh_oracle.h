@@ -76,6 +76,14 @@ void tsq_oracle_gotoh_id(const uint8_t *a, int m, const uint8_t *b, int n, const
                          int go, int ge, int32_t *score, int32_t *identities);
 
 /*
+ * One optimal alignment with its path.  out_a / out_b: m + n + 1 bytes each,
+ * symbols or 0xff for a gap.  Returns the column count; *score = the Gotoh score.  Tie rules:
+ * diagonal, then gap in a, then gap in b; open rather than extend.
+ */
+uint32_t tsq_oracle_traceback(const uint8_t *a, int m, const uint8_t *b, int n, const int8_t *mat, int nsym,
+                              int go, int ge, uint8_t *out_a, uint8_t *out_b, int32_t *score);
+
+/*
  * Consensus annotation: line-by-line restatement of Consensus::calculate,
  * tweakseq/Core/Annotations/Consensus.cpp:80-161, doubles and all: rows[r] has ncols characters
  * (already `& 0xff`), out gets ncols characters, '?' where the winner's matches < plurality.

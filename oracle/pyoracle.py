@@ -54,6 +54,8 @@ def lib():
         L.tsq_oracle_gotoh_id.argtypes = [u8p, C.c_int, u8p, C.c_int, i8p, C.c_int, C.c_int, C.c_int, i32p, i32p]
         L.tsq_oracle_consensus.restype = None
         L.tsq_oracle_consensus.argtypes = [C.POINTER(C.c_char_p), C.c_uint32, C.c_uint32, C.c_double, C.c_char_p]
+        L.tsq_oracle_traceback.restype = C.c_uint32
+        L.tsq_oracle_traceback.argtypes = [u8p, C.c_int, u8p, C.c_int, i8p, C.c_int, C.c_int, C.c_int, u8p, u8p, i32p]
         L.tsq_oracle_upgma.restype = None
         L.tsq_oracle_upgma.argtypes = [C.POINTER(C.c_double), C.c_uint32, u32p, u32p, C.POINTER(C.c_double)]
         _lib = L
@@ -200,6 +202,21 @@ def gotoh_id(a: np.ndarray, b: np.ndarray, mat: np.ndarray, go: int, ge: int):
     lib().tsq_oracle_gotoh_id(_p(a, C.c_uint8), len(a), _p(b, C.c_uint8), len(b), _p(m8, C.c_int8), m8.shape[0], go, ge,
                               C.byref(sc), C.byref(nid))
     return sc.value, nid.value
+
+
+def traceback(a: np.ndarray, b: np.ndarray, mat: np.ndarray, go: int, ge: int, alphabet: int = PROTEIN):
+    """(row_a, row_b, score): one optimal alignment as two gapped strings of canonical symbols."""
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    m8 = np.ascontiguousarray(mat, dtype=np.int8)
+    oa = np.empty(len(a) + len(b) + 1, dtype=np.uint8)
+    ob = np.empty(len(a) + len(b) + 1, dtype=np.uint8)
+    sc = C.c_int32()
+    k = lib().tsq_oracle_traceback(_p(a, C.c_uint8), len(a), _p(b, C.c_uint8), len(b), _p(m8, C.c_int8), m8.shape[0],
+                                   go, ge, _p(oa, C.c_uint8), _p(ob, C.c_uint8), C.byref(sc))
+    letters = "ACGTN" if alphabet == NUCLEOTIDE else "ARNDCQEGHILKMFPSTWYVBZX"
+    dec = lambda v: "".join("-" if x == 0xff else letters[x] for x in v[:k])
+    return dec(oa), dec(ob), sc.value
 
 
 def all_pairs_id(encoded, mat, go, ge):

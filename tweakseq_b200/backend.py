@@ -144,6 +144,15 @@ class B200Gotoh(AlignmentTool):
             self.last_stats = ctx.stats()
             return tree
 
+    def pairwise_alignment(self, residues_a, residues_b):
+        """One optimal global alignment of two sequences with its path: (row_a, row_b, score).
+        What running the external tool on a two-record FASTA would hand back, in process."""
+        with capi.Context(alphabet=self.alphabet, gap_open=self.gap_open, gap_extend=self.gap_extend,
+                          device=self.device) as ctx:
+            ctx.set_sequences([residues_a, residues_b])
+            ctx.upload()
+            return ctx.align_pair(0, 1)
+
     def consensus(self, aligned_rows, plurality: float = -1.0) -> str:
         """Consensus annotation of an alignment: Consensus::calculate (Consensus.cpp:80-161) on the GPU."""
         with capi.Context(device=self.device) as ctx:

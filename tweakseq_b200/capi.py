@@ -57,7 +57,7 @@ SYMBOLS = ["tsq_version", "tsq_version_string", "tsq_status_string", "tsq_device
            "tsq_download", "tsq_set_stream", "tsq_synchronize", "tsq_run", "tsq_scores", "tsq_distances",
            "tsq_self_scores", "tsq_identities", "tsq_device_scores", "tsq_partition", "tsq_finalize", "tsq_device_results",
            "tsq_get_stats", "tsq_measure_dpx_rate", "tsq_run_fasta", "tsq_plan_partition", "tsq_guide_tree",
-           "tsq_write_newick", "tsq_consensus"]
+           "tsq_write_newick", "tsq_consensus", "tsq_align_pair"]
 
 _lib = None
 
@@ -109,6 +109,8 @@ def load_library():
     L.tsq_guide_tree.argtypes = [vp, C.POINTER(C.POINTER(Merge)), C.POINTER(C.c_uint32)]
     L.tsq_write_newick.argtypes = [vp, C.POINTER(C.c_char_p), C.c_char_p]
     L.tsq_consensus.argtypes = [vp, C.POINTER(C.c_char_p), C.c_uint32, C.c_uint32, C.c_double, C.c_char_p]
+    L.tsq_align_pair.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32),
+                                 C.POINTER(C.c_int32)]
     L.tsq_plan_partition.argtypes = [C.POINTER(Params), C.POINTER(C.c_uint32), C.c_uint32, C.c_int32, u64p, u64p]
     L.tsq_measure_dpx_rate.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.tsq_run_fasta.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(Params), LOG_CB, vp, C.POINTER(C.c_int)]
@@ -204,6 +206,7 @@ class Context:
         self._keep = (raw, arr, lens)
         self._ck(self._L.tsq_set_sequences(self._h, arr, lens, n))
         self.n = n
+        self._pair_capacity = 2 * max((len(r) for r in raw), default=0) + 1
 
     def set_sequences_flat(self, buf: bytes, offsets: np.ndarray):
         """One contiguous host buffer + n+1 offsets (tsq_set_sequences_flat)."""
@@ -212,6 +215,7 @@ class Context:
         self._keep = (buf, offsets)
         self._ck(self._L.tsq_set_sequences_flat(self._h, buf, offsets.ctypes.data_as(C.POINTER(C.c_uint64)), n))
         self.n = n
+        self._pair_capacity = 2 * int(np.diff(offsets).max(initial=0)) + 1
 
     def upload(self):
         self._ck(self._L.tsq_upload(self._h))
@@ -313,6 +317,14 @@ class Context:
         out = C.create_string_buffer(ncols + 1)
         self._ck(self._L.tsq_consensus(self._h, arr, len(raw), ncols, plurality, out))
         return out.raw[:ncols].decode("latin-1")
+
+    def align_pair(self, i: int, j: int) -> tuple[str, str, int]:
+        """One optimal global alignment of submitted sequences i and j: (row_i, row_j, score)."""
+        cap = self._pair_capacity
+        a, b = C.create_string_buffer(cap), C.create_string_buffer(cap)
+        cols, score = C.c_uint32(), C.c_int32()
+        self._ck(self._L.tsq_align_pair(self._h, i, j, a, b, cap, C.byref(cols), C.byref(score)))
+        return a.raw[:cols.value].decode("ascii"), b.raw[:cols.value].decode("ascii"), score.value
 
     def stats(self) -> dict:
         st = Stats()

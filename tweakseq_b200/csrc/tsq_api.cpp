@@ -1304,6 +1304,71 @@ int tsq_write_newick(tsq_ctx* c, const char* const* labels, const char* path) {
   return TSQ_OK;
 }
 
+int tsq_align_pair(tsq_ctx* c, uint32_t i, uint32_t j, char* row_i, char* row_j, uint32_t capacity, uint32_t* columns,
+                   int32_t* score) {
+  if (!c || !row_i || !row_j) return TSQ_ERR_INVALID;
+  if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "tsq_align_pair before tsq_upload");
+  if (i >= c->n || j >= c->n) return fail(c, TSQ_ERR_INVALID, "pair (%u, %u) outside 0..%u", i, j, c->n);
+  uint32_t si = c->n, sj = c->n;   // sorted positions of the two submitted indices
+  for (uint32_t k = 0; k < c->n; k++) {
+    if (c->perm[k] == i) si = k;
+    if (c->perm[k] == j) sj = k;
+  }
+  const uint32_t m = c->lens[si], n = c->lens[sj];
+  if ((uint64_t)m + n + 1 > capacity) return fail(c, TSQ_ERR_INVALID, "capacity %u < %llu", capacity, (unsigned long long)m + n + 1);
+  const size_t dir_bytes = ((size_t)m + 1) * ((size_t)n + 1);
+  if (dir_bytes > ((size_t)16 << 30)) return fail(c, TSQ_ERR_NOMEM, "direction matrix of %u x %u cells exceeds 16 GiB", m, n);
+  TSQ_CUDA(c, cudaSetDevice(c->device));
+  DevBuf<uint8_t> d_dir, d_out;
+  DevBuf<int32_t> d_work;   // 7 rolling diagonals, the plain score table, info[2]
+  const uint32_t nsym = (uint32_t)c->nsym;
+  const size_t w_diag = 7 * ((size_t)m + 1), w_smat = (size_t)nsym * nsym;
+  std::vector<int32_t> smat(w_smat);
+  for (size_t k = 0; k < w_smat; k++) smat[k] = c->matrix[k];
+  std::vector<uint8_t> out(2 * ((size_t)m + n) + 1);
+  int32_t info[2] = {0, 0};
+  cudaError_t e = d_dir.reserve(dir_bytes);
+  if (e == cudaSuccess) e = d_out.reserve(2 * ((size_t)m + n) + 1);
+  if (e == cudaSuccess) e = d_work.reserve(w_diag + w_smat + 2);
+  if (e == cudaSuccess) {
+    cudaStream_t s = c->stream;
+    tsq::TbParams t{};
+    t.a = c->d_lin.p + c->loff[si];
+    t.b = c->d_lin.p + c->loff[sj];
+    t.m = m;
+    t.n = n;
+    t.diag = d_work.p;
+    t.smat = d_work.p + w_diag;
+    t.info = d_work.p + w_diag + w_smat;
+    t.nsym = nsym;
+    t.go = c->go;
+    t.ge = c->ge;
+    t.dir = d_dir.p;
+    t.out_a = d_out.p;
+    t.out_b = d_out.p + m + n;
+    e = cudaMemcpyAsync(d_work.p + w_diag, smat.data(), w_smat * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = tsq::traceback_launch(t, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out.data(), d_out.p, 2 * ((size_t)m + n), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(info, t.info, sizeof info, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  }
+  d_dir.release(); d_out.release(); d_work.release();
+  if (e != cudaSuccess) return fail(c, e == cudaErrorMemoryAllocation ? TSQ_ERR_NOMEM : TSQ_ERR_CUDA, "tsq_align_pair: %s", cudaGetErrorString(e));
+  const uint32_t cols = (uint32_t)info[0];
+  if (cols > m + n) return fail(c, TSQ_ERR_CUDA, "internal: traceback of %u columns for %u + %u residues", cols, m, n);
+  const char* letters = c->prm.alphabet == TSQ_NUCLEOTIDE ? "ACGTN" : "ARNDCQEGHILKMFPSTWYVBZX";
+  for (uint32_t k = 0; k < cols; k++) {   // the kernel wrote the path from the end: reverse
+    const uint8_t a = out[cols - 1 - k], b = out[(size_t)m + n + cols - 1 - k];
+    row_i[k] = a == 0xff ? '-' : letters[a];
+    row_j[k] = b == 0xff ? '-' : letters[b];
+  }
+  row_i[cols] = row_j[cols] = 0;
+  if (columns) *columns = cols;
+  if (score) *score = info[1];
+  c->st.launches += 1;
+  return TSQ_OK;
+}
+
 int tsq_consensus(tsq_ctx* c, const char* const* rows, uint32_t nrows, uint32_t ncols, double plurality, char* out) {
   if (!c) return TSQ_ERR_INVALID;
   if ((nrows > 0 && !rows) || (ncols > 0 && !out)) return fail(c, TSQ_ERR_INVALID, "null alignment / output");

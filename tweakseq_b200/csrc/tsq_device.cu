@@ -298,6 +298,12 @@ cudaError_t upgma_launch(const UpgmaParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// ---- pairwise traceback ------------------------------------------------------------------------------
+cudaError_t traceback_launch(const TbParams& p, cudaStream_t stream) {
+  traceback_kernel<<<1, TB_THREADS, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
 // ---- finalize: empties, un-sort, fp64 distances -----------------------------------------
 // One CTA per sorted row i; threads stride over j > i.  Distances follow the oracle's
 // tsq_oracle_distance(): two separately rounded IEEE operations (div, sub), no contraction.

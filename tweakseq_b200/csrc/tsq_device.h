@@ -8,6 +8,7 @@
 #include "wave32.cuh"
 #include "wave16.cuh"
 #include "upgma.cuh"
+#include "traceback.cuh"
 
 namespace tsq {
 
@@ -48,6 +49,9 @@ cudaError_t w16_launch(int grid, const W16Params& p, cudaStream_t stream);
 
 // UPGMA guide tree: init (one CTA per row) + one persistent CTA for the n-1 merges.
 cudaError_t upgma_launch(const UpgmaParams& p, cudaStream_t stream);
+
+// One pair with its path (traceback.cuh): a single CTA sweeps the anti-diagonals.
+cudaError_t traceback_launch(const TbParams& p, cudaStream_t stream);
 
 // Builds the 32-way interleaved subject database of the packed kernel from the linear residues:
 // per residue the 16-bit byte offset of its profile row, two rows per word, right-aligned to an
