@@ -1316,7 +1316,7 @@ int tsq_align_pair(tsq_ctx* c, uint32_t i, uint32_t j, char* row_i, char* row_j,
   }
   const uint32_t m = c->lens[si], n = c->lens[sj];
   if ((uint64_t)m + n + 1 > capacity) return fail(c, TSQ_ERR_INVALID, "capacity %u < %llu", capacity, (unsigned long long)m + n + 1);
-  const size_t dir_bytes = ((size_t)m + 1) * ((size_t)n + 1);
+  const size_t dir_bytes = ((size_t)m + n + 1) * ((size_t)std::min(m, n) + 1);   // diagonal-major, padded rows
   if (dir_bytes > ((size_t)16 << 30)) return fail(c, TSQ_ERR_NOMEM, "direction matrix of %u x %u cells exceeds 16 GiB", m, n);
   TSQ_CUDA(c, cudaSetDevice(c->device));
   DevBuf<uint8_t> d_dir, d_out;

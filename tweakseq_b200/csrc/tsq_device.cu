@@ -300,8 +300,24 @@ cudaError_t upgma_launch(const UpgmaParams& p, cudaStream_t stream) {
 
 // ---- pairwise traceback ------------------------------------------------------------------------------
 cudaError_t traceback_launch(const TbParams& p, cudaStream_t stream) {
-  traceback_kernel<<<1, TB_THREADS, 0, stream>>>(p);
-  return cudaGetLastError();
+  const uint32_t longest_diag = (p.m < p.n ? p.m : p.n) + 1;
+  if (longest_diag <= 2u * TB_THREADS) {   // a CTA covers the diagonal in <= 2 sweeps: the CTA barrier is cheaper
+    traceback_kernel<1><<<1, TB_THREADS, 0, stream>>>(p);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(TB_CLUSTER);
+  cfg.blockDim = dim3(TB_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = TB_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, traceback_kernel<TB_CLUSTER>, p);
 }
 
 // ---- finalize: empties, un-sort, fp64 distances -----------------------------------------
