@@ -158,6 +158,9 @@ int tsq_identities(tsq_ctx *ctx, const int32_t **packed_upper, uint64_t *count);
  */
 int tsq_device_scores(tsq_ctx *ctx, void **d_sorted_scores, uint64_t *count);
 int tsq_partition(tsq_ctx *ctx, uint64_t *part_begin, uint64_t *part_end);
+/* The slab of ANY rank of this context's partition (every rank plans all ranks identically from the
+ * same sequences, so no exchange of ranges is needed before the gather).  After tsq_upload. */
+int tsq_partition_of(tsq_ctx *ctx, int32_t rank, uint64_t *begin, uint64_t *end);
 /* Sorted-order slab complete on this device -> original-order scores (+distances). */
 int tsq_finalize(tsq_ctx *ctx);
 int tsq_device_results(tsq_ctx *ctx, void **d_scores, void **d_distances, uint64_t *count);

@@ -57,7 +57,7 @@ SYMBOLS = ["tsq_version", "tsq_version_string", "tsq_status_string", "tsq_device
            "tsq_download", "tsq_set_stream", "tsq_synchronize", "tsq_run", "tsq_scores", "tsq_distances",
            "tsq_self_scores", "tsq_identities", "tsq_device_scores", "tsq_partition", "tsq_finalize", "tsq_device_results",
            "tsq_get_stats", "tsq_measure_dpx_rate", "tsq_run_fasta", "tsq_plan_partition", "tsq_guide_tree",
-           "tsq_write_newick", "tsq_consensus", "tsq_align_pair"]
+           "tsq_write_newick", "tsq_consensus", "tsq_align_pair", "tsq_partition_of"]
 
 _lib = None
 
@@ -104,6 +104,7 @@ def load_library():
     L.tsq_identities.argtypes = [vp, C.POINTER(i32p), u64p]
     L.tsq_device_scores.argtypes = [vp, C.POINTER(vp), u64p]
     L.tsq_partition.argtypes = [vp, u64p, u64p]
+    L.tsq_partition_of.argtypes = [vp, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.tsq_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), u64p]
     L.tsq_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.tsq_guide_tree.argtypes = [vp, C.POINTER(C.POINTER(Merge)), C.POINTER(C.c_uint32)]
@@ -275,6 +276,12 @@ class Context:
     def partition(self) -> tuple[int, int]:
         b, e = C.c_uint64(), C.c_uint64()
         self._ck(self._L.tsq_partition(self._h, C.byref(b), C.byref(e)))
+        return b.value, e.value
+
+    def partition_of(self, rank: int) -> tuple[int, int]:
+        """[begin, end) slab of any rank of this context's partition (no communication needed)."""
+        b, e = C.c_uint64(), C.c_uint64()
+        self._ck(self._L.tsq_partition_of(self._h, rank, C.byref(b), C.byref(e)))
         return b.value, e.value
 
     def device_scores(self) -> _DevArray:

@@ -154,6 +154,7 @@ struct tsq_ctx {
   uint32_t lo = 0, hi = 0;  // sorted range eligible for the packed 16-bit kernel
   uint32_t row_a = 0, row_b = 0;  // this partition's sorted rows
   uint64_t part_begin = 0, part_end = 0;
+  std::vector<uint32_t> first_row;        // first sorted row of every rank of the partition (world + 1 entries)
   std::vector<unsigned long long> task_prefix;
   std::vector<uint2> pairs32;             // tasks of the 32-bit wavefront kernel (sorted indices)
   std::vector<uint4> tasks16w;            // tasks of the packed wavefront kernel (i1, i2, j, 0)
@@ -425,10 +426,9 @@ int host_plan_work(tsq_ctx* c) {
   const uint64_t npairs = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
   // ---- partition of the sorted rows across ranks (contiguous, balanced by DP cells) ---------
   const int world = c->prm.part_world, rank = c->prm.part_rank;
-  std::vector<uint32_t> first_row;
   c->use_w16 = wave16_ok(c, c->nsym, c->prm.flags) && c->idshift == 0;   // identity keys are too wide to pack
-  plan_rows(c->lens, lo, hi, world, first_row, c->use_w16 ? 1.5 : 2.4);
-  auto boundary = [&](int r) -> uint32_t { return first_row[(size_t)r]; };
+  plan_rows(c->lens, lo, hi, world, c->first_row, c->use_w16 ? 1.5 : 2.4);
+  auto boundary = [&](int r) -> uint32_t { return c->first_row[(size_t)r]; };
   c->row_a = boundary(rank);
   c->row_b = boundary(rank + 1);
   c->part_begin = (n >= 2 && c->row_a + 1 < n) ? tri(c->row_a, c->row_a + 1, n) : npairs;
@@ -1195,6 +1195,19 @@ int tsq_partition(tsq_ctx* c, uint64_t* b, uint64_t* e) {
   if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "tsq_partition before tsq_upload");
   if (b) *b = c->part_begin;
   if (e) *e = c->part_end;
+  return TSQ_OK;
+}
+
+int tsq_partition_of(tsq_ctx* c, int32_t rank, uint64_t* b, uint64_t* e) {
+  if (!c) return TSQ_ERR_INVALID;
+  if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "tsq_partition_of before tsq_upload");
+  if (rank < 0 || rank >= c->prm.part_world) return fail(c, TSQ_ERR_INVALID, "rank %d outside 0..%d", rank, c->prm.part_world);
+  const uint64_t n = c->n, npairs = n < 2 ? 0 : n * (n - 1) / 2;
+  auto start_of = [&](uint32_t row) -> uint64_t { return (n >= 2 && (uint64_t)row + 1 < n) ? tri(row, row + 1, n) : npairs; };
+  uint64_t lo = start_of(c->first_row[(size_t)rank]), hi = start_of(c->first_row[(size_t)rank + 1]);
+  if (lo > hi) lo = hi;
+  if (b) *b = lo;
+  if (e) *e = hi;
   return TSQ_OK;
 }
 

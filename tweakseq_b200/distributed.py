@@ -60,14 +60,9 @@ class ShardedRun:
 
     def upload(self):
         self.ctx.upload()
-        mine = self.ctx.partition()
-        if self.world > 1:
-            t = torch.tensor(mine, dtype=torch.int64, device="cuda")
-            allr = [torch.empty_like(t) for _ in range(self.world)]
-            dist.all_gather(allr, t, group=self.group)
-            self.ranges = [tuple(int(x) for x in a.tolist()) for a in allr]
-        else:
-            self.ranges = [mine]
+        # every rank plans all ranks' slabs from the same sequences: no exchange of ranges before the gather
+        self.ranges = [self.ctx.partition_of(r) for r in range(self.world)]
+        assert self.ranges[self.rank] == self.ctx.partition()
         self.buf = torch.as_tensor(self.ctx.device_scores(), device="cuda")
 
     def compute(self):
