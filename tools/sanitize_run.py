@@ -21,4 +21,10 @@ job(prot, tree=True)                                            # gotoh16 + fina
 nt = ["".join(rng.choice(list("ACGT"), int(l))) for l in rng.integers(1, 1300, 12)]
 job(nt, alphabet=1, flags=t.FLAG_FORCE_S32)                      # wave16 (TMA ring)
 job(nt[:8], alphabet=1, flags=t.FLAG_FORCE_S32 | t.FLAG_NO_WAVE16)  # wave32
+with t.Context(alphabet=1) as ctx:                               # traceback: single-CTA and 8-CTA cluster variants
+    ctx.set_sequences([nt[0][:300], nt[1][:200], "ACGT" * 600, "ACGA" * 560])
+    ctx.upload()
+    enc = [o.encode(x, 1) for x in (nt[0][:300], nt[1][:200], "ACGT" * 600, "ACGA" * 560)]
+    for i, j in ((0, 1), (2, 3)):
+        assert ctx.align_pair(i, j) == o.traceback(enc[i], enc[j], o.matrix(1), 10, 1, 1)
 print("sanitize_run ok")
