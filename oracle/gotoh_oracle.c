@@ -436,3 +436,133 @@ void tsq_oracle_consensus(const char *const *rows, uint32_t nrows, uint32_t ncol
   }
   free(scores); free(rindex);
 }
+
+/* ---- progressive multiple alignment along a guide tree (the step after SURVEY.md 8f-1) ----
+ * What the external aligner does with the tree (tweakseq/Core/ClustalO.cpp:48-52 run) and what
+ * Project::readNewAlignment (tweakseq/Core/Project.cpp:908-1032) ingests: equal-length gapped rows.
+ * Build-defined spec (the reference holds no aligner): the n-1 merges are applied in order; merge t
+ * aligns the alignments of clusters left[t] (X, its columns along i) and right[t] (Y, along j) by the
+ * Gotoh recurrence of SURVEY 8c over COLUMNS, with integer sum-of-pairs scores
+ *     sub(i, j) = sum over rows x of X, y of Y with residues in columns i, j of S(x_i, y_j)
+ * (a residue facing a gap scores 0) and a gap of k columns costing |X| |Y| (go + k ge); end gaps are
+ * penalised.  For two single sequences this is exactly the pairwise alignment of tsq_oracle_traceback,
+ * tie rules included (diagonal, then gap in X, then gap in Y; open rather than extend).  The merged
+ * cluster lists X's rows, then Y's.  This restatement keeps explicit row lists and recounts every
+ * column from the rows; all arithmetic is int64.
+ * rows_out: n x (*ncols_out) bytes, row r = submitted sequence r, symbols or 0xff for a gap (malloc'd,
+ * caller frees); merge_scores (n-1 entries or NULL) receives H(Lx, Ly) of every merge.  Returns 0. */
+typedef struct {
+  uint32_t nmem, L;
+  uint32_t *mem;
+  uint8_t *rows;   /* nmem x L */
+} msa_cluster;
+
+static int64_t msa_sub(const uint32_t *cx, const uint32_t *cy, const int8_t *mat, int nsym) {
+  int64_t s = 0;
+  for (int a = 0; a < nsym; a++) {
+    if (!cx[a]) continue;
+    for (int b = 0; b < nsym; b++)
+      if (cy[b]) s += (int64_t)cx[a] * cy[b] * mat[a * nsym + b];
+  }
+  return s;
+}
+
+static uint32_t *msa_counts(const msa_cluster *c, int nsym) {
+  uint32_t *cnt = (uint32_t *)calloc((size_t)(c->L ? c->L : 1) * nsym, sizeof(uint32_t));
+  for (uint32_t r = 0; r < c->nmem; r++)
+    for (uint32_t k = 0; k < c->L; k++) {
+      uint8_t v = c->rows[(size_t)r * c->L + k];
+      if (v != 0xff) cnt[(size_t)k * nsym + v]++;
+    }
+  return cnt;
+}
+
+int tsq_oracle_msa(const uint8_t *seqs, const uint64_t *offs, const uint32_t *lens, uint32_t n, const int8_t *mat,
+                   int nsym, int go, int ge, const uint32_t *left, const uint32_t *right, uint8_t **rows_out,
+                   uint32_t *ncols_out, int64_t *merge_scores) {
+  *rows_out = NULL; *ncols_out = 0;
+  if (n == 0) return 0;
+  const int64_t NEG = -((int64_t)1 << 60);
+  msa_cluster *cl = (msa_cluster *)calloc(2 * (size_t)n - 1, sizeof(msa_cluster));
+  for (uint32_t r = 0; r < n; r++) {
+    cl[r].nmem = 1; cl[r].L = lens[r];
+    cl[r].mem = (uint32_t *)malloc(sizeof(uint32_t)); cl[r].mem[0] = r;
+    cl[r].rows = (uint8_t *)malloc(lens[r] ? lens[r] : 1);
+    memcpy(cl[r].rows, seqs + offs[r], lens[r]);
+  }
+  for (uint32_t t = 0; t + 1 < n; t++) {
+    msa_cluster *X = &cl[left[t]], *Y = &cl[right[t]], *Z = &cl[n + t];
+    const int m = (int)X->L, q = (int)Y->L;
+    uint32_t *cx = msa_counts(X, nsym), *cy = msa_counts(Y, nsym);
+    const int64_t w = (int64_t)X->nmem * Y->nmem, GE = w * ge, GO = w * go, GOE = GO + GE;
+    const size_t ld = (size_t)q + 1, cells = ((size_t)m + 1) * ld;
+    int64_t *H = (int64_t *)malloc(sizeof(int64_t) * 3 * cells), *E = H + cells, *F = E + cells;
+    int64_t *S = (int64_t *)malloc(sizeof(int64_t) * cells);   /* sub(i, j), kept for the walk back */
+    H[0] = 0; E[0] = NEG; F[0] = NEG;
+    for (int j = 1; j <= q; j++) { H[j] = E[j] = -GO - j * GE; F[j] = NEG; }
+    for (int i = 1; i <= m; i++) {
+      int64_t *h = H + (size_t)i * ld, *e = E + (size_t)i * ld, *f = F + (size_t)i * ld;
+      const int64_t *hu = h - ld, *fu = f - ld;
+      h[0] = f[0] = -GO - i * GE; e[0] = NEG;
+      for (int j = 1; j <= q; j++) {
+        const int64_t sub = msa_sub(cx + (size_t)(i - 1) * nsym, cy + (size_t)(j - 1) * nsym, mat, nsym);
+        S[(size_t)i * ld + j] = sub;
+        const int64_t e1 = e[j - 1] - GE, e2 = h[j - 1] - GOE;
+        const int64_t f1 = fu[j] - GE, f2 = hu[j] - GOE;
+        const int64_t dg = hu[j - 1] + sub;
+        e[j] = e2 >= e1 ? e2 : e1;
+        f[j] = f2 >= f1 ? f2 : f1;
+        int64_t best = dg;
+        if (e[j] > best) best = e[j];
+        if (f[j] > best) best = f[j];
+        h[j] = best;
+      }
+    }
+    if (merge_scores) merge_scores[t] = H[(size_t)m * ld + q];
+    /* walk back: per merged column (last first) the X column and Y column it takes, -1 = gap */
+    int *pi = (int *)malloc(sizeof(int) * 2 * ((size_t)m + q + 1)), *pj = pi + m + q + 1;
+    uint32_t k = 0;
+    int i = m, j = q, state = 0;
+    while (i > 0 || j > 0) {
+      if (i == 0) { pi[k] = -1; pj[k] = j - 1; j--; k++; continue; }
+      if (j == 0) { pi[k] = i - 1; pj[k] = -1; i--; k++; continue; }
+      const size_t at = (size_t)i * ld + j;
+      if (state == 0) {
+        if (H[at] == H[at - ld - 1] + S[at]) { pi[k] = i - 1; pj[k] = j - 1; i--; j--; k++; }
+        else state = (H[at] == E[at]) ? 1 : 2;
+      } else if (state == 1) {
+        pi[k] = -1; pj[k] = j - 1; k++;
+        if (E[at] == H[at - 1] - GOE) state = 0;
+        j--;
+      } else {
+        pi[k] = i - 1; pj[k] = -1; k++;
+        if (F[at] == H[at - ld] - GOE) state = 0;
+        i--;
+      }
+    }
+    Z->nmem = X->nmem + Y->nmem; Z->L = k;
+    Z->mem = (uint32_t *)malloc(sizeof(uint32_t) * Z->nmem);
+    memcpy(Z->mem, X->mem, sizeof(uint32_t) * X->nmem);
+    memcpy(Z->mem + X->nmem, Y->mem, sizeof(uint32_t) * Y->nmem);
+    Z->rows = (uint8_t *)malloc((size_t)Z->nmem * (k ? k : 1));
+    for (uint32_t c = 0; c < k; c++) {
+      const int xi = pi[k - 1 - c], yj = pj[k - 1 - c];
+      for (uint32_t r = 0; r < X->nmem; r++)
+        Z->rows[(size_t)r * k + c] = xi < 0 ? 0xff : X->rows[(size_t)r * X->L + xi];
+      for (uint32_t r = 0; r < Y->nmem; r++)
+        Z->rows[(size_t)(X->nmem + r) * k + c] = yj < 0 ? 0xff : Y->rows[(size_t)r * Y->L + yj];
+    }
+    free(pi); free(S); free(H); free(cx); free(cy);
+    free(X->rows); free(X->mem); X->rows = NULL; X->mem = NULL;
+    free(Y->rows); free(Y->mem); Y->rows = NULL; Y->mem = NULL;
+  }
+  msa_cluster *R = &cl[n == 1 ? 0 : 2 * (size_t)n - 2];
+  const uint32_t L = R->L;
+  uint8_t *out = (uint8_t *)malloc((size_t)n * (L ? L : 1));
+  for (uint32_t r = 0; r < R->nmem; r++) memcpy(out + (size_t)R->mem[r] * L, R->rows + (size_t)r * L, L);
+  free(R->rows); free(R->mem); free(cl);
+  *rows_out = out; *ncols_out = L;
+  return 0;
+}
+
+void tsq_oracle_free(void *p) { free(p); }

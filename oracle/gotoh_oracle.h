@@ -99,6 +99,18 @@ void tsq_oracle_consensus(const char *const *rows, uint32_t nrows, uint32_t ncol
  */
 void tsq_oracle_upgma(const double *packed, uint32_t n, uint32_t *left, uint32_t *right, double *height);
 
+/*
+ * Progressive multiple alignment along a guide tree (the step after SURVEY.md 8f-1; spec at the
+ * definition in gotoh_oracle.c).  seqs/offs/lens as for tsq_oracle_all_pairs (submitted order); left/right
+ * = the n-1 merges (leaves 0..n-1, node of merge t = n+t, e.g. from tsq_oracle_upgma).  *rows_out =
+ * malloc'd n x *ncols_out bytes, row r = sequence r, symbols or 0xff for a gap: release it with
+ * tsq_oracle_free.  merge_scores: n-1 profile-alignment scores or NULL.  Returns 0.
+ */
+int tsq_oracle_msa(const uint8_t *seqs, const uint64_t *offs, const uint32_t *lens, uint32_t n, const int8_t *mat,
+                   int nsym, int go, int ge, const uint32_t *left, const uint32_t *right, uint8_t **rows_out,
+                   uint32_t *ncols_out, int64_t *merge_scores);
+void tsq_oracle_free(void *p);
+
 #ifdef __cplusplus
 }
 #endif

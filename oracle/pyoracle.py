@@ -58,6 +58,11 @@ def lib():
         L.tsq_oracle_traceback.argtypes = [u8p, C.c_int, u8p, C.c_int, i8p, C.c_int, C.c_int, C.c_int, u8p, u8p, i32p]
         L.tsq_oracle_upgma.restype = None
         L.tsq_oracle_upgma.argtypes = [C.POINTER(C.c_double), C.c_uint32, u32p, u32p, C.POINTER(C.c_double)]
+        L.tsq_oracle_msa.restype = C.c_int
+        L.tsq_oracle_msa.argtypes = [u8p, u64p, u32p, C.c_uint32, i8p, C.c_int, C.c_int, C.c_int, u32p, u32p,
+                                     C.POINTER(u8p), u32p, C.POINTER(C.c_int64)]
+        L.tsq_oracle_free.restype = None
+        L.tsq_oracle_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -239,3 +244,30 @@ def consensus(rows, plurality: float | None = None) -> str:
     out = C.create_string_buffer(ncols + 1)
     lib().tsq_oracle_consensus(arr, len(raw), ncols, len(raw) / 2.0 if plurality is None else plurality, out)
     return out.raw[:ncols].decode("latin-1")
+
+
+def msa(encoded, mat, go: int, ge: int, left, right, alphabet: int = PROTEIN):
+    """Progressive alignment along the merges (left, right): (rows as gapped strings in submitted
+    order, int64 profile-alignment score of every merge)."""
+    n = len(encoded)
+    flat, offs, lens = _pack(encoded) if n else (np.zeros(1, np.uint8), np.zeros(1, np.uint64), np.zeros(1, np.uint32))
+    m8 = np.ascontiguousarray(mat, dtype=np.int8)
+    left = np.ascontiguousarray(left, dtype=np.uint32)
+    right = np.ascontiguousarray(right, dtype=np.uint32)
+    lp = left if len(left) else np.zeros(1, np.uint32)
+    rp = right if len(right) else np.zeros(1, np.uint32)
+    sc = np.zeros(max(n - 1, 1), dtype=np.int64)
+    rows, ncols = C.POINTER(C.c_uint8)(), C.c_uint32()
+    rc = lib().tsq_oracle_msa(_p(flat, C.c_uint8), _p(offs, C.c_uint64), _p(lens, C.c_uint32), n, _p(m8, C.c_int8),
+                              m8.shape[0], go, ge, _p(lp, C.c_uint32), _p(rp, C.c_uint32), C.byref(rows),
+                              C.byref(ncols), _p(sc, C.c_int64))
+    assert rc == 0
+    letters = "ACGTN" if alphabet == NUCLEOTIDE else "ARNDCQEGHILKMFPSTWYVBZX"
+    out = []
+    if n:
+        arr = np.ctypeslib.as_array(rows, shape=(n * max(ncols.value, 1),))
+        for r in range(n):
+            v = arr[r * ncols.value:(r + 1) * ncols.value]
+            out.append("".join("-" if x == 0xff else letters[x] for x in v))
+        lib().tsq_oracle_free(rows)
+    return out, sc[:max(n - 1, 0)].copy()

@@ -1,0 +1,110 @@
+// msa_emul.cpp -- TEST INFRASTRUCTURE: runs the progressive-alignment plan of libtsqb200.so
+// (tweakseq_b200/csrc/msa_host.h) and the phase functions of its kernels (msa.cuh) on the CPU, one
+// emulated thread at a time, so that the product's own planning and per-thread code are compared with
+// the oracle (tsq_oracle_msa) in the CPU test tier.  A phase has no barrier inside, so running its
+// threads one after the other -- here in DESCENDING thread order, to expose any accidental dependence
+// on thread order -- is a legal schedule.  "Device" memory is malloc'd and filled with garbage so that
+// a read of something no phase wrote shows up as a wrong answer.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../tweakseq_b200/csrc/msa_host.h"
+
+namespace {
+
+class EmulDevice : public tsq::MsaDevice {
+ public:
+  std::vector<void*> blocks;
+  void* scr = nullptr;
+  size_t scr_cap = 0;
+  int order = 0;   // 0: threads descending, 1: ascending
+  uint32_t force_threads = 0;
+  ~EmulDevice() override {
+    for (void* p : blocks) free(p);
+    free(scr);
+  }
+  void* alloc(size_t bytes) override {
+    void* p = aligned_alloc(256, (bytes + 255) & ~(size_t)255);
+    if (p) { memset(p, 0xA7, bytes); blocks.push_back(p); }
+    return p;
+  }
+  void* scratch(size_t bytes) override {
+    if (bytes > scr_cap) {
+      free(scr);
+      scr = aligned_alloc(256, (bytes + 255) & ~(size_t)255);
+      scr_cap = scr ? bytes : 0;
+    }
+    if (scr) memset(scr, 0x5C, bytes);
+    return scr;
+  }
+  bool h2d(void* d, const void* s, size_t b) override { memcpy(d, s, b); return true; }
+  bool d2h(void* d, const void* s, size_t b) override { memcpy(d, s, b); return true; }
+  bool fill(void* d, int v, size_t b) override { memset(d, v, b); return true; }
+  template <class F>
+  void each_thread(int nt, F f) {
+    if (order) for (int t = 0; t < nt; t++) f(t);
+    else for (int t = nt - 1; t >= 0; t--) f(t);
+  }
+  bool launch_leaves(const tsq::MsaLeaf* l, uint32_t n, uint32_t nsym) override {
+    for (uint32_t r = 0; r < n; r++) each_thread(128, [&](int t) { tsq::msa_leaf_phase(l[r], nsym, t, 128); });
+    return true;
+  }
+  bool launch_merges(const tsq::MsaTask* tasks, uint32_t count, uint32_t threads, const tsq::MsaConst& k) override {
+    const int nt = (int)(force_threads ? force_threads : threads);
+    if (nt < 1 || nt > 1024) return false;
+    for (uint32_t b = 0; b < count; b++) {
+      const tsq::MsaTask t = tasks[b];
+      each_thread(nt, [&](int tid) { tsq::msa_py_phase(t, k, tid, nt); });
+      const int last = (int)(t.Lx + t.Ly);
+      for (int d = 0; d <= last; ++d) each_thread(nt, [&](int tid) { tsq::msa_diag_phase(t, k, d, tid, nt); });
+      tsq::msa_walk_phase(t);
+      each_thread(nt, [&](int tid) { tsq::msa_build_phase(t, k, tid, nt); });
+    }
+    return true;
+  }
+  bool launch_rows(const tsq::MsaRows& p) override {
+    for (uint32_t r = 0; r < p.n; r++) each_thread(256, [&](int t) { tsq::msa_rows_phase(p, r, t, 256); });
+    return true;
+  }
+};
+
+}  // namespace
+
+extern "C" int msa_emul(const uint8_t* seqs, const uint64_t* offs, const uint32_t* lens, uint32_t n, const int8_t* mat,
+                        int nsym, int go, int ge, const uint32_t* left, const uint32_t* right, const char* letters,
+                        uint8_t* rows_out, uint64_t rows_cap, uint32_t* ncols, long long* merge_scores,
+                        uint32_t* tree_order, uint64_t scratch_budget, uint32_t force_threads, int ascending,
+                        uint32_t* launches, uint32_t* levels) {
+  EmulDevice dev;
+  dev.order = ascending;
+  dev.force_threads = force_threads;
+  tsq::MsaJob job;
+  job.n = n;
+  job.d_sym = seqs;
+  job.sym_off.assign(offs, offs + n);
+  job.len.assign(lens, lens + n);
+  if (n > 1) {
+    job.left.assign(left, left + n - 1);
+    job.right.assign(right, right + n - 1);
+  }
+  job.smat.resize((size_t)nsym * nsym);
+  for (int i = 0; i < nsym * nsym; i++) job.smat[i] = mat[i];
+  job.nsym = (uint32_t)nsym;
+  job.go = go;
+  job.ge = ge;
+  job.letters = letters;
+  if (scratch_budget) job.scratch_budget = scratch_budget;
+  tsq::MsaOut out;
+  const int rc = tsq::msa_progressive(dev, job, out);
+  if (rc != tsq::MSA_OK) return rc;
+  if (out.rows.size() > rows_cap) return -1;
+  memcpy(rows_out, out.rows.data(), out.rows.size());
+  *ncols = out.ncols;
+  for (size_t t = 0; t < out.merge_score.size(); t++) merge_scores[t] = out.merge_score[t];
+  for (size_t i = 0; i < out.tree_order.size(); i++) tree_order[i] = out.tree_order[i];
+  if (launches) *launches = out.launches;
+  if (levels) *levels = out.levels;
+  return 0;
+}

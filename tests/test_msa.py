@@ -1,0 +1,219 @@
+"""Progressive multiple alignment along the guide tree (tweakseq_b200/csrc/msa.cuh, msa_host.h).
+
+CPU tier: the oracle (tsq_oracle_msa) against an independent pure-Python statement of the spec and
+against tsq_oracle_traceback for n = 2; then the product's own planning code and kernel phase functions,
+run thread by thread on the CPU by tests/msa_emul.cpp, against the oracle.
+GPU tier: tsq_msa / tsq_run_fasta through the C ABI against the oracle, byte for byte."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as o
+import np_msa
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PROT = "ARNDCQEGHILKMFPSTWYVBZX"
+NUC = "ACGTN"
+
+
+def smat_dict(alphabet):
+    letters = NUC if alphabet == o.NUCLEOTIDE else PROT
+    m = o.matrix(alphabet)
+    return {a: {b: int(m[i, j]) for j, b in enumerate(letters)} for i, a in enumerate(letters)}
+
+
+def family(rng, n, length, alphabet=o.PROTEIN, mut=0.25, indel=0.08):
+    letters = "ACGT" if alphabet == o.NUCLEOTIDE else PROT[:20]
+    root = rng.choice(list(letters), size=length)
+    out = []
+    for _ in range(n):
+        s = []
+        for ch in root:
+            u = rng.random()
+            if u < indel / 2:
+                continue
+            if u < indel:
+                s.append(rng.choice(list(letters)))
+            s.append(rng.choice(list(letters)) if rng.random() < mut else ch)
+        out.append("".join(s))
+    return out
+
+
+def random_tree(rng, n):
+    """A random binary merge order (not necessarily UPGMA): exercises arbitrary level structures."""
+    alive = list(range(n))
+    left, right = [], []
+    for t in range(n - 1):
+        i, j = sorted(rng.choice(len(alive), size=2, replace=False))
+        a, b = alive[i], alive[j]
+        if rng.random() < 0.5:
+            a, b = b, a
+        left.append(a); right.append(b)
+        alive = [x for k, x in enumerate(alive) if k not in (i, j)] + [n + t]
+    return np.array(left, np.uint32), np.array(right, np.uint32)
+
+
+def caterpillar(n):
+    left = [0] + [n + t - 1 for t in range(1, n - 1)]
+    right = list(range(1, n))
+    return np.array(left, np.uint32), np.array(right, np.uint32)
+
+
+def upgma_tree(seqs, alphabet, go, ge):
+    enc = [o.encode(s, alphabet) for s in seqs]
+    mat = o.matrix(alphabet)
+    sc, _ = o.all_pairs(enc, mat, go, ge)
+    selfs = np.array([o.self_score(e, mat) for e in enc], dtype=np.int32)
+    left, right, _ = o.upgma(o.distances(sc, selfs), len(seqs))
+    return left, right
+
+
+def check_rows(rows, seqs, alphabet):
+    """Properties every multiple alignment must have, whatever the scores."""
+    canon = lambda s: "".join((NUC if alphabet == o.NUCLEOTIDE else PROT)[v] for v in o.encode(s, alphabet))
+    assert len(rows) == len(seqs)
+    assert len({len(r) for r in rows}) <= 1
+    for r, s in zip(rows, seqs):
+        assert r.replace("-", "") == canon(s)
+    if rows and len(seqs) > 0:
+        for c in range(len(rows[0])):
+            assert any(r[c] != "-" for r in rows), f"column {c} is all gaps"
+
+
+# ---------------------------------------------------------------- oracle -------------------------
+
+def test_oracle_two_sequences_is_the_pairwise_traceback():
+    rng = np.random.default_rng(5)
+    mat = o.matrix(o.PROTEIN)
+    for _ in range(40):
+        a, b = family(rng, 2, int(rng.integers(0, 40)), mut=0.4, indel=0.2)
+        ea, eb = o.encode(a), o.encode(b)
+        go, ge = int(rng.integers(0, 14)), int(rng.integers(0, 4))
+        rows, sc = o.msa([ea, eb], mat, go, ge, [0], [1])
+        ra, rb, s = o.traceback(ea, eb, mat, go, ge)
+        assert (rows[0], rows[1], int(sc[0])) == (ra, rb, s)
+        assert s == o.gotoh(ea, eb, mat, go, ge)
+
+
+@pytest.mark.parametrize("alphabet", [o.PROTEIN, o.NUCLEOTIDE])
+def test_oracle_equals_independent_python_statement(alphabet):
+    rng = np.random.default_rng(11 + alphabet)
+    S = smat_dict(alphabet)
+    mat = o.matrix(alphabet)
+    letters = NUC if alphabet == o.NUCLEOTIDE else PROT
+    for trial in range(30):
+        n = int(rng.integers(1, 7))
+        seqs = family(rng, n, int(rng.integers(0, 14)), alphabet, mut=0.35, indel=0.25)
+        if trial % 5 == 0 and n > 1:
+            seqs[int(rng.integers(0, n))] = ""
+        go, ge = int(rng.integers(0, 13)), int(rng.integers(0, 3))
+        left, right = random_tree(rng, n) if n > 1 else (np.zeros(0, np.uint32),) * 2
+        enc = [o.encode(s, alphabet) for s in seqs]
+        rows, sc = o.msa(enc, mat, go, ge, left, right, alphabet)
+        canon = ["".join(letters[v] for v in e) for e in enc]
+        prow, psc = np_msa.progressive(canon, left.tolist(), right.tolist(), S, go, ge)
+        assert rows == prow
+        assert sc.tolist() == psc
+        check_rows(rows, seqs, alphabet)
+
+
+def test_oracle_identical_sequences_align_without_gaps():
+    s = "MKTAYIAKQRQISFVKSHFSRQLEERLGLIEVQ"
+    enc = [o.encode(s)] * 5
+    left, right = caterpillar(5)
+    rows, sc = o.msa(enc, o.matrix(0), 11, 1, left, right)
+    assert rows == [s] * 5
+    selfs = o.self_score(enc[0], o.matrix(0))
+    assert sc.tolist() == [selfs * k for k in (1, 2, 3, 4)]   # |X| |Y| pair sums, no gap
+
+
+# ---------------------------------------------------------------- emulator -----------------------
+
+@pytest.fixture(scope="module")
+def emul():
+    so = os.path.join(HERE, "_msa_emul.so")
+    src = [os.path.join(HERE, "msa_emul.cpp"), os.path.join(HERE, "..", "tweakseq_b200", "csrc", "msa.cuh"),
+           os.path.join(HERE, "..", "tweakseq_b200", "csrc", "msa_host.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(f) for f in src):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-shared", "-fPIC", "-o", so, src[0]])
+    L = C.CDLL(so)
+    u8p, u32p, u64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint32, C.c_uint64))
+    L.msa_emul.argtypes = [u8p, u64p, u32p, C.c_uint32, C.POINTER(C.c_int8), C.c_int, C.c_int, C.c_int, u32p, u32p,
+                           C.c_char_p, u8p, C.c_uint64, u32p, C.POINTER(C.c_longlong), u32p, C.c_uint64, C.c_uint32,
+                           C.c_int, u32p, u32p]
+
+    def run(enc, mat, go, ge, left, right, alphabet=o.PROTEIN, budget=0, threads=0, ascending=0):
+        n = len(enc)
+        flat, offs, lens = o._pack(enc)
+        m8 = np.ascontiguousarray(mat, dtype=np.int8)
+        left = np.ascontiguousarray(left, dtype=np.uint32) if n > 1 else np.zeros(1, np.uint32)
+        right = np.ascontiguousarray(right, dtype=np.uint32) if n > 1 else np.zeros(1, np.uint32)
+        cap = n * (int(lens.sum()) + 1)
+        rows = np.zeros(cap, np.uint8)
+        sc = np.zeros(max(n, 1), np.int64)
+        order = np.zeros(max(n, 1), np.uint32)
+        ncols, launches, levels = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        letters = (NUC if alphabet == o.NUCLEOTIDE else PROT).encode()
+        rc = L.msa_emul(p(flat, C.c_uint8), p(offs, C.c_uint64), p(lens, C.c_uint32), n, p(m8, C.c_int8), m8.shape[0],
+                        go, ge, p(left, C.c_uint32), p(right, C.c_uint32), letters, p(rows, C.c_uint8), cap,
+                        C.byref(ncols), p(sc, C.c_longlong), p(order, C.c_uint32), budget, threads, ascending,
+                        C.byref(launches), C.byref(levels))
+        assert rc == 0, rc
+        k = ncols.value
+        out = [rows[r * k:(r + 1) * k].tobytes().decode("ascii") for r in range(n)]
+        return out, sc[:max(n - 1, 0)].copy(), order[:n].copy(), launches.value, levels.value
+    return run
+
+
+@pytest.mark.parametrize("alphabet", [o.PROTEIN, o.NUCLEOTIDE])
+def test_kernel_phases_on_cpu_equal_oracle_random_trees(emul, alphabet):
+    rng = np.random.default_rng(101 + alphabet)
+    mat = o.matrix(alphabet)
+    for trial in range(40):
+        n = int(rng.integers(1, 14))
+        seqs = family(rng, n, int(rng.integers(0, 70)), alphabet, mut=0.3, indel=0.15)
+        if trial % 4 == 0 and n > 2:
+            seqs[int(rng.integers(0, n))] = ""
+        go, ge = int(rng.integers(0, 14)), int(rng.integers(0, 4))
+        left, right = random_tree(rng, n) if n > 1 else (np.zeros(0, np.uint32),) * 2
+        enc = [o.encode(s, alphabet) for s in seqs]
+        want, wsc = o.msa(enc, mat, go, ge, left, right, alphabet)
+        threads = [0, 1, 32, 96, 1024][trial % 5]
+        budget = [0, 1, 1 << 16][trial % 3]   # 1 byte: one merge per launch
+        got, gsc, order, launches, levels = emul(enc, mat, go, ge, left, right, alphabet, budget, threads, trial & 1)
+        assert got == want
+        assert gsc.tolist() == wsc.tolist()
+        assert sorted(order.tolist()) == list(range(n))
+        assert launches >= levels + 1
+        check_rows(got, seqs, alphabet)
+
+
+def test_kernel_phases_on_cpu_upgma_family_and_caterpillar(emul):
+    rng = np.random.default_rng(7)
+    mat = o.matrix(o.PROTEIN)
+    seqs = family(rng, 24, 120, mut=0.2, indel=0.06)
+    enc = [o.encode(s) for s in seqs]
+    for left, right in (upgma_tree(seqs, o.PROTEIN, 11, 1), caterpillar(len(seqs))):
+        want, wsc = o.msa(enc, mat, 11, 1, left, right)
+        got, gsc, order, launches, levels = emul(enc, mat, 11, 1, left, right)
+        assert got == want and gsc.tolist() == wsc.tolist()
+        check_rows(got, seqs, o.PROTEIN)
+    # leaves left to right of the caterpillar ((((0,1),2),3)...) are 0, 1, 2, ...
+    assert order.tolist() == list(range(len(seqs)))
+    assert levels == len(seqs) - 1
+
+
+def test_kernel_phases_on_cpu_custom_matrix_and_wide_counts(emul):
+    rng = np.random.default_rng(9)
+    m = rng.integers(-8, 12, size=(23, 23))
+    m = ((m + m.T) // 2).astype(np.int8)
+    seqs = family(rng, 40, 30, mut=0.5, indel=0.2)
+    enc = [o.encode(s) for s in seqs]
+    left, right = random_tree(rng, len(seqs))
+    want, wsc = o.msa(enc, m, 3, 2, left, right)
+    got, gsc, *_ = emul(enc, m, 3, 2, left, right)
+    assert got == want and gsc.tolist() == wsc.tolist()

@@ -1,0 +1,241 @@
+// msa.cuh -- progressive multiple alignment along the guide tree: the step after SURVEY.md 8f-1 that
+// turns the distance matrix + UPGMA tree into the equal-length gapped rows Project::readNewAlignment
+// (tweakseq/Core/Project.cpp:908-1032) ingests, i.e. what the external aligner launched at
+// tweakseq/UI/SeqEditMainWin.cpp:1654-1660 hands back.  Not the all-vs-all hot path: n-1 dependent
+// profile alignments, bound by the per-diagonal barrier like traceback.cuh.
+//
+// Spec (build-defined; restated independently, with explicit row lists, by tsq_oracle_msa): merge t
+// aligns the column profiles of clusters X = left[t] (columns along i) and Y = right[t] (along j) with
+// the Gotoh recurrence of SURVEY 8c over COLUMNS, int64 sum-of-pairs scores
+//     sub(i, j) = sum_a sum_b cntX[i][a] * cntY[j][b] * S(a, b)          (a residue facing a gap: 0)
+// and a gap of k columns costing |X| |Y| (go + k ge), end gaps penalised.  Tie rules of traceback.cuh:
+// H prefers the diagonal, then E (gap in X), then F (gap in Y); a gap run is opened rather than
+// extended.  Two single sequences therefore align exactly as tsq_align_pair aligns them.
+//
+// One CTA per merge, all merges of one tree level in one launch.  A merge is four phases separated by
+// CTA barriers; every phase is a function of (task, thread id, thread count) with no barrier inside, so
+// tests/msa_emul.cpp can run the very same phase code on the CPU, thread by thread, against the oracle:
+//   1. PY[a][j] = sum_b cntY[j][b] S(a, b)                  -> 23 multiply-adds per cell instead of 23^2
+//   2. anti-diagonal sweep, one barrier per diagonal: H (3 rolling diagonals), E, F (2 each) in an
+//      L2-resident scratch indexed by i; one direction byte per cell, diagonal-major (traceback.cuh)
+//   3. thread 0 walks the path back from (Lx, Ly): per merged column its X column and Y column or -1
+//   4. all threads: column maps old -> merged for X and Y, merged counts = cntX[px] + cntY[py]
+// Profiles are letter-major (c[a * cap + col]) so that a diagonal's threads read consecutive words.
+// No rows are materialised per merge: a leaf's residues reach their final columns by composing the
+// column maps up the tree once, at the end (msa_rows_phase).
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define TSQ_HD __host__ __device__ __forceinline__
+#else
+#define TSQ_HD inline
+#endif
+
+namespace tsq {
+
+struct MsaConst {
+  const int32_t* smat;   // nsym x nsym plain substitution scores
+  uint32_t nsym;
+  int32_t go, ge;
+};
+
+struct MsaResult {       // written by the walk-back of one merge
+  long long score;       // H(Lx, Ly)
+  uint32_t len;          // columns of the merged alignment
+  uint32_t pad;
+};
+
+struct MsaTask {         // one merge: X = left child, Y = right child
+  const uint32_t* cx;    // residue counts per column, letter-major: cx[a * capx + col]
+  const uint32_t* cy;
+  uint32_t* cn;          // counts of the merged alignment, capn >= Lx + Ly columns
+  uint32_t capx, capy, capn;
+  uint32_t Lx, Ly;       // columns of X and Y
+  uint32_t nx, ny;       // sequences in X and Y
+  uint32_t* mapx;        // Lx entries: X column -> merged column
+  uint32_t* mapy;        // Ly entries
+  long long* diag;       // scratch: 7 * (Lx + 1)
+  int32_t* py;           // scratch: nsym * Ly, PY[a * Ly + j]
+  uint8_t* dir;          // scratch: (Lx + Ly + 1) * (min(Lx, Ly) + 1) direction bytes, diagonal-major
+  int32_t* path;         // scratch: 2 * (Lx + Ly): (X column, Y column) per merged column, last column first
+  MsaResult* res;
+};
+
+struct MsaLeaf {         // one input sequence
+  const uint8_t* sym;    // encoded residues
+  uint32_t len;
+  uint32_t cap;          // column capacity of c (>= len)
+  uint32_t* c;           // its profile: c[a * cap + col] = (sym[col] == a)
+};
+
+struct MsaRows {         // final rows: every residue follows the column maps up to the root
+  const MsaLeaf* leaves;             // n
+  const uint32_t* parent;            // 2n-1 node ids, 0xffffffff = root
+  const uint32_t* const* nodemap;    // per node: its column map inside its parent's merge
+  uint8_t* out;                      // n x ncols characters, pre-filled with '-'
+  uint32_t ncols;
+  uint32_t n;
+  char letters[24];
+};
+
+constexpr long long kMsaNeg = -(1LL << 60);
+
+TSQ_HD void msa_leaf_phase(const MsaLeaf& l, uint32_t nsym, int tid, int nt) {
+  for (uint32_t col = (uint32_t)tid; col < l.len; col += (uint32_t)nt) {
+    const uint32_t s = l.sym[col];
+    for (uint32_t a = 0; a < nsym; ++a) l.c[(size_t)a * l.cap + col] = (a == s) ? 1u : 0u;
+  }
+}
+
+// phase 1
+TSQ_HD void msa_py_phase(const MsaTask& t, const MsaConst& k, int tid, int nt) {
+  const uint32_t total = k.nsym * t.Ly;
+  for (uint32_t idx = (uint32_t)tid; idx < total; idx += (uint32_t)nt) {
+    const uint32_t a = idx / t.Ly, j = idx - a * t.Ly;
+    int32_t s = 0;
+    for (uint32_t b = 0; b < k.nsym; ++b) {
+      const uint32_t c = t.cy[(size_t)b * t.capy + j];
+      if (c) s += (int32_t)c * k.smat[a * k.nsym + b];
+    }
+    t.py[idx] = s;
+  }
+}
+
+// phase 2, diagonal d in [0, Lx + Ly]
+TSQ_HD void msa_diag_phase(const MsaTask& t, const MsaConst& k, int d, int tid, int nt) {
+  const int m = (int)t.Lx, n = (int)t.Ly;
+  const size_t stride = (size_t)m + 1;
+  const long long w = (long long)t.nx * (long long)t.ny;
+  const long long GO = w * k.go, GE = w * k.ge, GOE = GO + GE;
+  long long* const Hc = t.diag + (size_t)(d % 3) * stride;
+  const long long* const Hp1 = t.diag + (size_t)((d + 2) % 3) * stride;
+  const long long* const Hp2 = t.diag + (size_t)((d + 1) % 3) * stride;
+  long long* const Ec = t.diag + (size_t)(3 + (d & 1)) * stride;
+  const long long* const Ep1 = t.diag + (size_t)(3 + ((d + 1) & 1)) * stride;
+  long long* const Fc = t.diag + (size_t)(5 + (d & 1)) * stride;
+  const long long* const Fp1 = t.diag + (size_t)(5 + ((d + 1) & 1)) * stride;
+  const int ilo = d > n ? d - n : 0;
+  const int ihi = d < m ? d : m;
+  const size_t ld = (size_t)(m < n ? m : n) + 1;
+  uint8_t* const drow = t.dir + (size_t)d * ld - ilo;
+  for (int i = ilo + tid; i <= ihi; i += nt) {
+    const int j = d - i;
+    long long H, E, F;
+    uint32_t code;
+    if (i == 0 && j == 0) {
+      H = 0; E = kMsaNeg; F = kMsaNeg; code = 0;
+    } else if (i == 0) {
+      H = E = -GO - (long long)j * GE; F = kMsaNeg; code = 1u | (j == 1 ? 4u : 0u);
+    } else if (j == 0) {
+      H = F = -GO - (long long)i * GE; E = kMsaNeg; code = 2u | (i == 1 ? 8u : 0u);
+    } else {
+      long long sub = 0;
+      for (uint32_t a = 0; a < k.nsym; ++a) {
+        const uint32_t c = t.cx[(size_t)a * t.capx + (uint32_t)(i - 1)];
+        if (c) sub += (long long)c * (long long)t.py[(size_t)a * t.Ly + (uint32_t)(j - 1)];
+      }
+      const long long hl = Hp1[i], hu = Hp1[i - 1], hd = Hp2[i - 1];
+      const long long e_ext = Ep1[i] - GE, e_open = hl - GOE;
+      const long long f_ext = Fp1[i - 1] - GE, f_open = hu - GOE;
+      const long long dg = hd + sub;
+      const bool eo = e_open >= e_ext, fo = f_open >= f_ext;
+      E = eo ? e_open : e_ext;
+      F = fo ? f_open : f_ext;
+      H = dg;
+      if (E > H) H = E;
+      if (F > H) H = F;
+      code = (H == dg ? 0u : (H == E ? 1u : 2u)) | (eo ? 4u : 0u) | (fo ? 8u : 0u);
+    }
+    Hc[i] = H; Ec[i] = E; Fc[i] = F;
+    drow[i] = (uint8_t)code;
+  }
+}
+
+// phase 3, one thread
+TSQ_HD void msa_walk_phase(const MsaTask& t) {
+  const int m = (int)t.Lx, n = (int)t.Ly;
+  const size_t ld = (size_t)(m < n ? m : n) + 1;
+  int i = m, j = n, state = 0;
+  uint32_t k = 0;
+  while (i > 0 || j > 0) {
+    if (i == 0) { t.path[2 * k] = -1; t.path[2 * k + 1] = j - 1; --j; ++k; continue; }
+    if (j == 0) { t.path[2 * k] = i - 1; t.path[2 * k + 1] = -1; --i; ++k; continue; }
+    const int d = i + j;
+    const uint32_t code = t.dir[(size_t)d * ld + (size_t)(i - (d > n ? d - n : 0))];
+    if (state == 0) {
+      const uint32_t src = code & 3u;
+      if (src == 0) { t.path[2 * k] = i - 1; t.path[2 * k + 1] = j - 1; --i; --j; ++k; }
+      else state = (int)src;
+    } else if (state == 1) {            // gap in X: the merged column takes Y's column only
+      t.path[2 * k] = -1; t.path[2 * k + 1] = j - 1; ++k;
+      if (code & 4u) state = 0;
+      --j;
+    } else {                            // gap in Y
+      t.path[2 * k] = i - 1; t.path[2 * k + 1] = -1; ++k;
+      if (code & 8u) state = 0;
+      --i;
+    }
+  }
+  t.res->len = k;
+  t.res->pad = 0;
+  t.res->score = t.diag[(size_t)((m + n) % 3) * ((size_t)m + 1) + (size_t)m];   // H of the last diagonal, i = Lx
+}
+
+// phase 4
+TSQ_HD void msa_build_phase(const MsaTask& t, const MsaConst& k, int tid, int nt) {
+  const uint32_t len = t.res->len;
+  for (uint32_t c = (uint32_t)tid; c < len; c += (uint32_t)nt) {
+    const uint32_t s = len - 1 - c;
+    const int32_t xi = t.path[2 * s], yj = t.path[2 * s + 1];
+    if (xi >= 0) t.mapx[xi] = c;
+    if (yj >= 0) t.mapy[yj] = c;
+    for (uint32_t a = 0; a < k.nsym; ++a) {
+      const uint32_t vx = xi >= 0 ? t.cx[(size_t)a * t.capx + (uint32_t)xi] : 0u;
+      const uint32_t vy = yj >= 0 ? t.cy[(size_t)a * t.capy + (uint32_t)yj] : 0u;
+      t.cn[(size_t)a * t.capn + c] = vx + vy;
+    }
+  }
+}
+
+// final rows: leaf r, its residues tid, tid + nt, ...
+TSQ_HD void msa_rows_phase(const MsaRows& p, uint32_t r, int tid, int nt) {
+  const MsaLeaf& l = p.leaves[r];
+  for (uint32_t q = (uint32_t)tid; q < l.len; q += (uint32_t)nt) {
+    uint32_t col = q, node = r;
+    for (;;) {
+      const uint32_t up = p.parent[node];
+      if (up == 0xffffffffu) break;
+      col = p.nodemap[node][col];
+      node = up;
+    }
+    p.out[(size_t)r * p.ncols + col] = (uint8_t)p.letters[l.sym[q]];
+  }
+}
+
+#ifdef TSQ_DEVICE_IMPL
+__global__ void __launch_bounds__(128) msa_leaf_kernel(const MsaLeaf* leaves, uint32_t n, uint32_t nsym) {
+  for (uint32_t r = blockIdx.x; r < n; r += gridDim.x) msa_leaf_phase(leaves[r], nsym, (int)threadIdx.x, (int)blockDim.x);
+}
+
+__global__ void __launch_bounds__(1024) msa_merge_kernel(const MsaTask* tasks, const MsaConst k) {
+  const MsaTask t = tasks[blockIdx.x];
+  const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
+  msa_py_phase(t, k, tid, nt);
+  __syncthreads();
+  const int last = (int)(t.Lx + t.Ly);
+  for (int d = 0; d <= last; ++d) {
+    msa_diag_phase(t, k, d, tid, nt);
+    __syncthreads();   // diagonal d complete and visible to the whole CTA before d + 1 starts
+  }
+  if (tid == 0) msa_walk_phase(t);
+  __syncthreads();
+  msa_build_phase(t, k, tid, nt);
+}
+
+__global__ void __launch_bounds__(256) msa_rows_kernel(const __grid_constant__ MsaRows p) {
+  for (uint32_t r = blockIdx.x; r < p.n; r += gridDim.x) msa_rows_phase(p, r, (int)threadIdx.x, (int)blockDim.x);
+}
+#endif  // TSQ_DEVICE_IMPL
+
+}  // namespace tsq
