@@ -60,6 +60,7 @@ static void fill(tsq_params& p, const B200Gotoh& t) {
   p.gap_extend = t.gapExtend;
   p.device = t.device;
   if (t.identityDistance) p.flags |= TSQ_FLAG_IDENTITY;
+  if (t.alignInProcess) p.flags |= TSQ_FLAG_MSA_OUT;
 }
 
 int B200Gotoh::run(const std::string& fin, const std::string& fout, const LogSink& log, CancelFlag* cancel) {
@@ -136,6 +137,33 @@ int B200Gotoh::guideTree(const std::vector<std::string>& residues, const std::ve
     rc = tsq_write_newick(c, labels.size() == residues.size() ? lab.data() : nullptr, newickPath.c_str());
   }
   if (rc != TSQ_OK && error) *error = tsq_last_error(c);
+  tsq_destroy(c);
+  return rc;
+}
+
+int B200Gotoh::multipleAlignment(const std::vector<std::string>& residues, std::vector<std::string>& rows,
+                                 std::vector<unsigned>& treeOrder, std::string* error) {
+  tsq_params p;
+  fill(p, *this);
+  tsq_ctx* c = nullptr;
+  int rc = tsq_create(&c, &p);
+  if (rc != TSQ_OK) {
+    if (error) *error = tsq_status_string(rc);
+    return rc;
+  }
+  rc = load(c, residues);
+  if (rc == TSQ_OK) rc = tsq_run(c, nullptr, nullptr, nullptr);
+  const char* flat = nullptr;
+  const uint32_t* order = nullptr;
+  uint32_t n = 0, cols = 0;
+  if (rc == TSQ_OK) rc = tsq_msa(c, &flat, &n, &cols, &order);
+  if (rc == TSQ_OK) {
+    rows.clear();
+    for (uint32_t r = 0; r < n; r++) rows.emplace_back(flat + (size_t)r * cols, cols);
+    treeOrder.assign(order, order + n);
+  } else if (error) {
+    *error = tsq_last_error(c);
+  }
   tsq_destroy(c);
   return rc;
 }

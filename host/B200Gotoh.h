@@ -30,6 +30,11 @@ class B200Gotoh : public AlignmentTool {
   // Guide tree of the same job: Newick text for clustalo --guidetree-in.
   int guideTree(const std::vector<std::string>& residues, const std::vector<std::string>& labels,
                 const std::string& newickPath, std::string* error = nullptr);
+  // Distances, guide tree and the progressive alignment along it, in memory: equal-length gapped rows in
+  // submitted order (what Project::readNewAlignment, Project.cpp:908-1032, takes from the aligner's
+  // output file) and the tree order of the rows.
+  int multipleAlignment(const std::vector<std::string>& residues, std::vector<std::string>& rows,
+                        std::vector<unsigned>& treeOrder, std::string* error = nullptr);
   // One optimal global alignment of two sequences with its path: two gapped rows.
   int pairwiseAlignment(const std::string& a, const std::string& b, std::string& rowA, std::string& rowB, int& score,
                         std::string* error = nullptr);
@@ -40,6 +45,8 @@ class B200Gotoh : public AlignmentTool {
   int gapOpen = -1, gapExtend = -1, device = 0;  // <0: library defaults (11/1 protein)
   bool nucleotide = false;
   bool identityDistance = false;                 // ClustalW-style 1 - identities/min(len)
+  bool alignInProcess = false;                   // run(): fout = the multiple alignment (FASTA, tree order) that
+                                                 // readNewAlignment ingests; the matrix goes to <fout>.distmat
 
  private:
   void init();

@@ -32,6 +32,7 @@ void B200GotohTool::writeSettings(QDomDocument &doc, QDomElement &parentElem)
 	XMLHelper::addElement(doc, pelem, "gap_open", QString::number(gapOpen));
 	XMLHelper::addElement(doc, pelem, "gap_extend", QString::number(gapExtend));
 	XMLHelper::addElement(doc, pelem, "device", QString::number(device));
+	XMLHelper::addElement(doc, pelem, "align_in_process", (alignInProcess ? "yes" : "no"));
 }
 
 void B200GotohTool::readSettings(QDomDocument &doc)
@@ -47,6 +48,7 @@ void B200GotohTool::readSettings(QDomDocument &doc)
 			if (elem.tagName() == "gap_open") gapOpen = elem.text().toInt();
 			if (elem.tagName() == "gap_extend") gapExtend = elem.text().toInt();
 			if (elem.tagName() == "device") device = elem.text().toInt();
+			if (elem.tagName() == "align_in_process") alignInProcess = (elem.text() == "yes");
 			elem = elem.nextSiblingElement();
 		}
 	}
@@ -67,6 +69,7 @@ int B200GotohTool::run(const QString &fin, const QString &fout, QObject *logRece
 	p.gap_open = gapOpen;
 	p.gap_extend = gapExtend;
 	p.device = device;
+	if (alignInProcess) p.flags |= TSQ_FLAG_MSA_OUT;
 	return tsq_run_fasta(fin.toLocal8Bit().constData(), fout.toLocal8Bit().constData(), &p, forwardLog, logReceiver, cancel);
 }
 
@@ -78,6 +81,7 @@ void B200GotohTool::init()
 	gapOpen = -1;
 	gapExtend = -1;
 	device = 0;
+	alignInProcess = true;
 }
 
 void B200GotohTool::getVersion()

@@ -21,10 +21,11 @@ class B200GotohTool : public AlignmentTool
 		virtual void readSettings(QDomDocument &);
 
 		virtual bool inProcess(){return true;}
-		// fin: FASTA written by Project::exportFASTA; fout: distance matrix for clustalo --distmat-in
+		// fin: FASTA written by Project::exportFASTA; fout: the alignment (alignInProcess) or the distance matrix for clustalo --distmat-in
 		virtual int run(const QString &fin, const QString &fout, QObject *logReceiver, volatile int *cancel);
 
 		int gapOpen, gapExtend, device;
+		bool alignInProcess; // fout = the multiple alignment readNewAlignment ingests (no clustalo needed); else the matrix
 
 	private:
 		void init();

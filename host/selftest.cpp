@@ -56,6 +56,10 @@ int main(int argc, char** argv) {
     int sc = 0;
     CHECK(g.pairwiseAlignment("WWCWW", "WWWW", ra, rb, sc, &err) == TSQ_OK);
     CHECK(ra == "WWCWW" && rb.size() == 5 && sc == 44 - 12);   // one gap of length 1 against C
+    std::vector<std::string> rows;
+    std::vector<unsigned> order;
+    CHECK(g.multipleAlignment({"WWCWW", "WWWW", "WWCWW"}, rows, order, &err) == TSQ_OK);
+    CHECK(rows.size() == 3 && rows[0] == "WWCWW" && rows[2] == "WWCWW" && rows[1].size() == 5 && order.size() == 3);
     g.identityDistance = true;
     CHECK(g.distanceMatrix({"WWWW", "WWCWW", "ACDEFG"}, s, d, &err) == TSQ_OK);
     CHECK(d[0] == 0.0);   // 4 identities over the shorter length 4
@@ -64,6 +68,11 @@ int main(int argc, char** argv) {
   if (argc >= 3) {
     int rc = g.run(argv[1], argv[2], [](const std::string& l) { printf("[log] %s\n", l.c_str()); }, nullptr);
     CHECK(rc == 0);
+    if (argc >= 4) {   // argv[3] = alignment out: the tool as a complete in-process aligner
+      g.alignInProcess = true;
+      rc = g.run(argv[1], argv[3], [](const std::string& l) { printf("[log] %s\n", l.c_str()); }, nullptr);
+      CHECK(rc == 0);
+    }
   }
   printf("host selftest ok (B200 path)\n");
   return 0;

@@ -64,6 +64,9 @@ extern "C" {
                                      (tsq_identities) and make the distance 1 - identities/min(len_i, len_j),
                                      the ClustalW pairwise distance.  Scores are unchanged. */
 
+#define TSQ_FLAG_MSA_OUT 16u       /* tsq_run_fasta only: write the multiple alignment (tsq_msa) to fout, in tree
+                                     order, and the distance matrix to <fout>.distmat */
+
 typedef struct tsq_ctx tsq_ctx;
 
 typedef struct tsq_params {
@@ -95,6 +98,7 @@ typedef struct tsq_stats {
   uint64_t h2d_bytes;        /* bytes the last tsq_upload copied host -> device */
   uint64_t d2h_bytes;        /* bytes the last tsq_download copied device -> host */
   double tree_ms;            /* CUDA-event time of the last tsq_guide_tree (device only) */
+  double msa_ms;             /* wall time of the last tsq_msa (plan, kernels, copies) */
 } tsq_stats;
 
 /* progress in [0,1]; msg may be NULL.  Return value ignored. */
@@ -182,6 +186,30 @@ int tsq_guide_tree(tsq_ctx *ctx, const tsq_merge **merges, uint32_t *count);
 int tsq_write_newick(tsq_ctx *ctx, const char *const *labels, const char *path);
 
 /*
+ * Progressive multiple alignment along that guide tree -- what the external aligner hands back and
+ * Project::readNewAlignment ingests (tweakseq/Core/Project.cpp:908-1032): equal-length gapped rows.
+ * With it the backend needs no clustalo at all.  The n-1 merges are applied in order; merge t aligns
+ * the alignments of its two clusters column against column with the recurrence of SURVEY 8c, the
+ * score of two columns being the sum of S(a, b) over all residue pairs across them (a residue facing
+ * a gap scores 0) and a gap of k columns costing |X| |Y| (gap_open + k gap_extend); ties as in
+ * tsq_align_pair, so two sequences align exactly as tsq_align_pair aligns them.  Computed on the device
+ * (one CTA per merge, all merges of a tree level in one launch).  Needs tsq_run (distances).
+ * *rows: n x *ncols characters, row-major, row r = submitted sequence r, canonical upper-case symbols
+ * and '-', no terminators; *tree_order: the n sequence indices left to right in the tree (the row
+ * order of `clustalo --output-order=tree-order`, ClustalO.cpp:51).  Library-owned; any out pointer
+ * may be NULL.
+ */
+int tsq_msa(tsq_ctx *ctx, const char **rows, uint32_t *nrows, uint32_t *ncols, const uint32_t **tree_order);
+/*
+ * That alignment as a FASTA file (60 columns per line).  headers[r]: header line of sequence r with or
+ * without its '>' (NULL or headers == NULL: ">s<r>").  residues/lengths (both or neither): the
+ * sequences as submitted; their own spelling (case, J/O/U, ...) then replaces the canonical symbols,
+ * as an external aligner would echo it.  tree_order != 0: rows in tree order, else as submitted.
+ */
+int tsq_write_msa_fasta(tsq_ctx *ctx, const char *const *headers, const char *const *residues,
+                        const uint32_t *lengths, const char *path, int tree_order);
+
+/*
  * One optimal global alignment of sequences i and j (submitted order) WITH its path -- the
  * "emit pairwise alignments" half of SURVEY.md section 8f-2; what a user would otherwise get by
  * running the external aligner on two sequences (tweakseq/Core/ClustalO.cpp:48-52 argv on a
@@ -230,7 +258,11 @@ int tsq_measure_dpx_rate(tsq_ctx *ctx, double *ops_per_clk_per_sm, double *sm_mh
  * File-level convenience for the Qt adapter: read the FASTA file tweakseq
  * exported (Project.cpp:870-881, FASTAFile.cpp:149-171), compute, and write a square
  * PHYLIP-style distance matrix (n, then "label d d d ..." rows) that clustalo accepts via
- * --distmat-in.  Labels follow FASTAFile::parseComment (FASTAFile.cpp:177-187).
+ * --distmat-in, plus the guide tree as <distmat_out>.dnd.  Labels follow FASTAFile::parseComment
+ * (FASTAFile.cpp:177-187).  With TSQ_FLAG_MSA_OUT in params->flags the file named by distmat_out
+ * instead receives the multiple alignment (FASTA, tree order, header lines and residue spelling as
+ * read) -- the file tweakseq reads back at SeqEditMainWin.cpp:836-861 -- and the matrix goes to
+ * <distmat_out>.distmat.
  */
 int tsq_run_fasta(const char *fasta_in, const char *distmat_out, const tsq_params *params,
                   tsq_log_cb log, void *user, volatile int *cancel);

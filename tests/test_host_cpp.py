@@ -39,10 +39,16 @@ def test_cpp_adapter_runs_fasta_end_to_end(tmp_path):
     exe = _build()
     _, seqs = synth.config(1, 0.2)
     labels = [f"s{k}" for k in range(len(seqs))]
-    fin, fout = str(tmp_path / "in.fa"), str(tmp_path / "out.mat")
+    fin, fout, faln = str(tmp_path / "in.fa"), str(tmp_path / "out.mat"), str(tmp_path / "out.aln.fa")
     write_fasta(fin, labels, seqs)
-    out = subprocess.run([exe, fin, fout], capture_output=True, text=True, timeout=300)
+    out = subprocess.run([exe, fin, fout, faln], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "B200 path" in out.stdout, out.stdout + out.stderr
+    # alignInProcess: the third file is the multiple alignment, every input row back under its label
+    from tweakseq_b200.fasta import read_fasta
+    alab, arows, _ = read_fasta(faln)
+    assert sorted(alab) == sorted(labels) and len({len(r) for r in arows}) == 1
+    for l, r in zip(alab, arows):
+        assert r.replace("-", "") == seqs[labels.index(l)]
     lab, rows = read_distmat(fout)
     assert lab == labels
     enc = [o.encode(s) for s in seqs]

@@ -217,3 +217,140 @@ def test_kernel_phases_on_cpu_custom_matrix_and_wide_counts(emul):
     want, wsc = o.msa(enc, m, 3, 2, left, right)
     got, gsc, *_ = emul(enc, m, 3, 2, left, right)
     assert got == want and gsc.tolist() == wsc.tolist()
+
+
+# ---------------------------------------------------------------- GPU, through the C ABI ---------
+
+def _gpu_msa(seqs, alphabet=o.PROTEIN, go=-1, ge=-1, matrix=None, flags=0):
+    """(rows, tree order, merges) from libtsqb200.so."""
+    import tweakseq_b200 as t
+    with t.Context(alphabet=alphabet, gap_open=go, gap_extend=ge, matrix=matrix, flags=flags) as ctx:
+        ctx.set_sequences(seqs)
+        ctx.run()
+        left, right, _ = ctx.guide_tree()
+        rows, order = ctx.msa()
+        again, _ = ctx.msa()          # cached result, same answer
+        assert again == rows
+        st = ctx.stats()
+    return rows, order, left, right, st
+
+
+def _tree_order(left, right, n):
+    if n == 0:
+        return []
+    out, st = [], [0 if n == 1 else 2 * n - 2]
+    while st:
+        i = st.pop()
+        if i < n:
+            out.append(i)
+        else:
+            st.append(int(right[i - n])); st.append(int(left[i - n]))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,length,alphabet", [(1, 30, 0), (2, 50, 0), (3, 40, 0), (17, 90, 0), (64, 150, 0),
+                                               (33, 200, 1), (150, 60, 0)])
+def test_gpu_msa_equals_oracle(n, length, alphabet):
+    rng = np.random.default_rng(1000 + n)
+    seqs = family(rng, n, length, alphabet, mut=0.25, indel=0.08)
+    if n >= 17:
+        seqs[5] = ""                                      # an empty sequence becomes an all-gap row
+        seqs[7] = seqs[7][:3]
+    go, ge = (11, 1) if alphabet == o.PROTEIN else (10, 1)
+    rows, order, left, right, st = _gpu_msa(seqs, alphabet)
+    enc = [o.encode(s, alphabet) for s in seqs]
+    want, _ = o.msa(enc, o.matrix(alphabet), go, ge, left, right, alphabet)
+    assert rows == want
+    assert order == _tree_order(left, right, n)
+    check_rows(rows, seqs, alphabet)
+    assert st["msa_ms"] > 0 or n == 0
+
+
+@pytest.mark.gpu
+def test_gpu_msa_of_two_sequences_is_align_pair():
+    import tweakseq_b200 as t
+    rng = np.random.default_rng(77)
+    a, b = family(rng, 2, 300, mut=0.3, indel=0.1)
+    with t.Context() as ctx:
+        ctx.set_sequences([a, b])
+        ctx.run()
+        rows, order = ctx.msa()
+        ra, rb, _ = ctx.align_pair(0, 1)
+    assert rows == [ra, rb] and order == [0, 1]
+
+
+@pytest.mark.gpu
+def test_gpu_msa_custom_matrix_gaps_and_identity_tree():
+    import tweakseq_b200 as t
+    rng = np.random.default_rng(78)
+    m = rng.integers(-6, 10, size=(23, 23))
+    m = ((m + m.T) // 2).astype(np.int8)
+    seqs = family(rng, 40, 80, mut=0.4, indel=0.15)
+    for flags in (0, t.FLAG_IDENTITY):
+        rows, order, left, right, _ = _gpu_msa(seqs, go=4, ge=2, matrix=m, flags=flags)
+        want, _ = o.msa([o.encode(s) for s in seqs], m, 4, 2, left, right)
+        assert rows == want
+
+
+@pytest.mark.gpu
+def test_gpu_msa_long_profiles_span_several_sweeps():
+    # diagonals longer than a CTA (1 024 threads): every thread takes several cells per diagonal
+    rng = np.random.default_rng(79)
+    seqs = family(rng, 6, 2600, o.NUCLEOTIDE, mut=0.1, indel=0.03)
+    rows, order, left, right, _ = _gpu_msa(seqs, o.NUCLEOTIDE)
+    want, _ = o.msa([o.encode(s, o.NUCLEOTIDE) for s in seqs], o.matrix(o.NUCLEOTIDE), 10, 1, left, right, o.NUCLEOTIDE)
+    assert rows == want
+
+
+@pytest.mark.gpu
+def test_gpu_run_fasta_writes_the_alignment_readNewAlignment_expects(tmp_path):
+    import tweakseq_b200 as t
+    from tweakseq_b200.fasta import read_fasta
+    rng = np.random.default_rng(80)
+    seqs = family(rng, 20, 130, mut=0.2, indel=0.06)
+    seqs[4] = seqs[4].lower()                              # the input's own spelling comes back
+    seqs[6] = seqs[6][:40] + "JOU" + seqs[6][40:]          # letters the matrix folds into X stay as typed
+    labels = [f"seq{k}" for k in range(len(seqs))]
+    fin, fout = str(tmp_path / "in.fa"), str(tmp_path / "out.fa")
+    with open(fin, "w") as f:
+        for l, s in zip(labels, seqs):
+            f.write(f">{l} some description\n")
+            for at in range(0, len(s), 70):
+                f.write(s[at:at + 70] + "\n")
+    tool = t.B200Gotoh()
+    tool.align = True
+    log = []
+    assert tool.run(fin, fout, log=log.append) == 0
+    assert any("progressive alignment" in m for m in log)
+    got_labels, got_rows, _ = read_fasta(fout)
+    # rows come in tree order; every label of the input is there exactly once (Project.cpp:908-1032 matches by label)
+    assert sorted(got_labels) == sorted(labels)
+    by_label = dict(zip(got_labels, got_rows))
+    assert len({len(r) for r in got_rows}) == 1
+    for l, s in zip(labels, seqs):
+        assert by_label[l].replace("-", "") == s
+    # the same rows, canonical spelling, from the in-memory API and from the oracle
+    rows, order, left, right, _ = _gpu_msa(seqs)
+    assert [got_labels.index(labels[r]) for r in order] == list(range(len(seqs)))
+    for l, r in zip(labels, rows):
+        assert len(by_label[l]) == len(r) and all((a == "-") == (b == "-") for a, b in zip(by_label[l], r))
+    want, _ = o.msa([o.encode(s) for s in seqs], o.matrix(0), 11, 1, left, right)
+    assert rows == want
+    # the matrix and the tree are written next to it
+    assert os.path.exists(fout + ".distmat") and os.path.exists(fout + ".dnd")
+
+
+def test_kernel_phases_on_cpu_degenerate_inputs(emul):
+    mat = o.matrix(o.PROTEIN)
+    none = np.zeros(0, np.uint32)
+    assert emul([], mat, 11, 1, none, none)[0] == []
+    empties = [o.encode(""), o.encode("--"), o.encode(" ")]
+    rows, sc, order, _, _ = emul(empties, mat, 11, 1, [0, 3], [1, 2])
+    assert rows == ["", "", ""] and sc.tolist() == [0, 0] and order.tolist() == [0, 1, 2]
+    one = [o.encode("MKV")]
+    assert emul(one, mat, 11, 1, none, none)[0] == ["MKV"]
+    # an empty cluster against a real one: every column is a gap column of the empty side
+    rows, sc, _, _, _ = emul([o.encode(""), o.encode("WW")], mat, 11, 1, [0], [1])
+    assert rows == ["--", "WW"] and sc.tolist() == [-(11 + 2)]
+    assert o.msa([o.encode(""), o.encode("WW")], mat, 11, 1, [0], [1])[0] == ["--", "WW"]

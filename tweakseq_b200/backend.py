@@ -64,6 +64,7 @@ class B200Gotoh(AlignmentTool):
         self.gap_extend = -1
         self.device = 0
         self.identity = False      # ClustalW-style identity distance instead of the score distance
+        self.align = False         # run(): write the multiple alignment (readNewAlignment's input) instead of the matrix
         self.last_stats: dict = {}
 
     def inProcess(self): return True
@@ -109,13 +110,26 @@ class B200Gotoh(AlignmentTool):
 
     # ---- the in-process path -------------------------------------------------------------
     def run(self, fin, fout, log=None, cancel: C.c_int | None = None) -> int:
-        """FASTA file in (what Project::exportFASTA wrote), distance matrix file out.
+        """FASTA file in (what Project::exportFASTA wrote), distance matrix file out -- or, with
+        ``align`` set, the multiple alignment itself (FASTA, tree order): the file
+        Project::readNewAlignment (Project.cpp:908-1032) reads back, no external aligner involved.
 
         Returns the exit status startAlignment()/alignmentFinished() would see (0 = success:
         SeqEditMainWin.cpp:836-861)."""
+        flags = (capi.FLAG_IDENTITY if self.identity else 0) | (capi.FLAG_MSA_OUT if self.align else 0)
         return capi.run_fasta(fin, fout, log=log, cancel=cancel, alphabet=self.alphabet,
-                              gap_open=self.gap_open, gap_extend=self.gap_extend, device=self.device,
-                              flags=capi.FLAG_IDENTITY if self.identity else 0)
+                              gap_open=self.gap_open, gap_extend=self.gap_extend, device=self.device, flags=flags)
+
+    def multiple_alignment(self, residues):
+        """Distances, UPGMA guide tree and the progressive alignment along it, in memory:
+        (rows in submitted order, tree order of the rows)."""
+        with capi.Context(alphabet=self.alphabet, gap_open=self.gap_open, gap_extend=self.gap_extend,
+                          device=self.device, flags=capi.FLAG_IDENTITY if self.identity else 0) as ctx:
+            ctx.set_sequences(residues)
+            ctx.run()
+            rows, order = ctx.msa()
+            self.last_stats = ctx.stats()
+            return rows, order
 
     def distance_matrix(self, residues, labels=None, progress=None, cancel=None, flags: int = 0):
         """Scores and distances for in-memory residues (what Sequence::filter(true) returns).

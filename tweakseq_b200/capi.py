@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 PROTEIN, NUCLEOTIDE = 0, 1
-FLAG_FORCE_S32, FLAG_NO_DISTANCES, FLAG_NO_WAVE16, FLAG_IDENTITY = 1, 2, 4, 8
+FLAG_FORCE_S32, FLAG_NO_DISTANCES, FLAG_NO_WAVE16, FLAG_IDENTITY, FLAG_MSA_OUT = 1, 2, 4, 8, 16
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libtsqb200.so")
@@ -42,7 +42,7 @@ class Stats(C.Structure):
                 ("cells_s16", C.c_uint64), ("cells_s32", C.c_uint64), ("kernel_ms", C.c_double),
                 ("upload_ms", C.c_double), ("download_ms", C.c_double), ("gcups_kernel", C.c_double),
                 ("launches", C.c_uint32), ("sm_count", C.c_uint32), ("strip_width", C.c_uint32),
-                ("upload_launches", C.c_uint32), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("tree_ms", C.c_double)]
+                ("upload_launches", C.c_uint32), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("tree_ms", C.c_double), ("msa_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -57,7 +57,7 @@ SYMBOLS = ["tsq_version", "tsq_version_string", "tsq_status_string", "tsq_device
            "tsq_download", "tsq_set_stream", "tsq_synchronize", "tsq_run", "tsq_scores", "tsq_distances",
            "tsq_self_scores", "tsq_identities", "tsq_device_scores", "tsq_partition", "tsq_finalize", "tsq_device_results",
            "tsq_get_stats", "tsq_measure_dpx_rate", "tsq_run_fasta", "tsq_plan_partition", "tsq_guide_tree",
-           "tsq_write_newick", "tsq_consensus", "tsq_align_pair", "tsq_partition_of"]
+           "tsq_write_newick", "tsq_consensus", "tsq_align_pair", "tsq_partition_of", "tsq_msa", "tsq_write_msa_fasta"]
 
 _lib = None
 
@@ -112,6 +112,9 @@ def load_library():
     L.tsq_consensus.argtypes = [vp, C.POINTER(C.c_char_p), C.c_uint32, C.c_uint32, C.c_double, C.c_char_p]
     L.tsq_align_pair.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32),
                                  C.POINTER(C.c_int32)]
+    L.tsq_msa.argtypes = [vp, C.POINTER(C.POINTER(C.c_char)), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                          C.POINTER(C.POINTER(C.c_uint32))]
+    L.tsq_write_msa_fasta.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), C.c_char_p, C.c_int]
     L.tsq_plan_partition.argtypes = [C.POINTER(Params), C.POINTER(C.c_uint32), C.c_uint32, C.c_int32, u64p, u64p]
     L.tsq_measure_dpx_rate.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.tsq_run_fasta.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(Params), LOG_CB, vp, C.POINTER(C.c_int)]
@@ -314,6 +317,28 @@ class Context:
             arr = (C.c_char_p * len(raw))(*raw)
         self._ck(self._L.tsq_write_newick(self._h, arr, path.encode()))
 
+    def msa(self):
+        """Progressive multiple alignment along the guide tree of the last run: (rows, tree_order) --
+        equal-length gapped strings in submitted order and the leaf order of the tree."""
+        rows, order = C.POINTER(C.c_char)(), C.POINTER(C.c_uint32)()
+        n, cols = C.c_uint32(), C.c_uint32()
+        self._ck(self._L.tsq_msa(self._h, C.byref(rows), C.byref(n), C.byref(cols), C.byref(order)))
+        raw = C.string_at(rows, n.value * cols.value) if n.value * cols.value else b""
+        out = [raw[r * cols.value:(r + 1) * cols.value].decode("ascii") for r in range(n.value)]
+        return out, [int(order[i]) for i in range(n.value)]
+
+    def write_msa_fasta(self, path: str, headers=None, residues=None, tree_order: bool = True):
+        """tsq_write_msa_fasta(): the alignment as FASTA; residues = the submitted spelling to echo."""
+        harr = rarr = larr = None
+        if headers is not None:
+            hraw = [h.encode("latin-1", "replace") for h in headers]
+            harr = (C.c_char_p * max(len(hraw), 1))(*hraw)
+        if residues is not None:
+            rraw = [s.encode("latin-1", "replace") if isinstance(s, str) else bytes(s) for s in residues]
+            rarr = (C.c_char_p * max(len(rraw), 1))(*rraw)
+            larr = (C.c_uint32 * max(len(rraw), 1))(*[len(r) for r in rraw])
+        self._ck(self._L.tsq_write_msa_fasta(self._h, harr, rarr, larr, path.encode(), 1 if tree_order else 0))
+
     def consensus(self, rows, plurality: float = -1.0) -> str:
         """Consensus annotation of equal-length aligned rows (Consensus.cpp:80-161); '?' = no plurality."""
         raw = [r.encode("latin-1", "replace") if isinstance(r, str) else bytes(r) for r in rows]
@@ -345,7 +370,8 @@ class Context:
 
 
 def run_fasta(fasta_in: str, distmat_out: str, log=None, cancel: C.c_int | None = None, **kw) -> int:
-    """tsq_run_fasta(): FASTA file in, PHYLIP-style distance matrix out.  Returns the status."""
+    """tsq_run_fasta(): FASTA file in, PHYLIP-style distance matrix out (flags=FLAG_MSA_OUT: the
+    multiple alignment out, matrix in <out>.distmat).  Returns the status."""
     L = load_library()
     p = Params()
     L.tsq_default_params(C.byref(p))

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -19,6 +20,7 @@
 
 #include "../../include/tsq_b200.h"
 #include "tsq_device.h"
+#include "msa_host.h"
 
 namespace {
 
@@ -185,6 +187,12 @@ struct tsq_ctx {
   std::vector<tsq_merge> merges;
   bool have_tree = false;
   double tree_ms = 0;
+  // progressive alignment along that tree (tsq_msa)
+  std::vector<uint8_t> msa_rows;          // n x msa_cols characters, submitted order
+  std::vector<uint32_t> msa_order;        // leaves left to right
+  uint32_t msa_cols = 0;
+  bool have_msa = false;
+  double msa_ms = 0;
   DevBuf<uint2> d_pairs32;
   DevBuf<uint4> d_tasks16w;
   DevBuf<uint2> d_bnd16w;
@@ -1062,6 +1070,7 @@ int tsq_finalize(tsq_ctx* c) {
   }
   c->finalized = true;
   c->have_tree = false;
+  c->have_msa = false;
   return TSQ_OK;
 }
 
@@ -1317,6 +1326,172 @@ int tsq_write_newick(tsq_ctx* c, const char* const* labels, const char* path) {
   return TSQ_OK;
 }
 
+namespace {
+
+// The device side of msa_host.h: persistent memory is bump-allocated from cudaMalloc'd chunks (a job
+// makes ~2n small allocations), scratch is one growing block, everything runs on the context's stream.
+class CudaMsaDevice : public tsq::MsaDevice {
+ public:
+  explicit CudaMsaDevice(cudaStream_t s) : s_(s) {}
+  ~CudaMsaDevice() override {
+    for (void* p : chunks_) cudaFree(p);
+    scr_.release();
+  }
+  cudaError_t err = cudaSuccess;   // first CUDA error seen
+
+  void* alloc(size_t bytes) override {
+    bytes = tsq::msa_align(std::max<size_t>(bytes, 1));
+    if (bytes > left_) {
+      const size_t chunk = std::max(bytes, (size_t)64 << 20);
+      void* p = nullptr;
+      if (!ok(cudaMalloc(&p, chunk))) return nullptr;
+      chunks_.push_back(p);
+      cur_ = (char*)p;
+      left_ = chunk;
+    }
+    void* r = cur_;
+    cur_ += bytes;
+    left_ -= bytes;
+    return r;
+  }
+  void* scratch(size_t bytes) override {
+    if (bytes > scr_.cap) {
+      if (!ok(cudaStreamSynchronize(s_))) return nullptr;   // nothing may still be using the old block
+      if (!ok(scr_.reserve(bytes + bytes / 4))) return nullptr;
+    }
+    return scr_.p;
+  }
+  bool h2d(void* d, const void* h, size_t b) override { return ok(cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, s_)); }
+  bool d2h(void* h, const void* d, size_t b) override {
+    return ok(cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, s_)) && ok(cudaStreamSynchronize(s_));
+  }
+  bool fill(void* d, int v, size_t b) override { return ok(cudaMemsetAsync(d, v, b, s_)); }
+  bool launch_leaves(const tsq::MsaLeaf* l, uint32_t n, uint32_t nsym) override { return ok(tsq::msa_leaf_launch(l, n, nsym, s_)); }
+  bool launch_merges(const tsq::MsaTask* t, uint32_t count, uint32_t threads, const tsq::MsaConst& k) override {
+    return ok(tsq::msa_merge_launch(t, count, threads, k, s_));
+  }
+  bool launch_rows(const tsq::MsaRows& p) override { return ok(tsq::msa_rows_launch(p, s_)); }
+
+ private:
+  bool ok(cudaError_t e) {
+    if (e != cudaSuccess && err == cudaSuccess) err = e;
+    return e == cudaSuccess;
+  }
+  cudaStream_t s_;
+  std::vector<void*> chunks_;
+  char* cur_ = nullptr;
+  size_t left_ = 0;
+  DevBuf<uint8_t> scr_;
+};
+
+const char* letters_of(const tsq_ctx* c) { return c->prm.alphabet == TSQ_NUCLEOTIDE ? "ACGTN" : "ARNDCQEGHILKMFPSTWYVBZX"; }
+
+}  // namespace
+
+int tsq_msa(tsq_ctx* c, const char** rows, uint32_t* nrows, uint32_t* ncols, const uint32_t** tree_order) {
+  if (!c) return TSQ_ERR_INVALID;
+  if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "tsq_msa before tsq_run");
+  const tsq_merge* mg = nullptr;
+  uint32_t cnt = 0;
+  int rc = tsq_guide_tree(c, &mg, &cnt);
+  if (rc != TSQ_OK) return rc;
+  if (!c->have_msa) {
+    const uint32_t n = c->n;
+    TSQ_CUDA(c, cudaSetDevice(c->device));
+    tsq::MsaJob job;
+    job.n = n;
+    job.d_sym = c->d_lin.p;
+    job.sym_off.assign(n, 0);
+    job.len.assign(n, 0);
+    for (uint32_t k = 0; k < n; k++) {   // perm: sorted position -> submitted index (the tree's leaf id)
+      job.sym_off[c->perm[k]] = c->loff[k];
+      job.len[c->perm[k]] = c->lens[k];
+    }
+    job.left.resize(cnt);
+    job.right.resize(cnt);
+    for (uint32_t t = 0; t < cnt; t++) {
+      job.left[t] = mg[t].left;
+      job.right[t] = mg[t].right;
+    }
+    job.nsym = (uint32_t)c->nsym;
+    job.smat.assign(c->matrix.begin(), c->matrix.end());
+    job.go = c->go;
+    job.ge = c->ge;
+    job.letters = letters_of(c);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) job.scratch_budget = std::max<size_t>(free_b / 4, (size_t)256 << 20);
+    else cudaGetLastError();
+    tsq::MsaOut out;
+    const double t0 = now_ms();
+    int mrc;
+    cudaError_t derr;
+    {
+      CudaMsaDevice dev(c->stream);
+      mrc = tsq::msa_progressive(dev, job, out);
+      derr = dev.err;
+      if (mrc == tsq::MSA_OK && derr == cudaSuccess) derr = cudaStreamSynchronize(c->stream);
+    }
+    if (derr != cudaSuccess) {
+      cudaGetLastError();
+      return fail(c, derr == cudaErrorMemoryAllocation ? TSQ_ERR_NOMEM : TSQ_ERR_CUDA, "tsq_msa: %s", cudaGetErrorString(derr));
+    }
+    if (mrc == tsq::MSA_NOMEM) return fail(c, TSQ_ERR_NOMEM, "tsq_msa: out of device memory");
+    if (mrc != tsq::MSA_OK) return fail(c, TSQ_ERR_CUDA, "tsq_msa: internal error %d", mrc);
+    c->msa_ms = now_ms() - t0;
+    c->msa_rows.swap(out.rows);
+    c->msa_order.swap(out.tree_order);
+    c->msa_cols = out.ncols;
+    c->st.launches += out.launches;
+    c->have_msa = true;
+  }
+  if (rows) *rows = reinterpret_cast<const char*>(c->msa_rows.data());
+  if (nrows) *nrows = c->n;
+  if (ncols) *ncols = c->msa_cols;
+  if (tree_order) *tree_order = c->msa_order.data();
+  return TSQ_OK;
+}
+
+int tsq_write_msa_fasta(tsq_ctx* c, const char* const* headers, const char* const* residues, const uint32_t* lengths,
+                        const char* path, int tree_order) {
+  if (!c || !path) return TSQ_ERR_INVALID;
+  const char* rows = nullptr;
+  const uint32_t* order = nullptr;
+  uint32_t n = 0, cols = 0;
+  int rc = tsq_msa(c, &rows, &n, &cols, &order);
+  if (rc != TSQ_OK) return rc;
+  if (residues && !lengths) return fail(c, TSQ_ERR_INVALID, "residues without lengths");
+  FILE* f = fopen(path, "w");
+  if (!f) return fail(c, TSQ_ERR_IO, "cannot write %s", path);
+  std::string row;
+  for (uint32_t q = 0; q < n; q++) {
+    const uint32_t r = tree_order ? order[q] : q;
+    row.assign(rows + (size_t)r * cols, cols);
+    if (residues && residues[r]) {
+      // the caller's own spelling of every residue (case, J/O/U, ...): k-th kept input byte -> k-th non-gap column
+      const unsigned char* in = reinterpret_cast<const unsigned char*>(residues[r]);
+      uint32_t k = 0;
+      for (uint32_t col = 0; col < cols; col++) {
+        if (row[col] == '-') continue;
+        while (k < lengths[r] && is_gap_or_space(in[k])) k++;
+        if (k < lengths[r]) row[col] = (char)in[k++];
+      }
+    }
+    if (headers && headers[r]) {
+      const char* h = headers[r];
+      fprintf(f, "%s%s\n", (h[0] == '>' ? "" : ">"), h);
+    } else {
+      fprintf(f, ">s%u\n", r);
+    }
+    for (uint32_t at = 0; at < cols; at += 60) {
+      fwrite(row.data() + at, 1, std::min<uint32_t>(60, cols - at), f);
+      fputc('\n', f);
+    }
+    if (cols == 0) fputc('\n', f);
+  }
+  if (fclose(f) != 0) return fail(c, TSQ_ERR_IO, "write to %s failed", path);
+  return TSQ_OK;
+}
+
 int tsq_align_pair(tsq_ctx* c, uint32_t i, uint32_t j, char* row_i, char* row_j, uint32_t capacity, uint32_t* columns,
                    int32_t* score) {
   if (!c || !row_i || !row_j) return TSQ_ERR_INVALID;
@@ -1473,6 +1648,7 @@ int tsq_get_stats(tsq_ctx* c, tsq_stats* out) {
   c->st.sm_count = (uint32_t)c->sm_count;
   c->st.strip_width = (uint32_t)c->K;
   c->st.tree_ms = c->tree_ms;
+  c->st.msa_ms = c->msa_ms;
   *out = c->st;
   return TSQ_OK;
 }
@@ -1497,7 +1673,7 @@ int tsq_run_fasta(const char* fin, const char* fout, const tsq_params* params, t
     say(std::string("cannot open ") + fin);
     return TSQ_ERR_IO;
   }
-  std::vector<std::string> labels, seqs;
+  std::vector<std::string> labels, headers, seqs;
   std::string line;
   int state = 0;  // 0 seeking header, 1 just read header, 2 reading residues
   auto trim = [](std::string& s) {
@@ -1516,14 +1692,14 @@ int tsq_run_fasta(const char* fin, const char* fout, const tsq_params* params, t
     const char f = line[0];
     const bool hdr = (f == '>' || f == ';');
     if (state == 0) {
-      if (hdr) { labels.push_back(label_of(line)); seqs.emplace_back(); state = 1; }
+      if (hdr) { labels.push_back(label_of(line)); headers.push_back(line); seqs.emplace_back(); state = 1; }
     } else if (state == 1) {
       if (f == ';') continue;
-      if (f == '>') { labels.push_back(label_of(line)); seqs.emplace_back(); continue; }
+      if (f == '>') { labels.push_back(label_of(line)); headers.push_back(line); seqs.emplace_back(); continue; }
       seqs.back() += line;
       state = 2;
     } else {
-      if (hdr) { labels.push_back(label_of(line)); seqs.emplace_back(); state = 1; }
+      if (hdr) { labels.push_back(label_of(line)); headers.push_back(line); seqs.emplace_back(); state = 1; }
       else seqs.back() += line;
     }
   }
@@ -1552,10 +1728,15 @@ int tsq_run_fasta(const char* fin, const char* fout, const tsq_params* params, t
   const double* d = nullptr;
   uint64_t cnt = 0;
   rc = tsq_distances(c, &d, &cnt);
+  // TSQ_FLAG_MSA_OUT: fout is the alignment itself (what Project::readNewAlignment ingests,
+  // Project.cpp:908-1032); the matrix moves to <fout>.distmat.  Otherwise fout is the matrix.
+  const bool msa_out = params && params->struct_size >= offsetof(tsq_params, flags) + sizeof(uint32_t) &&
+                       (params->flags & TSQ_FLAG_MSA_OUT);
+  const std::string matrix_path = msa_out ? std::string(fout) + ".distmat" : std::string(fout);
   if (rc == TSQ_OK) {
-    FILE* fo = fopen(fout, "w");
+    FILE* fo = fopen(matrix_path.c_str(), "w");
     if (!fo) {
-      say(std::string("cannot write ") + fout);
+      say(std::string("cannot write ") + matrix_path);
       rc = TSQ_ERR_IO;
     } else {
       const uint64_t n = seqs.size();
@@ -1579,8 +1760,31 @@ int tsq_run_fasta(const char* fin, const char* fout, const tsq_params* params, t
       tsq_stats st;
       tsq_get_stats(c, &st);
       snprintf(msg, sizeof msg, "tsq-b200: %llu pairs, %.3e cells, kernel %.3f ms (%.1f GCUPS), wrote %s",
-               (unsigned long long)cnt, (double)st.cells, st.kernel_ms, st.gcups_kernel, fout);
+               (unsigned long long)cnt, (double)st.cells, st.kernel_ms, st.gcups_kernel, matrix_path.c_str());
       say(msg);
+    }
+  }
+  if (rc == TSQ_OK && msa_out) {
+    if (cancel && *cancel) {
+      rc = TSQ_ERR_CANCELLED;
+    } else {
+      // rows in tree order like the reference's clustalo argv (--output-order=tree-order, ClustalO.cpp:51),
+      // header lines and residue spelling exactly as read, so readNewAlignment matches every label
+      std::vector<const char*> hdr(headers.size()), res(seqs.size());
+      for (size_t i = 0; i < headers.size(); i++) hdr[i] = headers[i].c_str();
+      for (size_t i = 0; i < seqs.size(); i++) res[i] = seqs[i].data();
+      rc = tsq_write_msa_fasta(c, hdr.data(), res.data(), lens.data(), fout, 1);
+      if (rc == TSQ_OK) {
+        tsq_stats st;
+        tsq_get_stats(c, &st);
+        uint32_t cols = 0;
+        tsq_msa(c, nullptr, nullptr, &cols, nullptr);
+        snprintf(msg, sizeof msg, "tsq-b200: progressive alignment, %zu rows x %u columns in %.1f ms, wrote %s", seqs.size(), cols,
+                 st.msa_ms, fout);
+        say(msg);
+      } else {
+        say(std::string("tsq-b200: ") + tsq_last_error(c));
+      }
     }
   }
   tsq_destroy(c);

@@ -320,6 +320,26 @@ cudaError_t traceback_launch(const TbParams& p, cudaStream_t stream) {
   return cudaLaunchKernelEx(&cfg, traceback_kernel<TB_CLUSTER>, p);
 }
 
+// ---- progressive alignment (msa.cuh) ---------------------------------------------------------
+cudaError_t msa_leaf_launch(const MsaLeaf* d_leaves, uint32_t n, uint32_t nsym, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  msa_leaf_kernel<<<n < 65535u ? n : 65535u, 128, 0, stream>>>(d_leaves, n, nsym);
+  return cudaGetLastError();
+}
+
+cudaError_t msa_merge_launch(const MsaTask* d_tasks, uint32_t count, uint32_t threads, const MsaConst& k, cudaStream_t stream) {
+  if (count == 0) return cudaSuccess;
+  if (threads < 32 || threads > 1024 || (threads & 31u)) return cudaErrorInvalidValue;
+  msa_merge_kernel<<<count, threads, 0, stream>>>(d_tasks, k);
+  return cudaGetLastError();
+}
+
+cudaError_t msa_rows_launch(const MsaRows& p, cudaStream_t stream) {
+  if (p.n == 0) return cudaSuccess;
+  msa_rows_kernel<<<p.n < 65535u ? p.n : 65535u, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
 // ---- finalize: empties, un-sort, fp64 distances -----------------------------------------
 // One CTA per sorted row i; threads stride over j > i.  Distances follow the oracle's
 // tsq_oracle_distance(): two separately rounded IEEE operations (div, sub), no contraction.

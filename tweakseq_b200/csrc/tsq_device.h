@@ -9,6 +9,7 @@
 #include "wave16.cuh"
 #include "upgma.cuh"
 #include "traceback.cuh"
+#include "msa.cuh"
 
 namespace tsq {
 
@@ -52,6 +53,12 @@ cudaError_t upgma_launch(const UpgmaParams& p, cudaStream_t stream);
 
 // One pair with its path (traceback.cuh): a single CTA sweeps the anti-diagonals.
 cudaError_t traceback_launch(const TbParams& p, cudaStream_t stream);
+
+// Progressive alignment along the guide tree (msa.cuh): leaf profiles, one launch per batch of
+// independent merges (one CTA each, `threads` per CTA), final rows.
+cudaError_t msa_leaf_launch(const MsaLeaf* d_leaves, uint32_t n, uint32_t nsym, cudaStream_t stream);
+cudaError_t msa_merge_launch(const MsaTask* d_tasks, uint32_t count, uint32_t threads, const MsaConst& k, cudaStream_t stream);
+cudaError_t msa_rows_launch(const MsaRows& p, cudaStream_t stream);
 
 // Builds the 32-way interleaved subject database of the packed kernel from the linear residues:
 // per residue the 16-bit byte offset of its profile row, two rows per word, right-aligned to an
