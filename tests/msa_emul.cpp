@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #include "../tweakseq_b200/csrc/msa_host.h"
@@ -21,6 +22,7 @@ class EmulDevice : public tsq::MsaDevice {
   size_t scr_cap = 0;
   int order = 0;   // 0: threads descending, 1: ascending
   uint32_t force_threads = 0;
+  bool no_smem = false;   // force the global-scratch path of the rolling diagonals
   ~EmulDevice() override {
     for (void* p : blocks) free(p);
     free(scr);
@@ -51,15 +53,20 @@ class EmulDevice : public tsq::MsaDevice {
     for (uint32_t r = 0; r < n; r++) each_thread(128, [&](int t) { tsq::msa_leaf_phase(l[r], nsym, t, 128); });
     return true;
   }
-  bool launch_merges(const tsq::MsaTask* tasks, uint32_t count, uint32_t threads, const tsq::MsaConst& k) override {
+  bool launch_merges(const tsq::MsaTask* tasks, uint32_t count, uint32_t threads, uint32_t smem_bytes,
+                     const tsq::MsaConst& k) override {
     const int nt = (int)(force_threads ? force_threads : threads);
-    if (nt < 1 || nt > 1024) return false;
+    if (nt < 1 || nt > 1024 || smem_bytes > 227 * 1024) return false;
+    if (no_smem) smem_bytes = 0;
+    std::vector<long long> shared(smem_bytes / sizeof(long long) + 1);
     for (uint32_t b = 0; b < count; b++) {
       const tsq::MsaTask t = tasks[b];
-      each_thread(nt, [&](int tid) { tsq::msa_py_phase(t, k, tid, nt); });
+      std::fill(shared.begin(), shared.end(), (long long)0x5C5C5C5C5C5C5C5CLL);   // a new CTA: shared memory is garbage
+      long long* const diag = tsq::msa_diag_bytes(t.Lx) <= (size_t)smem_bytes ? shared.data() : t.diag;   // as the kernel decides
+      each_thread(nt, [&](int tid) { tsq::msa_prep_phase(t, k, tid, nt); });
       const int last = (int)(t.Lx + t.Ly);
-      for (int d = 0; d <= last; ++d) each_thread(nt, [&](int tid) { tsq::msa_diag_phase(t, k, d, tid, nt); });
-      tsq::msa_walk_phase(t);
+      for (int d = 0; d <= last; ++d) each_thread(nt, [&](int tid) { tsq::msa_diag_phase(t, k, diag, d, tid, nt); });
+      tsq::msa_walk_phase(t, diag);
       each_thread(nt, [&](int tid) { tsq::msa_build_phase(t, k, tid, nt); });
     }
     return true;
@@ -79,7 +86,8 @@ extern "C" int msa_emul(const uint8_t* seqs, const uint64_t* offs, const uint32_
                         uint32_t* launches, uint32_t* levels) {
   EmulDevice dev;
   dev.order = ascending;
-  dev.force_threads = force_threads;
+  dev.force_threads = force_threads & 0xffffu;
+  dev.no_smem = (force_threads >> 16) & 1u;
   tsq::MsaJob job;
   job.n = n;
   job.d_sym = seqs;

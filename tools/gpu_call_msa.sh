@@ -8,3 +8,5 @@ mkdir -p gpurun_out
 ( timeout 180 python tools/prof_msa.py ; echo "exit $?" ) > gpurun_out/msa_prof.log 2>&1
 tail -3 gpurun_out/msa_tests.log gpurun_out/msa_regress.log gpurun_out/msa_memcheck.log gpurun_out/msa_initcheck.log
 cat gpurun_out/msa_prof.log
+( timeout 200 ncu --set full --clock-control none --import-source on -k regex:msa_merge -s 60 -c 2 -f -o gpurun_out/msa_merge python tools/prof_msa_one.py ; echo "exit $?" ) > gpurun_out/msa_ncu.log 2>&1
+tail -n 3 gpurun_out/msa_ncu.log

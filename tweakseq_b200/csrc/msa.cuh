@@ -15,10 +15,17 @@
 // One CTA per merge, all merges of one tree level in one launch.  A merge is four phases separated by
 // CTA barriers; every phase is a function of (task, thread id, thread count) with no barrier inside, so
 // tests/msa_emul.cpp can run the very same phase code on the CPU, thread by thread, against the oracle:
-//   1. PY[a][j] = sum_b cntY[j][b] S(a, b)                  -> 23 multiply-adds per cell instead of 23^2
-//   2. anti-diagonal sweep, one barrier per diagonal: H (3 rolling diagonals), E, F (2 each) in an
-//      L2-resident scratch indexed by i; one direction byte per cell, diagonal-major (traceback.cuh)
-//   3. thread 0 walks the path back from (Lx, Ly): per merged column its X column and Y column or -1
+//   1. the column score in two factors: for the cluster with MORE sequences ("big") the letter scores
+//      P[b][col] = sum_a cnt_big[col][a] S(a, b); for the other one ("small") per column the list of
+//      letters present with their counts.  sub(i, j) = sum over that list of count * P[letter][col_big]:
+//      one multiply-add per distinct letter of the small side's column -- exactly one when it is a
+//      single sequence, the common case of a guide tree over related sequences (a caterpillar).
+//   2. anti-diagonal sweep, one barrier per diagonal: H (3 rolling diagonals), E, F (2 each) indexed by
+//      i, in SHARED memory when 7 (Lx + 1) words fit (an L2 round trip per diagonal otherwise); one
+//      direction byte per cell, diagonal-major (traceback.cuh)
+//   3. thread 0 walks the path back from (Lx, Ly): per merged column its X column and Y column or -1.
+//      The direction bytes sit in L2, so it fetches the next 16 along the current run (diagonal, or a
+//      gap run) at once and consumes them from registers: one round trip per run piece, not per column
 //   4. all threads: column maps old -> merged for X and Y, merged counts = cntX[px] + cntY[py]
 // Profiles are letter-major (c[a * cap + col]) so that a diagonal's threads read consecutive words.
 // No rows are materialised per merge: a leaf's residues reach their final columns by composing the
@@ -30,6 +37,11 @@
 #define TSQ_HD __host__ __device__ __forceinline__
 #else
 #define TSQ_HD inline
+#endif
+#if defined(__CUDA_ARCH__)
+#define TSQ_UNROLL _Pragma("unroll")
+#else
+#define TSQ_UNROLL
 #endif
 
 namespace tsq {
@@ -55,8 +67,10 @@ struct MsaTask {         // one merge: X = left child, Y = right child
   uint32_t nx, ny;       // sequences in X and Y
   uint32_t* mapx;        // Lx entries: X column -> merged column
   uint32_t* mapy;        // Ly entries
-  long long* diag;       // scratch: 7 * (Lx + 1)
-  int32_t* py;           // scratch: nsym * Ly, PY[a * Ly + j]
+  long long* diag;       // scratch: 7 * (Lx + 1), used when the rolling diagonals do not fit shared memory
+  int32_t* pbig;         // scratch: nsym * max(Lx, Ly): P[b * Lbig + col] of the side with more sequences
+  uint32_t* lst;         // scratch: nsym * max(Lx, Ly): lst[k * Lsmall + col] = letter << 24 | count
+  uint32_t* lnz;         // scratch: max(Lx, Ly): distinct letters in the small side's column
   uint8_t* dir;          // scratch: (Lx + Ly + 1) * (min(Lx, Ly) + 1) direction bytes, diagonal-major
   int32_t* path;         // scratch: 2 * (Lx + Ly): (X column, Y column) per merged column, last column first
   MsaResult* res;
@@ -81,6 +95,9 @@ struct MsaRows {         // final rows: every residue follows the column maps up
 
 constexpr long long kMsaNeg = -(1LL << 60);
 
+// bytes of the 7 rolling diagonals (3 H, 2 E, 2 F) of a merge with Lx columns along i
+TSQ_HD size_t msa_diag_bytes(uint32_t Lx) { return 7 * ((size_t)Lx + 1) * sizeof(long long); }
+
 TSQ_HD void msa_leaf_phase(const MsaLeaf& l, uint32_t nsym, int tid, int nt) {
   for (uint32_t col = (uint32_t)tid; col < l.len; col += (uint32_t)nt) {
     const uint32_t s = l.sym[col];
@@ -88,33 +105,59 @@ TSQ_HD void msa_leaf_phase(const MsaLeaf& l, uint32_t nsym, int tid, int nt) {
   }
 }
 
-// phase 1
-TSQ_HD void msa_py_phase(const MsaTask& t, const MsaConst& k, int tid, int nt) {
-  const uint32_t total = k.nsym * t.Ly;
-  for (uint32_t idx = (uint32_t)tid; idx < total; idx += (uint32_t)nt) {
-    const uint32_t a = idx / t.Ly, j = idx - a * t.Ly;
-    int32_t s = 0;
-    for (uint32_t b = 0; b < k.nsym; ++b) {
-      const uint32_t c = t.cy[(size_t)b * t.capy + j];
-      if (c) s += (int32_t)c * k.smat[a * k.nsym + b];
+// Which side is factored into letter scores: the one with more sequences (ties: X).
+TSQ_HD bool msa_big_is_x(const MsaTask& t) { return t.nx >= t.ny; }
+
+// phase 1.  One thread per column: its counts are fetched with independent loads (one L2 round trip, not
+// one per letter), then the letter scores come out of registers.
+constexpr int kMsaMaxSym = 24;
+TSQ_HD void msa_prep_phase(const MsaTask& t, const MsaConst& k, int tid, int nt) {
+  const bool bx = msa_big_is_x(t);
+  const uint32_t* cb = bx ? t.cx : t.cy;
+  const uint32_t* cs = bx ? t.cy : t.cx;
+  const uint32_t capb = bx ? t.capx : t.capy, caps = bx ? t.capy : t.capx;
+  const uint32_t Lb = bx ? t.Lx : t.Ly, Ls = bx ? t.Ly : t.Lx;
+  const uint32_t nsym = k.nsym;   // <= kMsaMaxSym
+  for (uint32_t col = (uint32_t)tid; col < Lb; col += (uint32_t)nt) {
+    uint32_t cnt[kMsaMaxSym];
+TSQ_UNROLL
+    for (int a = 0; a < kMsaMaxSym; ++a) cnt[a] = (uint32_t)a < nsym ? cb[(size_t)a * capb + col] : 0u;
+    for (uint32_t b = 0; b < nsym; ++b) {   // b: a letter of the small side
+      int32_t s = 0;
+TSQ_UNROLL
+      for (int a = 0; a < kMsaMaxSym; ++a)
+        // S(x letter, y letter): the big side's letter is the row index when the big side is X
+        if ((uint32_t)a < nsym) s += (int32_t)cnt[a] * k.smat[bx ? (uint32_t)a * nsym + b : b * nsym + (uint32_t)a];
+      t.pbig[(size_t)b * Lb + col] = s;
     }
-    t.py[idx] = s;
+  }
+  for (uint32_t col = (uint32_t)tid; col < Ls; col += (uint32_t)nt) {
+    uint32_t cnt[kMsaMaxSym];
+TSQ_UNROLL
+    for (int a = 0; a < kMsaMaxSym; ++a) cnt[a] = (uint32_t)a < nsym ? cs[(size_t)a * caps + col] : 0u;
+    uint32_t nz = 0;
+TSQ_UNROLL
+    for (int a = 0; a < kMsaMaxSym; ++a)
+      if (cnt[a]) { t.lst[(size_t)nz * Ls + col] = ((uint32_t)a << 24) | cnt[a]; ++nz; }
+    t.lnz[col] = nz;
   }
 }
 
 // phase 2, diagonal d in [0, Lx + Ly]
-TSQ_HD void msa_diag_phase(const MsaTask& t, const MsaConst& k, int d, int tid, int nt) {
+TSQ_HD void msa_diag_phase(const MsaTask& t, const MsaConst& k, long long* diag, int d, int tid, int nt) {
   const int m = (int)t.Lx, n = (int)t.Ly;
   const size_t stride = (size_t)m + 1;
   const long long w = (long long)t.nx * (long long)t.ny;
   const long long GO = w * k.go, GE = w * k.ge, GOE = GO + GE;
-  long long* const Hc = t.diag + (size_t)(d % 3) * stride;
-  const long long* const Hp1 = t.diag + (size_t)((d + 2) % 3) * stride;
-  const long long* const Hp2 = t.diag + (size_t)((d + 1) % 3) * stride;
-  long long* const Ec = t.diag + (size_t)(3 + (d & 1)) * stride;
-  const long long* const Ep1 = t.diag + (size_t)(3 + ((d + 1) & 1)) * stride;
-  long long* const Fc = t.diag + (size_t)(5 + (d & 1)) * stride;
-  const long long* const Fp1 = t.diag + (size_t)(5 + ((d + 1) & 1)) * stride;
+  long long* const Hc = diag + (size_t)(d % 3) * stride;
+  const long long* const Hp1 = diag + (size_t)((d + 2) % 3) * stride;
+  const long long* const Hp2 = diag + (size_t)((d + 1) % 3) * stride;
+  long long* const Ec = diag + (size_t)(3 + (d & 1)) * stride;
+  const long long* const Ep1 = diag + (size_t)(3 + ((d + 1) & 1)) * stride;
+  long long* const Fc = diag + (size_t)(5 + (d & 1)) * stride;
+  const long long* const Fp1 = diag + (size_t)(5 + ((d + 1) & 1)) * stride;
+  const bool bx = msa_big_is_x(t);
+  const uint32_t Lb = bx ? t.Lx : t.Ly, Ls = bx ? t.Ly : t.Lx;
   const int ilo = d > n ? d - n : 0;
   const int ihi = d < m ? d : m;
   const size_t ld = (size_t)(m < n ? m : n) + 1;
@@ -130,10 +173,12 @@ TSQ_HD void msa_diag_phase(const MsaTask& t, const MsaConst& k, int d, int tid, 
     } else if (j == 0) {
       H = F = -GO - (long long)i * GE; E = kMsaNeg; code = 2u | (i == 1 ? 8u : 0u);
     } else {
+      const uint32_t colb = (uint32_t)(bx ? i - 1 : j - 1), cols = (uint32_t)(bx ? j - 1 : i - 1);
+      const uint32_t nz = t.lnz[cols];
       long long sub = 0;
-      for (uint32_t a = 0; a < k.nsym; ++a) {
-        const uint32_t c = t.cx[(size_t)a * t.capx + (uint32_t)(i - 1)];
-        if (c) sub += (long long)c * (long long)t.py[(size_t)a * t.Ly + (uint32_t)(j - 1)];
+      for (uint32_t q = 0; q < nz; ++q) {
+        const uint32_t e = t.lst[(size_t)q * Ls + cols];
+        sub += (long long)(e & 0xffffffu) * (long long)t.pbig[(size_t)(e >> 24) * Lb + colb];
       }
       const long long hl = Hp1[i], hu = Hp1[i - 1], hd = Hp2[i - 1];
       const long long e_ext = Ep1[i] - GE, e_open = hl - GOE;
@@ -152,49 +197,76 @@ TSQ_HD void msa_diag_phase(const MsaTask& t, const MsaConst& k, int d, int tid, 
   }
 }
 
-// phase 3, one thread
-TSQ_HD void msa_walk_phase(const MsaTask& t) {
+// phase 3, one thread.  `diag` = where phase 2 kept the rolling diagonals.
+TSQ_HD void msa_walk_phase(const MsaTask& t, const long long* diag) {
+  constexpr int B = 16;   // direction bytes fetched per round trip
   const int m = (int)t.Lx, n = (int)t.Ly;
   const size_t ld = (size_t)(m < n ? m : n) + 1;
   int i = m, j = n, state = 0;
   uint32_t k = 0;
-  while (i > 0 || j > 0) {
-    if (i == 0) { t.path[2 * k] = -1; t.path[2 * k + 1] = j - 1; --j; ++k; continue; }
-    if (j == 0) { t.path[2 * k] = i - 1; t.path[2 * k + 1] = -1; --i; ++k; continue; }
-    const int d = i + j;
-    const uint32_t code = t.dir[(size_t)d * ld + (size_t)(i - (d > n ? d - n : 0))];
-    if (state == 0) {
-      const uint32_t src = code & 3u;
-      if (src == 0) { t.path[2 * k] = i - 1; t.path[2 * k + 1] = j - 1; --i; --j; ++k; }
-      else state = (int)src;
-    } else if (state == 1) {            // gap in X: the merged column takes Y's column only
-      t.path[2 * k] = -1; t.path[2 * k + 1] = j - 1; ++k;
-      if (code & 4u) state = 0;
-      --j;
-    } else {                            // gap in Y
-      t.path[2 * k] = i - 1; t.path[2 * k + 1] = -1; ++k;
-      if (code & 8u) state = 0;
-      --i;
+  while (i > 0 && j > 0) {
+    // the next B cells along the current run: down the diagonal, or along the gap run
+    const int di = state == 1 ? 0 : 1, dj = state == 2 ? 0 : 1;
+    uint32_t codes[B];
+TSQ_UNROLL
+    for (int q = 0; q < B; ++q) {
+      const int ii = i - q * di, jj = j - q * dj;
+      uint32_t c = 0;
+      if (ii > 0 && jj > 0) {
+        const int d = ii + jj;
+        c = t.dir[(size_t)d * ld + (size_t)(ii - (d > n ? d - n : 0))];
+      }
+      codes[q] = c;
+    }
+    bool turned = false;
+TSQ_UNROLL
+    for (int q = 0; q < B; ++q) {
+      if (turned || i == 0 || j == 0) continue;
+      const uint32_t code = codes[q];
+      if (state == 0) {
+        const uint32_t src = code & 3u;
+        if (src == 0) { t.path[2 * k] = i - 1; t.path[2 * k + 1] = j - 1; --i; --j; ++k; }
+        else { state = (int)src; turned = true; }       // same cell again, as the start of a gap run
+      } else if (state == 1) {            // gap in X: the merged column takes Y's column only
+        t.path[2 * k] = -1; t.path[2 * k + 1] = j - 1; ++k;
+        if (code & 4u) { state = 0; turned = true; }
+        --j;
+      } else {                            // gap in Y
+        t.path[2 * k] = i - 1; t.path[2 * k + 1] = -1; ++k;
+        if (code & 8u) { state = 0; turned = true; }
+        --i;
+      }
     }
   }
+  while (j > 0) { t.path[2 * k] = -1; t.path[2 * k + 1] = j - 1; --j; ++k; }
+  while (i > 0) { t.path[2 * k] = i - 1; t.path[2 * k + 1] = -1; --i; ++k; }
   t.res->len = k;
   t.res->pad = 0;
-  t.res->score = t.diag[(size_t)((m + n) % 3) * ((size_t)m + 1) + (size_t)m];   // H of the last diagonal, i = Lx
+  t.res->score = diag[(size_t)((m + n) % 3) * ((size_t)m + 1) + (size_t)m];   // H of the last diagonal, i = Lx
 }
 
 // phase 4
 TSQ_HD void msa_build_phase(const MsaTask& t, const MsaConst& k, int tid, int nt) {
   const uint32_t len = t.res->len;
+  const uint32_t nsym = k.nsym;
   for (uint32_t c = (uint32_t)tid; c < len; c += (uint32_t)nt) {
     const uint32_t s = len - 1 - c;
     const int32_t xi = t.path[2 * s], yj = t.path[2 * s + 1];
     if (xi >= 0) t.mapx[xi] = c;
     if (yj >= 0) t.mapy[yj] = c;
-    for (uint32_t a = 0; a < k.nsym; ++a) {
-      const uint32_t vx = xi >= 0 ? t.cx[(size_t)a * t.capx + (uint32_t)xi] : 0u;
-      const uint32_t vy = yj >= 0 ? t.cy[(size_t)a * t.capy + (uint32_t)yj] : 0u;
-      t.cn[(size_t)a * t.capn + c] = vx + vy;
+    uint32_t v[kMsaMaxSym];
+TSQ_UNROLL
+    for (int a = 0; a < kMsaMaxSym; ++a) {   // all loads before the first store: they overlap
+      uint32_t sum = 0;
+      if ((uint32_t)a < nsym) {
+        if (xi >= 0) sum += t.cx[(size_t)a * t.capx + (uint32_t)xi];
+        if (yj >= 0) sum += t.cy[(size_t)a * t.capy + (uint32_t)yj];
+      }
+      v[a] = sum;
     }
+TSQ_UNROLL
+    for (int a = 0; a < kMsaMaxSym; ++a)
+      if ((uint32_t)a < nsym) t.cn[(size_t)a * t.capn + c] = v[a];
   }
 }
 
@@ -218,17 +290,20 @@ __global__ void __launch_bounds__(128) msa_leaf_kernel(const MsaLeaf* leaves, ui
   for (uint32_t r = blockIdx.x; r < n; r += gridDim.x) msa_leaf_phase(leaves[r], nsym, (int)threadIdx.x, (int)blockDim.x);
 }
 
-__global__ void __launch_bounds__(1024) msa_merge_kernel(const MsaTask* tasks, const MsaConst k) {
+// smem_bytes: dynamic shared memory of the launch; a merge whose 7 rolling diagonals fit uses it.
+__global__ void __launch_bounds__(1024) msa_merge_kernel(const MsaTask* tasks, const MsaConst k, uint32_t smem_bytes) {
+  extern __shared__ long long msa_shared_diag[];
   const MsaTask t = tasks[blockIdx.x];
   const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
-  msa_py_phase(t, k, tid, nt);
+  long long* const diag = msa_diag_bytes(t.Lx) <= (size_t)smem_bytes ? msa_shared_diag : t.diag;
+  msa_prep_phase(t, k, tid, nt);
   __syncthreads();
   const int last = (int)(t.Lx + t.Ly);
   for (int d = 0; d <= last; ++d) {
-    msa_diag_phase(t, k, d, tid, nt);
+    msa_diag_phase(t, k, diag, d, tid, nt);
     __syncthreads();   // diagonal d complete and visible to the whole CTA before d + 1 starts
   }
-  if (tid == 0) msa_walk_phase(t);
+  if (tid == 0) msa_walk_phase(t, diag);
   __syncthreads();
   msa_build_phase(t, k, tid, nt);
 }

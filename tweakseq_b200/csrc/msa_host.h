@@ -24,7 +24,8 @@ class MsaDevice {
   virtual bool d2h(void* dst, const void* src, size_t bytes) = 0;   // complete on return, after all earlier work
   virtual bool fill(void* dst, int byte, size_t bytes) = 0;
   virtual bool launch_leaves(const MsaLeaf* d_leaves, uint32_t n, uint32_t nsym) = 0;
-  virtual bool launch_merges(const MsaTask* d_tasks, uint32_t count, uint32_t threads, const MsaConst& k) = 0;
+  // smem_bytes: shared memory per CTA for the rolling diagonals (merges that need more use their global scratch)
+  virtual bool launch_merges(const MsaTask* d_tasks, uint32_t count, uint32_t threads, uint32_t smem_bytes, const MsaConst& k) = 0;
   virtual bool launch_rows(const MsaRows& p) = 0;
 };
 
@@ -53,11 +54,13 @@ struct MsaOut {
 enum { MSA_OK = 0, MSA_NOMEM = 1, MSA_DEVICE = 2, MSA_BAD_TREE = 3 };
 
 inline size_t msa_align(size_t x) { return (x + 255) & ~(size_t)255; }
+constexpr size_t kMsaSmemLimit = 200 * 1024;   // of the 227 KB a CTA may have on sm_100
 
 inline int msa_progressive(MsaDevice& dev, const MsaJob& job, MsaOut& out) {
   const uint32_t n = job.n, nsym = job.nsym;
   out = MsaOut();
   if (n == 0) return MSA_OK;
+  if (n >= (1u << 24) || nsym > (uint32_t)kMsaMaxSym) return MSA_BAD_TREE;   // column counts share a word with their letter (msa_prep_phase)
   const uint32_t nnodes = 2 * n - 1, NONE = 0xffffffffu;
   if (job.left.size() != n - 1 || job.right.size() != n - 1) return MSA_BAD_TREE;
 
@@ -125,10 +128,18 @@ inline int msa_progressive(MsaDevice& dev, const MsaJob& job, MsaOut& out) {
   uint32_t slot = 0;   // results are stored in launch order, so a batch reads back one contiguous range
   std::vector<MsaTask> tasks;
   std::vector<MsaResult> res;
-  auto scratch_of = [&](uint32_t Lx, uint32_t Ly) -> size_t {
-    const size_t mn = std::min(Lx, Ly);
-    return msa_align(7 * ((size_t)Lx + 1) * 8) + msa_align(std::max<size_t>((size_t)nsym * Ly, 1) * 4) +
-           msa_align(((size_t)Lx + Ly + 1) * (mn + 1)) + msa_align(std::max<size_t>(2 * ((size_t)Lx + Ly), 1) * 4);
+  struct Scratch { size_t diag, pbig, lst, lnz, dir, path, total; };
+  auto scratch_of = [&](uint32_t Lx, uint32_t Ly) -> Scratch {
+    const size_t mn = std::min(Lx, Ly), mx = std::max<size_t>(std::max(Lx, Ly), 1);
+    Scratch q;
+    q.diag = msa_align(msa_diag_bytes(Lx));
+    q.pbig = msa_align((size_t)nsym * mx * 4);
+    q.lst = msa_align((size_t)nsym * mx * 4);
+    q.lnz = msa_align(mx * 4);
+    q.dir = msa_align(((size_t)Lx + Ly + 1) * (mn + 1));
+    q.path = msa_align(std::max<size_t>(2 * ((size_t)Lx + Ly), 1) * 4);
+    q.total = q.diag + q.pbig + q.lst + q.lnz + q.dir + q.path;
+    return q;
   };
   for (uint32_t lv = 1; lv <= nlevels; lv++) {
     const std::vector<uint32_t>& ms = by_level[lv];
@@ -137,18 +148,20 @@ inline int msa_progressive(MsaDevice& dev, const MsaJob& job, MsaOut& out) {
       // batch [b, e): as many merges of this level as the scratch budget takes
       size_t e = b, bytes = msa_align(sizeof(MsaTask));
       uint32_t longest = 0;
+      size_t smem = 0;
       while (e < ms.size()) {
         const uint32_t t = ms[e], Lx = ncol[job.left[t]], Ly = ncol[job.right[t]];
-        const size_t need = scratch_of(Lx, Ly) + msa_align(sizeof(MsaTask));
+        const size_t need = scratch_of(Lx, Ly).total + msa_align(sizeof(MsaTask));
         if (e > b && bytes + need > job.scratch_budget) break;
         bytes += need;
         longest = std::max(longest, std::min(Lx, Ly) + 1);
+        if (msa_diag_bytes(Lx) <= kMsaSmemLimit) smem = std::max(smem, msa_diag_bytes(Lx));
         e++;
       }
       const size_t count = e - b;
       const size_t head = msa_align(count * sizeof(MsaTask));
       bytes = head;
-      for (size_t q = b; q < e; q++) bytes += scratch_of(ncol[job.left[ms[q]]], ncol[job.right[ms[q]]]);
+      for (size_t q = b; q < e; q++) bytes += scratch_of(ncol[job.left[ms[q]]], ncol[job.right[ms[q]]]).total;
       char* sc = (char*)dev.scratch(bytes);
       if (!sc) return MSA_NOMEM;
       tasks.assign(count, MsaTask{});
@@ -168,15 +181,18 @@ inline int msa_progressive(MsaDevice& dev, const MsaJob& job, MsaOut& out) {
         k.Lx = Lx; k.Ly = Ly; k.nx = size[x]; k.ny = size[y];
         k.mapx = p + pw; k.mapy = p + pw + Lx;
         nodemap[x] = k.mapx; nodemap[y] = k.mapy;
-        k.diag = (long long*)(sc + at);  at += msa_align(7 * ((size_t)Lx + 1) * 8);
-        k.py = (int32_t*)(sc + at);      at += msa_align(std::max<size_t>((size_t)nsym * Ly, 1) * 4);
-        k.dir = (uint8_t*)(sc + at);     at += msa_align(((size_t)Lx + Ly + 1) * ((size_t)std::min(Lx, Ly) + 1));
-        k.path = (int32_t*)(sc + at);    at += msa_align(std::max<size_t>(2 * ((size_t)Lx + Ly), 1) * 4);
+        const Scratch sz = scratch_of(Lx, Ly);
+        k.diag = (long long*)(sc + at);  at += sz.diag;
+        k.pbig = (int32_t*)(sc + at);    at += sz.pbig;
+        k.lst = (uint32_t*)(sc + at);    at += sz.lst;
+        k.lnz = (uint32_t*)(sc + at);    at += sz.lnz;
+        k.dir = (uint8_t*)(sc + at);     at += sz.dir;
+        k.path = (int32_t*)(sc + at);    at += sz.path;
         k.res = d_res + slot + (q - b);
       }
       if (!dev.h2d(sc, tasks.data(), count * sizeof(MsaTask))) return MSA_DEVICE;
       const uint32_t threads = std::min<uint32_t>(1024u, std::max<uint32_t>(64u, (longest + 31u) & ~31u));
-      if (!dev.launch_merges((const MsaTask*)sc, (uint32_t)count, threads, kc)) return MSA_DEVICE;
+      if (!dev.launch_merges((const MsaTask*)sc, (uint32_t)count, threads, (uint32_t)smem, kc)) return MSA_DEVICE;
       out.launches++;
       res.resize(count);
       if (!dev.d2h(res.data(), d_res + slot, count * sizeof(MsaResult))) return MSA_DEVICE;

@@ -1367,8 +1367,8 @@ class CudaMsaDevice : public tsq::MsaDevice {
   }
   bool fill(void* d, int v, size_t b) override { return ok(cudaMemsetAsync(d, v, b, s_)); }
   bool launch_leaves(const tsq::MsaLeaf* l, uint32_t n, uint32_t nsym) override { return ok(tsq::msa_leaf_launch(l, n, nsym, s_)); }
-  bool launch_merges(const tsq::MsaTask* t, uint32_t count, uint32_t threads, const tsq::MsaConst& k) override {
-    return ok(tsq::msa_merge_launch(t, count, threads, k, s_));
+  bool launch_merges(const tsq::MsaTask* t, uint32_t count, uint32_t threads, uint32_t smem_bytes, const tsq::MsaConst& k) override {
+    return ok(tsq::msa_merge_launch(t, count, threads, smem_bytes, k, s_));
   }
   bool launch_rows(const tsq::MsaRows& p) override { return ok(tsq::msa_rows_launch(p, s_)); }
 

@@ -327,10 +327,15 @@ cudaError_t msa_leaf_launch(const MsaLeaf* d_leaves, uint32_t n, uint32_t nsym, 
   return cudaGetLastError();
 }
 
-cudaError_t msa_merge_launch(const MsaTask* d_tasks, uint32_t count, uint32_t threads, const MsaConst& k, cudaStream_t stream) {
+cudaError_t msa_merge_launch(const MsaTask* d_tasks, uint32_t count, uint32_t threads, uint32_t smem_bytes, const MsaConst& k,
+                             cudaStream_t stream) {
   if (count == 0) return cudaSuccess;
-  if (threads < 32 || threads > 1024 || (threads & 31u)) return cudaErrorInvalidValue;
-  msa_merge_kernel<<<count, threads, 0, stream>>>(d_tasks, k);
+  if (threads < 32 || threads > 1024 || (threads & 31u) || smem_bytes > 227u * 1024u) return cudaErrorInvalidValue;
+  if (smem_bytes > 48u * 1024u) {   // above the default limit the kernel must opt in (per device, cheap to repeat)
+    cudaError_t e = cudaFuncSetAttribute(msa_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+  }
+  msa_merge_kernel<<<count, threads, smem_bytes, stream>>>(d_tasks, k, smem_bytes);
   return cudaGetLastError();
 }
 

@@ -57,7 +57,8 @@ cudaError_t traceback_launch(const TbParams& p, cudaStream_t stream);
 // Progressive alignment along the guide tree (msa.cuh): leaf profiles, one launch per batch of
 // independent merges (one CTA each, `threads` per CTA), final rows.
 cudaError_t msa_leaf_launch(const MsaLeaf* d_leaves, uint32_t n, uint32_t nsym, cudaStream_t stream);
-cudaError_t msa_merge_launch(const MsaTask* d_tasks, uint32_t count, uint32_t threads, const MsaConst& k, cudaStream_t stream);
+cudaError_t msa_merge_launch(const MsaTask* d_tasks, uint32_t count, uint32_t threads, uint32_t smem_bytes, const MsaConst& k,
+                             cudaStream_t stream);
 cudaError_t msa_rows_launch(const MsaRows& p, cudaStream_t stream);
 
 // Builds the 32-way interleaved subject database of the packed kernel from the linear residues:
