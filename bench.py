@@ -343,6 +343,15 @@ def main():
                 line["guide_tree"] = {"algorithm": "UPGMA", "n": len(seqs), "gpu_ms": run.ctx.stats()["tree_ms"]}
             except Exception as e:   # never let the extra row break the contract line
                 line["guide_tree"] = {"error": str(e)}
+            # the step after the tree: progressive alignment along it (tsq_msa), wall time of the call
+            try:
+                rows, _ = run.ctx.msa()
+                mst = run.ctx.stats()
+                line["msa"] = {"algorithm": "progressive, sum-of-pairs profile Gotoh along the UPGMA tree", "n": len(seqs),
+                               "columns": len(rows[0]) if rows else 0, "gpu_ms": mst["msa_ms"],
+                               "note": "plan + kernels + copies of one tsq_msa call; one CTA per merge, one launch per tree level"}
+            except Exception as e:
+                line["msa"] = {"error": str(e)}
         if world == 1 and args.workload == "c2":
             # the other "next" row: identity-aware scoring, 32-bit inter-task kernel
             try:
