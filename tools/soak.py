@@ -1,6 +1,6 @@
 """Randomised soak of the CUDA path against the CPU oracle: random alphabets, matrices, gap models,
 length mixes (empties, singletons, strip/pass boundaries, long tails), kernel-selection flags,
-identity mode, partitions, guide tree and traceback.  Runs until --seconds elapse; prints one line
+identity mode, partitions, guide tree, progressive alignment and traceback.  Runs until --seconds elapse; prints one line
 per trial class and a final summary; exits non-zero at the first mismatch (with the seed)."""
 import argparse
 import os
@@ -90,6 +90,12 @@ def trial(seed, counts):
                 rl, rr, rh = o.upgma(rd, n)
                 assert (left == rl).all() and (right == rr).all() and height.tobytes() == rh.tobytes(), "tree " + tag
                 counts["trees"] += 1
+                if n <= 48 and max(map(len, seqs)) <= 700:       # progressive alignment along that tree
+                    rows, order = ctx.msa()
+                    want, _ = o.msa(enc, mat, gov, ge, left, right, alphabet)
+                    assert rows == want, "msa " + tag
+                    assert sorted(order) == list(range(n)), "msa order " + tag
+                    counts["alignments"] += 1
             for _ in range(3):
                 i, j = int(rng.integers(0, n)), int(rng.integers(0, n))
                 if len(enc[i]) * len(enc[j]) > 4_000_000:
@@ -126,7 +132,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=120)
     ap.add_argument("--seed", type=int, default=1)
     a = ap.parse_args()
-    counts = dict(trials=0, pairs=0, cells=0, trees=0, tracebacks=0, partitions=0, range_refusals=0)
+    counts = dict(trials=0, pairs=0, cells=0, trees=0, alignments=0, tracebacks=0, partitions=0, range_refusals=0)
     t0 = time.time()
     seed = a.seed
     while time.time() - t0 < a.seconds:
