@@ -49,6 +49,20 @@ class EmulDevice : public tsq::MsaDevice {
     if (order) for (int t = 0; t < nt; t++) f(t);
     else for (int t = nt - 1; t >= 0; t--) f(t);
   }
+  // the body of msa_merge_cta<T>, barrier by barrier
+  template <typename T>
+  void sweep(const tsq::MsaTask& t, const tsq::MsaConst& k, void* shared, uint32_t smem_bytes, int nt) {
+    void* const diag = tsq::msa_diag_bytes(t.Lx, sizeof(T) == 4) <= (size_t)smem_bytes ? shared : (void*)t.diag;   // as the kernel decides
+    each_thread(nt, [&](int tid) { tsq::msa_prep_phase(t, k, tid, nt); });
+    const tsq::MsaSweep<T> sw = tsq::msa_sweep_init<T>(t, k, diag);
+    const int last = sw.m + sw.n;
+    int hc = 0;
+    for (int d = 0; d <= last; ++d) {
+      each_thread(nt, [&](int tid) { tsq::msa_diag_phase<T>(sw, d, hc, tid, nt); });
+      hc = hc == 2 ? 0 : hc + 1;
+    }
+    tsq::msa_walk_phase(t, tsq::msa_final_score<T>(sw));
+  }
   bool launch_leaves(const tsq::MsaLeaf* l, uint32_t n, uint32_t nsym) override {
     for (uint32_t r = 0; r < n; r++) each_thread(128, [&](int t) { tsq::msa_leaf_phase(l[r], nsym, t, 128); });
     return true;
@@ -62,11 +76,8 @@ class EmulDevice : public tsq::MsaDevice {
     for (uint32_t b = 0; b < count; b++) {
       const tsq::MsaTask t = tasks[b];
       std::fill(shared.begin(), shared.end(), (long long)0x5C5C5C5C5C5C5C5CLL);   // a new CTA: shared memory is garbage
-      long long* const diag = tsq::msa_diag_bytes(t.Lx) <= (size_t)smem_bytes ? shared.data() : t.diag;   // as the kernel decides
-      each_thread(nt, [&](int tid) { tsq::msa_prep_phase(t, k, tid, nt); });
-      const int last = (int)(t.Lx + t.Ly);
-      for (int d = 0; d <= last; ++d) each_thread(nt, [&](int tid) { tsq::msa_diag_phase(t, k, diag, d, tid, nt); });
-      tsq::msa_walk_phase(t, diag);
+      if (t.narrow) sweep<int32_t>(t, k, shared.data(), smem_bytes, nt);
+      else sweep<long long>(t, k, shared.data(), smem_bytes, nt);
       each_thread(nt, [&](int tid) { tsq::msa_build_phase(t, k, tid, nt); });
     }
     return true;
@@ -88,6 +99,7 @@ extern "C" int msa_emul(const uint8_t* seqs, const uint64_t* offs, const uint32_
   dev.order = ascending;
   dev.force_threads = force_threads & 0xffffu;
   dev.no_smem = (force_threads >> 16) & 1u;
+  const bool force_wide = (force_threads >> 17) & 1u;
   tsq::MsaJob job;
   job.n = n;
   job.d_sym = seqs;
@@ -104,6 +116,7 @@ extern "C" int msa_emul(const uint8_t* seqs, const uint64_t* offs, const uint32_
   job.ge = ge;
   job.letters = letters;
   if (scratch_budget) job.scratch_budget = scratch_budget;
+  job.force_wide = force_wide;
   tsq::MsaOut out;
   const int rc = tsq::msa_progressive(dev, job, out);
   if (rc != tsq::MSA_OK) return rc;

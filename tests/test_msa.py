@@ -182,7 +182,8 @@ def test_kernel_phases_on_cpu_equal_oracle_random_trees(emul, alphabet):
         left, right = random_tree(rng, n) if n > 1 else (np.zeros(0, np.uint32),) * 2
         enc = [o.encode(s, alphabet) for s in seqs]
         want, wsc = o.msa(enc, mat, go, ge, left, right, alphabet)
-        threads = [0, 1, 32, 96, 1024][trial % 5] | ((trial // 5) & 1) << 16   # bit 16: rolling diagonals in global scratch
+        # bit 16: rolling diagonals in global scratch; bit 17: int64 sweep even where int32 would do
+        threads = [0, 1, 32, 96, 1024][trial % 5] | ((trial // 5) & 1) << 16 | ((trial // 3) & 1) << 17
         budget = [0, 1, 1 << 16][trial % 3]   # 1 byte: one merge per launch
         got, gsc, order, launches, levels = emul(enc, mat, go, ge, left, right, alphabet, budget, threads, trial & 1)
         assert got == want
@@ -354,3 +355,43 @@ def test_kernel_phases_on_cpu_degenerate_inputs(emul):
     rows, sc, _, _, _ = emul([o.encode(""), o.encode("WW")], mat, 11, 1, [0], [1])
     assert rows == ["--", "WW"] and sc.tolist() == [-(11 + 2)]
     assert o.msa([o.encode(""), o.encode("WW")], mat, 11, 1, [0], [1])[0] == ["--", "WW"]
+
+
+def balanced(n):
+    """Pairs neighbours level by level: ((0,1),(2,3)),... -- the widest clusters meet at the root."""
+    left, right, alive, nxt = [], [], list(range(n)), n
+    while len(alive) > 1:
+        new = []
+        for a in range(0, len(alive) - 1, 2):
+            left.append(alive[a]); right.append(alive[a + 1]); new.append(nxt); nxt += 1
+        if len(alive) & 1:
+            new.append(alive[-1])
+        alive = new
+    return np.array(left, np.uint32), np.array(right, np.uint32)
+
+
+def test_int32_sweep_is_used_only_inside_its_range_bound(emul):
+    """Boundary cells reach -|X||Y| (go + L ge): with the largest gap costs the ABI admits, a 47 x 47 root
+    merge of ~100-column clusters sits just inside the +-2^29 bound of the int32 sweep (msa_fits_narrow) and
+    a 256 x 256 one would wrap 32 bits.  The oracle is int64 throughout, so a wrapped int32 anywhere shows
+    as different rows or scores."""
+    rng = np.random.default_rng(21)
+    mat = o.matrix(o.PROTEIN)
+    assert 47 * 47 * (4096 + 95 * 1024) > (1 << 27) and 256 * 256 * (4096 + 95 * 1024) > (1 << 31)
+    for n in (94, 512):
+        seqs = ["".join(rng.choice(list(PROT[:20]), int(rng.integers(95, 100)))) for _ in range(n)]
+        enc = [o.encode(s) for s in seqs]
+        left, right = balanced(n)
+        want, wsc = o.msa(enc, mat, 4096, 1024, left, right)
+        got, gsc, *_ = emul(enc, mat, 4096, 1024, left, right)
+        assert got == want and gsc.tolist() == wsc.tolist()
+
+
+@pytest.mark.gpu
+def test_gpu_msa_int32_and_int64_sweeps_at_the_range_boundary():
+    rng = np.random.default_rng(22)
+    for n in (94, 512):
+        seqs = ["".join(rng.choice(list(PROT[:20]), int(rng.integers(95, 100)))) for _ in range(n)]
+        rows, order, left, right, _ = _gpu_msa(seqs, go=4096, ge=1024)
+        want, wsc = o.msa([o.encode(s) for s in seqs], o.matrix(0), 4096, 1024, left, right)
+        assert rows == want

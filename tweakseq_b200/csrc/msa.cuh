@@ -21,8 +21,9 @@
 //      one multiply-add per distinct letter of the small side's column -- exactly one when it is a
 //      single sequence, the common case of a guide tree over related sequences (a caterpillar).
 //   2. anti-diagonal sweep, one barrier per diagonal: H (3 rolling diagonals), E, F (2 each) indexed by
-//      i, in SHARED memory when 7 (Lx + 1) words fit (an L2 round trip per diagonal otherwise); one
-//      direction byte per cell, diagonal-major (traceback.cuh)
+//      i, in SHARED memory when 7 (Lx + 1) scores fit (an L2 round trip per diagonal otherwise); one
+//      direction byte per cell, diagonal-major (traceback.cuh).  Scores are int32 when the merge's
+//      range bound allows (msa_fits_narrow: half the instructions of int64 on a 32-bit datapath)
 //   3. thread 0 walks the path back from (Lx, Ly): per merged column its X column and Y column or -1.
 //      The direction bytes sit in L2, so it fetches the next 16 along the current run (diagonal, or a
 //      gap run) at once and consumes them from registers: one round trip per run piece, not per column
@@ -40,8 +41,10 @@
 #endif
 #if defined(__CUDA_ARCH__)
 #define TSQ_UNROLL _Pragma("unroll")
+#define TSQ_NO_UNROLL _Pragma("unroll 1")
 #else
 #define TSQ_UNROLL
+#define TSQ_NO_UNROLL
 #endif
 
 namespace tsq {
@@ -65,9 +68,11 @@ struct MsaTask {         // one merge: X = left child, Y = right child
   uint32_t capx, capy, capn;
   uint32_t Lx, Ly;       // columns of X and Y
   uint32_t nx, ny;       // sequences in X and Y
+  uint32_t narrow;       // every H, E, F of this merge fits 30 bits (msa_fits_narrow): sweep in int32, else int64
+  uint32_t pad;
   uint32_t* mapx;        // Lx entries: X column -> merged column
   uint32_t* mapy;        // Ly entries
-  long long* diag;       // scratch: 7 * (Lx + 1), used when the rolling diagonals do not fit shared memory
+  long long* diag;       // scratch: 7 * (Lx + 1) scores, used when the rolling diagonals do not fit shared memory
   int32_t* pbig;         // scratch: nsym * max(Lx, Ly): P[b * Lbig + col] of the side with more sequences
   uint32_t* lst;         // scratch: nsym * max(Lx, Ly): lst[k * Lsmall + col] = letter << 24 | count
   uint32_t* lnz;         // scratch: max(Lx, Ly): distinct letters in the small side's column
@@ -93,10 +98,21 @@ struct MsaRows {         // final rows: every residue follows the column maps up
   char letters[24];
 };
 
-constexpr long long kMsaNeg = -(1LL << 60);
+// "minus infinity" of a score type: far below every real value, and NEG - GE still representable
+template <typename T> struct MsaNeg;
+template <> struct MsaNeg<long long> { static constexpr long long v = -(1LL << 60); };
+template <> struct MsaNeg<int32_t> { static constexpr int32_t v = -(1 << 30); };
 
 // bytes of the 7 rolling diagonals (3 H, 2 E, 2 F) of a merge with Lx columns along i
-TSQ_HD size_t msa_diag_bytes(uint32_t Lx) { return 7 * ((size_t)Lx + 1) * sizeof(long long); }
+TSQ_HD size_t msa_diag_bytes(uint32_t Lx, bool narrow) { return 7 * ((size_t)Lx + 1) * (narrow ? sizeof(int32_t) : sizeof(long long)); }
+
+// Whether the whole DP of a merge stays inside +-2^29, so that the sweep may run in int32 with -2^30 as
+// minus infinity: |H|, |E|, |F| <= |X||Y| (max|S| (Lx + Ly) + 2 go + (Lx + Ly + 2) ge).
+TSQ_HD bool msa_fits_narrow(uint32_t nx, uint32_t ny, uint32_t Lx, uint32_t Ly, int32_t max_abs_s, int32_t go, int32_t ge) {
+  const long long w = (long long)nx * (long long)ny;
+  const long long per = (long long)max_abs_s * ((long long)Lx + Ly) + 2LL * go + ((long long)Lx + Ly + 2) * ge;
+  return w < (1LL << 29) && per < (1LL << 29) && w * per < (1LL << 29);
+}
 
 TSQ_HD void msa_leaf_phase(const MsaLeaf& l, uint32_t nsym, int tid, int nt) {
   for (uint32_t col = (uint32_t)tid; col < l.len; col += (uint32_t)nt) {
@@ -143,47 +159,78 @@ TSQ_UNROLL
   }
 }
 
-// phase 2, diagonal d in [0, Lx + Ly]
-TSQ_HD void msa_diag_phase(const MsaTask& t, const MsaConst& k, long long* diag, int d, int tid, int nt) {
-  const int m = (int)t.Lx, n = (int)t.Ly;
-  const size_t stride = (size_t)m + 1;
+// phase 2.  Loop invariants of one merge's sweep, set up once per thread.
+template <typename T>
+struct MsaSweep {
+  T GO, GE, GOE;
+  int m, n;              // Lx, Ly
+  uint32_t stride;       // m + 1: one rolling diagonal
+  uint32_t ld;           // min(m, n) + 1: one diagonal of direction bytes
+  uint32_t Lb, Ls;       // columns of the big / small side
+  bool bx;               // the big side is X
+  const uint32_t* lnz;
+  const uint32_t* lst;
+  const int32_t* pbig;
+  uint8_t* dir;
+  T* diag;               // 3 H, 2 E, 2 F diagonals
+};
+
+template <typename T>
+TSQ_HD MsaSweep<T> msa_sweep_init(const MsaTask& t, const MsaConst& k, void* diag) {
+  MsaSweep<T> s;
   const long long w = (long long)t.nx * (long long)t.ny;
-  const long long GO = w * k.go, GE = w * k.ge, GOE = GO + GE;
-  long long* const Hc = diag + (size_t)(d % 3) * stride;
-  const long long* const Hp1 = diag + (size_t)((d + 2) % 3) * stride;
-  const long long* const Hp2 = diag + (size_t)((d + 1) % 3) * stride;
-  long long* const Ec = diag + (size_t)(3 + (d & 1)) * stride;
-  const long long* const Ep1 = diag + (size_t)(3 + ((d + 1) & 1)) * stride;
-  long long* const Fc = diag + (size_t)(5 + (d & 1)) * stride;
-  const long long* const Fp1 = diag + (size_t)(5 + ((d + 1) & 1)) * stride;
-  const bool bx = msa_big_is_x(t);
-  const uint32_t Lb = bx ? t.Lx : t.Ly, Ls = bx ? t.Ly : t.Lx;
-  const int ilo = d > n ? d - n : 0;
-  const int ihi = d < m ? d : m;
-  const size_t ld = (size_t)(m < n ? m : n) + 1;
-  uint8_t* const drow = t.dir + (size_t)d * ld - ilo;
+  s.GO = (T)(w * k.go); s.GE = (T)(w * k.ge); s.GOE = (T)(w * k.go + w * k.ge);
+  s.m = (int)t.Lx; s.n = (int)t.Ly;
+  s.stride = t.Lx + 1;
+  s.ld = (t.Lx < t.Ly ? t.Lx : t.Ly) + 1;
+  s.bx = msa_big_is_x(t);
+  s.Lb = s.bx ? t.Lx : t.Ly; s.Ls = s.bx ? t.Ly : t.Lx;
+  s.lnz = t.lnz; s.lst = t.lst; s.pbig = t.pbig; s.dir = t.dir;
+  s.diag = (T*)diag;
+  return s;
+}
+
+// H(Lx, Ly) after the sweep: diagonal Lx + Ly sits in H buffer (Lx + Ly) % 3
+template <typename T>
+TSQ_HD long long msa_final_score(const MsaSweep<T>& s) {
+  return (long long)s.diag[(size_t)((s.m + s.n) % 3) * s.stride + (size_t)s.m];
+}
+
+// One diagonal d in [0, Lx + Ly]; hc = d % 3 (the caller counts it along: no division per diagonal).
+template <typename T>
+TSQ_HD void msa_diag_phase(const MsaSweep<T>& s, int d, int hc, int tid, int nt) {
+  constexpr T NEG = MsaNeg<T>::v;
+  const int h1 = hc ? hc - 1 : 2, h2 = h1 ? h1 - 1 : 2;   // buffers of diagonals d-1, d-2
+  const int par = d & 1;
+  T* const Hc = s.diag + (size_t)hc * s.stride;
+  const T* const Hp1 = s.diag + (size_t)h1 * s.stride;
+  const T* const Hp2 = s.diag + (size_t)h2 * s.stride;
+  T* const Ec = s.diag + (size_t)(3 + par) * s.stride;
+  const T* const Ep1 = s.diag + (size_t)(4 - par) * s.stride;
+  T* const Fc = s.diag + (size_t)(5 + par) * s.stride;
+  const T* const Fp1 = s.diag + (size_t)(6 - par) * s.stride;
+  const int ilo = d > s.n ? d - s.n : 0;
+  const int ihi = d < s.m ? d : s.m;
+  uint8_t* const drow = s.dir + (size_t)d * s.ld - ilo;
   for (int i = ilo + tid; i <= ihi; i += nt) {
     const int j = d - i;
-    long long H, E, F;
+    T H, E, F;
     uint32_t code;
-    if (i == 0 && j == 0) {
-      H = 0; E = kMsaNeg; F = kMsaNeg; code = 0;
-    } else if (i == 0) {
-      H = E = -GO - (long long)j * GE; F = kMsaNeg; code = 1u | (j == 1 ? 4u : 0u);
-    } else if (j == 0) {
-      H = F = -GO - (long long)i * GE; E = kMsaNeg; code = 2u | (i == 1 ? 8u : 0u);
-    } else {
-      const uint32_t colb = (uint32_t)(bx ? i - 1 : j - 1), cols = (uint32_t)(bx ? j - 1 : i - 1);
-      const uint32_t nz = t.lnz[cols];
-      long long sub = 0;
-      for (uint32_t q = 0; q < nz; ++q) {
-        const uint32_t e = t.lst[(size_t)q * Ls + cols];
-        sub += (long long)(e & 0xffffffu) * (long long)t.pbig[(size_t)(e >> 24) * Lb + colb];
+    if (i != 0 && j != 0) {
+      const uint32_t colb = (uint32_t)(s.bx ? i - 1 : j - 1), cols = (uint32_t)(s.bx ? j - 1 : i - 1);
+      const uint32_t nz = s.lnz[cols];
+      const uint32_t* le = s.lst + cols;
+      const int32_t* pb = s.pbig + colb;
+      T sub = 0;
+      TSQ_NO_UNROLL   // usually one to three letters: an unrolled body costs more in remainder branches than it saves
+      for (uint32_t q = 0; q < nz; ++q, le += s.Ls) {
+        const uint32_t e = *le;
+        sub += (T)(e & 0xffffffu) * (T)pb[(e >> 24) * s.Lb];   // nsym * Lb words: a 32-bit offset
       }
-      const long long hl = Hp1[i], hu = Hp1[i - 1], hd = Hp2[i - 1];
-      const long long e_ext = Ep1[i] - GE, e_open = hl - GOE;
-      const long long f_ext = Fp1[i - 1] - GE, f_open = hu - GOE;
-      const long long dg = hd + sub;
+      const T hl = Hp1[i], hu = Hp1[i - 1], hd = Hp2[i - 1];
+      const T e_ext = Ep1[i] - s.GE, e_open = hl - s.GOE;
+      const T f_ext = Fp1[i - 1] - s.GE, f_open = hu - s.GOE;
+      const T dg = hd + sub;
       const bool eo = e_open >= e_ext, fo = f_open >= f_ext;
       E = eo ? e_open : e_ext;
       F = fo ? f_open : f_ext;
@@ -191,14 +238,20 @@ TSQ_HD void msa_diag_phase(const MsaTask& t, const MsaConst& k, long long* diag,
       if (E > H) H = E;
       if (F > H) H = F;
       code = (H == dg ? 0u : (H == E ? 1u : 2u)) | (eo ? 4u : 0u) | (fo ? 8u : 0u);
+    } else if (i == 0 && j == 0) {
+      H = 0; E = NEG; F = NEG; code = 0;
+    } else if (i == 0) {
+      H = E = (T)(-s.GO - (T)j * s.GE); F = NEG; code = 1u | (j == 1 ? 4u : 0u);
+    } else {
+      H = F = (T)(-s.GO - (T)i * s.GE); E = NEG; code = 2u | (i == 1 ? 8u : 0u);
     }
     Hc[i] = H; Ec[i] = E; Fc[i] = F;
     drow[i] = (uint8_t)code;
   }
 }
 
-// phase 3, one thread.  `diag` = where phase 2 kept the rolling diagonals.
-TSQ_HD void msa_walk_phase(const MsaTask& t, const long long* diag) {
+// phase 3, one thread.  score = H(Lx, Ly) (msa_final_score).
+TSQ_HD void msa_walk_phase(const MsaTask& t, long long score) {
   constexpr int B = 16;   // direction bytes fetched per round trip
   const int m = (int)t.Lx, n = (int)t.Ly;
   const size_t ld = (size_t)(m < n ? m : n) + 1;
@@ -242,7 +295,7 @@ TSQ_UNROLL
   while (i > 0) { t.path[2 * k] = i - 1; t.path[2 * k + 1] = -1; --i; ++k; }
   t.res->len = k;
   t.res->pad = 0;
-  t.res->score = diag[(size_t)((m + n) % 3) * ((size_t)m + 1) + (size_t)m];   // H of the last diagonal, i = Lx
+  t.res->score = score;
 }
 
 // phase 4
@@ -290,22 +343,46 @@ __global__ void __launch_bounds__(128) msa_leaf_kernel(const MsaLeaf* leaves, ui
   for (uint32_t r = blockIdx.x; r < n; r += gridDim.x) msa_leaf_phase(leaves[r], nsym, (int)threadIdx.x, (int)blockDim.x);
 }
 
-// smem_bytes: dynamic shared memory of the launch; a merge whose 7 rolling diagonals fit uses it.
-__global__ void __launch_bounds__(1024) msa_merge_kernel(const MsaTask* tasks, const MsaConst k, uint32_t smem_bytes) {
-  extern __shared__ long long msa_shared_diag[];
-  const MsaTask t = tasks[blockIdx.x];
-  const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
-  long long* const diag = msa_diag_bytes(t.Lx) <= (size_t)smem_bytes ? msa_shared_diag : t.diag;
-  msa_prep_phase(t, k, tid, nt);
-  __syncthreads();
-  const int last = (int)(t.Lx + t.Ly);
+// One merge by one CTA, in score type T.  smem_bytes: dynamic shared memory of the launch; a merge whose 7
+// rolling diagonals fit uses it, any other its global scratch.
+// The sweep of one merge with its rolling diagonals at `diag`.  Called once with the shared-memory array
+// and once with the global scratch, so that each copy of the loop knows its address space (LDS/STS with
+// 32-bit offsets instead of generic 64-bit addressing).
+template <typename T>
+__device__ __forceinline__ long long msa_sweep_cta(const MsaTask& t, const MsaConst& k, T* diag, int tid, int nt) {
+  const MsaSweep<T> sw = msa_sweep_init<T>(t, k, diag);
+  const int last = sw.m + sw.n;
+  int hc = 0;
   for (int d = 0; d <= last; ++d) {
-    msa_diag_phase(t, k, diag, d, tid, nt);
+    msa_diag_phase<T>(sw, d, hc, tid, nt);
+    hc = hc == 2 ? 0 : hc + 1;
     __syncthreads();   // diagonal d complete and visible to the whole CTA before d + 1 starts
   }
-  if (tid == 0) msa_walk_phase(t, diag);
+  return msa_final_score<T>(sw);
+}
+
+// One merge by one CTA, in score type T.  smem_bytes: dynamic shared memory of the launch; a merge whose 7
+// rolling diagonals fit uses it, any other its global scratch.
+template <typename T>
+__device__ __forceinline__ void msa_merge_cta(const MsaTask& t, const MsaConst& k, uint32_t smem_bytes, T* smem) {
+  const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
+  msa_prep_phase(t, k, tid, nt);
+  __syncthreads();
+  long long score;
+  if (msa_diag_bytes(t.Lx, sizeof(T) == 4) <= (size_t)smem_bytes) score = msa_sweep_cta<T>(t, k, smem, tid, nt);
+  else score = msa_sweep_cta<T>(t, k, reinterpret_cast<T*>(t.diag), tid, nt);
+  if (tid == 0) msa_walk_phase(t, score);
   __syncthreads();
   msa_build_phase(t, k, tid, nt);
+}
+
+// MAXT: the largest block size the variant is compiled for (registers per thread follow from it).
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) msa_merge_kernel(const MsaTask* tasks, const MsaConst k, uint32_t smem_bytes) {
+  extern __shared__ long long msa_shared_diag[];
+  const MsaTask t = tasks[blockIdx.x];
+  if (t.narrow) msa_merge_cta<int32_t>(t, k, smem_bytes, reinterpret_cast<int32_t*>(msa_shared_diag));
+  else msa_merge_cta<long long>(t, k, smem_bytes, msa_shared_diag);
 }
 
 __global__ void __launch_bounds__(256) msa_rows_kernel(const __grid_constant__ MsaRows p) {

@@ -40,6 +40,7 @@ struct MsaJob {
   int32_t go = 0, ge = 0;
   const char* letters = "";            // nsym characters
   size_t scratch_budget = (size_t)4 << 30;   // scratch bytes one launch may use (at least one merge always runs)
+  bool force_wide = false;              // tests: int64 sweep even where int32 would do
 };
 
 struct MsaOut {
@@ -132,7 +133,7 @@ inline int msa_progressive(MsaDevice& dev, const MsaJob& job, MsaOut& out) {
   auto scratch_of = [&](uint32_t Lx, uint32_t Ly) -> Scratch {
     const size_t mn = std::min(Lx, Ly), mx = std::max<size_t>(std::max(Lx, Ly), 1);
     Scratch q;
-    q.diag = msa_align(msa_diag_bytes(Lx));
+    q.diag = msa_align(msa_diag_bytes(Lx, false));
     q.pbig = msa_align((size_t)nsym * mx * 4);
     q.lst = msa_align((size_t)nsym * mx * 4);
     q.lnz = msa_align(mx * 4);
@@ -140,6 +141,12 @@ inline int msa_progressive(MsaDevice& dev, const MsaJob& job, MsaOut& out) {
     q.path = msa_align(std::max<size_t>(2 * ((size_t)Lx + Ly), 1) * 4);
     q.total = q.diag + q.pbig + q.lst + q.lnz + q.dir + q.path;
     return q;
+  };
+  int32_t max_abs_s = 0;
+  for (int32_t v : job.smat) max_abs_s = std::max(max_abs_s, v < 0 ? -v : v);
+  auto narrow_of = [&](uint32_t t) -> bool {
+    const uint32_t x = job.left[t], y = job.right[t];
+    return !job.force_wide && msa_fits_narrow(size[x], size[y], ncol[x], ncol[y], max_abs_s, job.go, job.ge);
   };
   for (uint32_t lv = 1; lv <= nlevels; lv++) {
     const std::vector<uint32_t>& ms = by_level[lv];
@@ -155,7 +162,8 @@ inline int msa_progressive(MsaDevice& dev, const MsaJob& job, MsaOut& out) {
         if (e > b && bytes + need > job.scratch_budget) break;
         bytes += need;
         longest = std::max(longest, std::min(Lx, Ly) + 1);
-        if (msa_diag_bytes(Lx) <= kMsaSmemLimit) smem = std::max(smem, msa_diag_bytes(Lx));
+        const size_t db = msa_diag_bytes(Lx, narrow_of(t));
+        if (db <= kMsaSmemLimit) smem = std::max(smem, db);
         e++;
       }
       const size_t count = e - b;
@@ -179,6 +187,7 @@ inline int msa_progressive(MsaDevice& dev, const MsaJob& job, MsaOut& out) {
         k.cx = prof[x]; k.cy = prof[y]; k.cn = p;
         k.capx = cap[x]; k.capy = cap[y]; k.capn = cap[z];
         k.Lx = Lx; k.Ly = Ly; k.nx = size[x]; k.ny = size[y];
+        k.narrow = narrow_of(t) ? 1u : 0u;
         k.mapx = p + pw; k.mapy = p + pw + Lx;
         nodemap[x] = k.mapx; nodemap[y] = k.mapy;
         const Scratch sz = scratch_of(Lx, Ly);

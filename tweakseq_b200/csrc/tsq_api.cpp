@@ -1338,8 +1338,10 @@ class CudaMsaDevice : public tsq::MsaDevice {
     scr_.release();
   }
   cudaError_t err = cudaSuccess;   // first CUDA error seen
+  double t_alloc = 0, t_scratch = 0, t_copy = 0, t_wait = 0, t_launch = 0;   // host clock per kind of call (TSQ_MSA_DEBUG)
 
   void* alloc(size_t bytes) override {
+    Timer tm(t_alloc);
     bytes = tsq::msa_align(std::max<size_t>(bytes, 1));
     if (bytes > left_) {
       const size_t chunk = std::max(bytes, (size_t)64 << 20);
@@ -1355,24 +1357,36 @@ class CudaMsaDevice : public tsq::MsaDevice {
     return r;
   }
   void* scratch(size_t bytes) override {
+    Timer tm(t_scratch);
     if (bytes > scr_.cap) {
       if (!ok(cudaStreamSynchronize(s_))) return nullptr;   // nothing may still be using the old block
       if (!ok(scr_.reserve(bytes + bytes / 4))) return nullptr;
     }
     return scr_.p;
   }
-  bool h2d(void* d, const void* h, size_t b) override { return ok(cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, s_)); }
+  bool h2d(void* d, const void* h, size_t b) override {
+    Timer tm(t_copy);
+    return ok(cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, s_));
+  }
   bool d2h(void* h, const void* d, size_t b) override {
+    Timer tm(t_wait);
     return ok(cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, s_)) && ok(cudaStreamSynchronize(s_));
   }
   bool fill(void* d, int v, size_t b) override { return ok(cudaMemsetAsync(d, v, b, s_)); }
   bool launch_leaves(const tsq::MsaLeaf* l, uint32_t n, uint32_t nsym) override { return ok(tsq::msa_leaf_launch(l, n, nsym, s_)); }
   bool launch_merges(const tsq::MsaTask* t, uint32_t count, uint32_t threads, uint32_t smem_bytes, const tsq::MsaConst& k) override {
+    Timer tm(t_launch);
     return ok(tsq::msa_merge_launch(t, count, threads, smem_bytes, k, s_));
   }
   bool launch_rows(const tsq::MsaRows& p) override { return ok(tsq::msa_rows_launch(p, s_)); }
 
  private:
+  struct Timer {
+    double& acc;
+    double t0;
+    explicit Timer(double& a) : acc(a), t0(now_ms()) {}
+    ~Timer() { acc += now_ms() - t0; }
+  };
   bool ok(cudaError_t e) {
     if (e != cudaSuccess && err == cudaSuccess) err = e;
     return e == cudaSuccess;
@@ -1430,6 +1444,9 @@ int tsq_msa(tsq_ctx* c, const char** rows, uint32_t* nrows, uint32_t* ncols, con
       mrc = tsq::msa_progressive(dev, job, out);
       derr = dev.err;
       if (mrc == tsq::MSA_OK && derr == cudaSuccess) derr = cudaStreamSynchronize(c->stream);
+      if (getenv("TSQ_MSA_DEBUG"))
+        fprintf(stderr, "tsq_msa: %.1f ms so far: alloc %.1f, scratch %.1f, copies %.1f, waiting on the device %.1f, launches %.1f; %u levels, %u launches\n",
+                now_ms() - t0, dev.t_alloc, dev.t_scratch, dev.t_copy, dev.t_wait, dev.t_launch, out.levels, out.launches);
     }
     if (derr != cudaSuccess) {
       cudaGetLastError();

@@ -331,11 +331,14 @@ cudaError_t msa_merge_launch(const MsaTask* d_tasks, uint32_t count, uint32_t th
                              cudaStream_t stream) {
   if (count == 0) return cudaSuccess;
   if (threads < 32 || threads > 1024 || (threads & 31u) || smem_bytes > 227u * 1024u) return cudaErrorInvalidValue;
+  // two compilations of the same kernel: up to 512 threads per CTA with 128 registers each (no spills),
+  // up to 1 024 with 64
+  auto kern = threads <= 512 ? msa_merge_kernel<512> : msa_merge_kernel<1024>;
   if (smem_bytes > 48u * 1024u) {   // above the default limit the kernel must opt in (per device, cheap to repeat)
-    cudaError_t e = cudaFuncSetAttribute(msa_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
   }
-  msa_merge_kernel<<<count, threads, smem_bytes, stream>>>(d_tasks, k, smem_bytes);
+  kern<<<count, threads, smem_bytes, stream>>>(d_tasks, k, smem_bytes);
   return cudaGetLastError();
 }
 
