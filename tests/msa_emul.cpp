@@ -117,6 +117,8 @@ extern "C" int msa_emul(const uint8_t* seqs, const uint64_t* offs, const uint32_
   job.letters = letters;
   if (scratch_budget) job.scratch_budget = scratch_budget;
   job.force_wide = force_wide;
+  const int raised = (force_threads >> 18) & 1u;   // the cancel flag, already up
+  job.cancel = &raised;
   tsq::MsaOut out;
   const int rc = tsq::msa_progressive(dev, job, out);
   if (rc != tsq::MSA_OK) return rc;

@@ -162,6 +162,8 @@ def emul():
                         go, ge, p(left, C.c_uint32), p(right, C.c_uint32), letters, p(rows, C.c_uint8), cap,
                         C.byref(ncols), p(sc, C.c_longlong), p(order, C.c_uint32), budget, threads, ascending,
                         C.byref(launches), C.byref(levels))
+        if rc == 4:
+            return "cancelled"
         assert rc == 0, rc
         k = ncols.value
         out = [rows[r * k:(r + 1) * k].tobytes().decode("ascii") for r in range(n)]
@@ -395,3 +397,33 @@ def test_gpu_msa_int32_and_int64_sweeps_at_the_range_boundary():
         rows, order, left, right, _ = _gpu_msa(seqs, go=4096, ge=1024)
         want, wsc = o.msa([o.encode(s) for s in seqs], o.matrix(0), 4096, 1024, left, right)
         assert rows == want
+
+
+# ---------------------------------------------------------------- committed golden vectors --------
+
+def _golden():
+    import json
+    return json.load(open(os.path.join(HERE, "golden", "msa_small.json")))
+
+
+def test_golden_alignments_oracle_and_kernel_phases(emul):
+    for g in _golden():
+        enc = [o.encode(s, g["alphabet"]) for s in g["seqs"]]
+        mat = o.matrix(g["alphabet"])
+        rows, sc = o.msa(enc, mat, g["go"], g["ge"], g["left"], g["right"], g["alphabet"])
+        assert rows == g["rows"] and sc.tolist() == g["merge_scores"]
+        rows, sc, *_ = emul(enc, mat, g["go"], g["ge"], g["left"], g["right"], g["alphabet"])
+        assert rows == g["rows"] and sc.tolist() == g["merge_scores"]
+
+
+@pytest.mark.gpu
+def test_gpu_golden_alignments():
+    for g in _golden():
+        rows, order, left, right, _ = _gpu_msa(g["seqs"], g["alphabet"], g["go"], g["ge"])
+        assert left.tolist() == g["left"] and right.tolist() == g["right"]     # the same tree ...
+        assert rows == g["rows"]                                               # ... and the same rows
+
+
+def test_plan_stops_at_the_cancel_flag(emul):
+    enc = [o.encode("MKTAYIAK"), o.encode("MKTAIAK"), o.encode("MKAYIAK")]
+    assert emul(enc, o.matrix(0), 11, 1, [0, 3], [1, 2], threads=1 << 18) == "cancelled"

@@ -41,6 +41,7 @@ struct MsaJob {
   const char* letters = "";            // nsym characters
   size_t scratch_budget = (size_t)4 << 30;   // scratch bytes one launch may use (at least one merge always runs)
   bool force_wide = false;              // tests: int64 sweep even where int32 would do
+  const volatile int* cancel = nullptr; // "Stop" (SeqEditMainWin.cpp:803-812): polled before every launch
 };
 
 struct MsaOut {
@@ -52,7 +53,7 @@ struct MsaOut {
   uint32_t launches = 0, levels = 0;
 };
 
-enum { MSA_OK = 0, MSA_NOMEM = 1, MSA_DEVICE = 2, MSA_BAD_TREE = 3 };
+enum { MSA_OK = 0, MSA_NOMEM = 1, MSA_DEVICE = 2, MSA_BAD_TREE = 3, MSA_CANCELLED = 4 };
 
 inline size_t msa_align(size_t x) { return (x + 255) & ~(size_t)255; }
 constexpr size_t kMsaSmemLimit = 200 * 1024;   // of the 227 KB a CTA may have on sm_100
@@ -152,6 +153,7 @@ inline int msa_progressive(MsaDevice& dev, const MsaJob& job, MsaOut& out) {
     const std::vector<uint32_t>& ms = by_level[lv];
     size_t b = 0;
     while (b < ms.size()) {
+      if (job.cancel && *job.cancel) return MSA_CANCELLED;
       // batch [b, e): as many merges of this level as the scratch budget takes
       size_t e = b, bytes = msa_align(sizeof(MsaTask));
       uint32_t longest = 0;

@@ -193,6 +193,7 @@ struct tsq_ctx {
   uint32_t msa_cols = 0;
   bool have_msa = false;
   double msa_ms = 0;
+  volatile int* msa_cancel = nullptr;     // set by tsq_run_fasta around its tsq_msa: polled before every launch
   DevBuf<uint2> d_pairs32;
   DevBuf<uint4> d_tasks16w;
   DevBuf<uint2> d_bnd16w;
@@ -1432,6 +1433,7 @@ int tsq_msa(tsq_ctx* c, const char** rows, uint32_t* nrows, uint32_t* ncols, con
     job.go = c->go;
     job.ge = c->ge;
     job.letters = letters_of(c);
+    job.cancel = c->msa_cancel;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) job.scratch_budget = std::max<size_t>(free_b / 4, (size_t)256 << 20);
     else cudaGetLastError();
@@ -1452,6 +1454,7 @@ int tsq_msa(tsq_ctx* c, const char** rows, uint32_t* nrows, uint32_t* ncols, con
       cudaGetLastError();
       return fail(c, derr == cudaErrorMemoryAllocation ? TSQ_ERR_NOMEM : TSQ_ERR_CUDA, "tsq_msa: %s", cudaGetErrorString(derr));
     }
+    if (mrc == tsq::MSA_CANCELLED) return fail(c, TSQ_ERR_CANCELLED, "cancelled");
     if (mrc == tsq::MSA_NOMEM) return fail(c, TSQ_ERR_NOMEM, "tsq_msa: out of device memory");
     if (mrc != tsq::MSA_OK) return fail(c, TSQ_ERR_CUDA, "tsq_msa: internal error %d", mrc);
     c->msa_ms = now_ms() - t0;
@@ -1790,7 +1793,9 @@ int tsq_run_fasta(const char* fin, const char* fout, const tsq_params* params, t
       std::vector<const char*> hdr(headers.size()), res(seqs.size());
       for (size_t i = 0; i < headers.size(); i++) hdr[i] = headers[i].c_str();
       for (size_t i = 0; i < seqs.size(); i++) res[i] = seqs[i].data();
+      c->msa_cancel = cancel;
       rc = tsq_write_msa_fasta(c, hdr.data(), res.data(), lens.data(), fout, 1);
+      c->msa_cancel = nullptr;
       if (rc == TSQ_OK) {
         tsq_stats st;
         tsq_get_stats(c, &st);
