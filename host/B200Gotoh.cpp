@@ -32,6 +32,7 @@ void B200Gotoh::writeSettings(SettingsDocument& doc) {  // ClustalO.cpp:54-61
   e.children.push_back({"gap_open", std::to_string(gapOpen)});
   e.children.push_back({"gap_extend", std::to_string(gapExtend)});
   e.children.push_back({"device", std::to_string(device)});
+  e.children.push_back({"align_in_process", alignInProcess ? "yes" : "no"});
   doc.alignment_tools.push_back(e);
 }
 
@@ -44,6 +45,7 @@ void B200Gotoh::readSettings(SettingsDocument& doc) {  // ClustalO.cpp:63-86
       if (kv.first == "gap_open") gapOpen = std::stoi(kv.second);
       if (kv.first == "gap_extend") gapExtend = std::stoi(kv.second);
       if (kv.first == "device") device = std::stoi(kv.second);
+      if (kv.first == "align_in_process") alignInProcess = kv.second == "yes";
     }
   }
   getVersion();

@@ -45,8 +45,9 @@ class B200Gotoh : public AlignmentTool {
   int gapOpen = -1, gapExtend = -1, device = 0;  // <0: library defaults (11/1 protein)
   bool nucleotide = false;
   bool identityDistance = false;                 // ClustalW-style 1 - identities/min(len)
-  bool alignInProcess = false;                   // run(): fout = the multiple alignment (FASTA, tree order) that
-                                                 // readNewAlignment ingests; the matrix goes to <fout>.distmat
+  bool alignInProcess = true;                    // run(): fout = the multiple alignment (FASTA, tree order) that
+                                                 // readNewAlignment ingests, the matrix goes to <fout>.distmat;
+                                                 // false: fout = the distance matrix for clustalo --distmat-in
 
  private:
   void init();

@@ -19,14 +19,16 @@ int main(int argc, char** argv) {
   t.setPreferred(true);
   t.gapOpen = 9;
   t.gapExtend = 2;
+  t.alignInProcess = false;
   SettingsDocument doc;
   SettingsElement other;
   other.children = {{"name", "clustalo"}, {"path", "/usr/local/bin/clustalo"}, {"preferred", "no"}};
   doc.alignment_tools.push_back(other);
   t.writeSettings(doc);
   B200Gotoh u;
+  CHECK(u.alignInProcess);   // the default: run() writes the alignment the editor ingests
   u.readSettings(doc);
-  CHECK(u.preferred() && u.gapOpen == 9 && u.gapExtend == 2 && u.executable() == t.executable());
+  CHECK(u.preferred() && u.gapOpen == 9 && u.gapExtend == 2 && !u.alignInProcess && u.executable() == t.executable());
   CHECK(u.version().find("tsq-b200") != std::string::npos);
   std::string fin = "in.fa", fout = "out.mat", exec;
   std::vector<std::string> args;
@@ -66,6 +68,7 @@ int main(int argc, char** argv) {
     g.identityDistance = false;
   }
   if (argc >= 3) {
+    g.alignInProcess = false;   // argv[2] = distance matrix out (the clustalo hand-off of SURVEY 8f-1)
     int rc = g.run(argv[1], argv[2], [](const std::string& l) { printf("[log] %s\n", l.c_str()); }, nullptr);
     CHECK(rc == 0);
     if (argc >= 4) {   // argv[3] = alignment out: the tool as a complete in-process aligner

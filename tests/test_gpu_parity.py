@@ -220,6 +220,7 @@ def test_run_fasta_writes_clustalo_distmat(tmp_path):
     write_fasta(fin, labels, seqs, [f">{l} some description" for l in labels])
     log = []
     tool = t.B200Gotoh()
+    tool.align = False                       # fout = the distance matrix (clustalo hand-off), not the alignment
     assert tool.run(fin, fout, log=log.append) == 0
     lab, rows = read_distmat(fout)
     assert lab == labels and len(rows) == 12 and any("GCUPS" in m for m in log)

@@ -52,6 +52,8 @@ def test_b200gotoh_settings_round_trip_like_clustalo():
     assert t.name() == "b200gotoh" and t.inProcess() and not t.usesStdOut()
     assert t.executable().endswith("libtsqb200.so")
     t.setPreferred(True); t.gap_open, t.gap_extend, t.device = 9, 2, 1
+    assert t.align
+    t.align = False
     root = ET.Element("settings")
     other = ET.SubElement(root, "alignment_tool")       # another tool's element must be ignored
     ET.SubElement(other, "name").text = "clustalo"
@@ -62,7 +64,7 @@ def test_b200gotoh_settings_round_trip_like_clustalo():
     assert [c.tag for c in e][:3] == ["name", "path", "preferred"] and e.find("preferred").text == "yes"
     u = B200Gotoh()
     u.readSettings(root)
-    assert u.preferred() and (u.gap_open, u.gap_extend, u.device) == (9, 2, 1)
+    assert u.preferred() and (u.gap_open, u.gap_extend, u.device) == (9, 2, 1) and not u.align
     assert u.executable() == t.executable() and "tsq-b200" in u.version()
 
 

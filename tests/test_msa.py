@@ -322,7 +322,7 @@ def test_gpu_run_fasta_writes_the_alignment_readNewAlignment_expects(tmp_path):
             for at in range(0, len(s), 70):
                 f.write(s[at:at + 70] + "\n")
     tool = t.B200Gotoh()
-    tool.align = True
+    assert tool.align                                      # the default: run() hands back what the editor ingests
     log = []
     assert tool.run(fin, fout, log=log.append) == 0
     assert any("progressive alignment" in m for m in log)

@@ -53,7 +53,7 @@ class AlignmentTool:
 
 
 class B200Gotoh(AlignmentTool):
-    """The in-process tool: all-vs-all Gotoh scores + guide-tree distances on a B200."""
+    """The in-process tool: all-vs-all Gotoh scores, guide-tree distances, tree and the progressive alignment on a B200."""
 
     def __init__(self):
         super().__init__()
@@ -64,15 +64,15 @@ class B200Gotoh(AlignmentTool):
         self.gap_extend = -1
         self.device = 0
         self.identity = False      # ClustalW-style identity distance instead of the score distance
-        self.align = False         # run(): write the multiple alignment (readNewAlignment's input) instead of the matrix
+        self.align = True          # run(): fout = the multiple alignment readNewAlignment ingests; False: the distance matrix
         self.last_stats: dict = {}
 
     def inProcess(self): return True
 
     def makeCommand(self, fin, fout):
         # What startAlignment() would exec for an external tool (ClustalO.cpp:48-52).  For the
-        # in-process tool this is informational: clustalo can consume the matrix we wrote.
-        return "", ["--in-process", "-i", fin, "--distmat-out", fout]
+        # in-process tool this is informational.
+        return "", ["--in-process", "-i", fin, "--outfmt=fa" if self.align else "--distmat-out", fout]
 
     def writeSettings(self, parent: ET.Element):
         e = ET.SubElement(parent, "alignment_tool")           # ClustalO.cpp:54-61
@@ -82,6 +82,7 @@ class B200Gotoh(AlignmentTool):
         ET.SubElement(e, "gap_open").text = str(self.gap_open)
         ET.SubElement(e, "gap_extend").text = str(self.gap_extend)
         ET.SubElement(e, "device").text = str(self.device)
+        ET.SubElement(e, "align_in_process").text = "yes" if self.align else "no"
 
     def readSettings(self, doc: ET.Element):
         for node in doc.iter("alignment_tool"):                # ClustalO.cpp:63-86
@@ -98,6 +99,8 @@ class B200Gotoh(AlignmentTool):
                     self.gap_extend = int(elem.text)
                 if elem.tag == "device":
                     self.device = int(elem.text)
+                if elem.tag == "align_in_process":
+                    self.align = (elem.text or "") == "yes"
         self.getVersion()
 
     def getVersion(self):
@@ -110,9 +113,10 @@ class B200Gotoh(AlignmentTool):
 
     # ---- the in-process path -------------------------------------------------------------
     def run(self, fin, fout, log=None, cancel: C.c_int | None = None) -> int:
-        """FASTA file in (what Project::exportFASTA wrote), distance matrix file out -- or, with
-        ``align`` set, the multiple alignment itself (FASTA, tree order): the file
-        Project::readNewAlignment (Project.cpp:908-1032) reads back, no external aligner involved.
+        """FASTA file in (what Project::exportFASTA wrote); out, with ``align`` set (the default), the
+        multiple alignment itself (FASTA, tree order): the file Project::readNewAlignment
+        (Project.cpp:908-1032) reads back, no external aligner involved -- the matrix and tree then go to
+        <fout>.distmat / <fout>.dnd.  With ``align`` off, fout is the PHYLIP distance matrix for clustalo.
 
         Returns the exit status startAlignment()/alignmentFinished() would see (0 = success:
         SeqEditMainWin.cpp:836-861)."""
