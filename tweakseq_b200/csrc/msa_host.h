@@ -41,6 +41,7 @@ struct MsaJob {
   const char* letters = "";            // nsym characters
   size_t scratch_budget = (size_t)4 << 30;   // scratch bytes one launch may use (at least one merge always runs)
   bool force_wide = false;              // tests: int64 sweep even where int32 would do
+  uint32_t cells_per_thread = 1;        // CTA size = longest diagonal / this (tuning knob; any value is correct)
   const volatile int* cancel = nullptr; // "Stop" (SeqEditMainWin.cpp:803-812): polled before every launch
 };
 
@@ -202,7 +203,10 @@ inline int msa_progressive(MsaDevice& dev, const MsaJob& job, MsaOut& out) {
         k.res = d_res + slot + (q - b);
       }
       if (!dev.h2d(sc, tasks.data(), count * sizeof(MsaTask))) return MSA_DEVICE;
-      const uint32_t threads = std::min<uint32_t>(1024u, std::max<uint32_t>(64u, (longest + 31u) & ~31u));
+      // one thread per cell of the longest diagonal (cells_per_thread = 1), or fewer, fatter threads
+      const uint32_t per_thread = std::max<uint32_t>(job.cells_per_thread, 1u);
+      const uint32_t want = (longest + per_thread - 1) / per_thread;
+      const uint32_t threads = std::min<uint32_t>(1024u, std::max<uint32_t>(64u, (want + 31u) & ~31u));
       if (!dev.launch_merges((const MsaTask*)sc, (uint32_t)count, threads, (uint32_t)smem, kc)) return MSA_DEVICE;
       out.launches++;
       res.resize(count);

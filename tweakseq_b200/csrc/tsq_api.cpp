@@ -1434,6 +1434,7 @@ int tsq_msa(tsq_ctx* c, const char** rows, uint32_t* nrows, uint32_t* ncols, con
     job.ge = c->ge;
     job.letters = letters_of(c);
     job.cancel = c->msa_cancel;
+    if (const char* e = getenv("TSQ_MSA_CELLS_PER_THREAD")) job.cells_per_thread = (uint32_t)std::max(1, atoi(e));   // tuning runs
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) job.scratch_budget = std::max<size_t>(free_b / 4, (size_t)256 << 20);
     else cudaGetLastError();
