@@ -46,7 +46,7 @@ class B200Gotoh : public AlignmentTool {
   bool nucleotide = false;
   bool identityDistance = false;                 // ClustalW-style 1 - identities/min(len)
   bool alignInProcess = true;                    // run(): fout = the multiple alignment (FASTA, tree order) that
-                                                 // readNewAlignment ingests, the matrix goes to <fout>.distmat;
+                                                 // readNewAlignment ingests (the tree goes to <fout>.dnd);
                                                  // false: fout = the distance matrix for clustalo --distmat-in
 
  private:

@@ -65,7 +65,9 @@ extern "C" {
                                      the ClustalW pairwise distance.  Scores are unchanged. */
 
 #define TSQ_FLAG_MSA_OUT 16u       /* tsq_run_fasta only: write the multiple alignment (tsq_msa) to fout, in tree
-                                     order, and the distance matrix to <fout>.distmat */
+                                     order (the guide tree still goes to <fout>.dnd) */
+#define TSQ_FLAG_KEEP_DISTMAT 32u /* with TSQ_FLAG_MSA_OUT: also write the distance matrix, to <fout>.distmat
+                                     (n^2 numbers of text; an external aligner writes it only on request too) */
 
 typedef struct tsq_ctx tsq_ctx;
 
@@ -261,9 +263,13 @@ int tsq_measure_dpx_rate(tsq_ctx *ctx, double *ops_per_clk_per_sm, double *sm_mh
  * --distmat-in, plus the guide tree as <distmat_out>.dnd.  Labels follow FASTAFile::parseComment
  * (FASTAFile.cpp:177-187).  With TSQ_FLAG_MSA_OUT in params->flags the file named by distmat_out
  * instead receives the multiple alignment (FASTA, tree order, header lines and residue spelling as
- * read) -- the file tweakseq reads back at SeqEditMainWin.cpp:836-861 -- and the matrix goes to
- * <distmat_out>.distmat.
+ * read) -- the file tweakseq reads back at SeqEditMainWin.cpp:836-861; the matrix is then written only
+ * with TSQ_FLAG_KEEP_DISTMAT, to <distmat_out>.distmat.
  */
+/* The matrix writer of tsq_run_fasta on its own (host only, no device): n, then one "label d d d ..." row per
+ * sequence with %.6f distances, from the packed upper triangle (n*(n-1)/2 values; diagonal 0). */
+int tsq_write_distmat(const char *path, const char *const *labels, uint32_t n, const double *packed_upper);
+
 int tsq_run_fasta(const char *fasta_in, const char *distmat_out, const tsq_params *params,
                   tsq_log_cb log, void *user, volatile int *cancel);
 

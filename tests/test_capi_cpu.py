@@ -80,3 +80,30 @@ def test_null_context_calls_are_errors_not_crashes():
     assert L.tsq_destroy(None) == 0
     assert L.tsq_last_error(None) == b"null context"
     assert L.tsq_run_fasta(None, None, None, capi.LOG_CB(0), None, None) == -1
+
+
+def test_distmat_writer_prints_what_printf_would(tmp_path):
+    """tsq_write_distmat (host only): same digits as "%.6f", including halves, tiny, negative and > 1 values."""
+    import numpy as np
+    from tweakseq_b200 import capi
+    from tweakseq_b200.fasta import read_distmat
+    rng = np.random.default_rng(4)
+    n = 37
+    d = rng.random(n * (n - 1) // 2)
+    d[:12] = [0.0, 1.0, 0.5, 0.0000005, 0.0000015, 0.9999995, 1.0000005, -0.25, 1e-9, 2.5, 0.1234565, 0.1234575]
+    labels = [f"seq{k}" for k in range(n)]
+    path = str(tmp_path / "m.dist")
+    capi.write_distmat(path, labels, d)
+    lines = open(path).read().split("\n")
+    assert lines[0] == str(n) and lines[-1] == ""
+    k = 0
+    for i in range(n):
+        parts = lines[1 + i].split(" ")
+        assert parts[0] == labels[i] and len(parts) == n + 1
+        for j in range(n):
+            v = 0.0 if i == j else d[capi.pair_index(min(i, j), max(i, j), n)]
+            assert parts[1 + j] == "%.6f" % v, (i, j, v)
+    lab, rows = read_distmat(path)
+    assert lab == labels and rows[3][3] == 0.0
+    capi.write_distmat(str(tmp_path / "empty.dist"), [], np.zeros(0))
+    assert open(tmp_path / "empty.dist").read() == "0\n"

@@ -340,8 +340,13 @@ def test_gpu_run_fasta_writes_the_alignment_readNewAlignment_expects(tmp_path):
         assert len(by_label[l]) == len(r) and all((a == "-") == (b == "-") for a, b in zip(by_label[l], r))
     want, _ = o.msa([o.encode(s) for s in seqs], o.matrix(0), 11, 1, left, right)
     assert rows == want
-    # the matrix and the tree are written next to it
-    assert os.path.exists(fout + ".distmat") and os.path.exists(fout + ".dnd")
+    # the tree is written next to it; the matrix (n^2 numbers of text) only on request
+    assert os.path.exists(fout + ".dnd") and not os.path.exists(fout + ".distmat")
+    tool.keep_distmat = True
+    assert tool.run(fin, fout) == 0
+    from tweakseq_b200.fasta import read_distmat
+    lab, mat = read_distmat(fout + ".distmat")
+    assert lab == labels and len(mat) == len(seqs)
 
 
 def test_kernel_phases_on_cpu_degenerate_inputs(emul):

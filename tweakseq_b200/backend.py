@@ -65,6 +65,7 @@ class B200Gotoh(AlignmentTool):
         self.device = 0
         self.identity = False      # ClustalW-style identity distance instead of the score distance
         self.align = True          # run(): fout = the multiple alignment readNewAlignment ingests; False: the distance matrix
+        self.keep_distmat = False  # with align: also write <fout>.distmat
         self.last_stats: dict = {}
 
     def inProcess(self): return True
@@ -115,12 +116,13 @@ class B200Gotoh(AlignmentTool):
     def run(self, fin, fout, log=None, cancel: C.c_int | None = None) -> int:
         """FASTA file in (what Project::exportFASTA wrote); out, with ``align`` set (the default), the
         multiple alignment itself (FASTA, tree order): the file Project::readNewAlignment
-        (Project.cpp:908-1032) reads back, no external aligner involved -- the matrix and tree then go to
-        <fout>.distmat / <fout>.dnd.  With ``align`` off, fout is the PHYLIP distance matrix for clustalo.
+        (Project.cpp:908-1032) reads back, no external aligner involved -- the tree then goes to <fout>.dnd
+        and, with ``keep_distmat``, the matrix to <fout>.distmat.  With ``align`` off, fout is the PHYLIP distance matrix for clustalo.
 
         Returns the exit status startAlignment()/alignmentFinished() would see (0 = success:
         SeqEditMainWin.cpp:836-861)."""
-        flags = (capi.FLAG_IDENTITY if self.identity else 0) | (capi.FLAG_MSA_OUT if self.align else 0)
+        flags = ((capi.FLAG_IDENTITY if self.identity else 0) | (capi.FLAG_MSA_OUT if self.align else 0) |
+                 (capi.FLAG_KEEP_DISTMAT if self.keep_distmat else 0))
         return capi.run_fasta(fin, fout, log=log, cancel=cancel, alphabet=self.alphabet,
                               gap_open=self.gap_open, gap_extend=self.gap_extend, device=self.device, flags=flags)
 

@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 PROTEIN, NUCLEOTIDE = 0, 1
-FLAG_FORCE_S32, FLAG_NO_DISTANCES, FLAG_NO_WAVE16, FLAG_IDENTITY, FLAG_MSA_OUT = 1, 2, 4, 8, 16
+FLAG_FORCE_S32, FLAG_NO_DISTANCES, FLAG_NO_WAVE16, FLAG_IDENTITY, FLAG_MSA_OUT, FLAG_KEEP_DISTMAT = 1, 2, 4, 8, 16, 32
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libtsqb200.so")
@@ -57,7 +57,7 @@ SYMBOLS = ["tsq_version", "tsq_version_string", "tsq_status_string", "tsq_device
            "tsq_download", "tsq_set_stream", "tsq_synchronize", "tsq_run", "tsq_scores", "tsq_distances",
            "tsq_self_scores", "tsq_identities", "tsq_device_scores", "tsq_partition", "tsq_finalize", "tsq_device_results",
            "tsq_get_stats", "tsq_measure_dpx_rate", "tsq_run_fasta", "tsq_plan_partition", "tsq_guide_tree",
-           "tsq_write_newick", "tsq_consensus", "tsq_align_pair", "tsq_partition_of", "tsq_msa", "tsq_write_msa_fasta"]
+           "tsq_write_newick", "tsq_consensus", "tsq_align_pair", "tsq_partition_of", "tsq_msa", "tsq_write_msa_fasta", "tsq_write_distmat"]
 
 _lib = None
 
@@ -115,6 +115,7 @@ def load_library():
     L.tsq_msa.argtypes = [vp, C.POINTER(C.POINTER(C.c_char)), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                           C.POINTER(C.POINTER(C.c_uint32))]
     L.tsq_write_msa_fasta.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), C.c_char_p, C.c_int]
+    L.tsq_write_distmat.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(C.c_double)]
     L.tsq_plan_partition.argtypes = [C.POINTER(Params), C.POINTER(C.c_uint32), C.c_uint32, C.c_int32, u64p, u64p]
     L.tsq_measure_dpx_rate.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.tsq_run_fasta.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(Params), LOG_CB, vp, C.POINTER(C.c_int)]
@@ -367,6 +368,17 @@ class Context:
         ops, mhz = C.c_double(), C.c_double()
         self._ck(self._L.tsq_measure_dpx_rate(self._h, C.byref(ops), C.byref(mhz)))
         return ops.value, mhz.value
+
+
+def write_distmat(path: str, labels, packed) -> None:
+    """tsq_write_distmat(): PHYLIP-style square matrix file from packed upper-triangle distances (host only)."""
+    L = load_library()
+    raw = [l.encode("latin-1", "replace") for l in labels]
+    arr = (C.c_char_p * max(len(raw), 1))(*raw) if raw else (C.c_char_p * 1)()
+    d = np.ascontiguousarray(packed, dtype=np.float64)
+    rc = L.tsq_write_distmat(path.encode(), arr, len(raw), d.ctypes.data_as(C.POINTER(C.c_double)))
+    if rc != 0:
+        raise TsqError(rc, "tsq_write_distmat")
 
 
 def run_fasta(fasta_in: str, distmat_out: str, log=None, cancel: C.c_int | None = None, **kw) -> int:

@@ -5,6 +5,7 @@
 // distance stage; matrix and alphabet from tweakseq/Core/Annotations/Consensus.cpp:34-69.
 // No CPU compute path exists here: every score comes out of the sm_100a kernels.
 #include <algorithm>
+#include <charconv>
 #include <chrono>
 #include <cstdarg>
 #include <cstddef>
@@ -1681,6 +1682,36 @@ int tsq_measure_dpx_rate(tsq_ctx* c, double* ops, double* mhz) {
   return TSQ_OK;
 }
 
+// Square PHYLIP-style matrix ("n", then "label d d d ..." rows, %.6f) from the packed upper triangle.
+// Host only.  std::to_chars(fixed, 6) prints the same correctly rounded digits as printf("%.6f") at a
+// fraction of the cost: at n = 1 000 the million fprintf calls of the first version took longer than the
+// whole GPU job.
+int tsq_write_distmat(const char* path, const char* const* labels, uint32_t n, const double* packed) {
+  if (!path || (n > 0 && !labels) || (n > 1 && !packed)) return TSQ_ERR_INVALID;
+  FILE* fo = fopen(path, "w");
+  if (!fo) return TSQ_ERR_IO;
+  std::string line;
+  line.reserve((size_t)n * 10 + 64);
+  char num[64];
+  fprintf(fo, "%u\n", n);
+  bool ok = true;
+  for (uint64_t i = 0; i < n && ok; i++) {
+    line.assign(labels[i] ? labels[i] : "");
+    for (uint64_t j = 0; j < n; j++) {
+      double v = 0.0;
+      if (i != j) v = packed[i < j ? tri(i, j, n) : tri(j, i, n)];
+      line.push_back(' ');
+      const auto r = std::to_chars(num, num + sizeof num, v, std::chars_format::fixed, 6);
+      if (r.ec == std::errc()) line.append(num, r.ptr);
+      else line.append("nan");
+    }
+    line.push_back('\n');
+    ok = fwrite(line.data(), 1, line.size(), fo) == line.size();
+  }
+  if (fclose(fo) != 0) ok = false;
+  return ok ? TSQ_OK : TSQ_ERR_IO;
+}
+
 // ---- file-level convenience -------------------------------------------------------------------
 // FASTA reading follows tweakseq/Core/FASTAFile.cpp:71-147 (state machine: '>' or ';' starts a
 // record, further ';' lines directly after a header are skipped, blank lines ignored, lines
@@ -1753,37 +1784,23 @@ int tsq_run_fasta(const char* fin, const char* fout, const tsq_params* params, t
   // Project.cpp:908-1032); the matrix moves to <fout>.distmat.  Otherwise fout is the matrix.
   const bool msa_out = params && params->struct_size >= offsetof(tsq_params, flags) + sizeof(uint32_t) &&
                        (params->flags & TSQ_FLAG_MSA_OUT);
+  const bool keep_matrix = !msa_out || (params->flags & TSQ_FLAG_KEEP_DISTMAT);   // n^2 numbers of text: only on request
   const std::string matrix_path = msa_out ? std::string(fout) + ".distmat" : std::string(fout);
+  std::vector<const char*> lab(labels.size());
+  for (size_t i = 0; i < labels.size(); i++) lab[i] = labels[i].c_str();
+  if (rc == TSQ_OK && keep_matrix && tsq_write_distmat(matrix_path.c_str(), lab.data(), (uint32_t)seqs.size(), d) != TSQ_OK) {
+    say(std::string("cannot write ") + matrix_path);
+    rc = TSQ_ERR_IO;
+  }
   if (rc == TSQ_OK) {
-    FILE* fo = fopen(matrix_path.c_str(), "w");
-    if (!fo) {
-      say(std::string("cannot write ") + matrix_path);
-      rc = TSQ_ERR_IO;
-    } else {
-      const uint64_t n = seqs.size();
-      fprintf(fo, "%llu\n", (unsigned long long)n);
-      for (uint64_t i = 0; i < n; i++) {
-        fprintf(fo, "%s", labels[i].c_str());
-        for (uint64_t j = 0; j < n; j++) {
-          double v = 0.0;
-          if (i != j) v = d[i < j ? tri(i, j, n) : tri(j, i, n)];
-          fprintf(fo, " %.6f", v);
-        }
-        fputc('\n', fo);
-      }
-      fclose(fo);
-      {  // guide tree for clustalo --guidetree-in, next to the matrix
-        std::vector<const char*> lab(labels.size());
-        for (size_t i = 0; i < labels.size(); i++) lab[i] = labels[i].c_str();
-        const std::string tree = std::string(fout) + ".dnd";
-        if (tsq_write_newick(c, lab.data(), tree.c_str()) == TSQ_OK) say("tsq-b200: wrote guide tree " + tree);
-      }
-      tsq_stats st;
-      tsq_get_stats(c, &st);
-      snprintf(msg, sizeof msg, "tsq-b200: %llu pairs, %.3e cells, kernel %.3f ms (%.1f GCUPS), wrote %s",
-               (unsigned long long)cnt, (double)st.cells, st.kernel_ms, st.gcups_kernel, matrix_path.c_str());
-      say(msg);
-    }
+    // guide tree for clustalo --guidetree-in, next to the matrix
+    const std::string tree = std::string(fout) + ".dnd";
+    if (tsq_write_newick(c, lab.data(), tree.c_str()) == TSQ_OK) say("tsq-b200: wrote guide tree " + tree);
+    tsq_stats st;
+    tsq_get_stats(c, &st);
+    snprintf(msg, sizeof msg, "tsq-b200: %llu pairs, %.3e cells, kernel %.3f ms (%.1f GCUPS)%s%s", (unsigned long long)cnt,
+             (double)st.cells, st.kernel_ms, st.gcups_kernel, keep_matrix ? ", wrote " : "", keep_matrix ? matrix_path.c_str() : "");
+    say(msg);
   }
   if (rc == TSQ_OK && msa_out) {
     if (cancel && *cancel) {
