@@ -164,6 +164,8 @@ def emul():
                         C.byref(launches), C.byref(levels))
         if rc == 4:
             return "cancelled"
+        if rc == 3:
+            return "bad tree"
         assert rc == 0, rc
         k = ncols.value
         out = [rows[r * k:(r + 1) * k].tobytes().decode("ascii") for r in range(n)]
@@ -432,3 +434,12 @@ def test_gpu_golden_alignments():
 def test_plan_stops_at_the_cancel_flag(emul):
     enc = [o.encode("MKTAYIAK"), o.encode("MKTAIAK"), o.encode("MKAYIAK")]
     assert emul(enc, o.matrix(0), 11, 1, [0, 3], [1, 2], threads=1 << 18) == "cancelled"
+
+
+def test_plan_rejects_merges_that_are_not_a_tree(emul):
+    enc = [o.encode(x) for x in ("MKTAYIAK", "MKTAIAK", "MKAYIAK", "MKAYIA")]
+    mat = o.matrix(0)
+    assert emul(enc, mat, 11, 1, [0, 0, 4], [1, 2, 5]) == "bad tree"        # leaf 0 merged twice
+    assert emul(enc, mat, 11, 1, [0, 5, 4], [1, 2, 3]) == "bad tree"        # node 5 used before it exists
+    assert emul(enc, mat, 11, 1, [0, 2, 4], [0, 3, 5]) == "bad tree"        # a node merged with itself
+    assert emul(enc, mat, 11, 1, [0, 2, 4], [1, 3, 5])[0][0].replace("-", "") == "MKTAYIAK"
