@@ -443,3 +443,66 @@ def test_plan_rejects_merges_that_are_not_a_tree(emul):
     assert emul(enc, mat, 11, 1, [0, 5, 4], [1, 2, 3]) == "bad tree"        # node 5 used before it exists
     assert emul(enc, mat, 11, 1, [0, 2, 4], [0, 3, 5]) == "bad tree"        # a node merged with itself
     assert emul(enc, mat, 11, 1, [0, 2, 4], [1, 3, 5])[0][0].replace("-", "") == "MKTAYIAK"
+
+
+# ---------------------------------------------------------------- the definition, by enumeration ---
+
+def _profile_paths(m, q):
+    """Every alignment of m columns against q columns as moves 'M' (both), 'D' (X only), 'I' (Y only)."""
+    out = []
+
+    def rec(i, j, acc):
+        if i == m and j == q:
+            out.append(acc)
+            return
+        if i < m and j < q:
+            rec(i + 1, j + 1, acc + "M")
+        if i < m:
+            rec(i + 1, j, acc + "D")
+        if j < q:
+            rec(i, j + 1, acc + "I")
+
+    rec(0, 0, "")
+    return out
+
+
+def test_every_merge_score_is_the_best_over_all_column_alignments():
+    """Pins the merge recurrence to its DEFINITION rather than to another DP: for tiny clusters every
+    alignment of the two column sets is enumerated and scored directly -- residue pairs across the two
+    clusters summed column by column, every maximal run of k columns taken from one cluster only costs
+    |X||Y| (go + k ge) -- and the best of them must be the score the oracle reports for that merge."""
+    rng = np.random.default_rng(314)
+    S = smat_dict(o.PROTEIN)
+    mat = o.matrix(o.PROTEIN)
+    for trial in range(25):
+        n = int(rng.integers(2, 5))
+        seqs = family(rng, n, int(rng.integers(1, 5)), mut=0.4, indel=0.3)
+        seqs = [s[:4] if s else PROT[int(rng.integers(0, 20))] for s in seqs]
+        go, ge = int(rng.integers(0, 13)), int(rng.integers(0, 3))
+        left, right = random_tree(rng, n)
+        enc = [o.encode(s) for s in seqs]
+        _, scores = o.msa(enc, mat, go, ge, left, right)
+        # rebuild every intermediate cluster with the independent Python statement to get its rows
+        canon = ["".join(PROT[v] for v in e) for e in enc]
+        rows = {r: [canon[r]] for r in range(n)}
+        for t, (l, r) in enumerate(zip(left.tolist(), right.tolist())):
+            X, Y = rows[l], rows[r]
+            m, q, w = len(X[0]), len(Y[0]), len(X) * len(Y)
+            best = None
+            for path in _profile_paths(m, q):
+                i = j = 0
+                total, prev = 0, ""
+                for mv in path:
+                    if mv == "M":
+                        total += np_msa.sub_score([x[i] for x in X], [y[j] for y in Y], S)
+                        i += 1; j += 1
+                    else:
+                        total -= w * (ge + (go if mv != prev else 0))
+                        if mv == "D":
+                            i += 1
+                        else:
+                            j += 1
+                    prev = mv
+                best = total if best is None or total > best else best
+            assert int(scores[t]) == best, (trial, t, seqs)
+            rows[n + t], _ = np_msa.align_profiles(X, Y, S, go, ge)
