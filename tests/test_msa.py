@@ -506,3 +506,15 @@ def test_every_merge_score_is_the_best_over_all_column_alignments():
                 best = total if best is None or total > best else best
             assert int(scores[t]) == best, (trial, t, seqs)
             rows[n + t], _ = np_msa.align_profiles(X, Y, S, go, ge)
+
+
+@pytest.mark.gpu
+def test_gpu_msa_profiles_beyond_shared_memory():
+    """7 rolling int32 diagonals of a 7 600-column profile need 213 KB: past the 200 KB the plan grants a CTA,
+    so this merge sweeps through its global (L2) scratch -- the one path the smaller tests never take."""
+    rng = np.random.default_rng(81)
+    seqs = family(rng, 3, 7600, o.NUCLEOTIDE, mut=0.05, indel=0.01)
+    assert min(len(s) for s in seqs) > 7400
+    rows, order, left, right, _ = _gpu_msa(seqs, o.NUCLEOTIDE)
+    want, _ = o.msa([o.encode(s, o.NUCLEOTIDE) for s in seqs], o.matrix(o.NUCLEOTIDE), 10, 1, left, right, o.NUCLEOTIDE)
+    assert rows == want
