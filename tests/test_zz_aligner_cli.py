@@ -1,0 +1,106 @@
+"""host/tsq-aligner: the backend behind the boundary tweakseq already has -- a child process started with the
+argv of its tool wrappers (ClustalO.cpp:51, Muscle.cpp:52, MAFFT.cpp:52; version probes ClustalO.cpp:100-111,
+Muscle.cpp:103).  CPU leg: argv handling, alphabet detection, loud failure without a B200.  GPU leg: the three
+argv conventions end to end against the in-memory alignment."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "host", "tsq-aligner")
+
+
+@pytest.fixture(scope="module")
+def exe():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tweakseq_b200", "csrc")], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "host")], stdout=subprocess.DEVNULL)
+    return EXE
+
+
+def run(exe, *args):
+    return subprocess.run([exe, *args], capture_output=True, text=True, timeout=300)
+
+
+def write(path, labels, seqs):
+    with open(path, "w") as f:
+        for l, s in zip(labels, seqs):
+            f.write(f">{l} a description\n{s}\n")
+
+
+def test_version_probes_of_all_three_wrappers(exe):
+    for flag in ("--version", "-version"):
+        out = run(exe, flag)
+        assert out.returncode == 0 and out.stdout.strip().startswith("tsq-b200")
+
+
+def test_the_three_argv_conventions_are_understood(exe, tmp_path):
+    prot, nuc = str(tmp_path / "p.fa"), str(tmp_path / "n.fa")
+    write(prot, ["a", "b"], ["MKTAYIAKQR", "MKTAYIAKQK"])
+    write(nuc, ["a", "b"], ["ACGTACGTNNACGU", "ACGTTTGA"])
+    fout = str(tmp_path / "o.fa")
+    # ClustalO.cpp:51
+    out = run(exe, "--force", "-v", "--outfmt=fa", "--output-order=tree-order", "-i", prot, "-o", fout, "--dry-run")
+    assert out.returncode == 0 and f"in={prot} out={fout} alphabet=protein" in out.stdout and "output=alignment" in out.stdout
+    # Muscle.cpp:52
+    out = run(exe, "-in", nuc, "-out", fout, "--dry-run")
+    assert out.returncode == 0 and f"in={nuc} out={fout} alphabet=nucleotide" in out.stdout
+    # MAFFT.cpp:52 (alignment on stdout, MAFFT.cpp:98)
+    out = run(exe, "--auto", "--thread", "-1", prot, "--dry-run")
+    assert out.returncode == 0 and f"in={prot} out=<stdout> alphabet=protein" in out.stdout
+    # explicit type beats detection; extras
+    out = run(exe, "-i", nuc, "-o", fout, "--seqtype=Protein", "--gap-open", "7", "--gap-extend=2", "--matrix-only", "--dry-run")
+    assert "alphabet=protein gap_open=7 gap_extend=2" in out.stdout and "output=matrix" in out.stdout
+
+
+def test_usage_errors_and_missing_files(exe, tmp_path):
+    assert run(exe).returncode == 2
+    assert run(exe, "--bogus").returncode == 2
+    assert run(exe, "-i").returncode == 2
+    assert run(exe, "-i", "x.fa", "-o", "y.fa", "--outfmt=clu").returncode == 2          # FASTA only
+    out = run(exe, "-i", str(tmp_path / "missing.fa"), "-o", str(tmp_path / "o.fa"))
+    assert out.returncode == 1 and "cannot open" in out.stderr
+
+
+def test_without_a_b200_it_fails_loudly(exe, tmp_path):
+    import tweakseq_b200 as t
+    if t.load_library().tsq_device_count() > 0:
+        pytest.skip("a B200 is present")
+    fin = str(tmp_path / "p.fa")
+    write(fin, ["a", "b"], ["MKTAYIAKQR", "MKTAYIAKQK"])
+    out = run(exe, "-i", fin, "-o", str(tmp_path / "o.fa"))
+    assert out.returncode == 1 and "no CPU path" in out.stderr and not os.path.exists(tmp_path / "o.fa.dnd")
+
+
+@pytest.mark.gpu
+def test_gpu_cli_end_to_end_all_conventions(exe, tmp_path):
+    import tweakseq_b200 as t
+    from tweakseq_b200.fasta import read_fasta
+    rng = np.random.default_rng(90)
+    root = rng.choice(list("ARNDCQEGHILKMFPSTWYV"), 90)
+    seqs = ["".join(c if rng.random() > 0.2 else rng.choice(list("ARNDCQEGHILKMFPSTWYV")) for c in root if rng.random() > 0.05)
+            for _ in range(12)]
+    labels = [f"s{k}" for k in range(12)]
+    fin = str(tmp_path / "in.fa")
+    write(fin, labels, seqs)
+    want, order = t.B200Gotoh().multiple_alignment(seqs)
+    expect = [(labels[r], want[r]) for r in order]                      # tree order, as --output-order=tree-order
+
+    fout = str(tmp_path / "clustalo.fa")
+    out = run(exe, "--force", "-v", "--outfmt=fa", "--output-order=tree-order", "-i", fin, "-o", fout)
+    assert out.returncode == 0 and "progressive alignment" in out.stdout, out.stdout + out.stderr
+    lab, rows, _ = read_fasta(fout)
+    assert list(zip(lab, rows)) == expect
+
+    fout = str(tmp_path / "muscle.fa")
+    assert run(exe, "-in", fin, "-out", fout).returncode == 0
+    lab, rows, _ = read_fasta(fout)
+    assert list(zip(lab, rows)) == expect
+
+    out = run(exe, "--auto", "--thread", "-1", fin)                     # mafft: the alignment IS stdout
+    assert out.returncode == 0
+    so = str(tmp_path / "mafft.fa")
+    open(so, "w").write(out.stdout)
+    lab, rows, _ = read_fasta(so)
+    assert list(zip(lab, rows)) == expect
