@@ -80,6 +80,11 @@ def test_null_context_calls_are_errors_not_crashes():
     assert L.tsq_destroy(None) == 0
     assert L.tsq_last_error(None) == b"null context"
     assert L.tsq_run_fasta(None, None, None, capi.LOG_CB(0), None, None) == -1
+    assert L.tsq_msa(None, None, None, None, None) == -1
+    assert L.tsq_write_msa_fasta(None, None, None, None, b"/tmp/x.fa", 1) == -1
+    assert L.tsq_guide_tree(None, None, None) == -1
+    assert L.tsq_write_distmat(None, None, 0, None) == -1
+    assert L.tsq_write_distmat(b"/nonexistent-dir/x.dist", None, 0, None) == -7
 
 
 def test_distmat_writer_prints_what_printf_would(tmp_path):
