@@ -32,6 +32,7 @@ struct Options {
   int alphabet = -1;   // -1 = detect from the residues
   int gap_open = -1, gap_extend = -1, device = 0;
   bool identity = false;
+  bool input_order = false;   // clustalo --output-order=input-order (default: tree order, what tweakseq asks for)
 };
 
 void usage(FILE* f) {
@@ -68,7 +69,11 @@ int parse(int argc, char** argv, Options& o, std::string& err) {
       if (!value(v)) return 2;
       if (v != "fa" && v != "fasta" && v != "a2m") { err = "only FASTA output is produced (--outfmt=" + v + ")"; return 2; }
     }
-    else if (starts_with(a, "--output-order")) { if (!value(v)) return 2; }   // rows come in tree order either way
+    else if (starts_with(a, "--output-order")) {
+      if (!value(v)) return 2;
+      if (v == "input-order") o.input_order = true;
+      else if (v != "tree-order") { err = "unknown --output-order " + v; return 2; }
+    }
     else if (starts_with(a, "--seqtype") || a == "-t") {
       if (!value(v)) return 2;
       for (char& ch : v) ch = (char)tolower((unsigned char)ch);
@@ -158,9 +163,9 @@ int main(int argc, char** argv) {
     out = tmpl;
   }
   if (o.dry_run) {
-    printf("in=%s out=%s alphabet=%s gap_open=%d gap_extend=%d device=%d output=%s\n", o.in.c_str(), o.to_stdout ? "<stdout>" : out.c_str(),
-           alphabet == TSQ_NUCLEOTIDE ? "nucleotide" : "protein", o.gap_open, o.gap_extend, o.device,
-           o.matrix_only ? "matrix" : "alignment");
+    printf("in=%s out=%s alphabet=%s gap_open=%d gap_extend=%d device=%d output=%s order=%s\n", o.in.c_str(),
+           o.to_stdout ? "<stdout>" : out.c_str(), alphabet == TSQ_NUCLEOTIDE ? "nucleotide" : "protein", o.gap_open, o.gap_extend,
+           o.device, o.matrix_only ? "matrix" : "alignment", o.input_order ? "input" : "tree");
     return 0;
   }
   tsq_params p;
@@ -172,6 +177,7 @@ int main(int argc, char** argv) {
   if (!o.matrix_only) p.flags |= TSQ_FLAG_MSA_OUT;
   if (o.keep_distmat) p.flags |= TSQ_FLAG_KEEP_DISTMAT;
   if (o.identity) p.flags |= TSQ_FLAG_IDENTITY;
+  if (o.input_order) p.flags |= TSQ_FLAG_INPUT_ORDER;
   bool to_stderr = o.to_stdout;
   const int rc = tsq_run_fasta(o.in.c_str(), out.c_str(), &p, log_line, &to_stderr, nullptr);
   if (rc != TSQ_OK) {

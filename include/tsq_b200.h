@@ -69,6 +69,9 @@ extern "C" {
 #define TSQ_FLAG_KEEP_DISTMAT 32u /* with TSQ_FLAG_MSA_OUT: also write the distance matrix, to <fout>.distmat
                                      (n^2 numbers of text; an external aligner writes it only on request too) */
 
+#define TSQ_FLAG_INPUT_ORDER 64u  /* with TSQ_FLAG_MSA_OUT: rows in the order of the input file instead of tree order
+                                     (clustalo's --output-order=input-order) */
+
 typedef struct tsq_ctx tsq_ctx;
 
 typedef struct tsq_params {

@@ -51,7 +51,10 @@ def test_the_three_argv_conventions_are_understood(exe, tmp_path):
     assert out.returncode == 0 and f"in={prot} out=<stdout> alphabet=protein" in out.stdout
     # explicit type beats detection; extras
     out = run(exe, "-i", nuc, "-o", fout, "--seqtype=Protein", "--gap-open", "7", "--gap-extend=2", "--matrix-only", "--dry-run")
-    assert "alphabet=protein gap_open=7 gap_extend=2" in out.stdout and "output=matrix" in out.stdout
+    assert "alphabet=protein gap_open=7 gap_extend=2" in out.stdout and "output=matrix" in out.stdout and "order=tree" in out.stdout
+    out = run(exe, "-i", prot, "-o", fout, "--output-order=input-order", "--dry-run")
+    assert out.returncode == 0 and "order=input" in out.stdout
+    assert run(exe, "-i", prot, "-o", fout, "--output-order=random", "--dry-run").returncode == 2
 
 
 def test_usage_errors_and_missing_files(exe, tmp_path):

@@ -1806,13 +1806,13 @@ int tsq_run_fasta(const char* fin, const char* fout, const tsq_params* params, t
     if (cancel && *cancel) {
       rc = TSQ_ERR_CANCELLED;
     } else {
-      // rows in tree order like the reference's clustalo argv (--output-order=tree-order, ClustalO.cpp:51),
-      // header lines and residue spelling exactly as read, so readNewAlignment matches every label
+      // rows in tree order like the reference's clustalo argv (--output-order=tree-order, ClustalO.cpp:51)
+      // unless TSQ_FLAG_INPUT_ORDER asks for the input's order, header lines and residue spelling exactly as read, so readNewAlignment matches every label
       std::vector<const char*> hdr(headers.size()), res(seqs.size());
       for (size_t i = 0; i < headers.size(); i++) hdr[i] = headers[i].c_str();
       for (size_t i = 0; i < seqs.size(); i++) res[i] = seqs[i].data();
       c->msa_cancel = cancel;
-      rc = tsq_write_msa_fasta(c, hdr.data(), res.data(), lens.data(), fout, 1);
+      rc = tsq_write_msa_fasta(c, hdr.data(), res.data(), lens.data(), fout, (params->flags & TSQ_FLAG_INPUT_ORDER) ? 0 : 1);
       c->msa_cancel = nullptr;
       if (rc == TSQ_OK) {
         tsq_stats st;
