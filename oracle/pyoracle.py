@@ -24,6 +24,36 @@ def build(force: bool = False) -> str:
     return _SO
 
 
+_REF_SO = os.path.join(_HERE, "_ref", "libref_consensus.so")
+_ref = None
+
+
+def ref_consensus_available() -> bool:
+    """oracle/_ref/libref_consensus.so: the reference's OWN Consensus.cpp, compiled where it lies by
+    oracle/Makefile (only possible where /root/reference exists; the built file travels with the snapshot)."""
+    if not os.path.exists(_REF_SO) and os.path.exists("/root/reference/tweakseq/Core/Annotations/Consensus.cpp"):
+        subprocess.call(["make", "-C", _HERE, "_ref/libref_consensus.so"], stdout=subprocess.DEVNULL)
+    return os.path.exists(_REF_SO)
+
+
+def ref_consensus(cell_rows, plurality: float = -1.0) -> str:
+    """Consensus::calculate of the reference itself (tweakseq/Core/Annotations/Consensus.cpp:80-161).
+    cell_rows: equal-length sequences of 16-bit residue cells (str, bytes or ints, flag bits allowed)."""
+    global _ref
+    if _ref is None:
+        _ref = C.CDLL(_REF_SO)
+        _ref.tsq_ref_consensus.restype = C.c_int
+        _ref.tsq_ref_consensus.argtypes = [C.POINTER(C.c_uint16), C.c_uint, C.c_uint, C.c_double, C.c_char_p]
+    rows = [[ord(ch) if isinstance(ch, str) else int(ch) for ch in r] for r in cell_rows]
+    ncols = len(rows[0]) if rows else 0
+    cells = np.ascontiguousarray(np.array(rows, dtype=np.uint16).reshape(len(rows), ncols))
+    out = C.create_string_buffer(ncols + 1)
+    rc = _ref.tsq_ref_consensus(cells.ctypes.data_as(C.POINTER(C.c_uint16)), len(rows), ncols, plurality, out)
+    if rc != 0:
+        raise RuntimeError(f"tsq_ref_consensus: {rc}")
+    return out.raw[:ncols].decode("latin-1")
+
+
 _lib = None
 
 

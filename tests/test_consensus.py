@@ -61,3 +61,54 @@ def test_gpu_consensus_edge_cases():
         assert ctx.consensus(["----", "----", "AC-D"]) == o.consensus(["----", "----", "AC-D"])
         rows = ["AWC-a", "AWC-A", "AYD-A", "RWC-x"]
         assert ctx.consensus(rows) == "AWC-?"
+
+
+# ---- the reference's OWN code (oracle/_ref/libref_consensus.so = tweakseq/Core/Annotations/Consensus.cpp
+# compiled where it lies by oracle/Makefile) beside the restatement and beside the CUDA path ------------
+
+needs_ref = pytest.mark.skipif(not o.ref_consensus_available(), reason="oracle/_ref/libref_consensus.so not built "
+                                                                       "(needs /root/reference at build time)")
+
+
+def _cells(rng, rows):
+    """The rows as 16-bit residue cells with tweakseq's flag bits (Sequence.h:36-39) sprinkled in: bits >= 0x100
+    vanish under Consensus.cpp's `& 0xff`; EXCLUDE_CELL (0x80) survives it and turns the cell into a non-residue."""
+    out = []
+    for r in rows:
+        cells = []
+        for ch in r:
+            v = ord(ch)
+            u = rng.random()
+            if u < 0.10:
+                v |= 0x0100            # HIGHLIGHT_CELL
+            elif u < 0.15:
+                v |= 0x0080            # EXCLUDE_CELL
+            cells.append(v)
+        out.append(cells)
+    return out
+
+
+@needs_ref
+def test_restatement_equals_the_references_own_consensus_code():
+    rng = np.random.default_rng(2026)
+    assert o.ref_consensus(["AWC-a", "AWC-A", "AYD-A", "RWC-x"]) == "AWC-?"
+    for trial in range(60):
+        nrows, ncols = int(rng.integers(1, 40)), int(rng.integers(1, 80))
+        rows = _random_alignment(rng, nrows, ncols)
+        cells = _cells(rng, rows)
+        seen = ["".join(chr(v & 0xff) for v in r) for r in cells]        # what `residues[c].unicode() & 0xff` yields
+        assert o.ref_consensus(cells) == o.consensus(seen), (trial, nrows, ncols)       # default plurality rows / 2
+        for pl in (0.0, 1.0, nrows * 0.8, nrows + 5.0):
+            assert o.ref_consensus(cells, pl) == o.consensus(seen, plurality=pl)
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("nrows,ncols", [(2, 33), (17, 64), (100, 301)])
+def test_gpu_consensus_equals_the_references_own_code(nrows, ncols):
+    import tweakseq_b200 as t
+    rng = np.random.default_rng(nrows * 7 + ncols)
+    rows = _random_alignment(rng, nrows, ncols)
+    with t.Context() as ctx:
+        assert ctx.consensus(rows) == o.ref_consensus(rows)
+        assert ctx.consensus(rows, plurality=nrows * 0.8) == o.ref_consensus(rows, nrows * 0.8)
