@@ -36,6 +36,49 @@ def ref_consensus_available() -> bool:
     return os.path.exists(_REF_SO)
 
 
+_REF_FASTA_SO = os.path.join(_HERE, "_ref", "libref_fasta.so")
+_ref_fasta = None
+
+
+def ref_fasta_available() -> bool:
+    """oracle/_ref/libref_fasta.so: the reference's OWN FASTAFile.cpp + SequenceFile.cpp, compiled where they lie."""
+    if not os.path.exists(_REF_FASTA_SO) and os.path.exists("/root/reference/tweakseq/Core/FASTAFile.cpp"):
+        subprocess.call(["make", "-C", _HERE, "_ref/libref_fasta.so"], stdout=subprocess.DEVNULL)
+    return os.path.exists(_REF_FASTA_SO)
+
+
+def _ref_fasta_lib():
+    global _ref_fasta
+    if _ref_fasta is None:
+        _ref_fasta = C.CDLL(_REF_FASTA_SO)
+        _ref_fasta.tsq_ref_fasta_read.restype = C.c_int
+        _ref_fasta.tsq_ref_fasta_read.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_ulong]
+        _ref_fasta.tsq_ref_fasta_write.restype = C.c_int
+        _ref_fasta.tsq_ref_fasta_write.argtypes = [C.c_char_p] * 4
+    return _ref_fasta
+
+
+def ref_fasta_read(path: str):
+    """FASTAFile::read of the reference itself (tweakseq/Core/FASTAFile.cpp:71-147): (labels, sequences, comments)."""
+    cap = max(os.path.getsize(path) * 2, 1 << 12) + 64
+    bufs = [C.create_string_buffer(cap) for _ in range(3)]
+    n = _ref_fasta_lib().tsq_ref_fasta_read(path.encode(), bufs[0], bufs[1], bufs[2], cap)
+    if n < 0:
+        raise RuntimeError(f"tsq_ref_fasta_read: {n}")
+    out = []
+    for b in bufs:
+        text = b.value.decode("latin-1")
+        out.append(text.split("\n")[:-1] if text else [])
+    return tuple(out)
+
+
+def ref_fasta_write(path: str, labels, seqs, comments) -> None:
+    """FASTAFile::write of the reference itself (tweakseq/Core/FASTAFile.cpp:149-171)."""
+    j = lambda l: ("".join(x + "\n" for x in l)).encode("latin-1")
+    if _ref_fasta_lib().tsq_ref_fasta_write(path.encode(), j(labels), j(seqs), j(comments)) != 0:
+        raise RuntimeError("tsq_ref_fasta_write failed")
+
+
 def ref_consensus(cell_rows, plurality: float = -1.0) -> str:
     """Consensus::calculate of the reference itself (tweakseq/Core/Annotations/Consensus.cpp:80-161).
     cell_rows: equal-length sequences of 16-bit residue cells (str, bytes or ints, flag bits allowed)."""

@@ -107,3 +107,32 @@ def test_gpu_cli_end_to_end_all_conventions(exe, tmp_path):
     open(so, "w").write(out.stdout)
     lab, rows, _ = read_fasta(so)
     assert list(zip(lab, rows)) == expect
+
+
+@pytest.mark.gpu
+def test_gpu_round_trip_through_the_references_own_fasta_code(exe, tmp_path):
+    """The drop-in property itself: the input file is written by the reference's OWN FASTAFile::write (what
+    Project::exportFASTA calls, Project.cpp:870-881) and the tool's output is parsed by the reference's OWN
+    FASTAFile::read (what Project::readNewAlignment calls, Project.cpp:908-915) -- both compiled from the
+    reference sources into oracle/_ref/libref_fasta.so.  Labels must come back one to one and the rows must be
+    the in-memory alignment."""
+    from oracle import pyoracle as o
+    if not o.ref_fasta_available():
+        pytest.skip("oracle/_ref/libref_fasta.so not built (needs /root/reference at build time)")
+    import tweakseq_b200 as t
+    rng = np.random.default_rng(91)
+    root = rng.choice(list("ARNDCQEGHILKMFPSTWYV"), 170)
+    seqs = ["".join(c if rng.random() > 0.25 else rng.choice(list("ARNDCQEGHILKMFPSTWYV")) for c in root if rng.random() > 0.06)
+            for _ in range(15)]
+    labels = [f"seq_{k}" for k in range(15)]
+    comments = [f">{l} exported by tweakseq" for l in labels]
+    fin, fout = str(tmp_path / "tweakseq.in.fa"), str(tmp_path / "tweakseq.out.fa")
+    o.ref_fasta_write(fin, labels, seqs, comments)                       # 80-column lines, comment line verbatim
+    out = run(exe, "--force", "-v", "--outfmt=fa", "--output-order=tree-order", "-i", fin, "-o", fout)
+    assert out.returncode == 0, out.stdout + out.stderr
+    got_labels, got_rows, got_comments = o.ref_fasta_read(fout)
+    want, order = t.B200Gotoh().multiple_alignment(seqs)
+    assert got_labels == [labels[r] for r in order]                      # every label, once, in tree order
+    assert got_rows == [want[r] for r in order]
+    assert got_comments == [comments[r] for r in order]                  # header lines come back verbatim
+    assert len({len(r) for r in got_rows}) == 1 and all(r.replace("-", "") == seqs[labels.index(l)] for l, r in zip(got_labels, got_rows))

@@ -28,8 +28,12 @@ def parse_comment(s: str) -> str:
     return s[1:] if idx == -1 else s[1:idx]
 
 
-def read_fasta(path: str):
-    """FASTAFile::read (FASTAFile.cpp:71-147).  Returns (labels, sequences, comments)."""
+def read_fasta(path: str, strict: bool = False):
+    """FASTAFile::read (FASTAFile.cpp:71-147).  Returns (labels, sequences, comments).
+
+    strict=True is the reference's reader to the letter (checked against its own compiled code in
+    tests/test_ref_fasta.py): a final header without residues leaves `sequences` one entry short.  The default
+    pads that entry with "" so that the three lists always line up."""
     SEEKING, COMMENT, SEQ = 0, 1, 2
     labels, seqs, comments = [], [], []
     state = SEEKING
@@ -57,7 +61,7 @@ def read_fasta(path: str):
                     labels.append(parse_comment(s))
                 else:
                     seqs[-1] += s
-    while len(seqs) < len(labels):   # a trailing header with no residues
+    while not strict and len(seqs) < len(labels):   # a trailing header with no residues
         seqs.append("")
     return labels, seqs, comments
 
