@@ -100,15 +100,3 @@ def test_restatement_equals_the_references_own_consensus_code():
         assert o.ref_consensus(cells) == o.consensus(seen), (trial, nrows, ncols)       # default plurality rows / 2
         for pl in (0.0, 1.0, nrows * 0.8, nrows + 5.0):
             assert o.ref_consensus(cells, pl) == o.consensus(seen, plurality=pl)
-
-
-@needs_ref
-@pytest.mark.gpu
-@pytest.mark.parametrize("nrows,ncols", [(2, 33), (17, 64), (100, 301)])
-def test_gpu_consensus_equals_the_references_own_code(nrows, ncols):
-    import tweakseq_b200 as t
-    rng = np.random.default_rng(nrows * 7 + ncols)
-    rows = _random_alignment(rng, nrows, ncols)
-    with t.Context() as ctx:
-        assert ctx.consensus(rows) == o.ref_consensus(rows)
-        assert ctx.consensus(rows, plurality=nrows * 0.8) == o.ref_consensus(rows, nrows * 0.8)

@@ -136,3 +136,20 @@ def test_gpu_round_trip_through_the_references_own_fasta_code(exe, tmp_path):
     assert got_rows == [want[r] for r in order]
     assert got_comments == [comments[r] for r in order]                  # header lines come back verbatim
     assert len({len(r) for r in got_rows}) == 1 and all(r.replace("-", "") == seqs[labels.index(l)] for l, r in zip(got_labels, got_rows))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nrows,ncols", [(2, 33), (17, 64), (100, 301)])
+def test_gpu_consensus_equals_the_references_own_code(nrows, ncols):
+    """tsq_consensus against Consensus::calculate of the reference itself (oracle/_ref/libref_consensus.so =
+    tweakseq/Core/Annotations/Consensus.cpp compiled where it lies), not only against the restatement."""
+    from oracle import pyoracle as o
+    if not o.ref_consensus_available():
+        pytest.skip("oracle/_ref/libref_consensus.so not built (needs /root/reference at build time)")
+    import tweakseq_b200 as t
+    from test_consensus import _random_alignment
+    rng = np.random.default_rng(nrows * 7 + ncols)
+    rows = _random_alignment(rng, nrows, ncols)
+    with t.Context() as ctx:
+        assert ctx.consensus(rows) == o.ref_consensus(rows)
+        assert ctx.consensus(rows, plurality=nrows * 0.8) == o.ref_consensus(rows, nrows * 0.8)
