@@ -79,6 +79,31 @@ def ref_fasta_write(path: str, labels, seqs, comments) -> None:
         raise RuntimeError("tsq_ref_fasta_write failed")
 
 
+_REF_SEQ_SO = os.path.join(_HERE, "_ref", "libref_sequence.so")
+_ref_seq = None
+
+
+def ref_sequence_available() -> bool:
+    """oracle/_ref/libref_sequence.so: the reference's OWN Sequence.cpp (Sequence::filter), compiled where it lies."""
+    if not os.path.exists(_REF_SEQ_SO) and os.path.exists("/root/reference/tweakseq/Core/Sequence.cpp"):
+        subprocess.call(["make", "-C", _HERE, "_ref/libref_sequence.so"], stdout=subprocess.DEVNULL)
+    return os.path.exists(_REF_SEQ_SO)
+
+
+def ref_filter(cells, apply_exclusions: bool) -> list[int]:
+    """Sequence::filter of the reference itself (tweakseq/Core/Sequence.cpp:57-69) on 16-bit residue cells."""
+    global _ref_seq
+    if _ref_seq is None:
+        _ref_seq = C.CDLL(_REF_SEQ_SO)
+        _ref_seq.tsq_ref_filter.restype = C.c_int
+        _ref_seq.tsq_ref_filter.argtypes = [C.POINTER(C.c_uint16), C.c_uint, C.c_int, C.POINTER(C.c_uint16)]
+    a = np.ascontiguousarray(np.array(list(cells), dtype=np.uint16))
+    out = np.zeros(max(len(a), 1), dtype=np.uint16)
+    k = _ref_seq.tsq_ref_filter(a.ctypes.data_as(C.POINTER(C.c_uint16)) if len(a) else out.ctypes.data_as(C.POINTER(C.c_uint16)),
+                                len(a), 1 if apply_exclusions else 0, out.ctypes.data_as(C.POINTER(C.c_uint16)))
+    return [int(v) for v in out[:k]]
+
+
 def ref_consensus(cell_rows, plurality: float = -1.0) -> str:
     """Consensus::calculate of the reference itself (tweakseq/Core/Annotations/Consensus.cpp:80-161).
     cell_rows: equal-length sequences of 16-bit residue cells (str, bytes or ints, flag bits allowed)."""

@@ -32,6 +32,9 @@ class QCharRef {
  public:
   QCharRef(QString& s, int i) : s_(s), i_(i) {}
   inline QCharRef& operator=(QChar c);
+  QCharRef& operator=(int v) { return *this = QChar(v); }
+  QCharRef& operator=(const QCharRef& o) { return *this = QChar((int)o.unicode()); }
+  operator QChar() const { return QChar((int)unicode()); }
   inline unsigned short unicode() const;
  private:
   QString& s_;
@@ -72,6 +75,12 @@ class QString {
     if (n >= 0 && (size_t)pos + (size_t)n < end) end = (size_t)pos + (size_t)n;
     q.d_.assign(d_.begin() + pos, d_.begin() + (long)end);
     return q;
+  }
+  QString& remove(int pos, int n) {   // Qt: out-of-range positions do nothing, n is clipped to the end
+    if (pos < 0 || (size_t)pos >= d_.size() || n <= 0) return *this;
+    const size_t end = (size_t)pos + (size_t)n < d_.size() ? (size_t)pos + (size_t)n : d_.size();
+    d_.erase(d_.begin() + pos, d_.begin() + (long)end);
+    return *this;
   }
   QString toLower() const { QString q = *this; for (auto& u : q.d_) if (u >= 'A' && u <= 'Z') u = (unsigned short)(u + 32); return q; }
   bool operator==(const QString& o) const { return d_ == o.d_; }

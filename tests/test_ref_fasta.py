@@ -67,3 +67,27 @@ def test_writer_restatement_equals_the_references_writer(tmp_path):
     seqs = ["".join(rng.choice(list(AA), int(l))) for l in (5, 80, 200)]
     o.ref_fasta_write(b, ["x", "y", "z"], seqs, [">x", ">y d", ">z"])
     assert o.ref_fasta_read(b) == (["x", "y", "z"], seqs, [">x", ">y d", ">z"])
+
+
+@pytest.mark.skipif(not o.ref_sequence_available(), reason="oracle/_ref/libref_sequence.so not built")
+def test_cell_filter_restatements_equal_the_references_sequence_filter():
+    """Sequence::filter (Sequence.cpp:57-69) is what exportFASTA applies before the aligner sees a sequence: the
+    Python restatement and the C++ adapter's filterCells (same rule, host/B200Gotoh.cpp) against the reference's
+    own compiled code on cells carrying its flag bits (Sequence.h:36-39)."""
+    rng = np.random.default_rng(12)
+    for trial in range(200):
+        n = int(rng.integers(0, 60))
+        cells = []
+        for _ in range(n):
+            v = ord(str(rng.choice(list(AA + "-acx"))))
+            u = rng.random()
+            if u < 0.2:
+                v |= fasta.EXCLUDE_CELL
+            if rng.random() < 0.2:
+                v |= fasta.HIGHLIGHT_CELL
+            if rng.random() < 0.05:
+                v |= 0x8000                      # any higher bit is a flag too (REMOVE_FLAGS = 0x007F)
+            cells.append(v)
+        for apply in (True, False):
+            want = "".join(chr(v) for v in o.ref_filter(cells, apply))
+            assert fasta.filter_cells(cells, apply) == want, (trial, apply)
