@@ -140,7 +140,10 @@ int main(int argc, char** argv) {
     return err == "help" ? 0 : 2;
   }
   if (o.version) {
-    printf("%s\n", tsq_version_string());   // what AlignmentTool::version() then shows (ClustalO.cpp:100-111)
+    // what AlignmentTool::version() then shows: ClustalO and MUSCLE read the probe's stdout (ClustalO.cpp:107,
+    // Muscle.cpp:107, which keeps the second word), MAFFT its stderr (MAFFT.cpp:111) -- so both get the line
+    printf("%s\n", tsq_version_string());
+    fprintf(stderr, "%s\n", tsq_version_string());
     return 0;
   }
   {

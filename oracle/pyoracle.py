@@ -104,6 +104,50 @@ def ref_filter(cells, apply_exclusions: bool) -> list[int]:
     return [int(v) for v in out[:k]]
 
 
+_REF_TOOLS_SO = os.path.join(_HERE, "_ref", "libref_tools.so")
+_ref_tools = None
+REF_TOOLS = {"clustalo": 0, "muscle": 1, "mafft": 2}
+
+
+def ref_tools_available() -> bool:
+    """oracle/_ref/libref_tools.so: the reference's OWN ClustalO / Muscle / MAFFT wrappers, compiled where they lie."""
+    if not os.path.exists(_REF_TOOLS_SO) and os.path.exists("/root/reference/tweakseq/Core/ClustalO.cpp"):
+        subprocess.call(["make", "-C", _HERE, "_ref/libref_tools.so"], stdout=subprocess.DEVNULL)
+    return os.path.exists(_REF_TOOLS_SO)
+
+
+def _ref_tools_lib():
+    global _ref_tools
+    if _ref_tools is None:
+        _ref_tools = C.CDLL(_REF_TOOLS_SO)
+        _ref_tools.tsq_ref_tool_command.restype = C.c_int
+        _ref_tools.tsq_ref_tool_command.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_ulong,
+                                                    C.POINTER(C.c_int)]
+        _ref_tools.tsq_ref_tool_version.restype = C.c_int
+        _ref_tools.tsq_ref_tool_version.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_ulong]
+    return _ref_tools
+
+
+def ref_tool_command(tool: str, fin: str, fout: str, exe: str = ""):
+    """What the reference's own wrapper hands to QProcess::start: (name, executable, argv list, uses_stdout)."""
+    buf = C.create_string_buffer(1 << 14)
+    so = C.c_int()
+    rc = _ref_tools_lib().tsq_ref_tool_command(REF_TOOLS[tool], exe.encode(), fin.encode(), fout.encode(), buf, len(buf), C.byref(so))
+    if rc != 0:
+        raise RuntimeError(f"tsq_ref_tool_command: {rc}")
+    parts = buf.value.decode().split("\n")[:-1]
+    return parts[0], parts[1], parts[2:], bool(so.value)
+
+
+def ref_tool_version(tool: str, exe: str) -> str:
+    """The wrapper's own getVersion() (a real fork + exec of `exe` with its version flag), as version() reports it."""
+    buf = C.create_string_buffer(1 << 12)
+    rc = _ref_tools_lib().tsq_ref_tool_version(REF_TOOLS[tool], exe.encode(), buf, len(buf))
+    if rc != 0:
+        raise RuntimeError(f"tsq_ref_tool_version: {rc}")
+    return buf.value.decode()
+
+
 def ref_consensus(cell_rows, plurality: float = -1.0) -> str:
     """Consensus::calculate of the reference itself (tweakseq/Core/Annotations/Consensus.cpp:80-161).
     cell_rows: equal-length sequences of 16-bit residue cells (str, bytes or ints, flag bits allowed)."""

@@ -28,6 +28,13 @@ class QChar {
 };
 
 class QString;
+class QByteArray;
+class QStringList;
+class QRegExp {   // only the pattern the reference uses: "\\s+" (Muscle.cpp:108)
+ public:
+  explicit QRegExp(const char* pattern) : p_(pattern) {}
+  std::string p_;
+};
 class QCharRef {
  public:
   QCharRef(QString& s, int i) : s_(s), i_(i) {}
@@ -45,6 +52,7 @@ class QString {
  public:
   QString() {}
   QString(const char* s) { while (s && *s) d_.push_back((unsigned short)(unsigned char)*s++); }
+  inline QString(const QByteArray& b);   // defined in qt_proc_dom.h
   static QString fromStd(const std::string& s) { QString q; for (unsigned char c : s) q.d_.push_back(c); return q; }
   std::string toStd() const { std::string s; for (unsigned short u : d_) s.push_back((char)(u & 0xff)); return s; }
   int length() const { return (int)d_.size(); }
@@ -82,6 +90,7 @@ class QString {
     d_.erase(d_.begin() + pos, d_.begin() + (long)end);
     return *this;
   }
+  inline QStringList split(const QRegExp& re) const;   // KeepEmptyParts, as Qt's default
   QString toLower() const { QString q = *this; for (auto& u : q.d_) if (u >= 'A' && u <= 'Z') u = (unsigned short)(u + 32); return q; }
   bool operator==(const QString& o) const { return d_ == o.d_; }
   bool operator!=(const QString& o) const { return d_ != o.d_; }
@@ -123,6 +132,25 @@ class QStringList : public QList<QString> {
     return false;
   }
 };
+
+inline QStringList QString::split(const QRegExp& re) const {
+  QStringList out;
+  if (re.p_ != "\\s+") return out;   // nothing else is needed here
+  auto sp = [](unsigned short u) { return u == ' ' || (u >= 9 && u <= 13); };
+  QString cur;
+  size_t i = 0;
+  while (i < d_.size()) {
+    if (sp(d_[i])) {
+      out << cur;
+      cur = QString();
+      while (i < d_.size() && sp(d_[i])) i++;
+    } else {
+      cur.append(QChar((int)d_[i++]));
+    }
+  }
+  out << cur;
+  return out;
+}
 
 class QIODevice {
  public:

@@ -153,3 +153,60 @@ def test_gpu_consensus_equals_the_references_own_code(nrows, ncols):
     with t.Context() as ctx:
         assert ctx.consensus(rows) == o.ref_consensus(rows)
         assert ctx.consensus(rows, plurality=nrows * 0.8) == o.ref_consensus(rows, nrows * 0.8)
+
+
+# ---- driven by the reference's OWN wrappers (oracle/_ref/libref_tools.so = tweakseq/Core/ClustalO.cpp, Muscle.cpp,
+# MAFFT.cpp, AlignmentTool.cpp compiled where they lie; QProcess stand-in that really forks and execs) -------------
+
+def _ref_tools():
+    from oracle import pyoracle as o
+    if not o.ref_tools_available():
+        pytest.skip("oracle/_ref/libref_tools.so not built (needs /root/reference at build time)")
+    return o
+
+
+def test_the_references_own_wrappers_probe_and_drive_the_binary(exe, tmp_path):
+    o = _ref_tools()
+    # getVersion() of each wrapper, run on tsq-aligner: what the editor would show as the tool's version
+    assert o.ref_tool_version("clustalo", exe).startswith("tsq-b200")          # ClustalO.cpp:100-111: stdout, trimmed
+    assert o.ref_tool_version("muscle", exe) == "0.1"                          # Muscle.cpp:100-112: second word of stdout
+    assert o.ref_tool_version("mafft", exe).startswith("tsq-b200")             # MAFFT.cpp:103-116: stderr
+    # makeCommand() of each wrapper: the argv is accepted and means what the wrapper means by it
+    fin, fout = str(tmp_path / "in.fa"), str(tmp_path / "out.fa")
+    write(fin, ["a", "b"], ["MKTAYIAKQR", "MKTAYIAKQK"])
+    for tool in ("clustalo", "muscle", "mafft"):
+        name, _, args, uses_stdout = o.ref_tool_command(tool, fin, fout, exe)
+        out = run(exe, *args, "--dry-run")
+        assert out.returncode == 0, (tool, args, out.stderr)
+        assert f"in={fin} " in out.stdout and "output=alignment" in out.stdout
+        assert ("out=<stdout>" in out.stdout) == uses_stdout                   # MAFFT.cpp:98: the alignment is stdout
+        if not uses_stdout:
+            assert f"out={fout} " in out.stdout
+
+
+@pytest.mark.gpu
+def test_gpu_editor_round_trip_with_reference_code_on_both_sides(exe, tmp_path):
+    """startAlignment() to readNewAlignment() with the reference's own code wherever it has any: its writer makes the
+    input file, its wrapper makes the argv (stdout redirected to the output file when the wrapper says so,
+    SeqEditMainWin.cpp:1655-1657), this repository's binary aligns on the B200, its reader parses the result."""
+    o = _ref_tools()
+    if not o.ref_fasta_available():
+        pytest.skip("oracle/_ref/libref_fasta.so not built")
+    import tweakseq_b200 as t
+    rng = np.random.default_rng(92)
+    root = rng.choice(list("ARNDCQEGHILKMFPSTWYV"), 120)
+    seqs = ["".join(c if rng.random() > 0.2 else rng.choice(list("ARNDCQEGHILKMFPSTWYV")) for c in root if rng.random() > 0.05)
+            for _ in range(10)]
+    labels = [f"p{k}" for k in range(10)]
+    comments = [f">{l} from the editor" for l in labels]
+    want, order = t.B200Gotoh().multiple_alignment(seqs)
+    for tool in ("clustalo", "muscle", "mafft"):
+        fin, fout = str(tmp_path / f"{tool}.in.fa"), str(tmp_path / f"{tool}.out.fa")
+        o.ref_fasta_write(fin, labels, seqs, comments)
+        _, exec_, args, uses_stdout = o.ref_tool_command(tool, fin, fout, exe)
+        out = subprocess.run([exec_, *args], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, (tool, out.stdout, out.stderr)
+        if uses_stdout:
+            open(fout, "w").write(out.stdout)
+        got_labels, got_rows, _ = o.ref_fasta_read(fout)
+        assert got_labels == [labels[r] for r in order] and got_rows == [want[r] for r in order], tool
