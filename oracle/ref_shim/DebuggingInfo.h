@@ -2,5 +2,5 @@
 #ifndef TSQ_REF_DEBUGGINGINFO_H
 #define TSQ_REF_DEBUGGINGINFO_H
 struct DebuggingInfo { const char* header(const char* s = "") { return s; } };
-static DebuggingInfo trace;
+[[maybe_unused]] static DebuggingInfo trace;
 #endif
