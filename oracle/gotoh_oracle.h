@@ -12,7 +12,9 @@
  * section 8c; what it takes from the reference is the substitution matrix and letter map
  * (tweakseq/Core/Annotations/Consensus.cpp:34-69) and the residue-cell filtering rule
  * (tweakseq/Core/Sequence.cpp:57-69).  It is pinned against hand-derived known answers and
- * an independent numpy formulation in tests/.
+ * an independent numpy formulation in tests/.  What the reference does implement on this path
+ * (consensus, FASTA reader / writer, cell filter, tool wrappers) is compiled from its own sources
+ * into oracle/_ref/ (oracle/Makefile) and pins those pieces directly; see DESIGN.md section 3.1.
  */
 #ifndef TSQ_GOTOH_ORACLE_H
 #define TSQ_GOTOH_ORACLE_H
