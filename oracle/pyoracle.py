@@ -148,6 +148,46 @@ def ref_tool_version(tool: str, exe: str) -> str:
     return buf.value.decode()
 
 
+_REF_QT_SO = os.path.join(_HERE, "_ref", "libref_qt_adapter.so")
+_ref_qt = None
+
+
+def ref_qt_adapter_available() -> bool:
+    """oracle/_ref/libref_qt_adapter.so: host/qt/B200GotohTool.cpp (the real Qt adapter) compiled against the
+    reference's AlignmentTool.h / ClustalO.cpp and the functional Qt stand-ins; links libtsqb200.so."""
+    if not os.path.exists(_REF_QT_SO) and os.path.exists("/root/reference/tweakseq/Core/ClustalO.cpp"):
+        subprocess.call(["make", "-C", _HERE, "_ref/libref_qt_adapter.so"], stdout=subprocess.DEVNULL)
+    return os.path.exists(_REF_QT_SO)
+
+
+def _ref_qt_lib():
+    global _ref_qt
+    if _ref_qt is None:
+        _ref_qt = C.CDLL(_REF_QT_SO)
+        _ref_qt.tsq_qt_settings_round_trip.argtypes = [C.c_char_p, C.c_ulong]
+        _ref_qt.tsq_qt_worker_run.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                              C.c_char_p, C.c_ulong]
+    return _ref_qt
+
+
+def qt_settings_round_trip() -> dict:
+    """ClustalO (reference) and B200GotohTool (host/qt) write into one settings element and read it back."""
+    buf = C.create_string_buffer(1 << 14)
+    if _ref_qt_lib().tsq_qt_settings_round_trip(buf, len(buf)) != 0:
+        raise RuntimeError("tsq_qt_settings_round_trip failed")
+    return dict(line.split("=", 1) for line in buf.value.decode().splitlines())
+
+
+def qt_worker_run(fin: str, fout: str, align_in_process: bool = True):
+    """B200GotohWorker::start() as startAlignment would use it: (exit code, exit status, log lines)."""
+    buf = C.create_string_buffer(1 << 16)
+    ec, es = C.c_int(), C.c_int()
+    if _ref_qt_lib().tsq_qt_worker_run(fin.encode(), fout.encode(), 1 if align_in_process else 0, C.byref(ec), C.byref(es),
+                                       buf, len(buf)) != 0:
+        raise RuntimeError("tsq_qt_worker_run failed")
+    return ec.value, es.value, buf.value.decode().splitlines()
+
+
 def ref_consensus(cell_rows, plurality: float = -1.0) -> str:
     """Consensus::calculate of the reference itself (tweakseq/Core/Annotations/Consensus.cpp:80-161).
     cell_rows: equal-length sequences of 16-bit residue cells (str, bytes or ints, flag bits allowed)."""

@@ -13,6 +13,7 @@
 #ifndef TSQ_REF_QT_MIN_H
 #define TSQ_REF_QT_MIN_H
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -91,6 +92,17 @@ class QString {
     return *this;
   }
   inline QStringList split(const QRegExp& re) const;   // KeepEmptyParts, as Qt's default
+  static QString number(int v) { return fromStd(std::to_string(v)); }
+  static QString fromUtf8(const char* s) { return QString(s); }
+  int toInt(bool* ok = nullptr) const {
+    const std::string t = trimmed().toStd();
+    char* end = nullptr;
+    const long v = strtol(t.c_str(), &end, 10);
+    const bool good = !t.empty() && end && *end == 0;
+    if (ok) *ok = good;
+    return good ? (int)v : 0;
+  }
+  inline QByteArray toLocal8Bit() const;   // defined in qt_proc_dom.h
   QString toLower() const { QString q = *this; for (auto& u : q.d_) if (u >= 'A' && u <= 'Z') u = (unsigned short)(u + 32); return q; }
   bool operator==(const QString& o) const { return d_ == o.d_; }
   bool operator!=(const QString& o) const { return d_ != o.d_; }

@@ -210,3 +210,27 @@ def test_gpu_editor_round_trip_with_reference_code_on_both_sides(exe, tmp_path):
             open(fout, "w").write(out.stdout)
         got_labels, got_rows, _ = o.ref_fasta_read(fout)
         assert got_labels == [labels[r] for r in order] and got_rows == [want[r] for r in order], tool
+
+
+@pytest.mark.gpu
+def test_gpu_qt_worker_runs_the_alignment_in_process(tmp_path):
+    """host/qt/B200GotohTool.cpp itself (compiled against the reference's AlignmentTool.h over functional Qt
+    stand-ins): B200GotohWorker::start() -> tool->run() -> tsq_run_fasta on the B200 -> finished(0, NormalExit), and
+    the output file read by the reference's own FASTA reader is the in-memory alignment."""
+    from oracle import pyoracle as o
+    if not (o.ref_qt_adapter_available() and o.ref_fasta_available()):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    import tweakseq_b200 as t
+    rng = np.random.default_rng(93)
+    root = rng.choice(list("ARNDCQEGHILKMFPSTWYV"), 100)
+    seqs = ["".join(c if rng.random() > 0.2 else rng.choice(list("ARNDCQEGHILKMFPSTWYV")) for c in root if rng.random() > 0.05)
+            for _ in range(9)]
+    labels = [f"q{k}" for k in range(9)]
+    fin, fout = str(tmp_path / "in.fa"), str(tmp_path / "out.fa")
+    o.ref_fasta_write(fin, labels, seqs, [f">{l}" for l in labels])
+    code, status, log = o.qt_worker_run(fin, fout, align_in_process=True)
+    assert (code, status) == (0, 0), log
+    assert any("progressive alignment" in l for l in log)
+    want, order = t.B200Gotoh().multiple_alignment(seqs)
+    got_labels, got_rows, _ = o.ref_fasta_read(fout)
+    assert got_labels == [labels[r] for r in order] and got_rows == [want[r] for r in order]
