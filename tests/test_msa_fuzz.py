@@ -30,7 +30,7 @@ def jobs(draw):
     return seqs, left, right, go, ge, knobs
 
 
-@settings(max_examples=150, deadline=None)
+@settings(max_examples=int(__import__("os").environ.get("TSQ_FUZZ_EXAMPLES", "150")), deadline=None)
 @given(jobs())
 def test_three_statements_of_the_alignment_agree(emul, job):
     seqs, left, right, go, ge, knobs = job
