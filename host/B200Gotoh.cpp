@@ -32,6 +32,8 @@ void B200Gotoh::writeSettings(SettingsDocument& doc) {  // ClustalO.cpp:54-61
   e.children.push_back({"gap_open", std::to_string(gapOpen)});
   e.children.push_back({"gap_extend", std::to_string(gapExtend)});
   e.children.push_back({"device", std::to_string(device)});
+  e.children.push_back({"devices", std::to_string(devices)});
+  e.children.push_back({"alphabet", detectAlphabet ? "auto" : nucleotide ? "nucleotide" : "protein"});
   e.children.push_back({"align_in_process", alignInProcess ? "yes" : "no"});
   doc.alignment_tools.push_back(e);
 }
@@ -45,6 +47,11 @@ void B200Gotoh::readSettings(SettingsDocument& doc) {  // ClustalO.cpp:63-86
       if (kv.first == "gap_open") gapOpen = std::stoi(kv.second);
       if (kv.first == "gap_extend") gapExtend = std::stoi(kv.second);
       if (kv.first == "device") device = std::stoi(kv.second);
+      if (kv.first == "devices") devices = std::stoi(kv.second);
+      if (kv.first == "alphabet") {
+        detectAlphabet = kv.second == "auto";
+        nucleotide = kv.second == "nucleotide";
+      }
       if (kv.first == "align_in_process") alignInProcess = kv.second == "yes";
     }
   }
@@ -61,6 +68,7 @@ static void fill(tsq_params& p, const B200Gotoh& t) {
   p.gap_open = t.gapOpen;
   p.gap_extend = t.gapExtend;
   p.device = t.device;
+  p.n_devices = t.devices;
   if (t.identityDistance) p.flags |= TSQ_FLAG_IDENTITY;
   if (t.alignInProcess) p.flags |= TSQ_FLAG_MSA_OUT;
 }
@@ -68,6 +76,7 @@ static void fill(tsq_params& p, const B200Gotoh& t) {
 int B200Gotoh::run(const std::string& fin, const std::string& fout, const LogSink& log, CancelFlag* cancel) {
   tsq_params p;
   fill(p, *this);
+  if (detectAlphabet) p.alphabet = TSQ_ALPHABET_AUTO;
   struct Ctx { const LogSink* log; } ctx{&log};
   auto cb = [](void* user, const char* line) {
     const LogSink* l = static_cast<Ctx*>(user)->log;

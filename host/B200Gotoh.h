@@ -43,10 +43,14 @@ class B200Gotoh : public AlignmentTool {
                 std::string* error = nullptr);
 
   int gapOpen = -1, gapExtend = -1, device = 0;  // <0: library defaults (11/1 protein)
+  int devices = 1;                               // how many B200s of the box one job uses (tsq_params.n_devices;
+                                                 // -1 = all): the pair space is cut into that many slabs
   bool nucleotide = false;
+  bool detectAlphabet = false;                   // run(): decide protein / nucleotide from the file's residues
+                                                 // (a project holds either kind: SequenceFile::DNA / ::Proteins)
   bool identityDistance = false;                 // ClustalW-style 1 - identities/min(len)
   bool alignInProcess = true;                    // run(): fout = the multiple alignment (FASTA, tree order) that
-                                                 // readNewAlignment ingests (the tree goes to <fout>.dnd);
+                                                 // readNewAlignment ingests;
                                                  // false: fout = the distance matrix for clustalo --distmat-in
 
  private:

@@ -32,6 +32,8 @@ void B200GotohTool::writeSettings(QDomDocument &doc, QDomElement &parentElem)
 	XMLHelper::addElement(doc, pelem, "gap_open", QString::number(gapOpen));
 	XMLHelper::addElement(doc, pelem, "gap_extend", QString::number(gapExtend));
 	XMLHelper::addElement(doc, pelem, "device", QString::number(device));
+	XMLHelper::addElement(doc, pelem, "devices", QString::number(devices));
+	XMLHelper::addElement(doc, pelem, "alphabet", (alphabet == TSQ_NUCLEOTIDE ? "nucleotide" : alphabet == TSQ_PROTEIN ? "protein" : "auto"));
 	XMLHelper::addElement(doc, pelem, "align_in_process", (alignInProcess ? "yes" : "no"));
 }
 
@@ -48,6 +50,8 @@ void B200GotohTool::readSettings(QDomDocument &doc)
 			if (elem.tagName() == "gap_open") gapOpen = elem.text().toInt();
 			if (elem.tagName() == "gap_extend") gapExtend = elem.text().toInt();
 			if (elem.tagName() == "device") device = elem.text().toInt();
+			if (elem.tagName() == "devices") devices = elem.text().toInt();
+			if (elem.tagName() == "alphabet") alphabet = (elem.text() == "nucleotide" ? TSQ_NUCLEOTIDE : elem.text() == "protein" ? TSQ_PROTEIN : TSQ_ALPHABET_AUTO);
 			if (elem.tagName() == "align_in_process") alignInProcess = (elem.text() == "yes");
 			elem = elem.nextSiblingElement();
 		}
@@ -69,6 +73,8 @@ int B200GotohTool::run(const QString &fin, const QString &fout, QObject *logRece
 	p.gap_open = gapOpen;
 	p.gap_extend = gapExtend;
 	p.device = device;
+	p.n_devices = devices;
+	p.alphabet = alphabet; // auto: tsq_run_fasta decides from the residues, as clustalo does without --seqtype
 	if (alignInProcess) p.flags |= TSQ_FLAG_MSA_OUT;
 	return tsq_run_fasta(fin.toLocal8Bit().constData(), fout.toLocal8Bit().constData(), &p, forwardLog, logReceiver, cancel);
 }
@@ -81,6 +87,8 @@ void B200GotohTool::init()
 	gapOpen = -1;
 	gapExtend = -1;
 	device = 0;
+	devices = 1;
+	alphabet = TSQ_ALPHABET_AUTO;
 	alignInProcess = true;
 }
 

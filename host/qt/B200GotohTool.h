@@ -25,6 +25,9 @@ class B200GotohTool : public AlignmentTool
 		virtual int run(const QString &fin, const QString &fout, QObject *logReceiver, volatile int *cancel);
 
 		int gapOpen, gapExtend, device;
+		int devices;   // B200s of the box one job uses (tsq_params.n_devices; -1 = all of them)
+		int alphabet;  // TSQ_ALPHABET_AUTO (default: decided from the exported residues), TSQ_PROTEIN, TSQ_NUCLEOTIDE;
+		               // Project::sequenceDataType() may set it: SequenceFile::DNA -> TSQ_NUCLEOTIDE, ::Proteins -> TSQ_PROTEIN
 		bool alignInProcess; // fout = the multiple alignment readNewAlignment ingests (no clustalo needed); else the matrix
 
 	private:

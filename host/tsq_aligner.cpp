@@ -31,6 +31,7 @@ struct Options {
   bool to_stdout = false, version = false, dry_run = false, verbose = false, keep_distmat = false, matrix_only = false;
   int alphabet = -1;   // -1 = detect from the residues
   int gap_open = -1, gap_extend = -1, device = 0;
+  int devices = 1;   // --devices N | all: B200s of the box this job is spread over (tsq_params.n_devices)
   bool identity = false;
   bool input_order = false;   // clustalo --output-order=input-order (default: tree order, what tweakseq asks for)
 };
@@ -41,12 +42,16 @@ void usage(FILE* f) {
         "       tsq-aligner [--auto --thread N] IN.fa    (mafft style: alignment on stdout)\n"
         "       tsq-aligner --version | -version\n"
         "options: --seqtype=Protein|DNA|RNA, --amino, --nuc (default: detected), --gap-open N, --gap-extend N,\n"
-        "         --device N, --identity-distance, --distmat-out (keep OUT.fa.distmat), --matrix-only (OUT = matrix),\n"
+        "         --device N, --devices N|all (several B200s; env TSQ_DEVICES), --identity-distance, --distmat-out (keep OUT.fa.distmat), --matrix-only (OUT = matrix),\n"
         "         --dry-run (print the parsed job and exit); clustalo's --force -v --outfmt=fa --output-order=... are accepted\n",
         f);
 }
 
-bool starts_with(const std::string& s, const char* p) { return s.compare(0, strlen(p), p) == 0; }
+// exactly --name or --name=value (prefix matching would take clustalo's --infmt or mafft's --inputorder for --in)
+bool is_opt(const std::string& s, const char* name) {
+  const size_t l = strlen(name);
+  return s.compare(0, l, name) == 0 && (s.size() == l || s[l] == '=');
+}
 
 // Returns 0 = ok, 2 = usage error (message in err).
 int parse(int argc, char** argv, Options& o, std::string& err) {
@@ -63,18 +68,23 @@ int parse(int argc, char** argv, Options& o, std::string& err) {
     std::string v;
     if (a == "--version" || a == "-version") o.version = true;
     else if (a == "-h" || a == "--help") { err = "help"; return 2; }
-    else if (a == "-i" || a == "-in" || starts_with(a, "--in") || starts_with(a, "--infile")) { if (!value(o.in)) return 2; }
-    else if (a == "-o" || a == "-out" || starts_with(a, "--out=") || a == "--out" || starts_with(a, "--outfile")) { if (!value(o.out)) return 2; }
-    else if (starts_with(a, "--outfmt")) {
+    else if (a == "-i" || a == "-in" || is_opt(a, "--in") || is_opt(a, "--infile")) { if (!value(o.in)) return 2; }
+    else if (a == "-o" || a == "-out" || is_opt(a, "--out") || is_opt(a, "--outfile")) { if (!value(o.out)) return 2; }
+    else if (is_opt(a, "--infmt")) {
+      if (!value(v)) return 2;
+      if (v != "fa" && v != "fasta" && v != "a2m") { err = "only FASTA input is read (--infmt=" + v + ")"; return 2; }
+    }
+    else if (a == "--inputorder" || a == "--reorder") {}                    // mafft: row order; tree order is what tweakseq asks for
+    else if (is_opt(a, "--outfmt")) {
       if (!value(v)) return 2;
       if (v != "fa" && v != "fasta" && v != "a2m") { err = "only FASTA output is produced (--outfmt=" + v + ")"; return 2; }
     }
-    else if (starts_with(a, "--output-order")) {
+    else if (is_opt(a, "--output-order")) {
       if (!value(v)) return 2;
       if (v == "input-order") o.input_order = true;
       else if (v != "tree-order") { err = "unknown --output-order " + v; return 2; }
     }
-    else if (starts_with(a, "--seqtype") || a == "-t") {
+    else if (is_opt(a, "--seqtype") || a == "-t") {
       if (!value(v)) return 2;
       for (char& ch : v) ch = (char)tolower((unsigned char)ch);
       if (v == "protein") o.alphabet = TSQ_PROTEIN;
@@ -83,10 +93,11 @@ int parse(int argc, char** argv, Options& o, std::string& err) {
     }
     else if (a == "--amino") o.alphabet = TSQ_PROTEIN;
     else if (a == "--nuc") o.alphabet = TSQ_NUCLEOTIDE;
-    else if (starts_with(a, "--gap-open")) { if (!value(v)) return 2; o.gap_open = atoi(v.c_str()); }
-    else if (starts_with(a, "--gap-extend")) { if (!value(v)) return 2; o.gap_extend = atoi(v.c_str()); }
-    else if (starts_with(a, "--device")) { if (!value(v)) return 2; o.device = atoi(v.c_str()); }
-    else if (starts_with(a, "--thread")) { if (!value(v)) return 2; }       // mafft: host threads mean nothing here
+    else if (is_opt(a, "--gap-open")) { if (!value(v)) return 2; o.gap_open = atoi(v.c_str()); }
+    else if (is_opt(a, "--gap-extend")) { if (!value(v)) return 2; o.gap_extend = atoi(v.c_str()); }
+    else if (is_opt(a, "--device")) { if (!value(v)) return 2; o.device = atoi(v.c_str()); }
+    else if (is_opt(a, "--devices")) { if (!value(v)) return 2; o.devices = v == "all" ? -1 : atoi(v.c_str()); }
+    else if (is_opt(a, "--thread") || is_opt(a, "--threads")) { if (!value(v)) return 2; }       // mafft: host threads mean nothing here
     else if (a == "--identity-distance") o.identity = true;
     else if (a == "--distmat-out") o.keep_distmat = true;
     else if (a == "--matrix-only") o.matrix_only = true;
@@ -96,6 +107,8 @@ int parse(int argc, char** argv, Options& o, std::string& err) {
     else if (!a.empty() && a[0] == '-' && a != "-") { err = "unknown option " + a; return 2; }
     else positional.push_back(a);
   }
+  if (const char* e = getenv("TSQ_DEVICES"))   // an unmodified tweakseq cannot add options to the wrapper's argv
+    if (o.devices == 1) o.devices = strcmp(e, "all") == 0 ? -1 : atoi(e);
   if (o.version) return 0;
   if (o.in.empty() && positional.size() == 1) { o.in = positional[0]; positional.clear(); }   // mafft style
   if (!positional.empty()) { err = "unexpected argument " + positional[0]; return 2; }
@@ -166,9 +179,9 @@ int main(int argc, char** argv) {
     out = tmpl;
   }
   if (o.dry_run) {
-    printf("in=%s out=%s alphabet=%s gap_open=%d gap_extend=%d device=%d output=%s order=%s\n", o.in.c_str(),
+    printf("in=%s out=%s alphabet=%s gap_open=%d gap_extend=%d device=%d devices=%d output=%s order=%s\n", o.in.c_str(),
            o.to_stdout ? "<stdout>" : out.c_str(), alphabet == TSQ_NUCLEOTIDE ? "nucleotide" : "protein", o.gap_open, o.gap_extend,
-           o.device, o.matrix_only ? "matrix" : "alignment", o.input_order ? "input" : "tree");
+           o.device, o.devices, o.matrix_only ? "matrix" : "alignment", o.input_order ? "input" : "tree");
     return 0;
   }
   tsq_params p;
@@ -177,6 +190,7 @@ int main(int argc, char** argv) {
   p.gap_open = o.gap_open;
   p.gap_extend = o.gap_extend;
   p.device = o.device;
+  p.n_devices = o.devices;
   if (!o.matrix_only) p.flags |= TSQ_FLAG_MSA_OUT;
   if (o.keep_distmat) p.flags |= TSQ_FLAG_KEEP_DISTMAT;
   if (o.identity) p.flags |= TSQ_FLAG_IDENTITY;

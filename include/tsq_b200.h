@@ -38,7 +38,7 @@ extern "C" {
 #endif
 
 #define TSQ_VERSION_MAJOR 0
-#define TSQ_VERSION_MINOR 1
+#define TSQ_VERSION_MINOR 2
 
 /* status codes */
 #define TSQ_OK 0
@@ -54,6 +54,9 @@ extern "C" {
 
 #define TSQ_PROTEIN 0    /* 23 symbols ARNDCQEGHILKMFPSTWYVBZX, Consensus.cpp:34-69 */
 #define TSQ_NUCLEOTIDE 1 /* 5 symbols ACGTN (U->T, other letters -> N) */
+#define TSQ_ALPHABET_AUTO (-1) /* tsq_run_fasta only: decided from the residues of the file, as clustalo does without
+                                  --seqtype (>= 90 % of the letters in ACGTUN = nucleotide); tweakseq projects hold
+                                  either kind (SequenceFile::DNA / ::Proteins, Core/SequenceFile.h) */
 
 /* flags */
 #define TSQ_FLAG_FORCE_S32 1u     /* never use the packed 16-bit kernel */
@@ -65,12 +68,15 @@ extern "C" {
                                      the ClustalW pairwise distance.  Scores are unchanged. */
 
 #define TSQ_FLAG_MSA_OUT 16u       /* tsq_run_fasta only: write the multiple alignment (tsq_msa) to fout, in tree
-                                     order (the guide tree still goes to <fout>.dnd) */
+                                     order (the guide tree goes to <fout>.dnd only with TSQ_FLAG_KEEP_TREE) */
 #define TSQ_FLAG_KEEP_DISTMAT 32u /* with TSQ_FLAG_MSA_OUT: also write the distance matrix, to <fout>.distmat
                                      (n^2 numbers of text; an external aligner writes it only on request too) */
 
 #define TSQ_FLAG_INPUT_ORDER 64u  /* with TSQ_FLAG_MSA_OUT: rows in the order of the input file instead of tree order
                                      (clustalo's --output-order=input-order) */
+
+#define TSQ_FLAG_KEEP_TREE 128u    /* with TSQ_FLAG_MSA_OUT: also write the guide tree, to <fout>.dnd (without MSA_OUT the
+                                     tree always accompanies the matrix: the two files clustalo takes) */
 
 typedef struct tsq_ctx tsq_ctx;
 
@@ -84,6 +90,12 @@ typedef struct tsq_params {
   int32_t part_rank;     /* this context's share of the pair space: rank ... */
   int32_t part_world;    /* ... of world (1 = everything).  See tsq_partition. */
   uint32_t flags;        /* TSQ_FLAG_* */
+  int32_t n_devices;     /* 0 or 1: the one device above.  2, 4, 8, ...: this context drives devices
+                            device .. device + n_devices - 1 of the box from one process (one host thread and
+                            one stream per device); the sorted rows are cut into n_devices slabs by the same
+                            planner as part_rank/part_world (which must then be 0/1), every device finalizes
+                            its own slab and copies it over its OWN PCIe link into the one pinned host result.
+                            -1 = every usable device of the box (tsq_device_count).  SURVEY.md section 8b/8e. */
 } tsq_params;
 
 typedef struct tsq_stats {
@@ -173,6 +185,29 @@ int tsq_partition_of(tsq_ctx *ctx, int32_t rank, uint64_t *begin, uint64_t *end)
 /* Sorted-order slab complete on this device -> original-order scores (+distances). */
 int tsq_finalize(tsq_ctx *ctx);
 int tsq_device_results(tsq_ctx *ctx, void **d_scores, void **d_distances, uint64_t *count);
+/*
+ * The device buffer of sorted-order scores this context really holds: packed indices [*first, *first + *count).
+ * The whole triangle on a single-rank context and on rank 0 of a partition whose slabs must be gathered; only the
+ * rank's own slab otherwise (a rank of world 8 at 100 000 sequences holds 2.5 GB, not 20 GB).  After tsq_upload.
+ */
+int tsq_device_slab(tsq_ctx *ctx, void **d_sorted_scores, uint64_t *first, uint64_t *count);
+/*
+ * How the results of a partitioned job (part_world > 1) come together.  *sharded = 1: the length sort left the
+ * submitted order unchanged (fixed-length input, no empty sequence, no identity keys), so a rank's slab is a
+ * contiguous piece of the final packed triangle: every rank runs tsq_finalize/tsq_download on its own slab and
+ * copies it to the host over its own PCIe link -- no gather at all (point all ranks at one shared host buffer with
+ * tsq_set_result_buffers).  *sharded = 0: the un-sort scatters a slab over the triangle: gather the slabs into
+ * rank 0's buffer (tsq_device_slab; NCCL send/recv) and finalize/download there.  After tsq_upload.
+ */
+int tsq_results_sharded(tsq_ctx *ctx, int *sharded);
+/*
+ * Caller-owned host memory for the results instead of the library's own pinned buffers: `count` = n*(n-1)/2
+ * int32 scores and (unless NULL / TSQ_FLAG_NO_DISTANCES) as many doubles, e.g. one POSIX shared-memory segment
+ * that every rank of a torchrun job maps.  The library page-locks what it writes (cudaHostRegister) on first use
+ * and releases it in tsq_destroy or at the next call of this function; tsq_scores/tsq_distances then return these
+ * pointers.  NULL, NULL, 0 restores the library's buffers.
+ */
+int tsq_set_result_buffers(tsq_ctx *ctx, int32_t *scores, double *distances, uint64_t count);
 
 /*
  * Guide tree (UPGMA, average linkage) from the distance matrix of the last run -- the next
@@ -252,6 +287,9 @@ int tsq_plan_partition(const tsq_params *params, const uint32_t *lengths, uint32
                        int32_t world, uint64_t *begins, uint64_t *ends);
 
 int tsq_get_stats(tsq_ctx *ctx, tsq_stats *out);
+/* Multi-device contexts (n_devices > 1): the figures of device number `index` (0 .. n_devices-1) alone;
+ * tsq_get_stats then reports the whole job (sums; kernel_ms = the slowest device). */
+int tsq_get_device_stats(tsq_ctx *ctx, int32_t index, tsq_stats *out);
 
 /*
  * Integer-pipe issue-rate probe ("measure, don't assume"): thread-level

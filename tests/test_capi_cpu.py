@@ -31,7 +31,7 @@ def test_version_and_status_strings():
     L = t.load_library()
     ma, mi = C.c_int(), C.c_int()
     assert L.tsq_version(C.byref(ma), C.byref(mi)) == 0
-    assert (ma.value, mi.value) == (0, 1)
+    assert (ma.value, mi.value) == (0, 2)
     assert b"sm_100a" in L.tsq_version_string()
     assert L.tsq_status_string(0) == b"ok"
     assert L.tsq_status_string(-2) == b"no sm_100 CUDA device"
@@ -42,6 +42,23 @@ def test_default_params():
     t.load_library().tsq_default_params(C.byref(p))
     assert p.struct_size == C.sizeof(capi.Params)
     assert (p.alphabet, p.gap_open, p.gap_extend, p.part_rank, p.part_world, p.flags) == (0, -1, -1, 0, 1, 0)
+    assert p.n_devices == 1
+
+
+def test_an_older_callers_shorter_parameter_block_is_accepted():
+    """struct_size lets tsq_params grow: a caller compiled against 0.1 (no n_devices) still gets through the
+    parameter checks (and then, here, fails on the missing device, not on the block)."""
+    L = t.load_library()
+    h = C.c_void_p()
+    p = capi.Params()
+    L.tsq_default_params(C.byref(p))
+    p.struct_size = capi.Params.n_devices.offset
+    p.n_devices = 99                     # beyond struct_size: must be ignored
+    assert L.tsq_create(C.byref(h), C.byref(p)) in (0, -2)
+    if h.value:
+        L.tsq_destroy(h)
+    p.struct_size = C.sizeof(capi.Params) + 8
+    assert L.tsq_create(C.byref(h), C.byref(p)) == -1
 
 
 def test_parameter_validation_happens_before_device_probe():

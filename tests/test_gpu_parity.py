@@ -198,14 +198,18 @@ def test_partition_slabs_tile_the_matrix():
         ctx = t.Context(part_rank=r, part_world=world, flags=t.FLAG_NO_DISTANCES)
         ctx.set_sequences(seqs); ctx.upload(); ctx.compute(); ctx.synchronize()
         ranges.append(ctx.partition())
-        bufs.append(torch.as_tensor(ctx.device_scores(), device="cuda"))
+        arr, first = ctx.device_slab()                 # rank 0: the whole triangle; the others: their slab only
+        assert first == (0 if r == 0 else ranges[r][0])
+        bufs.append(torch.as_tensor(arr, device="cuda"))
         ctxs.append(ctx)
     assert ranges == capi.plan_partition([len(s) for s in seqs], world)
     assert ranges[0][0] == 0 and ranges[-1][1] == len(full)
     root = bufs[0]
+    assert len(root) == len(full)
     for r in range(1, world):
         b, e = ranges[r]
-        root[b:e] = bufs[r][b:e]                       # what the NCCL gather does across ranks
+        assert len(bufs[r]) == e - b
+        root[b:e] = bufs[r]                            # what the NCCL gather does across ranks
     ctxs[0].finalize(); ctxs[0].download()
     assert (ctxs[0].scores() == full).all()
     for c in ctxs:

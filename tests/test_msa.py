@@ -342,10 +342,11 @@ def test_gpu_run_fasta_writes_the_alignment_readNewAlignment_expects(tmp_path):
         assert len(by_label[l]) == len(r) and all((a == "-") == (b == "-") for a, b in zip(by_label[l], r))
     want, _ = o.msa([o.encode(s) for s in seqs], o.matrix(0), 11, 1, left, right)
     assert rows == want
-    # the tree is written next to it; the matrix (n^2 numbers of text) only on request
-    assert os.path.exists(fout + ".dnd") and not os.path.exists(fout + ".distmat")
-    tool.keep_distmat = True
+    # nothing else appears next to the editor's temporary file: tree and matrix (n^2 numbers of text) on request only
+    assert not os.path.exists(fout + ".dnd") and not os.path.exists(fout + ".distmat")
+    tool.keep_distmat = tool.keep_tree = True
     assert tool.run(fin, fout) == 0
+    assert os.path.exists(fout + ".dnd")
     from tweakseq_b200.fasta import read_distmat
     lab, mat = read_distmat(fout + ".distmat")
     assert lab == labels and len(mat) == len(seqs)

@@ -18,7 +18,9 @@ AA = "ARNDCQEGHILKMFPSTWYVBZX"
 cases = [
     (0, ["".join(rng.choice(list(AA), int(l))) for l in rng.integers(0, 400, 300)] + [""]),
     (1, ["".join(rng.choice(list("ACGT"), int(l))) for l in rng.integers(20, 900, 60)] + synth.nucleotide(4, 8000, 9500, 3)),
-    (0, synth.protein(256, 300, 2)),
+    (0, synth.protein(256, 300, 2)),          # fixed length: results stay sharded, every rank downloads its slab
+    (0, synth.protein(1001, 120, 7)),
+    (1, synth.nucleotide(24, 9000, 9000, 9)),  # fixed length, wavefront kernel
 ]
 for alphabet, seqs in cases:
     run = ShardedRun(seqs, alphabet=alphabet, device=local)
@@ -29,9 +31,9 @@ for alphabet, seqs in cases:
         mat = o.matrix(alphabet)
         ref, _ = o.all_pairs(enc, mat, 10 if alphabet else 11, 1, nthreads=os.cpu_count())
         selfs = np.array([o.self_score(e, mat) for e in enc], dtype=np.int32)
-        assert (run.ctx.scores() == ref).all(), "scores differ"
-        assert run.ctx.distances().tobytes() == o.distances(ref, selfs).tobytes(), "distances differ"
-        print(f"sharded ok: world {world}, alphabet {alphabet}, n {len(seqs)}, ranges {run.ranges}", flush=True)
+        assert (run.scores() == ref).all(), "scores differ"
+        assert np.asarray(run.distances()).tobytes() == o.distances(ref, selfs).tobytes(), "distances differ"
+        print(f"sharded ok: world {world}, alphabet {alphabet}, n {len(seqs)}, results {'sharded over the ranks (own PCIe links)' if run.sharded else 'gathered to rank 0 (NCCL)'}, ranges {run.ranges}", flush=True)
     run.close()
 dist.barrier()
 dist.destroy_process_group()

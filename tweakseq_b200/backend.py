@@ -63,9 +63,11 @@ class B200Gotoh(AlignmentTool):
         self.gap_open = -1
         self.gap_extend = -1
         self.device = 0
+        self.devices = 1           # B200s of the box one job uses (tsq_params.n_devices; -1 = all of them)
         self.identity = False      # ClustalW-style identity distance instead of the score distance
         self.align = True          # run(): fout = the multiple alignment readNewAlignment ingests; False: the distance matrix
         self.keep_distmat = False  # with align: also write <fout>.distmat
+        self.keep_tree = False     # with align: also write <fout>.dnd (without align the tree always accompanies the matrix)
         self.last_stats: dict = {}
 
     def inProcess(self): return True
@@ -83,6 +85,8 @@ class B200Gotoh(AlignmentTool):
         ET.SubElement(e, "gap_open").text = str(self.gap_open)
         ET.SubElement(e, "gap_extend").text = str(self.gap_extend)
         ET.SubElement(e, "device").text = str(self.device)
+        ET.SubElement(e, "devices").text = str(self.devices)
+        ET.SubElement(e, "alphabet").text = {capi.ALPHABET_AUTO: "auto", capi.NUCLEOTIDE: "nucleotide"}.get(self.alphabet, "protein")
         ET.SubElement(e, "align_in_process").text = "yes" if self.align else "no"
 
     def readSettings(self, doc: ET.Element):
@@ -100,6 +104,10 @@ class B200Gotoh(AlignmentTool):
                     self.gap_extend = int(elem.text)
                 if elem.tag == "device":
                     self.device = int(elem.text)
+                if elem.tag == "devices":
+                    self.devices = int(elem.text)
+                if elem.tag == "alphabet":
+                    self.alphabet = {"auto": capi.ALPHABET_AUTO, "nucleotide": capi.NUCLEOTIDE}.get(elem.text or "", capi.PROTEIN)
                 if elem.tag == "align_in_process":
                     self.align = (elem.text or "") == "yes"
         self.getVersion()
@@ -116,21 +124,23 @@ class B200Gotoh(AlignmentTool):
     def run(self, fin, fout, log=None, cancel: C.c_int | None = None) -> int:
         """FASTA file in (what Project::exportFASTA wrote); out, with ``align`` set (the default), the
         multiple alignment itself (FASTA, tree order): the file Project::readNewAlignment
-        (Project.cpp:908-1032) reads back, no external aligner involved -- the tree then goes to <fout>.dnd
-        and, with ``keep_distmat``, the matrix to <fout>.distmat.  With ``align`` off, fout is the PHYLIP distance matrix for clustalo.
+        (Project.cpp:908-1032) reads back, no external aligner involved -- with ``keep_tree`` the tree goes to
+        <fout>.dnd and with ``keep_distmat`` the matrix to <fout>.distmat.  ``alphabet`` may be ALPHABET_AUTO here
+        (decided from the file's residues).  With ``align`` off, fout is the PHYLIP distance matrix for clustalo.
 
         Returns the exit status startAlignment()/alignmentFinished() would see (0 = success:
         SeqEditMainWin.cpp:836-861)."""
         flags = ((capi.FLAG_IDENTITY if self.identity else 0) | (capi.FLAG_MSA_OUT if self.align else 0) |
-                 (capi.FLAG_KEEP_DISTMAT if self.keep_distmat else 0))
+                 (capi.FLAG_KEEP_DISTMAT if self.keep_distmat else 0) | (capi.FLAG_KEEP_TREE if self.keep_tree else 0))
         return capi.run_fasta(fin, fout, log=log, cancel=cancel, alphabet=self.alphabet,
-                              gap_open=self.gap_open, gap_extend=self.gap_extend, device=self.device, flags=flags)
+                              gap_open=self.gap_open, gap_extend=self.gap_extend, device=self.device, flags=flags,
+                              n_devices=self.devices)
 
     def multiple_alignment(self, residues):
         """Distances, UPGMA guide tree and the progressive alignment along it, in memory:
         (rows in submitted order, tree order of the rows)."""
         with capi.Context(alphabet=self.alphabet, gap_open=self.gap_open, gap_extend=self.gap_extend,
-                          device=self.device, flags=capi.FLAG_IDENTITY if self.identity else 0) as ctx:
+                          device=self.device, n_devices=self.devices, flags=capi.FLAG_IDENTITY if self.identity else 0) as ctx:
             ctx.set_sequences(residues)
             ctx.run()
             rows, order = ctx.msa()
@@ -144,7 +154,7 @@ class B200Gotoh(AlignmentTool):
         if self.identity:
             flags |= capi.FLAG_IDENTITY
         with capi.Context(alphabet=self.alphabet, gap_open=self.gap_open, gap_extend=self.gap_extend,
-                          device=self.device, flags=flags) as ctx:
+                          device=self.device, n_devices=self.devices, flags=flags) as ctx:
             ctx.set_sequences(residues)
             ctx.run(progress=progress, cancel=cancel)
             self.last_stats = ctx.stats()
@@ -155,7 +165,7 @@ class B200Gotoh(AlignmentTool):
         """Distances + UPGMA guide tree.  Returns (left, right, height) merge arrays and
         writes Newick to newick_path if given (what clustalo takes as --guidetree-in)."""
         with capi.Context(alphabet=self.alphabet, gap_open=self.gap_open, gap_extend=self.gap_extend,
-                          device=self.device, flags=capi.FLAG_IDENTITY if self.identity else 0) as ctx:
+                          device=self.device, n_devices=self.devices, flags=capi.FLAG_IDENTITY if self.identity else 0) as ctx:
             ctx.set_sequences(residues)
             ctx.run()
             tree = ctx.guide_tree()

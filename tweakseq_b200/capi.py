@@ -12,6 +12,8 @@ import numpy as np
 
 PROTEIN, NUCLEOTIDE = 0, 1
 FLAG_FORCE_S32, FLAG_NO_DISTANCES, FLAG_NO_WAVE16, FLAG_IDENTITY, FLAG_MSA_OUT, FLAG_KEEP_DISTMAT, FLAG_INPUT_ORDER = 1, 2, 4, 8, 16, 32, 64
+FLAG_KEEP_TREE = 128
+ALPHABET_AUTO = -1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libtsqb200.so")
@@ -30,7 +32,8 @@ class TsqError(RuntimeError):
 class Params(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("alphabet", C.c_int32), ("gap_open", C.c_int32),
                 ("gap_extend", C.c_int32), ("matrix", C.POINTER(C.c_int8)), ("device", C.c_int32),
-                ("part_rank", C.c_int32), ("part_world", C.c_int32), ("flags", C.c_uint32)]
+                ("part_rank", C.c_int32), ("part_world", C.c_int32), ("flags", C.c_uint32),
+                ("n_devices", C.c_int32)]
 
 
 class Merge(C.Structure):
@@ -57,7 +60,8 @@ SYMBOLS = ["tsq_version", "tsq_version_string", "tsq_status_string", "tsq_device
            "tsq_download", "tsq_set_stream", "tsq_synchronize", "tsq_run", "tsq_scores", "tsq_distances",
            "tsq_self_scores", "tsq_identities", "tsq_device_scores", "tsq_partition", "tsq_finalize", "tsq_device_results",
            "tsq_get_stats", "tsq_measure_dpx_rate", "tsq_run_fasta", "tsq_plan_partition", "tsq_guide_tree",
-           "tsq_write_newick", "tsq_consensus", "tsq_align_pair", "tsq_partition_of", "tsq_msa", "tsq_write_msa_fasta", "tsq_write_distmat"]
+           "tsq_write_newick", "tsq_consensus", "tsq_align_pair", "tsq_partition_of", "tsq_msa", "tsq_write_msa_fasta", "tsq_write_distmat",
+           "tsq_device_slab", "tsq_results_sharded", "tsq_set_result_buffers", "tsq_get_device_stats"]
 
 _lib = None
 
@@ -107,6 +111,10 @@ def load_library():
     L.tsq_partition_of.argtypes = [vp, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.tsq_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), u64p]
     L.tsq_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.tsq_get_device_stats.argtypes = [vp, C.c_int32, C.POINTER(Stats)]
+    L.tsq_device_slab.argtypes = [vp, C.POINTER(vp), u64p, u64p]
+    L.tsq_results_sharded.argtypes = [vp, C.POINTER(C.c_int)]
+    L.tsq_set_result_buffers.argtypes = [vp, vp, vp, C.c_uint64]
     L.tsq_guide_tree.argtypes = [vp, C.POINTER(C.POINTER(Merge)), C.POINTER(C.c_uint32)]
     L.tsq_write_newick.argtypes = [vp, C.POINTER(C.c_char_p), C.c_char_p]
     L.tsq_consensus.argtypes = [vp, C.POINTER(C.c_char_p), C.c_uint32, C.c_uint32, C.c_double, C.c_char_p]
@@ -167,12 +175,13 @@ class Context:
 
     def __init__(self, alphabet: int = PROTEIN, gap_open: int = -1, gap_extend: int = -1,
                  matrix: np.ndarray | None = None, device: int = 0, part_rank: int = 0,
-                 part_world: int = 1, flags: int = 0):
+                 part_world: int = 1, flags: int = 0, n_devices: int = 1):
         self._L = load_library()
         p = Params()
         self._L.tsq_default_params(C.byref(p))
         p.alphabet, p.gap_open, p.gap_extend = alphabet, gap_open, gap_extend
         p.device, p.part_rank, p.part_world, p.flags = device, part_rank, part_world, flags
+        p.n_devices = n_devices
         self._matrix = None
         if matrix is not None:
             self._matrix = np.ascontiguousarray(matrix, dtype=np.int8)
@@ -248,19 +257,23 @@ class Context:
     def npairs(self) -> int:
         return self.n * (self.n - 1) // 2 if self.n >= 2 else 0
 
-    def scores(self) -> np.ndarray:
+    def scores(self, copy: bool = True) -> np.ndarray:
+        """Packed int32 scores (copy=False: a view of the library's buffer, valid until the next run -- what a
+        20 GB result wants).  A rank of a sharded partition without result buffers sees its own slab only."""
         p, cnt = C.POINTER(C.c_int32)(), C.c_uint64()
         self._ck(self._L.tsq_scores(self._h, C.byref(p), C.byref(cnt)))
         if cnt.value == 0:
             return np.zeros(0, np.int32)
-        return np.ctypeslib.as_array(p, shape=(cnt.value,)).copy()
+        a = np.ctypeslib.as_array(p, shape=(cnt.value,))
+        return a.copy() if copy else a
 
-    def distances(self) -> np.ndarray:
+    def distances(self, copy: bool = True) -> np.ndarray:
         p, cnt = C.POINTER(C.c_double)(), C.c_uint64()
         self._ck(self._L.tsq_distances(self._h, C.byref(p), C.byref(cnt)))
         if cnt.value == 0:
             return np.zeros(0, np.float64)
-        return np.ctypeslib.as_array(p, shape=(cnt.value,)).copy()
+        a = np.ctypeslib.as_array(p, shape=(cnt.value,))
+        return a.copy() if copy else a
 
     def identities(self) -> np.ndarray:
         """FLAG_IDENTITY: identical residue pairs on the chosen optimal alignment, packed like scores()."""
@@ -293,6 +306,39 @@ class Context:
         d, cnt = C.c_void_p(), C.c_uint64()
         self._ck(self._L.tsq_device_scores(self._h, C.byref(d), C.byref(cnt)))
         return _DevArray(d.value or 0, cnt.value, "<i4", self)
+
+    def device_slab(self):
+        """(device array, first packed index) of the sorted-order scores this context really holds: the whole
+        triangle, or a partitioned rank's own slab (tsq_device_slab)."""
+        d, first, cnt = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self._ck(self._L.tsq_device_slab(self._h, C.byref(d), C.byref(first), C.byref(cnt)))
+        return _DevArray(d.value or 0, cnt.value, "<i4", self), first.value
+
+    def results_sharded(self) -> bool:
+        """True: every rank of the partition finalizes and downloads its own slab (fixed-length input);
+        False: the slabs must be gathered into rank 0 first (tsq_results_sharded)."""
+        v = C.c_int()
+        self._ck(self._L.tsq_results_sharded(self._h, C.byref(v)))
+        return bool(v.value)
+
+    def set_result_buffers(self, scores: np.ndarray | None, distances: np.ndarray | None = None):
+        """Caller-owned host arrays (int32 / float64, n*(n-1)/2 each) that receive the results, e.g. views of one
+        shared-memory segment mapped by every rank (tsq_set_result_buffers).  None restores the library's own."""
+        if scores is None:
+            self._ext = None
+            self._ck(self._L.tsq_set_result_buffers(self._h, None, None, 0))
+            return
+        assert scores.dtype == np.int32 and scores.flags.c_contiguous
+        assert distances is None or (distances.dtype == np.float64 and distances.flags.c_contiguous and len(distances) == len(scores))
+        self._ext = (scores, distances)
+        self._ck(self._L.tsq_set_result_buffers(self._h, scores.ctypes.data, distances.ctypes.data if distances is not None else None,
+                                                len(scores)))
+
+    def device_stats(self, index: int) -> dict:
+        """Figures of one device of a multi-device context (tsq_get_device_stats)."""
+        st = Stats()
+        self._ck(self._L.tsq_get_device_stats(self._h, index, C.byref(st)))
+        return st.as_dict()
 
     def device_results(self):
         ds, dd, cnt = C.c_void_p(), C.c_void_p(), C.c_uint64()

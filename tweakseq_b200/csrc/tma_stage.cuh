@@ -43,11 +43,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Warp-uniform bounded wait: every lane of a converged warp polls the same barrier and the loop
 // condition is a warp vote, so control flow stays uniform.  try_wait suspends in hardware between
-// probes; the cap only exists so that a protocol bug can never hang the GPU (results would then be
-// wrong and the parity tests fail).
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
-  for (int it = 0; it < (1 << 22); ++it)
-    if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
+// probes.  A copy that has not landed after 2^29 clocks (~0.3 s; a tile takes microseconds) is a
+// protocol failure: the warp raises the context's device fault word and returns false (warp-uniform),
+// whereupon the caller abandons its task; other warps stop fetching tasks, and the host turns the word
+// into TSQ_ERR_CUDA and discards the results (tsq_api.cpp: check_device_fault) -- never a silently
+// wrong score.
+__device__ __forceinline__ bool mbar_wait_warp(uint64_t* bar, uint32_t parity, int* fault) {
+  if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return true;
+  const long long t0 = clock64();
+  for (;;) {
+    if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return true;
+    const bool give_up = (clock64() - t0 > (1ll << 29)) || *reinterpret_cast<volatile int*>(fault) != 0;
+    if (__any_sync(0xffffffffu, give_up)) break;
+  }
+  if ((threadIdx.x & 31) == 0) atomicOr(fault, 1);
+  return false;
 }
 
 }  // namespace tsq

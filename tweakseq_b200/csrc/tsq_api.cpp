@@ -15,6 +15,7 @@
 #include <fstream>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -100,7 +101,8 @@ struct PinnedBuf {
     if (p) cudaFreeHost(p);
     p = nullptr;
     cap = 0;
-    cudaError_t e = cudaMallocHost((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
+    // portable: every device of a multi-device context copies its slab straight into this buffer
+    cudaError_t e = cudaHostAlloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocPortable);
     if (e == cudaSuccess) cap = n;
     return e;
   }
@@ -213,6 +215,29 @@ struct tsq_ctx {
 
   bool have_seqs = false, uploaded = false, computed = false, finalized = false, downloaded = false;
   tsq_stats st{};
+
+  // ---- partitioned jobs (part_world > 1, or the children of a multi-device context) -------------------
+  // slab_mode: the length sort is the identity (and no identity keys), so this rank's slab of the sorted
+  // triangle IS a contiguous piece of the final one: the rank finalizes and downloads it itself
+  // (tsq_results_sharded).  full_sorted: d_sorted spans the whole triangle (single rank, or the root of a
+  // gather); otherwise it holds [part_begin, part_end) only and kernels get a pointer biased by part_begin.
+  bool slab_mode = false;
+  bool full_sorted = true;
+  // ---- multi-device (tsq_params.n_devices > 1): a LEADER owns one child context per device ------------
+  std::vector<tsq_ctx*> kids;      // leader only
+  tsq_ctx* leader = nullptr;       // child only
+  const std::vector<std::vector<uint8_t>>* encp = nullptr;   // encoded sequences: own `enc`, or the leader's
+  const std::vector<int32_t>* selfp = nullptr;                // self scores: own `self_input`, or the leader's
+  cudaEvent_t fin_ev = nullptr;    // recorded behind this context's finalize (cross-device stream waits)
+  DevBuf<double> d_dist_full;      // child 0 of a leader in slab mode: all slabs of the distance matrix (guide tree)
+  // ---- caller-owned host result buffers (tsq_set_result_buffers) ---------------------------------------
+  int32_t* ext_scores = nullptr;
+  double* ext_dist = nullptr;
+  uint64_t ext_count = 0;
+  std::vector<void*> ext_registered;   // page ranges this context has page-locked
+  // Device-side fault word next to the cancel flag (d_cancel[1]): a kernel that gives up on a TMA barrier
+  // sets it; tsq_synchronize turns it into TSQ_ERR_CUDA.
+  int* h_fault = nullptr;          // pinned landing place of its copy
 };
 
 namespace {
@@ -239,6 +264,17 @@ int fail(tsq_ctx* c, int code, const char* fmt, ...) {
   } while (0)
 
 inline uint64_t tri(uint64_t i, uint64_t j, uint64_t n) { return i * n - i * (i + 1) / 2 + (j - i - 1); }
+
+// Kernels index the sorted-order score buffer by ABSOLUTE packed index; a rank that holds only its slab
+// hands them the buffer's address moved back by part_begin elements (never dereferenced below the slab).
+inline int32_t* sorted_base(const tsq_ctx* c) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(c->d_sorted.p);
+  return reinterpret_cast<int32_t*>(c->full_sorted ? a : a - (uintptr_t)c->part_begin * sizeof(int32_t));
+}
+template <typename T>
+inline T* biased(T* p, uint64_t first) {
+  return reinterpret_cast<T*>(reinterpret_cast<uintptr_t>(p) - (uintptr_t)first * sizeof(T));
+}
 
 bool is_gap_or_space(unsigned char c) {
   return c == '-' || c == '.' || c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f';
@@ -358,13 +394,13 @@ int host_sort_and_pack(tsq_ctx* c) {
   c->perm.resize(n);
   std::iota(c->perm.begin(), c->perm.end(), 0u);
   std::stable_sort(c->perm.begin(), c->perm.end(),
-                   [&](uint32_t a, uint32_t b) { return c->enc[a].size() < c->enc[b].size(); });
+                   [&](uint32_t a, uint32_t b) { return (*c->encp)[a].size() < (*c->encp)[b].size(); });
   c->lens.resize(n);
   c->loff.resize(n + 1);
   uint64_t total = 0;
   c->perm_identity = true;
   for (uint32_t i = 0; i < n; i++) {
-    const size_t l = c->enc[c->perm[i]].size();
+    const size_t l = (*c->encp)[c->perm[i]].size();
     if (l > 0x7fffffffu) return fail(c, TSQ_ERR_RANGE, "sequence too long");
     c->lens[i] = (uint32_t)l;
     c->loff[i] = (uint32_t)total;
@@ -383,7 +419,7 @@ int host_sort_and_pack(tsq_ctx* c) {
   }
   uint8_t* const lin = c->h_blob.p;
   for (uint32_t i = 0; i < n; i++) {
-    const std::vector<uint8_t>& e = c->enc[c->perm[i]];
+    const std::vector<uint8_t>& e = (*c->encp)[c->perm[i]];
     if (!e.empty()) memcpy(lin + c->loff[i], e.data(), e.size());
     const size_t end = (size_t)c->loff[i] + e.size();
     memset(lin + end, 0, (size_t)c->loff[i + 1] - end);   // the pad up to the next 16-byte aligned start
@@ -427,6 +463,9 @@ int host_sort_and_pack(tsq_ctx* c) {
   if (c->perm_identity && lo > 0) c->perm_identity = false;  // empties are filled in by finalize
   c->lo = lo;
   c->hi = hi;
+  // how a partitioned job's results come together (tsq_results_sharded) and what this rank must hold
+  c->slab_mode = c->prm.part_world > 1 && c->perm_identity && c->idshift == 0;
+  c->full_sorted = c->prm.part_world == 1 || (!c->leader && c->prm.part_rank == 0 && !c->slab_mode);
   return TSQ_OK;
 }
 
@@ -599,7 +638,7 @@ int device_upload(tsq_ctx* c) {
     memcpy(hb + o_lens, c->lens.data(), (size_t)n * 4);
     memcpy(hb + o_perm, c->perm.data(), (size_t)n * 4);
     int32_t* self_sorted = reinterpret_cast<int32_t*>(hb + o_self);
-    for (uint32_t i = 0; i < n; i++) self_sorted[i] = c->self_input[c->perm[i]];
+    for (uint32_t i = 0; i < n; i++) self_sorted[i] = (*c->selfp)[c->perm[i]];
   }
   {  // biased score table of the packed kernels: S + 2 delta >= 0, one extra all-zero row
     uint32_t* sbias = reinterpret_cast<uint32_t*>(hb + o_sbias);
@@ -623,7 +662,7 @@ int device_upload(tsq_ctx* c) {
   c->d_prefix.p = reinterpret_cast<unsigned long long*>(db + o_prefix);
   TSQ_CUDA(c, c->d_dbw.reserve(c->dbw_size));
   TSQ_CUDA(c, c->d_counter.reserve(16));
-  TSQ_CUDA(c, c->d_sorted.reserve(npairs));
+  TSQ_CUDA(c, c->d_sorted.reserve(c->full_sorted ? npairs : c->part_end - c->part_begin));
   TSQ_CUDA(c, cudaMemcpyAsync(db, hb, c->blob_size, cudaMemcpyHostToDevice, s));
   c->st.upload_launches = 0;
   if (c->dbw_size && c->hi > c->lo) c->st.upload_launches = 1;
@@ -682,7 +721,7 @@ int enqueue_gotoh16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
       g.cancel = c->d_cancel;
       g.bnd = reinterpret_cast<int2*>(c->d_bnd.p);
       g.smat = c->d_smat.p;
-      g.out = c->d_sorted.p;
+      g.out = sorted_base(c);
       g.ntasks = ntasks;
       g.bnd_rows = bnd_rows;
       g.n_total = c->n;
@@ -710,7 +749,7 @@ int enqueue_gotoh16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
     p.cancel = c->d_cancel;
     p.bnd = c->d_bnd.p;
     p.sbias = c->d_sbias.p;
-    p.out = c->d_sorted.p;
+    p.out = sorted_base(c);
     p.ntasks = ntasks;
     p.bnd_rows = bnd_rows;
     p.n_total = c->n;
@@ -750,9 +789,14 @@ int enqueue_wave16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
     w.tasks = c->d_tasks16w.p;
     w.counter = c->d_counter.p + 2;
     w.cancel = c->d_cancel;
+    w.fault = c->d_cancel + 1;
+    {   // test hook (tests/test_gpu_parity.py): the first task arms a tile barrier whose copy never comes
+      const char* fi = getenv("TSQ_FAULT_INJECT");
+      w.inject_fault = (fi && strcmp(fi, "tma") == 0) ? 1u : 0u;
+    }
     w.bnd = c->d_bnd16w.p;
     w.sbias = c->d_sbias.p;
-    w.out = c->d_sorted.p;
+    w.out = sorted_base(c);
     w.ntasks = c->tasks16w.size();
     w.bnd_rows = bnd_rows;
     w.n_total = c->n;
@@ -788,7 +832,7 @@ int enqueue_wave32(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
     w.cancel = c->d_cancel;
     w.bnd = c->d_bnd32.p;
     w.smat = c->d_smat.p;
-    w.out = c->d_sorted.p;
+    w.out = sorted_base(c);
     w.ntasks = c->pairs32.size();
     w.bnd_rows = bnd_rows;
     w.n_total = c->n;
@@ -857,7 +901,338 @@ void tsq_default_params(tsq_params* p) {
   p->part_rank = 0;
   p->part_world = 1;
   p->flags = 0;
+  p->n_devices = 1;
 }
+
+}  // extern "C"
+
+namespace {
+
+// Usable devices: compute capability 10.x (sm_100a SASS only: nothing else can run these kernels).
+bool device_usable(int d) {
+  int major = 0;
+  return cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10;
+}
+
+void copy_error(tsq_ctx* to, const tsq_ctx* from) {
+  if (to && from) to->err = from->err;
+}
+
+// ---- host result buffers ---------------------------------------------------------------------------------
+// Who owns them: a child of a multi-device context writes into its leader's; everything else into its own.
+tsq_ctx* result_owner(tsq_ctx* c) { return c->leader ? c->leader : c; }
+
+// A partitioned rank without caller buffers keeps only its slab on the host (a rank of world 8 at 100 000
+// sequences: 2.5 GB, not 20 GB of page-locked memory): [first, first + count) of the packed triangle.
+void host_extent(const tsq_ctx* c, uint64_t* first, uint64_t* count) {
+  const uint64_t n = c->n, npairs = n < 2 ? 0 : n * (n - 1) / 2;
+  const bool slab_only = c->slab_mode && c->kids.empty() && !c->leader && !c->ext_scores;
+  *first = slab_only ? c->part_begin : 0;
+  *count = slab_only ? c->part_end - c->part_begin : npairs;
+}
+
+// Page-locks [p, p + bytes) of caller memory (whole pages) unless an earlier call already did.
+int register_range(tsq_ctx* c, void* p, size_t bytes) {
+  if (!p || bytes == 0) return TSQ_OK;
+  const uintptr_t page = 4096;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p) & ~(page - 1);
+  const uintptr_t b = (reinterpret_cast<uintptr_t>(p) + bytes + page - 1) & ~(page - 1);
+  for (void* r : c->ext_registered)
+    if (r == reinterpret_cast<void*>(a)) return TSQ_OK;
+  const cudaError_t e = cudaHostRegister(reinterpret_cast<void*>(a), b - a, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    return TSQ_OK;
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(c, TSQ_ERR_CUDA, "cudaHostRegister of the caller's result buffer failed: %s", cudaGetErrorString(e));
+  }
+  c->ext_registered.push_back(reinterpret_cast<void*>(a));
+  return TSQ_OK;
+}
+
+void unregister_all(tsq_ctx* c) {
+  for (void* r : c->ext_registered)
+    if (cudaHostUnregister(r) != cudaSuccess) cudaGetLastError();
+  c->ext_registered.clear();
+}
+
+// Host destinations of context c's results, as pointers indexed by ABSOLUTE packed index (so that a slab
+// lands at its place whatever the buffer really spans).  Reserves / page-locks on first use.
+struct HostDst {
+  int32_t* scores = nullptr;
+  int32_t* nid = nullptr;
+  double* dist = nullptr;
+};
+int host_results(tsq_ctx* c, bool want_dist, bool want_nid, HostDst* out) {
+  tsq_ctx* o = result_owner(c);
+  uint64_t first = 0, count = 0;
+  host_extent(o, &first, &count);   // a leader's buffers span the whole triangle
+  if (o->ext_scores) {
+    if (o->ext_count < count) return fail(c, TSQ_ERR_INVALID, "result buffers hold %llu pairs, the job has %llu",
+                                          (unsigned long long)o->ext_count, (unsigned long long)count);
+    if (want_dist && !o->ext_dist) return fail(c, TSQ_ERR_INVALID, "tsq_set_result_buffers: no distance buffer, but distances are on");
+    // page-lock what this process writes: a lone rank's slab, or everything
+    uint64_t lb = 0, le = count;
+    if (!c->leader && c->slab_mode) {
+      lb = c->part_begin;
+      le = c->part_end;
+    }
+    int rc = register_range(o, o->ext_scores + lb, (size_t)(le - lb) * sizeof(int32_t));
+    if (rc == TSQ_OK && want_dist) rc = register_range(o, o->ext_dist + lb, (size_t)(le - lb) * sizeof(double));
+    if (rc != TSQ_OK) {
+      if (o != c) copy_error(c, o);
+      return rc;
+    }
+    out->scores = o->ext_scores;
+    out->dist = want_dist ? o->ext_dist : nullptr;
+  } else {
+    TSQ_CUDA(c, o->h_scores.reserve(count));
+    out->scores = biased(o->h_scores.p, first);
+    if (want_dist) {
+      TSQ_CUDA(c, o->h_dist.reserve(count));
+      out->dist = biased(o->h_dist.p, first);
+    }
+  }
+  if (want_nid) {
+    TSQ_CUDA(c, o->h_nid.reserve(count));
+    out->nid = biased(o->h_nid.p, first);
+  }
+  return TSQ_OK;
+}
+
+// ---- finalize --------------------------------------------------------------------------------------------
+// Sorted rows [row_begin, row_end) of context c, read from ITS sorted buffer, written to the given packed
+// triangles (absolute index; possibly another device's memory).
+int launch_finalize(tsq_ctx* c, uint32_t row_begin, uint32_t row_end, int32_t* out_scores, int32_t* out_nid, double* out_dist) {
+  tsq::FinalizeParams f{};
+  f.sorted = sorted_base(c);
+  f.lens = c->d_lens.p;
+  f.perm = c->d_perm.p;
+  f.self = c->d_self.p;
+  f.out_scores = out_scores;
+  f.out_nid = out_nid;
+  f.out_dist = out_dist;
+  f.idshift = c->idshift;
+  f.n = c->n;
+  f.row_begin = row_begin;
+  f.row_end = row_end;
+  f.go = c->go;
+  f.ge = c->ge;
+  f.perm_identity = c->perm_identity ? 1u : 0u;
+  TSQ_CUDA(c, tsq::finalize_launch(f, c->stream));
+  c->st.launches++;
+  return TSQ_OK;
+}
+
+// The fault word a kernel sets when it gives up on a TMA barrier (tma_stage.cuh): read back with every
+// synchronize so that a protocol failure is an error code, never a silently wrong score.
+int check_device_fault(tsq_ctx* c) {
+  if (!c->d_cancel || !c->h_fault) return TSQ_OK;
+  *c->h_fault = 0;
+  TSQ_CUDA(c, cudaMemcpyAsync(c->h_fault, c->d_cancel + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  TSQ_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (*c->h_fault != 0) {
+    c->computed = c->finalized = c->downloaded = false;
+    return fail(c, TSQ_ERR_CUDA, "device fault 0x%x: a wavefront kernel timed out on a TMA tile barrier; results discarded", *c->h_fault);
+  }
+  return TSQ_OK;
+}
+
+// ---- multi-device leader: every entry point fans out to the per-device children ----------------------------
+template <typename F>
+int for_each_kid_parallel(tsq_ctx* c, F&& body) {
+  const size_t nk = c->kids.size();
+  std::vector<int> rcs(nk, TSQ_OK);
+  std::vector<std::thread> th;
+  th.reserve(nk);
+  for (size_t r = 0; r < nk; r++) th.emplace_back([&, r]() { rcs[r] = body(c->kids[r]); });
+  for (auto& t : th) t.join();
+  for (size_t r = 0; r < nk; r++)
+    if (rcs[r] != TSQ_OK) {
+      c->err = "device " + std::to_string(c->kids[r]->device) + ": " + c->kids[r]->err;
+      return rcs[r];
+    }
+  return TSQ_OK;
+}
+
+void multi_share_sequences(tsq_ctx* c) {
+  for (tsq_ctx* k : c->kids) {
+    k->encp = &c->enc;
+    k->selfp = &c->self_input;
+    k->n = c->n;
+    k->have_seqs = true;
+    k->uploaded = k->computed = k->finalized = k->downloaded = false;
+    k->err.clear();
+  }
+}
+
+int multi_upload(tsq_ctx* c) {
+  const double t0 = now_ms();
+  // one host thread per device: each sorts, plans ITS rows, packs and copies over its own link
+  int rc = for_each_kid_parallel(c, [](tsq_ctx* k) { return tsq_upload(k); });
+  if (rc != TSQ_OK) return rc;
+  const tsq_ctx* k0 = c->kids[0];
+  c->perm_identity = k0->perm_identity;
+  c->idshift = k0->idshift;
+  c->slab_mode = k0->slab_mode;
+  c->uploaded = true;
+  c->computed = c->finalized = c->downloaded = false;
+  c->st.upload_ms = now_ms() - t0;
+  return TSQ_OK;
+}
+
+int multi_compute(tsq_ctx* c) {
+  for (tsq_ctx* k : c->kids) {   // launches are asynchronous: one thread enqueues on every device's stream
+    const int rc = tsq_compute(k);
+    if (rc != TSQ_OK) {
+      copy_error(c, k);
+      return rc;
+    }
+  }
+  c->computed = true;
+  c->finalized = c->downloaded = false;
+  return TSQ_OK;
+}
+
+int multi_synchronize(tsq_ctx* c) {
+  double worst = 0;
+  for (tsq_ctx* k : c->kids) {
+    const int rc = tsq_synchronize(k);
+    if (rc != TSQ_OK) {
+      copy_error(c, k);
+      if (rc == TSQ_ERR_CUDA) c->computed = c->finalized = c->downloaded = false;
+      return rc;
+    }
+    worst = std::max(worst, k->st.kernel_ms);
+  }
+  c->st.kernel_ms = worst;
+  return TSQ_OK;
+}
+
+int multi_finalize(tsq_ctx* c) {
+  const uint32_t n = c->n;
+  const uint64_t npairs = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
+  const bool want_dist = !(c->prm.flags & TSQ_FLAG_NO_DISTANCES);
+  tsq_ctx* k0 = c->kids[0];
+  if (c->slab_mode) {
+    // fixed-length input: a device's slab is a contiguous piece of the final triangle -- finalize in place
+    for (tsq_ctx* k : c->kids) {
+      const int rc = tsq_finalize(k);
+      if (rc != TSQ_OK) {
+        copy_error(c, k);
+        return rc;
+      }
+    }
+  } else if (npairs > 0) {
+    // the un-sort scatters every slab over the triangle: each device un-sorts its rows STRAIGHT INTO device
+    // 0's matrix with peer stores over NVLink (finalize + gather in one kernel, no staging copy)
+    TSQ_CUDA(c, cudaSetDevice(k0->device));
+    TSQ_CUDA(c, k0->d_scores.reserve(npairs));
+    if (c->idshift) TSQ_CUDA(c, k0->d_nid.reserve(npairs));
+    if (want_dist) TSQ_CUDA(c, k0->d_dist.reserve(npairs));
+    for (tsq_ctx* k : c->kids) {
+      if (k->device != k0->device) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, k->device, k0->device) != cudaSuccess || !can) {
+          cudaGetLastError();
+          return fail(c, TSQ_ERR_CUDA, "device %d cannot reach device %d's memory (no NVLink/PCIe peer access): "
+                      "ragged input on several devices needs it", k->device, k0->device);
+        }
+      }
+      TSQ_CUDA(c, cudaSetDevice(k->device));
+      const int rc = launch_finalize(k, k->row_a, k->row_b, k0->d_scores.p, c->idshift ? k0->d_nid.p : nullptr,
+                                     want_dist ? k0->d_dist.p : nullptr);
+      if (rc != TSQ_OK) {
+        copy_error(c, k);
+        return rc;
+      }
+      TSQ_CUDA(c, cudaEventRecord(k->fin_ev, k->stream));
+      k->finalized = true;
+    }
+    TSQ_CUDA(c, cudaSetDevice(k0->device));
+    for (tsq_ctx* k : c->kids)
+      if (k != k0) TSQ_CUDA(c, cudaStreamWaitEvent(k0->stream, k->fin_ev, 0));
+  }
+  for (tsq_ctx* k : c->kids) {
+    k->finalized = true;
+    k->have_tree = k->have_msa = false;
+  }
+  k0->d_dist_full.release();
+  c->finalized = true;
+  return TSQ_OK;
+}
+
+int multi_download(tsq_ctx* c) {
+  if (!c->finalized) {
+    const int rc = multi_finalize(c);
+    if (rc != TSQ_OK) return rc;
+  }
+  const double t0 = now_ms();
+  const uint32_t n = c->n;
+  const uint64_t npairs = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
+  const bool want_dist = !(c->prm.flags & TSQ_FLAG_NO_DISTANCES);
+  uint64_t bytes = 0;
+  if (npairs > 0) {
+    if (c->slab_mode) {
+      // every device copies ITS slab over ITS OWN PCIe link into the one host result
+      for (tsq_ctx* k : c->kids) {
+        const int rc = tsq_download(k);   // enqueues; see the slab branch there
+        if (rc != TSQ_OK) {
+          copy_error(c, k);
+          return rc;
+        }
+      }
+    } else {
+      tsq_ctx* k0 = c->kids[0];
+      HostDst h;
+      int rc = host_results(k0, want_dist, c->idshift != 0, &h);
+      if (rc != TSQ_OK) {
+        copy_error(c, k0);
+        return rc;
+      }
+      TSQ_CUDA(c, cudaSetDevice(k0->device));
+      TSQ_CUDA(c, cudaMemcpyAsync(h.scores, k0->d_scores.p, npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, k0->stream));
+      if (c->idshift) TSQ_CUDA(c, cudaMemcpyAsync(h.nid, k0->d_nid.p, npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, k0->stream));
+      if (want_dist) TSQ_CUDA(c, cudaMemcpyAsync(h.dist, k0->d_dist.p, npairs * sizeof(double), cudaMemcpyDeviceToHost, k0->stream));
+    }
+    bytes = npairs * (want_dist ? 12ull : 4ull) + (c->idshift ? npairs * 4ull : 0ull);
+  }
+  int rc = multi_synchronize(c);
+  if (rc != TSQ_OK) return rc;
+  for (tsq_ctx* k : c->kids) k->downloaded = true;
+  c->downloaded = true;
+  c->st.download_ms = now_ms() - t0;
+  c->st.d2h_bytes = bytes;
+  return TSQ_OK;
+}
+
+// Guide tree, alignment, traceback and consensus of a multi-device context run on its first device, which
+// holds the whole database; the distance matrix is assembled there from the slabs with peer copies (NVLink).
+int multi_prepare_first_device(tsq_ctx* c) {
+  if (!c->finalized) return fail(c, TSQ_ERR_STATE, "no results yet: call tsq_run first");
+  tsq_ctx* k0 = c->kids[0];
+  const bool want_dist = !(c->prm.flags & TSQ_FLAG_NO_DISTANCES);
+  const uint32_t n = c->n;
+  const uint64_t npairs = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
+  if (c->slab_mode && want_dist && npairs > 0 && !k0->d_dist_full.p) {
+    TSQ_CUDA(c, cudaSetDevice(k0->device));
+    TSQ_CUDA(c, k0->d_dist_full.reserve(npairs));
+    for (tsq_ctx* k : c->kids) {
+      const uint64_t cnt = k->part_end - k->part_begin;
+      if (cnt == 0) continue;
+      TSQ_CUDA(c, cudaMemcpyPeerAsync(k0->d_dist_full.p + k->part_begin, k0->device, k->d_dist.p, k->device,
+                                      cnt * sizeof(double), k0->stream));
+    }
+    TSQ_CUDA(c, cudaStreamSynchronize(k0->stream));
+  }
+  return TSQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
 
 int tsq_create(tsq_ctx** out, const tsq_params* params) {
   if (!out) return TSQ_ERR_INVALID;
@@ -887,9 +1262,26 @@ int tsq_create(tsq_ctx** out, const tsq_params* params) {
     return TSQ_ERR_NO_DEVICE;
   }
   if (p.device < 0 || p.device >= ndev) return TSQ_ERR_NO_DEVICE;
-  int major = 0, sms = 0;
-  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, p.device) != cudaSuccess || major != 10)
-    return TSQ_ERR_NO_DEVICE;  // sm_100a SASS only: nothing else can run these kernels
+  if (!device_usable(p.device)) return TSQ_ERR_NO_DEVICE;
+  // ---- several devices behind one context ----------------------------------------------------------------
+  if (p.n_devices < 0) {   // all usable devices from `device` on
+    int cnt = 0;
+    for (int d = p.device; d < ndev && device_usable(d); d++) cnt++;
+    p.n_devices = cnt;
+  }
+  if (p.n_devices == 0) p.n_devices = 1;
+  // test hook: all children on the one device, so that the multi-device host logic (slab finalize, peer-store
+  // finalize, own-link downloads, collected distances) also runs on a one-GPU box
+  const bool same_device = p.n_devices > 1 && getenv("TSQ_MULTI_SAME_DEVICE") != nullptr;
+  if (p.n_devices > 1) {
+    if (p.part_world != 1) return TSQ_ERR_INVALID;          // one way of partitioning at a time
+    if (!same_device) {
+      if (p.device + p.n_devices > ndev) return TSQ_ERR_NO_DEVICE;
+      for (int d = p.device; d < p.device + p.n_devices; d++)
+        if (!device_usable(d)) return TSQ_ERR_NO_DEVICE;
+    }
+  }
+  int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p.device);
 
   tsq_ctx* c = new (std::nothrow) tsq_ctx();
@@ -902,6 +1294,8 @@ int tsq_create(tsq_ctx** out, const tsq_params* params) {
   c->ge = ge;
   c->device = p.device;
   c->sm_count = sms;
+  c->encp = &c->enc;
+  c->selfp = &c->self_input;
   c->smin = *std::min_element(c->matrix.begin(), c->matrix.end());
   c->smax = *std::max_element(c->matrix.begin(), c->matrix.end());
   c->delta = c->smin < 0 ? (-c->smin + 1) / 2 : 0;
@@ -910,21 +1304,58 @@ int tsq_create(tsq_ctx** out, const tsq_params* params) {
     for (int b = 0; b < 256; b++) c->diag_by_byte[b] = lut[b] == 0xff ? 0 : c->matrix[lut[b] * (nsym + 1)];
   }
   c->max_len16 = (p.flags & TSQ_FLAG_FORCE_S32) ? 0 : max_len16_of(c);
+  if (p.n_devices > 1) {
+    // the leader owns no device state: one child context per device does the work
+    for (int r = 0; r < p.n_devices; r++) {
+      tsq_params kp = p;
+      kp.matrix = c->matrix.data();
+      kp.device = same_device ? p.device : p.device + r;
+      kp.n_devices = 1;
+      kp.part_rank = r;
+      kp.part_world = p.n_devices;
+      tsq_ctx* k = nullptr;
+      const int rc = tsq_create(&k, &kp);
+      if (rc != TSQ_OK) {
+        tsq_destroy(c);
+        return rc;
+      }
+      k->leader = c;
+      c->kids.push_back(k);
+    }
+    // peer access towards the first device (ragged input: every device un-sorts its rows into device 0's
+    // matrix) and back (the distance slabs collected for the guide tree); absence is an error only when used
+    for (int r = 1; r < p.n_devices && !same_device; r++) {
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, p.device + r, p.device) == cudaSuccess && can) {
+        cudaSetDevice(p.device + r);
+        if (cudaDeviceEnablePeerAccess(p.device, 0) != cudaSuccess) cudaGetLastError();
+        cudaSetDevice(p.device);
+        if (cudaDeviceEnablePeerAccess(p.device + r, 0) != cudaSuccess) cudaGetLastError();
+      } else {
+        cudaGetLastError();
+      }
+    }
+    *out = c;
+    return TSQ_OK;
+  }
   if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
-      cudaEventCreate(&c->tev0) != cudaSuccess || cudaEventCreate(&c->tev1) != cudaSuccess) {
+      cudaEventCreate(&c->tev0) != cudaSuccess || cudaEventCreate(&c->tev1) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->fin_ev, cudaEventDisableTiming) != cudaSuccess) {
     cudaGetLastError();
     tsq_destroy(c);
     return TSQ_ERR_CUDA;
   }
-  if (cudaMalloc((void**)&c->d_cancel, sizeof(int)) != cudaSuccess || cudaMemset(c->d_cancel, 0, sizeof(int)) != cudaSuccess ||
-      cudaMallocHost((void**)&c->h_one, sizeof(int)) != cudaSuccess ||
+  if (cudaMalloc((void**)&c->d_cancel, 2 * sizeof(int)) != cudaSuccess || cudaMemset(c->d_cancel, 0, 2 * sizeof(int)) != cudaSuccess ||
+      cudaHostAlloc((void**)&c->h_one, 2 * sizeof(int), cudaHostAllocPortable) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->cancel_stream, cudaStreamNonBlocking) != cudaSuccess) {
     cudaGetLastError();
     tsq_destroy(c);
     return TSQ_ERR_CUDA;
   }
-  *c->h_one = 1;
+  c->h_one[0] = 1;
+  c->h_one[1] = 0;
+  c->h_fault = c->h_one + 1;
   c->stream = c->own_stream;
   *out = c;
   return TSQ_OK;
@@ -932,10 +1363,13 @@ int tsq_create(tsq_ctx** out, const tsq_params* params) {
 
 int tsq_destroy(tsq_ctx* c) {
   if (!c) return TSQ_OK;
+  for (tsq_ctx* k : c->kids) tsq_destroy(k);
+  c->kids.clear();
   cudaSetDevice(c->device);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+  unregister_all(c);
   c->d_dbw.release(); c->d_blob.release(); c->h_blob.release();
-  c->d_sorted.release(); c->d_scores.release(); c->d_nid.release(); c->h_nid.release(); c->d_dist.release();
+  c->d_sorted.release(); c->d_scores.release(); c->d_nid.release(); c->h_nid.release(); c->d_dist.release(); c->d_dist_full.release();
   c->d_counter.release(); c->d_bnd.release(); c->h_scores.release(); c->h_dist.release();
   c->d_treeD.release(); c->d_treemin.release(); c->d_treeh.release(); c->d_treeu.release(); c->d_merges.release();
   c->d_pairs32.release(); c->d_tasks16w.release(); c->d_bnd16w.release(); c->d_bnd32.release(); c->d_smat.release();
@@ -946,6 +1380,7 @@ int tsq_destroy(tsq_ctx* c) {
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->tev0) cudaEventDestroy(c->tev0);
   if (c->tev1) cudaEventDestroy(c->tev1);
+  if (c->fin_ev) cudaEventDestroy(c->fin_ev);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return TSQ_OK;
@@ -955,6 +1390,7 @@ const char* tsq_last_error(const tsq_ctx* c) { return c ? c->err.c_str() : "null
 
 int tsq_set_stream(tsq_ctx* c, void* s) {
   if (!c) return TSQ_ERR_INVALID;
+  if (!c->kids.empty()) return fail(c, TSQ_ERR_INVALID, "a multi-device context runs on its own per-device streams");
   c->stream = s ? (cudaStream_t)s : c->own_stream;
   return TSQ_OK;
 }
@@ -975,6 +1411,7 @@ int tsq_set_sequences(tsq_ctx* c, const char* const* residues, const uint32_t* l
   c->have_seqs = true;
   c->uploaded = c->computed = c->finalized = c->downloaded = false;
   c->err.clear();
+  multi_share_sequences(c);   // children of a multi-device context read the leader's encoding
   return TSQ_OK;
 }
 
@@ -994,12 +1431,14 @@ int tsq_set_sequences_flat(tsq_ctx* c, const char* residues, const uint64_t* off
   c->have_seqs = true;
   c->uploaded = c->computed = c->finalized = c->downloaded = false;
   c->err.clear();
+  multi_share_sequences(c);
   return TSQ_OK;
 }
 
 int tsq_upload(tsq_ctx* c) {
   if (!c) return TSQ_ERR_INVALID;
   if (!c->have_seqs) return fail(c, TSQ_ERR_STATE, "tsq_upload before tsq_set_sequences");
+  if (!c->kids.empty()) return multi_upload(c);
   const double t0 = now_ms();
   TSQ_CUDA(c, cudaSetDevice(c->device));
   int rc = host_sort_and_pack(c);
@@ -1016,10 +1455,11 @@ int tsq_upload(tsq_ctx* c) {
 int tsq_compute(tsq_ctx* c) {
   if (!c) return TSQ_ERR_INVALID;
   if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "tsq_compute before tsq_upload");
+  if (!c->kids.empty()) return multi_compute(c);
   TSQ_CUDA(c, cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   uint32_t launches = 0;
-  TSQ_CUDA(c, cudaMemsetAsync(c->d_cancel, 0, sizeof(int), s));
+  TSQ_CUDA(c, cudaMemsetAsync(c->d_cancel, 0, 2 * sizeof(int), s));   // cancel flag and fault word
   TSQ_CUDA(c, cudaEventRecord(c->ev0, s));
   int rc = enqueue_gotoh16(c, s, launches);                 // regime 1: packed inter-task kernel
   if (rc == TSQ_OK) rc = enqueue_wave16(c, s, launches);    // regime 2: packed wavefront kernel
@@ -1035,40 +1475,31 @@ int tsq_compute(tsq_ctx* c) {
 int tsq_finalize(tsq_ctx* c) {
   if (!c) return TSQ_ERR_INVALID;
   if (!c->computed) return fail(c, TSQ_ERR_STATE, "tsq_finalize before tsq_compute");
+  if (!c->kids.empty()) return multi_finalize(c);
   TSQ_CUDA(c, cudaSetDevice(c->device));
   const uint32_t n = c->n;
   const uint64_t npairs = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
   const bool want_dist = !(c->prm.flags & TSQ_FLAG_NO_DISTANCES);
-  if (npairs > 0 && (want_dist || !c->perm_identity || c->idshift)) {
-    tsq::FinalizeParams f{};
-    f.sorted = c->d_sorted.p;
-    f.lens = c->d_lens.p;
-    f.perm = c->d_perm.p;
-    f.self = c->d_self.p;
+  if (c->slab_mode) {
+    // this rank's slab is a contiguous piece of the final triangle: distances next to it, scores in place
+    const uint64_t cnt = c->part_end - c->part_begin;
+    if (cnt > 0 && want_dist) {
+      TSQ_CUDA(c, c->d_dist.reserve(cnt));
+      const int rc = launch_finalize(c, c->row_a, c->row_b, sorted_base(c), nullptr, biased(c->d_dist.p, c->part_begin));
+      if (rc != TSQ_OK) return rc;
+    }
+    if (c->fin_ev) TSQ_CUDA(c, cudaEventRecord(c->fin_ev, c->stream));
+  } else if (c->prm.part_world > 1 && (c->prm.part_rank != 0 || c->leader)) {
+    // a rank whose slab is gathered elsewhere (rank 0 / the leader's peer-store finalize) has nothing to do
+    return fail(c, TSQ_ERR_STATE, "rank %d holds a slab only: gather it into rank 0 (tsq_device_slab) and finalize there", c->prm.part_rank);
+  } else if (npairs > 0 && (want_dist || !c->perm_identity || c->idshift)) {
     const bool inplace = c->perm_identity && c->idshift == 0;   // identity keys are decoded into a separate buffer
-    if (inplace) {
-      f.out_scores = c->d_sorted.p;
-    } else {
-      TSQ_CUDA(c, c->d_scores.reserve(npairs));
-      f.out_scores = c->d_scores.p;
-    }
-    f.idshift = c->idshift;
-    f.out_nid = nullptr;
-    if (c->idshift) {
-      TSQ_CUDA(c, c->d_nid.reserve(npairs));
-      f.out_nid = c->d_nid.p;
-    }
-    f.out_dist = nullptr;
-    if (want_dist) {
-      TSQ_CUDA(c, c->d_dist.reserve(npairs));
-      f.out_dist = c->d_dist.p;
-    }
-    f.n = n;
-    f.go = c->go;
-    f.ge = c->ge;
-    f.perm_identity = c->perm_identity ? 1u : 0u;
-    TSQ_CUDA(c, tsq::finalize_launch(f, c->stream));
-    c->st.launches++;
+    if (!inplace) TSQ_CUDA(c, c->d_scores.reserve(npairs));
+    if (c->idshift) TSQ_CUDA(c, c->d_nid.reserve(npairs));
+    if (want_dist) TSQ_CUDA(c, c->d_dist.reserve(npairs));
+    const int rc = launch_finalize(c, 0, n, inplace ? c->d_sorted.p : c->d_scores.p, c->idshift ? c->d_nid.p : nullptr,
+                                   want_dist ? c->d_dist.p : nullptr);
+    if (rc != TSQ_OK) return rc;
   }
   c->finalized = true;
   c->have_tree = false;
@@ -1078,12 +1509,14 @@ int tsq_finalize(tsq_ctx* c) {
 
 int tsq_synchronize(tsq_ctx* c) {
   if (!c) return TSQ_ERR_INVALID;
+  if (!c->kids.empty()) return multi_synchronize(c);
   TSQ_CUDA(c, cudaSetDevice(c->device));
   TSQ_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->computed) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->st.kernel_ms = ms;
     else cudaGetLastError();
+    return check_device_fault(c);
   }
   return TSQ_OK;
 }
@@ -1091,37 +1524,49 @@ int tsq_synchronize(tsq_ctx* c) {
 int tsq_download(tsq_ctx* c) {
   if (!c) return TSQ_ERR_INVALID;
   if (!c->computed) return fail(c, TSQ_ERR_STATE, "tsq_download before tsq_compute");
-  if (!c->finalized) {
-    if (c->prm.part_world > 1 && c->prm.part_rank != 0) {
-      // non-root ranks only hold a slab; nothing to assemble here
-    } else {
-      int rc = tsq_finalize(c);
-      if (rc != TSQ_OK) return rc;
-    }
+  if (!c->kids.empty()) return multi_download(c);
+  const bool gathered_elsewhere = c->prm.part_world > 1 && !c->slab_mode && (c->prm.part_rank != 0 || c->leader);
+  if (!c->finalized && !gathered_elsewhere) {
+    int rc = tsq_finalize(c);
+    if (rc != TSQ_OK) return rc;
   }
   const double t0 = now_ms();
+  TSQ_CUDA(c, cudaSetDevice(c->device));
   const uint32_t n = c->n;
   const uint64_t npairs = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
   const bool want_dist = !(c->prm.flags & TSQ_FLAG_NO_DISTANCES);
   cudaStream_t s = c->stream;
-  if (npairs > 0 && c->finalized) {
-    TSQ_CUDA(c, c->h_scores.reserve(npairs));
+  uint64_t bytes = 0;
+  if (c->slab_mode) {
+    // this rank's slab goes over this device's own PCIe link to its place in the host result
+    const uint64_t cnt = c->part_end - c->part_begin;
+    if (cnt > 0) {
+      HostDst h;
+      int rc = host_results(c, want_dist, false, &h);
+      if (rc != TSQ_OK) return rc;
+      TSQ_CUDA(c, cudaMemcpyAsync(h.scores + c->part_begin, c->d_sorted.p, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      if (want_dist) TSQ_CUDA(c, cudaMemcpyAsync(h.dist + c->part_begin, c->d_dist.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
+      bytes = cnt * (want_dist ? 12ull : 4ull);
+    }
+    if (c->leader) {   // the leader synchronizes all its devices once every copy is in flight
+      c->st.d2h_bytes = bytes;
+      return TSQ_OK;
+    }
+  } else if (npairs > 0 && c->finalized) {
+    HostDst h;
+    int rc = host_results(c, want_dist, c->idshift != 0, &h);
+    if (rc != TSQ_OK) return rc;
     const int32_t* src = (c->perm_identity && c->idshift == 0) ? c->d_sorted.p : c->d_scores.p;
-    TSQ_CUDA(c, cudaMemcpyAsync(c->h_scores.p, src, npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    if (c->idshift) {
-      TSQ_CUDA(c, c->h_nid.reserve(npairs));
-      TSQ_CUDA(c, cudaMemcpyAsync(c->h_nid.p, c->d_nid.p, npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    }
-    if (want_dist) {
-      TSQ_CUDA(c, c->h_dist.reserve(npairs));
-      TSQ_CUDA(c, cudaMemcpyAsync(c->h_dist.p, c->d_dist.p, npairs * sizeof(double), cudaMemcpyDeviceToHost, s));
-    }
+    TSQ_CUDA(c, cudaMemcpyAsync(h.scores, src, npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (c->idshift) TSQ_CUDA(c, cudaMemcpyAsync(h.nid, c->d_nid.p, npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (want_dist) TSQ_CUDA(c, cudaMemcpyAsync(h.dist, c->d_dist.p, npairs * sizeof(double), cudaMemcpyDeviceToHost, s));
+    bytes = npairs * (want_dist ? 12ull : 4ull) + (c->idshift ? npairs * 4ull : 0ull);
   }
   int rc = tsq_synchronize(c);
   if (rc != TSQ_OK) return rc;
   c->downloaded = c->finalized;
   c->st.download_ms = now_ms() - t0;
-  c->st.d2h_bytes = (npairs > 0 && c->finalized) ? npairs * (want_dist ? 12ull : 4ull) : 0ull;
+  c->st.d2h_bytes = bytes;
   return TSQ_OK;
 }
 
@@ -1136,16 +1581,26 @@ int tsq_run(tsq_ctx* c, tsq_progress_cb cb, void* user, volatile int* cancel) {
   if (cb) cb(user, 0.05, "computing pairwise scores");
   rc = tsq_compute(c);
   if (rc != TSQ_OK) return rc;
-  // poll the stream so that "Stop" (SeqEditMainWin.cpp:803-812) is honoured while kernels run
+  // poll the stream(s) so that "Stop" (SeqEditMainWin.cpp:803-812) is honoured while kernels run
+  std::vector<tsq_ctx*> devs;
+  if (c->kids.empty()) devs.push_back(c);
+  else devs = c->kids;
   for (;;) {
-    cudaError_t q = cudaStreamQuery(c->stream);
-    if (q == cudaSuccess) break;
-    if (q != cudaErrorNotReady) return fail(c, TSQ_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(q));
+    bool busy = false;
+    for (tsq_ctx* k : devs) {
+      cudaError_t q = cudaStreamQuery(k->stream);
+      if (q == cudaErrorNotReady) busy = true;
+      else if (q != cudaSuccess) return fail(c, TSQ_ERR_CUDA, "kernel failed on device %d: %s", k->device, cudaGetErrorString(q));
+    }
+    if (!busy) break;
     if (cancelled()) {
       // the kernels poll the flag at every task fetch and drain within one task
-      cudaMemcpyAsync(c->d_cancel, c->h_one, sizeof(int), cudaMemcpyHostToDevice, c->cancel_stream);
-      cudaStreamSynchronize(c->cancel_stream);
-      cudaStreamSynchronize(c->stream);
+      for (tsq_ctx* k : devs) cudaMemcpyAsync(k->d_cancel, k->h_one, sizeof(int), cudaMemcpyHostToDevice, k->cancel_stream);
+      for (tsq_ctx* k : devs) {
+        cudaStreamSynchronize(k->cancel_stream);
+        cudaStreamSynchronize(k->stream);
+        k->computed = false;
+      }
       c->computed = false;
       return fail(c, TSQ_ERR_CANCELLED, "cancelled");
     }
@@ -1159,11 +1614,34 @@ int tsq_run(tsq_ctx* c, tsq_progress_cb cb, void* user, volatile int* cancel) {
   return TSQ_OK;
 }
 
+int tsq_set_result_buffers(tsq_ctx* c, int32_t* scores, double* distances, uint64_t count) {
+  if (!c) return TSQ_ERR_INVALID;
+  if (c->leader) return fail(c, TSQ_ERR_INVALID, "set the buffers on the multi-device context, not on its children");
+  if ((scores == nullptr) != (count == 0)) return fail(c, TSQ_ERR_INVALID, "scores buffer and count must both be given or both be absent");
+  if (c->kids.empty()) cudaSetDevice(c->device);
+  unregister_all(c);
+  c->ext_scores = scores;
+  c->ext_dist = distances;
+  c->ext_count = count;
+  c->downloaded = false;
+  for (tsq_ctx* k : c->kids) k->downloaded = false;
+  return TSQ_OK;
+}
+
+int tsq_results_sharded(tsq_ctx* c, int* sharded) {
+  if (!c || !sharded) return TSQ_ERR_INVALID;
+  if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "tsq_results_sharded before tsq_upload");
+  *sharded = c->slab_mode ? 1 : 0;
+  return TSQ_OK;
+}
+
 int tsq_scores(tsq_ctx* c, const int32_t** out, uint64_t* count) {
   if (!c || !out) return TSQ_ERR_INVALID;
   if (!c->downloaded) return fail(c, TSQ_ERR_STATE, "no results: call tsq_run or tsq_download first");
-  *out = c->h_scores.p;
-  if (count) *count = c->n < 2 ? 0 : (uint64_t)c->n * (c->n - 1) / 2;
+  uint64_t first = 0, cnt = 0;
+  host_extent(c, &first, &cnt);
+  *out = c->ext_scores ? c->ext_scores : c->h_scores.p;
+  if (count) *count = cnt;
   return TSQ_OK;
 }
 
@@ -1171,8 +1649,10 @@ int tsq_distances(tsq_ctx* c, const double** out, uint64_t* count) {
   if (!c || !out) return TSQ_ERR_INVALID;
   if (!c->downloaded) return fail(c, TSQ_ERR_STATE, "no results: call tsq_run or tsq_download first");
   if (c->prm.flags & TSQ_FLAG_NO_DISTANCES) return fail(c, TSQ_ERR_STATE, "distances disabled by TSQ_FLAG_NO_DISTANCES");
-  *out = c->h_dist.p;
-  if (count) *count = c->n < 2 ? 0 : (uint64_t)c->n * (c->n - 1) / 2;
+  uint64_t first = 0, cnt = 0;
+  host_extent(c, &first, &cnt);
+  *out = c->ext_scores ? c->ext_dist : c->h_dist.p;
+  if (count) *count = cnt;
   return TSQ_OK;
 }
 
@@ -1188,22 +1668,39 @@ int tsq_identities(tsq_ctx* c, const int32_t** out, uint64_t* count) {
 int tsq_self_scores(tsq_ctx* c, const int32_t** self, uint32_t* n) {
   if (!c || !self) return TSQ_ERR_INVALID;
   if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "no sequences uploaded");
-  *self = c->self_input.data();
+  *self = c->selfp->data();
   if (n) *n = c->n;
   return TSQ_OK;
 }
 
 int tsq_device_scores(tsq_ctx* c, void** d, uint64_t* count) {
   if (!c || !d) return TSQ_ERR_INVALID;
+  if (!c->kids.empty()) return fail(c, TSQ_ERR_STATE, "a multi-device context has no single device buffer");
   if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "tsq_device_scores before tsq_upload");
+  if (!c->full_sorted) return fail(c, TSQ_ERR_STATE, "rank %d holds only its slab: use tsq_device_slab", c->prm.part_rank);
   *d = c->d_sorted.p;
   if (count) *count = c->n < 2 ? 0 : (uint64_t)c->n * (c->n - 1) / 2;
+  return TSQ_OK;
+}
+
+int tsq_device_slab(tsq_ctx* c, void** d, uint64_t* first, uint64_t* count) {
+  if (!c || !d) return TSQ_ERR_INVALID;
+  if (!c->kids.empty()) return fail(c, TSQ_ERR_STATE, "a multi-device context has no single device buffer");
+  if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "tsq_device_slab before tsq_upload");
+  *d = c->d_sorted.p;
+  if (first) *first = c->full_sorted ? 0 : c->part_begin;
+  if (count) *count = c->full_sorted ? (c->n < 2 ? 0 : (uint64_t)c->n * (c->n - 1) / 2) : c->part_end - c->part_begin;
   return TSQ_OK;
 }
 
 int tsq_partition(tsq_ctx* c, uint64_t* b, uint64_t* e) {
   if (!c) return TSQ_ERR_INVALID;
   if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "tsq_partition before tsq_upload");
+  if (!c->kids.empty()) {   // the whole triangle
+    if (b) *b = 0;
+    if (e) *e = c->n < 2 ? 0 : (uint64_t)c->n * (c->n - 1) / 2;
+    return TSQ_OK;
+  }
   if (b) *b = c->part_begin;
   if (e) *e = c->part_end;
   return TSQ_OK;
@@ -1212,6 +1709,12 @@ int tsq_partition(tsq_ctx* c, uint64_t* b, uint64_t* e) {
 int tsq_partition_of(tsq_ctx* c, int32_t rank, uint64_t* b, uint64_t* e) {
   if (!c) return TSQ_ERR_INVALID;
   if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "tsq_partition_of before tsq_upload");
+  if (!c->kids.empty()) {   // device number `rank` of a multi-device context
+    if (rank < 0 || rank >= (int32_t)c->kids.size()) return fail(c, TSQ_ERR_INVALID, "device %d outside 0..%zu", rank, c->kids.size());
+    if (b) *b = c->kids[(size_t)rank]->part_begin;
+    if (e) *e = c->kids[(size_t)rank]->part_end;
+    return TSQ_OK;
+  }
   if (rank < 0 || rank >= c->prm.part_world) return fail(c, TSQ_ERR_INVALID, "rank %d outside 0..%d", rank, c->prm.part_world);
   const uint64_t n = c->n, npairs = n < 2 ? 0 : n * (n - 1) / 2;
   auto start_of = [&](uint32_t row) -> uint64_t { return (n >= 2 && (uint64_t)row + 1 < n) ? tri(row, row + 1, n) : npairs; };
@@ -1224,7 +1727,9 @@ int tsq_partition_of(tsq_ctx* c, int32_t rank, uint64_t* b, uint64_t* e) {
 
 int tsq_device_results(tsq_ctx* c, void** d_scores, void** d_dist, uint64_t* count) {
   if (!c) return TSQ_ERR_INVALID;
+  if (!c->kids.empty()) return fail(c, TSQ_ERR_STATE, "a multi-device context has no single device buffer");
   if (!c->finalized) return fail(c, TSQ_ERR_STATE, "tsq_device_results before tsq_finalize");
+  if (c->slab_mode) return fail(c, TSQ_ERR_STATE, "results of this partition stay sharded (tsq_results_sharded)");
   if (d_scores) *d_scores = (c->perm_identity && c->idshift == 0) ? (void*)c->d_sorted.p : (void*)c->d_scores.p;
   if (d_dist) *d_dist = (c->prm.flags & TSQ_FLAG_NO_DISTANCES) ? nullptr : (void*)c->d_dist.p;
   if (count) *count = c->n < 2 ? 0 : (uint64_t)c->n * (c->n - 1) / 2;
@@ -1233,8 +1738,17 @@ int tsq_device_results(tsq_ctx* c, void** d_scores, void** d_dist, uint64_t* cou
 
 int tsq_guide_tree(tsq_ctx* c, const tsq_merge** merges, uint32_t* count) {
   if (!c) return TSQ_ERR_INVALID;
-  if (!c->finalized) return fail(c, TSQ_ERR_STATE, "tsq_guide_tree before tsq_run / tsq_finalize");
   if (c->prm.flags & TSQ_FLAG_NO_DISTANCES) return fail(c, TSQ_ERR_STATE, "guide tree needs distances (TSQ_FLAG_NO_DISTANCES set)");
+  if (!c->kids.empty()) {   // on the first device, from the distance slabs collected there
+    int rc = multi_prepare_first_device(c);
+    if (rc == TSQ_OK) rc = tsq_guide_tree(c->kids[0], merges, count);
+    if (rc != TSQ_OK && !c->kids[0]->err.empty()) copy_error(c, c->kids[0]);
+    c->tree_ms = c->kids[0]->tree_ms;
+    return rc;
+  }
+  if (!c->finalized) return fail(c, TSQ_ERR_STATE, "tsq_guide_tree before tsq_run / tsq_finalize");
+  if (c->slab_mode && !c->d_dist_full.p)
+    return fail(c, TSQ_ERR_STATE, "this rank holds a slab of the matrix only (tsq_results_sharded): build the tree from the assembled host matrix");
   const uint32_t n = c->n;
   if (!c->have_tree) {
     c->merges.assign(n >= 2 ? n - 1 : 0, tsq_merge{0, 0, 0.0});
@@ -1246,7 +1760,7 @@ int tsq_guide_tree(tsq_ctx* c, const tsq_merge** merges, uint32_t* count) {
       TSQ_CUDA(c, c->d_treeu.reserve((size_t)5 * n + 8));
       TSQ_CUDA(c, c->d_merges.reserve(n - 1));
       tsq::UpgmaParams u{};
-      u.dist = c->d_dist.p;
+      u.dist = c->d_dist_full.p ? c->d_dist_full.p : c->d_dist.p;   // child 0 of a multi-device context: the collected slabs
       u.D = c->d_treeD.p;
       u.rowmin = c->d_treemin.p;
       u.nheight = c->d_treeh.p;
@@ -1285,10 +1799,19 @@ int tsq_write_newick(tsq_ctx* c, const char* const* labels, const char* path) {
   if (!f) return fail(c, TSQ_ERR_IO, "cannot write %s", path);
   auto leaf_name = [&](uint32_t i) -> std::string {
     if (!(labels && labels[i])) return "s" + std::to_string(i);
-    std::string name = labels[i];   // Newick structure characters inside a label would break the tree
-    for (char& ch : name)
-      if (strchr("():;,[]'\" \t", ch)) ch = '_';
-    return name.empty() ? "s" + std::to_string(i) : name;
+    // the label as the matrix file and the FASTA headers spell it; one that contains Newick structure
+    // characters goes in single quotes (a quote inside doubled), as the format prescribes, so that
+    // `clustalo --guidetree-in` and `--distmat-in` see the same names
+    const std::string name = labels[i];
+    if (name.empty()) return "s" + std::to_string(i);
+    if (name.find_first_of("():;,[]'\" \t") == std::string::npos) return name;
+    std::string q = "'";
+    for (char ch : name) {
+      q.push_back(ch);
+      if (ch == '\'') q.push_back('\'');
+    }
+    q.push_back('\'');
+    return q;
   };
   if (n == 0) {
     fputs(";\n", f);
@@ -1407,6 +1930,18 @@ const char* letters_of(const tsq_ctx* c) { return c->prm.alphabet == TSQ_NUCLEOT
 int tsq_msa(tsq_ctx* c, const char** rows, uint32_t* nrows, uint32_t* ncols, const uint32_t** tree_order) {
   if (!c) return TSQ_ERR_INVALID;
   if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "tsq_msa before tsq_run");
+  if (!c->kids.empty()) {   // the progressive alignment is a chain of dependent merges: one device (the first) runs it
+    tsq_ctx* k0 = c->kids[0];
+    int rc = multi_prepare_first_device(c);
+    if (rc != TSQ_OK) return rc;
+    k0->msa_cancel = c->msa_cancel;
+    rc = tsq_msa(k0, rows, nrows, ncols, tree_order);
+    k0->msa_cancel = nullptr;
+    if (rc != TSQ_OK) copy_error(c, k0);
+    c->msa_ms = k0->msa_ms;
+    c->tree_ms = k0->tree_ms;
+    return rc;
+  }
   const tsq_merge* mg = nullptr;
   uint32_t cnt = 0;
   int rc = tsq_guide_tree(c, &mg, &cnt);
@@ -1508,7 +2043,6 @@ int tsq_write_msa_fasta(tsq_ctx* c, const char* const* headers, const char* cons
       fwrite(row.data() + at, 1, std::min<uint32_t>(60, cols - at), f);
       fputc('\n', f);
     }
-    if (cols == 0) fputc('\n', f);
   }
   if (fclose(f) != 0) return fail(c, TSQ_ERR_IO, "write to %s failed", path);
   return TSQ_OK;
@@ -1518,6 +2052,11 @@ int tsq_align_pair(tsq_ctx* c, uint32_t i, uint32_t j, char* row_i, char* row_j,
                    int32_t* score) {
   if (!c || !row_i || !row_j) return TSQ_ERR_INVALID;
   if (!c->uploaded) return fail(c, TSQ_ERR_STATE, "tsq_align_pair before tsq_upload");
+  if (!c->kids.empty()) {   // every device holds the whole database: the first one serves single pairs
+    const int rc = tsq_align_pair(c->kids[0], i, j, row_i, row_j, capacity, columns, score);
+    if (rc != TSQ_OK) copy_error(c, c->kids[0]);
+    return rc;
+  }
   if (i >= c->n || j >= c->n) return fail(c, TSQ_ERR_INVALID, "pair (%u, %u) outside 0..%u", i, j, c->n);
   uint32_t si = c->n, sj = c->n;   // sorted positions of the two submitted indices
   for (uint32_t k = 0; k < c->n; k++) {
@@ -1582,6 +2121,11 @@ int tsq_align_pair(tsq_ctx* c, uint32_t i, uint32_t j, char* row_i, char* row_j,
 int tsq_consensus(tsq_ctx* c, const char* const* rows, uint32_t nrows, uint32_t ncols, double plurality, char* out) {
   if (!c) return TSQ_ERR_INVALID;
   if ((nrows > 0 && !rows) || (ncols > 0 && !out)) return fail(c, TSQ_ERR_INVALID, "null alignment / output");
+  if (!c->kids.empty()) {
+    const int rc = tsq_consensus(c->kids[0], rows, nrows, ncols, plurality, out);
+    if (rc != TSQ_OK) copy_error(c, c->kids[0]);
+    return rc;
+  }
   if (ncols == 0) return TSQ_OK;
   if (nrows == 0) {
     memset(out, '?', ncols);
@@ -1661,6 +2205,34 @@ int tsq_plan_partition(const tsq_params* params, const uint32_t* lengths, uint32
 
 int tsq_get_stats(tsq_ctx* c, tsq_stats* out) {
   if (!c || !out) return TSQ_ERR_INVALID;
+  if (!c->kids.empty()) {
+    // the whole job: sums over the devices; kernel_ms = the slowest device (they run side by side)
+    tsq_stats t = c->st;
+    t.n_pairs = t.cells = t.cells_s16 = t.cells_s32 = 0;
+    t.launches = t.upload_launches = 0;
+    t.h2d_bytes = 0;
+    t.kernel_ms = 0;
+    for (tsq_ctx* k : c->kids) {
+      tsq_stats ks;
+      tsq_get_stats(k, &ks);
+      t.n_pairs += ks.n_pairs;
+      t.cells += ks.cells;
+      t.cells_s16 += ks.cells_s16;
+      t.cells_s32 += ks.cells_s32;
+      t.launches += ks.launches;
+      t.upload_launches += ks.upload_launches;
+      t.h2d_bytes += ks.h2d_bytes;
+      t.kernel_ms = std::max(t.kernel_ms, ks.kernel_ms);
+      t.strip_width = ks.strip_width;
+    }
+    t.n_sequences = c->n;
+    t.gcups_kernel = t.kernel_ms > 0 ? (double)t.cells / (t.kernel_ms * 1e6) : 0.0;
+    t.sm_count = (uint32_t)c->sm_count * (uint32_t)c->kids.size();
+    t.tree_ms = c->tree_ms;
+    t.msa_ms = c->msa_ms;
+    *out = t;
+    return TSQ_OK;
+  }
   c->st.n_sequences = c->n;
   c->st.n_pairs = c->pairs_part;
   c->st.cells_s16 = c->cells16;
@@ -1675,8 +2247,16 @@ int tsq_get_stats(tsq_ctx* c, tsq_stats* out) {
   return TSQ_OK;
 }
 
+int tsq_get_device_stats(tsq_ctx* c, int32_t index, tsq_stats* out) {
+  if (!c || !out) return TSQ_ERR_INVALID;
+  if (c->kids.empty()) return index == 0 ? tsq_get_stats(c, out) : fail(c, TSQ_ERR_INVALID, "device index %d of a one-device context", index);
+  if (index < 0 || index >= (int32_t)c->kids.size()) return fail(c, TSQ_ERR_INVALID, "device index %d outside 0..%zu", index, c->kids.size());
+  return tsq_get_stats(c->kids[(size_t)index], out);
+}
+
 int tsq_measure_dpx_rate(tsq_ctx* c, double* ops, double* mhz) {
   if (!c) return TSQ_ERR_INVALID;
+  if (!c->kids.empty()) return tsq_measure_dpx_rate(c->kids[0], ops, mhz);
   TSQ_CUDA(c, cudaSetDevice(c->device));
   TSQ_CUDA(c, tsq::dpx_probe(c->sm_count, ops, mhz, c->stream));
   return TSQ_OK;
@@ -1747,8 +2327,7 @@ int tsq_run_fasta(const char* fin, const char* fout, const tsq_params* params, t
       if (hdr) { labels.push_back(label_of(line)); headers.push_back(line); seqs.emplace_back(); state = 1; }
     } else if (state == 1) {
       if (f == ';') continue;
-      if (f == '>') { labels.push_back(label_of(line)); headers.push_back(line); seqs.emplace_back(); continue; }
-      seqs.back() += line;
+      seqs.back() += line;   // whatever follows a header is residues, a second '>' line included (FASTAFile.cpp:117-124)
       state = 2;
     } else {
       if (hdr) { labels.push_back(label_of(line)); headers.push_back(line); seqs.emplace_back(); state = 1; }
@@ -1758,6 +2337,28 @@ int tsq_run_fasta(const char* fin, const char* fout, const tsq_params* params, t
   char msg[256];
   snprintf(msg, sizeof msg, "tsq-b200: read %zu sequences from %s", seqs.size(), fin);
   say(msg);
+  tsq_params prm;
+  tsq_default_params(&prm);
+  if (params) {
+    if (params->struct_size < 8 || params->struct_size > sizeof(tsq_params)) return TSQ_ERR_INVALID;
+    memcpy(&prm, params, params->struct_size);
+    prm.struct_size = (uint32_t)sizeof(tsq_params);
+  }
+  if (prm.alphabet == TSQ_ALPHABET_AUTO) {
+    // what clustalo does without --seqtype: at least 90 % of the letters being ACGTUN means nucleotide
+    // (a tweakseq project holds either kind: SequenceFile::DNA / ::Proteins)
+    unsigned long long letters = 0, nuc = 0;
+    for (const std::string& sq : seqs)
+      for (unsigned char ch : sq) {
+        if (!isalpha(ch)) continue;
+        letters++;
+        if (strchr("ACGTUNacgtun", ch)) nuc++;
+      }
+    prm.alphabet = (letters > 0 && nuc * 10 >= letters * 9) ? TSQ_NUCLEOTIDE : TSQ_PROTEIN;
+    say(prm.alphabet == TSQ_NUCLEOTIDE ? "tsq-b200: residues look like nucleotides (ACGTN +5/-4, gap 10/1)"
+                                       : "tsq-b200: residues look like protein (BLOSUM62, gap 11/1)");
+  }
+  params = &prm;
   tsq_ctx* c = nullptr;
   int rc = tsq_create(&c, params);
   if (rc != TSQ_OK) {
@@ -1782,8 +2383,7 @@ int tsq_run_fasta(const char* fin, const char* fout, const tsq_params* params, t
   rc = tsq_distances(c, &d, &cnt);
   // TSQ_FLAG_MSA_OUT: fout is the alignment itself (what Project::readNewAlignment ingests,
   // Project.cpp:908-1032); the matrix moves to <fout>.distmat.  Otherwise fout is the matrix.
-  const bool msa_out = params && params->struct_size >= offsetof(tsq_params, flags) + sizeof(uint32_t) &&
-                       (params->flags & TSQ_FLAG_MSA_OUT);
+  const bool msa_out = (params->flags & TSQ_FLAG_MSA_OUT) != 0;
   const bool keep_matrix = !msa_out || (params->flags & TSQ_FLAG_KEEP_DISTMAT);   // n^2 numbers of text: only on request
   const std::string matrix_path = msa_out ? std::string(fout) + ".distmat" : std::string(fout);
   std::vector<const char*> lab(labels.size());
@@ -1793,13 +2393,16 @@ int tsq_run_fasta(const char* fin, const char* fout, const tsq_params* params, t
     rc = TSQ_ERR_IO;
   }
   if (rc == TSQ_OK) {
-    // guide tree for clustalo --guidetree-in, next to the matrix
+    // guide tree for clustalo --guidetree-in, next to the matrix; with the alignment itself as the output
+    // the tree file is written on request only (nothing should appear next to tweakseq's temporary file)
     const std::string tree = std::string(fout) + ".dnd";
-    if (tsq_write_newick(c, lab.data(), tree.c_str()) == TSQ_OK) say("tsq-b200: wrote guide tree " + tree);
+    if ((!msa_out || (params->flags & TSQ_FLAG_KEEP_TREE)) && tsq_write_newick(c, lab.data(), tree.c_str()) == TSQ_OK)
+      say("tsq-b200: wrote guide tree " + tree);
     tsq_stats st;
     tsq_get_stats(c, &st);
-    snprintf(msg, sizeof msg, "tsq-b200: %llu pairs, %.3e cells, kernel %.3f ms (%.1f GCUPS)%s%s", (unsigned long long)cnt,
-             (double)st.cells, st.kernel_ms, st.gcups_kernel, keep_matrix ? ", wrote " : "", keep_matrix ? matrix_path.c_str() : "");
+    snprintf(msg, sizeof msg, "tsq-b200: %llu pairs, %.3e cells on %d device%s, kernel %.3f ms (%.1f GCUPS)%s%s", (unsigned long long)cnt,
+             (double)st.cells, std::max(1, params->n_devices), params->n_devices > 1 ? "s" : "", st.kernel_ms, st.gcups_kernel,
+             keep_matrix ? ", wrote " : "", keep_matrix ? matrix_path.c_str() : "");
     say(msg);
   }
   if (rc == TSQ_OK && msa_out) {

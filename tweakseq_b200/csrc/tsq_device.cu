@@ -353,7 +353,7 @@ cudaError_t msa_rows_launch(const MsaRows& p, cudaStream_t stream) {
 // tsq_oracle_distance(): two separately rounded IEEE operations (div, sub), no contraction.
 __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeParams p) {
   const unsigned long long n = p.n;
-  for (unsigned long long i = blockIdx.x; i + 1 < n; i += gridDim.x) {
+  for (unsigned long long i = (unsigned long long)p.row_begin + blockIdx.x; i < p.row_end && i + 1 < n; i += gridDim.x) {
     const uint32_t li = p.lens[i];
     const uint32_t oi = p.perm_identity ? (uint32_t)i : p.perm[i];
     const int32_t si = p.self[i];
@@ -398,8 +398,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
 }
 
 cudaError_t finalize_launch(const FinalizeParams& p, cudaStream_t stream) {
-  if (p.n < 2) return cudaSuccess;
-  unsigned int grid = p.n - 1;
+  if (p.n < 2 || p.row_end <= p.row_begin) return cudaSuccess;
+  unsigned int grid = p.row_end - p.row_begin;
   if (grid > 148u * 64u) grid = 148u * 64u;
   finalize_kernel<<<grid, 256, 0, stream>>>(p);
   return cudaGetLastError();

@@ -72,6 +72,10 @@ cudaError_t consensus_launch(const uint8_t* aln, uint32_t nrows, uint32_t ncols,
                              const int8_t* blosum /*23x23*/, const uint8_t* letter_map /*26*/, uint8_t* out,
                              cudaStream_t stream);
 
+// All three packed-triangle pointers are indexed by ABSOLUTE packed index: a context that holds only its
+// slab passes addresses moved back by the slab's first index.  out_scores / out_nid / out_dist may point into
+// ANOTHER device's memory (peer access over NVLink): the children of a multi-device context un-sort their
+// rows straight into device 0's matrix -- finalize and gather in one kernel, no staging copy.
 struct FinalizeParams {
   const int32_t* sorted;      // packed triangle, sorted order
   const uint32_t* lens;       // sorted lengths
@@ -80,6 +84,7 @@ struct FinalizeParams {
   int32_t* out_scores;        // packed triangle, original order (may alias sorted if perm_identity)
   double* out_dist;           // packed triangle, original order, or nullptr
   uint32_t n;
+  uint32_t row_begin, row_end;   // sorted rows this launch covers (a rank's own rows; 0, n for everything)
   int32_t go, ge;
   uint32_t perm_identity;        // perm is the identity and there are no empty sequences
   uint32_t idshift;           // identity mode: sorted[] holds score * 2^idshift + identities; 0 = off

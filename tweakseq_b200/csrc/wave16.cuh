@@ -45,6 +45,8 @@ struct W16Params {
   const uint4* tasks;          // (i1, i2, j, 0): queries i1 <= i2 (i2 == i1: single), subject j
   unsigned long long* counter; // dynamic task cursor
   const int* cancel;           // device flag (set by a side-stream copy): != 0 stops task fetching
+  int* fault;                  // device fault word (cancel + 1): raised when a TMA tile barrier times out
+  uint32_t inject_fault;       // test hook: task 0 arms its first tile barrier without issuing the copy
   uint2* bnd;                  // pass boundary scratch per warp slot: [bnd_rows] rows of (H, E) packed
                                // relative, then [bnd_rows/4 + 16] (base_lo, base_hi) per step
   const uint32_t* sbias;       // (nsym+1) x nsym biased scores S' = S + 2*delta (row nsym = 0)
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
     if (lane == 0) {
       task = atomicAdd(p.counter, 1ULL);
       if (*reinterpret_cast<const volatile int*>(p.cancel) != 0) task = ~0ULL;   // "Stop" pressed
+      if (*reinterpret_cast<const volatile int*>(p.fault) != 0) task = ~0ULL;    // a warp hit a device fault: drain
     }
     task = __shfl_sync(0xffffffffu, task, 0);
     if (task >= p.ntasks) break;
@@ -117,8 +120,9 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
     const uint32_t pass1 = (n1 - 1) / PW;   // pass in which query 1 ends
     const uint32_t nquads = (m + 3) / 4;    // steps per lane: four rows each
     int32_t res_lo = 0, res_hi = 0;
+    bool dead = false;   // a tile barrier timed out (warp-uniform): abandon the task, the fault word is raised
 
-    for (uint32_t pass = 0; pass < npass; ++pass) {
+    for (uint32_t pass = 0; pass < npass && !dead; ++pass) {
       const uint32_t pcol0 = pass * PW;
       const bool firstp = (pass == 0), lastp = (pass + 1 == npass);
       // ---- packed profile of this pass: prof[b][c][l] = S'(A1[col],b) | S'(A2[col],b) << 16 ------
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
       if (lane == 0) {
         fence_proxy_async_smem();
         mbar_arrive_expect_tx(&tbar[0], TILE);
-        bulk_copy_g2s(stile, sq, TILE, &tbar[0]);
+        if (!(p.inject_fault && task == 0 && pass == 0)) bulk_copy_g2s(stile, sq, TILE, &tbar[0]);
         if (ntiles > 1) {
           mbar_arrive_expect_tx(&tbar[1], TILE);
           bulk_copy_g2s(stile + TILE, sq + TILE, TILE, &tbar[1]);
@@ -173,11 +177,11 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
           nbase = bbase[0];
         }
       }
-      mbar_wait_warp(&tbar[0], tph0);
+      dead = !mbar_wait_warp(&tbar[0], tph0, p.fault);
       tph0 ^= 1u;
       uint32_t nlet = lane == 0 ? *reinterpret_cast<const uint32_t*>(stile) : 0u;
       const uint32_t nsteps = nquads + 31;
-      for (uint32_t s = 0; s < nsteps; ++s) {
+      for (uint32_t s = 0; s < nsteps && !dead; ++s) {
         const uint32_t let4 = nlet;
         // ---- tile ring upkeep for the next step (uniform) ------------------------------------------
         {
@@ -185,8 +189,8 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
           if ((s1 & (TSTEPS - 1)) == 0) {            // lane 0 enters tile s1 / TSTEPS
             const uint32_t tix = s1 / TSTEPS;
             if (tix < ntiles) {
-              if (tix & 1u) { mbar_wait_warp(&tbar[1], tph1); tph1 ^= 1u; }
-              else          { mbar_wait_warp(&tbar[0], tph0); tph0 ^= 1u; }
+              if (tix & 1u) { dead = !mbar_wait_warp(&tbar[1], tph1, p.fault); tph1 ^= 1u; }
+              else          { dead = !mbar_wait_warp(&tbar[0], tph0, p.fault); tph0 ^= 1u; }
             }
           }
           if ((s & (TSTEPS - 1)) == 32 && s >= TSTEPS) {   // lane 31 has left tile tix-1: refill its slot
@@ -341,6 +345,7 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
       }
       __syncwarp();
     }
+    if (dead) break;
     // results live in the lanes that own column n1 / n2
     const int own1 = (int)(((n1 - 1) % PW) / KW), own2 = (int)(((n2 - 1) % PW) / KW);
     res_lo = __shfl_sync(0xffffffffu, res_lo, own1);
