@@ -292,10 +292,41 @@ int tsq_get_stats(tsq_ctx *ctx, tsq_stats *out);
 int tsq_get_device_stats(tsq_ctx *ctx, int32_t index, tsq_stats *out);
 
 /*
+ * The length limits that select a kernel under this context's matrix and gap model (host arithmetic; DESIGN.md
+ * section 4).  The packed 16-bit kernels are exact only while every intermediate of the recurrence stays inside an
+ * unsigned 16-bit half; these are the bounds the library enforces -- tests feed the kernels inputs AT them.
+ */
+typedef struct tsq_limits {
+  uint32_t max_len_packed;  /* longest sequence the packed 16-bit inter-task kernel takes (0: none) */
+  uint32_t max_len_inter;   /* longest sequence the inter-task kernel of this context takes; longer: wavefront */
+  int32_t inter_is_32bit;   /* that kernel is the 32-bit one (identity keys, or parameters too wide for 16 bits) */
+  int32_t wave_packed;      /* long sequences run on the packed wavefront kernel (else the 32-bit one) */
+  int64_t wave_window;      /* span, in score units, of the cells a warp of that kernel holds at one time; the kernel
+                               is selected while it is <= wave_window_max */
+  int64_t wave_window_max;
+  int32_t delta;            /* skew per anti-diagonal, ceil(-min S / 2) */
+  int32_t bias_at_limit;    /* BIAS of a job whose longest packed sequence is max_len_packed */
+} tsq_limits;
+int tsq_get_limits(tsq_ctx *ctx, tsq_limits *out);
+
+/*
  * Integer-pipe issue-rate probe ("measure, don't assume"): thread-level
  * VIADDMNMX.U16x2 / VIMNMX3.U16x2 results per clock per SM on this context's device.
  */
 int tsq_measure_dpx_rate(tsq_ctx *ctx, double *ops_per_clk_per_sm, double *sm_mhz);
+/*
+ * All three live denominators of the roofline bench.py reports (nothing hard-coded): the DPX rate above, the issue
+ * ceiling (independent full-rate integer instructions per clock per SM, thread level: 128 on paper) and the packed
+ * cells per clock per SM that the inner loop's own instruction mix (3 DPX + 2 adds + 1 LDS) reaches in isolation,
+ * dependency-free.  Two-pipe bound of the packed kernels: min(dpx / 3, issue / 6) packed cells per clock per SM.
+ */
+typedef struct tsq_pipe_rates {
+  double dpx_per_clk_sm;
+  double issue_per_clk_sm;
+  double mix_packed_cells_per_clk_sm;
+  double sm_mhz;
+} tsq_pipe_rates;
+int tsq_measure_pipe_rates(tsq_ctx *ctx, tsq_pipe_rates *out);
 
 /*
  * File-level convenience for the Qt adapter: read the FASTA file tweakseq

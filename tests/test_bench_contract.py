@@ -26,3 +26,30 @@ def test_reference_arm_is_silent_on_other_ranks():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                           "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_parity_block_checks_the_delivered_result_against_the_oracle():
+    """bench.py's in-line parity object (sampled pairs + first and last rows), on the CPU: clean on the oracle's
+    own matrix, and it sees a single wrong score or distance wherever it sits in the checked set."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import pyoracle as o
+    from tweakseq_b200 import synth
+    seqs = synth.protein(40, 60, 9)
+    enc = [o.encode(s) for s in seqs]
+    mat = o.matrix(0)
+    s, _ = o.all_pairs(enc, mat, 11, 1, nthreads=2)
+    d = o.distances(s, np.array([o.self_score(e, mat) for e in enc], dtype=np.int32))
+    n = len(seqs)
+    blk = bench.parity_block(seqs, 0, s, d, 10_000, 1, 2)
+    assert blk["mismatches"] == 0 and blk["distance_mismatches"] == 0
+    assert blk["pairs_checked"] == n * (n - 1) // 2 and blk["first_row_pairs"] == n - 1    # sample >= population: everything
+    blk = bench.parity_block(seqs, 0, s, None, 50, 2, 2)
+    assert blk["mismatches"] == 0 and "distance_mismatches" not in blk and n - 1 + 6 <= blk["pairs_checked"] <= 70 + n - 1 + 6
+    for bad in (0, n - 2, len(s) - 1):           # first pair, end of the first row, the very last pair: always checked
+        s2, d2 = s.copy(), d.copy()
+        s2[bad] += 1
+        d2[bad] = np.nextafter(d2[bad], 2.0)
+        blk = bench.parity_block(seqs, 0, s2, d2, 10, 3, 2)
+        assert blk["mismatches"] == 1 and blk["distance_mismatches"] == 1

@@ -17,15 +17,25 @@ __global__ void __launch_bounds__(1024, 1) probe(uint32_t* out, const uint32_t k
 #pragma unroll
   for (int i = 0; i < NCH; i++) { a[i] = 0x40004000u + threadIdx.x * 7 + i; b[i] = 0x40004000u + threadIdx.x * 3 + i * 5; h[i] = 0x40004000u + i; }
   const uint32_t* sp = sm + (threadIdx.x & 31);
+  const uint2* sp2 = reinterpret_cast<const uint2*>(sm) + (threadIdx.x & 31);   // lane-private 8-byte column: LDS.64, conflict-free
+  const uint4* sp4 = reinterpret_cast<const uint4*>(sm) + (threadIdx.x & 31);   // lane-private 16-byte column: LDS.128
   const uint32_t goe_r = opaque(k1);      // vector-register copy of a parameter
   const uint32_t nge_r = opaque(k2);
   long long t0 = clock64();
 #pragma unroll 1
   for (int it = 0; it < ITER; it++) {
     const uint32_t* row = sp + (it & 7) * 64;
+    uint32_t sv[NCH];
+    if (V == 6) {          // one LDS.64 per two cells
+#pragma unroll
+      for (int i = 0; i < NCH; i += 2) { const uint2 v = sp2[(it & 7) * 32 + (i / 2) * 256]; sv[i] = v.x; sv[i + 1] = v.y; }
+    } else if (V == 7) {   // one LDS.128 per four cells
+#pragma unroll
+      for (int i = 0; i < NCH; i += 4) { const uint4 v = sp4[(it & 3) * 32 + (i / 4) * 128]; sv[i] = v.x; sv[i + 1] = v.y; sv[i + 2] = v.z; sv[i + 3] = v.w; }
+    }
 #pragma unroll
     for (int i = 0; i < NCH; i++) {
-      uint32_t s = row[i * 33];
+      uint32_t s = (V == 6 || V == 7) ? sv[i] : row[i * 33];
       uint32_t t = h[i] + s;
       uint32_t hh, hg;
       if (V == 0) {        // all register operands, forced IMAD for hg
@@ -43,6 +53,9 @@ __global__ void __launch_bounds__(1024, 1) probe(uint32_t* out, const uint32_t k
       } else if (V == 4) { // register -ge' (param), hg = hh - param (uniform)
         hh = __vimax3_u16x2(t, a[i], b[i]); hg = hh - k1;
         a[i] = __viaddmax_u16x2(a[i], k2, hg); b[i] = __viaddmax_u16x2(b[i], k2, hg);
+      } else if (V == 6 || V == 7) { // vector LDS, immediates, hg = hh - vector register
+        hh = __vimax3_u16x2(t, a[i], b[i]); hg = hh - goe_r;
+        a[i] = __viaddmax_u16x2(a[i], 0x00010001u, hg); b[i] = __viaddmax_u16x2(b[i], 0x00010001u, hg);
       } else {             // 5: no LDS, immediates, hg = hh - vector register
         t = h[i] + k2;
         hh = __vimax3_u16x2(t, a[i], b[i]); hg = hh - goe_r;
@@ -78,6 +91,8 @@ int main() {
     run<3>("V3 imm ge, forced IMAD", threads, nsm, out, dcyc);
     run<4>("V4 param ge, hg=h-param", threads, nsm, out, dcyc);
     run<5>("V5 no LDS, imm ge, hg=h-vreg", threads, nsm, out, dcyc);
+    run<6>("V6 LDS.64 per 2 cells, imm ge, hg=h-vreg", threads, nsm, out, dcyc);
+    run<7>("V7 LDS.128 per 4 cells, imm ge, hg=h-vreg", threads, nsm, out, dcyc);
   }
   return 0;
 }

@@ -51,6 +51,17 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class Limits(C.Structure):
+    _fields_ = [("max_len_packed", C.c_uint32), ("max_len_inter", C.c_uint32), ("inter_is_32bit", C.c_int32),
+                ("wave_packed", C.c_int32), ("wave_window", C.c_int64), ("wave_window_max", C.c_int64),
+                ("delta", C.c_int32), ("bias_at_limit", C.c_int32)]
+
+
+class PipeRates(C.Structure):
+    _fields_ = [("dpx_per_clk_sm", C.c_double), ("issue_per_clk_sm", C.c_double),
+                ("mix_packed_cells_per_clk_sm", C.c_double), ("sm_mhz", C.c_double)]
+
+
 PROGRESS_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_double, C.c_char_p)
 LOG_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p)
 
@@ -61,7 +72,7 @@ SYMBOLS = ["tsq_version", "tsq_version_string", "tsq_status_string", "tsq_device
            "tsq_self_scores", "tsq_identities", "tsq_device_scores", "tsq_partition", "tsq_finalize", "tsq_device_results",
            "tsq_get_stats", "tsq_measure_dpx_rate", "tsq_run_fasta", "tsq_plan_partition", "tsq_guide_tree",
            "tsq_write_newick", "tsq_consensus", "tsq_align_pair", "tsq_partition_of", "tsq_msa", "tsq_write_msa_fasta", "tsq_write_distmat",
-           "tsq_device_slab", "tsq_results_sharded", "tsq_set_result_buffers", "tsq_get_device_stats"]
+           "tsq_device_slab", "tsq_results_sharded", "tsq_set_result_buffers", "tsq_get_device_stats", "tsq_get_limits", "tsq_measure_pipe_rates"]
 
 _lib = None
 
@@ -112,6 +123,8 @@ def load_library():
     L.tsq_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), u64p]
     L.tsq_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.tsq_get_device_stats.argtypes = [vp, C.c_int32, C.POINTER(Stats)]
+    L.tsq_get_limits.argtypes = [vp, C.POINTER(Limits)]
+    L.tsq_measure_pipe_rates.argtypes = [vp, C.POINTER(PipeRates)]
     L.tsq_device_slab.argtypes = [vp, C.POINTER(vp), u64p, u64p]
     L.tsq_results_sharded.argtypes = [vp, C.POINTER(C.c_int)]
     L.tsq_set_result_buffers.argtypes = [vp, vp, vp, C.c_uint64]
@@ -409,6 +422,18 @@ class Context:
         st = Stats()
         self._ck(self._L.tsq_get_stats(self._h, C.byref(st)))
         return st.as_dict()
+
+    def limits(self) -> dict:
+        """The length limits that select a kernel under this context's matrix and gap model (tsq_get_limits)."""
+        lim = Limits()
+        self._ck(self._L.tsq_get_limits(self._h, C.byref(lim)))
+        return {k: getattr(lim, k) for k, _ in lim._fields_}
+
+    def measure_pipe_rates(self) -> dict:
+        """Live roofline denominators: DPX rate, issue ceiling, the inner loop's mix in isolation (tsq_measure_pipe_rates)."""
+        r = PipeRates()
+        self._ck(self._L.tsq_measure_pipe_rates(self._h, C.byref(r)))
+        return {k: getattr(r, k) for k, _ in r._fields_}
 
     def measure_dpx_rate(self) -> tuple[float, float]:
         ops, mhz = C.c_double(), C.c_double()

@@ -473,4 +473,86 @@ cudaError_t dpx_probe(int sms, double* ops_per_clk_per_sm, double* sm_mhz, cudaS
   return e;
 }
 
+// ---- issue-rate and instruction-mix probes (the denominators of bench.py's two-pipe roofline) -----------
+// MODE 0: the issue ceiling -- independent 32-bit adds and xors (full-rate integer work on both pipes).
+// MODE 1: the inner loop's own mix per packed cell, dependency-free: 1 LDS.32 (conflict-free), t = h + s,
+//         h = VIMNMX3.U16x2(t, E, F), hg = h - goe, E/F = VIADDMNMX.U16x2(., imm, hg) -- gotoh16.cuh's cell.
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) mix_probe_kernel(uint32_t* out, uint32_t k1, uint32_t k2, long long* cyc) {
+  constexpr int NCH = 8, ITER = 4096;
+  __shared__ uint32_t sm[2048];
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) sm[i] = i & 15;
+  __syncthreads();
+  uint32_t a[NCH], b[NCH], h[NCH];
+#pragma unroll
+  for (int i = 0; i < NCH; i++) {
+    a[i] = 0x40004000u + threadIdx.x * 7 + i;
+    b[i] = 0x40004000u + threadIdx.x * 3 + i * 5;
+    h[i] = 0x40004000u + i;
+  }
+  const uint32_t* sp = sm + (threadIdx.x & 31);
+  uint32_t goe_r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(goe_r) : "r"(k1));
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < ITER; it++) {
+    const uint32_t* row = sp + (it & 7) * 64;
+#pragma unroll
+    for (int i = 0; i < NCH; i++) {
+      if (MODE == 0) {
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(k1));
+        asm volatile("xor.b32 %0, %0, %1;" : "+r"(b[i]) : "r"(k2));
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(h[i]) : "r"(k2));
+      } else {
+        const uint32_t s = row[i * 33];
+        const uint32_t t = h[i] + s;
+        const uint32_t hh = __vimax3_u16x2(t, a[i], b[i]);
+        const uint32_t hg = hh - goe_r;
+        a[i] = __viaddmax_u16x2(a[i], 0x00010001u, hg);
+        b[i] = __viaddmax_u16x2(b[i], 0x00010001u, hg);
+        h[i] = hh;
+      }
+    }
+  }
+  const long long t1 = clock64();
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < NCH; i++) r ^= a[i] ^ b[i] ^ h[i];
+  if (r == 0x12345678u) out[threadIdx.x] = r;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+cudaError_t mix_probe(int sms, double* issue_per_clk_per_sm, double* mix_cells_per_clk_per_sm, cudaStream_t stream) {
+  uint32_t* d_out = nullptr;
+  long long* d_cyc = nullptr;
+  cudaError_t e;
+  if ((e = cudaMalloc(&d_out, 1024 * sizeof(uint32_t))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&d_cyc, sizeof(long long) * sms)) != cudaSuccess) {
+    cudaFree(d_out);
+    return e;
+  }
+  long long* h = new long long[sms];
+  auto avg_cycles = [&](int mode) -> double {
+    for (int rep = 0; rep < 2; rep++) {   // the first launch warms up
+      if (mode == 0) mix_probe_kernel<0><<<sms, 512, 0, stream>>>(d_out, 0x000a000a, 0x00010001, d_cyc);
+      else mix_probe_kernel<1><<<sms, 512, 0, stream>>>(d_out, 0x000a000a, 0x00010001, d_cyc);
+    }
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return 0.0;
+    if ((e = cudaMemcpy(h, d_cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost)) != cudaSuccess) return 0.0;
+    double avg = 0;
+    for (int i = 0; i < sms; i++) avg += (double)h[i];
+    return avg / sms;
+  };
+  const double c0 = avg_cycles(0);
+  const double c1 = e == cudaSuccess ? avg_cycles(1) : 0.0;
+  if (e == cudaSuccess && c0 > 0 && c1 > 0) {
+    if (issue_per_clk_per_sm) *issue_per_clk_per_sm = 512.0 * 8 * 4096 * 3 / c0;
+    if (mix_cells_per_clk_per_sm) *mix_cells_per_clk_per_sm = 512.0 * 8 * 4096 / c1;
+  }
+  delete[] h;
+  cudaFree(d_out);
+  cudaFree(d_cyc);
+  return e;
+}
+
 }  // namespace tsq

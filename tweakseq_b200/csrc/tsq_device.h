@@ -95,4 +95,8 @@ cudaError_t finalize_launch(const FinalizeParams& p, cudaStream_t stream);
 // DPX issue-rate probe: thread-level VIADDMNMX.U16x2 + VIMNMX3.U16x2 results / clk / SM.
 cudaError_t dpx_probe(int device_sms, double* ops_per_clk_per_sm, double* sm_mhz, cudaStream_t stream);
 
+// Issue ceiling (independent full-rate integer instructions, thread-level per clk per SM) and the packed cells
+// per clk per SM the inner loop's own instruction mix reaches in isolation (dependency-free).
+cudaError_t mix_probe(int device_sms, double* issue_per_clk_per_sm, double* mix_cells_per_clk_per_sm, cudaStream_t stream);
+
 }  // namespace tsq
