@@ -375,10 +375,10 @@ def test_partition_slabs_with_wavefront_rows():
     for r in range(world):
         ctx = t.Context(alphabet=1, part_rank=r, part_world=world, flags=t.FLAG_NO_DISTANCES)
         ctx.set_sequences(seqs); ctx.upload(); ctx.compute(); ctx.synchronize()
-        ranges.append(ctx.partition()); bufs.append(torch.as_tensor(ctx.device_scores(), device="cuda")); ctxs.append(ctx)
+        ranges.append(ctx.partition()); bufs.append(torch.as_tensor(ctx.device_slab()[0], device="cuda")); ctxs.append(ctx)
     assert ranges == capi.plan_partition([len(s) for s in seqs], world, alphabet=1)
     b, e = ranges[1]
-    bufs[0][b:e] = bufs[1][b:e]
+    bufs[0][b:e] = bufs[1]                              # rank 1 holds its slab only
     ctxs[0].finalize(); ctxs[0].download()
     assert (ctxs[0].scores() == full).all()
     rs, _, _, _ = oracle_run(seqs, 1)

@@ -104,13 +104,21 @@ def test_run_fasta_writes_the_guide_tree_next_to_the_matrix(tmp_path):
 
 
 @pytest.mark.gpu
-def test_newick_labels_are_sanitised(tmp_path):
+def test_newick_labels_with_structure_characters_are_quoted_not_rewritten(tmp_path):
+    """The tree file must name the leaves as the matrix file and the FASTA headers do (clustalo reads both): a label
+    holding Newick structure characters goes in single quotes, a quote inside doubled."""
     import tweakseq_b200 as t
     with t.Context() as ctx:
         ctx.set_sequences(["ACDEFGHIK", "ACDEFGHIR", "WWWWWWW"])
         ctx.run()
         path = str(tmp_path / "t.dnd")
-        ctx.write_newick(path, ["sp|P1|A:1", "b (x)", "c;d,e"])
+        ctx.write_newick(path, ["sp|P1|A:1", "b (x)", "c;d'e"])
     txt = open(path).read().strip()
-    assert "sp|P1|A_1:" in txt and "b__x_:" in txt and "c_d_e:" in txt
-    assert txt.count("(") == 2 and txt.count(")") == 2 and txt.endswith(";") and txt.count(";") == 1
+    assert "'sp|P1|A:1':" in txt and "'b (x)':" in txt and "'c;d''e':" in txt
+    bare = txt.replace("'sp|P1|A:1'", "a").replace("'b (x)'", "b").replace("'c;d''e'", "c")
+    assert bare.count("(") == 2 and bare.count(")") == 2 and bare.endswith(";") and bare.count(";") == 1
+    with t.Context() as ctx:
+        ctx.set_sequences(["ACDEFGHIK", "ACDEFGHIR", "WWWWWWW"])
+        ctx.run()
+        ctx.write_newick(path, ["plain_1", "sp|P2|B", "x.y-z"])
+    assert "'" not in open(path).read()          # ordinary labels stay bare

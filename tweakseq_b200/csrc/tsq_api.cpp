@@ -258,6 +258,7 @@ int fail(tsq_ctx* c, int code, const char* fmt, ...) {
   do {                                                                                     \
     cudaError_t e_ = (call);                                                               \
     if (e_ != cudaSuccess) {                                                               \
+      cudaGetLastError(); /* not sticky: the next launch check must not report this one */ \
       return fail((c), e_ == cudaErrorMemoryAllocation ? TSQ_ERR_NOMEM : TSQ_ERR_CUDA,     \
                   "%s failed: %s", #call, cudaGetErrorString(e_));                         \
     }                                                                                      \
@@ -932,16 +933,23 @@ void host_extent(const tsq_ctx* c, uint64_t* first, uint64_t* count) {
   *count = slab_only ? c->part_end - c->part_begin : npairs;
 }
 
-// Page-locks [p, p + bytes) of caller memory (whole pages) unless an earlier call already did.
+// Page-locks the whole pages INSIDE [p, p + bytes) of caller memory, unless an earlier call already did.  The
+// partial pages at either end stay pageable: they may be shared with a neighbouring array or with another rank's
+// slab (whose owner would register them too, and overlapping registrations are refused); copy_out() moves them
+// with small pageable copies, because a copy may not span page-locked and pageable memory.
+constexpr uintptr_t kPage = 4096;
+inline uintptr_t page_up(uintptr_t x) { return (x + kPage - 1) & ~(kPage - 1); }
+inline uintptr_t page_down(uintptr_t x) { return x & ~(kPage - 1); }
+
 int register_range(tsq_ctx* c, void* p, size_t bytes) {
   if (!p || bytes == 0) return TSQ_OK;
-  const uintptr_t page = 4096;
-  const uintptr_t a = reinterpret_cast<uintptr_t>(p) & ~(page - 1);
-  const uintptr_t b = (reinterpret_cast<uintptr_t>(p) + bytes + page - 1) & ~(page - 1);
+  const uintptr_t a = page_up(reinterpret_cast<uintptr_t>(p));
+  const uintptr_t b = page_down(reinterpret_cast<uintptr_t>(p) + bytes);
+  if (b <= a) return TSQ_OK;
   for (void* r : c->ext_registered)
     if (r == reinterpret_cast<void*>(a)) return TSQ_OK;
   const cudaError_t e = cudaHostRegister(reinterpret_cast<void*>(a), b - a, cudaHostRegisterPortable);
-  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {   // the caller pinned it already (cudaHostAlloc, or its own register)
     cudaGetLastError();
     return TSQ_OK;
   }
@@ -951,6 +959,22 @@ int register_range(tsq_ctx* c, void* p, size_t bytes) {
   }
   c->ext_registered.push_back(reinterpret_cast<void*>(a));
   return TSQ_OK;
+}
+
+// Device -> host copy of one slab.  Into caller memory (registered as above): head partial page, whole pages,
+// tail partial page, so that no copy spans page-locked and pageable memory; into the library's own pinned
+// buffers: one copy.
+cudaError_t copy_out(const tsq_ctx* owner, void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return cudaSuccess;
+  if (!owner->ext_scores) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s);
+  const uintptr_t p = reinterpret_cast<uintptr_t>(dst);
+  const uintptr_t a = std::min(page_up(p), p + bytes), b = std::max(page_down(p + bytes), a);
+  const char* sp = static_cast<const char*>(src);
+  cudaError_t e = cudaSuccess;
+  if (a > p) e = cudaMemcpyAsync(dst, sp, a - p, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && b > a) e = cudaMemcpyAsync(reinterpret_cast<void*>(a), sp + (a - p), b - a, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && p + bytes > b) e = cudaMemcpyAsync(reinterpret_cast<void*>(b), sp + (b - p), p + bytes - b, cudaMemcpyDeviceToHost, s);
+  return e;
 }
 
 void unregister_all(tsq_ctx* c) {
@@ -1194,9 +1218,9 @@ int multi_download(tsq_ctx* c) {
         return rc;
       }
       TSQ_CUDA(c, cudaSetDevice(k0->device));
-      TSQ_CUDA(c, cudaMemcpyAsync(h.scores, k0->d_scores.p, npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, k0->stream));
+      TSQ_CUDA(c, copy_out(c, h.scores, k0->d_scores.p, npairs * sizeof(int32_t), k0->stream));
       if (c->idshift) TSQ_CUDA(c, cudaMemcpyAsync(h.nid, k0->d_nid.p, npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, k0->stream));
-      if (want_dist) TSQ_CUDA(c, cudaMemcpyAsync(h.dist, k0->d_dist.p, npairs * sizeof(double), cudaMemcpyDeviceToHost, k0->stream));
+      if (want_dist) TSQ_CUDA(c, copy_out(c, h.dist, k0->d_dist.p, npairs * sizeof(double), k0->stream));
     }
     bytes = npairs * (want_dist ? 12ull : 4ull) + (c->idshift ? npairs * 4ull : 0ull);
   }
@@ -1545,8 +1569,8 @@ int tsq_download(tsq_ctx* c) {
       HostDst h;
       int rc = host_results(c, want_dist, false, &h);
       if (rc != TSQ_OK) return rc;
-      TSQ_CUDA(c, cudaMemcpyAsync(h.scores + c->part_begin, c->d_sorted.p, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-      if (want_dist) TSQ_CUDA(c, cudaMemcpyAsync(h.dist + c->part_begin, c->d_dist.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
+      TSQ_CUDA(c, copy_out(result_owner(c), h.scores + c->part_begin, c->d_sorted.p, cnt * sizeof(int32_t), s));
+      if (want_dist) TSQ_CUDA(c, copy_out(result_owner(c), h.dist + c->part_begin, c->d_dist.p, cnt * sizeof(double), s));
       bytes = cnt * (want_dist ? 12ull : 4ull);
     }
     if (c->leader) {   // the leader synchronizes all its devices once every copy is in flight
@@ -1558,9 +1582,9 @@ int tsq_download(tsq_ctx* c) {
     int rc = host_results(c, want_dist, c->idshift != 0, &h);
     if (rc != TSQ_OK) return rc;
     const int32_t* src = (c->perm_identity && c->idshift == 0) ? c->d_sorted.p : c->d_scores.p;
-    TSQ_CUDA(c, cudaMemcpyAsync(h.scores, src, npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    TSQ_CUDA(c, copy_out(c, h.scores, src, npairs * sizeof(int32_t), s));
     if (c->idshift) TSQ_CUDA(c, cudaMemcpyAsync(h.nid, c->d_nid.p, npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    if (want_dist) TSQ_CUDA(c, cudaMemcpyAsync(h.dist, c->d_dist.p, npairs * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (want_dist) TSQ_CUDA(c, copy_out(c, h.dist, c->d_dist.p, npairs * sizeof(double), s));
     bytes = npairs * (want_dist ? 12ull : 4ull) + (c->idshift ? npairs * 4ull : 0ull);
   }
   int rc = tsq_synchronize(c);

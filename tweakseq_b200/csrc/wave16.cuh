@@ -66,6 +66,10 @@ __device__ __forceinline__ uint32_t pack_rel(int32_t a, int32_t base_lo, int32_t
   return ((uint32_t)(a - base_lo) & 0xffffu) | ((uint32_t)(a - base_hi) << 16);
 }
 
+__device__ __forceinline__ uint32_t comp4(const uint4& v, int k) {   // k is a compile-time constant after unrolling
+  return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w;
+}
+
 template <int KW, int TPB, int MINB, uint32_t NGE>
 __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant__ W16Params p) {
   constexpr int PW = 32 * KW;        // columns per pass
@@ -133,10 +137,14 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
         const uint32_t a2 = col < n2 ? q2[col] : nsym;
         const uint32_t* r1 = sb + a1 * nsym;
         const uint32_t* r2 = sb + a2 * nsym;
-        for (uint32_t b = 0; b < nsym; ++b) prof[b * PW + c2 * 32 + lane] = r1[b] | (r2[b] << 16);
+        // layout [letter][column group of 4][lane][4]: a lane's four adjacent columns are one 16-byte vector,
+        // and the 8 lanes of a quarter-warp cover 128 contiguous bytes -> one conflict-free LDS.128 per four
+        // packed cells, whatever the letters
+        uint32_t* dst = prof + (c2 >> 2) * 128 + lane * 4 + (c2 & 3);
+        for (uint32_t b = 0; b < nsym; ++b) dst[b * PW] = r1[b] | (r2[b] << 16);
       }
       __syncwarp();
-      const uint32_t* myprof = prof + lane;
+      const uint32_t* myprof = prof + lane * 4;
 
       // ---- row 0 of this lane's column block; absolute skewed A(0,j) = -go - j*ge' ----------------
       const int32_t col0 = (int32_t)(pcol0 + lane * KW);
@@ -246,12 +254,15 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
             if (ra == m) {
               // ---- last row of an odd-length subject ----------------------------------------------
               uint32_t E = iEa;
-              uint32_t t = hdiag + prow_a[0];
+              uint4 va[KW / 4];
+#pragma unroll
+              for (int g = 0; g < KW / 4; ++g) va[g] = *reinterpret_cast<const uint4*>(prow_a + g * 128);
+              uint32_t t = hdiag + va[0].x;
               hdiag = iHa;
 #pragma unroll
               for (int c = 0; c < KW; ++c) {
                 uint32_t tn = 0;
-                if (c + 1 < KW) tn = H[c] + prow_a[(c + 1) * 32];
+                if (c + 1 < KW) tn = H[c] + comp4(va[(c + 1) >> 2], (c + 1) & 3);
                 const uint32_t h = __vimax3_u16x2(t, E, F[c]);
                 H[c] = h;
                 const uint32_t hg = h - goe2;
@@ -266,15 +277,25 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
               // ---- rows ra (A) and ra+1 (B), B one column behind A ----------------------------------
               const uint32_t* prow_b = myprof + ((let4 >> (16 * q + 8)) & 0xffu) * PW;
               uint32_t Ea = iEa, Eb = iEb;
-              uint32_t ta = hdiag + prow_a[0];
-              uint32_t tb = iHa + prow_b[0];
+              // substitution scores: one LDS.128 per four columns and row, fetched two columns ahead of use
+              // (one register group per four columns, each live only around its own columns: no copies)
+              uint4 va[KW / 4], vb[KW / 4];
+              va[0] = *reinterpret_cast<const uint4*>(prow_a);
+              vb[0] = *reinterpret_cast<const uint4*>(prow_b);
+              uint32_t ta = hdiag + va[0].x;
+              uint32_t tb = iHa + vb[0].x;
               hdiag = iHb;
               uint32_t ha_last = 0;
 #pragma unroll
               for (int c = 0; c <= KW; ++c) {
+                // columns 4g .. 4g+3 of both rows are first needed at c = 4g - 1 (row A) / c = 4g (row B)
+                if ((c & 3) == 1 && c + 3 < KW) {
+                  va[(c + 3) >> 2] = *reinterpret_cast<const uint4*>(prow_a + ((c + 3) >> 2) * 128);
+                  vb[(c + 3) >> 2] = *reinterpret_cast<const uint4*>(prow_b + ((c + 3) >> 2) * 128);
+                }
                 if (c < KW) {
                   uint32_t tn = 0;
-                  if (c + 1 < KW) tn = H[c] + prow_a[(c + 1) * 32];
+                  if (c + 1 < KW) tn = H[c] + comp4(va[(c + 1) >> 2], (c + 1) & 3);
                   const uint32_t h = __vimax3_u16x2(ta, Ea, F[c]);
                   H[c] = h;
                   const uint32_t hg = h - goe2;
@@ -285,7 +306,7 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
                 }
                 if (c >= 1) {
                   uint32_t tn = 0;
-                  if (c < KW) tn = H[c - 1] + prow_b[c * 32];
+                  if (c < KW) tn = H[c - 1] + comp4(vb[c >> 2], c & 3);
                   const uint32_t h = __vimax3_u16x2(tb, Eb, F[c - 1]);
                   H[c - 1] = h;
                   const uint32_t hg = h - goe2;
