@@ -216,6 +216,10 @@ int tsq_set_result_buffers(tsq_ctx *ctx, int32_t *scores, double *distances, uin
  * n+t; height = half the distance of the merged clusters.  Ties: smallest first slot, then
  * smallest second slot; the merged cluster keeps the first slot.  Computed on the device.
  */
+#define TSQ_GUIDE_TREE_MAX_N 32768u /* tsq_guide_tree / tsq_msa / tsq_write_newick beyond this: TSQ_ERR_RANGE.  The tree
+                                       kernel holds a dense n x n fp64 matrix (8.6 GB at the limit) and its n-1 merges are
+                                       dependent steps of one persistent CTA (~6 us each: 0.2 s at the limit).  BASELINE
+                                       configs[4] (100 000 sequences) is a distance-matrix job; its matrix would be 80 GB. */
 typedef struct tsq_merge {
   uint32_t left, right;
   double height;

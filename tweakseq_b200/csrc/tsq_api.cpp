@@ -13,9 +13,11 @@
 #include <cstring>
 #include <cstdlib>
 #include <fstream>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -65,17 +67,112 @@ double now_ms() {
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
+// Process-wide caches of released device and page-locked host blocks.  The plugin call (tsq_run_fasta) builds a
+// context per alignment job; cudaMalloc / cudaHostAlloc / cudaFree of its dozen buffers cost more than the kernels
+// of a 100-sequence job, so released blocks are kept (up to a bound) and handed to the next context that asks for
+// a similar size on the same device.  Never freed at exit: the CUDA runtime may be gone by then.
+class BlockCache {
+ public:
+  static BlockCache& get() {
+    static BlockCache* inst = new BlockCache();   // intentionally leaked
+    return *inst;
+  }
+  // device < 0: page-locked host memory (portable: any device may copy into it)
+  cudaError_t take(int device, size_t bytes, void** out) {
+    {
+      std::lock_guard<std::mutex> g(m_);
+      size_t best = free_.size();
+      for (size_t i = 0; i < free_.size(); i++)
+        if (free_[i].device == device && free_[i].bytes >= bytes && free_[i].bytes <= 2 * bytes + 4096 &&
+            (best == free_.size() || free_[i].bytes < free_[best].bytes))
+          best = i;
+      if (best != free_.size()) {
+        *out = free_[best].p;
+        live_[*out] = free_[best].bytes;
+        cached_ -= free_[best].bytes;
+        free_.erase(free_.begin() + (long)best);
+        return cudaSuccess;
+      }
+    }
+    cudaError_t e = device < 0 ? cudaHostAlloc(out, bytes, cudaHostAllocPortable) : cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {   // give the cache back and try once more
+      cudaGetLastError();
+      trim(device);
+      e = device < 0 ? cudaHostAlloc(out, bytes, cudaHostAllocPortable) : cudaMalloc(out, bytes);
+    }
+    if (e == cudaSuccess) {
+      std::lock_guard<std::mutex> g(m_);
+      live_[*out] = bytes;
+    }
+    return e;
+  }
+  void give(int device, void* p) {
+    if (!p) return;
+    size_t bytes = 0;
+    {
+      std::lock_guard<std::mutex> g(m_);
+      auto it = live_.find(p);
+      if (it != live_.end()) {
+        bytes = it->second;
+        live_.erase(it);
+      }
+      if (bytes > 0 && bytes <= kMaxBlock && cached_ + bytes <= kMaxCached && free_.size() < 64) {
+        free_.push_back({p, bytes, device});
+        cached_ += bytes;
+        return;
+      }
+    }
+    if (device < 0) cudaFreeHost(p);
+    else cudaFree(p);
+  }
+
+ private:
+  struct Entry {
+    void* p;
+    size_t bytes;
+    int device;
+  };
+  static constexpr size_t kMaxBlock = (size_t)256 << 20, kMaxCached = (size_t)1 << 30;
+  void trim(int device) {
+    std::vector<Entry> drop;
+    {
+      std::lock_guard<std::mutex> g(m_);
+      for (size_t i = free_.size(); i-- > 0;)
+        if (free_[i].device == device) {
+          drop.push_back(free_[i]);
+          cached_ -= free_[i].bytes;
+          free_.erase(free_.begin() + (long)i);
+        }
+    }
+    for (const Entry& e : drop) {
+      if (e.device < 0) cudaFreeHost(e.p);
+      else cudaFree(e.p);
+    }
+  }
+  std::mutex m_;
+  std::vector<Entry> free_;
+  std::unordered_map<void*, size_t> live_;
+  size_t cached_ = 0;
+};
+
+int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) cudaGetLastError();
+  return d;
+}
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t cap = 0;  // elements
+  int dev = 0;     // the device the block lives on
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
+    release();
+    dev = current_device();
+    cudaError_t e = BlockCache::get().take(dev, std::max<size_t>(n, 1) * sizeof(T), (void**)&p);
     if (e == cudaSuccess) cap = n;
+    else p = nullptr;
     return e;
   }
   // scratch that kernels read a few slack rows beyond what they wrote (prefetch): zero it once
@@ -86,7 +183,15 @@ struct DevBuf {
     return e;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      // what cudaFree did implicitly: nothing in flight on the block's device may still use it when the cache
+      // hands it to the next taker
+      const int cur = current_device();
+      if (cur != dev) cudaSetDevice(dev);
+      if (cudaDeviceSynchronize() != cudaSuccess) cudaGetLastError();
+      if (cur != dev) cudaSetDevice(cur);
+      BlockCache::get().give(dev, p);
+    }
     p = nullptr;
     cap = 0;
   }
@@ -98,16 +203,15 @@ struct PinnedBuf {
   size_t cap = 0;
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    cap = 0;
+    release();
     // portable: every device of a multi-device context copies its slab straight into this buffer
-    cudaError_t e = cudaHostAlloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocPortable);
+    cudaError_t e = BlockCache::get().take(-1, std::max<size_t>(n, 1) * sizeof(T), (void**)&p);
     if (e == cudaSuccess) cap = n;
+    else p = nullptr;
     return e;
   }
   void release() {
-    if (p) cudaFreeHost(p);
+    if (p) BlockCache::get().give(-1, p);
     p = nullptr;
     cap = 0;
   }
@@ -1371,8 +1475,9 @@ int tsq_create(tsq_ctx** out, const tsq_params* params) {
     tsq_destroy(c);
     return TSQ_ERR_CUDA;
   }
-  if (cudaMalloc((void**)&c->d_cancel, 2 * sizeof(int)) != cudaSuccess || cudaMemset(c->d_cancel, 0, 2 * sizeof(int)) != cudaSuccess ||
-      cudaHostAlloc((void**)&c->h_one, 2 * sizeof(int), cudaHostAllocPortable) != cudaSuccess ||
+  if (BlockCache::get().take(c->device, 2 * sizeof(int), (void**)&c->d_cancel) != cudaSuccess ||
+      cudaMemset(c->d_cancel, 0, 2 * sizeof(int)) != cudaSuccess ||
+      BlockCache::get().take(-1, 2 * sizeof(int), (void**)&c->h_one) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->cancel_stream, cudaStreamNonBlocking) != cudaSuccess) {
     cudaGetLastError();
     tsq_destroy(c);
@@ -1392,14 +1497,15 @@ int tsq_destroy(tsq_ctx* c) {
   c->kids.clear();
   cudaSetDevice(c->device);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+  if (c->stream && c->stream != c->own_stream && cudaStreamSynchronize(c->stream) != cudaSuccess) cudaGetLastError();
   unregister_all(c);
   c->d_dbw.release(); c->d_blob.release(); c->h_blob.release();
   c->d_sorted.release(); c->d_scores.release(); c->d_nid.release(); c->h_nid.release(); c->d_dist.release(); c->d_dist_full.release();
   c->d_counter.release(); c->d_bnd.release(); c->h_scores.release(); c->h_dist.release();
   c->d_treeD.release(); c->d_treemin.release(); c->d_treeh.release(); c->d_treeu.release(); c->d_merges.release();
   c->d_pairs32.release(); c->d_tasks16w.release(); c->d_bnd16w.release(); c->d_bnd32.release(); c->d_smat.release();
-  if (c->d_cancel) cudaFree(c->d_cancel);
-  if (c->h_one) cudaFreeHost(c->h_one);
+  if (c->d_cancel) BlockCache::get().give(c->device, c->d_cancel);
+  if (c->h_one) BlockCache::get().give(-1, c->h_one);
   if (c->cancel_stream) cudaStreamDestroy(c->cancel_stream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1775,6 +1881,10 @@ int tsq_guide_tree(tsq_ctx* c, const tsq_merge** merges, uint32_t* count) {
   if (c->slab_mode && !c->d_dist_full.p)
     return fail(c, TSQ_ERR_STATE, "this rank holds a slab of the matrix only (tsq_results_sharded): build the tree from the assembled host matrix");
   const uint32_t n = c->n;
+  if (!c->have_tree && n > TSQ_GUIDE_TREE_MAX_N)
+    return fail(c, TSQ_ERR_RANGE, "guide tree of %u sequences: the UPGMA kernel keeps a dense n x n fp64 matrix and runs its n-1 "
+                "dependent merges on one SM; the limit is %u sequences (%.1f GB)", n, (unsigned)TSQ_GUIDE_TREE_MAX_N,
+                (double)TSQ_GUIDE_TREE_MAX_N * TSQ_GUIDE_TREE_MAX_N * 8 / 1e9);
   if (!c->have_tree) {
     c->merges.assign(n >= 2 ? n - 1 : 0, tsq_merge{0, 0, 0.0});
     if (n >= 2) {
@@ -1882,9 +1992,10 @@ namespace {
 // makes ~2n small allocations), scratch is one growing block, everything runs on the context's stream.
 class CudaMsaDevice : public tsq::MsaDevice {
  public:
-  explicit CudaMsaDevice(cudaStream_t s) : s_(s) {}
+  explicit CudaMsaDevice(cudaStream_t s) : s_(s), dev_(current_device()) {}
   ~CudaMsaDevice() override {
-    for (void* p : chunks_) cudaFree(p);
+    if (!chunks_.empty() && cudaDeviceSynchronize() != cudaSuccess) cudaGetLastError();
+    for (void* p : chunks_) BlockCache::get().give(dev_, p);
     scr_.release();
   }
   cudaError_t err = cudaSuccess;   // first CUDA error seen
@@ -1896,7 +2007,7 @@ class CudaMsaDevice : public tsq::MsaDevice {
     if (bytes > left_) {
       const size_t chunk = std::max(bytes, (size_t)64 << 20);
       void* p = nullptr;
-      if (!ok(cudaMalloc(&p, chunk))) return nullptr;
+      if (!ok(BlockCache::get().take(dev_, chunk, &p))) return nullptr;
       chunks_.push_back(p);
       cur_ = (char*)p;
       left_ = chunk;
@@ -1942,6 +2053,7 @@ class CudaMsaDevice : public tsq::MsaDevice {
     return e == cudaSuccess;
   }
   cudaStream_t s_;
+  int dev_;
   std::vector<void*> chunks_;
   char* cur_ = nullptr;
   size_t left_ = 0;

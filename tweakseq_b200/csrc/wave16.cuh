@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
       // first pass: column 0 of the matrix, A(r,0) = -go - r*ge', kept packed and relative for row 4s+1
       uint32_t colH = pack_rel(-go - gep, base_lo, base_hi);
 
-      uint32_t oH[2][2] = {{0u, 0u}, {0u, 0u}}, oE[2][2] = {{0u, 0u}, {0u, 0u}};  // to the right neighbour
+      uint32_t oH[4] = {0u, 0u, 0u, 0u}, oE[4] = {0u, 0u, 0u, 0u};  // right edge of this step's four rows: to lane l+1
       uint2 nb[4] = {make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u)};
       int2 nbase = make_int2(0, 0);
       // ---- subject tiles: 2 x 1 KB ring in shared memory, filled by TMA bulk copies ----------------
@@ -239,15 +239,90 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
         }
         const int32_t ps = (int32_t)s - lane;
         const bool lane_on = ps >= 0 && (uint32_t)ps < nquads;
+        // the left neighbour's right edge of the same four rows (its previous step), all lanes converged
+        uint32_t iH[4], iE[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          iH[k] = __shfl_up_sync(0xffffffffu, oH[k], 1);
+          iE[k] = __shfl_up_sync(0xffffffffu, oE[k], 1);
+          if (lane == 0) {
+            iH[k] = lH[k];
+            iE[k] = lE[k];
+          }
+        }
+        const uint32_t ra0 = 4 * (uint32_t)ps + 1;
+        if (lane_on && ra0 + 3 <= m) {
+          // ---- the common case: all four rows exist.  Rows A..D together, each one column behind the one
+          //      above: FOUR independent dependency chains per lane (the two-row body of the tail path below
+          //      has two), which is what keeps the half-rate DPX pipe fed from three warps per scheduler ------
+          const uint32_t* prow[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) prow[r] = myprof + ((let4 >> (8 * r)) & 0xffu) * PW;
+          uint32_t E[4], t[4], hl[4] = {0u, 0u, 0u, 0u};
+          uint4 v[4][KW / 4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            E[r] = iE[r];
+            v[r][0] = *reinterpret_cast<const uint4*>(prow[r]);
+          }
+          t[0] = hdiag + v[0][0].x;       // diagonal of row A's first cell: the left lane's H of the row above
+          t[1] = iH[0] + v[1][0].x;
+          t[2] = iH[1] + v[2][0].x;
+          t[3] = iH[2] + v[3][0].x;
+          hdiag = iH[3];
+#pragma unroll
+          for (int c = 0; c < KW + 3; ++c) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const int k = c - r;          // row r works on its column k in this round
+              if (k >= 0 && k < KW) {
+                // scores of columns 4g .. 4g+3: one LDS.128, issued one column before its first use
+                if (((k + 2) & 3) == 0 && k + 2 < KW)
+                  v[r][(k + 2) >> 2] = *reinterpret_cast<const uint4*>(prow[r] + ((k + 2) >> 2) * 128);
+                uint32_t tn = 0;
+                if (k + 1 < KW) tn = H[k] + comp4(v[r][(k + 1) >> 2], (k + 1) & 3);   // H[k]: still the row above
+                const uint32_t h = __vimax3_u16x2(t[r], E[r], F[k]);
+                H[k] = h;
+                const uint32_t hg = h - goe2;
+                E[r] = __viaddmax_u16x2(E[r], nge, hg);
+                F[k] = __viaddmax_u16x2(F[k], nge, hg);
+                t[r] = tn;
+                if (k == KW - 1) hl[r] = h;
+              }
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            oH[r] = hl[r];
+            oE[r] = E[r];
+          }
+          if (lane == 31 && !lastp) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) brow[ra0 + r] = make_uint2(oH[r], oE[r]);
+          }
+          if (ra0 + 3 == m) {   // the subject's last row: H(m, n) of a query that ends in this block, made absolute
+            if (pass == pass1) {
+              const int32_t c1 = (int32_t)n1 - 1 - col0;
+              if (c1 >= 0 && c1 < KW) {
+#pragma unroll
+                for (int c = 0; c < KW; ++c)
+                  if (c == c1) res_lo = (int32_t)(H[c] & 0xffffu) + base_lo;
+              }
+            }
+            if (lastp) {
+              const int32_t c2 = (int32_t)n2 - 1 - col0;
+              if (c2 >= 0 && c2 < KW) {
+#pragma unroll
+                for (int c = 0; c < KW; ++c)
+                  if (c == c2) res_hi = (int32_t)(H[c] >> 16) + base_hi;
+              }
+            }
+          }
+        } else {
+        // ---- the last step of a lane whose subject length is not a multiple of four: two rows, then one ----
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          uint32_t iHa = __shfl_up_sync(0xffffffffu, oH[q][0], 1);
-          uint32_t iEa = __shfl_up_sync(0xffffffffu, oE[q][0], 1);
-          uint32_t iHb = __shfl_up_sync(0xffffffffu, oH[q][1], 1);
-          uint32_t iEb = __shfl_up_sync(0xffffffffu, oE[q][1], 1);
-          if (lane == 0) {
-            iHa = lH[2 * q]; iEa = lE[2 * q]; iHb = lH[2 * q + 1]; iEb = lE[2 * q + 1];
-          }
+          const uint32_t iHa = iH[2 * q], iEa = iE[2 * q], iHb = iH[2 * q + 1], iEb = iE[2 * q + 1];
           const uint32_t ra = 4 * (uint32_t)ps + 2 * q + 1;
           if (lane_on && ra <= m) {
             const uint32_t* prow_a = myprof + ((let4 >> (16 * q)) & 0xffu) * PW;
@@ -270,9 +345,9 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
                 F[c] = __viaddmax_u16x2(F[c], nge, hg);
                 t = tn;
               }
-              oH[q][0] = H[KW - 1];
-              oE[q][0] = E;
-              if (lane == 31 && !lastp) brow[ra] = make_uint2(oH[q][0], oE[q][0]);
+              oH[2 * q] = H[KW - 1];
+              oE[2 * q] = E;
+              if (lane == 31 && !lastp) brow[ra] = make_uint2(oH[2 * q], oE[2 * q]);
             } else {
               // ---- rows ra (A) and ra+1 (B), B one column behind A ----------------------------------
               const uint32_t* prow_b = myprof + ((let4 >> (16 * q + 8)) & 0xffu) * PW;
@@ -315,10 +390,10 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
                   tb = tn;
                 }
               }
-              oH[q][0] = ha_last; oE[q][0] = Ea; oH[q][1] = H[KW - 1]; oE[q][1] = Eb;
+              oH[2 * q] = ha_last; oE[2 * q] = Ea; oH[2 * q + 1] = H[KW - 1]; oE[2 * q + 1] = Eb;
               if (lane == 31 && !lastp) {
-                brow[ra] = make_uint2(oH[q][0], oE[q][0]);
-                brow[ra + 1] = make_uint2(oH[q][1], oE[q][1]);
+                brow[ra] = make_uint2(oH[2 * q], oE[2 * q]);
+                brow[ra + 1] = make_uint2(oH[2 * q + 1], oE[2 * q + 1]);
               }
             }
             // ---- the subject's last row: H(m, n) of a query that ends in this block, made absolute ----
@@ -342,6 +417,7 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
             }
           }
         }
+        }
         if (lane == 31 && !lastp && lane_on) bbase[ps] = make_int2(base_lo, base_hi);
         // ---- re-centre the base on lane 16's first column (all lanes, uniform) ----------------------
         if ((s & (RB - 1)) == RB - 1 && s < nquads) {
@@ -357,8 +433,9 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
           hdiag -= shift2;
           colH -= shift2;
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            oH[q][0] -= shift2; oE[q][0] -= shift2; oH[q][1] -= shift2; oE[q][1] -= shift2;
+          for (int k = 0; k < 4; ++k) {
+            oH[k] -= shift2;
+            oE[k] -= shift2;
           }
           base_lo += sh_lo;
           base_hi += sh_hi;
