@@ -132,6 +132,12 @@ const char *tsq_status_string(int status);
 int tsq_device_count(void);
 
 void tsq_default_params(tsq_params *p);
+/*
+ * Protein or nucleotide?  What clustalo decides without --seqtype, and what TSQ_ALPHABET_AUTO means in
+ * tsq_run_fasta: TSQ_NUCLEOTIDE when at least 90 % of the letters are ACGTUN, else TSQ_PROTEIN (also for no
+ * letters at all).  Host only; for callers that hold the residues in memory.
+ */
+int tsq_detect_alphabet(const char *const *residues, const uint32_t *lengths, uint32_t n);
 int tsq_create(tsq_ctx **out, const tsq_params *params);
 int tsq_destroy(tsq_ctx *ctx);
 /* Last error text of this context ("" if none).  Never NULL. */

@@ -167,6 +167,8 @@ def _ref_qt_lib():
         _ref_qt.tsq_qt_settings_round_trip.argtypes = [C.c_char_p, C.c_ulong]
         _ref_qt.tsq_qt_worker_run.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                               C.c_char_p, C.c_ulong]
+        _ref_qt.tsq_qt_worker_run_in_memory.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                                        C.c_char_p, C.c_ulong]
     return _ref_qt
 
 
@@ -185,6 +187,18 @@ def qt_worker_run(fin: str, fout: str, align_in_process: bool = True):
     if _ref_qt_lib().tsq_qt_worker_run(fin.encode(), fout.encode(), 1 if align_in_process else 0, C.byref(ec), C.byref(es),
                                        buf, len(buf)) != 0:
         raise RuntimeError("tsq_qt_worker_run failed")
+    return ec.value, es.value, buf.value.decode().splitlines()
+
+
+def qt_worker_run_in_memory(labels, residues, fout: str):
+    """The in-memory worker: (label, Sequence::filter(true)) pairs as startAlignment takes them from the model;
+    fout receives the alignment with ">label" headers.  (exit code, exit status, log lines)."""
+    buf = C.create_string_buffer(1 << 16)
+    ec, es = C.c_int(), C.c_int()
+    lab = "".join(l + "\n" for l in labels).encode()
+    res = "".join(r + "\n" for r in residues).encode()
+    if _ref_qt_lib().tsq_qt_worker_run_in_memory(lab, res, fout.encode(), C.byref(ec), C.byref(es), buf, len(buf)) != 0:
+        raise RuntimeError("tsq_qt_worker_run_in_memory failed")
     return ec.value, es.value, buf.value.decode().splitlines()
 
 

@@ -72,18 +72,46 @@ extern "C" int tsq_qt_settings_round_trip(char* out, unsigned long cap) {
 // read what it emitted through finished(int, int); log lines arrive as queued addMessage(QString) invocations.
 extern "C" int tsq_qt_worker_run(const char* fin, const char* fout, int align_in_process, int* exit_code, int* exit_status,
                                  char* log, unsigned long cap) {
-  QObject message_window;
+  QObject main_window;
   B200GotohTool tool;
   tool.alignInProcess = align_in_process != 0;
   g_exit_code = g_exit_status = -999;
   qtShimInvocations().clear();
-  B200GotohWorker w(&tool, QString::fromStd(fin), QString::fromStd(fout), &message_window);
+  B200GotohWorker w(&tool, QString::fromStd(fin), QString::fromStd(fout), &main_window);
+  w.start();
+  w.wait();
+  *exit_code = g_exit_code;
+  *exit_status = g_exit_status;
+  std::string s;
+  for (auto& inv : qtShimInvocations())   // every log line leaves as the worker's own message(QString) signal
+    if (inv.receiver == &w && inv.member == "message") s += inv.text + "\n";
+  return put(s, log, cap);
+}
+
+// The in-memory route: labels and residues as startAlignment takes them from the
+// model -- label and Sequence::filter(true) -- `n` of each, '\n'-separated; fout = the alignment, headers ">label".
+extern "C" int tsq_qt_worker_run_in_memory(const char* labels_nl, const char* residues_nl, const char* fout, int* exit_code,
+                                           int* exit_status, char* log, unsigned long cap) {
+  auto split = [](const char* s) {
+    QStringList out;
+    std::string cur;
+    for (const char* p = s; *p; ++p) {
+      if (*p == '\n') { out << QString::fromStd(cur); cur.clear(); }
+      else cur.push_back(*p);
+    }
+    return out;
+  };
+  QObject main_window;
+  B200GotohTool tool;
+  g_exit_code = g_exit_status = -999;
+  qtShimInvocations().clear();
+  B200GotohWorker w(&tool, split(labels_nl), split(residues_nl), QString::fromStd(fout), &main_window);
   w.start();
   w.wait();
   *exit_code = g_exit_code;
   *exit_status = g_exit_status;
   std::string s;
   for (auto& inv : qtShimInvocations())
-    if (inv.receiver == &message_window && inv.member == "addMessage") s += inv.text + "\n";
+    if (inv.receiver == &w && inv.member == "message") s += inv.text + "\n";
   return put(s, log, cap);
 }

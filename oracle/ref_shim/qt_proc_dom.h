@@ -25,6 +25,7 @@ class QByteArray {
   QByteArray() {}
   explicit QByteArray(const std::string& s) : s_(s) {}
   const char* constData() const { return s_.c_str(); }
+  int size() const { return (int)s_.size(); }
   std::string s_;
 };
 inline QByteArray QString::toLocal8Bit() const { return QByteArray(toStd()); }

@@ -34,7 +34,9 @@ class QString {
   QByteArray toLatin1() const;
   static QString number(int, int base = 10);
   static QString fromUtf8(const char *, int size = -1);
+  friend const QString operator+(const QString &, const QString &);
 };
+const QString operator+(const QString &, const QString &);
 
 template <typename T>
 class QList {

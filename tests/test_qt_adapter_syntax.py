@@ -4,6 +4,7 @@ be type-checked: g++ -fsyntax-only against the REAL reference headers it derives
 Skipped where /root/reference is absent (the GPU box)."""
 import os
 import subprocess
+import sys
 
 import pytest
 
@@ -23,11 +24,11 @@ def test_qt_adapter_type_checks_against_the_reference_headers():
 def test_qt_adapter_overrides_exactly_the_reference_virtuals():
     """Every virtual of the reference class is re-declared with the same parameter list, plus the two additions."""
     src = open(os.path.join(ROOT, "host", "qt", "B200GotohTool.h")).read()
-    for decl in ("virtual void makeCommand(QString &, QString &, QString &, QStringList &);",
-                 "virtual void writeSettings(QDomDocument &, QDomElement &);",
-                 "virtual void readSettings(QDomDocument &);",
-                 "virtual bool inProcess(){return true;}",
-                 "virtual int run(const QString &fin, const QString &fout, QObject *logReceiver, volatile int *cancel);"):
+    for decl in ("virtual void makeCommand(QString &, QString &, QString &, QStringList &) override;",
+                 "virtual void writeSettings(QDomDocument &, QDomElement &) override;",
+                 "virtual void readSettings(QDomDocument &) override;",
+                 "virtual bool inProcess() TSQ_OVERRIDE {return true;}",
+                 "virtual int run(const QString &fin, const QString &fout, QObject *logReceiver, volatile int *cancel) TSQ_OVERRIDE;"):
         assert decl in src, decl
 
 
@@ -63,3 +64,47 @@ def test_qt_worker_reports_like_qprocess_finished_and_refuses_without_a_b200(tmp
     code, status, log = o.qt_worker_run(fin, str(tmp_path / "out.fa"))
     assert (code, status) == (-2, 0)                       # TSQ_ERR_NO_DEVICE through finished(int, int): no fallback
     assert any("read 2 sequences" in l for l in log)       # log lines arrive as queued MessageWin::addMessage calls
+
+
+# ---- the registration edits as an artifact: host/qt/tweakseq_registration.patch -----------------
+PATCH = os.path.join(ROOT, "host", "qt", "tweakseq_registration.patch")
+REF_ROOT = "/root/reference"
+PATCHED_FILES = ["tweakseq/Core/AlignmentTool.h", "tweakseq/Core/Project.h", "tweakseq/Core/Project.cpp",
+                 "tweakseq/Core/Application.h", "tweakseq/Core/Application.cpp", "tweakseq/UI/SeqEditMainWin.h",
+                 "tweakseq/UI/SeqEditMainWin.cpp", "tweakseq/tweakseq.pro"]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_CORE, "AlignmentTool.h")), reason="reference sources not present")
+def test_registration_patch_applies_to_the_reference_and_the_adapter_overrides_the_patched_virtuals(tmp_path):
+    import shutil
+    # the committed patch is what the generator produces from the reference as it is
+    regen = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_qt_patch.py"), REF_ROOT, str(tmp_path / "regen.patch")],
+                           capture_output=True, text=True, timeout=120)
+    assert regen.returncode == 0, regen.stderr
+    assert open(tmp_path / "regen.patch", encoding="latin-1").read() == open(PATCH, encoding="latin-1").read()
+    # dry run against the reference tree itself (read-only: nothing is written) ...
+    dry = subprocess.run(["patch", "-p1", "--dry-run", "-d", REF_ROOT, "-i", PATCH], capture_output=True, text=True, timeout=120)
+    assert dry.returncode == 0, dry.stdout + dry.stderr
+    assert dry.stdout.count("checking file") == len(PATCHED_FILES) and "FAILED" not in dry.stdout and "fuzz" not in dry.stdout
+    # ... and for real on a copy of the eight files
+    work = tmp_path / "tree"
+    for f in PATCHED_FILES:
+        os.makedirs(work / os.path.dirname(f), exist_ok=True)
+        shutil.copy(os.path.join(REF_ROOT, f), work / f)
+    out = subprocess.run(["patch", "-p1", "-d", str(work), "-i", PATCH], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and not list(work.rglob("*.rej")), out.stdout + out.stderr
+    txt = {f: open(work / f, encoding="latin-1").read() for f in PATCHED_FILES}
+    assert "virtual bool inProcess(){return false;}" in txt["tweakseq/Core/AlignmentTool.h"]
+    assert txt["tweakseq/Core/Project.cpp"].count("b200GotohTool_") >= 9 and "Core/B200GotohTool.cpp" in txt["tweakseq/tweakseq.pro"]
+    cpp = txt["tweakseq/UI/SeqEditMainWin.cpp"]
+    assert "SLOT(alignmentFinishedInProcess(int,int))" in cpp and "SLOT(alignmentMessage(QString))" in cpp
+    assert "->filter(true)" in cpp and "alignmentWorker_->requestCancel()" in cpp
+    # the slots the worker's signals are connected to exist with exactly those signatures
+    assert "void alignmentFinishedInProcess(int,int);" in txt["tweakseq/UI/SeqEditMainWin.h"]
+    assert "void alignmentMessage(const QString &);" in txt["tweakseq/UI/SeqEditMainWin.h"]
+    # against the PATCHED AlignmentTool.h the adapter's inProcess()/run() are checked overrides (TSQ_OVERRIDE = override)
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Wno-unused-parameter", "-Werror=suggest-override",
+           "-I", os.path.join(ROOT, "tests", "qt_stub"), "-I", str(work / "tweakseq" / "Core"), "-I", REF_CORE,
+           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "host", "qt", "B200GotohTool.cpp")]
+    chk = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert chk.returncode == 0, chk.stderr

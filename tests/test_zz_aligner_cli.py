@@ -234,3 +234,27 @@ def test_gpu_qt_worker_runs_the_alignment_in_process(tmp_path):
     want, order = t.B200Gotoh().multiple_alignment(seqs)
     got_labels, got_rows, _ = o.ref_fasta_read(fout)
     assert got_labels == [labels[r] for r in order] and got_rows == [want[r] for r in order]
+
+
+@pytest.mark.gpu
+def test_gpu_qt_worker_in_memory_route_keeps_the_labels(tmp_path):
+    """The hazard of the file route (SURVEY 8b): Project::exportFASTA writes `comment` as the header
+    (Project.cpp:876-880), so a renamed sequence or a PDB import (comment without '>') comes back under a label
+    readNewAlignment cannot match.  The in-memory worker takes (label, filter(true)) from the model and writes
+    ">label": the reference's own reader must find exactly the labels that went in, nucleotides detected."""
+    from oracle import pyoracle as o
+    if not (o.ref_qt_adapter_available() and o.ref_fasta_available()):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    import tweakseq_b200 as t
+    rng = np.random.default_rng(94)
+    seqs = ["".join(rng.choice(list("ACGT"), int(l))) for l in rng.integers(60, 110, 7)]
+    labels = ["renamed_1", "1abc_A", "chr1:100-200", "s3", "s4", "s5", "s6"]      # none of them is its comment's first word
+    fout = str(tmp_path / "out.fa")
+    code, status, log = o.qt_worker_run_in_memory(labels, seqs, fout)
+    assert (code, status) == (0, 0), log
+    assert any("7 sequences from the project (nucleotide)" in l for l in log), log
+    tool = t.B200Gotoh()
+    tool.alphabet = t.NUCLEOTIDE
+    want, order = tool.multiple_alignment(seqs)
+    got_labels, got_rows, _ = o.ref_fasta_read(fout)
+    assert got_labels == [labels[r] for r in order] and got_rows == [want[r] for r in order]

@@ -72,7 +72,7 @@ SYMBOLS = ["tsq_version", "tsq_version_string", "tsq_status_string", "tsq_device
            "tsq_self_scores", "tsq_identities", "tsq_device_scores", "tsq_partition", "tsq_finalize", "tsq_device_results",
            "tsq_get_stats", "tsq_measure_dpx_rate", "tsq_run_fasta", "tsq_plan_partition", "tsq_guide_tree",
            "tsq_write_newick", "tsq_consensus", "tsq_align_pair", "tsq_partition_of", "tsq_msa", "tsq_write_msa_fasta", "tsq_write_distmat",
-           "tsq_device_slab", "tsq_results_sharded", "tsq_set_result_buffers", "tsq_get_device_stats", "tsq_get_limits", "tsq_measure_pipe_rates"]
+           "tsq_device_slab", "tsq_results_sharded", "tsq_set_result_buffers", "tsq_get_device_stats", "tsq_get_limits", "tsq_measure_pipe_rates", "tsq_detect_alphabet"]
 
 _lib = None
 
@@ -124,6 +124,7 @@ def load_library():
     L.tsq_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.tsq_get_device_stats.argtypes = [vp, C.c_int32, C.POINTER(Stats)]
     L.tsq_get_limits.argtypes = [vp, C.POINTER(Limits)]
+    L.tsq_detect_alphabet.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), C.c_uint32]
     L.tsq_measure_pipe_rates.argtypes = [vp, C.POINTER(PipeRates)]
     L.tsq_device_slab.argtypes = [vp, C.POINTER(vp), u64p, u64p]
     L.tsq_results_sharded.argtypes = [vp, C.POINTER(C.c_int)]
@@ -156,6 +157,15 @@ def flatten(seqs):
     if raw:
         offs[1:] = np.cumsum([len(r) for r in raw], dtype=np.uint64)
     return b"".join(raw), offs
+
+
+def detect_alphabet(seqs) -> int:
+    """tsq_detect_alphabet(): NUCLEOTIDE when at least 90 % of the letters are ACGTUN, else PROTEIN (host only)."""
+    L = load_library()
+    raw = [s.encode("latin-1", "replace") if isinstance(s, str) else bytes(s) for s in seqs]
+    arr = (C.c_char_p * max(len(raw), 1))(*raw) if raw else (C.c_char_p * 1)()
+    lens = (C.c_uint32 * max(len(raw), 1))(*[len(r) for r in raw]) if raw else (C.c_uint32 * 1)()
+    return L.tsq_detect_alphabet(arr, lens, len(raw))
 
 
 def plan_partition(lengths, world: int, **kw) -> list[tuple[int, int]]:

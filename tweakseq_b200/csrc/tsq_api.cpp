@@ -433,7 +433,8 @@ bool fits16(const tsq_ctx* c, uint32_t lpad) {
 
 // The packed wavefront kernel (wave16.cuh) is exact while the cells a warp holds at one time span
 // less than 2^15 score units: window = cells in flight x per-step Lipschitz bound of the skewed DP.
-constexpr long long kWave16WindowMax = 30000;
+constexpr long long kWave16WindowMax = tsq::kW16WindowMax;
+inline long long lipschitz_of(const tsq_ctx* c) { return std::max(std::abs(c->smax), std::abs(c->smin)) + c->go + c->ge + 2 * c->delta; }
 bool wave16_ok(const tsq_ctx* c, int nsym, uint32_t flags) {
   if (flags & TSQ_FLAG_NO_WAVE16) return false;
   const long long lip = std::max(std::abs(c->smax), std::abs(c->smin)) + c->go + c->ge + 2 * c->delta;
@@ -880,7 +881,7 @@ int enqueue_gotoh16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
 int enqueue_wave16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
   if (!c->tasks16w.empty()) {
     tsq::W32Launch v;
-    if (!tsq::w16_variant((uint32_t)c->nsym, &v)) return fail(c, TSQ_ERR_INVALID, "no packed wavefront kernel variant");
+    if (!tsq::w16_variant((uint32_t)c->nsym, lipschitz_of(c), &v)) return fail(c, TSQ_ERR_INVALID, "no packed wavefront kernel variant");
     const int warps_per_cta = v.tpb / 32;
     int grid = c->sm_count * v.ctas_sm;
     const unsigned long long need = (c->tasks16w.size() + warps_per_cta - 1) / warps_per_cta;
@@ -912,7 +913,7 @@ int enqueue_wave16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
     w.gep = c->ge - c->delta;
     w.goep = c->go + c->ge - c->delta;
     w.negge2 = ((uint32_t)(-(c->ge - c->delta)) & 0xffffu) * 0x10001u;
-    TSQ_CUDA(c, tsq::w16_launch(grid, w, s));
+    TSQ_CUDA(c, tsq::w16_launch(grid, w, lipschitz_of(c), s));
     launches++;
   }
   return TSQ_OK;
@@ -1362,6 +1363,18 @@ int multi_prepare_first_device(tsq_ctx* c) {
 }  // namespace
 
 extern "C" {
+
+int tsq_detect_alphabet(const char* const* residues, const uint32_t* lengths, uint32_t n) {
+  unsigned long long letters = 0, nuc = 0;
+  for (uint32_t i = 0; i < n && residues && lengths; i++)
+    for (uint32_t k = 0; residues[i] && k < lengths[i]; k++) {
+      const unsigned char ch = (unsigned char)residues[i][k];
+      if (!isalpha(ch)) continue;
+      letters++;
+      if (strchr("ACGTUNacgtun", ch)) nuc++;
+    }
+  return (letters > 0 && nuc * 10 >= letters * 9) ? TSQ_NUCLEOTIDE : TSQ_PROTEIN;
+}
 
 int tsq_create(tsq_ctx** out, const tsq_params* params) {
   if (!out) return TSQ_ERR_INVALID;
@@ -2510,16 +2523,14 @@ int tsq_run_fasta(const char* fin, const char* fout, const tsq_params* params, t
     prm.struct_size = (uint32_t)sizeof(tsq_params);
   }
   if (prm.alphabet == TSQ_ALPHABET_AUTO) {
-    // what clustalo does without --seqtype: at least 90 % of the letters being ACGTUN means nucleotide
-    // (a tweakseq project holds either kind: SequenceFile::DNA / ::Proteins)
-    unsigned long long letters = 0, nuc = 0;
-    for (const std::string& sq : seqs)
-      for (unsigned char ch : sq) {
-        if (!isalpha(ch)) continue;
-        letters++;
-        if (strchr("ACGTUNacgtun", ch)) nuc++;
-      }
-    prm.alphabet = (letters > 0 && nuc * 10 >= letters * 9) ? TSQ_NUCLEOTIDE : TSQ_PROTEIN;
+    // what clustalo does without --seqtype (a tweakseq project holds either kind: SequenceFile::DNA / ::Proteins)
+    std::vector<const char*> rp(seqs.size());
+    std::vector<uint32_t> rl(seqs.size());
+    for (size_t i = 0; i < seqs.size(); i++) {
+      rp[i] = seqs[i].data();
+      rl[i] = (uint32_t)seqs[i].size();
+    }
+    prm.alphabet = tsq_detect_alphabet(rp.data(), rl.data(), (uint32_t)seqs.size());
     say(prm.alphabet == TSQ_NUCLEOTIDE ? "tsq-b200: residues look like nucleotides (ACGTN +5/-4, gap 10/1)"
                                        : "tsq-b200: residues look like protein (BLOSUM62, gap 11/1)");
   }

@@ -133,12 +133,25 @@ cudaError_t w32_launch(int grid, const W32Params& p, cudaStream_t stream) {
   X(16, 128, 3)             \
   X(8, 128, 2)
 
-bool w16_variant(uint32_t nsym, W32Launch* out) {
+// Columns per lane and CTAs per SM.  Small alphabets (nucleotides): 32 columns per lane, 2 CTAs (8 warps) per SM --
+// r02 sweep on 120 genomes of 10-30 kb with the four-row body: 32,2 -> 6 864 GCUPS; 24,3 -> 6 366; 16,3 -> 5 830 (a
+// wider block spreads the per-step hand-off over more cells and needs fewer passes) -- unless the window of 32
+// columns is too wide for the gap model at hand, then 24,3.  Proteins: 8 columns (23.5 KB of profile per warp).
+static bool w16_pick(uint32_t nsym, long long lipschitz, W32Launch* out) {
   if (nsym == 0 || nsym > 24) return false;
   W32Launch v;
-  v.KW = nsym <= 8 ? 24 : 8;
   v.tpb = 128;
-  v.ctas_sm = nsym <= 8 ? 3 : 2;
+  if (nsym <= 8) {
+    v.KW = 32;
+    v.ctas_sm = 2;
+    if (lipschitz > 0 && (32ll * 32 + 4 * 31 + 4 * 16 + 16) * lipschitz > kW16WindowMax) {
+      v.KW = 24;
+      v.ctas_sm = 3;
+    }
+  } else {
+    v.KW = 8;
+    v.ctas_sm = 2;
+  }
   if (const char* e = getenv("TSQ_FORCE_KW16")) {  // developer override for tuning runs: "KW,ctas"
     int kw = 0, ct = 0;
     if (sscanf(e, "%d,%d", &kw, &ct) == 2) {
@@ -154,15 +167,17 @@ bool w16_variant(uint32_t nsym, W32Launch* out) {
   return true;
 }
 
+bool w16_variant(uint32_t nsym, long long lipschitz, W32Launch* out) { return w16_pick(nsym, lipschitz, out); }
+
 long long w16_window(uint32_t nsym, long long lipschitz) {
   W32Launch v;
-  if (!w16_variant(nsym, &v)) return 1ll << 40;
+  if (!w16_pick(nsym, lipschitz, &v)) return 1ll << 40;
   return (32ll * v.KW + 4 * 31 + 4 * 16 + 16) * lipschitz;  // 4 rows per step, RB = 16 steps between re-centrings
 }
 
-cudaError_t w16_launch(int grid, const W16Params& p, cudaStream_t stream) {
+cudaError_t w16_launch(int grid, const W16Params& p, long long lipschitz, cudaStream_t stream) {
   W32Launch v;
-  if (!w16_variant(p.nsym, &v)) return cudaErrorInvalidValue;
+  if (!w16_variant(p.nsym, lipschitz, &v)) return cudaErrorInvalidValue;
 #define X(KK, TT, MM)                                                                        \
   if (v.KW == KK && v.ctas_sm == MM) {                                                       \
     auto kern = p.negge2 == 0x00010001u ? wave16_kernel<KK, TT, MM, 0x00010001u>             \

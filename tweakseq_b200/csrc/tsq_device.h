@@ -44,9 +44,11 @@ cudaError_t w32_launch(int grid, const W32Params& p, cudaStream_t stream);
 
 // Packed wavefront kernel (wave16.cuh).  w16_window() is the span D (in score units) of the cells a
 // warp holds at one time for a per-step Lipschitz bound L; the kernel is exact while D <= 30000.
-bool w16_variant(uint32_t nsym, W32Launch* out);
+// The variant depends on the per-step Lipschitz bound too: the widest column block whose window still fits.
+constexpr long long kW16WindowMax = 30000;
+bool w16_variant(uint32_t nsym, long long lipschitz, W32Launch* out);
 long long w16_window(uint32_t nsym, long long lipschitz);
-cudaError_t w16_launch(int grid, const W16Params& p, cudaStream_t stream);
+cudaError_t w16_launch(int grid, const W16Params& p, long long lipschitz, cudaStream_t stream);
 
 // UPGMA guide tree: init (one CTA per row) + one persistent CTA for the n-1 merges.
 cudaError_t upgma_launch(const UpgmaParams& p, cudaStream_t stream);
