@@ -157,6 +157,25 @@ def cpu_oracle_gcups(seqs, alphabet: int, budget_s: float, threads: int):
     return cells / dt / 1e9, f"first {npairs} of {total} packed pairs ({cells:.3e} cells, {dt:.1f} s)"
 
 
+def cpu_simd_gcups(seqs, alphabet: int, budget_s: float, threads: int):
+    """Times the SIMD CPU kernel (oracle/gotoh_simd.c: one subject per int16 lane, 32 lanes; AVX-512BW / AVX2 by
+    target_clones; bit-identical to the scalar port) on a bounded prefix of the rows.  Returns (gcups, sample)."""
+    from oracle import pyoracle as o
+    enc = [o.encode(s, alphabet) for s in seqs]
+    mat = o.matrix(alphabet)
+    go = 10 if alphabet else 11
+    n = len(enc)
+    probe_rows = min(n - 1, max(1, 2 * threads))
+    t0 = time.perf_counter()
+    _, cells = o.rows_simd(enc, mat, go, 1, nthreads=threads, row_begin=0, row_end=probe_rows)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    rows = int(min(n - 1, max(probe_rows, budget_s * (cells / dt) / max(cells / probe_rows, 1))))
+    t0 = time.perf_counter()
+    _, cells = o.rows_simd(enc, mat, go, 1, nthreads=threads, row_begin=0, row_end=rows)
+    dt = time.perf_counter() - t0
+    return cells / dt / 1e9, f"rows 0..{rows} of {n} against all later sequences ({cells:.3e} cells, {dt:.1f} s)"
+
+
 def parity_block(seqs, alphabet: int, scores, dist, n_sample: int, seed: int, threads: int):
     """Sampled pairs + complete first and last rows of the DELIVERED host result against the oracle."""
     import numpy as np
@@ -248,26 +267,42 @@ def reference_arm(args):
     go = 10 if alphabet else 11
     n = len(enc)
     total = n * (n - 1) // 2
-    per_step = min(total, 3000 * threads)       # ~0.3-0.5 s of CPU work per step
+    # The CPU arm is the better of the oracle's two kernels: the inter-sequence SIMD one (gotoh_simd.c; int16 lanes,
+    # AVX-512BW / AVX2) where the scores fit 16 bits, on all host threads.  A step = a block of rows against all
+    # later sequences, sized for ~0.5 s.
     steps, warm = args.steps, args.warmup
+    rows_per_step = max(1, min(n - 1, 4 * threads))
+    t0 = time.perf_counter()
+    _, c0 = o.rows_simd(enc, mat, go, 1, nthreads=threads, row_begin=0, row_end=rows_per_step)
+    dt0 = max(time.perf_counter() - t0, 1e-6)
+    rows_per_step = int(max(1, min(n - 1, rows_per_step * 0.5 / dt0)))
     cells_total, t_total = 0, 0.0
     for it in range(warm + steps):
-        b = (it * per_step) % max(total - per_step, 1)
+        b = (it * rows_per_step) % max(n - 1 - rows_per_step, 1)
         t0 = time.perf_counter()
-        _, cells = o.all_pairs(enc, mat, go, 1, nthreads=threads, pair_begin=b, pair_end=b + per_step)
+        _, cells = o.rows_simd(enc, mat, go, 1, nthreads=threads, row_begin=b, row_end=b + rows_per_step)
         dt = time.perf_counter() - t0
         if it >= warm:
             cells_total += cells
             t_total += dt
     gcups = cells_total / t_total / 1e9
+    # the scalar port beside it (what round 1 reported as the CPU arm)
+    per_step = min(total, 1500 * threads)
+    t0 = time.perf_counter()
+    _, sc = o.all_pairs(enc, mat, go, 1, nthreads=threads, pair_begin=0, pair_end=per_step)
+    scalar_gcups = sc / (time.perf_counter() - t0) / 1e9
     line = {"impl": "reference", "metric": METRIC, "value": gcups, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": 1e3 * t_total / steps, "higher_is_better": True,
-            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": label, "sample_pairs_per_step": per_step},
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "int16 SIMD lanes (exact; int32 scalar beyond the 16-bit range)", "data": "synthetic",
+            "config": {"workload": label, "sample_rows_per_step": rows_per_step},
             "cpu_baseline": {"value": gcups, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{per_step} consecutive packed pairs per step, {steps} steps",
-                             "note": "scalar int32 Gotoh, two rolling rows, pthreads over pairs (no SIMD): a stated baseline, "
-                                     "an AVX-512 int16 inter-task CPU kernel would be ~10-20x faster per core"},
+                             "sample": f"{rows_per_step} rows against all later sequences per step, {steps} steps",
+                             "kernel": "oracle/gotoh_simd.c: inter-sequence SIMD, one subject per int16 lane x 32 (AVX-512BW / AVX2 by "
+                                       "target_clones), bit-identical to the scalar port",
+                             "scalar_port_gcups": scalar_gcups,
+                             "note": "the reference holds no Gotoh code and no clustalo binary exists in the image: this is the "
+                                     "oracle port's SIMD kernel on all host threads, the competent CPU path; the scalar int32 port "
+                                     "(round 1's CPU arm) is quoted beside it"},
             "e2e": {"value": gcups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "clustalo": shutil.which("clustalo") or "ClustalO not available in image"}
@@ -662,10 +697,14 @@ def main():
                 except Exception as e:
                     line["e2e_plugin"] = {"error": str(e)}
         if env.n_gpus == 1 and not args.no_cpu:
-            g, sample = cpu_oracle_gcups(ex["seqs"], ex["alphabet"], 10.0, env.threads)
-            line["cpu_baseline"] = {"value": g, "unit": UNIT, "cores": env.threads, "kind": "port", "sample": sample,
-                                    "note": "scalar int32 Gotoh (no SIMD): a stated baseline, not the target -- an AVX-512 int16 "
-                                            "inter-task CPU kernel would recover ~10-20x per core; kernel quality is the roofline fraction"}
+            g, sample = cpu_oracle_gcups(ex["seqs"], ex["alphabet"], 8.0, env.threads)
+            gs, ssample = cpu_simd_gcups(ex["seqs"], ex["alphabet"], 8.0, env.threads)
+            line["cpu_baseline"] = {"value": gs, "unit": UNIT, "cores": env.threads, "kind": "port", "sample": ssample,
+                                    "kernel": "oracle/gotoh_simd.c: inter-sequence SIMD, one subject per int16 lane x 32 (AVX-512BW / "
+                                              "AVX2 by target_clones); bit-identical to the scalar port (tests/test_oracle.py)",
+                                    "scalar_port": {"value": g, "unit": UNIT, "sample": sample,
+                                                    "kernel": "oracle/gotoh_oracle.c: scalar int32, two rolling rows"},
+                                    "note": "a reported baseline, not the target: kernel quality is the roofline fraction"}
             if ctx is not None and "gpu_ms" in line.get("guide_tree", {}):
                 from oracle import pyoracle as o
                 d = ctx.distances()

@@ -69,6 +69,16 @@ uint64_t tsq_oracle_pair_list(const uint8_t *seqs, const uint64_t *offs, const u
                               const uint32_t *pj, uint64_t npairs, int32_t *out, int nthreads);
 
 /*
+ * The CPU BASELINE kernel (gotoh_simd.c): the same recurrence with one subject per int16 SIMD lane, 32 subjects
+ * per query pass (AVX-512BW / AVX2 / SSE2 by target_clones).  All pairs (i, j) with row_begin <= i < row_end and
+ * i < j < n; out[packed(i, j) - packed(row_begin, row_begin + 1)].  Bit-identical to tsq_oracle_all_pairs
+ * (tests/test_oracle.py); pairs whose scores could leave int16 run through the scalar routine.  Returns DP cells.
+ */
+uint64_t tsq_oracle_rows_simd(const uint8_t *seqs, const uint64_t *offs, const uint32_t *lens, uint32_t n,
+                              const int8_t *mat, int nsym, int go, int ge, uint32_t row_begin, uint32_t row_end,
+                              int32_t *out, int nthreads);
+
+/*
  * Identity-aware score: the Gotoh score of tsq_oracle_gotoh() and, among all
  * alignments that reach it, the largest number of columns pairing identical symbols.  Restated as
  * one DP over 64-bit keys  score * 2^32 + identities  (every substitution score and gap penalty

@@ -351,6 +351,28 @@ def pair_list(encoded: list[np.ndarray], pi: np.ndarray, pj: np.ndarray, mat: np
     return out, int(cells)
 
 
+def rows_simd(encoded: list[np.ndarray], mat: np.ndarray, go: int, ge: int, nthreads: int = 1,
+              row_begin: int = 0, row_end: int | None = None):
+    """The SIMD CPU baseline kernel (gotoh_simd.c): all pairs (i, j), row_begin <= i < row_end, j > i.
+    Returns (int32 scores of packed indices [packed(row_begin, row_begin+1), packed(row_end, row_end+1)), cells)."""
+    n = len(encoded)
+    if row_end is None or row_end > n - 1:
+        row_end = max(n - 1, 0)
+    flat, offs, lens = _pack(encoded)
+    first = pair_index(row_begin, row_begin + 1, n) if row_begin + 1 < n else n * (n - 1) // 2
+    last = pair_index(row_end, row_end + 1, n) if row_end + 1 < n else n * (n - 1) // 2
+    out = np.zeros(max(last - first, 0), dtype=np.int32)
+    m8 = np.ascontiguousarray(mat, dtype=np.int8)
+    L = lib()
+    L.tsq_oracle_rows_simd.restype = C.c_uint64
+    L.tsq_oracle_rows_simd.argtypes = [C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_uint32,
+                                       C.POINTER(C.c_int8), C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32,
+                                       C.POINTER(C.c_int32), C.c_int]
+    cells = L.tsq_oracle_rows_simd(_p(flat, C.c_uint8), _p(offs, C.c_uint64), _p(lens, C.c_uint32), n, _p(m8, C.c_int8),
+                                   m8.shape[0], go, ge, row_begin, row_end, _p(out, C.c_int32), nthreads)
+    return out, int(cells)
+
+
 def distances(scores: np.ndarray, selfs: np.ndarray) -> np.ndarray:
     """Packed fp64 distances from packed int32 scores and per-sequence self scores."""
     n = len(selfs)

@@ -194,3 +194,32 @@ def test_distance_function():
     assert o.distance(-5, 10, 20) == 1.5
     assert o.distance(3, 0, 20) == 1.0 and o.distance(3, -4, 20) == 1.0
     assert o.distance(7, 30, 21) == 1.0 - 7.0 / 21.0
+
+
+def test_simd_cpu_baseline_kernel_is_bit_identical_to_the_scalar_oracle():
+    """oracle/gotoh_simd.c (bench.py's CPU arm: one subject per int16 lane) against tsq_oracle_all_pairs: ragged
+    lengths, empties, several gap models, both alphabets, a row sub-range, and sequences long enough that the int16
+    bound fails and the kernel must hand the pair to the scalar routine."""
+    rng = np.random.default_rng(77)
+    AA = "ARNDCQEGHILKMFPSTWYVBZX"
+    seqs = ["".join(rng.choice(list(AA), int(l))) for l in rng.integers(0, 130, 70)] + ["", "W", "acd-ef"]
+    enc = [o.encode(s) for s in seqs]
+    mat = o.matrix(0)
+    for go, ge in [(11, 1), (5, 2), (0, 0), (0, 3), (30, 0), (1, 7)]:
+        a, ca = o.all_pairs(enc, mat, go, ge, nthreads=2)
+        b, cb = o.rows_simd(enc, mat, go, ge, nthreads=3)
+        assert (a == b).all() and ca == cb, (go, ge)
+    n = len(enc)
+    a, _ = o.all_pairs(enc, mat, 11, 1, nthreads=2)
+    part, _ = o.rows_simd(enc, mat, 11, 1, nthreads=2, row_begin=9, row_end=41)
+    assert (part == a[o.pair_index(9, 10, n):o.pair_index(41, 42, n)]).all()
+    nt = ["".join(rng.choice(list("ACGTN"), int(l))) for l in rng.integers(1, 300, 40)]
+    encn = [o.encode(s, 1) for s in nt]
+    a, _ = o.all_pairs(encn, o.matrix(1), 10, 1, nthreads=2)
+    b, _ = o.rows_simd(encn, o.matrix(1), 10, 1, nthreads=2)
+    assert (a == b).all()
+    long_ = ["W" * 3100, "W" * 3100, "".join(rng.choice(list(AA[:20]), 3000)), "A" * 40]     # 11 * 3100 > int16
+    encl = [o.encode(s) for s in long_]
+    a, _ = o.all_pairs(encl, mat, 11, 1, nthreads=2)
+    b, _ = o.rows_simd(encl, mat, 11, 1, nthreads=2)
+    assert (a == b).all() and a[0] == 11 * 3100

@@ -232,6 +232,8 @@ struct tsq_ctx {
   int go = 11, ge = 1;
   int device = 0;
   int sm_count = 0;
+  size_t l2_persist_bytes = 0;   // persisting L2 carve-out of the device (0: unsupported / not set)
+  size_t l2_window_max = 0;      // largest access policy window the device takes
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;    // around the score kernels of tsq_compute
@@ -872,7 +874,20 @@ int enqueue_gotoh16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
     p.negge2 = ((uint32_t)(-(c->ge - c->delta)) & 0xffffu) * 0x10001u;
     p.goe2 = (uint32_t)(c->go + c->ge - c->delta) * 0x10001u;
     if (!fits16(c, lpad)) return fail(c, TSQ_ERR_RANGE, "internal: padded length %u outside the 16-bit bound", lpad);
-    TSQ_CUDA(c, tsq::g16_launch(c->K, grid, p, s));
+    // L2 policy of the scratch column: written by one strip, read back once by the next, then overwritten in
+    // place.  Its live set (warps x rows x 256 B: 140 MB at configs[1]) cycles through a 126 MB L2 under LRU, so
+    // without a policy most rows make a round trip through HBM (6.3 GB per launch, r01).  The share that fits the
+    // persisting carve-out is pinned for this launch; the rest streams.
+    cudaAccessPolicyWindow win{};
+    const size_t bnd_bytes = (size_t)grid * warps_per_cta * bnd_rows * 32 * sizeof(uint2);
+    if (c->l2_persist_bytes > 0 && !getenv("TSQ_NO_L2_POLICY")) {
+      win.base_ptr = c->d_bnd.p;
+      win.num_bytes = std::min(bnd_bytes, c->l2_window_max);
+      win.hitRatio = (float)std::min(1.0, 0.9 * (double)c->l2_persist_bytes / (double)std::max<size_t>(win.num_bytes, 1));
+      win.hitProp = cudaAccessPropertyPersisting;
+      win.missProp = cudaAccessPropertyStreaming;
+    }
+    TSQ_CUDA(c, tsq::g16_launch(c->K, grid, p, s, win.num_bytes ? &win : nullptr));
     launches++;
   }
   return TSQ_OK;
@@ -1495,6 +1510,17 @@ int tsq_create(tsq_ctx** out, const tsq_params* params) {
     cudaGetLastError();
     tsq_destroy(c);
     return TSQ_ERR_CUDA;
+  }
+  {   // persisting L2 carve-out for the strip-boundary scratch of the packed kernel (see enqueue_gotoh16)
+    int max_persist = 0, max_window = 0;
+    if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device) == cudaSuccess && max_persist > 0 &&
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device) == cudaSuccess && max_window > 0 &&
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess) {
+      c->l2_persist_bytes = (size_t)max_persist;
+      c->l2_window_max = (size_t)max_window;
+    } else {
+      cudaGetLastError();
+    }
   }
   c->h_one[0] = 1;
   c->h_one[1] = 0;

@@ -40,9 +40,25 @@ bool g16_variant(int K, uint32_t nsym, G16Launch* out) {
   return false;
 }
 
-cudaError_t g16_launch(int K, int grid, const G16Params& p, cudaStream_t stream) {
+cudaError_t g16_launch(int K, int grid, const G16Params& p, cudaStream_t stream, const cudaAccessPolicyWindow* scratch_window) {
   G16Launch v;
   if (!g16_variant(K, p.nsym, &v)) return cudaErrorInvalidValue;
+  // the strip-boundary scratch column gets an L2 access policy for THIS launch only: the share of it that fits the
+  // persisting carve-out stays resident between the strip that writes a row and the strip that reads it back, the
+  // rest streams (evict-first) instead of thrashing the whole cache (tsq_api.cpp: enqueue_gotoh16)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)v.tpb);
+  cfg.dynamicSmemBytes = v.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = 0;
+  if (scratch_window && scratch_window->num_bytes > 0) {
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow = *scratch_window;
+    cfg.numAttrs = 1;
+  }
 #define X(KK, TT, MM)                                                                          \
   if (K == KK) {                                                                               \
     /* -ge' == +1 in both halves (ge = 1, delta = 2: the protein and nucleotide defaults) gets */ \
@@ -52,8 +68,7 @@ cudaError_t g16_launch(int K, int grid, const G16Params& p, cudaStream_t stream)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                          (int)v.smem);                                         \
     if (e != cudaSuccess) return e;                                                            \
-    kern<<<grid, TT, v.smem, stream>>>(p);                                                     \
-    return cudaGetLastError();                                                                 \
+    return cudaLaunchKernelEx(&cfg, kern, p);                                                  \
   }
   TSQ_G16_VARIANTS(X)
 #undef X

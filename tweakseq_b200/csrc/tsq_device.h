@@ -27,8 +27,9 @@ struct G16Launch {
 
 // Static description of the variant with strip width K (nullptr-safe: returns false).
 bool g16_variant(int K, uint32_t nsym, G16Launch* out);
-// Launch the packed 16-bit kernel: grid CTAs of the variant's size on `stream`.
-cudaError_t g16_launch(int K, int grid, const G16Params& p, cudaStream_t stream);
+// Launch the packed 16-bit kernel: grid CTAs of the variant's size on `stream`; scratch_window (may be null): L2
+// access policy of the strip-boundary scratch for this launch.
+cudaError_t g16_launch(int K, int grid, const G16Params& p, cudaStream_t stream, const cudaAccessPolicyWindow* scratch_window);
 
 // 32-bit inter-task kernel (gotoh32.cuh): same strip widths / launch shapes as the packed one.
 cudaError_t g32_launch(int K, int grid, const G32Params& p, cudaStream_t stream);
