@@ -33,6 +33,7 @@ struct Options {
   int gap_open = -1, gap_extend = -1, device = 0;
   int devices = 1;   // --devices N | all: B200s of the box this job is spread over (tsq_params.n_devices)
   bool identity = false;
+  bool kimura = false;        // --kimura: Kimura-corrected identity distances (implies --identity-distance)
   bool input_order = false;   // clustalo --output-order=input-order (default: tree order, what tweakseq asks for)
 };
 
@@ -42,7 +43,7 @@ void usage(FILE* f) {
         "       tsq-aligner [--auto --thread N] IN.fa    (mafft style: alignment on stdout)\n"
         "       tsq-aligner --version | -version\n"
         "options: --seqtype=Protein|DNA|RNA, --amino, --nuc (default: detected), --gap-open N, --gap-extend N,\n"
-        "         --device N, --devices N|all (several B200s; env TSQ_DEVICES), --identity-distance, --distmat-out (keep OUT.fa.distmat), --matrix-only (OUT = matrix),\n"
+        "         --device N, --devices N|all (several B200s; env TSQ_DEVICES), --identity-distance, --kimura (corrected identity distance; fails above D = 0.75), --distmat-out (keep OUT.fa.distmat), --matrix-only (OUT = matrix),\n"
         "         --dry-run (print the parsed job and exit); clustalo's --force -v --outfmt=fa --output-order=... are accepted\n",
         f);
 }
@@ -99,6 +100,7 @@ int parse(int argc, char** argv, Options& o, std::string& err) {
     else if (is_opt(a, "--devices")) { if (!value(v)) return 2; o.devices = v == "all" ? -1 : atoi(v.c_str()); }
     else if (is_opt(a, "--thread") || is_opt(a, "--threads")) { if (!value(v)) return 2; }       // mafft: host threads mean nothing here
     else if (a == "--identity-distance") o.identity = true;
+    else if (a == "--kimura") o.identity = o.kimura = true;
     else if (a == "--distmat-out") o.keep_distmat = true;
     else if (a == "--matrix-only") o.matrix_only = true;
     else if (a == "--dry-run") o.dry_run = true;
@@ -194,6 +196,7 @@ int main(int argc, char** argv) {
   if (!o.matrix_only) p.flags |= TSQ_FLAG_MSA_OUT;
   if (o.keep_distmat) p.flags |= TSQ_FLAG_KEEP_DISTMAT;
   if (o.identity) p.flags |= TSQ_FLAG_IDENTITY;
+  if (o.kimura) p.flags |= TSQ_FLAG_KIMURA;
   if (o.input_order) p.flags |= TSQ_FLAG_INPUT_ORDER;
   bool to_stderr = o.to_stdout;
   const int rc = tsq_run_fasta(o.in.c_str(), out.c_str(), &p, log_line, &to_stderr, nullptr);

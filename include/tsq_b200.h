@@ -78,6 +78,13 @@ extern "C" {
 #define TSQ_FLAG_KEEP_TREE 128u    /* with TSQ_FLAG_MSA_OUT: also write the guide tree, to <fout>.dnd (without MSA_OUT the
                                      tree always accompanies the matrix: the two files clustalo takes) */
 
+#define TSQ_FLAG_KIMURA 256u       /* with TSQ_FLAG_IDENTITY: the distance is Kimura-corrected, -ln(1 - D - D^2/5) with
+                                     D = 1 - identities/min(len) (ClustalW's correction for multiple substitutions).  The
+                                     formula holds for D < 0.75; beyond it ClustalW reads a table the reference does not
+                                     hold, so a job with such a pair fails with TSQ_ERR_RANGE instead of guessing.  The
+                                     logarithm is evaluated by a fixed sequence of IEEE double operations (bit-identical
+                                     on CPU oracle and GPU; within 2 ulp of ln). */
+
 typedef struct tsq_ctx tsq_ctx;
 
 typedef struct tsq_params {

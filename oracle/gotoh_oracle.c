@@ -150,6 +150,61 @@ double tsq_oracle_distance(int32_t s_ij, int32_t s_ii, int32_t s_jj) {
   return 1.0 - q;
 }
 
+/* ---- Kimura-corrected identity distance (SURVEY.md 8f-2 "+ Kimura") ----
+ * ClustalW corrects the observed protein distance D = 1 - identities / min(len) for multiple substitutions with
+ * Kimura's formula  d = -ln(1 - D - D^2 / 5),  valid for D < 0.75 (above it ClustalW switches to a lookup table that
+ * the reference does not hold: those pairs are an error, never a guess).  Bit-equality between CPU and GPU cannot
+ * rest on two libm's, so the logarithm is part of the spec: ln x = e ln 2 + 2 z (1 + w/3 + w^2/5 + ... + w^11/23)
+ * with x = m 2^e, m in [sqrt(1/2), sqrt(2)), z = (m - 1)/(m + 1), w = z z, evaluated by Horner's rule in IEEE double
+ * operations in exactly this order, no fused multiply-add (this file is built with -ffp-contract=off; the kernel
+ * uses the _rn intrinsics).  Within 2 ulp of the true logarithm on the range used (tests/test_identity.py). */
+double tsq_oracle_ln(double x) {
+  union { double d; uint64_t u; } v;
+  v.d = x;
+  int e = (int)((v.u >> 52) & 0x7ff) - 1022;                 /* x = m 2^e, m in [1/2, 1) */
+  v.u = (v.u & 0x000fffffffffffffull) | 0x3fe0000000000000ull;
+  double m = v.d;
+  if (m < 0.70710678118654752440) {
+    m = m * 2.0;
+    e -= 1;
+  }
+  const double z = (m - 1.0) / (m + 1.0);
+  const double w = z * z;
+  double p = 1.0 / 23.0;
+  p = p * w + 1.0 / 21.0;
+  p = p * w + 1.0 / 19.0;
+  p = p * w + 1.0 / 17.0;
+  p = p * w + 1.0 / 15.0;
+  p = p * w + 1.0 / 13.0;
+  p = p * w + 1.0 / 11.0;
+  p = p * w + 1.0 / 9.0;
+  p = p * w + 1.0 / 7.0;
+  p = p * w + 1.0 / 5.0;
+  p = p * w + 1.0 / 3.0;
+  p = p * w + 1.0;
+  const double lnm = (2.0 * z) * p;
+  return (double)e * 0.693147180559945309417 + lnm;
+}
+
+/* identities, shorter length -> (corrected distance, ok).  ok = 0: D >= 0.75, the formula does not apply. */
+double tsq_oracle_kimura(int32_t identities, int32_t min_len, int *ok) {
+  if (ok) *ok = 1;
+  if (min_len <= 0) {           /* no residues to compare: the uncorrected convention, D = 1 */
+    if (ok) *ok = 0;
+    return 1.0;
+  }
+  const double D = 1.0 - (double)identities / (double)min_len;
+  if (!(D < 0.75)) {
+    if (ok) *ok = 0;
+    return D;
+  }
+  const double t = D * D;
+  const double u = t / 5.0;
+  const double a = 1.0 - D;
+  const double arg = a - u;
+  return 0.0 - tsq_oracle_ln(arg);
+}
+
 uint64_t tsq_oracle_pair_index(uint64_t i, uint64_t j, uint64_t n) {
   return i * n - i * (i + 1) / 2 + (j - i - 1);
 }

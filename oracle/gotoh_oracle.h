@@ -50,6 +50,12 @@ int32_t tsq_oracle_self_score(const uint8_t *a, int m, const int8_t *mat, int ns
 /* d = 1 - s_ij / min(s_ii, s_jj); 1.0 if that minimum is <= 0. */
 double tsq_oracle_distance(int32_t s_ij, int32_t s_ii, int32_t s_jj);
 
+/* Kimura-corrected identity distance -ln(1 - D - D^2/5), D = 1 - identities/min_len, for D < 0.75 (*ok = 0 and the
+ * uncorrected D above: ClustalW's table for that range is not restated).  tsq_oracle_ln is the logarithm the spec
+ * fixes operation by operation, so that CPU and GPU agree bit for bit. */
+double tsq_oracle_ln(double x);
+double tsq_oracle_kimura(int32_t identities, int32_t min_len, int *ok);
+
 /* Packed upper-triangle index of (i,j), i<j, over n sequences. */
 uint64_t tsq_oracle_pair_index(uint64_t i, uint64_t j, uint64_t n);
 

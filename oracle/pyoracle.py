@@ -442,6 +442,24 @@ def traceback(a: np.ndarray, b: np.ndarray, mat: np.ndarray, go: int, ge: int, a
     return dec(oa), dec(ob), sc.value
 
 
+def ln(x: float) -> float:
+    """The spec's own logarithm (tsq_oracle_ln): fixed sequence of IEEE double operations."""
+    L = lib()
+    L.tsq_oracle_ln.restype = C.c_double
+    L.tsq_oracle_ln.argtypes = [C.c_double]
+    return L.tsq_oracle_ln(x)
+
+
+def kimura(identities: int, min_len: int):
+    """(Kimura-corrected identity distance, ok); ok False: D >= 0.75, the formula does not apply."""
+    L = lib()
+    L.tsq_oracle_kimura.restype = C.c_double
+    L.tsq_oracle_kimura.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int)]
+    ok = C.c_int()
+    d = L.tsq_oracle_kimura(identities, min_len, C.byref(ok))
+    return d, bool(ok.value)
+
+
 def all_pairs_id(encoded, mat, go, ge):
     """Packed (scores, identities, clustalw distances) by the identity-aware oracle (single thread)."""
     n = len(encoded)

@@ -122,3 +122,73 @@ def test_every_strip_width_of_the_32_bit_inter_task_kernel(K, monkeypatch):
     assert st["strip_width"] == K and st["cells_s16"] == 0
     rs, rk, _ = o.all_pairs_id([o.encode(x) for x in seqs], MAT, 11, 1)
     assert (s == rs).all() and (k == rk).all()
+
+
+# ---- Kimura-corrected identity distance (SURVEY 8f-2 "+ Kimura") ---------------------------------------------------
+def test_the_specs_logarithm_is_a_logarithm():
+    """tsq_oracle_ln: the fixed sequence of IEEE operations both sides evaluate; within 2 ulp of libm on the range the
+    correction uses (arguments 0.1375 .. 1) and beyond."""
+    import math
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([np.linspace(0.1375, 1.0, 5001), rng.uniform(1e-3, 1.0, 5000), rng.uniform(1.0, 1e6, 2000)])
+    for x in xs:
+        a, b = o.ln(float(x)), math.log(float(x))
+        assert abs(a - b) <= 2 * np.spacing(abs(b)) + 1e-300, x
+    assert o.ln(1.0) == 0.0
+    d, ok = o.kimura(100, 100)
+    assert ok and d == 0.0
+    d, ok = o.kimura(60, 100)                          # D = 0.4: -ln(1 - 0.4 - 0.032)
+    assert ok and abs(d - (-math.log(1 - 0.4 - 0.4 * 0.4 / 5))) < 1e-15
+    assert o.kimura(25, 100) == (0.75, False) and o.kimura(26, 100)[1] and not o.kimura(0, 0)[1]
+
+
+@pytest.mark.gpu
+def test_gpu_kimura_distances_equal_the_oracles_bit_for_bit():
+    import tweakseq_b200 as t
+    from tweakseq_b200 import synth
+    fam = [s for s in synth.protein(60, (150, 260, 200, 25), 11, family=True)]
+    enc = [o.encode(s) for s in fam]
+    mat = o.matrix(0)
+    # a family mutated at 10-60 %: keep the members whose every pair stays below D = 0.75
+    with t.Context(flags=t.FLAG_IDENTITY) as ctx:
+        ctx.set_sequences(fam)
+        ctx.run()
+        nid, d0 = ctx.identities(), ctx.distances()
+    n = len(fam)
+    keep = [i for i in range(n) if all(d0[t.pair_index(min(i, j), max(i, j), n)] < 0.7 for j in range(n) if j != i)][:24]
+    if len(keep) < 8:                                  # fall back to close copies of one member
+        keep = list(range(8))
+        fam = [fam[0][:k] + fam[0][k + 1:] for k in range(3, 83, 10)]
+    else:
+        fam = [fam[i] for i in keep]
+    with t.Context(flags=t.FLAG_IDENTITY | t.FLAG_KIMURA) as ctx:
+        ctx.set_sequences(fam)
+        ctx.run()
+        s, nid, d = ctx.scores(), ctx.identities(), ctx.distances()
+    m = len(fam)
+    want = []
+    for i in range(m):
+        for j in range(i + 1, m):
+            k = nid[t.pair_index(i, j, m)]
+            dd, ok = o.kimura(int(k), min(len(fam[i]), len(fam[j])))
+            assert ok
+            want.append(dd)
+    assert d.tobytes() == np.array(want, dtype=np.float64).tobytes()
+    assert (d >= 0).all() and d.max() > 0.05
+
+
+@pytest.mark.gpu
+def test_gpu_kimura_beyond_its_range_is_an_error_not_a_guess():
+    import tweakseq_b200 as t
+    from tweakseq_b200 import synth
+    seqs = synth.protein(12, 120, 12)                   # unrelated: D ~ 0.9
+    with t.Context(flags=t.FLAG_IDENTITY | t.FLAG_KIMURA) as ctx:
+        ctx.set_sequences(seqs)
+        with pytest.raises(t.TsqError) as e:
+            ctx.run()
+        assert e.value.status == -9 and "0.75" in str(e.value)
+        with pytest.raises(t.TsqError):
+            ctx.distances()
+    with pytest.raises(t.TsqError) as e:
+        t.Context(flags=t.FLAG_KIMURA)                  # corrects the identity distance: needs TSQ_FLAG_IDENTITY
+    assert e.value.status == -1

@@ -6,7 +6,7 @@ from tweakseq_b200 import synth
 which = sys.argv[1] if len(sys.argv) > 1 else "c2"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 alpha, seqs = {"c2": lambda: synth.config(2), "c3s": lambda: synth.config(3, 0.3), "c1": lambda: synth.config(1),
-               "c4s": lambda: synth.config(4, 0.06), "c4m": lambda: synth.config(4, 0.24), "c5s": lambda: synth.config(5, 0.1)}[which]()
+               "c4s": lambda: synth.config(4, 0.06), "c4m": lambda: synth.config(4, 0.24), "c4": lambda: synth.config(4), "c3": lambda: synth.config(3), "c5s": lambda: synth.config(5, 0.2), "c5t": lambda: synth.config(5, 0.1)}[which]()
 flags = int(os.environ.get("TSQ_FLAGS", "0"))
 with t.Context(alphabet=alpha, flags=flags | t.FLAG_NO_DISTANCES) as ctx:
     ctx.set_sequences(seqs); ctx.upload()

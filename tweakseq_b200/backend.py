@@ -65,6 +65,7 @@ class B200Gotoh(AlignmentTool):
         self.device = 0
         self.devices = 1           # B200s of the box one job uses (tsq_params.n_devices; -1 = all of them)
         self.identity = False      # ClustalW-style identity distance instead of the score distance
+        self.kimura = False        # ... Kimura-corrected, -ln(1 - D - D^2/5); a pair with D >= 0.75 is an error (implies identity)
         self.align = True          # run(): fout = the multiple alignment readNewAlignment ingests; False: the distance matrix
         self.keep_distmat = False  # with align: also write <fout>.distmat
         self.keep_tree = False     # with align: also write <fout>.dnd (without align the tree always accompanies the matrix)
@@ -130,7 +131,7 @@ class B200Gotoh(AlignmentTool):
 
         Returns the exit status startAlignment()/alignmentFinished() would see (0 = success:
         SeqEditMainWin.cpp:836-861)."""
-        flags = ((capi.FLAG_IDENTITY if self.identity else 0) | (capi.FLAG_MSA_OUT if self.align else 0) |
+        flags = ((capi.FLAG_IDENTITY if (self.identity or self.kimura) else 0) | (capi.FLAG_KIMURA if self.kimura else 0) | (capi.FLAG_MSA_OUT if self.align else 0) |
                  (capi.FLAG_KEEP_DISTMAT if self.keep_distmat else 0) | (capi.FLAG_KEEP_TREE if self.keep_tree else 0))
         return capi.run_fasta(fin, fout, log=log, cancel=cancel, alphabet=self.alphabet,
                               gap_open=self.gap_open, gap_extend=self.gap_extend, device=self.device, flags=flags,
@@ -151,8 +152,10 @@ class B200Gotoh(AlignmentTool):
         """Scores and distances for in-memory residues (what Sequence::filter(true) returns).
 
         Returns (scores int32 packed, distances float64 packed)."""
-        if self.identity:
+        if self.identity or self.kimura:
             flags |= capi.FLAG_IDENTITY
+        if self.kimura:
+            flags |= capi.FLAG_KIMURA
         with capi.Context(alphabet=self.alphabet, gap_open=self.gap_open, gap_extend=self.gap_extend,
                           device=self.device, n_devices=self.devices, flags=flags) as ctx:
             ctx.set_sequences(residues)

@@ -13,6 +13,7 @@ import numpy as np
 PROTEIN, NUCLEOTIDE = 0, 1
 FLAG_FORCE_S32, FLAG_NO_DISTANCES, FLAG_NO_WAVE16, FLAG_IDENTITY, FLAG_MSA_OUT, FLAG_KEEP_DISTMAT, FLAG_INPUT_ORDER = 1, 2, 4, 8, 16, 32, 64
 FLAG_KEEP_TREE = 128
+FLAG_KIMURA = 256
 ALPHABET_AUTO = -1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

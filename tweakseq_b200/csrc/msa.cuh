@@ -106,6 +106,16 @@ template <> struct MsaNeg<int32_t> { static constexpr int32_t v = -(1 << 30); };
 // bytes of the 7 rolling diagonals (3 H, 2 E, 2 F) of a merge with Lx columns along i
 TSQ_HD size_t msa_diag_bytes(uint32_t Lx, bool narrow) { return 7 * ((size_t)Lx + 1) * (narrow ? sizeof(int32_t) : sizeof(long long)); }
 
+// bytes of the three column-score tables of a merge (msa_prep_phase): letter scores of the big side, letter lists
+// and list lengths of the small side.  When they fit shared memory next to the rolling diagonals the sweep reads
+// them from there: the dependent chain list length -> letter -> letter score is then three shared-memory loads per
+// diagonal instead of three L2 round trips (which were most of the ~1 000 clocks a diagonal took in r01).
+TSQ_HD size_t msa_round16(size_t x) { return (x + 15) & ~(size_t)15; }
+TSQ_HD size_t msa_table_bytes(uint32_t Lx, uint32_t Ly, uint32_t nsym) {
+  const size_t mx = Lx > Ly ? Lx : Ly;   // either side may be the big one: size for the longer
+  return msa_round16((size_t)nsym * mx * 4) + msa_round16((size_t)nsym * mx * 4) + msa_round16(mx * 4);
+}
+
 // Whether the whole DP of a merge stays inside +-2^29, so that the sweep may run in int32 with -2^30 as
 // minus infinity: |H|, |E|, |F| <= |X||Y| (max|S| (Lx + Ly) + 2 go + (Lx + Ly + 2) ge).
 TSQ_HD bool msa_fits_narrow(uint32_t nx, uint32_t ny, uint32_t Lx, uint32_t Ly, int32_t max_abs_s, int32_t go, int32_t ge) {
@@ -175,8 +185,14 @@ struct MsaSweep {
   T* diag;               // 3 H, 2 E, 2 F diagonals
 };
 
+struct MsaTables {       // where the sweep reads the column-score tables from (the task's scratch, or shared memory)
+  const int32_t* pbig;
+  const uint32_t* lst;
+  const uint32_t* lnz;
+};
+
 template <typename T>
-TSQ_HD MsaSweep<T> msa_sweep_init(const MsaTask& t, const MsaConst& k, void* diag) {
+TSQ_HD MsaSweep<T> msa_sweep_init(const MsaTask& t, const MsaConst& k, void* diag, const MsaTables* tab = nullptr) {
   MsaSweep<T> s;
   const long long w = (long long)t.nx * (long long)t.ny;
   s.GO = (T)(w * k.go); s.GE = (T)(w * k.ge); s.GOE = (T)(w * k.go + w * k.ge);
@@ -185,7 +201,10 @@ TSQ_HD MsaSweep<T> msa_sweep_init(const MsaTask& t, const MsaConst& k, void* dia
   s.ld = (t.Lx < t.Ly ? t.Lx : t.Ly) + 1;
   s.bx = msa_big_is_x(t);
   s.Lb = s.bx ? t.Lx : t.Ly; s.Ls = s.bx ? t.Ly : t.Lx;
-  s.lnz = t.lnz; s.lst = t.lst; s.pbig = t.pbig; s.dir = t.dir;
+  s.lnz = tab ? tab->lnz : t.lnz;
+  s.lst = tab ? tab->lst : t.lst;
+  s.pbig = tab ? tab->pbig : t.pbig;
+  s.dir = t.dir;
   s.diag = (T*)diag;
   return s;
 }
@@ -349,8 +368,8 @@ __global__ void __launch_bounds__(128) msa_leaf_kernel(const MsaLeaf* leaves, ui
 // and once with the global scratch, so that each copy of the loop knows its address space (LDS/STS with
 // 32-bit offsets instead of generic 64-bit addressing).
 template <typename T>
-__device__ __forceinline__ long long msa_sweep_cta(const MsaTask& t, const MsaConst& k, T* diag, int tid, int nt) {
-  const MsaSweep<T> sw = msa_sweep_init<T>(t, k, diag);
+__device__ __forceinline__ long long msa_sweep_cta(const MsaTask& t, const MsaConst& k, T* diag, const MsaTables* tab, int tid, int nt) {
+  const MsaSweep<T> sw = msa_sweep_init<T>(t, k, diag, tab);
   const int last = sw.m + sw.n;
   int hc = 0;
   for (int d = 0; d <= last; ++d) {
@@ -361,16 +380,39 @@ __device__ __forceinline__ long long msa_sweep_cta(const MsaTask& t, const MsaCo
   return msa_final_score<T>(sw);
 }
 
-// One merge by one CTA, in score type T.  smem_bytes: dynamic shared memory of the launch; a merge whose 7
-// rolling diagonals fit uses it, any other its global scratch.
+// One merge by one CTA, in score type T.  smem_bytes: dynamic shared memory of the launch.  A merge whose 7 rolling
+// diagonals fit uses it for them (its global scratch otherwise), and one whose column-score tables fit behind the
+// diagonals copies them there after the prep phase.
 template <typename T>
 __device__ __forceinline__ void msa_merge_cta(const MsaTask& t, const MsaConst& k, uint32_t smem_bytes, T* smem) {
   const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
   msa_prep_phase(t, k, tid, nt);
   __syncthreads();
   long long score;
-  if (msa_diag_bytes(t.Lx, sizeof(T) == 4) <= (size_t)smem_bytes) score = msa_sweep_cta<T>(t, k, smem, tid, nt);
-  else score = msa_sweep_cta<T>(t, k, reinterpret_cast<T*>(t.diag), tid, nt);
+  const size_t db = msa_round16(msa_diag_bytes(t.Lx, sizeof(T) == 4));
+  if (db <= (size_t)smem_bytes) {
+    const uint32_t Lb = msa_big_is_x(t) ? t.Lx : t.Ly, Ls = msa_big_is_x(t) ? t.Ly : t.Lx;
+    const size_t pb = msa_round16((size_t)k.nsym * Lb * 4), lb = msa_round16((size_t)k.nsym * Ls * 4), nb = msa_round16((size_t)Ls * 4);
+    if (db + pb + lb + nb <= (size_t)smem_bytes) {
+      char* base = reinterpret_cast<char*>(smem) + db;
+      int32_t* s_pbig = reinterpret_cast<int32_t*>(base);
+      uint32_t* s_lst = reinterpret_cast<uint32_t*>(base + pb);
+      uint32_t* s_lnz = reinterpret_cast<uint32_t*>(base + pb + lb);
+      for (uint32_t q = (uint32_t)tid; q < k.nsym * Lb; q += (uint32_t)nt) s_pbig[q] = t.pbig[q];
+      for (uint32_t q = (uint32_t)tid; q < Ls; q += (uint32_t)nt) {
+        const uint32_t nz = t.lnz[q];
+        s_lnz[q] = nz;
+        for (uint32_t r = 0; r < nz; ++r) s_lst[(size_t)r * Ls + q] = t.lst[(size_t)r * Ls + q];   // only the entries in use
+      }
+      __syncthreads();
+      const MsaTables tab{s_pbig, s_lst, s_lnz};
+      score = msa_sweep_cta<T>(t, k, smem, &tab, tid, nt);
+    } else {
+      score = msa_sweep_cta<T>(t, k, smem, nullptr, tid, nt);
+    }
+  } else {
+    score = msa_sweep_cta<T>(t, k, reinterpret_cast<T*>(t.diag), nullptr, tid, nt);
+  }
   if (tid == 0) msa_walk_phase(t, score);
   __syncthreads();
   msa_build_phase(t, k, tid, nt);

@@ -165,8 +165,12 @@ inline int msa_progressive(MsaDevice& dev, const MsaJob& job, MsaOut& out) {
         if (e > b && bytes + need > job.scratch_budget) break;
         bytes += need;
         longest = std::max(longest, std::min(Lx, Ly) + 1);
-        const size_t db = msa_diag_bytes(Lx, narrow_of(t));
-        if (db <= kMsaSmemLimit) smem = std::max(smem, db);
+        // shared memory of the launch: the rolling diagonals of every merge that fits, and behind them the
+        // column-score tables where those fit too (msa.cuh: msa_merge_cta decides per merge with the same sizes)
+        const size_t db = msa_round16(msa_diag_bytes(Lx, narrow_of(t)));
+        const size_t tb = msa_table_bytes(Lx, Ly, nsym);
+        if (db + tb <= kMsaSmemLimit) smem = std::max(smem, db + tb);
+        else if (db <= kMsaSmemLimit) smem = std::max(smem, db);
         e++;
       }
       const size_t count = e - b;

@@ -1166,6 +1166,9 @@ int launch_finalize(tsq_ctx* c, uint32_t row_begin, uint32_t row_end, int32_t* o
   f.go = c->go;
   f.ge = c->ge;
   f.perm_identity = c->perm_identity ? 1u : 0u;
+  f.kimura = (c->prm.flags & TSQ_FLAG_KIMURA) ? 1u : 0u;
+  f.kimura_oob = c->d_cancel + 2;
+  if (f.kimura) TSQ_CUDA(c, cudaMemsetAsync(c->d_cancel + 2, 0, sizeof(int), c->stream));
   TSQ_CUDA(c, tsq::finalize_launch(f, c->stream));
   c->st.launches++;
   return TSQ_OK;
@@ -1175,12 +1178,17 @@ int launch_finalize(tsq_ctx* c, uint32_t row_begin, uint32_t row_end, int32_t* o
 // synchronize so that a protocol failure is an error code, never a silently wrong score.
 int check_device_fault(tsq_ctx* c) {
   if (!c->d_cancel || !c->h_fault) return TSQ_OK;
-  *c->h_fault = 0;
-  TSQ_CUDA(c, cudaMemcpyAsync(c->h_fault, c->d_cancel + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  c->h_fault[0] = c->h_fault[1] = 0;
+  TSQ_CUDA(c, cudaMemcpyAsync(c->h_fault, c->d_cancel + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   TSQ_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (*c->h_fault != 0) {
+  if (c->h_fault[0] != 0) {
     c->computed = c->finalized = c->downloaded = false;
-    return fail(c, TSQ_ERR_CUDA, "device fault 0x%x: a wavefront kernel timed out on a TMA tile barrier; results discarded", *c->h_fault);
+    return fail(c, TSQ_ERR_CUDA, "device fault 0x%x: a wavefront kernel timed out on a TMA tile barrier; results discarded", c->h_fault[0]);
+  }
+  if ((c->prm.flags & TSQ_FLAG_KIMURA) && c->finalized && c->h_fault[1] != 0) {
+    c->finalized = c->downloaded = false;
+    return fail(c, TSQ_ERR_RANGE, "%d pair(s) have an identity distance of 0.75 or more: Kimura's correction -ln(1 - D - D^2/5) does not "
+                "apply there (ClustalW switches to a lookup table that cannot be restated); run without TSQ_FLAG_KIMURA", c->h_fault[1]);
   }
   return TSQ_OK;
 }
@@ -1402,6 +1410,7 @@ int tsq_create(tsq_ctx** out, const tsq_params* params) {
     p.struct_size = (uint32_t)sizeof(tsq_params);
   }
   if (p.alphabet != TSQ_PROTEIN && p.alphabet != TSQ_NUCLEOTIDE) return TSQ_ERR_INVALID;
+  if ((p.flags & TSQ_FLAG_KIMURA) && !(p.flags & TSQ_FLAG_IDENTITY)) return TSQ_ERR_INVALID;   // corrects the identity distance
   if (p.part_world < 1) p.part_world = 1;
   if (p.part_rank < 0 || p.part_rank >= p.part_world) return TSQ_ERR_INVALID;
   const int nsym = p.alphabet == TSQ_NUCLEOTIDE ? 5 : 23;
@@ -1503,9 +1512,9 @@ int tsq_create(tsq_ctx** out, const tsq_params* params) {
     tsq_destroy(c);
     return TSQ_ERR_CUDA;
   }
-  if (BlockCache::get().take(c->device, 2 * sizeof(int), (void**)&c->d_cancel) != cudaSuccess ||
-      cudaMemset(c->d_cancel, 0, 2 * sizeof(int)) != cudaSuccess ||
-      BlockCache::get().take(-1, 2 * sizeof(int), (void**)&c->h_one) != cudaSuccess ||
+  if (BlockCache::get().take(c->device, 4 * sizeof(int), (void**)&c->d_cancel) != cudaSuccess ||
+      cudaMemset(c->d_cancel, 0, 4 * sizeof(int)) != cudaSuccess ||
+      BlockCache::get().take(-1, 4 * sizeof(int), (void**)&c->h_one) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->cancel_stream, cudaStreamNonBlocking) != cudaSuccess) {
     cudaGetLastError();
     tsq_destroy(c);
@@ -1523,7 +1532,7 @@ int tsq_create(tsq_ctx** out, const tsq_params* params) {
     }
   }
   c->h_one[0] = 1;
-  c->h_one[1] = 0;
+  c->h_one[1] = c->h_one[2] = c->h_one[3] = 0;
   c->h_fault = c->h_one + 1;
   c->stream = c->own_stream;
   *out = c;
@@ -1629,7 +1638,7 @@ int tsq_compute(tsq_ctx* c) {
   TSQ_CUDA(c, cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   uint32_t launches = 0;
-  TSQ_CUDA(c, cudaMemsetAsync(c->d_cancel, 0, 2 * sizeof(int), s));   // cancel flag and fault word
+  TSQ_CUDA(c, cudaMemsetAsync(c->d_cancel, 0, 4 * sizeof(int), s));   // cancel flag, fault word, Kimura out-of-range count
   TSQ_CUDA(c, cudaEventRecord(c->ev0, s));
   int rc = enqueue_gotoh16(c, s, launches);                 // regime 1: packed inter-task kernel
   if (rc == TSQ_OK) rc = enqueue_wave16(c, s, launches);    // regime 2: packed wavefront kernel

@@ -381,6 +381,34 @@ cudaError_t msa_rows_launch(const MsaRows& p, cudaStream_t stream) {
 // ---- finalize: empties, un-sort, fp64 distances -----------------------------------------
 // One CTA per sorted row i; threads stride over j > i.  Distances follow the oracle's
 // tsq_oracle_distance(): two separately rounded IEEE operations (div, sub), no contraction.
+// The logarithm of the Kimura correction is part of the spec (oracle/gotoh_oracle.c: tsq_oracle_ln): the same
+// sequence of separately rounded IEEE double operations, so that the distances equal the oracle's bit for bit.
+__device__ __forceinline__ double ln_spec(double x) {
+  long long bits = __double_as_longlong(x);
+  int e = (int)((bits >> 52) & 0x7ff) - 1022;                 // x = m 2^e, m in [1/2, 1)
+  double m = __longlong_as_double((bits & 0x000fffffffffffffll) | 0x3fe0000000000000ll);
+  if (m < 0.70710678118654752440) {
+    m = __dmul_rn(m, 2.0);
+    e -= 1;
+  }
+  const double z = __ddiv_rn(__dsub_rn(m, 1.0), __dadd_rn(m, 1.0));
+  const double w = __dmul_rn(z, z);
+  double p = 1.0 / 23.0;
+  p = __dadd_rn(__dmul_rn(p, w), 1.0 / 21.0);
+  p = __dadd_rn(__dmul_rn(p, w), 1.0 / 19.0);
+  p = __dadd_rn(__dmul_rn(p, w), 1.0 / 17.0);
+  p = __dadd_rn(__dmul_rn(p, w), 1.0 / 15.0);
+  p = __dadd_rn(__dmul_rn(p, w), 1.0 / 13.0);
+  p = __dadd_rn(__dmul_rn(p, w), 1.0 / 11.0);
+  p = __dadd_rn(__dmul_rn(p, w), 1.0 / 9.0);
+  p = __dadd_rn(__dmul_rn(p, w), 1.0 / 7.0);
+  p = __dadd_rn(__dmul_rn(p, w), 1.0 / 5.0);
+  p = __dadd_rn(__dmul_rn(p, w), 1.0 / 3.0);
+  p = __dadd_rn(__dmul_rn(p, w), 1.0);
+  const double lnm = __dmul_rn(__dmul_rn(2.0, z), p);
+  return __dadd_rn(__dmul_rn((double)e, 0.693147180559945309417), lnm);
+}
+
 __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeParams p) {
   const unsigned long long n = p.n;
   for (unsigned long long i = (unsigned long long)p.row_begin + blockIdx.x; i < p.row_end && i + 1 < n; i += gridDim.x) {
@@ -418,6 +446,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
           const uint32_t lj = p.lens[j];
           const uint32_t ml = li < lj ? li : lj;
           if (ml > 0) d = __dsub_rn(1.0, __ddiv_rn((double)nid, (double)ml));
+          if (p.kimura) {           // -ln(1 - D - D^2/5), operation for operation as tsq_oracle_kimura
+            if (ml > 0 && d < 0.75) {
+              const double u = __ddiv_rn(__dmul_rn(d, d), 5.0);
+              d = __dsub_rn(0.0, ln_spec(__dsub_rn(__dsub_rn(1.0, d), u)));
+            } else {
+              atomicAdd(p.kimura_oob, 1);   // the uncorrected value stays in place; the host turns the count into an error
+            }
+          }
         } else if (mn > 0) {
           d = __dsub_rn(1.0, __ddiv_rn((double)s, (double)mn));
         }

@@ -92,6 +92,8 @@ struct FinalizeParams {
   uint32_t perm_identity;        // perm is the identity and there are no empty sequences
   uint32_t idshift;           // identity mode: sorted[] holds score * 2^idshift + identities; 0 = off
   int32_t* out_nid;           // identity mode: identities, packed triangle, original order
+  uint32_t kimura;            // identity mode: distances Kimura-corrected, -ln(1 - D - D^2/5) for D < 0.75
+  int* kimura_oob;            // counts the pairs with D >= 0.75 (the formula does not apply: the host reports an error)
 };
 cudaError_t finalize_launch(const FinalizeParams& p, cudaStream_t stream);
 
