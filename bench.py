@@ -462,6 +462,7 @@ def time_workload(env: Env, name: str, steps: int, warmup: int, e2e_steps: int, 
 
     # ---- end to end through the public calls, host buffers ------------------------------------
     host_buf, host_offs = flatten(seqs)     # the job's input as it sits in host memory: ASCII residues
+    run.ctx.stream_results(True)            # finished row ranges leave for the host behind their launch (as tsq_run does)
     h2d = d2h = 0
     e2e_t = 0.0
     e2e_launches = 0

@@ -166,6 +166,15 @@ int tsq_set_sequences_flat(tsq_ctx *ctx, const char *residues, const uint64_t *o
 int tsq_upload(tsq_ctx *ctx);   /* sort/pack on the host, H2D */
 int tsq_compute(tsq_ctx *ctx);  /* enqueue all kernels on the context's stream (async) */
 int tsq_download(tsq_ctx *ctx); /* synchronise, D2H of scores (+ distances) */
+/*
+ * Streamed results for the staged calls (tsq_run always streams): with enable != 0 a later tsq_compute sends the
+ * packed kernel's tasks out in a few launches over consecutive row ranges and, behind each, finalizes those rows
+ * and copies scores (+ distances) to the host on a side stream while the next launch computes -- SURVEY.md
+ * section 8e's "slabs overlapped with remaining compute".  tsq_download then only waits.  Takes effect where the
+ * results need no un-sort (fixed-length input, no identity keys, short sequences only); other jobs run as before.
+ * The host destination (the library's pinned buffer, or tsq_set_result_buffers) must not change in between.
+ */
+int tsq_stream_results(tsq_ctx *ctx, int enable);
 /* Make tsq_compute enqueue on a caller-owned cudaStream_t (passed as void*); NULL = own. */
 int tsq_set_stream(tsq_ctx *ctx, void *cuda_stream);
 /* Block until everything enqueued by tsq_compute has finished. */

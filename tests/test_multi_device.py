@@ -252,3 +252,66 @@ def test_ragged_ranks_still_gather_into_rank_0():
         with pytest.raises(t.TsqError) as e:
             ctx.finalize()
         assert e.value.status == -6
+
+
+# ---- streamed results: row ranges leave for the host behind the launch that computed them --------------------------
+@pytest.mark.parametrize("chunks", ["1", "3", "8"])
+@pytest.mark.parametrize("dist", [True, False])
+def test_streamed_results_equal_the_plain_ones(chunks, dist, monkeypatch):
+    """tsq_stream_results: the packed kernel's tasks in `chunks` launches over consecutive row ranges, each followed
+    on a side stream by finalize + copy-out of those rows (TSQ_STREAM_CHUNKS forces the split on a small job)."""
+    monkeypatch.setenv("TSQ_STREAM_CHUNKS", chunks)
+    _, seqs = synth.config(2, 0.45)                     # 450 x 300 aa; also an odd row count below
+    seqs = seqs[:449]
+    rs, rd, _, _ = oracle_run(seqs)
+    flags = 0 if dist else t.FLAG_NO_DISTANCES
+    with t.Context(flags=flags) as ctx:
+        ctx.set_sequences(seqs)
+        ctx.stream_results(True)
+        ctx.upload()
+        for _ in range(2):                              # staged, repeated: the side stream is reused
+            ctx.compute()
+            ctx.download()
+            assert (ctx.scores() == rs).all()
+            if dist:
+                assert ctx.distances().tobytes() == rd.tobytes()
+        st = ctx.stats()
+        assert st["launches"] >= int(chunks) and st["d2h_bytes"] == len(rs) * (12 if dist else 4)
+        if dist:
+            tree = ctx.guide_tree()                     # the main stream sees the side stream's distances
+            assert len(tree[0]) == len(seqs) - 1
+        ctx.stream_results(False)
+        ctx.compute(); ctx.download()
+        assert (ctx.scores() == rs).all()
+
+
+def test_streaming_is_skipped_where_the_results_need_an_unsort(monkeypatch):
+    monkeypatch.setenv("TSQ_STREAM_CHUNKS", "4")
+    rng = np.random.default_rng(47)
+    seqs = ragged(rng, 120, 0, 200, AA[:20])            # ragged: the un-sort scatters rows, nothing can leave early
+    rs, rd, _, _ = oracle_run(seqs)
+    with t.Context() as ctx:
+        ctx.set_sequences(seqs)
+        ctx.stream_results(True)
+        ctx.run()
+        assert (ctx.scores() == rs).all() and ctx.distances().tobytes() == rd.tobytes()
+
+
+def test_streamed_results_on_several_devices_into_caller_buffers(ndev, monkeypatch):
+    monkeypatch.setenv("TSQ_STREAM_CHUNKS", "3")
+    _, seqs = synth.config(2, 0.5)
+    n = len(seqs)
+    scores = np.full(n * (n - 1) // 2, -7, dtype=np.int32)
+    dist = np.full(n * (n - 1) // 2, -7.0, dtype=np.float64)
+    rs, rd, _, _ = oracle_run(seqs)
+    with t.Context(n_devices=ndev) as ctx:
+        ctx.set_result_buffers(scores, dist)
+        ctx.set_sequences(seqs)
+        ctx.run()                                       # tsq_run streams by itself
+        assert (scores == rs).all() and dist.tobytes() == rd.tobytes()
+        tree = ctx.guide_tree()
+    with t.Context() as ctx:
+        ctx.set_sequences(seqs)
+        ctx.run()
+        tree1 = ctx.guide_tree()
+    assert all((x == y).all() for x, y in zip(tree, tree1))

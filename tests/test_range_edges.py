@@ -134,17 +134,18 @@ def _long_set(rng, alphabet_letters, lens):
     return [rand(rng, l, alphabet_letters) for l in lens]
 
 
-@pytest.mark.parametrize("go,packed", [(20, True), (21, False)])
-def test_wave16_window_just_under_and_just_over_the_limit(go, packed):
-    """Nucleotides, 24 columns per lane: window = 972 * (5 + go + 1 + 4).  go = 20: 29 160 <= 30 000, the packed
-    wavefront kernel; go = 21: 30 132, the host must take the 32-bit kernel.  Sequences beyond the inter-task
-    limit; poly-A pairs (steepest climb), unrelated ones (steepest fall) and very unequal lengths."""
+@pytest.mark.parametrize("go,packed,cols", [(20, True, 24), (21, True, 16), (31, True, 16), (32, False, 16)])
+def test_wave16_window_just_under_and_just_over_the_limit(go, packed, cols):
+    """Nucleotides: window = (32 * columns per lane + 204) * (5 + go + 1 + 4).  24 columns per lane while that fits
+    30 000 (go = 20: 972 * 30 = 29 160), 16 columns beyond (go = 21: 716 * 31; go = 31: 716 * 41 = 29 356), and from
+    go = 32 (716 * 42 = 30 072) the host must take the 32-bit kernel.  Sequences beyond the inter-task limit;
+    poly-A pairs (steepest climb), unrelated ones (steepest fall) and very unequal lengths."""
     rng = np.random.default_rng(606)
     with t.Context(alphabet=1, gap_open=go, gap_extend=1) as ctx:
         lim = ctx.limits()
     assert bool(lim["wave_packed"]) == packed
     assert (lim["wave_window"] <= lim["wave_window_max"]) == packed
-    assert lim["wave_window"] == 972 * (5 + go + 1 + 4)
+    assert lim["wave_window"] == (32 * cols + 204) * (5 + go + 1 + 4)
     Lw = lim["max_len_inter"] + 1
     seqs = (["A" * (Lw + 700), "A" * (Lw + 300), "C" * (Lw + 10), rand(rng, Lw + 1200, "ACGT"), rand(rng, Lw, "ACGT")] +
             ["A" * 1500, rand(rng, 2200, "ACGT"), "ACGT" * 300, "G"])

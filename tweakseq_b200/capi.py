@@ -73,7 +73,7 @@ SYMBOLS = ["tsq_version", "tsq_version_string", "tsq_status_string", "tsq_device
            "tsq_self_scores", "tsq_identities", "tsq_device_scores", "tsq_partition", "tsq_finalize", "tsq_device_results",
            "tsq_get_stats", "tsq_measure_dpx_rate", "tsq_run_fasta", "tsq_plan_partition", "tsq_guide_tree",
            "tsq_write_newick", "tsq_consensus", "tsq_align_pair", "tsq_partition_of", "tsq_msa", "tsq_write_msa_fasta", "tsq_write_distmat",
-           "tsq_device_slab", "tsq_results_sharded", "tsq_set_result_buffers", "tsq_get_device_stats", "tsq_get_limits", "tsq_measure_pipe_rates", "tsq_detect_alphabet"]
+           "tsq_device_slab", "tsq_results_sharded", "tsq_set_result_buffers", "tsq_get_device_stats", "tsq_get_limits", "tsq_measure_pipe_rates", "tsq_detect_alphabet", "tsq_stream_results"]
 
 _lib = None
 
@@ -113,6 +113,7 @@ def load_library():
     for f in ("tsq_upload", "tsq_compute", "tsq_download", "tsq_synchronize", "tsq_finalize"):
         getattr(L, f).argtypes = [vp]
     L.tsq_set_stream.argtypes = [vp, vp]
+    L.tsq_stream_results.argtypes = [vp, C.c_int]
     L.tsq_run.argtypes = [vp, PROGRESS_CB, vp, C.POINTER(C.c_int)]
     L.tsq_scores.argtypes = [vp, C.POINTER(i32p), u64p]
     L.tsq_distances.argtypes = [vp, C.POINTER(C.POINTER(C.c_double)), u64p]
@@ -269,6 +270,10 @@ class Context:
 
     def synchronize(self):
         self._ck(self._L.tsq_synchronize(self._h))
+
+    def stream_results(self, enable: bool = True):
+        """Staged calls: let compute() send finished row ranges to the host behind its launches (tsq_stream_results)."""
+        self._ck(self._L.tsq_stream_results(self._h, 1 if enable else 0))
 
     def set_stream(self, cuda_stream_ptr: int | None):
         self._ck(self._L.tsq_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))

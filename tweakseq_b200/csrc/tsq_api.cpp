@@ -232,8 +232,6 @@ struct tsq_ctx {
   int go = 11, ge = 1;
   int device = 0;
   int sm_count = 0;
-  size_t l2_persist_bytes = 0;   // persisting L2 carve-out of the device (0: unsupported / not set)
-  size_t l2_window_max = 0;      // largest access policy window the device takes
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;    // around the score kernels of tsq_compute
@@ -336,6 +334,15 @@ struct tsq_ctx {
   const std::vector<int32_t>* selfp = nullptr;                // self scores: own `self_input`, or the leader's
   cudaEvent_t fin_ev = nullptr;    // recorded behind this context's finalize (cross-device stream waits)
   DevBuf<double> d_dist_full;      // child 0 of a leader in slab mode: all slabs of the distance matrix (guide tree)
+  // ---- streamed results (tsq_run, tsq_stream_results): the packed kernel's tasks go out in a few launches over
+  // consecutive row ranges; behind each one a side stream finalizes those rows and copies them to the host while
+  // the next launch computes ("slabs overlapped with remaining compute on a side stream")
+  bool stream_out = false;          // asked for
+  bool streamed = false;            // the last tsq_compute did it: tsq_download has nothing left to copy
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> chunk_ev;
+  unsigned long long* h_starts = nullptr;   // pinned: first task of every chunk (the kernel's cursor is set from it)
+  uint64_t streamed_bytes = 0;
   // ---- caller-owned host result buffers (tsq_set_result_buffers) ---------------------------------------
   int32_t* ext_scores = nullptr;
   double* ext_dist = nullptr;
@@ -800,6 +807,19 @@ int device_upload(tsq_ctx* c) {
 
 namespace {
 
+struct StreamChunk {   // one launch of a streamed compute: tasks [t0, t1) = sorted rows [row0, row1)
+  unsigned long long t0, t1;
+  uint32_t row0, row1;
+};
+int stream_chunk_out(tsq_ctx* c, const StreamChunk& ch, cudaStream_t compute_stream, size_t index);   // defined below
+
+// Whether the results of this job can leave in row-range chunks: the packed kernel only, scores in place
+// (sorted order = submitted order, no identity keys), the whole triangle or a sharded slab.
+bool can_stream(const tsq_ctx* c) {
+  return c->stream_out && !c->use_g32 && c->idshift == 0 && c->tasks16w.empty() && c->pairs32.empty() &&
+         (c->prm.part_world == 1 ? c->perm_identity : c->slab_mode);
+}
+
 // ---- tsq_compute: the three score kernels, each enqueued on stream s when it has tasks ---------------
 int enqueue_gotoh16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
   const uint32_t nq = c->q_end - c->q_begin;
@@ -874,21 +894,54 @@ int enqueue_gotoh16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
     p.negge2 = ((uint32_t)(-(c->ge - c->delta)) & 0xffffu) * 0x10001u;
     p.goe2 = (uint32_t)(c->go + c->ge - c->delta) * 0x10001u;
     if (!fits16(c, lpad)) return fail(c, TSQ_ERR_RANGE, "internal: padded length %u outside the 16-bit bound", lpad);
-    // L2 policy of the scratch column: written by one strip, read back once by the next, then overwritten in
-    // place.  Its live set (warps x rows x 256 B: 140 MB at configs[1]) cycles through a 126 MB L2 under LRU, so
-    // without a policy most rows make a round trip through HBM (6.3 GB per launch, r01).  The share that fits the
-    // persisting carve-out is pinned for this launch; the rest streams.
-    cudaAccessPolicyWindow win{};
-    const size_t bnd_bytes = (size_t)grid * warps_per_cta * bnd_rows * 32 * sizeof(uint2);
-    if (c->l2_persist_bytes > 0 && !getenv("TSQ_NO_L2_POLICY")) {
-      win.base_ptr = c->d_bnd.p;
-      win.num_bytes = std::min(bnd_bytes, c->l2_window_max);
-      win.hitRatio = (float)std::min(1.0, 0.9 * (double)c->l2_persist_bytes / (double)std::max<size_t>(win.num_bytes, 1));
-      win.hitProp = cudaAccessPropertyPersisting;
-      win.missProp = cudaAccessPropertyStreaming;
+    // (r02: an L2 access-policy window over the scratch column -- persisting for the share that fits the carve-out,
+    //  streaming for the rest -- was measured on configs[1] and changed neither the time nor the DRAM bytes
+    //  (profiles/l2_policy_ab_r02.txt), so the launch carries no policy.)
+    c->streamed = false;
+    // how many launches: one, unless the results are streamed out and the job is long enough that every launch
+    // still fills the device for many waves (a launch ends in a partly filled wave: ~half a task time lost)
+    size_t nchunks = 1;
+    if (can_stream(c)) {
+      const unsigned long long resident = (unsigned long long)grid * warps_per_cta;
+      nchunks = (size_t)std::min<unsigned long long>(8, ntasks / (16 * std::max<unsigned long long>(resident, 1)));
+      if (nchunks < 1) nchunks = 1;
+      if (const char* e = getenv("TSQ_STREAM_CHUNKS")) nchunks = (size_t)std::min(8, std::max(1, atoi(e)));   // tests: force a split
+      if (nchunks > nq) nchunks = std::max<size_t>(nq, 1);
     }
-    TSQ_CUDA(c, tsq::g16_launch(c->K, grid, p, s, win.num_bytes ? &win : nullptr));
-    launches++;
+    if (nchunks == 1 && !can_stream(c)) {
+      TSQ_CUDA(c, tsq::g16_launch(c->K, grid, p, s, nullptr));
+      launches++;
+    } else {
+      // chunk k = task rows r in [r_k, r_k+1): tasks [prefix[r_k], prefix[r_k+1]), i.e. query pairs
+      // q_end-1-r, which are consecutive sorted rows -- long queries first, as the task order has it
+      if (c->chunk_ev.size() < nchunks) {
+        const size_t old = c->chunk_ev.size();
+        c->chunk_ev.resize(nchunks, nullptr);
+        for (size_t k = old; k < nchunks; k++) TSQ_CUDA(c, cudaEventCreateWithFlags(&c->chunk_ev[k], cudaEventDisableTiming));
+      }
+      if (!c->copy_stream) TSQ_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+      if (!c->h_starts) TSQ_CUDA(c, BlockCache::get().take(-1, 8 * sizeof(unsigned long long), (void**)&c->h_starts));
+      c->streamed_bytes = 0;
+      for (size_t k = 0; k < nchunks; k++) {
+        const uint32_t r0 = (uint32_t)((unsigned long long)nq * k / nchunks), r1 = (uint32_t)((unsigned long long)nq * (k + 1) / nchunks);
+        if (r1 <= r0) continue;
+        StreamChunk ch;
+        ch.t0 = c->task_prefix[r0];
+        ch.t1 = c->task_prefix[r1];
+        ch.row0 = c->lo + 2 * (c->q_end - r1);           // query pairs q_end-r1 .. q_end-1-r0
+        ch.row1 = c->lo + 2 * (c->q_end - r0);
+        if (k + 1 == nchunks) ch.row0 = std::min(ch.row0, c->row_a);            // rows without tasks of their own (none today)
+        if (k == 0) ch.row1 = std::max(ch.row1, std::min(c->row_b, c->n));     // a last odd row has no pairs: empty range
+        c->h_starts[k] = ch.t0;
+        TSQ_CUDA(c, cudaMemcpyAsync(c->d_counter.p, &c->h_starts[k], sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+        p.ntasks = ch.t1;
+        TSQ_CUDA(c, tsq::g16_launch(c->K, grid, p, s, nullptr));
+        launches++;
+        const int rc = stream_chunk_out(c, ch, s, k);
+        if (rc != TSQ_OK) return rc;
+      }
+      c->streamed = true;
+    }
   }
   return TSQ_OK;
 }
@@ -1193,6 +1246,49 @@ int check_device_fault(tsq_ctx* c) {
   return TSQ_OK;
 }
 
+// Behind one launch of a streamed compute: on the side stream, once that launch is done, finalize its rows
+// (distances next to the scores) and copy both to their place in the host result -- while the next launch runs.
+int stream_chunk_out(tsq_ctx* c, const StreamChunk& ch, cudaStream_t compute_stream, size_t index) {
+  const uint64_t n = c->n, npairs = n < 2 ? 0 : n * (n - 1) / 2;
+  auto start_of = [&](uint32_t row) -> uint64_t { return (n >= 2 && (uint64_t)row + 1 < n) ? tri(row, row + 1, n) : npairs; };
+  const uint64_t pb = start_of(ch.row0), pe = start_of(ch.row1);
+  TSQ_CUDA(c, cudaEventRecord(c->chunk_ev[index], compute_stream));
+  if (pe <= pb) return TSQ_OK;
+  const bool want_dist = !(c->prm.flags & TSQ_FLAG_NO_DISTANCES);
+  HostDst h;
+  int rc = host_results(c, want_dist, false, &h);
+  if (rc != TSQ_OK) return rc;
+  TSQ_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->chunk_ev[index], 0));
+  const uint64_t first = c->full_sorted ? 0 : c->part_begin;   // what the device buffers start at
+  if (want_dist) {
+    TSQ_CUDA(c, c->d_dist.reserve(c->full_sorted ? npairs : c->part_end - c->part_begin));
+    tsq::FinalizeParams f{};
+    f.sorted = sorted_base(c);
+    f.lens = c->d_lens.p;
+    f.perm = c->d_perm.p;
+    f.self = c->d_self.p;
+    f.out_scores = sorted_base(c);
+    f.out_nid = nullptr;
+    f.out_dist = biased(c->d_dist.p, first);
+    f.idshift = 0;
+    f.n = c->n;
+    f.row_begin = ch.row0;
+    f.row_end = ch.row1;
+    f.go = c->go;
+    f.ge = c->ge;
+    f.perm_identity = 1u;
+    f.kimura = 0;
+    f.kimura_oob = c->d_cancel + 2;
+    TSQ_CUDA(c, tsq::finalize_launch(f, c->copy_stream));
+    c->st.launches++;
+  }
+  tsq_ctx* owner = result_owner(c);
+  TSQ_CUDA(c, copy_out(owner, h.scores + pb, c->d_sorted.p + (pb - first), (pe - pb) * sizeof(int32_t), c->copy_stream));
+  if (want_dist) TSQ_CUDA(c, copy_out(owner, h.dist + pb, c->d_dist.p + (pb - first), (pe - pb) * sizeof(double), c->copy_stream));
+  c->streamed_bytes += (pe - pb) * (want_dist ? 12ull : 4ull);
+  return TSQ_OK;
+}
+
 // ---- multi-device leader: every entry point fans out to the per-device children ----------------------------
 template <typename F>
 int for_each_kid_parallel(tsq_ctx* c, F&& body) {
@@ -1271,6 +1367,7 @@ int multi_finalize(tsq_ctx* c) {
   tsq_ctx* k0 = c->kids[0];
   if (c->slab_mode) {
     // fixed-length input: a device's slab is a contiguous piece of the final triangle -- finalize in place
+    // (children that streamed their rows out behind the launches have done it already)
     for (tsq_ctx* k : c->kids) {
       const int rc = tsq_finalize(k);
       if (rc != TSQ_OK) {
@@ -1375,6 +1472,7 @@ int multi_prepare_first_device(tsq_ctx* c) {
     for (tsq_ctx* k : c->kids) {
       const uint64_t cnt = k->part_end - k->part_begin;
       if (cnt == 0) continue;
+      TSQ_CUDA(c, cudaStreamWaitEvent(k0->stream, k->fin_ev, 0));   // that device's distances are complete
       TSQ_CUDA(c, cudaMemcpyPeerAsync(k0->d_dist_full.p + k->part_begin, k0->device, k->d_dist.p, k->device,
                                       cnt * sizeof(double), k0->stream));
     }
@@ -1520,17 +1618,6 @@ int tsq_create(tsq_ctx** out, const tsq_params* params) {
     tsq_destroy(c);
     return TSQ_ERR_CUDA;
   }
-  {   // persisting L2 carve-out for the strip-boundary scratch of the packed kernel (see enqueue_gotoh16)
-    int max_persist = 0, max_window = 0;
-    if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device) == cudaSuccess && max_persist > 0 &&
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device) == cudaSuccess && max_window > 0 &&
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess) {
-      c->l2_persist_bytes = (size_t)max_persist;
-      c->l2_window_max = (size_t)max_window;
-    } else {
-      cudaGetLastError();
-    }
-  }
   c->h_one[0] = 1;
   c->h_one[1] = c->h_one[2] = c->h_one[3] = 0;
   c->h_fault = c->h_one + 1;
@@ -1546,6 +1633,7 @@ int tsq_destroy(tsq_ctx* c) {
   cudaSetDevice(c->device);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
   if (c->stream && c->stream != c->own_stream && cudaStreamSynchronize(c->stream) != cudaSuccess) cudaGetLastError();
+  if (c->copy_stream && cudaStreamSynchronize(c->copy_stream) != cudaSuccess) cudaGetLastError();
   unregister_all(c);
   c->d_dbw.release(); c->d_blob.release(); c->h_blob.release();
   c->d_sorted.release(); c->d_scores.release(); c->d_nid.release(); c->h_nid.release(); c->d_dist.release(); c->d_dist_full.release();
@@ -1554,6 +1642,13 @@ int tsq_destroy(tsq_ctx* c) {
   c->d_pairs32.release(); c->d_tasks16w.release(); c->d_bnd16w.release(); c->d_bnd32.release(); c->d_smat.release();
   if (c->d_cancel) BlockCache::get().give(c->device, c->d_cancel);
   if (c->h_one) BlockCache::get().give(-1, c->h_one);
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
+  }
+  for (cudaEvent_t e : c->chunk_ev)
+    if (e) cudaEventDestroy(e);
+  if (c->h_starts) BlockCache::get().give(-1, c->h_starts);
   if (c->cancel_stream) cudaStreamDestroy(c->cancel_stream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1638,6 +1733,8 @@ int tsq_compute(tsq_ctx* c) {
   TSQ_CUDA(c, cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   uint32_t launches = 0;
+  c->st.launches = 0;
+  c->streamed = false;
   TSQ_CUDA(c, cudaMemsetAsync(c->d_cancel, 0, 4 * sizeof(int), s));   // cancel flag, fault word, Kimura out-of-range count
   TSQ_CUDA(c, cudaEventRecord(c->ev0, s));
   int rc = enqueue_gotoh16(c, s, launches);                 // regime 1: packed inter-task kernel
@@ -1645,9 +1742,14 @@ int tsq_compute(tsq_ctx* c) {
   if (rc == TSQ_OK) rc = enqueue_wave32(c, s, launches);    // regime 2 fallback: 32-bit wavefront kernel
   if (rc != TSQ_OK) return rc;
   TSQ_CUDA(c, cudaEventRecord(c->ev1, s));
-  c->st.launches = launches;
+  c->st.launches += launches;
   c->computed = true;
   c->finalized = c->downloaded = false;
+  if (c->streamed) {   // rows finalized and on their way to the host: what tsq_finalize / tsq_download would have done
+    TSQ_CUDA(c, cudaEventRecord(c->fin_ev, c->copy_stream));
+    c->finalized = true;
+    c->have_tree = c->have_msa = false;
+  }
   return TSQ_OK;
 }
 
@@ -1656,6 +1758,11 @@ int tsq_finalize(tsq_ctx* c) {
   if (!c->computed) return fail(c, TSQ_ERR_STATE, "tsq_finalize before tsq_compute");
   if (!c->kids.empty()) return multi_finalize(c);
   TSQ_CUDA(c, cudaSetDevice(c->device));
+  if (c->streamed) {   // done chunk by chunk behind the launches; whatever follows on the main stream sees the result
+    TSQ_CUDA(c, cudaStreamWaitEvent(c->stream, c->fin_ev, 0));
+    c->finalized = true;
+    return TSQ_OK;
+  }
   const uint32_t n = c->n;
   const uint64_t npairs = n < 2 ? 0 : (uint64_t)n * (n - 1) / 2;
   const bool want_dist = !(c->prm.flags & TSQ_FLAG_NO_DISTANCES);
@@ -1691,6 +1798,7 @@ int tsq_synchronize(tsq_ctx* c) {
   if (!c->kids.empty()) return multi_synchronize(c);
   TSQ_CUDA(c, cudaSetDevice(c->device));
   TSQ_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->copy_stream) TSQ_CUDA(c, cudaStreamSynchronize(c->copy_stream));
   if (c->computed) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->st.kernel_ms = ms;
@@ -1704,6 +1812,16 @@ int tsq_download(tsq_ctx* c) {
   if (!c) return TSQ_ERR_INVALID;
   if (!c->computed) return fail(c, TSQ_ERR_STATE, "tsq_download before tsq_compute");
   if (!c->kids.empty()) return multi_download(c);
+  if (c->streamed) {   // every row range was copied behind its launch: only the wait is left
+    const double t0s = now_ms();
+    c->st.d2h_bytes = c->streamed_bytes;
+    if (c->leader) return TSQ_OK;   // the leader synchronizes all its devices
+    const int rc = tsq_synchronize(c);
+    if (rc != TSQ_OK) return rc;
+    c->downloaded = true;
+    c->st.download_ms = now_ms() - t0s;
+    return TSQ_OK;
+  }
   const bool gathered_elsewhere = c->prm.part_world > 1 && !c->slab_mode && (c->prm.part_rank != 0 || c->leader);
   if (!c->finalized && !gathered_elsewhere) {
     int rc = tsq_finalize(c);
@@ -1758,7 +1876,11 @@ int tsq_run(tsq_ctx* c, tsq_progress_cb cb, void* user, volatile int* cancel) {
   if (rc != TSQ_OK) return rc;
   if (cancelled()) return fail(c, TSQ_ERR_CANCELLED, "cancelled");
   if (cb) cb(user, 0.05, "computing pairwise scores");
+  // the blocking call knows the results are wanted on the host: let finished row ranges leave while the rest computes
+  const bool was_streaming = c->stream_out;
+  tsq_stream_results(c, 1);
   rc = tsq_compute(c);
+  tsq_stream_results(c, was_streaming ? 1 : 0);
   if (rc != TSQ_OK) return rc;
   // poll the stream(s) so that "Stop" (SeqEditMainWin.cpp:803-812) is honoured while kernels run
   std::vector<tsq_ctx*> devs;
@@ -1790,6 +1912,13 @@ int tsq_run(tsq_ctx* c, tsq_progress_cb cb, void* user, volatile int* cancel) {
   rc = tsq_download(c);
   if (rc != TSQ_OK) return rc;
   if (cb) cb(user, 1.0, "done");
+  return TSQ_OK;
+}
+
+int tsq_stream_results(tsq_ctx* c, int enable) {
+  if (!c) return TSQ_ERR_INVALID;
+  c->stream_out = enable != 0;
+  for (tsq_ctx* k : c->kids) k->stream_out = c->stream_out;
   return TSQ_OK;
 }
 

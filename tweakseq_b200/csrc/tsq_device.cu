@@ -148,21 +148,19 @@ cudaError_t w32_launch(int grid, const W32Params& p, cudaStream_t stream) {
   X(16, 128, 3)             \
   X(8, 128, 2)
 
-// Columns per lane and CTAs per SM.  Small alphabets (nucleotides): 32 columns per lane, 2 CTAs (8 warps) per SM --
-// r02 sweep on 120 genomes of 10-30 kb with the four-row body: 32,2 -> 6 864 GCUPS; 24,3 -> 6 366; 16,3 -> 5 830 (a
-// wider block spreads the per-step hand-off over more cells and needs fewer passes) -- unless the window of 32
-// columns is too wide for the gap model at hand, then 24,3.  Proteins: 8 columns (23.5 KB of profile per warp).
+// Columns per lane and CTAs per SM.  Small alphabets (nucleotides): 24 columns per lane, 3 CTAs (12 warps) per SM.
+// r02, four-row body, A/B inside one box on the FULL configs[3] (62 375 tasks): 24,3 -> 7 730 GCUPS, 32,2 -> 7 417
+// (on 120 genomes 32,2 looked better, 6 864 vs 6 366 -- a wave-quantisation accident: 3 570 tasks are exactly three
+// waves of 1 184 warps but 2.01 of 1 776).  A gap model whose window of 24 columns is too wide gets 16 columns
+// before the job falls back to the 32-bit kernel.  Proteins: 8 columns (23.5 KB of profile per warp).
 static bool w16_pick(uint32_t nsym, long long lipschitz, W32Launch* out) {
   if (nsym == 0 || nsym > 24) return false;
   W32Launch v;
   v.tpb = 128;
   if (nsym <= 8) {
-    v.KW = 32;
-    v.ctas_sm = 2;
-    if (lipschitz > 0 && (32ll * 32 + 4 * 31 + 4 * 16 + 16) * lipschitz > kW16WindowMax) {
-      v.KW = 24;
-      v.ctas_sm = 3;
-    }
+    v.KW = 24;
+    v.ctas_sm = 3;
+    if (lipschitz > 0 && (32ll * 24 + 4 * 31 + 4 * 16 + 16) * lipschitz > kW16WindowMax) v.KW = 16;
   } else {
     v.KW = 8;
     v.ctas_sm = 2;
