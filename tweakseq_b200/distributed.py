@@ -61,10 +61,24 @@ class SharedResult:
 
     def __init__(self, count: int, want_dist: bool, group=None):
         rank = dist.get_rank(group) if dist.is_initialized() else 0
-        name = [f"/dev/shm/tsq_b200_{os.getpid()}_{uuid.uuid4().hex[:12]}" if rank == 0 else None]
         off_d = (count * 4 + 4095) & ~4095
         size = max(off_d + (count * 8 if want_dist else 0), 4096)
+        name = [None]
         if rank == 0:
+            # /dev/shm when it has the room (a container's default is small: a page touched beyond it is a SIGBUS,
+            # not an error code), else a temporary directory on disk: page-locked and mapped the same way
+            where = None
+            for d in ("/dev/shm", os.environ.get("TMPDIR", "/tmp"), "/tmp"):
+                try:
+                    st = os.statvfs(d)
+                    if st.f_bavail * st.f_frsize > size + (256 << 20):
+                        where = d
+                        break
+                except OSError:
+                    pass
+            if where is None:
+                raise RuntimeError(f"no room for a shared result of {size} bytes in /dev/shm or /tmp")
+            name = [f"{where}/tsq_b200_{os.getpid()}_{uuid.uuid4().hex[:12]}"]
             with open(name[0], "wb") as f:
                 f.truncate(size)
         if dist.is_initialized() and dist.get_world_size(group) > 1:
