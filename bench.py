@@ -466,6 +466,7 @@ def time_workload(env: Env, name: str, steps: int, warmup: int, e2e_steps: int, 
     h2d = d2h = 0
     e2e_t = 0.0
     e2e_launches = 0
+    e2e_stages = {}
     for k in range(e2e_warm + e2e_steps):
         env.barrier()
         t0 = time.perf_counter()
@@ -481,6 +482,8 @@ def time_workload(env: Env, name: str, steps: int, warmup: int, e2e_steps: int, 
             s2 = run.ctx.stats()
             h2d, d2h = s2["h2d_bytes"], s2["d2h_bytes"]
             e2e_launches = s2["launches"] + s2["upload_launches"]
+            e2e_stages = {"encode": round(s2["encode_ms"], 3), "sort_pack_h2d": round(s2["upload_ms"], 3),
+                          "kernels": round(s2["kernel_ms"], 3), "wait_for_results": round(s2["download_ms"], 3)}
     if env.world > 1:     # whole-job bytes: every rank copies its own share
         tt = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
         env.dist.all_reduce(tt)
@@ -502,6 +505,7 @@ def time_workload(env: Env, name: str, steps: int, warmup: int, e2e_steps: int, 
             "kernel_ms_per_rank": [round(x, 4) for x in per_rank_ms],
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_t / e2e_steps, "steps": e2e_steps, "launches_per_step": int(e2e_launches),
+                    "stages_ms_rank0": e2e_stages,
                     "results": ("one multi-device context (tsq_params.n_devices): " if env.inprocess else "") +
                                ("every rank finalizes its slab and copies it over its own PCIe link into one shared host result"
                                 if run.sharded else ("one device" if env.n_gpus == 1 else

@@ -123,6 +123,7 @@ typedef struct tsq_stats {
   uint64_t d2h_bytes;        /* bytes the last tsq_download copied device -> host */
   double tree_ms;            /* CUDA-event time of the last tsq_guide_tree (device only) */
   double msa_ms;             /* wall time of the last tsq_msa (plan, kernels, copies) */
+  double encode_ms;          /* host time of the last tsq_set_sequences[_flat] (gap stripping, letter map, self scores) */
 } tsq_stats;
 
 /* progress in [0,1]; msg may be NULL.  Return value ignored. */

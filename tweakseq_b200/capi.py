@@ -46,7 +46,7 @@ class Stats(C.Structure):
                 ("cells_s16", C.c_uint64), ("cells_s32", C.c_uint64), ("kernel_ms", C.c_double),
                 ("upload_ms", C.c_double), ("download_ms", C.c_double), ("gcups_kernel", C.c_double),
                 ("launches", C.c_uint32), ("sm_count", C.c_uint32), ("strip_width", C.c_uint32),
-                ("upload_launches", C.c_uint32), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("tree_ms", C.c_double), ("msa_ms", C.c_double)]
+                ("upload_launches", C.c_uint32), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("tree_ms", C.c_double), ("msa_ms", C.c_double), ("encode_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -1669,43 +1669,99 @@ int tsq_set_stream(tsq_ctx* c, void* s) {
   return TSQ_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+// Encodes all sequences (gap stripping, letter map, self scores).  Large inputs are cut into byte-balanced ranges
+// of sequences for a few host threads: at 10^5 sequences this pass is the longest host step of a job, and in a
+// weak-scaled multi-GPU run every rank repeats it for the whole input.
+template <typename Get>
+void encode_all(tsq_ctx* c, uint32_t n, uint64_t total_bytes, Get&& get) {
+  auto work = [&](uint32_t a, uint32_t b) {
+    for (uint32_t i = a; i < b; i++) {
+      const char* p = nullptr;
+      size_t len = 0;
+      get(i, &p, &len);
+      c->self_input[i] = (int32_t)encode_into(c->prm.alphabet, c->diag_by_byte, p, len, c->enc[i]);
+    }
+  };
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  unsigned nt = total_bytes >= (256u << 10) ? std::min<unsigned>({4u, hw, n}) : 1u;
+  if (nt <= 1) {
+    work(0, n);
+    return;
+  }
+  std::vector<uint32_t> cut(nt + 1, n);
+  cut[0] = 0;
+  {
+    uint64_t acc = 0;
+    unsigned k = 1;
+    for (uint32_t i = 0; i < n && k < nt; i++) {
+      const char* p = nullptr;
+      size_t len = 0;
+      get(i, &p, &len);
+      acc += len;
+      if (acc >= total_bytes * k / nt) cut[k++] = i + 1;
+    }
+  }
+  std::vector<std::thread> th;
+  for (unsigned k = 1; k < nt; k++) th.emplace_back(work, cut[k], cut[k + 1]);
+  work(cut[0], cut[1]);
+  for (auto& t : th) t.join();
+}
+
+}  // namespace
+
+extern "C" {
+
 int tsq_set_sequences(tsq_ctx* c, const char* const* residues, const uint32_t* lengths, uint32_t n) {
   if (!c) return TSQ_ERR_INVALID;
   if (n > 0 && (!residues || !lengths)) return fail(c, TSQ_ERR_INVALID, "null sequence arrays");
+  const double t0 = now_ms();
   // a failed call leaves the context without sequences rather than with half of the new set
   c->have_seqs = c->uploaded = c->computed = c->finalized = c->downloaded = false;
   c->n = 0;
-  c->enc.resize(n);
-  c->self_input.resize(n);
+  uint64_t total = 0;
   for (uint32_t i = 0; i < n; i++) {
     if (lengths[i] > 0 && !residues[i]) return fail(c, TSQ_ERR_INVALID, "sequence %u is null", i);
-    c->self_input[i] = (int32_t)encode_into(c->prm.alphabet, c->diag_by_byte, residues[i], lengths[i], c->enc[i]);
+    total += lengths[i];
   }
+  c->enc.resize(n);
+  c->self_input.resize(n);
+  encode_all(c, n, total, [&](uint32_t i, const char** p, size_t* len) {
+    *p = residues[i];
+    *len = lengths[i];
+  });
   c->n = n;
   c->have_seqs = true;
   c->uploaded = c->computed = c->finalized = c->downloaded = false;
   c->err.clear();
   multi_share_sequences(c);   // children of a multi-device context read the leader's encoding
+  c->st.encode_ms = now_ms() - t0;
   return TSQ_OK;
 }
 
 int tsq_set_sequences_flat(tsq_ctx* c, const char* residues, const uint64_t* offsets, uint32_t n) {
   if (!c) return TSQ_ERR_INVALID;
   if (n > 0 && (!residues || !offsets)) return fail(c, TSQ_ERR_INVALID, "null sequence buffer");
+  const double t0 = now_ms();
   c->have_seqs = c->uploaded = c->computed = c->finalized = c->downloaded = false;
   c->n = 0;
+  for (uint32_t i = 0; i < n; i++)
+    if (offsets[i + 1] < offsets[i]) return fail(c, TSQ_ERR_INVALID, "offsets not ascending at %u", i);
   c->enc.resize(n);
   c->self_input.resize(n);
-  for (uint32_t i = 0; i < n; i++) {
-    if (offsets[i + 1] < offsets[i]) return fail(c, TSQ_ERR_INVALID, "offsets not ascending at %u", i);
-    c->self_input[i] = (int32_t)encode_into(c->prm.alphabet, c->diag_by_byte, residues + offsets[i],
-                                            (size_t)(offsets[i + 1] - offsets[i]), c->enc[i]);
-  }
+  encode_all(c, n, n ? offsets[n] - offsets[0] : 0, [&](uint32_t i, const char** p, size_t* len) {
+    *p = residues + offsets[i];
+    *len = (size_t)(offsets[i + 1] - offsets[i]);
+  });
   c->n = n;
   c->have_seqs = true;
   c->uploaded = c->computed = c->finalized = c->downloaded = false;
   c->err.clear();
   multi_share_sequences(c);
+  c->st.encode_ms = now_ms() - t0;
   return TSQ_OK;
 }
 
