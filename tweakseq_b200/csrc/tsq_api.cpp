@@ -2389,7 +2389,10 @@ int tsq_write_msa_fasta(tsq_ctx* c, const char* const* headers, const char* cons
   if (residues && !lengths) return fail(c, TSQ_ERR_INVALID, "residues without lengths");
   FILE* f = fopen(path, "w");
   if (!f) return fail(c, TSQ_ERR_IO, "cannot write %s", path);
-  std::string row;
+  // the whole file is assembled in memory and written once (a thousand rows are seven thousand lines:
+  // formatted writes per line cost more than the alignment kernels of a small job)
+  std::string row, text;
+  text.reserve((size_t)n * ((size_t)cols + cols / 60 + 64));
   for (uint32_t q = 0; q < n; q++) {
     const uint32_t r = tree_order ? order[q] : q;
     row.assign(rows + (size_t)r * cols, cols);
@@ -2405,14 +2408,20 @@ int tsq_write_msa_fasta(tsq_ctx* c, const char* const* headers, const char* cons
     }
     if (headers && headers[r]) {
       const char* h = headers[r];
-      fprintf(f, "%s%s\n", (h[0] == '>' ? "" : ">"), h);
+      if (h[0] != '>') text.push_back('>');
+      text.append(h);
+      text.push_back('\n');
     } else {
-      fprintf(f, ">s%u\n", r);
+      text.append(">s").append(std::to_string(r)).push_back('\n');
     }
     for (uint32_t at = 0; at < cols; at += 60) {
-      fwrite(row.data() + at, 1, std::min<uint32_t>(60, cols - at), f);
-      fputc('\n', f);
+      text.append(row, at, std::min<uint32_t>(60, cols - at));
+      text.push_back('\n');
     }
+  }
+  if (!text.empty() && fwrite(text.data(), 1, text.size(), f) != text.size()) {
+    fclose(f);
+    return fail(c, TSQ_ERR_IO, "write to %s failed", path);
   }
   if (fclose(f) != 0) return fail(c, TSQ_ERR_IO, "write to %s failed", path);
   return TSQ_OK;
