@@ -253,6 +253,11 @@ def clustalo_leg(seqs, our_dist):
         return res
 
 
+def synth_cells(seqs) -> int:
+    from tweakseq_b200 import synth
+    return synth.total_cells(seqs)
+
+
 def reference_arm(args):
     """--impl reference: the reference's CPU implementation of the path.  groundstate/tweakseq has
     none in-process (it execs clustalo, absent from this image), so this is the oracle port."""
@@ -294,7 +299,11 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": gcups, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": 1e3 * t_total / steps, "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "int16 SIMD lanes (exact; int32 scalar beyond the 16-bit range)", "data": "synthetic",
-            "config": {"workload": label, "sample_rows_per_step": rows_per_step},
+            "config": {"workload": label, "n_sequences": n, "pairs": total, "cells": synth_cells(seqs),
+                       "gap_open": go, "gap_extend": 1,
+                       "matrix": "ACGTN +5/-4 (SURVEY 8c)" if alphabet else "BLOSUM62 (Consensus.cpp:34-59)",
+                       "seed": 20261017 + (4 if alphabet else 2),
+                       "sample_rows_per_step": rows_per_step},
             "cpu_baseline": {"value": gcups, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{rows_per_step} rows against all later sequences per step, {steps} steps",
                              "kernel": "oracle/gotoh_simd.c: inter-sequence SIMD, one subject per int16 lane x 32 (AVX-512BW / AVX2 by "

@@ -27,4 +27,21 @@ with t.Context(alphabet=1) as ctx:                               # traceback: si
     enc = [o.encode(x, 1) for x in (nt[0][:300], nt[1][:200], "ACGT" * 600, "ACGA" * 560)]
     for i, j in ((0, 1), (2, 3)):
         assert ctx.align_pair(i, j) == o.traceback(enc[i], enc[j], o.matrix(1), 10, 1, 1)
+# round 2: several devices behind one context (children on one device here), ragged (peer-store finalize) and
+# fixed-length (slab finalize, streamed out in three launches), caller-owned result buffers
+os.environ["TSQ_MULTI_SAME_DEVICE"] = "1"
+os.environ["TSQ_STREAM_CHUNKS"] = "3"
+for seqs in (prot, synth.protein(96, 60, 3)):
+    n = len(seqs)
+    bs, bd = np.zeros(n * (n - 1) // 2, np.int32), np.zeros(n * (n - 1) // 2, np.float64)
+    with t.Context(n_devices=3) as ctx:
+        ctx.set_result_buffers(bs, bd)
+        ctx.set_sequences(seqs); ctx.run(); ctx.guide_tree()
+    enc = [o.encode(x) for x in seqs]
+    ref, _ = o.all_pairs(enc, o.matrix(0), 11, 1, nthreads=4)
+    assert (bs == ref).all()
+fam = ["ACDEFGHIKLMNPQRSTVWY" * 3, "ACDEFGHIKLMNPQRSTVWY" * 3, "ACDEFGHIKLMNPQRSTVWA" * 3, "ACDEFGHIKLMNPQRSTVWY" * 2 + "ACDEFGHIKL"]
+with t.Context(flags=t.FLAG_IDENTITY | t.FLAG_KIMURA) as ctx:      # Kimura branch of finalize
+    ctx.set_sequences(fam); ctx.run()
+    assert (ctx.distances() >= 0).all()
 print("sanitize_run ok")

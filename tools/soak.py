@@ -1,6 +1,8 @@
 """Randomised soak of the CUDA path against the CPU oracle: random alphabets, matrices, gap models,
 length mixes (empties, singletons, strip/pass boundaries, long tails), kernel-selection flags,
-identity mode, partitions, guide tree, progressive alignment and traceback.  Runs until --seconds elapse; prints one line
+identity mode (with and without the Kimura correction), partitions, several devices behind one context (real ones, or
+all children on one device), streamed results in 1-8 launches, caller-owned result buffers, guide tree, progressive
+alignment and traceback.  Runs until --seconds elapse; prints one line
 per trial class and a final summary; exits non-zero at the first mismatch (with the seed)."""
 import argparse
 import os
@@ -62,19 +64,45 @@ def trial(seed, counts):
     mat = o.matrix(alphabet) if matrix is None else matrix
     flags = int(rng.choice([0, 0, 0, t.FLAG_FORCE_S32, t.FLAG_FORCE_S32 | t.FLAG_NO_WAVE16, t.FLAG_NO_WAVE16]))
     identity = rng.random() < 0.25
+    kimura = identity and rng.random() < 0.4
     if identity:
         flags |= t.FLAG_IDENTITY
+    if kimura:
+        flags |= t.FLAG_KIMURA
+    # several devices behind one context, streamed results, caller-owned result buffers
+    ndev = int(rng.choice([1, 1, 2, 3]))
+    if ndev > 1 and t.load_library().tsq_device_count() < ndev:
+        os.environ["TSQ_MULTI_SAME_DEVICE"] = "1"
+    chunks = rng.choice(["", "1", "3", "8"])
+    if chunks:
+        os.environ["TSQ_STREAM_CHUNKS"] = str(chunks)
+    else:
+        os.environ.pop("TSQ_STREAM_CHUNKS", None)
+    own_buffers = rng.random() < 0.3
     enc = [o.encode(s, alphabet) for s in seqs]
     n = len(seqs)
-    tag = f"seed={seed} alphabet={alphabet} n={n} go={gov} ge={ge} flags={flags} custom={matrix is not None} maxlen={max(map(len, seqs))}"
+    tag = (f"seed={seed} alphabet={alphabet} n={n} go={gov} ge={ge} flags={flags} custom={matrix is not None} maxlen={max(map(len, seqs))} "
+           f"ndev={ndev} chunks={chunks!r} own_buffers={own_buffers}")
     try:
-        with t.Context(alphabet=alphabet, gap_open=-1 if go is None else go, gap_extend=ge, matrix=matrix, flags=flags) as ctx:
+        with t.Context(alphabet=alphabet, gap_open=-1 if go is None else go, gap_extend=ge, matrix=matrix, flags=flags, n_devices=ndev) as ctx:
+            npairs = n * (n - 1) // 2
+            if own_buffers and npairs:
+                bs, bd = np.full(npairs, -7, dtype=np.int32), np.full(npairs, -7.0, dtype=np.float64)
+                ctx.set_result_buffers(bs, bd)
             ctx.set_sequences(seqs)
             ctx.run()
             s, d, st = ctx.scores(), ctx.distances(), ctx.stats()
+            if own_buffers and npairs:
+                assert (bs == s).all() and bd.tobytes() == d.tobytes(), "caller buffers " + tag
+            if ndev > 1:
+                counts["multi_device"] += 1
             if identity:
                 rs, rk, rd = o.all_pairs_id(enc, mat, gov, ge)
                 assert (ctx.identities() == rk).all(), "identities " + tag
+                if kimura:      # reached only if every pair is below D = 0.75 (else TsqError -9 above)
+                    rd = np.array([o.kimura(int(k), min(len(enc[i]), len(enc[j])))[0]
+                                   for k, (i, j) in zip(rk, ((i, j) for i in range(n) for j in range(i + 1, n)))], dtype=np.float64)
+                    counts["kimura"] += 1
             else:
                 rs, _ = o.all_pairs(enc, mat, gov, ge, nthreads=NT)
                 selfs = np.array([o.self_score(e, mat) for e in enc], dtype=np.int32)
@@ -83,7 +111,7 @@ def trial(seed, counts):
             assert d.tobytes() == rd.tobytes(), "distances " + tag
             counts["pairs"] += len(rs)
             import torch
-            ref_sorted = None if identity or n < 2 else torch.as_tensor(ctx.device_scores(), device="cuda").cpu().numpy().copy()
+            ref_sorted = None if identity or n < 2 or ndev > 1 else torch.as_tensor(ctx.device_scores(), device="cuda").cpu().numpy().copy()
             counts["cells"] += st["cells"]
             if n >= 2 and rng.random() < 0.5:
                 left, right, height = ctx.guide_tree()
@@ -113,7 +141,8 @@ def trial(seed, counts):
                     ctx.set_sequences(seqs)
                     ctx.upload(); ctx.compute(); ctx.synchronize()
                     b, e = ctx.partition()
-                    slab = torch.as_tensor(ctx.device_scores(), device="cuda")[b:e].cpu().numpy()
+                    arr, first = ctx.device_slab()          # rank 0 may hold the whole triangle, the others their slab only
+                    slab = torch.as_tensor(arr, device="cuda")[b - first:e - first].cpu().numpy() if e > b else np.zeros(0, np.int32)
                     got[b:e] = slab
                     cover[b:e] += 1
             assert (cover == 1).all(), "partition cover " + tag
@@ -132,7 +161,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=120)
     ap.add_argument("--seed", type=int, default=1)
     a = ap.parse_args()
-    counts = dict(trials=0, pairs=0, cells=0, trees=0, alignments=0, tracebacks=0, partitions=0, range_refusals=0)
+    counts = dict(trials=0, pairs=0, cells=0, trees=0, alignments=0, tracebacks=0, partitions=0, range_refusals=0, multi_device=0, kimura=0)
     t0 = time.time()
     seed = a.seed
     while time.time() - t0 < a.seconds:
