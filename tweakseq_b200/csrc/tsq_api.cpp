@@ -16,6 +16,8 @@
 #include <mutex>
 #include <numeric>
 #include <string>
+#include <condition_variable>
+#include <functional>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -225,6 +227,61 @@ struct DevView {
 
 }  // namespace
 
+struct tsq_ctx;
+
+// One persistent host thread per device of a multi-device context: upload (sort, plan, pack, H2D) and compute
+// (a dozen runtime calls per device when the results are streamed) run side by side instead of one device after
+// the other; a job is handed over with one condition-variable round trip (~10 us), not a thread start.
+struct KidPool {
+  std::vector<std::thread> threads;
+  std::mutex m;
+  std::condition_variable cv_go, cv_done;
+  std::function<int(tsq_ctx*)> job;
+  std::vector<int> rc;
+  uint64_t generation = 0;
+  size_t pending = 0;
+  bool quit = false;
+
+  explicit KidPool(std::vector<tsq_ctx*>& kids) : rc(kids.size(), TSQ_OK) {
+    for (size_t r = 0; r < kids.size(); r++)
+      threads.emplace_back([this, r, k = kids[r]]() {
+        uint64_t seen = 0;
+        for (;;) {
+          std::function<int(tsq_ctx*)> f;
+          {
+            std::unique_lock<std::mutex> lk(m);
+            cv_go.wait(lk, [&] { return quit || generation != seen; });
+            if (quit) return;
+            seen = generation;
+            f = job;
+          }
+          const int v = f(k);
+          {
+            std::lock_guard<std::mutex> lk(m);
+            rc[r] = v;
+            if (--pending == 0) cv_done.notify_one();
+          }
+        }
+      });
+  }
+  ~KidPool() {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      quit = true;
+    }
+    cv_go.notify_all();
+    for (auto& t : threads) t.join();
+  }
+  void run(std::function<int(tsq_ctx*)> f) {
+    std::unique_lock<std::mutex> lk(m);
+    job = std::move(f);
+    pending = threads.size();
+    generation++;
+    cv_go.notify_all();
+    cv_done.wait(lk, [&] { return pending == 0; });
+  }
+};
+
 struct tsq_ctx {
   tsq_params prm{};
   int nsym = 23;
@@ -329,6 +386,7 @@ struct tsq_ctx {
   bool full_sorted = true;
   // ---- multi-device (tsq_params.n_devices > 1): a LEADER owns one child context per device ------------
   std::vector<tsq_ctx*> kids;      // leader only
+  KidPool* pool = nullptr;         // leader only: one persistent host thread per device
   tsq_ctx* leader = nullptr;       // child only
   const std::vector<std::vector<uint8_t>>* encp = nullptr;   // encoded sequences: own `enc`, or the leader's
   const std::vector<int32_t>* selfp = nullptr;                // self scores: own `self_input`, or the leader's
@@ -1293,15 +1351,12 @@ int stream_chunk_out(tsq_ctx* c, const StreamChunk& ch, cudaStream_t compute_str
 template <typename F>
 int for_each_kid_parallel(tsq_ctx* c, F&& body) {
   const size_t nk = c->kids.size();
-  std::vector<int> rcs(nk, TSQ_OK);
-  std::vector<std::thread> th;
-  th.reserve(nk);
-  for (size_t r = 0; r < nk; r++) th.emplace_back([&, r]() { rcs[r] = body(c->kids[r]); });
-  for (auto& t : th) t.join();
+  if (!c->pool) c->pool = new KidPool(c->kids);
+  c->pool->run(std::function<int(tsq_ctx*)>(body));
   for (size_t r = 0; r < nk; r++)
-    if (rcs[r] != TSQ_OK) {
+    if (c->pool->rc[r] != TSQ_OK) {
       c->err = "device " + std::to_string(c->kids[r]->device) + ": " + c->kids[r]->err;
-      return rcs[r];
+      return c->pool->rc[r];
     }
   return TSQ_OK;
 }
@@ -1333,13 +1388,20 @@ int multi_upload(tsq_ctx* c) {
 }
 
 int multi_compute(tsq_ctx* c) {
-  for (tsq_ctx* k : c->kids) {   // launches are asynchronous: one thread enqueues on every device's stream
-    const int rc = tsq_compute(k);
+  // the host result must exist before the devices start streaming into it (one owner, several writers: reserve or
+  // page-lock it here, on one thread)
+  tsq_ctx* k0 = c->kids[0];
+  if (k0->stream_out && c->slab_mode && c->idshift == 0 && c->n >= 2) {
+    HostDst h;
+    const int rc = host_results(k0, !(c->prm.flags & TSQ_FLAG_NO_DISTANCES), false, &h);
     if (rc != TSQ_OK) {
-      copy_error(c, k);
+      copy_error(c, k0);
       return rc;
     }
   }
+  // every device's launches (and, when streamed, its finalize and copy-out enqueues) from its own host thread
+  const int rc = for_each_kid_parallel(c, [](tsq_ctx* k) { return tsq_compute(k); });
+  if (rc != TSQ_OK) return rc;
   c->computed = true;
   c->finalized = c->downloaded = false;
   return TSQ_OK;
@@ -1628,6 +1690,10 @@ int tsq_create(tsq_ctx** out, const tsq_params* params) {
 
 int tsq_destroy(tsq_ctx* c) {
   if (!c) return TSQ_OK;
+  if (c->pool) {
+    delete c->pool;
+    c->pool = nullptr;
+  }
   for (tsq_ctx* k : c->kids) tsq_destroy(k);
   c->kids.clear();
   cudaSetDevice(c->device);
