@@ -88,3 +88,47 @@ def test_planner_balances_cells_and_cuts_on_pair_boundaries():
     starts = [next(i for i in range(len(lens) + 1) if (i * 400 - i * (i + 1) // 2 if i < 399 else 400 * 399 // 2) >= b) for b, _ in r] + [400]
     cells = [rowcost[a:b].sum() for a, b in zip(starts[:-1], starts[1:])]
     assert max(cells) / (sum(cells) / 4) < 1.05
+
+
+def _shared_worker(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tweakseq_b200 import capi
+    from tweakseq_b200.distributed import SharedResult
+    count = n * (n - 1) // 2
+    ranges = capi.plan_partition([300] * n, world)            # fixed length: the slabs tile the FINAL triangle
+    res = SharedResult(count, want_dist=True)                 # rank 0 creates the segment, everyone maps it
+    b, e = ranges[rank]
+    res.scores[b:e] = np.arange(b, e, dtype=np.int32)         # what tsq_download does with each rank's own slab
+    res.distances[b:e] = np.arange(b, e, dtype=np.float64) * 0.5
+    res._map.flush()
+    dist.barrier()
+    if rank == 0:
+        ok = bool((res.scores == np.arange(count, dtype=np.int32)).all() and
+                  (res.distances == np.arange(count, dtype=np.float64) * 0.5).all())
+        q.put((ok, res.path, ranges))
+    dist.barrier()
+    res.close()                                               # rank 0 removes the file
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_shared_result_segment_receives_every_ranks_slab(world):
+    """The sharded result path of tweakseq_b200/distributed.py without a GPU: one host segment (a file in /dev/shm or
+    /tmp), created by rank 0 and mapped by all ranks; each rank writes only the slab the library's planner gives it;
+    after the barrier rank 0 holds the whole matrix; the segment is removed on close."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shared_worker, args=(r, world, port, 257, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ok, path, ranges = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok and not os.path.exists(path)
+    assert ranges[0][0] == 0 and ranges[-1][1] == 257 * 256 // 2
