@@ -53,3 +53,48 @@ def test_parity_block_checks_the_delivered_result_against_the_oracle():
         d2[bad] = np.nextafter(d2[bad], 2.0)
         blk = bench.parity_block(seqs, 0, s2, d2, 10, 3, 2)
         assert blk["mismatches"] == 1 and blk["distance_mismatches"] == 1
+
+
+def test_clustalo_leg_runs_the_wrappers_argv_when_a_binary_is_on_path(tmp_path, monkeypatch):
+    """with a `clustalo` on PATH the CPU-baseline leg runs the reference wrapper's argv
+    (Core/ClustalO.cpp:51) + --full --distmat-out on configs[0] and reports wall time and the rank correlation of its
+    distances with ours.  No such binary exists in the image, so a stand-in that honours exactly that argv (and
+    writes a distance matrix in clustalo's format) exercises the leg end to end; without one it reports absence."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    monkeypatch.setenv("PATH", "/nonexistent")
+    assert bench.clustalo_leg(["ACD", "ACE"], np.zeros(1)) == {"available": False, "note": "ClustalO not available in image"}
+    fake = tmp_path / "clustalo"
+    fake.write_text(f"""#!{sys.executable}
+import sys
+args = sys.argv[1:]
+assert args[:4] == ["--force", "-v", "--outfmt=fa", "--output-order=tree-order"], args      # ClustalO.cpp:51
+fin, fout = args[args.index("-i") + 1], args[args.index("-o") + 1]
+assert "--full" in args
+mat = [a.split("=", 1)[1] for a in args if a.startswith("--distmat-out=")][0]
+names, seqs = [], []
+for line in open(fin):
+    line = line.strip()
+    if line.startswith(">"):
+        names.append(line[1:].split()[0]); seqs.append("")
+    elif line:
+        seqs[-1] += line
+def d(a, b):                       # a crude composition distance: enough for a rank correlation
+    return sum(abs(a.count(c) - b.count(c)) for c in set(a + b)) / max(len(a) + len(b), 1)
+with open(mat, "w") as f:
+    f.write(f"{{len(names)}}\\n")
+    for i, n in enumerate(names):
+        f.write(n + " " + " ".join(f"{{d(seqs[i], s):.6f}}" for s in seqs) + "\\n")
+open(fout, "w").write("".join(f">{{n}}\\n{{s}}\\n" for n, s in zip(names, seqs)))
+""")
+    fake.chmod(0o755)
+    monkeypatch.setenv("PATH", str(tmp_path) + os.pathsep + os.path.dirname(sys.executable))
+    from tweakseq_b200 import synth
+    seqs = synth.protein(12, 40, 3, family=True)
+    ours = np.array([sum(abs(a.count(c) - b.count(c)) for c in set(a + b)) / (len(a) + len(b))
+                     for i, a in enumerate(seqs) for b in seqs[i + 1:]])
+    leg = bench.clustalo_leg(seqs, ours)
+    assert leg["available"] and leg["returncode"] == 0 and leg["n"] == 12 and leg["seconds"] > 0
+    assert "--full" in leg["argv"] and "--distmat-out=" in leg["argv"] and "--output-order=tree-order" in leg["argv"]
+    assert abs(leg["spearman_vs_ours"] - 1.0) < 1e-9, leg
