@@ -406,6 +406,12 @@ struct tsq_ctx {
   double* ext_dist = nullptr;
   uint64_t ext_count = 0;
   std::vector<void*> ext_registered;   // page ranges this context has page-locked
+  // partial pages at the ends of a slab in caller memory: copied into this pinned bounce block asynchronously and
+  // moved to their place by the host after the synchronize (copy_out / apply_fixups)
+  struct Fixup { void* dst; size_t off, bytes; };
+  PinnedBuf<uint8_t> bounce;
+  size_t bounce_used = 0;
+  std::vector<Fixup> fixups;
   // Device-side fault word next to the cancel flag (d_cancel[1]): a kernel that gives up on a TMA barrier
   // sets it; tsq_synchronize turns it into TSQ_ERR_CUDA.
   int* h_fault = nullptr;          // pinned landing place of its copy
@@ -995,6 +1001,7 @@ int enqueue_gotoh16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
         p.ntasks = ch.t1;
         TSQ_CUDA(c, tsq::g16_launch(c->K, grid, p, s, nullptr));
         launches++;
+        if (k + 1 == nchunks) TSQ_CUDA(c, cudaEventRecord(c->ev1, s));   // kernel_ms: the kernels, not the enqueues behind them
         const int rc = stream_chunk_out(c, ch, s, k);
         if (rc != TSQ_OK) return rc;
       }
@@ -1192,20 +1199,42 @@ int register_range(tsq_ctx* c, void* p, size_t bytes) {
   return TSQ_OK;
 }
 
-// Device -> host copy of one slab.  Into caller memory (registered as above): head partial page, whole pages,
-// tail partial page, so that no copy spans page-locked and pageable memory; into the library's own pinned
-// buffers: one copy.
-cudaError_t copy_out(const tsq_ctx* owner, void* dst, const void* src, size_t bytes, cudaStream_t s) {
+// Device -> host copy of one slab, by context c.  Into the library's own pinned buffers: one copy.  Into caller
+// memory (registered as above): the whole pages go straight to their place; the partial pages at either end (which
+// may be shared with a neighbour, so they are not page-locked, and a copy may not span page-locked and pageable
+// memory) go into c's pinned bounce block, asynchronously like everything else, and the host moves those few
+// bytes to their place after the synchronize (apply_fixups).  A pageable cudaMemcpyAsync would block the host until
+// the kernels before it have finished.
+constexpr size_t kBounceBytes = 64 * 4096;
+cudaError_t copy_out(tsq_ctx* c, const tsq_ctx* owner, void* dst, const void* src, size_t bytes, cudaStream_t s) {
   if (bytes == 0) return cudaSuccess;
   if (!owner->ext_scores) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s);
   const uintptr_t p = reinterpret_cast<uintptr_t>(dst);
   const uintptr_t a = std::min(page_up(p), p + bytes), b = std::max(page_down(p + bytes), a);
   const char* sp = static_cast<const char*>(src);
   cudaError_t e = cudaSuccess;
-  if (a > p) e = cudaMemcpyAsync(dst, sp, a - p, cudaMemcpyDeviceToHost, s);
+  auto piece = [&](uintptr_t to, const char* from, size_t n) -> cudaError_t {
+    if (n == 0) return cudaSuccess;
+    if (c->bounce.cap == 0 && c->bounce.reserve(kBounceBytes) != cudaSuccess) cudaGetLastError();
+    if (c->bounce.cap >= c->bounce_used + n) {
+      const size_t off = c->bounce_used;
+      c->bounce_used += (n + 15) & ~(size_t)15;
+      c->fixups.push_back({reinterpret_cast<void*>(to), off, n});
+      return cudaMemcpyAsync(c->bounce.p + off, from, n, cudaMemcpyDeviceToHost, s);
+    }
+    return cudaMemcpyAsync(reinterpret_cast<void*>(to), from, n, cudaMemcpyDeviceToHost, s);   // out of slots: pageable (blocks)
+  };
+  e = piece(p, sp, a - p);
   if (e == cudaSuccess && b > a) e = cudaMemcpyAsync(reinterpret_cast<void*>(a), sp + (a - p), b - a, cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess && p + bytes > b) e = cudaMemcpyAsync(reinterpret_cast<void*>(b), sp + (b - p), p + bytes - b, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = piece(b, sp + (b - p), p + bytes - b);
   return e;
+}
+
+// After the streams of c have been synchronized: the partial pages wait in the bounce block.
+void apply_fixups(tsq_ctx* c) {
+  for (const tsq_ctx::Fixup& f : c->fixups) memcpy(f.dst, c->bounce.p + f.off, f.bytes);
+  c->fixups.clear();
+  c->bounce_used = 0;
 }
 
 void unregister_all(tsq_ctx* c) {
@@ -1341,8 +1370,8 @@ int stream_chunk_out(tsq_ctx* c, const StreamChunk& ch, cudaStream_t compute_str
     c->st.launches++;
   }
   tsq_ctx* owner = result_owner(c);
-  TSQ_CUDA(c, copy_out(owner, h.scores + pb, c->d_sorted.p + (pb - first), (pe - pb) * sizeof(int32_t), c->copy_stream));
-  if (want_dist) TSQ_CUDA(c, copy_out(owner, h.dist + pb, c->d_dist.p + (pb - first), (pe - pb) * sizeof(double), c->copy_stream));
+  TSQ_CUDA(c, copy_out(c, owner, h.scores + pb, c->d_sorted.p + (pb - first), (pe - pb) * sizeof(int32_t), c->copy_stream));
+  if (want_dist) TSQ_CUDA(c, copy_out(c, owner, h.dist + pb, c->d_dist.p + (pb - first), (pe - pb) * sizeof(double), c->copy_stream));
   c->streamed_bytes += (pe - pb) * (want_dist ? 12ull : 4ull);
   return TSQ_OK;
 }
@@ -1505,9 +1534,9 @@ int multi_download(tsq_ctx* c) {
         return rc;
       }
       TSQ_CUDA(c, cudaSetDevice(k0->device));
-      TSQ_CUDA(c, copy_out(c, h.scores, k0->d_scores.p, npairs * sizeof(int32_t), k0->stream));
+      TSQ_CUDA(c, copy_out(k0, c, h.scores, k0->d_scores.p, npairs * sizeof(int32_t), k0->stream));
       if (c->idshift) TSQ_CUDA(c, cudaMemcpyAsync(h.nid, k0->d_nid.p, npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, k0->stream));
-      if (want_dist) TSQ_CUDA(c, copy_out(c, h.dist, k0->d_dist.p, npairs * sizeof(double), k0->stream));
+      if (want_dist) TSQ_CUDA(c, copy_out(k0, c, h.dist, k0->d_dist.p, npairs * sizeof(double), k0->stream));
     }
     bytes = npairs * (want_dist ? 12ull : 4ull) + (c->idshift ? npairs * 4ull : 0ull);
   }
@@ -1703,7 +1732,7 @@ int tsq_destroy(tsq_ctx* c) {
   unregister_all(c);
   c->d_dbw.release(); c->d_blob.release(); c->h_blob.release();
   c->d_sorted.release(); c->d_scores.release(); c->d_nid.release(); c->h_nid.release(); c->d_dist.release(); c->d_dist_full.release();
-  c->d_counter.release(); c->d_bnd.release(); c->h_scores.release(); c->h_dist.release();
+  c->d_counter.release(); c->d_bnd.release(); c->h_scores.release(); c->h_dist.release(); c->bounce.release();
   c->d_treeD.release(); c->d_treemin.release(); c->d_treeh.release(); c->d_treeu.release(); c->d_merges.release();
   c->d_pairs32.release(); c->d_tasks16w.release(); c->d_bnd16w.release(); c->d_bnd32.release(); c->d_smat.release();
   if (c->d_cancel) BlockCache::get().give(c->device, c->d_cancel);
@@ -1857,13 +1886,17 @@ int tsq_compute(tsq_ctx* c) {
   uint32_t launches = 0;
   c->st.launches = 0;
   c->streamed = false;
+  if (!c->fixups.empty()) {   // an earlier compute streamed into caller memory and was never waited for
+    const int rcs = tsq_synchronize(c);
+    if (rcs != TSQ_OK) return rcs;
+  }
   TSQ_CUDA(c, cudaMemsetAsync(c->d_cancel, 0, 4 * sizeof(int), s));   // cancel flag, fault word, Kimura out-of-range count
   TSQ_CUDA(c, cudaEventRecord(c->ev0, s));
   int rc = enqueue_gotoh16(c, s, launches);                 // regime 1: packed inter-task kernel
   if (rc == TSQ_OK) rc = enqueue_wave16(c, s, launches);    // regime 2: packed wavefront kernel
   if (rc == TSQ_OK) rc = enqueue_wave32(c, s, launches);    // regime 2 fallback: 32-bit wavefront kernel
   if (rc != TSQ_OK) return rc;
-  TSQ_CUDA(c, cudaEventRecord(c->ev1, s));
+  if (!c->streamed) TSQ_CUDA(c, cudaEventRecord(c->ev1, s));
   c->st.launches += launches;
   c->computed = true;
   c->finalized = c->downloaded = false;
@@ -1921,6 +1954,7 @@ int tsq_synchronize(tsq_ctx* c) {
   TSQ_CUDA(c, cudaSetDevice(c->device));
   TSQ_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->copy_stream) TSQ_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+  apply_fixups(c);
   if (c->computed) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->st.kernel_ms = ms;
@@ -1963,8 +1997,8 @@ int tsq_download(tsq_ctx* c) {
       HostDst h;
       int rc = host_results(c, want_dist, false, &h);
       if (rc != TSQ_OK) return rc;
-      TSQ_CUDA(c, copy_out(result_owner(c), h.scores + c->part_begin, c->d_sorted.p, cnt * sizeof(int32_t), s));
-      if (want_dist) TSQ_CUDA(c, copy_out(result_owner(c), h.dist + c->part_begin, c->d_dist.p, cnt * sizeof(double), s));
+      TSQ_CUDA(c, copy_out(c, result_owner(c), h.scores + c->part_begin, c->d_sorted.p, cnt * sizeof(int32_t), s));
+      if (want_dist) TSQ_CUDA(c, copy_out(c, result_owner(c), h.dist + c->part_begin, c->d_dist.p, cnt * sizeof(double), s));
       bytes = cnt * (want_dist ? 12ull : 4ull);
     }
     if (c->leader) {   // the leader synchronizes all its devices once every copy is in flight
@@ -1976,9 +2010,9 @@ int tsq_download(tsq_ctx* c) {
     int rc = host_results(c, want_dist, c->idshift != 0, &h);
     if (rc != TSQ_OK) return rc;
     const int32_t* src = (c->perm_identity && c->idshift == 0) ? c->d_sorted.p : c->d_scores.p;
-    TSQ_CUDA(c, copy_out(c, h.scores, src, npairs * sizeof(int32_t), s));
+    TSQ_CUDA(c, copy_out(c, c, h.scores, src, npairs * sizeof(int32_t), s));
     if (c->idshift) TSQ_CUDA(c, cudaMemcpyAsync(h.nid, c->d_nid.p, npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    if (want_dist) TSQ_CUDA(c, copy_out(c, h.dist, c->d_dist.p, npairs * sizeof(double), s));
+    if (want_dist) TSQ_CUDA(c, copy_out(c, c, h.dist, c->d_dist.p, npairs * sizeof(double), s));
     bytes = npairs * (want_dist ? 12ull : 4ull) + (c->idshift ? npairs * 4ull : 0ull);
   }
   int rc = tsq_synchronize(c);
