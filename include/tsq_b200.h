@@ -146,6 +146,14 @@ void tsq_default_params(tsq_params *p);
  * letters at all).  Host only; for callers that hold the residues in memory.
  */
 int tsq_detect_alphabet(const char *const *residues, const uint32_t *lengths, uint32_t n);
+/*
+ * The encoding tsq_set_sequences applies, for callers that want the symbols themselves (and for the tests
+ * that pin the vectorised encoder against the oracle): letter map of Consensus.cpp:61-69, case-insensitive;
+ * '-', '.' and whitespace dropped; any other byte -> X / N.  `out` needs room for `len` bytes; *out_len
+ * receives the number of symbols.  *self_score (may be NULL) = sum of S(x, x) under the alphabet's default
+ * matrix.  Host only, no device.  TSQ_ERR_INVALID for a bad alphabet or null pointers.
+ */
+int tsq_encode(int alphabet, const char *residues, uint64_t len, uint8_t *out, uint64_t *out_len, int64_t *self_score);
 int tsq_create(tsq_ctx **out, const tsq_params *params);
 int tsq_destroy(tsq_ctx *ctx);
 /* Last error text of this context ("" if none).  Never NULL. */
@@ -168,11 +176,14 @@ int tsq_upload(tsq_ctx *ctx);   /* sort/pack on the host, H2D */
 int tsq_compute(tsq_ctx *ctx);  /* enqueue all kernels on the context's stream (async) */
 int tsq_download(tsq_ctx *ctx); /* synchronise, D2H of scores (+ distances) */
 /*
- * Streamed results for the staged calls (tsq_run always streams): with enable != 0 a later tsq_compute sends the
- * packed kernel's tasks out in a few launches over consecutive row ranges and, behind each, finalizes those rows
- * and copies scores (+ distances) to the host on a side stream while the next launch computes -- SURVEY.md
- * section 8e's "slabs overlapped with remaining compute".  tsq_download then only waits.  Takes effect where the
- * results need no un-sort (fixed-length input, no identity keys, short sequences only); other jobs run as before.
+ * Streamed results for the staged calls (tsq_run always streams): with enable != 0 a later tsq_compute lets
+ * finished row ranges leave for the host while the packed kernel is still running -- SURVEY.md section 8e's
+ * "slabs overlapped with remaining compute".  The kernel writes the distance next to every score and counts
+ * finished tasks per row range; a side stream waits for a range's count (a stream memory operation,
+ * cuStreamWaitValue32) and copies its scores (+ distances) out: one launch, no launch boundary per range.
+ * (Without stream memory operations: a few launches over consecutive row ranges, each followed by finalize +
+ * copy-out on the side stream.)  tsq_download then only waits.  Takes effect where the results need no un-sort
+ * (fixed-length input, no identity keys, short sequences only); other jobs run as before.
  * The host destination (the library's pinned buffer, or tsq_set_result_buffers) must not change in between.
  */
 int tsq_stream_results(tsq_ctx *ctx, int enable);

@@ -5,6 +5,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 import tweakseq_b200 as t
 from tweakseq_b200 import capi
@@ -129,3 +130,34 @@ def test_distmat_writer_prints_what_printf_would(tmp_path):
     assert lab == labels and rows[3][3] == 0.0
     capi.write_distmat(str(tmp_path / "empty.dist"), [], np.zeros(0))
     assert open(tmp_path / "empty.dist").read() == "0\n"
+
+
+# ---- tsq_encode: the (vectorised) encoder of tsq_set_sequences against the oracle's ---------------------------
+@pytest.mark.parametrize("alphabet", [0, 1])
+def test_encode_matches_the_oracle_on_every_byte_and_length(alphabet, monkeypatch):
+    """encode_simd.cpp maps 32 bytes per step with two 16-entry shuffles; the oracle walks its 256-entry table.
+    Every byte value, every length around the block size, runs of dropped bytes ('-', '.', whitespace) at block
+    boundaries, and the self score S(x, x) summed on the way."""
+    from tweakseq_b200 import capi
+    from oracle import pyoracle as o
+    rng = np.random.default_rng(4100 + alphabet)
+    mat = o.matrix(alphabet)
+    letters = np.frombuffer(b"ARNDCQEGHILKMFPSTWYVBZXJOUacgtun-. \t\n\r*1", dtype=np.uint8)
+    cases = [bytes(range(256)), bytes(range(256)) * 3, b"", b"-", b"A", b"-" * 70, b"A" * 31 + b"-" + b"C" * 32 + b"." + b"G" * 33]
+    for l in list(range(0, 100)) + [127, 128, 129, 1000, 4097]:
+        cases.append(rng.choice(letters, l).tobytes())
+        cases.append(rng.integers(0, 256, l, dtype=np.uint8).tobytes())
+    for hook in (False, True):
+        if hook:
+            monkeypatch.setenv("TSQ_ENCODE_SCALAR", "1")
+        for raw in cases:
+            got, self_score = capi.encode(raw, alphabet)
+            want = o.encode(raw, alphabet)
+            assert got.tobytes() == want.tobytes(), raw[:80]
+            assert self_score == o.self_score(want, mat)
+
+
+def test_encode_rejects_bad_arguments():
+    from tweakseq_b200 import capi
+    with pytest.raises(capi.TsqError):
+        capi.encode(b"ACGT", 7)

@@ -255,12 +255,18 @@ def test_ragged_ranks_still_gather_into_rank_0():
 
 
 # ---- streamed results: row ranges leave for the host behind the launch that computed them --------------------------
-@pytest.mark.parametrize("chunks", ["1", "3", "8"])
+@pytest.mark.parametrize("chunks", ["1", "3", "8", "16"])
 @pytest.mark.parametrize("dist", [True, False])
-def test_streamed_results_equal_the_plain_ones(chunks, dist, monkeypatch):
-    """tsq_stream_results: the packed kernel's tasks in `chunks` launches over consecutive row ranges, each followed
-    on a side stream by finalize + copy-out of those rows (TSQ_STREAM_CHUNKS forces the split on a small job)."""
+@pytest.mark.parametrize("by", ["counters", "launches"])
+def test_streamed_results_equal_the_plain_ones(chunks, dist, by, monkeypatch):
+    """tsq_stream_results, both flavours.  "counters" (the default): ONE launch; the kernel writes the distances itself
+    and ticks a counter per row range at the end of every task, the copy stream waits for a range's count
+    (cuStreamWaitValue32) and copies it out while the launch runs on.  "launches" (TSQ_STREAM_LAUNCHES, the fallback
+    without stream memory operations): the tasks in `chunks` launches over consecutive row ranges, each followed on the
+    side stream by finalize + copy-out of those rows.  TSQ_STREAM_CHUNKS forces the split on a small job."""
     monkeypatch.setenv("TSQ_STREAM_CHUNKS", chunks)
+    if by == "launches":
+        monkeypatch.setenv("TSQ_STREAM_LAUNCHES", "1")
     _, seqs = synth.config(2, 0.45)                     # 450 x 300 aa; also an odd row count below
     seqs = seqs[:449]
     rs, rd, _, _ = oracle_run(seqs)
@@ -276,7 +282,8 @@ def test_streamed_results_equal_the_plain_ones(chunks, dist, monkeypatch):
             if dist:
                 assert ctx.distances().tobytes() == rd.tobytes()
         st = ctx.stats()
-        assert st["launches"] >= int(chunks) and st["d2h_bytes"] == len(rs) * (12 if dist else 4)
+        assert st["d2h_bytes"] == len(rs) * (12 if dist else 4)
+        assert st["launches"] == 1 if by == "counters" else st["launches"] >= min(int(chunks), 8)
         if dist:
             tree = ctx.guide_tree()                     # the main stream sees the side stream's distances
             assert len(tree[0]) == len(seqs) - 1

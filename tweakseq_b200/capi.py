@@ -73,7 +73,7 @@ SYMBOLS = ["tsq_version", "tsq_version_string", "tsq_status_string", "tsq_device
            "tsq_self_scores", "tsq_identities", "tsq_device_scores", "tsq_partition", "tsq_finalize", "tsq_device_results",
            "tsq_get_stats", "tsq_measure_dpx_rate", "tsq_run_fasta", "tsq_plan_partition", "tsq_guide_tree",
            "tsq_write_newick", "tsq_consensus", "tsq_align_pair", "tsq_partition_of", "tsq_msa", "tsq_write_msa_fasta", "tsq_write_distmat",
-           "tsq_device_slab", "tsq_results_sharded", "tsq_set_result_buffers", "tsq_get_device_stats", "tsq_get_limits", "tsq_measure_pipe_rates", "tsq_detect_alphabet", "tsq_stream_results"]
+           "tsq_device_slab", "tsq_results_sharded", "tsq_set_result_buffers", "tsq_get_device_stats", "tsq_get_limits", "tsq_measure_pipe_rates", "tsq_detect_alphabet", "tsq_stream_results", "tsq_encode"]
 
 _lib = None
 
@@ -127,6 +127,7 @@ def load_library():
     L.tsq_get_device_stats.argtypes = [vp, C.c_int32, C.POINTER(Stats)]
     L.tsq_get_limits.argtypes = [vp, C.POINTER(Limits)]
     L.tsq_detect_alphabet.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), C.c_uint32]
+    L.tsq_encode.argtypes = [C.c_int, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
     L.tsq_measure_pipe_rates.argtypes = [vp, C.POINTER(PipeRates)]
     L.tsq_device_slab.argtypes = [vp, C.POINTER(vp), u64p, u64p]
     L.tsq_results_sharded.argtypes = [vp, C.POINTER(C.c_int)]
@@ -168,6 +169,19 @@ def detect_alphabet(seqs) -> int:
     arr = (C.c_char_p * max(len(raw), 1))(*raw) if raw else (C.c_char_p * 1)()
     lens = (C.c_uint32 * max(len(raw), 1))(*[len(r) for r in raw]) if raw else (C.c_uint32 * 1)()
     return L.tsq_detect_alphabet(arr, lens, len(raw))
+
+
+def encode(seq, alphabet: int = PROTEIN) -> tuple[np.ndarray, int]:
+    """tsq_encode(): the symbols tsq_set_sequences would store for `seq`, and the sum of S(x, x) under the
+    alphabet's default matrix (host only)."""
+    L = load_library()
+    raw = seq.encode("latin-1", "replace") if isinstance(seq, str) else bytes(seq)
+    out = np.empty(max(len(raw), 1), dtype=np.uint8)
+    n, self_score = C.c_uint64(0), C.c_int64(0)
+    rc = L.tsq_encode(alphabet, raw, len(raw), out.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(n), C.byref(self_score))
+    if rc != 0:
+        raise TsqError(rc, "tsq_encode")
+    return out[:n.value].copy(), int(self_score.value)
 
 
 def plan_partition(lengths, world: int, **kw) -> list[tuple[int, int]]:

@@ -39,6 +39,8 @@
 
 namespace tsq {
 
+constexpr int kG16MaxRanges = 16;
+
 struct G16Params {
   const uint32_t* dbw;         // subject residues, 32-way interleaved, 2 rows per word as 16-bit
                                // profile-row byte offsets (letter * STRIDE * 4), see the row loop
@@ -64,6 +66,14 @@ struct G16Params {
   int32_t gep;                 // ge' = ge - delta
   uint32_t negge2;             // (-ge' mod 2^16) in both halves
   uint32_t goe2;               // goe' * 0x10001 (mod 2^32)
+  // ---- results that leave while the launch is still running (tsq_stream_results, sorted order = final order) ----
+  const int32_t* self;         // self scores S(x, x), sorted order
+  double* out_dist;            // != nullptr: the distance 1 - S / min(S_ii, S_jj) goes out next to every score
+                               //   (what finalize_kernel would compute from it afterwards, operation for operation)
+  unsigned int* done;          // != nullptr: done[k] counts the finished tasks of row range k; a copy stream waits
+                               //   for done[k] == its task count (stream memory operation) and copies the range out
+  uint32_t nranges;
+  unsigned long long range_end[kG16MaxRanges];   // tasks [range_end[k-1], range_end[k]) belong to range k
 };
 
 __device__ __forceinline__ unsigned long long tri_index(unsigned long long i, unsigned long long j,
@@ -75,6 +85,38 @@ template <int K>
 struct G16Cfg {
   static constexpr int STRIDE = ((K + 31) & ~31) + 1;  // == 1 (mod 32)
 };
+
+// End of a task: the two scores of every lane, un-biased; when the results are streamed (tsq_stream_results) also
+// their distances and the task's tick in its row range's counter.  Not inlined: once per task, and its temporaries
+// stay out of the row loop's register allocation.
+static __device__ __noinline__ void g16_task_results(const G16Params& p, unsigned long long task, int lane, bool valid, uint32_t A1,
+                                              uint32_t j, uint32_t L1, uint32_t L2, uint32_t Ls, uint32_t res1, uint32_t res2) {
+  const uint32_t A2 = A1 + 1;
+  if (valid) {
+    const int32_t base = -(int32_t)p.bias - p.delta * (int32_t)Ls;
+    const int32_t s1 = (int32_t)res1 + base - p.delta * (int32_t)L1;
+    const int32_t s2 = (int32_t)res2 + base - p.delta * (int32_t)L2;
+    const unsigned long long i1 = tri_index(A1, j, p.n_total), i2 = tri_index(A2, j, p.n_total);
+    p.out[i1] = s1;
+    if (j > A2) p.out[i2] = s2;
+    if (p.out_dist) {   // finalize_kernel's distance (tsq_device.cu), here because the rows leave before the launch ends
+      const int32_t sj = p.self[j], sa = p.self[A1], sb = p.self[A2];
+      const int32_t m1 = sa < sj ? sa : sj, m2 = sb < sj ? sb : sj;
+      p.out_dist[i1] = m1 > 0 ? __dsub_rn(1.0, __ddiv_rn((double)s1, (double)m1)) : 1.0;
+      if (j > A2) p.out_dist[i2] = m2 > 0 ? __dsub_rn(1.0, __ddiv_rn((double)s2, (double)m2)) : 1.0;
+    }
+  }
+  if (p.done) {
+    // every lane's results are visible device-wide before lane 0 counts the task as finished
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+      uint32_t k = 0;
+      while (k + 1 < p.nranges && task >= p.range_end[k]) ++k;
+      atomicAdd(p.done + k, 1u);
+    }
+  }
+}
 
 // NGE != 0: -ge' (both halves) is the compile-time constant NGE, so the two VIADDMNMX of a cell
 // take it as an immediate (one register read less each); NGE == 0: taken from the parameters.
@@ -273,11 +315,7 @@ __global__ void __launch_bounds__(TPB, MINB) gotoh16_kernel(const __grid_constan
       }
     }
 
-    if (valid) {
-      const int32_t base = -(int32_t)p.bias - p.delta * (int32_t)Ls;
-      p.out[tri_index(A1, j, p.n_total)] = (int32_t)res1 + base - p.delta * (int32_t)L1;
-      if (j > A2) p.out[tri_index(A2, j, p.n_total)] = (int32_t)res2 + base - p.delta * (int32_t)L2;
-    }
+    g16_task_results(p, task, lane, valid, A1, j, L1, L2, Ls, res1, res2);
   }
 }
 

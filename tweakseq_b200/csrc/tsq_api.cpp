@@ -22,10 +22,12 @@
 #include <unordered_map>
 #include <vector>
 
+#include <cuda.h>   // types of the one driver entry point resolved at run time (no link dependency)
 #include <cuda_runtime.h>
 
 #include "../../include/tsq_b200.h"
 #include "tsq_device.h"
+#include "encode_simd.h"
 #include "msa_host.h"
 
 namespace {
@@ -312,7 +314,7 @@ struct tsq_ctx {
   size_t lin_size = 0;                    // residue part of the blob
   size_t blob_size = 0;                   // bytes in use
   std::vector<int32_t> self_input;        // self scores, submitted order (computed while encoding)
-  int32_t diag_by_byte[256] = {};         // input byte -> S(x, x) of its symbol (0 for dropped bytes)
+  tsq::EncodeTables enct = {};            // input byte -> symbol and S(x, x) of its symbol (encode_simd.h)
   size_t dbw_size = 0;                    // interleaved subject database: words (built on the device)
   uint32_t db_scale = 0;                  // letter -> profile-row byte offset factor (STRIDE(K) * 4)
   std::vector<uint32_t> goff;             // group offsets
@@ -401,6 +403,7 @@ struct tsq_ctx {
   std::vector<cudaEvent_t> chunk_ev;
   unsigned long long* h_starts = nullptr;   // pinned: first task of every chunk (the kernel's cursor is set from it)
   uint64_t streamed_bytes = 0;
+  DevBuf<unsigned int> d_done;             // per row range: finished tasks of the running packed-kernel launch
   // ---- caller-owned host result buffers (tsq_set_result_buffers) ---------------------------------------
   int32_t* ext_scores = nullptr;
   double* ext_dist = nullptr;
@@ -472,23 +475,6 @@ struct EncodeLut {
   }
 };
 const EncodeLut kLut;
-
-// Encodes one sequence (dropping gap / whitespace bytes) and returns its self score sum S(x, x).
-int64_t encode_into(int alphabet, const int32_t* diag_by_byte, const char* s, size_t len, std::vector<uint8_t>& out) {
-  const uint8_t* lut = alphabet == TSQ_NUCLEOTIDE ? kLut.nuc : kLut.prot;
-  out.resize(len);
-  size_t k = 0;
-  int64_t self = 0;
-  for (size_t i = 0; i < len; i++) {
-    const unsigned char ch = (unsigned char)s[i];
-    const uint8_t v = lut[ch];
-    out[k] = v;
-    k += (v != 0xff);
-    self += diag_by_byte[ch];
-  }
-  out.resize(k);
-  return self;
-}
 
 // Packed-16 range analysis.  Values live as v + delta*(i+j) + BIAS in
 // an unsigned 16-bit half; this returns BIAS and the largest padded length that stays inside
@@ -571,10 +557,30 @@ namespace {
 int host_sort_and_pack(tsq_ctx* c) {
   const uint32_t n = c->n;
   // ---- stable length sort ---------------------------------------------------------------
+  // (keys = length << 32 | input index: an ordinary sort of them is the stable length sort; input that is
+  //  already in order -- every fixed-length workload -- is recognised in one pass)
   c->perm.resize(n);
-  std::iota(c->perm.begin(), c->perm.end(), 0u);
-  std::stable_sort(c->perm.begin(), c->perm.end(),
-                   [&](uint32_t a, uint32_t b) { return (*c->encp)[a].size() < (*c->encp)[b].size(); });
+  {
+    bool ordered = true;
+    size_t prev = 0;
+    for (uint32_t i = 0; i < n && ordered; i++) {
+      const size_t l = (*c->encp)[i].size();
+      ordered = l >= prev;
+      prev = l;
+    }
+    if (ordered) {
+      std::iota(c->perm.begin(), c->perm.end(), 0u);
+    } else {
+      std::vector<uint64_t> keys(n);
+      for (uint32_t i = 0; i < n; i++) {
+        const size_t l = (*c->encp)[i].size();
+        if (l > 0x7fffffffu) return fail(c, TSQ_ERR_RANGE, "sequence too long");
+        keys[i] = ((uint64_t)l << 32) | i;
+      }
+      std::sort(keys.begin(), keys.end());
+      for (uint32_t i = 0; i < n; i++) c->perm[i] = (uint32_t)keys[i];
+    }
+  }
   c->lens.resize(n);
   c->loff.resize(n + 1);
   uint64_t total = 0;
@@ -737,16 +743,22 @@ int host_plan_work(tsq_ctx* c) {
   // A strip of K columns costs about K + 2.5 cell-times per row (the row's letter fetch, boundary
   // load/store and loop control are worth ~2.5 cells: profiles/ r01 sweep), padding included.
   {
+    // (tasks per distinct query length first: a fixed-length workload is one run, and the estimate below costs a
+    //  division per run and variant instead of one per query pair and variant)
+    std::vector<std::pair<uint32_t, double>> runs;
+    for (uint32_t r = 0; r < nq; r++) {
+      const uint32_t q = c->q_end - 1 - r;
+      const uint32_t l2 = c->lens[c->use_g32 ? lo + q : lo + 2 * q + 1];
+      const double nt = (double)(c->task_prefix[r + 1] - c->task_prefix[r]);
+      if (!runs.empty() && runs.back().first == l2) runs.back().second += nt;
+      else runs.emplace_back(l2, nt);
+    }
     double best = 1e300;
     int bestK = tsq::kStripWidths[0];
     for (int v = 0; v < tsq::kNumStripWidths; v++) {
       const int K = tsq::kStripWidths[v];
       double work = 0;
-      for (uint32_t r = 0; r < nq; r++) {
-        const uint32_t q = c->q_end - 1 - r;
-        const uint32_t l2 = c->lens[c->use_g32 ? lo + q : lo + 2 * q + 1];
-        work += (double)((l2 + K - 1) / K) * (K + 2.5) * (double)(c->task_prefix[r + 1] - c->task_prefix[r]);
-      }
+      for (const auto& run : runs) work += (double)((run.first + K - 1) / K) * (K + 2.5) * run.second;
       if (K <= 32) work *= 1.05;  // the 16-warp variants run ~4-5 % slower per cell (r01 sweep)
       if (work < best * 0.999 || (work <= best * 1.001 && K > bestK)) {
         if (work < best) best = work;
@@ -861,7 +873,8 @@ int device_upload(tsq_ctx* c) {
     if (!c->pairs32.empty())
       TSQ_CUDA(c, cudaMemcpyAsync(c->d_pairs32.p, c->pairs32.data(), c->pairs32.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
   }
-  TSQ_CUDA(c, cudaStreamSynchronize(s));
+  // no host wait here: the kernels of tsq_compute queue up behind the copy on the same stream, and the next
+  // tsq_upload waits for the stream before it touches the staging blob again
   c->st.h2d_bytes = c->blob_size + c->tasks16w.size() * sizeof(uint4) + c->pairs32.size() * sizeof(uint2) +
                     ((!c->pairs32.empty() || c->use_g32) ? c->smat_k.size() * 4 : 0);
   return TSQ_OK;
@@ -876,6 +889,24 @@ struct StreamChunk {   // one launch of a streamed compute: tasks [t0, t1) = sor
   uint32_t row0, row1;
 };
 int stream_chunk_out(tsq_ctx* c, const StreamChunk& ch, cudaStream_t compute_stream, size_t index);   // defined below
+int stream_ranges_out(tsq_ctx* c, const std::vector<StreamChunk>& ranges);                            // defined below
+
+// cuStreamWaitValue32, resolved through the runtime (the library does not link libcuda): lets the copy stream wait
+// for a counter the RUNNING kernel advances, so that row ranges leave without cutting the launch into pieces.
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamWaitValue32Fn stream_wait_value32() {
+  static const StreamWaitValue32Fn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      f = nullptr;
+    }
+    return reinterpret_cast<StreamWaitValue32Fn>(f);
+  }();
+  return fn;
+}
+constexpr unsigned kDoneSlots = 32;
 
 // Whether the results of this job can leave in row-range chunks: the packed kernel only, scores in place
 // (sorted order = submitted order, no identity keys), the whole triangle or a sharded slab.
@@ -972,9 +1003,58 @@ int enqueue_gotoh16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
       if (const char* e = getenv("TSQ_STREAM_CHUNKS")) nchunks = (size_t)std::min(8, std::max(1, atoi(e)));   // tests: force a split
       if (nchunks > nq) nchunks = std::max<size_t>(nq, 1);
     }
+    const bool by_counters = can_stream(c) && stream_wait_value32() != nullptr && getenv("TSQ_STREAM_LAUNCHES") == nullptr;
     if (nchunks == 1 && !can_stream(c)) {
       TSQ_CUDA(c, tsq::g16_launch(c->K, grid, p, s, nullptr));
       launches++;
+    } else if (by_counters) {
+      // ---- ONE launch; row ranges leave as their tasks finish -----------------------------------------------
+      // The kernel writes the distance next to every score and ticks its row range's counter at the end of a
+      // task; the copy stream waits for a range's count (stream memory operation) and copies the range out while
+      // the same launch works on the next rows.  No launch boundary, so no partly filled wave per range, and
+      // short jobs (configs[1]: 4.4 waves) stream too.
+      const bool want_dist = !(c->prm.flags & TSQ_FLAG_NO_DISTANCES);
+      const uint64_t n = c->n, npairs = n < 2 ? 0 : n * (n - 1) / 2;
+      const uint64_t first = c->full_sorted ? 0 : c->part_begin;
+      const uint64_t out_bytes = c->pairs_part * (want_dist ? 12ull : 4ull);
+      size_t nr = (size_t)std::min<uint64_t>(tsq::kG16MaxRanges, std::max<uint64_t>(1, out_bytes / (384u << 10)));
+      if (const char* e = getenv("TSQ_STREAM_CHUNKS")) nr = (size_t)std::min(tsq::kG16MaxRanges, std::max(1, atoi(e)));
+      if (nr > nq) nr = std::max<size_t>(nq, 1);
+      if (c->chunk_ev.empty()) {
+        c->chunk_ev.resize(1, nullptr);
+        TSQ_CUDA(c, cudaEventCreateWithFlags(&c->chunk_ev[0], cudaEventDisableTiming));
+      }
+      if (!c->copy_stream) TSQ_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+      TSQ_CUDA(c, c->d_done.reserve(kDoneSlots));
+      if (want_dist) {
+        TSQ_CUDA(c, c->d_dist.reserve(c->full_sorted ? npairs : c->part_end - c->part_begin));
+        p.self = c->d_self.p;
+        p.out_dist = biased(c->d_dist.p, first);
+      }
+      p.done = c->d_done.p;
+      p.nranges = (uint32_t)nr;
+      std::vector<StreamChunk> ranges(nr);
+      for (size_t k = 0; k < nr; k++) {
+        const uint32_t r0 = (uint32_t)((unsigned long long)nq * k / nr), r1 = (uint32_t)((unsigned long long)nq * (k + 1) / nr);
+        StreamChunk& ch = ranges[k];
+        ch.t0 = c->task_prefix[r0];
+        ch.t1 = c->task_prefix[r1];
+        ch.row0 = c->lo + 2 * (c->q_end - r1);           // query pairs q_end-r1 .. q_end-1-r0
+        ch.row1 = c->lo + 2 * (c->q_end - r0);
+        if (k + 1 == nr) ch.row0 = std::min(ch.row0, c->row_a);
+        if (k == 0) ch.row1 = std::max(ch.row1, std::min(c->row_b, c->n));
+        p.range_end[k] = ch.t1;
+      }
+      // the copies of an earlier streamed compute read these counters: they must be through before the reset
+      TSQ_CUDA(c, cudaStreamWaitEvent(s, c->fin_ev, 0));
+      TSQ_CUDA(c, cudaMemsetAsync(c->d_done.p, 0, kDoneSlots * sizeof(unsigned int), s));
+      TSQ_CUDA(c, cudaEventRecord(c->chunk_ev[0], s));
+      TSQ_CUDA(c, tsq::g16_launch(c->K, grid, p, s, nullptr));
+      launches++;
+      TSQ_CUDA(c, cudaEventRecord(c->ev1, s));
+      const int rcs = stream_ranges_out(c, ranges);
+      if (rcs != TSQ_OK) return rcs;
+      c->streamed = true;
     } else {
       // chunk k = task rows r in [r_k, r_k+1): tasks [prefix[r_k], prefix[r_k+1]), i.e. query pairs
       // q_end-1-r, which are consecutive sorted rows -- long queries first, as the task order has it
@@ -1376,6 +1456,36 @@ int stream_chunk_out(tsq_ctx* c, const StreamChunk& ch, cudaStream_t compute_str
   return TSQ_OK;
 }
 
+// Counter-driven flavour (one launch, enqueue_gotoh16): behind the event that says "counters zeroed", the copy stream
+// waits for each row range's task count and copies the range -- scores and the distances the kernel wrote -- out.
+int stream_ranges_out(tsq_ctx* c, const std::vector<StreamChunk>& ranges) {
+  const bool want_dist = !(c->prm.flags & TSQ_FLAG_NO_DISTANCES);
+  const uint64_t n = c->n, npairs = n < 2 ? 0 : n * (n - 1) / 2;
+  const uint64_t first = c->full_sorted ? 0 : c->part_begin;
+  const size_t nr = ranges.size();
+  HostDst h;
+  const int rch = host_results(c, want_dist, false, &h);
+  if (rch != TSQ_OK) return rch;
+  TSQ_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->chunk_ev[0], 0));   // counters zeroed (not: kernel finished)
+  tsq_ctx* owner = result_owner(c);
+  auto start_of = [&](uint32_t row) -> uint64_t { return (n >= 2 && (uint64_t)row + 1 < n) ? tri(row, row + 1, n) : npairs; };
+  c->streamed_bytes = 0;
+  for (size_t k = 0; k < nr; k++) {
+    const StreamChunk& ch = ranges[k];
+    const uint64_t pb = start_of(ch.row0), pe = start_of(ch.row1);
+    if (ch.t1 > ch.t0) {
+      const CUresult wr = stream_wait_value32()((CUstream)c->copy_stream, (CUdeviceptr)(uintptr_t)(c->d_done.p + k),
+                                                (cuuint32_t)(ch.t1 - ch.t0), CU_STREAM_WAIT_VALUE_GEQ);
+      if (wr != CUDA_SUCCESS) return fail(c, TSQ_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)wr);
+    }
+    if (pe <= pb) continue;
+    TSQ_CUDA(c, copy_out(c, owner, h.scores + pb, c->d_sorted.p + (pb - first), (pe - pb) * sizeof(int32_t), c->copy_stream));
+    if (want_dist) TSQ_CUDA(c, copy_out(c, owner, h.dist + pb, c->d_dist.p + (pb - first), (pe - pb) * sizeof(double), c->copy_stream));
+    c->streamed_bytes += (pe - pb) * (want_dist ? 12ull : 4ull);
+  }
+  return TSQ_OK;
+}
+
 // ---- multi-device leader: every entry point fans out to the per-device children ----------------------------
 template <typename F>
 int for_each_kid_parallel(tsq_ctx* c, F&& body) {
@@ -1588,6 +1698,31 @@ int tsq_detect_alphabet(const char* const* residues, const uint32_t* lengths, ui
   return (letters > 0 && nuc * 10 >= letters * 9) ? TSQ_NUCLEOTIDE : TSQ_PROTEIN;
 }
 
+int tsq_encode(int alphabet, const char* residues, uint64_t len, uint8_t* out, uint64_t* out_len, int64_t* self_score) {
+  if ((alphabet != TSQ_PROTEIN && alphabet != TSQ_NUCLEOTIDE) || !out_len || (len > 0 && (!residues || !out))) return TSQ_ERR_INVALID;
+  static const tsq::EncodeTables* const tabs = [] {   // default matrices; built once, thread-safe
+    static tsq::EncodeTables t[2];
+    for (int a = 0; a < 2; a++) {
+      const uint8_t* lut = a == TSQ_NUCLEOTIDE ? kLut.nuc : kLut.prot;
+      const int nsym = a == TSQ_NUCLEOTIDE ? 5 : 23;
+      const int8_t* m = a == TSQ_NUCLEOTIDE ? kDna : kBlosum62;
+      for (int b = 0; b < 256; b++) {
+        t[a].lut[b] = lut[b];
+        t[a].diag_by_byte[b] = lut[b] == 0xff ? 0 : m[lut[b] * (nsym + 1)];
+      }
+      tsq::encode_tables_finish(&t[a]);
+    }
+    return t;
+  }();
+  int64_t self = 0;
+  // (stores of the vector path stay inside out[0, len): a block is written at or before where it was read)
+  const bool scalar = getenv("TSQ_ENCODE_SCALAR") != nullptr;   // test hook: the table loop
+  *out_len = scalar ? tsq::encode_residues_scalar(tabs[alphabet], residues, (size_t)len, out, &self)
+                    : tsq::encode_residues(tabs[alphabet], residues, (size_t)len, out, &self);
+  if (self_score) *self_score = self;
+  return TSQ_OK;
+}
+
 int tsq_create(tsq_ctx** out, const tsq_params* params) {
   if (!out) return TSQ_ERR_INVALID;
   *out = nullptr;
@@ -1656,7 +1791,11 @@ int tsq_create(tsq_ctx** out, const tsq_params* params) {
   c->delta = c->smin < 0 ? (-c->smin + 1) / 2 : 0;
   {
     const uint8_t* lut = p.alphabet == TSQ_NUCLEOTIDE ? kLut.nuc : kLut.prot;
-    for (int b = 0; b < 256; b++) c->diag_by_byte[b] = lut[b] == 0xff ? 0 : c->matrix[lut[b] * (nsym + 1)];
+    for (int b = 0; b < 256; b++) {
+      c->enct.lut[b] = lut[b];
+      c->enct.diag_by_byte[b] = lut[b] == 0xff ? 0 : c->matrix[lut[b] * (nsym + 1)];
+    }
+    tsq::encode_tables_finish(&c->enct);
   }
   c->max_len16 = (p.flags & TSQ_FLAG_FORCE_S32) ? 0 : max_len16_of(c);
   if (p.n_devices > 1) {
@@ -1732,7 +1871,7 @@ int tsq_destroy(tsq_ctx* c) {
   unregister_all(c);
   c->d_dbw.release(); c->d_blob.release(); c->h_blob.release();
   c->d_sorted.release(); c->d_scores.release(); c->d_nid.release(); c->h_nid.release(); c->d_dist.release(); c->d_dist_full.release();
-  c->d_counter.release(); c->d_bnd.release(); c->h_scores.release(); c->h_dist.release(); c->bounce.release();
+  c->d_counter.release(); c->d_done.release(); c->d_bnd.release(); c->h_scores.release(); c->h_dist.release(); c->bounce.release();
   c->d_treeD.release(); c->d_treemin.release(); c->d_treeh.release(); c->d_treeu.release(); c->d_merges.release();
   c->d_pairs32.release(); c->d_tasks16w.release(); c->d_bnd16w.release(); c->d_bnd32.release(); c->d_smat.release();
   if (c->d_cancel) BlockCache::get().give(c->device, c->d_cancel);
@@ -1760,7 +1899,12 @@ const char* tsq_last_error(const tsq_ctx* c) { return c ? c->err.c_str() : "null
 int tsq_set_stream(tsq_ctx* c, void* s) {
   if (!c) return TSQ_ERR_INVALID;
   if (!c->kids.empty()) return fail(c, TSQ_ERR_INVALID, "a multi-device context runs on its own per-device streams");
-  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  cudaStream_t ns = s ? (cudaStream_t)s : c->own_stream;
+  if (ns != c->stream && c->stream) {   // work queued on the old stream (an upload's copies) is not ordered before the new one
+    TSQ_CUDA(c, cudaSetDevice(c->device));
+    TSQ_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  c->stream = ns;
   return TSQ_OK;
 }
 
@@ -1774,15 +1918,22 @@ namespace {
 template <typename Get>
 void encode_all(tsq_ctx* c, uint32_t n, uint64_t total_bytes, Get&& get) {
   auto work = [&](uint32_t a, uint32_t b) {
+    std::vector<tsq::EncodeJob> jobs(b - a);
     for (uint32_t i = a; i < b; i++) {
       const char* p = nullptr;
       size_t len = 0;
       get(i, &p, &len);
-      c->self_input[i] = (int32_t)encode_into(c->prm.alphabet, c->diag_by_byte, p, len, c->enc[i]);
+      if (c->enc[i].size() < len) c->enc[i].resize(len);
+      jobs[i - a] = tsq::EncodeJob{p, len, c->enc[i].data(), 0, 0};
+    }
+    tsq::encode_many(c->enct, jobs.data(), jobs.size());   // gap stripping, letter map, S(x, x): 32 bytes per step
+    for (uint32_t i = a; i < b; i++) {
+      c->enc[i].resize(jobs[i - a].out_len);
+      c->self_input[i] = (int32_t)jobs[i - a].self;
     }
   };
   const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-  unsigned nt = total_bytes >= (256u << 10) ? std::min<unsigned>({4u, hw, n}) : 1u;
+  unsigned nt = total_bytes >= (2u << 20) ? std::min<unsigned>({4u, hw, n}) : 1u;   // ~0.1 ms per MB on one thread
   if (nt <= 1) {
     work(0, n);
     return;
@@ -1866,6 +2017,9 @@ int tsq_upload(tsq_ctx* c) {
   if (!c->kids.empty()) return multi_upload(c);
   const double t0 = now_ms();
   TSQ_CUDA(c, cudaSetDevice(c->device));
+  // an earlier job may still be reading the staging blob or the device buffers this call re-uses (or returns to the
+  // block cache when they grow): wait for it; free when the stream is idle
+  TSQ_CUDA(c, cudaStreamSynchronize(c->stream));
   int rc = host_sort_and_pack(c);
   if (rc == TSQ_OK) rc = host_plan_work(c);
   if (rc == TSQ_OK) rc = host_build_subject_db(c);
@@ -2056,6 +2210,13 @@ int tsq_run(tsq_ctx* c, tsq_progress_cb cb, void* user, volatile int* cancel) {
       for (tsq_ctx* k : devs) {
         cudaStreamSynchronize(k->cancel_stream);
         cudaStreamSynchronize(k->stream);
+        if (k->d_done.p && k->copy_stream) {
+          // row ranges whose tasks were never fetched: let the copy stream's waits pass (the results are discarded)
+          cudaMemsetAsync(k->d_done.p, 0x7f, kDoneSlots * sizeof(unsigned int), k->cancel_stream);
+          cudaStreamSynchronize(k->cancel_stream);
+          cudaStreamSynchronize(k->copy_stream);
+          apply_fixups(k);
+        }
         k->computed = false;
       }
       c->computed = false;
