@@ -4,6 +4,7 @@ slab.  Rank 0 must end up with exactly the single-process matrix."""
 import os
 import socket
 import sys
+import time
 
 import numpy as np
 import pytest
@@ -101,13 +102,21 @@ def _shared_worker(rank, world, port, n, q):
     ranges = capi.plan_partition([300] * n, world)            # fixed length: the slabs tile the FINAL triangle
     res = SharedResult(count, want_dist=True)                 # rank 0 creates the segment, everyone maps it
     b, e = ranges[rank]
-    res.scores[b:e] = np.arange(b, e, dtype=np.int32)         # what tsq_download does with each rank's own slab
-    res.distances[b:e] = np.arange(b, e, dtype=np.float64) * 0.5
-    res._map.flush()
-    dist.barrier()
+    ok = True
+    for epoch in (1, 2):                                      # two jobs through the same segment
+        if rank == world - 1:
+            time.sleep(0.2)                                   # a late rank: rank 0 must wait for its mark
+        res.scores[b:e] = np.arange(b, e, dtype=np.int32) * epoch   # what tsq_download does with each rank's own slab
+        res.distances[b:e] = np.arange(b, e, dtype=np.float64) * 0.5 * epoch
+        res.arrive(rank, epoch)                               # ShardedRun.finish: a mark in the segment, no collective
+        if rank == 0:
+            res.wait_all(epoch)
+            ok = ok and bool((res.scores == np.arange(count, dtype=np.int32) * epoch).all() and
+                             (res.distances == np.arange(count, dtype=np.float64) * 0.5 * epoch).all())
+        dist.barrier()                                        # (the caller's own step boundary)
     if rank == 0:
-        ok = bool((res.scores == np.arange(count, dtype=np.int32)).all() and
-                  (res.distances == np.arange(count, dtype=np.float64) * 0.5).all())
+        with pytest.raises(RuntimeError):
+            res.wait_all(3, timeout_s=0.05)                   # nobody arrives at job 3: an error, not a hang
         q.put((ok, res.path, ranges))
     dist.barrier()
     res.close()                                               # rank 0 removes the file

@@ -20,6 +20,7 @@ library's device buffer.
 from __future__ import annotations
 
 import os
+import time
 import uuid
 
 import numpy as np
@@ -61,8 +62,11 @@ class SharedResult:
 
     def __init__(self, count: int, want_dist: bool, group=None):
         rank = dist.get_rank(group) if dist.is_initialized() else 0
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        # layout: scores | distances | one page of arrival flags (int64 per rank), each part page-aligned
         off_d = (count * 4 + 4095) & ~4095
-        size = max(off_d + (count * 8 if want_dist else 0), 4096)
+        off_f = (off_d + (count * 8 if want_dist else 0) + 4095) & ~4095
+        size = off_f + max(4096, (world * 8 + 4095) & ~4095)
         name = [None]
         if rank == 0:
             # /dev/shm when it has the room (a container's default is small: a page touched beyond it is a SIGBUS,
@@ -87,10 +91,25 @@ class SharedResult:
         self._map = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(size,))
         self.scores = self._map[:count * 4].view(np.int32)
         self.distances = self._map[off_d:off_d + count * 8].view(np.float64) if want_dist else None
+        self.flags = self._map[off_f:off_f + world * 8].view(np.int64)     # zero-filled by the truncate
         self.count = count
 
+    def arrive(self, rank: int, epoch: int):
+        """This rank's slab of job `epoch` has landed (called after its download returned)."""
+        self.flags[rank] = epoch
+
+    def wait_all(self, epoch: int, timeout_s: float = 600.0):
+        """Rank 0: until every rank has arrived at `epoch`.  A flag in the mapped segment instead of a collective:
+        the slabs already meet in host memory, and an NCCL barrier costs more than the whole copy of a small job."""
+        t_end = time.monotonic() + timeout_s
+        spins = 0
+        while int(self.flags.min()) < epoch:
+            spins += 1
+            if (spins & 0x3ff) == 0 and time.monotonic() > t_end:
+                raise RuntimeError(f"shared result: ranks {np.nonzero(self.flags < epoch)[0].tolist()} never arrived at job {epoch}")
+
     def close(self):
-        self.scores = self.distances = None
+        self.scores = self.distances = self.flags = None
         self._map = None
         if self.owner and self.path and os.path.exists(self.path):
             os.unlink(self.path)
@@ -119,6 +138,7 @@ class ShardedRun:
         self.first = 0
         self.sharded = False
         self.shared: SharedResult | None = None
+        self.epoch = 0                        # jobs finished through the current shared result
 
     def upload(self):
         self.ctx.upload()
@@ -133,6 +153,7 @@ class ShardedRun:
                     self.ctx.set_result_buffers(None)
                     self.shared.close()
                 self.shared = SharedResult(count, not (self.flags & capi.FLAG_NO_DISTANCES), self.group)
+                self.epoch = 0
                 self.ctx.set_result_buffers(self.shared.scores, self.shared.distances)
         else:
             arr, self.first = self.ctx.device_slab()
@@ -147,11 +168,14 @@ class ShardedRun:
 
     def finish(self):
         """Results to the host.  Sharded: every rank finalizes its slab and copies it over its own PCIe
-        link into the shared result, then all meet.  Gathered: rank 0 un-sorts, derives the distances and
+        link into the shared result and marks its arrival there; rank 0 waits for all the marks (the others are free).  Gathered: rank 0 un-sorts, derives the distances and
         downloads; the others wait for their stream."""
         if self.sharded:
             self.ctx.download()
-            dist.barrier(self.group)          # rank 0 may read once every rank's copy has landed
+            self.epoch += 1                   # rank 0 may read once every rank's copy has landed
+            self.shared.arrive(self.rank, self.epoch)
+            if self.rank == 0:
+                self.shared.wait_all(self.epoch)
         elif self.rank == 0:
             self.ctx.finalize()
             self.ctx.download()
