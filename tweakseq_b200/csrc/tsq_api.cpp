@@ -1100,7 +1100,7 @@ int enqueue_wave16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
     const unsigned long long need = (c->tasks16w.size() + warps_per_cta - 1) / warps_per_cta;
     if ((unsigned long long)grid > need) grid = (int)need;
     const uint32_t bnd_rows = c->lens[c->n - 1] + 8;
-    TSQ_CUDA(c, c->d_bnd16w.reserve_zeroed((size_t)grid * warps_per_cta * ((size_t)bnd_rows + bnd_rows / 4 + 16)));
+    TSQ_CUDA(c, c->d_bnd16w.reserve_zeroed((size_t)grid * warps_per_cta * tsq::w16_slot_elems(bnd_rows)));
     TSQ_CUDA(c, cudaMemsetAsync(c->d_counter.p + 2, 0, 12 * sizeof(unsigned long long), s));
     tsq::W16Params w{};
     w.lin = c->d_lin.p;

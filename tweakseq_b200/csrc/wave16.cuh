@@ -47,8 +47,7 @@ struct W16Params {
   const int* cancel;           // device flag (set by a side-stream copy): != 0 stops task fetching
   int* fault;                  // device fault word (cancel + 1): raised when a TMA tile barrier times out
   uint32_t inject_fault;       // test hook: task 0 arms its first tile barrier without issuing the copy
-  uint2* bnd;                  // pass boundary scratch per warp slot: [bnd_rows] rows of (H, E) packed
-                               // relative, then [bnd_rows/4 + 16] (base_lo, base_hi) per step
+  uint2* bnd;                  // pass boundary scratch per warp slot (w16_slot_elems): one record per step
   const uint32_t* sbias;       // (nsym+1) x nsym biased scores S' = S + 2*delta (row nsym = 0)
   int32_t* out;                // scores, packed upper triangle in sorted order
   unsigned long long ntasks;
@@ -61,6 +60,15 @@ struct W16Params {
   int32_t goep;                // goe' = go + ge - delta
   uint32_t negge2;             // (-ge' mod 2^16) in both halves
 };
+
+// Pass-boundary scratch of one warp: one 48-byte RECORD per step -- the (H, E) of the step's four rows 4q+1 .. 4q+4
+// as two 16-byte vectors, then (base_lo, base_hi) in force when they were written, 8 bytes of padding.  Lane 31
+// writes record s - 31 while lane 0 of the next pass reads record s + 1: ONE running pointer serves both, every
+// access is that pointer plus a constant.  Size in uint2 elements (the type of W16Params::bnd).
+constexpr uint32_t kW16RecBytes = 48;
+__host__ __device__ inline size_t w16_slot_elems(uint32_t bnd_rows) {
+  return ((size_t)(bnd_rows + 3) / 4 + 4) * (kW16RecBytes / 8);
+}
 
 __device__ __forceinline__ uint32_t pack_rel(int32_t a, int32_t base_lo, int32_t base_hi) {
   return ((uint32_t)(a - base_lo) & 0xffffu) | ((uint32_t)(a - base_hi) << 16);
@@ -98,9 +106,7 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
   __syncthreads();
 
   const uint32_t gw = blockIdx.x * (TPB / 32) + wib;
-  const size_t slot = (size_t)p.bnd_rows + p.bnd_rows / 4 + 16;
-  uint2* const brow = p.bnd + (size_t)gw * slot;                               // (H, E) per row
-  int2* const bbase = reinterpret_cast<int2*>(brow + p.bnd_rows);              // (base_lo, base_hi) per step
+  char* const bslot = reinterpret_cast<char*>(p.bnd + (size_t)gw * w16_slot_elems(p.bnd_rows));   // record q at 48 q
   const uint32_t nge = NGE ? NGE : p.negge2;
   const int32_t go = p.go, gep = p.gep, goep = p.goep;
   const uint32_t goe2 = (uint32_t)goep * 0x10001u;
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
       uint32_t colH = pack_rel(-go - gep, base_lo, base_hi);
 
       uint32_t oH[4] = {0u, 0u, 0u, 0u}, oE[4] = {0u, 0u, 0u, 0u};  // right edge of this step's four rows: to lane l+1
-      uint2 nb[4] = {make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u)};
+      uint4 nb0 = make_uint4(0u, 0u, 0u, 0u), nb1 = nb0;   // lane 0, later passes: (H, E) of the next step's rows 1,2 / 3,4
       int2 nbase = make_int2(0, 0);
       // ---- subject tiles: 2 x 1 KB ring in shared memory, filled by TMA bulk copies ----------------
       // Tile k covers rows [1024k, 1024k+1024) and lives in ring slot k & 1.  All tile bookkeeping is
@@ -180,30 +186,37 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
           bulk_copy_g2s(stile + TILE, sq + TILE, TILE, &tbar[1]);
         }
         if (!firstp) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) nb[k] = brow[1 + k];
-          nbase = bbase[0];
+          nb0 = *reinterpret_cast<const uint4*>(bslot);
+          nb1 = *reinterpret_cast<const uint4*>(bslot + 16);
+          nbase = *reinterpret_cast<const int2*>(bslot + 32);
         }
       }
       dead = !mbar_wait_warp(&tbar[0], tph0, p.fault);
       tph0 ^= 1u;
+      if (dead) break;
       uint32_t nlet = lane == 0 ? *reinterpret_cast<const uint32_t*>(stile) : 0u;
       const uint32_t nsteps = nquads + 31;
-      for (uint32_t s = 0; s < nsteps && !dead; ++s) {
+      const uint32_t nfull = m / 4;                   // steps of a lane in which all four rows exist
+      int32_t ps = -lane;                             // this lane's own step: rows 4 ps + 1 .. 4 ps + 4
+      uint32_t roff = (uint32_t)(4 * (1 - lane)) & (2 * TILE - 1);   // ring offset of this lane's NEXT four letters
+      const char* const myprofb = reinterpret_cast<const char*>(prof) + lane * 16;   // this lane's profile vectors, as bytes
+      char* rp = bslot;                               // record s of the boundary scratch (warp-uniform)
+      for (uint32_t s = 0; s < nsteps; ++s) {
         const uint32_t let4 = nlet;
-        // ---- tile ring upkeep for the next step (uniform) ------------------------------------------
+        char* const wp = rp - 31 * (int)kW16RecBytes;  // record s - 31: what lane 31 writes in this step
+        // ---- tile ring upkeep for the next step (uniform), behind ONE test that is false on 31 steps of 32 ----
         {
           const uint32_t s1 = s + 1;                 // lane 0 reads bytes 4*s1 .. 4*s1+3 next step
-          if ((s1 & (TSTEPS - 1)) == 0) {            // lane 0 enters tile s1 / TSTEPS
-            const uint32_t tix = s1 / TSTEPS;
-            if (tix < ntiles) {
+          if ((s1 & 31u) == 0) {
+            const uint32_t tix = s1 / TSTEPS, tin = s1 & (TSTEPS - 1);
+            if (tin == 0 && tix < ntiles) {          // lane 0 enters tile tix
               if (tix & 1u) { dead = !mbar_wait_warp(&tbar[1], tph1, p.fault); tph1 ^= 1u; }
               else          { dead = !mbar_wait_warp(&tbar[0], tph0, p.fault); tph0 ^= 1u; }
+              if (dead) break;
             }
-          }
-          if ((s & (TSTEPS - 1)) == 32 && s >= TSTEPS) {   // lane 31 has left tile tix-1: refill its slot
-            const uint32_t tix = s / TSTEPS;
-            if (tix + 1 < ntiles && lane == 0) {
+            // lane 31 left tile tix-1 at step 256 tix + 31: its slot is refilled with tile tix+1, which lane 0
+            // enters 192 steps from here
+            if (tin == 64 && tix >= 1 && tix + 1 < ntiles && lane == 0) {
               fence_proxy_async_smem();
               uint64_t* br = &tbar[(tix + 1) & 1u];
               mbar_arrive_expect_tx(br, TILE);
@@ -212,58 +225,53 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
           }
           // lanes that have not started yet must not touch the ring: their wrapped offsets can fall
           // into a slot a TMA copy is still writing (racecheck), and they need no letters anyway
-          if (s1 >= (uint32_t)lane)
-            nlet = *reinterpret_cast<const uint32_t*>(stile + ((4u * (s1 - (uint32_t)lane)) & (2 * TILE - 1)));
+          if (ps >= -1) nlet = *reinterpret_cast<const uint32_t*>(stile + roff);
+          roff = (roff + 4u) & (2 * TILE - 1);
         }
-        // ---- lane 0's left boundary of this step's four rows (computed by all lanes, uniform code) ----
-        uint32_t lH[4], lE[4];
-        if (firstp) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            lH[k] = colH - (uint32_t)k * gep2;
-            lE[k] = lH[k] - goe2;
-          }
-          colH -= 4u * gep2;
-        } else {
-          const uint32_t d2 = (uint32_t)((nbase.y - base_hi) * 65536 + (nbase.x - base_lo));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            lH[k] = nb[k].x + d2;
-            lE[k] = nb[k].y + d2;
-          }
-          if (lane == 0 && s + 1 < nquads) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) nb[k] = brow[4 * (s + 1) + 1 + k];
-            nbase = bbase[s + 1];
-          }
-        }
-        const int32_t ps = (int32_t)s - lane;
-        const bool lane_on = ps >= 0 && (uint32_t)ps < nquads;
-        // the left neighbour's right edge of the same four rows (its previous step), all lanes converged
+        // ---- the left neighbour's right edge of the same four rows (its previous step), all lanes converged;
+        //      lane 0 takes the pass's left boundary instead: column 0 of the matrix, A(r,0) = -go - r*ge', in the
+        //      first pass, else what lane 31 of the previous pass left in the scratch, re-based ---------------------
         uint32_t iH[4], iE[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           iH[k] = __shfl_up_sync(0xffffffffu, oH[k], 1);
           iE[k] = __shfl_up_sync(0xffffffffu, oE[k], 1);
+        }
+        if (firstp) {
           if (lane == 0) {
-            iH[k] = lH[k];
-            iE[k] = lE[k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              iH[k] = colH - (uint32_t)k * gep2;
+              iE[k] = iH[k] - goe2;
+            }
+          }
+          colH -= 4u * gep2;
+        } else if (lane == 0) {
+          const uint32_t d2 = (uint32_t)((nbase.y - base_hi) * 65536 + (nbase.x - base_lo));
+          iH[0] = nb0.x + d2; iE[0] = nb0.y + d2; iH[1] = nb0.z + d2; iE[1] = nb0.w + d2;
+          iH[2] = nb1.x + d2; iE[2] = nb1.y + d2; iH[3] = nb1.z + d2; iE[3] = nb1.w + d2;
+          if (s + 1 < nquads) {
+            nb0 = *reinterpret_cast<const uint4*>(rp + kW16RecBytes);        // record s + 1
+            nb1 = *reinterpret_cast<const uint4*>(rp + kW16RecBytes + 16);
+            nbase = *reinterpret_cast<const int2*>(rp + kW16RecBytes + 32);
           }
         }
+        const bool lane_on = ps >= 0 && (uint32_t)ps < nquads;
         const uint32_t ra0 = 4 * (uint32_t)ps + 1;
-        if (lane_on && ra0 + 3 <= m) {
+        if ((uint32_t)ps < nfull) {
           // ---- the common case: all four rows exist.  Rows A..D together, each one column behind the one
           //      above: FOUR independent dependency chains per lane (the two-row body of the tail path below
           //      has two), which is what keeps the half-rate DPX pipe fed from three warps per scheduler ------
-          const uint32_t* prow[4];
+          const uint4* prow[4];   // the row's first vector: one PRMT (letter) + one IMAD (byte offset) per row
 #pragma unroll
-          for (int r = 0; r < 4; ++r) prow[r] = myprof + ((let4 >> (8 * r)) & 0xffu) * PW;
+          for (int r = 0; r < 4; ++r)
+            prow[r] = reinterpret_cast<const uint4*>(myprofb + __byte_perm(let4, 0u, 0x4440u + (uint32_t)r) * (uint32_t)(PW * 4));
           uint32_t E[4], t[4], hl[4] = {0u, 0u, 0u, 0u};
           uint4 v[4][KW / 4];
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             E[r] = iE[r];
-            v[r][0] = *reinterpret_cast<const uint4*>(prow[r]);
+            v[r][0] = prow[r][0];
           }
           t[0] = hdiag + v[0][0].x;       // diagonal of row A's first cell: the left lane's H of the row above
           t[1] = iH[0] + v[1][0].x;
@@ -278,7 +286,7 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
               if (k >= 0 && k < KW) {
                 // scores of columns 4g .. 4g+3: one LDS.128, issued one column before its first use
                 if (((k + 2) & 3) == 0 && k + 2 < KW)
-                  v[r][(k + 2) >> 2] = *reinterpret_cast<const uint4*>(prow[r] + ((k + 2) >> 2) * 128);
+                  v[r][(k + 2) >> 2] = prow[r][((k + 2) >> 2) * 32];
                 uint32_t tn = 0;
                 if (k + 1 < KW) tn = H[k] + comp4(v[r][(k + 1) >> 2], (k + 1) & 3);   // H[k]: still the row above
                 const uint32_t h = __vimax3_u16x2(t[r], E[r], F[k]);
@@ -297,8 +305,8 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
             oE[r] = E[r];
           }
           if (lane == 31 && !lastp) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) brow[ra0 + r] = make_uint2(oH[r], oE[r]);
+            *reinterpret_cast<uint4*>(wp) = make_uint4(oH[0], oE[0], oH[1], oE[1]);   // lane 31: record ps = s - 31
+            *reinterpret_cast<uint4*>(wp + 16) = make_uint4(oH[2], oE[2], oH[3], oE[3]);
           }
           if (ra0 + 3 == m) {   // the subject's last row: H(m, n) of a query that ends in this block, made absolute
             if (pass == pass1) {
@@ -347,7 +355,7 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
               }
               oH[2 * q] = H[KW - 1];
               oE[2 * q] = E;
-              if (lane == 31 && !lastp) brow[ra] = make_uint2(oH[2 * q], oE[2 * q]);
+              if (lane == 31 && !lastp) *reinterpret_cast<uint2*>(wp + 16 * q) = make_uint2(oH[2 * q], oE[2 * q]);
             } else {
               // ---- rows ra (A) and ra+1 (B), B one column behind A ----------------------------------
               const uint32_t* prow_b = myprof + ((let4 >> (16 * q + 8)) & 0xffu) * PW;
@@ -392,8 +400,7 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
               }
               oH[2 * q] = ha_last; oE[2 * q] = Ea; oH[2 * q + 1] = H[KW - 1]; oE[2 * q + 1] = Eb;
               if (lane == 31 && !lastp) {
-                brow[ra] = make_uint2(oH[2 * q], oE[2 * q]);
-                brow[ra + 1] = make_uint2(oH[2 * q + 1], oE[2 * q + 1]);
+                *reinterpret_cast<uint4*>(wp + 16 * q) = make_uint4(oH[2 * q], oE[2 * q], oH[2 * q + 1], oE[2 * q + 1]);
               }
             }
             // ---- the subject's last row: H(m, n) of a query that ends in this block, made absolute ----
@@ -418,7 +425,7 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
           }
         }
         }
-        if (lane == 31 && !lastp && lane_on) bbase[ps] = make_int2(base_lo, base_hi);
+        if (lane == 31 && !lastp && lane_on) *reinterpret_cast<int2*>(wp + 32) = make_int2(base_lo, base_hi);
         // ---- re-centre the base on lane 16's first column (all lanes, uniform) ----------------------
         if ((s & (RB - 1)) == RB - 1 && s < nquads) {
           const uint32_t ref = __shfl_sync(0xffffffffu, H[0], 16);
@@ -440,6 +447,8 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
           base_lo += sh_lo;
           base_hi += sh_hi;
         }
+        ++ps;
+        rp += kW16RecBytes;
       }
       __syncwarp();
     }
