@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
       uint32_t nlet = lane == 0 ? *reinterpret_cast<const uint32_t*>(stile) : 0u;
       const uint32_t nsteps = nquads + 31;
       const uint32_t nfull = m / 4;                   // steps of a lane in which all four rows exist
+      const uint32_t ps_last = (m & 3u) == 0 ? nfull - 1 : 0xffffffffu;   // the full step that holds the subject's last row
       int32_t ps = -lane;                             // this lane's own step: rows 4 ps + 1 .. 4 ps + 4
       uint32_t roff = (uint32_t)(4 * (1 - lane)) & (2 * TILE - 1);   // ring offset of this lane's NEXT four letters
       const char* const myprofb = reinterpret_cast<const char*>(prof) + lane * 16;   // this lane's profile vectors, as bytes
@@ -204,25 +205,47 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
       for (uint32_t s = 0; s < nsteps; ++s) {
         const uint32_t let4 = nlet;
         char* const wp = rp - 31 * (int)kW16RecBytes;  // record s - 31: what lane 31 writes in this step
-        // ---- tile ring upkeep for the next step (uniform), behind ONE test that is false on 31 steps of 32 ----
-        {
-          const uint32_t s1 = s + 1;                 // lane 0 reads bytes 4*s1 .. 4*s1+3 next step
-          if ((s1 & 31u) == 0) {
-            const uint32_t tix = s1 / TSTEPS, tin = s1 & (TSTEPS - 1);
-            if (tin == 0 && tix < ntiles) {          // lane 0 enters tile tix
-              if (tix & 1u) { dead = !mbar_wait_warp(&tbar[1], tph1, p.fault); tph1 ^= 1u; }
-              else          { dead = !mbar_wait_warp(&tbar[0], tph0, p.fault); tph0 ^= 1u; }
-              if (dead) break;
+        // ---- everything that happens once in many steps, behind ONE test that is false on 15 steps of 16 (uniform):
+        //      re-centring the base, waiting for the next subject tile, refilling the slot of the one before ----------
+        if ((s & (RB - 1)) == 0) {
+          if (s != 0 && s - 1 < nquads) {
+            // re-centre the base on lane 16's first column (all lanes; the state is that of the end of step s - 1)
+            const uint32_t ref = __shfl_sync(0xffffffffu, H[0], 16);
+            const int32_t sh_lo = (int32_t)(ref & 0xffffu) - CENTER;
+            const int32_t sh_hi = (int32_t)(ref >> 16) - CENTER;
+            const uint32_t shift2 = (uint32_t)(sh_hi * 65536 + sh_lo);
+#pragma unroll
+            for (int c = 0; c < KW; ++c) {
+              H[c] -= shift2;
+              F[c] -= shift2;
             }
-            // lane 31 left tile tix-1 at step 256 tix + 31: its slot is refilled with tile tix+1, which lane 0
-            // enters 192 steps from here
-            if (tin == 64 && tix >= 1 && tix + 1 < ntiles && lane == 0) {
-              fence_proxy_async_smem();
-              uint64_t* br = &tbar[(tix + 1) & 1u];
-              mbar_arrive_expect_tx(br, TILE);
-              bulk_copy_g2s(stile + ((tix + 1) & 1u) * TILE, sq + (size_t)(tix + 1) * TILE, TILE, br);
+            hdiag -= shift2;
+            colH -= shift2;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              oH[k] -= shift2;
+              oE[k] -= shift2;
             }
+            base_lo += sh_lo;
+            base_hi += sh_hi;
           }
+          const uint32_t tix = s / TSTEPS, tin = s & (TSTEPS - 1);
+          // lane 0 enters tile tix + 1 in 16 steps (its letters are fetched one step ahead): the copy, issued 176
+          // steps ago (or at the start of the pass), has to have landed
+          if (tin == TSTEPS - 16 && tix + 1 < ntiles) {
+            if ((tix + 1) & 1u) { dead = !mbar_wait_warp(&tbar[1], tph1, p.fault); tph1 ^= 1u; }
+            else                { dead = !mbar_wait_warp(&tbar[0], tph0, p.fault); tph0 ^= 1u; }
+            if (dead) break;
+          }
+          // lane 31 left tile tix - 1 at step 256 tix + 31: its slot is refilled with tile tix + 1
+          if (tin == 64 && tix >= 1 && tix + 1 < ntiles && lane == 0) {
+            fence_proxy_async_smem();
+            uint64_t* br = &tbar[(tix + 1) & 1u];
+            mbar_arrive_expect_tx(br, TILE);
+            bulk_copy_g2s(stile + ((tix + 1) & 1u) * TILE, sq + (size_t)(tix + 1) * TILE, TILE, br);
+          }
+        }
+        {
           // lanes that have not started yet must not touch the ring: their wrapped offsets can fall
           // into a slot a TMA copy is still writing (racecheck), and they need no letters anyway
           if (ps >= -1) nlet = *reinterpret_cast<const uint32_t*>(stile + roff);
@@ -257,7 +280,6 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
           }
         }
         const bool lane_on = ps >= 0 && (uint32_t)ps < nquads;
-        const uint32_t ra0 = 4 * (uint32_t)ps + 1;
         if ((uint32_t)ps < nfull) {
           // ---- the common case: all four rows exist.  Rows A..D together, each one column behind the one
           //      above: FOUR independent dependency chains per lane (the two-row body of the tail path below
@@ -307,8 +329,9 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
           if (lane == 31 && !lastp) {
             *reinterpret_cast<uint4*>(wp) = make_uint4(oH[0], oE[0], oH[1], oE[1]);   // lane 31: record ps = s - 31
             *reinterpret_cast<uint4*>(wp + 16) = make_uint4(oH[2], oE[2], oH[3], oE[3]);
+            *reinterpret_cast<int2*>(wp + 32) = make_int2(base_lo, base_hi);
           }
-          if (ra0 + 3 == m) {   // the subject's last row: H(m, n) of a query that ends in this block, made absolute
+          if ((uint32_t)ps == ps_last) {   // the subject's last row: H(m, n) of a query that ends in this block, made absolute
             if (pass == pass1) {
               const int32_t c1 = (int32_t)n1 - 1 - col0;
               if (c1 >= 0 && c1 < KW) {
@@ -328,6 +351,7 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
           }
         } else {
         // ---- the last step of a lane whose subject length is not a multiple of four: two rows, then one ----
+        if (lane == 31 && !lastp && lane_on) *reinterpret_cast<int2*>(wp + 32) = make_int2(base_lo, base_hi);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const uint32_t iHa = iH[2 * q], iEa = iE[2 * q], iHb = iH[2 * q + 1], iEb = iE[2 * q + 1];
@@ -424,28 +448,6 @@ __global__ void __launch_bounds__(TPB, MINB) wave16_kernel(const __grid_constant
             }
           }
         }
-        }
-        if (lane == 31 && !lastp && lane_on) *reinterpret_cast<int2*>(wp + 32) = make_int2(base_lo, base_hi);
-        // ---- re-centre the base on lane 16's first column (all lanes, uniform) ----------------------
-        if ((s & (RB - 1)) == RB - 1 && s < nquads) {
-          const uint32_t ref = __shfl_sync(0xffffffffu, H[0], 16);
-          const int32_t sh_lo = (int32_t)(ref & 0xffffu) - CENTER;
-          const int32_t sh_hi = (int32_t)(ref >> 16) - CENTER;
-          const uint32_t shift2 = (uint32_t)(sh_hi * 65536 + sh_lo);
-#pragma unroll
-          for (int c = 0; c < KW; ++c) {
-            H[c] -= shift2;
-            F[c] -= shift2;
-          }
-          hdiag -= shift2;
-          colH -= shift2;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            oH[k] -= shift2;
-            oE[k] -= shift2;
-          }
-          base_lo += sh_lo;
-          base_hi += sh_hi;
         }
         ++ps;
         rp += kW16RecBytes;
