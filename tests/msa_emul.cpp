@@ -52,16 +52,23 @@ class EmulDevice : public tsq::MsaDevice {
   // the body of msa_merge_cta<T>, barrier by barrier
   template <typename T>
   void sweep(const tsq::MsaTask& t, const tsq::MsaConst& k, void* shared, uint32_t smem_bytes, int nt) {
-    void* const diag = tsq::msa_diag_bytes(t.Lx, sizeof(T) == 4) <= (size_t)smem_bytes ? shared : (void*)t.diag;   // as the kernel decides
-    each_thread(nt, [&](int tid) { tsq::msa_prep_phase(t, k, tid, nt); });
-    const tsq::MsaSweep<T> sw = tsq::msa_sweep_init<T>(t, k, diag);
-    const int last = sw.m + sw.n;
-    int hc = 0;
-    for (int d = 0; d <= last; ++d) {
-      each_thread(nt, [&](int tid) { tsq::msa_diag_phase<T>(sw, d, hc, tid, nt); });
-      hc = hc == 2 ? 0 : hc + 1;
+    // what lives in "shared memory": as msa_merge_cta decides, with the same sizes
+    const size_t db = tsq::msa_round16(tsq::msa_diag_bytes(t.Lx, t.Ly, sizeof(T) == 4));
+    void* const edge = db <= (size_t)smem_bytes ? shared : (void*)t.diag;
+    uint16_t* codes = nullptr;   // 4-bit direction codes behind the edge arrays and the column-score tables
+    if (db <= (size_t)smem_bytes) {
+      const uint32_t Lb = tsq::msa_big_is_x(t) ? t.Lx : t.Ly, Ls = tsq::msa_big_is_x(t) ? t.Ly : t.Lx;
+      const size_t pb = tsq::msa_round16((size_t)k.nsym * Lb * 4), lb = tsq::msa_round16((size_t)k.nsym * Ls * 4),
+                   nb = tsq::msa_round16((size_t)Ls * 4);
+      if (db + pb + lb + nb + tsq::msa_round16(tsq::msa_code_bytes(t.Lx, t.Ly)) <= (size_t)smem_bytes)
+        codes = reinterpret_cast<uint16_t*>(static_cast<char*>(shared) + db + pb + lb + nb);
     }
-    tsq::msa_walk_phase(t, tsq::msa_final_score<T>(sw));
+    each_thread(nt, [&](int tid) { tsq::msa_prep_phase(t, k, tid, nt); });
+    const tsq::MsaSweep<T> sw = tsq::msa_sweep_init<T>(t, k, edge, nullptr, codes);
+    each_thread(nt, [&](int tid) { tsq::msa_edge_phase<T>(sw, tid, nt); });
+    const int steps = tsq::msa_sweep_steps<T>(sw);
+    for (int st = 0; st < steps; ++st) each_thread(nt, [&](int tid) { tsq::msa_tile_phase<T>(sw, st, tid, nt); });
+    tsq::msa_walk_phase(t, tsq::msa_final_score<T>(sw), codes);
   }
   bool launch_leaves(const tsq::MsaLeaf* l, uint32_t n, uint32_t nsym) override {
     for (uint32_t r = 0; r < n; r++) each_thread(128, [&](int t) { tsq::msa_leaf_phase(l[r], nsym, t, 128); });

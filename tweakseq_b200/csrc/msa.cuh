@@ -20,10 +20,12 @@
 //      letters present with their counts.  sub(i, j) = sum over that list of count * P[letter][col_big]:
 //      one multiply-add per distinct letter of the small side's column -- exactly one when it is a
 //      single sequence, the common case of a guide tree over related sequences (a caterpillar).
-//   2. anti-diagonal sweep, one barrier per diagonal: H (3 rolling diagonals), E, F (2 each) indexed by
-//      i, in SHARED memory when 7 (Lx + 1) scores fit (an L2 round trip per diagonal otherwise); one
-//      direction byte per cell, diagonal-major (traceback.cuh).  Scores are int32 when the merge's
-//      range bound allows (msa_fits_narrow: half the instructions of int64 on a 32-bit datapath)
+//   2. the sweep, in TILES of 4 x 4 cells: one thread per tile, one step (and one barrier) per anti-diagonal of
+//      tiles; a thread fetches its tile's 16 column scores first, then runs the cells out of registers.  What
+//      crosses a tile edge -- H and F of the last finished row per column, H and E of the last finished column per
+//      row, one corner per tile row -- sits in SHARED memory when it fits (msa_diag_bytes; global scratch
+//      otherwise); one direction byte per cell, diagonal-major (traceback.cuh).  Scores are int32 when the
+//      merge's range bound allows (msa_fits_narrow: half the instructions of int64 on a 32-bit datapath)
 //   3. thread 0 walks the path back from (Lx, Ly): per merged column its X column and Y column or -1.
 //      The direction bytes sit in L2, so it fetches the next 16 along the current run (diagonal, or a
 //      gap run) at once and consumes them from registers: one round trip per run piece, not per column
@@ -72,7 +74,7 @@ struct MsaTask {         // one merge: X = left child, Y = right child
   uint32_t pad;
   uint32_t* mapx;        // Lx entries: X column -> merged column
   uint32_t* mapy;        // Ly entries
-  long long* diag;       // scratch: 7 * (Lx + 1) scores, used when the rolling diagonals do not fit shared memory
+  long long* diag;       // scratch: msa_diag_bytes, used when the sweep's edge arrays do not fit shared memory
   int32_t* pbig;         // scratch: nsym * max(Lx, Ly): P[b * Lbig + col] of the side with more sequences
   uint32_t* lst;         // scratch: nsym * max(Lx, Ly): lst[k * Lsmall + col] = letter << 24 | count
   uint32_t* lnz;         // scratch: max(Lx, Ly): distinct letters in the small side's column
@@ -103,8 +105,29 @@ template <typename T> struct MsaNeg;
 template <> struct MsaNeg<long long> { static constexpr long long v = -(1LL << 60); };
 template <> struct MsaNeg<int32_t> { static constexpr int32_t v = -(1 << 30); };
 
-// bytes of the 7 rolling diagonals (3 H, 2 E, 2 F) of a merge with Lx columns along i
-TSQ_HD size_t msa_diag_bytes(uint32_t Lx, bool narrow) { return 7 * ((size_t)Lx + 1) * (narrow ? sizeof(int32_t) : sizeof(long long)); }
+// The sweep works on TILES of kMsaTile x kMsaTile cells, one thread per tile, the tiles of one anti-diagonal of tiles
+// per step (r02; one cell per thread and one CTA barrier per cell diagonal before: 4x the barriers, and a thread's
+// whole dependent chain -- list length -> letter -> letter score -> max -- between every two of them).  What
+// crosses a tile edge lives in five small arrays: H and F of the last finished row, per column (Ly + 1 each), H and
+// E of the last finished column, per row (Lx + 1 each), and per tile row the corner H(i0 - 1, j0 - 1) of its next tile.
+constexpr int kMsaTile = 4;
+TSQ_HD size_t msa_diag_bytes(uint32_t Lx, uint32_t Ly, bool narrow) {
+  return (2 * ((size_t)Ly + 1) + 2 * ((size_t)Lx + 1) + ((size_t)Lx + kMsaTile - 1) / kMsaTile + 1) *
+         (narrow ? sizeof(int32_t) : sizeof(long long));
+}
+
+// Direction codes in shared memory: 4 bits per cell, row-major, a row padded to a multiple of 4 cells so that the four
+// codes of a tile row are one aligned 16-bit word.  90 000 cells (a 300 x 300 merge) take 45 KB; the walk-back then
+// reads them at shared-memory latency instead of one L2 round trip per run piece (once the sweep was tiled, the
+// walk was two thirds of a merge).  Merges whose codes do not fit keep the diagonal-major bytes in global scratch.
+TSQ_HD uint32_t msa_code_row_words(uint32_t Ly) { return (Ly + 3u) / 4u; }          // 16-bit words per matrix row
+TSQ_HD size_t msa_code_bytes(uint32_t Lx, uint32_t Ly) { return (size_t)Lx * msa_code_row_words(Ly) * 2; }
+// code of cell (i, j), 1-based: from the 4-bit array when there is one, else from the diagonal-major bytes
+TSQ_HD uint32_t msa_read_code(const uint16_t* codes, const uint8_t* dir, int i, int j, int n, size_t ld) {
+  if (codes) return ((uint32_t)codes[(size_t)(i - 1) * msa_code_row_words((uint32_t)n) + (uint32_t)((j - 1) >> 2)] >> (4 * ((j - 1) & 3))) & 15u;
+  const int d = i + j;
+  return dir[(size_t)d * ld + (size_t)(i - (d > n ? d - n : 0))];
+}
 
 // bytes of the three column-score tables of a merge (msa_prep_phase): letter scores of the big side, letter lists
 // and list lengths of the small side.  When they fit shared memory next to the rolling diagonals the sweep reads
@@ -174,15 +197,20 @@ template <typename T>
 struct MsaSweep {
   T GO, GE, GOE;
   int m, n;              // Lx, Ly
-  uint32_t stride;       // m + 1: one rolling diagonal
+  int ntr, ntc;          // rows / columns of tiles
   uint32_t ld;           // min(m, n) + 1: one diagonal of direction bytes
   uint32_t Lb, Ls;       // columns of the big / small side
   bool bx;               // the big side is X
   const uint32_t* lnz;
   const uint32_t* lst;
   const int32_t* pbig;
-  uint8_t* dir;
-  T* diag;               // 3 H, 2 E, 2 F diagonals
+  uint8_t* dir;          // direction bytes, diagonal-major (global scratch); used when codes == nullptr
+  uint16_t* codes;       // direction codes, 4 bits per cell, row-major (shared memory), or nullptr
+  T* Hrow;               // [n + 1] H of the last finished row, per column
+  T* Frow;               // [n + 1] F of it
+  T* Hcol;               // [m + 1] H of the last finished column, per row
+  T* Ecol;               // [m + 1] E of it
+  T* corner;             // [ntr + 1] H(i0 - 1, j0 - 1) of the next tile of a tile row
 };
 
 struct MsaTables {       // where the sweep reads the column-score tables from (the task's scratch, or shared memory)
@@ -192,12 +220,12 @@ struct MsaTables {       // where the sweep reads the column-score tables from (
 };
 
 template <typename T>
-TSQ_HD MsaSweep<T> msa_sweep_init(const MsaTask& t, const MsaConst& k, void* diag, const MsaTables* tab = nullptr) {
+TSQ_HD MsaSweep<T> msa_sweep_init(const MsaTask& t, const MsaConst& k, void* edge, const MsaTables* tab = nullptr, uint16_t* codes = nullptr) {
   MsaSweep<T> s;
   const long long w = (long long)t.nx * (long long)t.ny;
   s.GO = (T)(w * k.go); s.GE = (T)(w * k.ge); s.GOE = (T)(w * k.go + w * k.ge);
   s.m = (int)t.Lx; s.n = (int)t.Ly;
-  s.stride = t.Lx + 1;
+  s.ntr = (s.m + kMsaTile - 1) / kMsaTile; s.ntc = (s.n + kMsaTile - 1) / kMsaTile;
   s.ld = (t.Lx < t.Ly ? t.Lx : t.Ly) + 1;
   s.bx = msa_big_is_x(t);
   s.Lb = s.bx ? t.Lx : t.Ly; s.Ls = s.bx ? t.Ly : t.Lx;
@@ -205,72 +233,172 @@ TSQ_HD MsaSweep<T> msa_sweep_init(const MsaTask& t, const MsaConst& k, void* dia
   s.lst = tab ? tab->lst : t.lst;
   s.pbig = tab ? tab->pbig : t.pbig;
   s.dir = t.dir;
-  s.diag = (T*)diag;
+  s.codes = codes;
+  s.Hrow = (T*)edge;
+  s.Frow = s.Hrow + (s.n + 1);
+  s.Hcol = s.Frow + (s.n + 1);
+  s.Ecol = s.Hcol + (s.m + 1);
+  s.corner = s.Ecol + (s.m + 1);
   return s;
 }
 
-// H(Lx, Ly) after the sweep: diagonal Lx + Ly sits in H buffer (Lx + Ly) % 3
+// steps of the sweep: one per anti-diagonal of tiles
+template <typename T>
+TSQ_HD int msa_sweep_steps(const MsaSweep<T>& s) { return (s.ntr > 0 && s.ntc > 0) ? s.ntr + s.ntc - 1 : 0; }
+
+// H(Lx, Ly) after the sweep
 template <typename T>
 TSQ_HD long long msa_final_score(const MsaSweep<T>& s) {
-  return (long long)s.diag[(size_t)((s.m + s.n) % 3) * s.stride + (size_t)s.m];
+  return (long long)(s.m > 0 ? s.Hcol[s.m] : s.Hrow[s.n]);
 }
 
-// One diagonal d in [0, Lx + Ly]; hc = d % 3 (the caller counts it along: no division per diagonal).
+// Row 0 and column 0 of the matrix, as the edges the first tiles read: H(0, j) = -GO - j GE, F(0, j) = -inf,
+// H(i, 0) = -GO - i GE, E(i, 0) = -inf, H(0, 0) = 0.
 template <typename T>
-TSQ_HD void msa_diag_phase(const MsaSweep<T>& s, int d, int hc, int tid, int nt) {
+TSQ_HD void msa_edge_phase(const MsaSweep<T>& s, int tid, int nt) {
   constexpr T NEG = MsaNeg<T>::v;
-  const int h1 = hc ? hc - 1 : 2, h2 = h1 ? h1 - 1 : 2;   // buffers of diagonals d-1, d-2
-  const int par = d & 1;
-  T* const Hc = s.diag + (size_t)hc * s.stride;
-  const T* const Hp1 = s.diag + (size_t)h1 * s.stride;
-  const T* const Hp2 = s.diag + (size_t)h2 * s.stride;
-  T* const Ec = s.diag + (size_t)(3 + par) * s.stride;
-  const T* const Ep1 = s.diag + (size_t)(4 - par) * s.stride;
-  T* const Fc = s.diag + (size_t)(5 + par) * s.stride;
-  const T* const Fp1 = s.diag + (size_t)(6 - par) * s.stride;
-  const int ilo = d > s.n ? d - s.n : 0;
-  const int ihi = d < s.m ? d : s.m;
-  uint8_t* const drow = s.dir + (size_t)d * s.ld - ilo;
-  for (int i = ilo + tid; i <= ihi; i += nt) {
-    const int j = d - i;
-    T H, E, F;
-    uint32_t code;
-    if (i != 0 && j != 0) {
-      const uint32_t colb = (uint32_t)(s.bx ? i - 1 : j - 1), cols = (uint32_t)(s.bx ? j - 1 : i - 1);
-      const uint32_t nz = s.lnz[cols];
-      const uint32_t* le = s.lst + cols;
-      const int32_t* pb = s.pbig + colb;
-      T sub = 0;
-      TSQ_NO_UNROLL   // usually one to three letters: an unrolled body costs more in remainder branches than it saves
-      for (uint32_t q = 0; q < nz; ++q, le += s.Ls) {
-        const uint32_t e = *le;
-        sub += (T)(e & 0xffffffu) * (T)pb[(e >> 24) * s.Lb];   // nsym * Lb words: a 32-bit offset
+  for (int j = tid; j <= s.n; j += nt) {
+    s.Hrow[j] = j == 0 ? (T)0 : (T)(-s.GO - (T)j * s.GE);
+    s.Frow[j] = NEG;
+  }
+  for (int i = tid; i <= s.m; i += nt) {
+    s.Hcol[i] = i == 0 ? (T)0 : (T)(-s.GO - (T)i * s.GE);
+    s.Ecol[i] = NEG;
+  }
+  for (int I = tid; I <= s.ntr; I += nt) s.corner[I] = I == 0 ? (T)0 : (T)(-s.GO - (T)(I * kMsaTile) * s.GE);   // H(I * tile, 0)
+}
+
+// The cells of one tile, row by row out of registers.  FULL: all kMsaTile x kMsaTile cells exist -- no guards, one
+// straight-line block in which the scheduler interleaves the independent cells of the tile's own anti-diagonals (a
+// thread's dependent chain is 7 cells long, not 16).
+template <typename T, bool FULL>
+TSQ_HD void msa_tile_cells(const MsaSweep<T>& s, int I, int i0, int j0, int ih, int jw, const T (&sub)[kMsaTile][kMsaTile]) {
+  constexpr int TB = kMsaTile;
+  // ---- edges in ----
+  T th[TB], tf[TB];      // H and F of the row above, per tile column
+  T hl[TB], el[TB];      // H and E of the column to the left, per tile row
+TSQ_UNROLL
+  for (int c = 0; c < TB; ++c) {
+    th[c] = (FULL || c < jw) ? s.Hrow[j0 + c] : (T)0;
+    tf[c] = (FULL || c < jw) ? s.Frow[j0 + c] : (T)0;
+  }
+TSQ_UNROLL
+  for (int r = 0; r < TB; ++r) {
+    hl[r] = (FULL || r < ih) ? s.Hcol[i0 + r] : (T)0;
+    el[r] = (FULL || r < ih) ? s.Ecol[i0 + r] : (T)0;
+  }
+  T dcorner = s.corner[I];                               // H(i0 - 1, j0 - 1)
+  s.corner[I] = FULL ? th[TB - 1] : s.Hrow[j0 + jw - 1];  // H(i0 - 1, j0 + jw - 1): the corner of tile (I, J + 1)
+  // direction bytes: cell (i, j) at dir[d * ld + i - max(0, d - n)], d = i + j
+  const size_t ld = s.ld;
+  // ---- cells ----
+TSQ_UNROLL
+  for (int r = 0; r < TB; ++r) {
+    if (FULL || r < ih) {
+      const int i = i0 + r;
+      T h = hl[r], e = el[r];              // H(i, j0 - 1), E(i, j0 - 1)
+      T dg0 = dcorner;
+      dcorner = h;                         // H(i, j0 - 1): the diagonal of row i + 1's first cell
+      uint32_t rowcodes = 0;               // the row's codes, 4 bits each
+TSQ_UNROLL
+      for (int c = 0; c < TB; ++c) {
+        if (FULL || c < jw) {
+          const int j = j0 + c;
+          const T e_ext = e - s.GE, e_open = h - s.GOE;
+          const T f_ext = tf[c] - s.GE, f_open = th[c] - s.GOE;
+          const T dg = dg0 + sub[r][c];
+          const bool eo = e_open >= e_ext, fo = f_open >= f_ext;
+          const T E = eo ? e_open : e_ext;
+          const T F = fo ? f_open : f_ext;
+          T H = dg;
+          if (E > H) H = E;
+          if (F > H) H = F;
+          const uint32_t code = (H == dg ? 0u : (H == E ? 1u : 2u)) | (eo ? 4u : 0u) | (fo ? 8u : 0u);
+          rowcodes |= code << (4 * c);
+          if (!s.codes) {
+            const int d = i + j;
+            s.dir[(size_t)d * ld + (size_t)(i - (d > s.n ? d - s.n : 0))] = (uint8_t)code;
+          }
+          dg0 = th[c];                     // H(i - 1, j): the diagonal of (i, j + 1)
+          th[c] = H; tf[c] = F;
+          h = H; e = E;
+        }
       }
-      const T hl = Hp1[i], hu = Hp1[i - 1], hd = Hp2[i - 1];
-      const T e_ext = Ep1[i] - s.GE, e_open = hl - s.GOE;
-      const T f_ext = Fp1[i - 1] - s.GE, f_open = hu - s.GOE;
-      const T dg = hd + sub;
-      const bool eo = e_open >= e_ext, fo = f_open >= f_ext;
-      E = eo ? e_open : e_ext;
-      F = fo ? f_open : f_ext;
-      H = dg;
-      if (E > H) H = E;
-      if (F > H) H = F;
-      code = (H == dg ? 0u : (H == E ? 1u : 2u)) | (eo ? 4u : 0u) | (fo ? 8u : 0u);
-    } else if (i == 0 && j == 0) {
-      H = 0; E = NEG; F = NEG; code = 0;
-    } else if (i == 0) {
-      H = E = (T)(-s.GO - (T)j * s.GE); F = NEG; code = 1u | (j == 1 ? 4u : 0u);
-    } else {
-      H = F = (T)(-s.GO - (T)i * s.GE); E = NEG; code = 2u | (i == 1 ? 8u : 0u);
+      s.Hcol[i] = h;                       // H(i, j0 + jw - 1), E of it
+      s.Ecol[i] = e;
+      if (s.codes) s.codes[(size_t)(i - 1) * msa_code_row_words((uint32_t)s.n) + (uint32_t)((j0 - 1) >> 2)] = (uint16_t)rowcodes;
     }
-    Hc[i] = H; Ec[i] = E; Fc[i] = F;
-    drow[i] = (uint8_t)code;
+  }
+  // ---- edges out ----
+TSQ_UNROLL
+  for (int c = 0; c < TB; ++c)
+    if (FULL || c < jw) { s.Hrow[j0 + c] = th[c]; s.Frow[j0 + c] = tf[c]; }
+}
+
+// One step: the tiles (I, J) with I + J == st; thread tid takes tile row Ilo + tid (+ nt, ...).  Rows i0 .. i0 + ih - 1,
+// columns j0 .. j0 + jw - 1 of the matrix (1-based cells).  All column scores of the tile first (loads only: they
+// overlap), then the cells.
+template <typename T>
+TSQ_HD void msa_tile_phase(const MsaSweep<T>& s, int st, int tid, int nt) {
+  constexpr int TB = kMsaTile;
+  const int Ilo = st >= s.ntc ? st - s.ntc + 1 : 0;
+  const int Ihi = st < s.ntr ? st : s.ntr - 1;
+  for (int I = Ilo + tid; I <= Ihi; I += nt) {
+    const int J = st - I;
+    const int i0 = I * TB + 1, j0 = J * TB + 1;
+    const int ih = s.m - i0 + 1 < TB ? s.m - i0 + 1 : TB;
+    const int jw = s.n - j0 + 1 < TB ? s.n - j0 + 1 : TB;
+    const bool full = ih == TB && jw == TB;
+    // ---- column scores sub(i, j) = sum over the small side's letters of count * letter score of the big side ----
+    T sub[TB][TB];
+    // the small side runs along j when the big side is X (one letter list per tile column, used by every row),
+    // along i otherwise; a0 / b0: first small-side / big-side column of the tile, na / nb: how many
+    const uint32_t a0 = (uint32_t)(s.bx ? j0 : i0) - 1, b0 = (uint32_t)(s.bx ? i0 : j0) - 1;
+    const int na = s.bx ? jw : ih, nb = s.bx ? ih : jw;
+    uint32_t nz[TB];
+TSQ_UNROLL
+    for (int a = 0; a < TB; ++a) nz[a] = (full || a < na) ? s.lnz[a0 + a] : 0u;
+    T sa[TB][TB];        // [small-side column][big-side column]
+    if (full && nz[0] == 1u && nz[1] == 1u && nz[2] == 1u && nz[3] == 1u) {
+      // one letter per small-side column (a single sequence joins a profile: the common shape): straight-line
+      uint32_t e[TB];
+TSQ_UNROLL
+      for (int a = 0; a < TB; ++a) e[a] = s.lst[a0 + a];
+TSQ_UNROLL
+      for (int a = 0; a < TB; ++a) {
+        const int32_t* pb = s.pbig + (size_t)(e[a] >> 24) * s.Lb + b0;
+        const T cnt = (T)(e[a] & 0xffffffu);
+TSQ_UNROLL
+        for (int b = 0; b < TB; ++b) sa[a][b] = cnt * (T)pb[b];
+      }
+    } else {
+TSQ_UNROLL
+      for (int a = 0; a < TB; ++a) {
+TSQ_UNROLL
+        for (int b = 0; b < TB; ++b) sa[a][b] = 0;
+        const uint32_t* le = s.lst + a0 + a;
+        TSQ_NO_UNROLL
+        for (uint32_t q = 0; q < nz[a]; ++q, le += s.Ls) {
+          const uint32_t e = *le;
+          const T cnt = (T)(e & 0xffffffu);
+          const int32_t* pb = s.pbig + (size_t)(e >> 24) * s.Lb + b0;
+TSQ_UNROLL
+          for (int b = 0; b < TB; ++b)
+            if (full || b < nb) sa[a][b] += cnt * (T)pb[b];
+        }
+      }
+    }
+TSQ_UNROLL
+    for (int r = 0; r < TB; ++r)
+TSQ_UNROLL
+      for (int c = 0; c < TB; ++c) sub[r][c] = s.bx ? sa[c][r] : sa[r][c];
+    if (full) msa_tile_cells<T, true>(s, I, i0, j0, ih, jw, sub);
+    else msa_tile_cells<T, false>(s, I, i0, j0, ih, jw, sub);
   }
 }
 
 // phase 3, one thread.  score = H(Lx, Ly) (msa_final_score).
-TSQ_HD void msa_walk_phase(const MsaTask& t, long long score) {
+TSQ_HD void msa_walk_phase(const MsaTask& t, long long score, const uint16_t* codes4 = nullptr) {
   constexpr int B = 16;   // direction bytes fetched per round trip
   const int m = (int)t.Lx, n = (int)t.Ly;
   const size_t ld = (size_t)(m < n ? m : n) + 1;
@@ -284,10 +412,7 @@ TSQ_UNROLL
     for (int q = 0; q < B; ++q) {
       const int ii = i - q * di, jj = j - q * dj;
       uint32_t c = 0;
-      if (ii > 0 && jj > 0) {
-        const int d = ii + jj;
-        c = t.dir[(size_t)d * ld + (size_t)(ii - (d > n ? d - n : 0))];
-      }
+      if (ii > 0 && jj > 0) c = msa_read_code(codes4, t.dir, ii, jj, n, ld);
       codes[q] = c;
     }
     bool turned = false;
@@ -358,38 +483,100 @@ TSQ_HD void msa_rows_phase(const MsaRows& p, uint32_t r, int tid, int nt) {
 }
 
 #ifdef TSQ_DEVICE_IMPL
+// phase 3 on the device: msa_walk_phase's walk by ONE WARP.  The serial walk is a chain of L2 round trips (16
+// direction bytes per trip, consumed one by one by one thread): a third of a merge's time once the sweep was tiled.
+// Here lane q fetches the direction bytes of the cells q and q + 32 steps ahead along the current run (down the
+// diagonal, or along the gap run), a ballot finds where the run ends, and all lanes before that point write their
+// path entries at once.  Same state machine, same path, entry for entry (GPU tests against the oracle; the CPU
+// emulation keeps running the serial statement above).
+__device__ __forceinline__ void msa_walk_warp(const MsaTask& t, long long score, int lane, const uint16_t* codes4) {
+  const int m = (int)t.Lx, n = (int)t.Ly;
+  const size_t ld = (size_t)(m < n ? m : n) + 1;
+  int i = m, j = n, state = 0;
+  uint32_t k = 0;
+  while (i > 0 && j > 0) {
+    const int di = state == 1 ? 0 : 1, dj = state == 2 ? 0 : 1;
+    uint32_t code[2];
+    bool valid[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = lane + 32 * h;
+      const int ii = i - q * di, jj = j - q * dj;
+      valid[h] = ii > 0 && jj > 0;
+      uint32_t c = 0;
+      if (valid[h]) c = msa_read_code(codes4, t.dir, ii, jj, n, ld);
+      code[h] = c;
+    }
+    bool more = true;   // warp-uniform: the run went through all 32 cells of the half
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (!more) break;
+      const int ii = i - lane * di, jj = j - lane * dj;   // this lane's cell of the half (i, j have moved past the first half)
+      // a lane stops the run: off the matrix, or (state 0) a cell that opens a gap run, or (gap states) the cell
+      // whose flag says the run was opened here -- that cell still belongs to the run
+      const bool off = !valid[h];
+      const bool turn = !off && (state == 0 ? (code[h] & 3u) != 0u : state == 1 ? (code[h] & 4u) != 0u : (code[h] & 8u) != 0u);
+      const uint32_t stops = __ballot_sync(0xffffffffu, off || turn);
+      const int s = stops ? __ffs((int)stops) - 1 : 32;             // first stopping lane
+      const bool s_turn = s < 32 && ((__ballot_sync(0xffffffffu, turn) >> s) & 1u);
+      const int count = (state != 0 && s_turn) ? s + 1 : s;         // path entries of this half
+      if (lane < count) {
+        t.path[2 * (k + (uint32_t)lane)] = state == 1 ? -1 : ii - 1;
+        t.path[2 * (k + (uint32_t)lane) + 1] = state == 2 ? -1 : jj - 1;
+      }
+      k += (uint32_t)count;
+      i -= count * di;
+      j -= count * dj;
+      if (s < 32) {
+        more = false;
+        if (s_turn) state = state == 0 ? (int)(__shfl_sync(0xffffffffu, code[h], s) & 3u) : 0;
+        // (off the matrix: i or j is 0 now, the loop ends)
+      }
+    }
+  }
+  // the rest of the longer side faces gaps
+  for (int q = lane; q < j; q += 32) { t.path[2 * (k + (uint32_t)q)] = -1; t.path[2 * (k + (uint32_t)q) + 1] = j - 1 - q; }
+  k += (uint32_t)(j > 0 ? j : 0);
+  for (int q = lane; q < i; q += 32) { t.path[2 * (k + (uint32_t)q)] = i - 1 - q; t.path[2 * (k + (uint32_t)q) + 1] = -1; }
+  k += (uint32_t)(i > 0 ? i : 0);
+  if (lane == 0) {
+    t.res->len = k;
+    t.res->pad = 0;
+    t.res->score = score;
+  }
+}
+
 __global__ void __launch_bounds__(128) msa_leaf_kernel(const MsaLeaf* leaves, uint32_t n, uint32_t nsym) {
   for (uint32_t r = blockIdx.x; r < n; r += gridDim.x) msa_leaf_phase(leaves[r], nsym, (int)threadIdx.x, (int)blockDim.x);
 }
 
-// One merge by one CTA, in score type T.  smem_bytes: dynamic shared memory of the launch; a merge whose 7
-// rolling diagonals fit uses it, any other its global scratch.
-// The sweep of one merge with its rolling diagonals at `diag`.  Called once with the shared-memory array
-// and once with the global scratch, so that each copy of the loop knows its address space (LDS/STS with
-// 32-bit offsets instead of generic 64-bit addressing).
+// The sweep of one merge with its edge arrays at `edge`.  Called once with the shared-memory array and once with
+// the global scratch, so that each copy of the loop knows its address space (LDS/STS with 32-bit offsets instead
+// of generic 64-bit addressing).
 template <typename T>
-__device__ __forceinline__ long long msa_sweep_cta(const MsaTask& t, const MsaConst& k, T* diag, const MsaTables* tab, int tid, int nt) {
-  const MsaSweep<T> sw = msa_sweep_init<T>(t, k, diag, tab);
-  const int last = sw.m + sw.n;
-  int hc = 0;
-  for (int d = 0; d <= last; ++d) {
-    msa_diag_phase<T>(sw, d, hc, tid, nt);
-    hc = hc == 2 ? 0 : hc + 1;
-    __syncthreads();   // diagonal d complete and visible to the whole CTA before d + 1 starts
+__device__ __forceinline__ long long msa_sweep_cta(const MsaTask& t, const MsaConst& k, T* edge, const MsaTables* tab, uint16_t* codes, int tid, int nt) {
+  const MsaSweep<T> sw = msa_sweep_init<T>(t, k, edge, tab, codes);
+  msa_edge_phase<T>(sw, tid, nt);
+  __syncthreads();
+  const int steps = msa_sweep_steps<T>(sw);
+  for (int st = 0; st < steps; ++st) {
+    msa_tile_phase<T>(sw, st, tid, nt);
+    __syncthreads();   // the tiles of step st complete and visible to the whole CTA before st + 1 starts
   }
   return msa_final_score<T>(sw);
 }
 
-// One merge by one CTA, in score type T.  smem_bytes: dynamic shared memory of the launch.  A merge whose 7 rolling
-// diagonals fit uses it for them (its global scratch otherwise), and one whose column-score tables fit behind the
-// diagonals copies them there after the prep phase.
+// One merge by one CTA, in score type T.  smem_bytes: dynamic shared memory of the launch.  A merge whose edge
+// arrays fit uses it for them (its global scratch otherwise), and one whose column-score tables fit behind them
+// copies them there after the prep phase.
 template <typename T>
 __device__ __forceinline__ void msa_merge_cta(const MsaTask& t, const MsaConst& k, uint32_t smem_bytes, T* smem) {
   const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
   msa_prep_phase(t, k, tid, nt);
   __syncthreads();
   long long score;
-  const size_t db = msa_round16(msa_diag_bytes(t.Lx, sizeof(T) == 4));
+  uint16_t* codes = nullptr;   // direction codes in shared memory, where they fit too
+  const size_t db = msa_round16(msa_diag_bytes(t.Lx, t.Ly, sizeof(T) == 4));
   if (db <= (size_t)smem_bytes) {
     const uint32_t Lb = msa_big_is_x(t) ? t.Lx : t.Ly, Ls = msa_big_is_x(t) ? t.Ly : t.Lx;
     const size_t pb = msa_round16((size_t)k.nsym * Lb * 4), lb = msa_round16((size_t)k.nsym * Ls * 4), nb = msa_round16((size_t)Ls * 4);
@@ -398,6 +585,8 @@ __device__ __forceinline__ void msa_merge_cta(const MsaTask& t, const MsaConst& 
       int32_t* s_pbig = reinterpret_cast<int32_t*>(base);
       uint32_t* s_lst = reinterpret_cast<uint32_t*>(base + pb);
       uint32_t* s_lnz = reinterpret_cast<uint32_t*>(base + pb + lb);
+      if (db + pb + lb + nb + msa_round16(msa_code_bytes(t.Lx, t.Ly)) <= (size_t)smem_bytes)
+        codes = reinterpret_cast<uint16_t*>(base + pb + lb + nb);
       for (uint32_t q = (uint32_t)tid; q < k.nsym * Lb; q += (uint32_t)nt) s_pbig[q] = t.pbig[q];
       for (uint32_t q = (uint32_t)tid; q < Ls; q += (uint32_t)nt) {
         const uint32_t nz = t.lnz[q];
@@ -406,14 +595,14 @@ __device__ __forceinline__ void msa_merge_cta(const MsaTask& t, const MsaConst& 
       }
       __syncthreads();
       const MsaTables tab{s_pbig, s_lst, s_lnz};
-      score = msa_sweep_cta<T>(t, k, smem, &tab, tid, nt);
+      score = msa_sweep_cta<T>(t, k, smem, &tab, codes, tid, nt);
     } else {
-      score = msa_sweep_cta<T>(t, k, smem, nullptr, tid, nt);
+      score = msa_sweep_cta<T>(t, k, smem, nullptr, nullptr, tid, nt);
     }
   } else {
-    score = msa_sweep_cta<T>(t, k, reinterpret_cast<T*>(t.diag), nullptr, tid, nt);
+    score = msa_sweep_cta<T>(t, k, reinterpret_cast<T*>(t.diag), nullptr, nullptr, tid, nt);
   }
-  if (tid == 0) msa_walk_phase(t, score);
+  if (tid < 32) msa_walk_warp(t, score, tid, codes);
   __syncthreads();
   msa_build_phase(t, k, tid, nt);
 }

@@ -5,6 +5,9 @@
 // exact planning code is checked against the oracle without a GPU.  No alignment arithmetic lives here.
 #pragma once
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -24,7 +27,7 @@ class MsaDevice {
   virtual bool d2h(void* dst, const void* src, size_t bytes) = 0;   // complete on return, after all earlier work
   virtual bool fill(void* dst, int byte, size_t bytes) = 0;
   virtual bool launch_leaves(const MsaLeaf* d_leaves, uint32_t n, uint32_t nsym) = 0;
-  // smem_bytes: shared memory per CTA for the rolling diagonals (merges that need more use their global scratch)
+  // smem_bytes: shared memory per CTA for the sweep's edge arrays (merges that need more use their global scratch)
   virtual bool launch_merges(const MsaTask* d_tasks, uint32_t count, uint32_t threads, uint32_t smem_bytes, const MsaConst& k) = 0;
   virtual bool launch_rows(const MsaRows& p) = 0;
 };
@@ -41,7 +44,8 @@ struct MsaJob {
   const char* letters = "";            // nsym characters
   size_t scratch_budget = (size_t)4 << 30;   // scratch bytes one launch may use (at least one merge always runs)
   bool force_wide = false;              // tests: int64 sweep even where int32 would do
-  uint32_t cells_per_thread = 1;        // CTA size = longest diagonal / this (tuning knob; any value is correct)
+  uint32_t cells_per_thread = 1;        // CTA size = longest diagonal of tiles / this (tuning knob; any value is correct)
+  uint32_t device_sms = 148;            // SMs of the device (CTA-size policy only)
   const volatile int* cancel = nullptr; // "Stop" (SeqEditMainWin.cpp:803-812): polled before every launch
 };
 
@@ -135,7 +139,7 @@ inline int msa_progressive(MsaDevice& dev, const MsaJob& job, MsaOut& out) {
   auto scratch_of = [&](uint32_t Lx, uint32_t Ly) -> Scratch {
     const size_t mn = std::min(Lx, Ly), mx = std::max<size_t>(std::max(Lx, Ly), 1);
     Scratch q;
-    q.diag = msa_align(msa_diag_bytes(Lx, false));
+    q.diag = msa_align(msa_diag_bytes(Lx, Ly, false));
     q.pbig = msa_align((size_t)nsym * mx * 4);
     q.lst = msa_align((size_t)nsym * mx * 4);
     q.lnz = msa_align(mx * 4);
@@ -150,6 +154,8 @@ inline int msa_progressive(MsaDevice& dev, const MsaJob& job, MsaOut& out) {
     const uint32_t x = job.left[t], y = job.right[t];
     return !job.force_wide && msa_fits_narrow(size[x], size[y], ncol[x], ncol[y], max_abs_s, job.go, job.ge);
   };
+  const char* trace_env = getenv("TSQ_MSA_DEBUG");
+  const bool trace = trace_env && atoi(trace_env) >= 2;
   for (uint32_t lv = 1; lv <= nlevels; lv++) {
     const std::vector<uint32_t>& ms = by_level[lv];
     size_t b = 0;
@@ -165,11 +171,13 @@ inline int msa_progressive(MsaDevice& dev, const MsaJob& job, MsaOut& out) {
         if (e > b && bytes + need > job.scratch_budget) break;
         bytes += need;
         longest = std::max(longest, std::min(Lx, Ly) + 1);
-        // shared memory of the launch: the rolling diagonals of every merge that fits, and behind them the
+        // shared memory of the launch: the sweep's edge arrays of every merge that fits, and behind them the
         // column-score tables where those fit too (msa.cuh: msa_merge_cta decides per merge with the same sizes)
-        const size_t db = msa_round16(msa_diag_bytes(Lx, narrow_of(t)));
+        const size_t db = msa_round16(msa_diag_bytes(Lx, Ly, narrow_of(t)));
         const size_t tb = msa_table_bytes(Lx, Ly, nsym);
-        if (db + tb <= kMsaSmemLimit) smem = std::max(smem, db + tb);
+        const size_t cb = msa_round16(msa_code_bytes(Lx, Ly));   // 4-bit direction codes, where they fit as well
+        if (db + tb + cb <= kMsaSmemLimit) smem = std::max(smem, db + tb + cb);
+        else if (db + tb <= kMsaSmemLimit) smem = std::max(smem, db + tb);
         else if (db <= kMsaSmemLimit) smem = std::max(smem, db);
         e++;
       }
@@ -207,14 +215,22 @@ inline int msa_progressive(MsaDevice& dev, const MsaJob& job, MsaOut& out) {
         k.res = d_res + slot + (q - b);
       }
       if (!dev.h2d(sc, tasks.data(), count * sizeof(MsaTask))) return MSA_DEVICE;
-      // one thread per cell of the longest diagonal (cells_per_thread = 1), or fewer, fatter threads
-      const uint32_t per_thread = std::max<uint32_t>(job.cells_per_thread, 1u);
+      // one thread per tile of the longest anti-diagonal of tiles (cells_per_thread = 1), or fewer threads that take
+      // several tiles each; never under 128, for the column-parallel phases around the sweep
+      const uint32_t per_thread = std::max<uint32_t>(job.cells_per_thread, 1u) * (uint32_t)kMsaTile;
       const uint32_t want = (longest + per_thread - 1) / per_thread;
-      const uint32_t threads = std::min<uint32_t>(1024u, std::max<uint32_t>(64u, (want + 31u) & ~31u));
+      // the column-parallel phases around the sweep (letter scores: nsym^2 multiply-adds per column) want many threads;
+      // a level with more merges than the device holds CTAs of 512 threads wants many CTAs per SM instead
+      const uint32_t floor_threads = count <= job.device_sms ? 512u : count <= 2 * job.device_sms ? 256u : 128u;
+      const uint32_t threads = std::min<uint32_t>(512u, std::max<uint32_t>(floor_threads, (want + 31u) & ~31u));
+      const auto t_l0 = std::chrono::steady_clock::now();
       if (!dev.launch_merges((const MsaTask*)sc, (uint32_t)count, threads, (uint32_t)smem, kc)) return MSA_DEVICE;
       out.launches++;
       res.resize(count);
       if (!dev.d2h(res.data(), d_res + slot, count * sizeof(MsaResult))) return MSA_DEVICE;
+      if (trace)   // TSQ_MSA_DEBUG=2: one line per launch (launch + wait + read-back of the merged lengths)
+        fprintf(stderr, "tsq_msa: level %u: %zu merges, longest diagonal %u, %u threads, %zu B shared, %.3f ms\n", lv, count, longest,
+                threads, smem, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_l0).count());
       for (size_t q = b; q < e; q++) {
         const uint32_t t = ms[q], z = n + t;
         const MsaResult& r = res[q - b];

@@ -1687,14 +1687,29 @@ int multi_prepare_first_device(tsq_ctx* c) {
 extern "C" {
 
 int tsq_detect_alphabet(const char* const* residues, const uint32_t* lengths, uint32_t n) {
-  unsigned long long letters = 0, nuc = 0;
-  for (uint32_t i = 0; i < n && residues && lengths; i++)
-    for (uint32_t k = 0; residues[i] && k < lengths[i]; k++) {
-      const unsigned char ch = (unsigned char)residues[i][k];
-      if (!isalpha(ch)) continue;
-      letters++;
-      if (strchr("ACGTUNacgtun", ch)) nuc++;
+  // class of a byte: 1 = letter, 3 = letter of ACGTUN; counted per byte value first (one table look-up per residue)
+  static const struct Cls {
+    uint8_t v[256];
+    Cls() {
+      for (int b = 0; b < 256; b++) {
+        const bool letter = (b >= 'A' && b <= 'Z') || (b >= 'a' && b <= 'z');
+        v[b] = !letter ? 0 : (b != 0 && strchr("ACGTUNacgtun", b)) ? 3 : 1;
+      }
     }
+  } cls;
+  unsigned long long letters = 0, nuc = 0;
+  for (uint32_t i = 0; i < n && residues && lengths; i++) {
+    if (!residues[i]) continue;
+    const unsigned char* r = reinterpret_cast<const unsigned char*>(residues[i]);
+    unsigned long long l = 0, u = 0;
+    for (uint32_t k = 0; k < lengths[i]; k++) {
+      const unsigned v = cls.v[r[k]];
+      l += v & 1u;
+      u += v >> 1;
+    }
+    letters += l;
+    nuc += u;
+  }
   return (letters > 0 && nuc * 10 >= letters * 9) ? TSQ_NUCLEOTIDE : TSQ_PROTEIN;
 }
 
@@ -2602,6 +2617,7 @@ int tsq_msa(tsq_ctx* c, const char** rows, uint32_t* nrows, uint32_t* ncols, con
     job.letters = letters_of(c);
     job.cancel = c->msa_cancel;
     if (const char* e = getenv("TSQ_MSA_CELLS_PER_THREAD")) job.cells_per_thread = (uint32_t)std::max(1, atoi(e));   // tuning runs
+    job.device_sms = (uint32_t)std::max(1, c->sm_count);
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) job.scratch_budget = std::max<size_t>(free_b / 4, (size_t)256 << 20);
     else cudaGetLastError();
@@ -2968,38 +2984,54 @@ int tsq_run_fasta(const char* fin, const char* fout, const tsq_params* params, t
   auto say = [&](const std::string& s) { if (log) log(user, s.c_str()); };
   const double t_start = now_ms();
   double t_read = 0, t_create = 0, t_dist = 0, t_files = 0, t_align = 0;   // stage split of the call (last log line)
-  std::ifstream in(fin);
-  if (!in) {
-    say(std::string("cannot open ") + fin);
-    return TSQ_ERR_IO;
+  // the whole file in one read, then lines by memchr (the state machine is the reference reader's, FASTAFile.cpp:96-140)
+  std::string text;
+  {
+    FILE* f = fopen(fin, "rb");
+    if (!f) {
+      say(std::string("cannot open ") + fin);
+      return TSQ_ERR_IO;
+    }
+    char chunk[1 << 16];
+    size_t got;
+    while ((got = fread(chunk, 1, sizeof chunk, f)) > 0) text.append(chunk, got);
+    const bool bad = ferror(f) != 0;
+    fclose(f);
+    if (bad) {
+      say(std::string("cannot read ") + fin);
+      return TSQ_ERR_IO;
+    }
   }
   std::vector<std::string> labels, headers, seqs;
-  std::string line;
   int state = 0;  // 0 seeking header, 1 just read header, 2 reading residues
-  auto trim = [](std::string& s) {
-    size_t a = 0, b = s.size();
-    while (a < b && isspace((unsigned char)s[a])) a++;
-    while (b > a && isspace((unsigned char)s[b - 1])) b--;
-    s = s.substr(a, b - a);
+  auto add_header = [&](const char* a, size_t len) {
+    // label: what follows the marker up to the first blank from position 1 on (find(' ', 1) of the old reader)
+    const char* sp = len > 1 ? static_cast<const char*>(memchr(a + 1, ' ', len - 1)) : nullptr;
+    labels.emplace_back(a + 1, sp ? (size_t)(sp - a - 1) : len - 1);
+    headers.emplace_back(a, len);
+    seqs.emplace_back();
+    state = 1;
   };
-  auto label_of = [](const std::string& h) {
-    const size_t sp = h.find(' ', 1);
-    return sp == std::string::npos ? h.substr(1) : h.substr(1, sp - 1);
-  };
-  while (std::getline(in, line)) {
-    trim(line);
-    if (line.empty()) continue;
-    const char f = line[0];
+  for (size_t pos = 0; pos < text.size();) {
+    const char* a = text.data() + pos;
+    const char* nl = static_cast<const char*>(memchr(a, '\n', text.size() - pos));
+    const char* b = nl ? nl : text.data() + text.size();
+    pos = (size_t)(b - text.data()) + 1;
+    while (a < b && isspace((unsigned char)*a)) a++;           // trim
+    while (b > a && isspace((unsigned char)b[-1])) b--;
+    if (a == b) continue;
+    const size_t len = (size_t)(b - a);
+    const char f = *a;
     const bool hdr = (f == '>' || f == ';');
     if (state == 0) {
-      if (hdr) { labels.push_back(label_of(line)); headers.push_back(line); seqs.emplace_back(); state = 1; }
+      if (hdr) add_header(a, len);
     } else if (state == 1) {
       if (f == ';') continue;
-      seqs.back() += line;   // whatever follows a header is residues, a second '>' line included (FASTAFile.cpp:117-124)
+      seqs.back().append(a, len);   // whatever follows a header is residues, a second '>' line included (FASTAFile.cpp:117-124)
       state = 2;
     } else {
-      if (hdr) { labels.push_back(label_of(line)); headers.push_back(line); seqs.emplace_back(); state = 1; }
-      else seqs.back() += line;
+      if (hdr) add_header(a, len);
+      else seqs.back().append(a, len);
     }
   }
   char msg[256];

@@ -358,10 +358,10 @@ cudaError_t msa_leaf_launch(const MsaLeaf* d_leaves, uint32_t n, uint32_t nsym, 
 cudaError_t msa_merge_launch(const MsaTask* d_tasks, uint32_t count, uint32_t threads, uint32_t smem_bytes, const MsaConst& k,
                              cudaStream_t stream) {
   if (count == 0) return cudaSuccess;
-  if (threads < 32 || threads > 1024 || (threads & 31u) || smem_bytes > 227u * 1024u) return cudaErrorInvalidValue;
-  // two compilations of the same kernel: up to 512 threads per CTA with 128 registers each (no spills),
-  // up to 1 024 with 64
-  auto kern = threads <= 512 ? msa_merge_kernel<512> : msa_merge_kernel<1024>;
+  if (threads < 32 || threads > 512 || (threads & 31u) || smem_bytes > 227u * 1024u) return cudaErrorInvalidValue;
+  // one thread per 4 x 4 tile of the longest anti-diagonal of tiles: 512 threads cover 2 048 columns at once (longer
+  // ones loop), with 128 registers each -- the tile's 16 column scores and its edges live in registers, no spills
+  auto kern = msa_merge_kernel<512>;
   if (smem_bytes > 48u * 1024u) {   // above the default limit the kernel must opt in (per device, cheap to repeat)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
