@@ -58,16 +58,25 @@ class EmulDevice : public tsq::MsaDevice {
     uint16_t* codes = nullptr;   // 4-bit direction codes behind the edge arrays and the column-score tables
     if (db <= (size_t)smem_bytes) {
       const uint32_t Lb = tsq::msa_big_is_x(t) ? t.Lx : t.Ly, Ls = tsq::msa_big_is_x(t) ? t.Ly : t.Lx;
-      const size_t pb = tsq::msa_round16((size_t)k.nsym * Lb * 4), lb = tsq::msa_round16((size_t)k.nsym * Ls * 4),
-                   nb = tsq::msa_round16((size_t)Ls * 4);
+      const uint32_t nsmall = tsq::msa_big_is_x(t) ? t.ny : t.nx;
+      const size_t pb = tsq::msa_round16((size_t)k.nsym * Lb * 4),
+                   lb = tsq::msa_round16((size_t)tsq::msa_list_rows(k.nsym, nsmall) * Ls * 4), nb = tsq::msa_round16((size_t)Ls * 4);
       if (db + pb + lb + nb + tsq::msa_round16(tsq::msa_code_bytes(t.Lx, t.Ly)) <= (size_t)smem_bytes)
         codes = reinterpret_cast<uint16_t*>(static_cast<char*>(shared) + db + pb + lb + nb);
     }
     each_thread(nt, [&](int tid) { tsq::msa_prep_phase(t, k, tid, nt); });
     const tsq::MsaSweep<T> sw = tsq::msa_sweep_init<T>(t, k, edge, nullptr, codes);
-    each_thread(nt, [&](int tid) { tsq::msa_edge_phase<T>(sw, tid, nt); });
+    // barrier by barrier as msa_sweep_cta: tile threads and column-score workers share an interval
+    const int tw = tsq::msa_tile_threads(t.Lx, t.Ly, nt);
+    each_thread(nt, [&](int tid) { tsq::msa_edge_phase<T>(sw, tid, nt); tsq::msa_sub_phase<T>(sw, 0, tid, nt); });
     const int steps = tsq::msa_sweep_steps<T>(sw);
-    for (int st = 0; st < steps; ++st) each_thread(nt, [&](int tid) { tsq::msa_tile_phase<T>(sw, st, tid, nt); });
+    for (int st = 0; st < steps; ++st) {
+      each_thread(nt, [&](int tid) {
+        if (tid < tw) tsq::msa_tile_phase<T>(sw, st, tid, tw);
+        else tsq::msa_sub_phase<T>(sw, st + 1, tid - tw, nt - tw);
+      });
+      if (tw == nt) each_thread(nt, [&](int tid) { tsq::msa_sub_phase<T>(sw, st + 1, tid, nt); });
+    }
     tsq::msa_walk_phase(t, tsq::msa_final_score<T>(sw), codes);
   }
   bool launch_leaves(const tsq::MsaLeaf* l, uint32_t n, uint32_t nsym) override {

@@ -111,8 +111,16 @@ template <> struct MsaNeg<int32_t> { static constexpr int32_t v = -(1 << 30); };
 // crosses a tile edge lives in five small arrays: H and F of the last finished row, per column (Ly + 1 each), H and
 // E of the last finished column, per row (Lx + 1 each), and per tile row the corner H(i0 - 1, j0 - 1) of its next tile.
 constexpr int kMsaTile = 4;
+// Column scores do not come from the tile's own thread: while the tile threads run step st, the CTA's OTHER warps
+// compute the scores of step st + 1 (one cell per worker at a time: a big x big merge has ~20 letters per column,
+// and that serial chain inside the tile thread was 4/5 of its step) into one of two buffers of 16 scores per tile.
+TSQ_HD size_t msa_tiles_per_step(uint32_t Lx, uint32_t Ly) {
+  const size_t a = ((size_t)Lx + kMsaTile - 1) / kMsaTile, b = ((size_t)Ly + kMsaTile - 1) / kMsaTile;
+  return a < b ? a : b;
+}
 TSQ_HD size_t msa_diag_bytes(uint32_t Lx, uint32_t Ly, bool narrow) {
-  return (2 * ((size_t)Ly + 1) + 2 * ((size_t)Lx + 1) + ((size_t)Lx + kMsaTile - 1) / kMsaTile + 1) *
+  return (2 * ((size_t)Ly + 1) + 2 * ((size_t)Lx + 1) + ((size_t)Lx + kMsaTile - 1) / kMsaTile + 1 +
+          2 * msa_tiles_per_step(Lx, Ly) * kMsaTile * kMsaTile + 4) *
          (narrow ? sizeof(int32_t) : sizeof(long long));
 }
 
@@ -134,9 +142,11 @@ TSQ_HD uint32_t msa_read_code(const uint16_t* codes, const uint8_t* dir, int i, 
 // them from there: the dependent chain list length -> letter -> letter score is then three shared-memory loads per
 // diagonal instead of three L2 round trips (which were most of the ~1 000 clocks a diagonal took in r01).
 TSQ_HD size_t msa_round16(size_t x) { return (x + 15) & ~(size_t)15; }
-TSQ_HD size_t msa_table_bytes(uint32_t Lx, uint32_t Ly, uint32_t nsym) {
+// rows of the small side's letter lists: a column of n sequences holds at most min(nsym, n) distinct letters
+TSQ_HD uint32_t msa_list_rows(uint32_t nsym, uint32_t nsmall) { return nsmall < nsym ? nsmall : nsym; }
+TSQ_HD size_t msa_table_bytes(uint32_t Lx, uint32_t Ly, uint32_t nsym, uint32_t nsmall) {
   const size_t mx = Lx > Ly ? Lx : Ly;   // either side may be the big one: size for the longer
-  return msa_round16((size_t)nsym * mx * 4) + msa_round16((size_t)nsym * mx * 4) + msa_round16(mx * 4);
+  return msa_round16((size_t)nsym * mx * 4) + msa_round16((size_t)msa_list_rows(nsym, nsmall) * mx * 4) + msa_round16(mx * 4);
 }
 
 // Whether the whole DP of a merge stays inside +-2^29, so that the sweep may run in int32 with -2^30 as
@@ -201,6 +211,7 @@ struct MsaSweep {
   uint32_t ld;           // min(m, n) + 1: one diagonal of direction bytes
   uint32_t Lb, Ls;       // columns of the big / small side
   bool bx;               // the big side is X
+  bool single;           // the small side is ONE sequence: at most one letter per column, scored inside the tile thread
   const uint32_t* lnz;
   const uint32_t* lst;
   const int32_t* pbig;
@@ -211,6 +222,8 @@ struct MsaSweep {
   T* Hcol;               // [m + 1] H of the last finished column, per row
   T* Ecol;               // [m + 1] E of it
   T* corner;             // [ntr + 1] H(i0 - 1, j0 - 1) of the next tile of a tile row
+  T* subbuf;             // 2 x [tiles per step][16] column scores: step st reads half st & 1
+  uint32_t subhalf;      // scores in one half
 };
 
 struct MsaTables {       // where the sweep reads the column-score tables from (the task's scratch, or shared memory)
@@ -229,6 +242,7 @@ TSQ_HD MsaSweep<T> msa_sweep_init(const MsaTask& t, const MsaConst& k, void* edg
   s.ld = (t.Lx < t.Ly ? t.Lx : t.Ly) + 1;
   s.bx = msa_big_is_x(t);
   s.Lb = s.bx ? t.Lx : t.Ly; s.Ls = s.bx ? t.Ly : t.Lx;
+  s.single = (s.bx ? t.ny : t.nx) == 1;
   s.lnz = tab ? tab->lnz : t.lnz;
   s.lst = tab ? tab->lst : t.lst;
   s.pbig = tab ? tab->pbig : t.pbig;
@@ -239,6 +253,9 @@ TSQ_HD MsaSweep<T> msa_sweep_init(const MsaTask& t, const MsaConst& k, void* edg
   s.Hcol = s.Frow + (s.n + 1);
   s.Ecol = s.Hcol + (s.m + 1);
   s.corner = s.Ecol + (s.m + 1);
+  s.subbuf = s.corner + (s.ntr + 1);
+  s.subbuf += (4 - ((s.subbuf - (T*)edge) & 3)) & 3;   // a tile's 16 scores start on a 4-element boundary
+  s.subhalf = (uint32_t)(msa_tiles_per_step(t.Lx, t.Ly) * kMsaTile * kMsaTile);
   return s;
 }
 
@@ -271,7 +288,10 @@ TSQ_HD void msa_edge_phase(const MsaSweep<T>& s, int tid, int nt) {
 // The cells of one tile, row by row out of registers.  FULL: all kMsaTile x kMsaTile cells exist -- no guards, one
 // straight-line block in which the scheduler interleaves the independent cells of the tile's own anti-diagonals (a
 // thread's dependent chain is 7 cells long, not 16).
-template <typename T, bool FULL>
+// CODES4: the direction codes go to the 4-bit array in shared memory, one 16-bit store per tile row; else one byte per
+// cell to the diagonal-major array in global scratch.  A template argument, not a test per cell: a branch inside the
+// block would end the scheduler's window at every cell and serialise the tile.
+template <typename T, bool FULL, bool CODES4>
 TSQ_HD void msa_tile_cells(const MsaSweep<T>& s, int I, int i0, int j0, int ih, int jw, const T (&sub)[kMsaTile][kMsaTile]) {
   constexpr int TB = kMsaTile;
   // ---- edges in ----
@@ -314,8 +334,9 @@ TSQ_UNROLL
           if (E > H) H = E;
           if (F > H) H = F;
           const uint32_t code = (H == dg ? 0u : (H == E ? 1u : 2u)) | (eo ? 4u : 0u) | (fo ? 8u : 0u);
-          rowcodes |= code << (4 * c);
-          if (!s.codes) {
+          if (CODES4) {
+            rowcodes |= code << (4 * c);
+          } else {
             const int d = i + j;
             s.dir[(size_t)d * ld + (size_t)(i - (d > s.n ? d - s.n : 0))] = (uint8_t)code;
           }
@@ -326,7 +347,7 @@ TSQ_UNROLL
       }
       s.Hcol[i] = h;                       // H(i, j0 + jw - 1), E of it
       s.Ecol[i] = e;
-      if (s.codes) s.codes[(size_t)(i - 1) * msa_code_row_words((uint32_t)s.n) + (uint32_t)((j0 - 1) >> 2)] = (uint16_t)rowcodes;
+      if (CODES4) s.codes[(size_t)(i - 1) * msa_code_row_words((uint32_t)s.n) + (uint32_t)((j0 - 1) >> 2)] = (uint16_t)rowcodes;
     }
   }
   // ---- edges out ----
@@ -335,66 +356,94 @@ TSQ_UNROLL
     if (FULL || c < jw) { s.Hrow[j0 + c] = th[c]; s.Frow[j0 + c] = tf[c]; }
 }
 
+// The column scores of step st, sub(i, j) = sum over the small side's letters of count * letter score of the big
+// side: worker w of nw takes the cells w, w + nw, ... of the step's tiles (16 per tile, row-major; cells off the
+// matrix stay unwritten and unread).
+template <typename T>
+TSQ_HD void msa_sub_phase(const MsaSweep<T>& s, int st, int w, int nw) {
+  constexpr int TB = kMsaTile;
+  if (s.single || st >= msa_sweep_steps<T>(s)) return;   // (a single sequence's scores come out of the tile thread)
+  const int Ilo = st >= s.ntc ? st - s.ntc + 1 : 0;
+  const int Ihi = st < s.ntr ? st : s.ntr - 1;
+  T* const out = s.subbuf + (size_t)(st & 1) * s.subhalf;
+  const int ncell = (Ihi - Ilo + 1) * TB * TB;
+  for (int f = w; f < ncell; f += nw) {
+    const int I = Ilo + (f >> 4), r = (f >> 2) & 3, c = f & 3;
+    const int i = I * TB + 1 + r, j = (st - I) * TB + 1 + c;
+    if (i > s.m || j > s.n) continue;
+    const uint32_t colb = (uint32_t)(s.bx ? i - 1 : j - 1), cols = (uint32_t)(s.bx ? j - 1 : i - 1);
+    const uint32_t nz = s.lnz[cols];
+    const uint32_t* le = s.lst + cols;
+    const int32_t* pb = s.pbig + colb;
+    T sub = 0;
+    TSQ_NO_UNROLL
+    for (uint32_t q = 0; q < nz; ++q, le += s.Ls) {
+      const uint32_t e = *le;
+      sub += (T)(e & 0xffffffu) * (T)pb[(e >> 24) * s.Lb];
+    }
+    out[f] = sub;
+  }
+}
+
 // One step: the tiles (I, J) with I + J == st; thread tid takes tile row Ilo + tid (+ nt, ...).  Rows i0 .. i0 + ih - 1,
-// columns j0 .. j0 + jw - 1 of the matrix (1-based cells).  All column scores of the tile first (loads only: they
-// overlap), then the cells.
+// columns j0 .. j0 + jw - 1 of the matrix (1-based cells).  The tile's column scores were left by msa_sub_phase.
 template <typename T>
 TSQ_HD void msa_tile_phase(const MsaSweep<T>& s, int st, int tid, int nt) {
   constexpr int TB = kMsaTile;
   const int Ilo = st >= s.ntc ? st - s.ntc + 1 : 0;
   const int Ihi = st < s.ntr ? st : s.ntr - 1;
+  const T* const in = s.subbuf + (size_t)(st & 1) * s.subhalf;
   for (int I = Ilo + tid; I <= Ihi; I += nt) {
     const int J = st - I;
     const int i0 = I * TB + 1, j0 = J * TB + 1;
     const int ih = s.m - i0 + 1 < TB ? s.m - i0 + 1 : TB;
     const int jw = s.n - j0 + 1 < TB ? s.n - j0 + 1 : TB;
     const bool full = ih == TB && jw == TB;
-    // ---- column scores sub(i, j) = sum over the small side's letters of count * letter score of the big side ----
     T sub[TB][TB];
-    // the small side runs along j when the big side is X (one letter list per tile column, used by every row),
-    // along i otherwise; a0 / b0: first small-side / big-side column of the tile, na / nb: how many
-    const uint32_t a0 = (uint32_t)(s.bx ? j0 : i0) - 1, b0 = (uint32_t)(s.bx ? i0 : j0) - 1;
-    const int na = s.bx ? jw : ih, nb = s.bx ? ih : jw;
-    uint32_t nz[TB];
-TSQ_UNROLL
-    for (int a = 0; a < TB; ++a) nz[a] = (full || a < na) ? s.lnz[a0 + a] : 0u;
-    T sa[TB][TB];        // [small-side column][big-side column]
-    if (full && nz[0] == 1u && nz[1] == 1u && nz[2] == 1u && nz[3] == 1u) {
-      // one letter per small-side column (a single sequence joins a profile: the common shape): straight-line
+    if (s.single) {
+      // one sequence on the small side: one letter (or none) per small-side column, 4 loads + 16 loads + 16 products,
+      // straight-line.  The small side runs along j when the big side is X, along i otherwise; a0 / b0: first
+      // small-side / big-side column of the tile, na / nb: how many of each exist
+      const uint32_t a0 = (uint32_t)(s.bx ? j0 : i0) - 1, b0 = (uint32_t)(s.bx ? i0 : j0) - 1;
+      const int na = s.bx ? jw : ih, nb = s.bx ? ih : jw;
+      T sa[TB][TB];      // [small-side column][big-side column]
       uint32_t e[TB];
 TSQ_UNROLL
-      for (int a = 0; a < TB; ++a) e[a] = s.lst[a0 + a];
+      for (int a = 0; a < TB; ++a) e[a] = ((full || a < na) && s.lnz[a0 + a] != 0u) ? s.lst[a0 + a] : 0u;   // count 0: scores 0
 TSQ_UNROLL
       for (int a = 0; a < TB; ++a) {
         const int32_t* pb = s.pbig + (size_t)(e[a] >> 24) * s.Lb + b0;
         const T cnt = (T)(e[a] & 0xffffffu);
 TSQ_UNROLL
-        for (int b = 0; b < TB; ++b) sa[a][b] = cnt * (T)pb[b];
+        for (int b = 0; b < TB; ++b) sa[a][b] = (full || b < nb) ? cnt * (T)pb[b] : (T)0;
       }
+TSQ_UNROLL
+      for (int r = 0; r < TB; ++r)
+TSQ_UNROLL
+        for (int c = 0; c < TB; ++c) sub[r][c] = s.bx ? sa[c][r] : sa[r][c];
     } else {
+      const T* const mine = in + (size_t)(I - Ilo) * (TB * TB);
 TSQ_UNROLL
-      for (int a = 0; a < TB; ++a) {
+      for (int r = 0; r < TB; ++r)
 TSQ_UNROLL
-        for (int b = 0; b < TB; ++b) sa[a][b] = 0;
-        const uint32_t* le = s.lst + a0 + a;
-        TSQ_NO_UNROLL
-        for (uint32_t q = 0; q < nz[a]; ++q, le += s.Ls) {
-          const uint32_t e = *le;
-          const T cnt = (T)(e & 0xffffffu);
-          const int32_t* pb = s.pbig + (size_t)(e >> 24) * s.Lb + b0;
-TSQ_UNROLL
-          for (int b = 0; b < TB; ++b)
-            if (full || b < nb) sa[a][b] += cnt * (T)pb[b];
-        }
-      }
+        for (int c = 0; c < TB; ++c) sub[r][c] = (full || (r < ih && c < jw)) ? mine[r * TB + c] : (T)0;
     }
-TSQ_UNROLL
-    for (int r = 0; r < TB; ++r)
-TSQ_UNROLL
-      for (int c = 0; c < TB; ++c) sub[r][c] = s.bx ? sa[c][r] : sa[r][c];
-    if (full) msa_tile_cells<T, true>(s, I, i0, j0, ih, jw, sub);
-    else msa_tile_cells<T, false>(s, I, i0, j0, ih, jw, sub);
+    if (s.codes) {
+      if (full) msa_tile_cells<T, true, true>(s, I, i0, j0, ih, jw, sub);
+      else msa_tile_cells<T, false, true>(s, I, i0, j0, ih, jw, sub);
+    } else {
+      if (full) msa_tile_cells<T, true, false>(s, I, i0, j0, ih, jw, sub);
+      else msa_tile_cells<T, false, false>(s, I, i0, j0, ih, jw, sub);
+    }
   }
+}
+
+// How a CTA (or the emulation) of nt threads splits into tile threads and column-score workers: the first tw threads
+// run the tiles; the rest, if there is at least a warp of them, compute the next step's column scores meanwhile.
+// Otherwise everybody does both, one after the other.
+TSQ_HD int msa_tile_threads(uint32_t Lx, uint32_t Ly, int nt) {
+  const int tw = (int)((msa_tiles_per_step(Lx, Ly) + 31) & ~(size_t)31);
+  return nt - tw >= 32 ? tw : nt;
 }
 
 // phase 3, one thread.  score = H(Lx, Ly) (msa_final_score).
@@ -556,12 +605,20 @@ __global__ void __launch_bounds__(128) msa_leaf_kernel(const MsaLeaf* leaves, ui
 template <typename T>
 __device__ __forceinline__ long long msa_sweep_cta(const MsaTask& t, const MsaConst& k, T* edge, const MsaTables* tab, uint16_t* codes, int tid, int nt) {
   const MsaSweep<T> sw = msa_sweep_init<T>(t, k, edge, tab, codes);
+  const int tw = msa_tile_threads(t.Lx, t.Ly, nt);
+  const bool split = tw < nt;                 // warps tw/32 .. are column-score workers
   msa_edge_phase<T>(sw, tid, nt);
+  msa_sub_phase<T>(sw, 0, tid, nt);
   __syncthreads();
   const int steps = msa_sweep_steps<T>(sw);
   for (int st = 0; st < steps; ++st) {
-    msa_tile_phase<T>(sw, st, tid, nt);
-    __syncthreads();   // the tiles of step st complete and visible to the whole CTA before st + 1 starts
+    if (tid < tw) msa_tile_phase<T>(sw, st, tid, tw);
+    else msa_sub_phase<T>(sw, st + 1, tid - tw, nt - tw);
+    __syncthreads();   // the tiles of step st and the column scores of st + 1 complete and visible to the whole CTA
+    if (!split) {
+      msa_sub_phase<T>(sw, st + 1, tid, nt);
+      __syncthreads();
+    }
   }
   return msa_final_score<T>(sw);
 }
@@ -579,7 +636,8 @@ __device__ __forceinline__ void msa_merge_cta(const MsaTask& t, const MsaConst& 
   const size_t db = msa_round16(msa_diag_bytes(t.Lx, t.Ly, sizeof(T) == 4));
   if (db <= (size_t)smem_bytes) {
     const uint32_t Lb = msa_big_is_x(t) ? t.Lx : t.Ly, Ls = msa_big_is_x(t) ? t.Ly : t.Lx;
-    const size_t pb = msa_round16((size_t)k.nsym * Lb * 4), lb = msa_round16((size_t)k.nsym * Ls * 4), nb = msa_round16((size_t)Ls * 4);
+    const uint32_t nsmall = msa_big_is_x(t) ? t.ny : t.nx;
+    const size_t pb = msa_round16((size_t)k.nsym * Lb * 4), lb = msa_round16((size_t)msa_list_rows(k.nsym, nsmall) * Ls * 4), nb = msa_round16((size_t)Ls * 4);
     if (db + pb + lb + nb <= (size_t)smem_bytes) {
       char* base = reinterpret_cast<char*>(smem) + db;
       int32_t* s_pbig = reinterpret_cast<int32_t*>(base);

@@ -174,7 +174,7 @@ inline int msa_progressive(MsaDevice& dev, const MsaJob& job, MsaOut& out) {
         // shared memory of the launch: the sweep's edge arrays of every merge that fits, and behind them the
         // column-score tables where those fit too (msa.cuh: msa_merge_cta decides per merge with the same sizes)
         const size_t db = msa_round16(msa_diag_bytes(Lx, Ly, narrow_of(t)));
-        const size_t tb = msa_table_bytes(Lx, Ly, nsym);
+        const size_t tb = msa_table_bytes(Lx, Ly, nsym, std::min(size[job.left[t]], size[job.right[t]]));
         const size_t cb = msa_round16(msa_code_bytes(Lx, Ly));   // 4-bit direction codes, where they fit as well
         if (db + tb + cb <= kMsaSmemLimit) smem = std::max(smem, db + tb + cb);
         else if (db + tb <= kMsaSmemLimit) smem = std::max(smem, db + tb);

@@ -315,13 +315,21 @@ cudaError_t upgma_launch(const UpgmaParams& p, cudaStream_t stream) {
   upgma_init_kernel<<<grid, 256, 0, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  // One matrix entry per thread and step at n = 1 000: fewer, fatter threads were measured and are slower (r02,
+  // profiles/upgma_threads_r02.txt: 5.8 ms at 1 024 threads, 6.4 at 512, 8.6 at 256 -- the step is the latency of its
+  // row re-scans, which more threads hide better).  TSQ_UPGMA_THREADS: the tuning override that sweep used.
+  unsigned int threads = (unsigned)UPGMA_THREADS;
+  if (const char* ev = getenv("TSQ_UPGMA_THREADS")) {
+    const int t = atoi(ev);
+    if (t >= 32 && t <= UPGMA_THREADS && (t & 31) == 0) threads = (unsigned)t;
+  }
   if (p.n <= UPGMA_SMEM_N) {
     const size_t smem = (size_t)p.n * (sizeof(double) + sizeof(uint32_t) + 1) + 16;
     e = cudaFuncSetAttribute(upgma_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    upgma_merge_kernel<true><<<1, UPGMA_THREADS, smem, stream>>>(p);
+    upgma_merge_kernel<true><<<1, threads, smem, stream>>>(p);
   } else {
-    upgma_merge_kernel<false><<<1, UPGMA_THREADS, 0, stream>>>(p);
+    upgma_merge_kernel<false><<<1, threads, 0, stream>>>(p);
   }
   return cudaGetLastError();
 }

@@ -96,11 +96,13 @@ __device__ __forceinline__ void upgma_block_argmin(double& v, uint32_t& i, uint3
     if (upgma_less(v2, i2, j2, v, i, j)) { v = v2; i = i2; j = j2; }
   }
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int nwarps = (int)(blockDim.x >> 5);
   __syncthreads();
   if (l == 0) { sv[w] = v; si[w] = i; sj[w] = j; }
   __syncthreads();
   if (w == 0) {
-    v = sv[l]; i = si[l]; j = sj[l];
+    if (l < nwarps) { v = sv[l]; i = si[l]; j = sj[l]; }
+    else { v = __longlong_as_double(0x7ff0000000000000ll); i = 0xffffffffu; j = 0xffffffffu; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
@@ -133,8 +135,9 @@ __global__ void __launch_bounds__(UPGMA_THREADS, 1) upgma_merge_kernel(const __g
   uint8_t* act8 = reinterpret_cast<uint8_t*>(rowarg + n);   // SMEM only
   uint32_t* const rescan = p.rescan;
   const uint32_t tid = threadIdx.x;
+  const uint32_t NT = blockDim.x;   // UPGMA_THREADS unless a tuning run asks for fewer (upgma_launch)
   if (SMEM) {
-    for (uint32_t i = tid; i < n; i += UPGMA_THREADS) {
+    for (uint32_t i = tid; i < n; i += NT) {
       rowmin[i] = p.rowmin[i];
       rowarg[i] = p.rowarg[i];
       act8[i] = 1;
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(UPGMA_THREADS, 1) upgma_merge_kernel(const __g
     // ---- 1. the closest active pair --------------------------------------------------------------
     double v = INF;
     uint32_t a = 0xffffffffu, b = 0xffffffffu;
-    for (uint32_t i = tid; i < n; i += UPGMA_THREADS) {
+    for (uint32_t i = tid; i < n; i += NT) {
       if (is_active(i)) {
         const double rv = rowmin[i];
         const uint32_t rj = rowarg[i];
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(UPGMA_THREADS, 1) upgma_merge_kernel(const __g
     const double da = (double)sa, db = (double)sb, dsum = (double)(sa + sb);
     double* Da = p.D + (size_t)a * n;
     const double* Db = p.D + (size_t)b * n;
-    for (uint32_t k = tid; k < n; k += UPGMA_THREADS) {
+    for (uint32_t k = tid; k < n; k += NT) {
       if (k == a || k == b || !is_active(k)) continue;
       const double nd = __ddiv_rn(__dadd_rn(__dmul_rn(da, Da[k]), __dmul_rn(db, Db[k])), dsum);
       Da[k] = nd;
@@ -207,15 +210,16 @@ __global__ void __launch_bounds__(UPGMA_THREADS, 1) upgma_merge_kernel(const __g
     // result in shared memory; after ONE barrier, warp r finishes row r.  (A block-wide reduction per
     // row cost three barriers each and made the barriers the kernel's top stall.)
     const uint32_t nr = nrescan;
-    for (uint32_t r0 = 0; r0 < nr; r0 += 32) {
-      const uint32_t nb = nr - r0 < 32u ? nr - r0 : 32u;
+    const uint32_t nwarps = NT >> 5;   // a batch: as many rows as the CTA has warps
+    for (uint32_t r0 = 0; r0 < nr; r0 += nwarps) {
+      const uint32_t nb = nr - r0 < nwarps ? nr - r0 : nwarps;
 #pragma unroll 4
       for (uint32_t r = 0; r < nb; ++r) {
         const uint32_t row = rescan[r0 + r];
         const double* Dr = p.D + (size_t)row * n;
         double bv = INF;
         uint32_t bj = 0xffffffffu;
-        for (uint32_t j = row + 1 + tid; j < n; j += UPGMA_THREADS) {
+        for (uint32_t j = row + 1 + tid; j < n; j += NT) {
           if (is_active(j)) {
             const double x = Dr[j];
             if (x < bv || (x == bv && j < bj)) { bv = x; bj = j; }
@@ -232,8 +236,8 @@ __global__ void __launch_bounds__(UPGMA_THREADS, 1) upgma_merge_kernel(const __g
       __syncthreads();
       if ((tid >> 5) < nb) {
         const uint32_t r = tid >> 5;
-        double bv = pv[r][tid & 31];
-        uint32_t bj = pj[r][tid & 31];
+        double bv = (tid & 31) < nwarps ? pv[r][tid & 31] : INF;
+        uint32_t bj = (tid & 31) < nwarps ? pj[r][tid & 31] : 0xffffffffu;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           const double v2 = __shfl_xor_sync(0xffffffffu, bv, o);
