@@ -1034,8 +1034,28 @@ int enqueue_gotoh16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
       p.done = c->d_done.p;
       p.nranges = (uint32_t)nr;
       std::vector<StreamChunk> ranges(nr);
+      // Range boundaries by TASK count (= output bytes: every task is 64 pairs), not by query pairs -- the first rows of
+      // the triangle are the longest and come last in task order -- and the last of the equal parts is cut again into
+      // 1/2, 1/4, 1/8, 1/8: what is still on the device when the kernel ends is under 1 % of the result.
+      std::vector<uint32_t> rcut(nr + 1, nq);
+      rcut[0] = 0;
+      for (size_t k = 1; k < nr; k++) {
+        double f;
+        if (nr < 5) f = (double)k / (double)nr;
+        else {
+          const size_t base = nr - 3;                       // equal parts; the last one holds four ranges
+          if (k < base) f = (double)k / (double)base;
+          else {
+            static const double sub[3] = {0.5, 0.75, 0.875};
+            f = ((double)(base - 1) + sub[k - base]) / (double)base;
+          }
+        }
+        const unsigned long long target = (unsigned long long)(f * (double)ntasks);
+        const uint32_t r = (uint32_t)(std::lower_bound(c->task_prefix.begin(), c->task_prefix.begin() + nq + 1, target) - c->task_prefix.begin());
+        rcut[k] = std::max(rcut[k - 1], std::min(r, nq));
+      }
       for (size_t k = 0; k < nr; k++) {
-        const uint32_t r0 = (uint32_t)((unsigned long long)nq * k / nr), r1 = (uint32_t)((unsigned long long)nq * (k + 1) / nr);
+        const uint32_t r0 = rcut[k], r1 = rcut[k + 1];
         StreamChunk& ch = ranges[k];
         ch.t0 = c->task_prefix[r0];
         ch.t1 = c->task_prefix[r1];
