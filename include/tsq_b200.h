@@ -84,6 +84,11 @@ extern "C" {
                                      hold, so a job with such a pair fails with TSQ_ERR_RANGE instead of guessing.  The
                                      logarithm is evaluated by a fixed sequence of IEEE double operations (bit-identical
                                      on CPU oracle and GPU; within 2 ulp of ln). */
+#define TSQ_FLAG_SCORES_I16 512u   /* scores come back as int16 (tsq_scores16; tsq_scores is refused): half the bytes on the
+                                     PCIe link and in host memory (10 GB instead of 20 GB at
+                                     configs[4]).  Exact or refused: tsq_upload returns TSQ_ERR_RANGE when a score of the
+                                     job could leave [-32767, 32767].  Not with TSQ_FLAG_IDENTITY, not with
+                                     tsq_set_result_buffers */
 
 typedef struct tsq_ctx tsq_ctx;
 
@@ -200,6 +205,8 @@ int tsq_run(tsq_ctx *ctx, tsq_progress_cb cb, void *user, volatile int *cancel);
 
 /* Host results (after tsq_run or tsq_download). count = n*(n-1)/2. */
 int tsq_scores(tsq_ctx *ctx, const int32_t **packed_upper, uint64_t *count);
+/* With TSQ_FLAG_SCORES_I16: the same matrix as int16. */
+int tsq_scores16(tsq_ctx *ctx, const int16_t **packed_upper, uint64_t *count);
 int tsq_distances(tsq_ctx *ctx, const double **packed_upper, uint64_t *count);
 int tsq_self_scores(tsq_ctx *ctx, const int32_t **self, uint32_t *n);
 /* TSQ_FLAG_IDENTITY only: identical residue pairs on the chosen optimal alignment, per pair. */

@@ -6,11 +6,11 @@ interface (tweakseq/Core/AlignmentTool.h:36-71) on top of that ABI.  There is no
 path: importing works anywhere, computing requires the built library and a B200.
 """
 from .capi import (TsqError, Context, Params, Stats, PROTEIN, NUCLEOTIDE, FLAG_FORCE_S32,
-                   FLAG_NO_DISTANCES, FLAG_NO_WAVE16, FLAG_IDENTITY, FLAG_MSA_OUT, FLAG_KEEP_DISTMAT, FLAG_INPUT_ORDER, FLAG_KEEP_TREE, FLAG_KIMURA, ALPHABET_AUTO,
+                   FLAG_NO_DISTANCES, FLAG_NO_WAVE16, FLAG_IDENTITY, FLAG_MSA_OUT, FLAG_KEEP_DISTMAT, FLAG_INPUT_ORDER, FLAG_KEEP_TREE, FLAG_KIMURA, FLAG_SCORES_I16, ALPHABET_AUTO,
                    library_path, load_library, pair_index)
 from .backend import AlignmentTool, B200Gotoh
 
 __all__ = ["TsqError", "Context", "Params", "Stats", "PROTEIN", "NUCLEOTIDE", "FLAG_FORCE_S32",
-           "FLAG_NO_DISTANCES", "FLAG_NO_WAVE16", "FLAG_IDENTITY", "FLAG_MSA_OUT", "FLAG_KEEP_DISTMAT", "FLAG_INPUT_ORDER", "FLAG_KEEP_TREE", "FLAG_KIMURA", "ALPHABET_AUTO", "library_path", "load_library", "pair_index", "AlignmentTool",
+           "FLAG_NO_DISTANCES", "FLAG_NO_WAVE16", "FLAG_IDENTITY", "FLAG_MSA_OUT", "FLAG_KEEP_DISTMAT", "FLAG_INPUT_ORDER", "FLAG_KEEP_TREE", "FLAG_KIMURA", "FLAG_SCORES_I16", "ALPHABET_AUTO", "library_path", "load_library", "pair_index", "AlignmentTool",
            "B200Gotoh"]
 __version__ = "0.2"

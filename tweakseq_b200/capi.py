@@ -14,6 +14,7 @@ PROTEIN, NUCLEOTIDE = 0, 1
 FLAG_FORCE_S32, FLAG_NO_DISTANCES, FLAG_NO_WAVE16, FLAG_IDENTITY, FLAG_MSA_OUT, FLAG_KEEP_DISTMAT, FLAG_INPUT_ORDER = 1, 2, 4, 8, 16, 32, 64
 FLAG_KEEP_TREE = 128
 FLAG_KIMURA = 256
+FLAG_SCORES_I16 = 512
 ALPHABET_AUTO = -1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -73,7 +74,7 @@ SYMBOLS = ["tsq_version", "tsq_version_string", "tsq_status_string", "tsq_device
            "tsq_self_scores", "tsq_identities", "tsq_device_scores", "tsq_partition", "tsq_finalize", "tsq_device_results",
            "tsq_get_stats", "tsq_measure_dpx_rate", "tsq_run_fasta", "tsq_plan_partition", "tsq_guide_tree",
            "tsq_write_newick", "tsq_consensus", "tsq_align_pair", "tsq_partition_of", "tsq_msa", "tsq_write_msa_fasta", "tsq_write_distmat",
-           "tsq_device_slab", "tsq_results_sharded", "tsq_set_result_buffers", "tsq_get_device_stats", "tsq_get_limits", "tsq_measure_pipe_rates", "tsq_detect_alphabet", "tsq_stream_results", "tsq_encode"]
+           "tsq_device_slab", "tsq_results_sharded", "tsq_set_result_buffers", "tsq_get_device_stats", "tsq_get_limits", "tsq_measure_pipe_rates", "tsq_detect_alphabet", "tsq_stream_results", "tsq_encode", "tsq_scores16"]
 
 _lib = None
 
@@ -116,6 +117,7 @@ def load_library():
     L.tsq_stream_results.argtypes = [vp, C.c_int]
     L.tsq_run.argtypes = [vp, PROGRESS_CB, vp, C.POINTER(C.c_int)]
     L.tsq_scores.argtypes = [vp, C.POINTER(i32p), u64p]
+    L.tsq_scores16.argtypes = [vp, C.POINTER(C.POINTER(C.c_int16)), u64p]
     L.tsq_distances.argtypes = [vp, C.POINTER(C.POINTER(C.c_double)), u64p]
     L.tsq_self_scores.argtypes = [vp, C.POINTER(i32p), C.POINTER(C.c_uint32)]
     L.tsq_identities.argtypes = [vp, C.POINTER(i32p), u64p]
@@ -307,6 +309,15 @@ class Context:
         self._ck(self._L.tsq_scores(self._h, C.byref(p), C.byref(cnt)))
         if cnt.value == 0:
             return np.zeros(0, np.int32)
+        a = np.ctypeslib.as_array(p, shape=(cnt.value,))
+        return a.copy() if copy else a
+
+    def scores16(self, copy: bool = True) -> np.ndarray:
+        """Packed int16 scores of a context created with FLAG_SCORES_I16 (tsq_scores16)."""
+        p, cnt = C.POINTER(C.c_int16)(), C.c_uint64()
+        self._ck(self._L.tsq_scores16(self._h, C.byref(p), C.byref(cnt)))
+        if cnt.value == 0:
+            return np.zeros(0, np.int16)
         a = np.ctypeslib.as_array(p, shape=(cnt.value,))
         return a.copy() if copy else a
 

@@ -67,6 +67,7 @@ struct G16Params {
   uint32_t negge2;             // (-ge' mod 2^16) in both halves
   uint32_t goe2;               // goe' * 0x10001 (mod 2^32)
   // ---- results that leave while the launch is still running (tsq_stream_results, sorted order = final order) ----
+  int16_t* out16;              // != nullptr: every score also as int16 (TSQ_FLAG_SCORES_I16; the host has checked the range)
   const int32_t* self;         // self scores S(x, x), sorted order
   double* out_dist;            // != nullptr: the distance 1 - S / min(S_ii, S_jj) goes out next to every score
                                //   (what finalize_kernel would compute from it afterwards, operation for operation)
@@ -99,6 +100,10 @@ static __device__ __noinline__ void g16_task_results(const G16Params& p, unsigne
     const unsigned long long i1 = tri_index(A1, j, p.n_total), i2 = tri_index(A2, j, p.n_total);
     p.out[i1] = s1;
     if (j > A2) p.out[i2] = s2;
+    if (p.out16) {
+      p.out16[i1] = (int16_t)s1;
+      if (j > A2) p.out16[i2] = (int16_t)s2;
+    }
     if (p.out_dist) {   // finalize_kernel's distance (tsq_device.cu), here because the rows leave before the launch ends
       const int32_t sj = p.self[j], sa = p.self[A1], sb = p.self[A2];
       const int32_t m1 = sa < sj ? sa : sj, m2 = sb < sj ? sb : sj;

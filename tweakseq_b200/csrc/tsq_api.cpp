@@ -367,6 +367,8 @@ struct tsq_ctx {
   DevBuf<int32_t> d_smat;
   // host results
   PinnedBuf<int32_t> h_scores, h_nid;
+  PinnedBuf<int16_t> h_scores16;           // TSQ_FLAG_SCORES_I16: the host result instead of h_scores
+  DevBuf<int16_t> d_scores16;              // ... and its device source (same extent as the int32 buffer it narrows)
   PinnedBuf<double> h_dist;
 
   // Cancel flag the kernels poll at every task fetch.  It lives in DEVICE memory and is written by a
@@ -445,6 +447,7 @@ int fail(tsq_ctx* c, int code, const char* fmt, ...) {
   } while (0)
 
 inline uint64_t tri(uint64_t i, uint64_t j, uint64_t n) { return i * n - i * (i + 1) / 2 + (j - i - 1); }
+inline uint64_t score_bytes(const tsq_ctx* c) { return (c->prm.flags & TSQ_FLAG_SCORES_I16) ? 2ull : 4ull; }   // per pair, on the way out
 
 // Kernels index the sorted-order score buffer by ABSOLUTE packed index; a rank that holds only its slab
 // hands them the buffer's address moved back by part_begin elements (never dereferenced below the slab).
@@ -644,6 +647,9 @@ int host_sort_and_pack(tsq_ctx* c) {
       if (bound * M >= (1ll << 31) - (1ll << 20))
         return fail(c, TSQ_ERR_RANGE, "sequence of length %u: %s would not fit 32 bits", c->lens[n - 1],
                     idmode ? "identity-aware keys" : "scores");
+      if ((c->prm.flags & TSQ_FLAG_SCORES_I16) && bound > 32767)
+        return fail(c, TSQ_ERR_RANGE, "TSQ_FLAG_SCORES_I16: a score of a sequence of length %u could leave int16 (bound %lld)",
+                    c->lens[n - 1], (long long)bound);
     }
   }
   if (c->perm_identity && lo > 0) c->perm_identity = false;  // empties are filled in by finalize
@@ -1031,6 +1037,10 @@ int enqueue_gotoh16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
         p.self = c->d_self.p;
         p.out_dist = biased(c->d_dist.p, first);
       }
+      if (c->prm.flags & TSQ_FLAG_SCORES_I16) {
+        TSQ_CUDA(c, c->d_scores16.reserve(c->full_sorted ? npairs : c->part_end - c->part_begin));
+        p.out16 = biased(c->d_scores16.p, first);
+      }
       p.done = c->d_done.p;
       p.nranges = (uint32_t)nr;
       std::vector<StreamChunk> ranges(nr);
@@ -1347,6 +1357,7 @@ void unregister_all(tsq_ctx* c) {
 // lands at its place whatever the buffer really spans).  Reserves / page-locks on first use.
 struct HostDst {
   int32_t* scores = nullptr;
+  int16_t* scores16 = nullptr;   // TSQ_FLAG_SCORES_I16: instead of scores
   int32_t* nid = nullptr;
   double* dist = nullptr;
 };
@@ -1355,6 +1366,7 @@ int host_results(tsq_ctx* c, bool want_dist, bool want_nid, HostDst* out) {
   uint64_t first = 0, count = 0;
   host_extent(o, &first, &count);   // a leader's buffers span the whole triangle
   if (o->ext_scores) {
+    if (c->prm.flags & TSQ_FLAG_SCORES_I16) return fail(c, TSQ_ERR_INVALID, "TSQ_FLAG_SCORES_I16 delivers into the library's own buffer (tsq_scores16), not into tsq_set_result_buffers");
     if (o->ext_count < count) return fail(c, TSQ_ERR_INVALID, "result buffers hold %llu pairs, the job has %llu",
                                           (unsigned long long)o->ext_count, (unsigned long long)count);
     if (want_dist && !o->ext_dist) return fail(c, TSQ_ERR_INVALID, "tsq_set_result_buffers: no distance buffer, but distances are on");
@@ -1373,8 +1385,13 @@ int host_results(tsq_ctx* c, bool want_dist, bool want_nid, HostDst* out) {
     out->scores = o->ext_scores;
     out->dist = want_dist ? o->ext_dist : nullptr;
   } else {
-    TSQ_CUDA(c, o->h_scores.reserve(count));
-    out->scores = biased(o->h_scores.p, first);
+    if (c->prm.flags & TSQ_FLAG_SCORES_I16) {
+      TSQ_CUDA(c, o->h_scores16.reserve(count));
+      out->scores16 = biased(o->h_scores16.p, first);
+    } else {
+      TSQ_CUDA(c, o->h_scores.reserve(count));
+      out->scores = biased(o->h_scores.p, first);
+    }
     if (want_dist) {
       TSQ_CUDA(c, o->h_dist.reserve(count));
       out->dist = biased(o->h_dist.p, first);
@@ -1435,6 +1452,25 @@ int check_device_fault(tsq_ctx* c) {
 
 // Behind one launch of a streamed compute: on the side stream, once that launch is done, finalize its rows
 // (distances next to the scores) and copy both to their place in the host result -- while the next launch runs.
+// The scores of packed indices [pb, pe) to the host result: as they are, or narrowed to int16 first
+// (TSQ_FLAG_SCORES_I16).  src: the device's final int32 scores, src[0] = packed index `first`; ready16: the
+// int16 copy is there already (the packed kernel wrote it next to the int32 one).
+int scores_out(tsq_ctx* c, tsq_ctx* owner, const HostDst& h, uint64_t pb, uint64_t pe, const int32_t* src, uint64_t first,
+               uint64_t extent, bool ready16, cudaStream_t s) {
+  if (pe <= pb) return TSQ_OK;
+  if (!(c->prm.flags & TSQ_FLAG_SCORES_I16)) {
+    TSQ_CUDA(c, copy_out(c, owner, h.scores + pb, src + (pb - first), (pe - pb) * sizeof(int32_t), s));
+    return TSQ_OK;
+  }
+  TSQ_CUDA(c, c->d_scores16.reserve(extent));
+  if (!ready16) {
+    TSQ_CUDA(c, tsq::narrow_scores_launch(src + (pb - first), c->d_scores16.p + (pb - first), pe - pb, s));
+    c->st.launches++;
+  }
+  TSQ_CUDA(c, copy_out(c, owner, h.scores16 + pb, c->d_scores16.p + (pb - first), (pe - pb) * sizeof(int16_t), s));
+  return TSQ_OK;
+}
+
 int stream_chunk_out(tsq_ctx* c, const StreamChunk& ch, cudaStream_t compute_stream, size_t index) {
   const uint64_t n = c->n, npairs = n < 2 ? 0 : n * (n - 1) / 2;
   auto start_of = [&](uint32_t row) -> uint64_t { return (n >= 2 && (uint64_t)row + 1 < n) ? tri(row, row + 1, n) : npairs; };
@@ -1470,9 +1506,10 @@ int stream_chunk_out(tsq_ctx* c, const StreamChunk& ch, cudaStream_t compute_str
     c->st.launches++;
   }
   tsq_ctx* owner = result_owner(c);
-  TSQ_CUDA(c, copy_out(c, owner, h.scores + pb, c->d_sorted.p + (pb - first), (pe - pb) * sizeof(int32_t), c->copy_stream));
+  rc = scores_out(c, owner, h, pb, pe, c->d_sorted.p, first, c->full_sorted ? npairs : c->part_end - c->part_begin, false, c->copy_stream);
+  if (rc != TSQ_OK) return rc;
   if (want_dist) TSQ_CUDA(c, copy_out(c, owner, h.dist + pb, c->d_dist.p + (pb - first), (pe - pb) * sizeof(double), c->copy_stream));
-  c->streamed_bytes += (pe - pb) * (want_dist ? 12ull : 4ull);
+  c->streamed_bytes += (pe - pb) * (score_bytes(c) + (want_dist ? 8ull : 0ull));
   return TSQ_OK;
 }
 
@@ -1499,9 +1536,10 @@ int stream_ranges_out(tsq_ctx* c, const std::vector<StreamChunk>& ranges) {
       if (wr != CUDA_SUCCESS) return fail(c, TSQ_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)wr);
     }
     if (pe <= pb) continue;
-    TSQ_CUDA(c, copy_out(c, owner, h.scores + pb, c->d_sorted.p + (pb - first), (pe - pb) * sizeof(int32_t), c->copy_stream));
+    const int rco = scores_out(c, owner, h, pb, pe, c->d_sorted.p, first, c->full_sorted ? npairs : c->part_end - c->part_begin, true, c->copy_stream);
+    if (rco != TSQ_OK) return rco;
     if (want_dist) TSQ_CUDA(c, copy_out(c, owner, h.dist + pb, c->d_dist.p + (pb - first), (pe - pb) * sizeof(double), c->copy_stream));
-    c->streamed_bytes += (pe - pb) * (want_dist ? 12ull : 4ull);
+    c->streamed_bytes += (pe - pb) * (score_bytes(c) + (want_dist ? 8ull : 0ull));
   }
   return TSQ_OK;
 }
@@ -1664,7 +1702,13 @@ int multi_download(tsq_ctx* c) {
         return rc;
       }
       TSQ_CUDA(c, cudaSetDevice(k0->device));
-      TSQ_CUDA(c, copy_out(k0, c, h.scores, k0->d_scores.p, npairs * sizeof(int32_t), k0->stream));
+      {
+        const int rco = scores_out(k0, c, h, 0, npairs, k0->d_scores.p, 0, npairs, false, k0->stream);
+        if (rco != TSQ_OK) {
+          copy_error(c, k0);
+          return rco;
+        }
+      }
       if (c->idshift) TSQ_CUDA(c, cudaMemcpyAsync(h.nid, k0->d_nid.p, npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, k0->stream));
       if (want_dist) TSQ_CUDA(c, copy_out(k0, c, h.dist, k0->d_dist.p, npairs * sizeof(double), k0->stream));
     }
@@ -1770,6 +1814,7 @@ int tsq_create(tsq_ctx** out, const tsq_params* params) {
   }
   if (p.alphabet != TSQ_PROTEIN && p.alphabet != TSQ_NUCLEOTIDE) return TSQ_ERR_INVALID;
   if ((p.flags & TSQ_FLAG_KIMURA) && !(p.flags & TSQ_FLAG_IDENTITY)) return TSQ_ERR_INVALID;   // corrects the identity distance
+  if ((p.flags & TSQ_FLAG_SCORES_I16) && (p.flags & TSQ_FLAG_IDENTITY)) return TSQ_ERR_INVALID;   // identity keys are decoded into int32 arrays
   if (p.part_world < 1) p.part_world = 1;
   if (p.part_rank < 0 || p.part_rank >= p.part_world) return TSQ_ERR_INVALID;
   const int nsym = p.alphabet == TSQ_NUCLEOTIDE ? 5 : 23;
@@ -1906,7 +1951,7 @@ int tsq_destroy(tsq_ctx* c) {
   unregister_all(c);
   c->d_dbw.release(); c->d_blob.release(); c->h_blob.release();
   c->d_sorted.release(); c->d_scores.release(); c->d_nid.release(); c->h_nid.release(); c->d_dist.release(); c->d_dist_full.release();
-  c->d_counter.release(); c->d_done.release(); c->d_bnd.release(); c->h_scores.release(); c->h_dist.release(); c->bounce.release();
+  c->d_counter.release(); c->d_done.release(); c->d_bnd.release(); c->h_scores.release(); c->h_scores16.release(); c->d_scores16.release(); c->h_dist.release(); c->bounce.release();
   c->d_treeD.release(); c->d_treemin.release(); c->d_treeh.release(); c->d_treeu.release(); c->d_merges.release();
   c->d_pairs32.release(); c->d_tasks16w.release(); c->d_bnd16w.release(); c->d_bnd32.release(); c->d_smat.release();
   if (c->d_cancel) BlockCache::get().give(c->device, c->d_cancel);
@@ -2186,9 +2231,10 @@ int tsq_download(tsq_ctx* c) {
       HostDst h;
       int rc = host_results(c, want_dist, false, &h);
       if (rc != TSQ_OK) return rc;
-      TSQ_CUDA(c, copy_out(c, result_owner(c), h.scores + c->part_begin, c->d_sorted.p, cnt * sizeof(int32_t), s));
+      rc = scores_out(c, result_owner(c), h, c->part_begin, c->part_end, c->d_sorted.p, c->part_begin, cnt, false, s);
+      if (rc != TSQ_OK) return rc;
       if (want_dist) TSQ_CUDA(c, copy_out(c, result_owner(c), h.dist + c->part_begin, c->d_dist.p, cnt * sizeof(double), s));
-      bytes = cnt * (want_dist ? 12ull : 4ull);
+      bytes = cnt * (score_bytes(c) + (want_dist ? 8ull : 0ull));
     }
     if (c->leader) {   // the leader synchronizes all its devices once every copy is in flight
       c->st.d2h_bytes = bytes;
@@ -2199,10 +2245,11 @@ int tsq_download(tsq_ctx* c) {
     int rc = host_results(c, want_dist, c->idshift != 0, &h);
     if (rc != TSQ_OK) return rc;
     const int32_t* src = (c->perm_identity && c->idshift == 0) ? c->d_sorted.p : c->d_scores.p;
-    TSQ_CUDA(c, copy_out(c, c, h.scores, src, npairs * sizeof(int32_t), s));
+    rc = scores_out(c, c, h, 0, npairs, src, 0, npairs, false, s);
+    if (rc != TSQ_OK) return rc;
     if (c->idshift) TSQ_CUDA(c, cudaMemcpyAsync(h.nid, c->d_nid.p, npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     if (want_dist) TSQ_CUDA(c, copy_out(c, c, h.dist, c->d_dist.p, npairs * sizeof(double), s));
-    bytes = npairs * (want_dist ? 12ull : 4ull) + (c->idshift ? npairs * 4ull : 0ull);
+    bytes = npairs * (score_bytes(c) + (want_dist ? 8ull : 0ull)) + (c->idshift ? npairs * 4ull : 0ull);
   }
   int rc = tsq_synchronize(c);
   if (rc != TSQ_OK) return rc;
@@ -2278,6 +2325,7 @@ int tsq_set_result_buffers(tsq_ctx* c, int32_t* scores, double* distances, uint6
   if (!c) return TSQ_ERR_INVALID;
   if (c->leader) return fail(c, TSQ_ERR_INVALID, "set the buffers on the multi-device context, not on its children");
   if ((scores == nullptr) != (count == 0)) return fail(c, TSQ_ERR_INVALID, "scores buffer and count must both be given or both be absent");
+  if (scores && (c->prm.flags & TSQ_FLAG_SCORES_I16)) return fail(c, TSQ_ERR_INVALID, "TSQ_FLAG_SCORES_I16 delivers into the library's own buffer (tsq_scores16)");
   if (c->kids.empty()) cudaSetDevice(c->device);
   unregister_all(c);
   c->ext_scores = scores;
@@ -2298,9 +2346,21 @@ int tsq_results_sharded(tsq_ctx* c, int* sharded) {
 int tsq_scores(tsq_ctx* c, const int32_t** out, uint64_t* count) {
   if (!c || !out) return TSQ_ERR_INVALID;
   if (!c->downloaded) return fail(c, TSQ_ERR_STATE, "no results: call tsq_run or tsq_download first");
+  if (c->prm.flags & TSQ_FLAG_SCORES_I16) return fail(c, TSQ_ERR_STATE, "TSQ_FLAG_SCORES_I16: the scores are int16, ask tsq_scores16");
   uint64_t first = 0, cnt = 0;
   host_extent(c, &first, &cnt);
   *out = c->ext_scores ? c->ext_scores : c->h_scores.p;
+  if (count) *count = cnt;
+  return TSQ_OK;
+}
+
+int tsq_scores16(tsq_ctx* c, const int16_t** out, uint64_t* count) {
+  if (!c || !out) return TSQ_ERR_INVALID;
+  if (!(c->prm.flags & TSQ_FLAG_SCORES_I16)) return fail(c, TSQ_ERR_STATE, "tsq_scores16 needs TSQ_FLAG_SCORES_I16");
+  if (!c->downloaded) return fail(c, TSQ_ERR_STATE, "no results: call tsq_run or tsq_download first");
+  uint64_t first = 0, cnt = 0;
+  host_extent(c, &first, &cnt);
+  *out = c->h_scores16.p;
   if (count) *count = cnt;
   return TSQ_OK;
 }

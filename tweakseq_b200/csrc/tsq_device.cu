@@ -477,6 +477,22 @@ cudaError_t finalize_launch(const FinalizeParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// ---- int32 -> int16 scores -------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) narrow_scores_kernel(const int32_t* __restrict__ src, int16_t* __restrict__ dst,
+                                                            unsigned long long count) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+    dst[i] = (int16_t)src[i];
+}
+
+cudaError_t narrow_scores_launch(const int32_t* src, int16_t* dst, unsigned long long count, cudaStream_t stream) {
+  if (count == 0) return cudaSuccess;
+  unsigned long long blocks = (count + 255) / 256;
+  if (blocks > 148ull * 32ull) blocks = 148ull * 32ull;
+  narrow_scores_kernel<<<(unsigned int)blocks, 256, 0, stream>>>(src, dst, count);
+  return cudaGetLastError();
+}
+
 // ---- DPX issue-rate probe -----------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1) dpx_probe_kernel(uint32_t* out, uint32_t k1, uint32_t k2,
                                                             long long* cyc) {

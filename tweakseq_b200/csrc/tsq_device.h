@@ -97,6 +97,9 @@ struct FinalizeParams {
 };
 cudaError_t finalize_launch(const FinalizeParams& p, cudaStream_t stream);
 
+// int32 scores -> int16 (TSQ_FLAG_SCORES_I16; the host has checked that every score fits)
+cudaError_t narrow_scores_launch(const int32_t* src, int16_t* dst, unsigned long long count, cudaStream_t stream);
+
 // DPX issue-rate probe: thread-level VIADDMNMX.U16x2 + VIMNMX3.U16x2 results / clk / SM.
 cudaError_t dpx_probe(int device_sms, double* ops_per_clk_per_sm, double* sm_mhz, cudaStream_t stream);
 
