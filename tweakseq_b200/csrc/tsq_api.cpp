@@ -396,9 +396,10 @@ struct tsq_ctx {
   const std::vector<int32_t>* selfp = nullptr;                // self scores: own `self_input`, or the leader's
   cudaEvent_t fin_ev = nullptr;    // recorded behind this context's finalize (cross-device stream waits)
   DevBuf<double> d_dist_full;      // child 0 of a leader in slab mode: all slabs of the distance matrix (guide tree)
-  // ---- streamed results (tsq_run, tsq_stream_results): the packed kernel's tasks go out in a few launches over
-  // consecutive row ranges; behind each one a side stream finalizes those rows and copies them to the host while
-  // the next launch computes ("slabs overlapped with remaining compute on a side stream")
+  // ---- streamed results (tsq_run, tsq_stream_results): consecutive row ranges of the result leave for the host on a
+  // side stream while the packed kernel is still running -- it counts finished tasks per range in d_done and the side
+  // stream waits on the counters; or, without stream memory operations, behind one launch per range (SURVEY.md
+  // section 8e: "slabs overlapped with remaining compute on a side stream")
   bool stream_out = false;          // asked for
   bool streamed = false;            // the last tsq_compute did it: tsq_download has nothing left to copy
   cudaStream_t copy_stream = nullptr;
