@@ -400,6 +400,7 @@ struct tsq_ctx {
   // side stream while the packed kernel is still running -- it counts finished tasks per range in d_done and the side
   // stream waits on the counters; or, without stream memory operations, behind one launch per range (SURVEY.md
   // section 8e: "slabs overlapped with remaining compute on a side stream")
+  bool ev0_set = false;             // this tsq_compute has recorded its kernel-start event (right ahead of its first launch)
   bool stream_out = false;          // asked for
   bool streamed = false;            // the last tsq_compute did it: tsq_download has nothing left to copy
   cudaStream_t copy_stream = nullptr;
@@ -915,6 +916,16 @@ StreamWaitValue32Fn stream_wait_value32() {
 }
 constexpr unsigned kDoneSlots = 32;
 
+// kernel_ms runs from the first launch of a tsq_compute, not from its first allocation: a context's first compute
+// reserves its scratch between the two.
+#define TSQ_MARK_START(c, s)                          \
+  do {                                                \
+    if (!(c)->ev0_set) {                              \
+      TSQ_CUDA((c), cudaEventRecord((c)->ev0, (s))); \
+      (c)->ev0_set = true;                            \
+    }                                                 \
+  } while (0)
+
 // Whether the results of this job can leave in row-range chunks: the packed kernel only, scores in place
 // (sorted order = submitted order, no identity keys), the whole triangle or a sharded slab.
 bool can_stream(const tsq_ctx* c) {
@@ -964,6 +975,7 @@ int enqueue_gotoh16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
       g.go = c->go_k;
       g.ge = c->ge_k;
       g.one = 1;
+      TSQ_MARK_START(c, s);
       TSQ_CUDA(c, tsq::g32_launch(c->K, grid, g, s));
       launches++;
       return TSQ_OK;
@@ -1012,6 +1024,7 @@ int enqueue_gotoh16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
     }
     const bool by_counters = can_stream(c) && stream_wait_value32() != nullptr && getenv("TSQ_STREAM_LAUNCHES") == nullptr;
     if (nchunks == 1 && !can_stream(c)) {
+      TSQ_MARK_START(c, s);
       TSQ_CUDA(c, tsq::g16_launch(c->K, grid, p, s, nullptr));
       launches++;
     } else if (by_counters) {
@@ -1080,6 +1093,7 @@ int enqueue_gotoh16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
       TSQ_CUDA(c, cudaStreamWaitEvent(s, c->fin_ev, 0));
       TSQ_CUDA(c, cudaMemsetAsync(c->d_done.p, 0, kDoneSlots * sizeof(unsigned int), s));
       TSQ_CUDA(c, cudaEventRecord(c->chunk_ev[0], s));
+      TSQ_MARK_START(c, s);
       TSQ_CUDA(c, tsq::g16_launch(c->K, grid, p, s, nullptr));
       launches++;
       TSQ_CUDA(c, cudaEventRecord(c->ev1, s));
@@ -1110,6 +1124,7 @@ int enqueue_gotoh16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
         c->h_starts[k] = ch.t0;
         TSQ_CUDA(c, cudaMemcpyAsync(c->d_counter.p, &c->h_starts[k], sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
         p.ntasks = ch.t1;
+        TSQ_MARK_START(c, s);
         TSQ_CUDA(c, tsq::g16_launch(c->K, grid, p, s, nullptr));
         launches++;
         if (k + 1 == nchunks) TSQ_CUDA(c, cudaEventRecord(c->ev1, s));   // kernel_ms: the kernels, not the enqueues behind them
@@ -1157,6 +1172,7 @@ int enqueue_wave16(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
     w.gep = c->ge - c->delta;
     w.goep = c->go + c->ge - c->delta;
     w.negge2 = ((uint32_t)(-(c->ge - c->delta)) & 0xffffu) * 0x10001u;
+    TSQ_MARK_START(c, s);
     TSQ_CUDA(c, tsq::w16_launch(grid, w, lipschitz_of(c), s));
     launches++;
   }
@@ -1191,6 +1207,7 @@ int enqueue_wave32(tsq_ctx* c, cudaStream_t s, uint32_t& launches) {
     w.go = c->go_k;
     w.ge = c->ge_k;
     w.one = 1;
+    TSQ_MARK_START(c, s);
     TSQ_CUDA(c, tsq::w32_launch(grid, w, s));
     launches++;
   }
@@ -2101,6 +2118,10 @@ int tsq_upload(tsq_ctx* c) {
   // an earlier job may still be reading the staging blob or the device buffers this call re-uses (or returns to the
   // block cache when they grow): wait for it; free when the stream is idle
   TSQ_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->copy_stream) {   // ... and the side stream of a streamed compute nobody waited for (it reads the buffers re-sized below)
+    TSQ_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    apply_fixups(c);
+  }
   int rc = host_sort_and_pack(c);
   if (rc == TSQ_OK) rc = host_plan_work(c);
   if (rc == TSQ_OK) rc = host_build_subject_db(c);
@@ -2126,11 +2147,12 @@ int tsq_compute(tsq_ctx* c) {
     if (rcs != TSQ_OK) return rcs;
   }
   TSQ_CUDA(c, cudaMemsetAsync(c->d_cancel, 0, 4 * sizeof(int), s));   // cancel flag, fault word, Kimura out-of-range count
-  TSQ_CUDA(c, cudaEventRecord(c->ev0, s));
+  c->ev0_set = false;
   int rc = enqueue_gotoh16(c, s, launches);                 // regime 1: packed inter-task kernel
   if (rc == TSQ_OK) rc = enqueue_wave16(c, s, launches);    // regime 2: packed wavefront kernel
   if (rc == TSQ_OK) rc = enqueue_wave32(c, s, launches);    // regime 2 fallback: 32-bit wavefront kernel
   if (rc != TSQ_OK) return rc;
+  TSQ_MARK_START(c, s);   // (a job without a single task)
   if (!c->streamed) TSQ_CUDA(c, cudaEventRecord(c->ev1, s));
   c->st.launches += launches;
   c->computed = true;
@@ -2587,6 +2609,7 @@ class CudaMsaDevice : public tsq::MsaDevice {
     if (!chunks_.empty() && cudaDeviceSynchronize() != cudaSuccess) cudaGetLastError();
     for (void* p : chunks_) BlockCache::get().give(dev_, p);
     scr_.release();
+    stage_.release();
   }
   cudaError_t err = cudaSuccess;   // first CUDA error seen
   double t_alloc = 0, t_scratch = 0, t_copy = 0, t_wait = 0, t_launch = 0;   // host clock per kind of call (TSQ_MSA_DEBUG)
@@ -2615,12 +2638,25 @@ class CudaMsaDevice : public tsq::MsaDevice {
     }
     return scr_.p;
   }
+  // Small copies (a level's task list up, its merged lengths back: once per tree level, a thousand times for a deep
+  // tree) go through a page-locked staging block: a pageable cudaMemcpyAsync stages and waits inside the driver.
+  // Safe to reuse per call: every level ends in d2h's synchronize before the next h2d writes the block.
   bool h2d(void* d, const void* h, size_t b) override {
     Timer tm(t_copy);
+    if (b <= kStage && stage_up()) {
+      if (!ok(cudaStreamSynchronize(s_))) return false;   // (an earlier staged upload of this stream has left the block)
+      memcpy(stage_.p, h, b);
+      return ok(cudaMemcpyAsync(d, stage_.p, b, cudaMemcpyHostToDevice, s_));
+    }
     return ok(cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, s_));
   }
   bool d2h(void* h, const void* d, size_t b) override {
     Timer tm(t_wait);
+    if (b <= kStage && stage_up()) {
+      if (!ok(cudaMemcpyAsync(stage_.p + kStage, d, b, cudaMemcpyDeviceToHost, s_)) || !ok(cudaStreamSynchronize(s_))) return false;
+      memcpy(h, stage_.p + kStage, b);
+      return true;
+    }
     return ok(cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, s_)) && ok(cudaStreamSynchronize(s_));
   }
   bool fill(void* d, int v, size_t b) override { return ok(cudaMemsetAsync(d, v, b, s_)); }
@@ -2642,6 +2678,9 @@ class CudaMsaDevice : public tsq::MsaDevice {
     if (e != cudaSuccess && err == cudaSuccess) err = e;
     return e == cudaSuccess;
   }
+  static constexpr size_t kStage = 256u << 10;   // bytes per direction
+  bool stage_up() { return stage_.p != nullptr || stage_.reserve(2 * kStage) == cudaSuccess; }
+  PinnedBuf<uint8_t> stage_;
   cudaStream_t s_;
   int dev_;
   std::vector<void*> chunks_;
