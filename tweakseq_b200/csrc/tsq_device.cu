@@ -324,7 +324,7 @@ cudaError_t upgma_launch(const UpgmaParams& p, cudaStream_t stream) {
     if (t >= 32 && t <= UPGMA_THREADS && (t & 31) == 0) threads = (unsigned)t;
   }
   if (p.n <= UPGMA_SMEM_N) {
-    const size_t smem = (size_t)p.n * (sizeof(double) + sizeof(uint32_t) + 1) + 16;
+    const size_t smem = upgma_smem_bytes(p.n);
     e = cudaFuncSetAttribute(upgma_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     upgma_merge_kernel<true><<<1, threads, smem, stream>>>(p);

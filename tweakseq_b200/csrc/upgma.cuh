@@ -18,6 +18,12 @@
 
 #include "../../include/tsq_b200.h"
 
+#ifdef __CUDACC__
+#define TSQ_UPGMA_HD __host__ __device__
+#else
+#define TSQ_UPGMA_HD
+#endif
+
 namespace tsq {
 
 struct UpgmaParams {
@@ -119,6 +125,14 @@ __device__ __forceinline__ void upgma_block_argmin(double& v, uint32_t& i, uint3
 // SMEM: row minima, their arguments and the active flags live in shared memory (n <= UPGMA_SMEM_N);
 // every step then touches global memory only for the two matrix rows it combines and for re-scans.
 constexpr uint32_t UPGMA_SMEM_N = 12288;   // 12288 * (8 + 4 + 1) B = 156 KB
+// ... and up to this n the cluster sizes and node ids too (8 B more per slot): they are read right behind the arg-min of
+// every step, two L2 round trips on the critical path of a 6 us step otherwise
+constexpr uint32_t UPGMA_SMEM_N2 = 8192;
+TSQ_UPGMA_HD inline size_t upgma_smem_bytes(uint32_t n) {
+  size_t b = (size_t)n * (sizeof(double) + sizeof(uint32_t) + 1) + 16;
+  if (n <= UPGMA_SMEM_N2) b = ((b + 15) & ~(size_t)15) + (size_t)n * 8;
+  return b;
+}
 
 template <bool SMEM>
 __global__ void __launch_bounds__(UPGMA_THREADS, 1) upgma_merge_kernel(const __grid_constant__ UpgmaParams p) {
@@ -133,6 +147,9 @@ __global__ void __launch_bounds__(UPGMA_THREADS, 1) upgma_merge_kernel(const __g
   double* rowmin = SMEM ? upgma_dyn : p.rowmin;
   uint32_t* rowarg = SMEM ? reinterpret_cast<uint32_t*>(upgma_dyn + n) : p.rowarg;
   uint8_t* act8 = reinterpret_cast<uint8_t*>(rowarg + n);   // SMEM only
+  const bool small = SMEM && n <= UPGMA_SMEM_N2;            // cluster sizes and node ids in shared memory as well
+  uint32_t* const csize = small ? reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(upgma_dyn) + (((size_t)n * 13 + 16 + 15) & ~(size_t)15)) : p.csize;
+  uint32_t* const node = small ? csize + n : p.node;
   uint32_t* const rescan = p.rescan;
   const uint32_t tid = threadIdx.x;
   const uint32_t NT = blockDim.x;   // UPGMA_THREADS unless a tuning run asks for fewer (upgma_launch)
@@ -141,6 +158,10 @@ __global__ void __launch_bounds__(UPGMA_THREADS, 1) upgma_merge_kernel(const __g
       rowmin[i] = p.rowmin[i];
       rowarg[i] = p.rowarg[i];
       act8[i] = 1;
+      if (small) {
+        csize[i] = 1;
+        node[i] = i;
+      }
     }
     __syncthreads();
   }
@@ -159,11 +180,11 @@ __global__ void __launch_bounds__(UPGMA_THREADS, 1) upgma_merge_kernel(const __g
     }
     upgma_block_argmin(v, a, b, sv, si, sj);
     // ---- 2. record the merge ----------------------------------------------------------------------
-    const uint32_t sa = p.csize[a], sb = p.csize[b];
+    const uint32_t sa = csize[a], sb = csize[b];
     if (tid == 0) {
       tsq_merge mg;
-      mg.left = p.node[a];
-      mg.right = p.node[b];
+      mg.left = node[a];
+      mg.right = node[b];
       mg.height = __dmul_rn(v, 0.5);
       p.merges[step] = mg;
       nrescan = 0;
@@ -199,8 +220,8 @@ __global__ void __launch_bounds__(UPGMA_THREADS, 1) upgma_merge_kernel(const __g
     __syncthreads();
     if (tid == 0) {
       if (SMEM) act8[b] = 0; else p.active[b] = 0;
-      p.csize[a] = sa + sb;
-      p.node[a] = n + step;
+      csize[a] = sa + sb;
+      node[a] = n + step;
       rescan[nrescan] = a;   // row a always
       nrescan = nrescan + 1;
     }
