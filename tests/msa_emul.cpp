@@ -77,7 +77,42 @@ class EmulDevice : public tsq::MsaDevice {
       });
       if (tw == nt) each_thread(nt, [&](int tid) { tsq::msa_sub_phase<T>(sw, st + 1, tid, nt); });
     }
-    tsq::msa_walk_phase(t, tsq::msa_final_score<T>(sw), codes);
+    // phase 3 twice: the serial statement, then the device's one-warp walk with its ballots done by a loop over 32
+    // lanes (lanes in the emulation's thread order); the two paths must agree entry for entry
+    const long long score = tsq::msa_final_score<T>(sw);
+    tsq::msa_walk_phase(t, score, codes);
+    const uint32_t len1 = t.res->len;
+    std::vector<int32_t> path1(t.path, t.path + 2 * (size_t)len1);
+    memset(t.path, 0x5C, 2 * (size_t)len1 * sizeof(int32_t));
+    t.res->len = 0xdeadbeefu;
+    walk_warp(t, score, codes);
+    if (t.res->len != len1 || memcmp(path1.data(), t.path, path1.size() * sizeof(int32_t)) != 0 || t.res->score != score) walk_mismatch = true;
+  }
+  bool walk_mismatch = false;
+  // msa_walk_warp (msa.cuh), the collectives emulated: every per-lane piece runs for all 32 lanes before the next one
+  void walk_warp(const tsq::MsaTask& t, long long score, const uint16_t* codes) {
+    tsq::MsaWalk w{(int)t.Lx, (int)t.Ly, 0, 0u};
+    while (w.i > 0 && w.j > 0) {
+      uint32_t code[32][2];
+      bool valid[32][2];
+      each_thread(32, [&](int lane) { tsq::msa_walk_fetch(t, codes, w, lane, code[lane], valid[lane]); });
+      bool more = true;
+      for (int h = 0; h < 2 && more; ++h) {
+        uint32_t stops = 0, turns = 0;
+        each_thread(32, [&](int lane) {
+          const bool turn = valid[lane][h] && tsq::msa_walk_turn(w.state, code[lane][h]);
+          if (!valid[lane][h] || turn) stops |= 1u << lane;
+          if (turn) turns |= 1u << lane;
+        });
+        int s;
+        bool s_turn;
+        const int count = tsq::msa_walk_count(w.state, stops, turns, &s, &s_turn);
+        each_thread(32, [&](int lane) { tsq::msa_walk_store(t, w, lane, count); });
+        more = tsq::msa_walk_advance(w, s, s_turn, count, code[s & 31][h]);
+      }
+    }
+    each_thread(32, [&](int lane) { tsq::msa_walk_tails(t, w, lane); });
+    tsq::msa_walk_finish(t, w, score);
   }
   bool launch_leaves(const tsq::MsaLeaf* l, uint32_t n, uint32_t nsym) override {
     for (uint32_t r = 0; r < n; r++) each_thread(128, [&](int t) { tsq::msa_leaf_phase(l[r], nsym, t, 128); });
@@ -138,6 +173,7 @@ extern "C" int msa_emul(const uint8_t* seqs, const uint64_t* offs, const uint32_
   tsq::MsaOut out;
   const int rc = tsq::msa_progressive(dev, job, out);
   if (rc != tsq::MSA_OK) return rc;
+  if (dev.walk_mismatch) return -2;   // the one-warp walk-back and the serial one disagree
   if (out.rows.size() > rows_cap) return -1;
   memcpy(rows_out, out.rows.data(), out.rows.size());
   *ncols = out.ncols;

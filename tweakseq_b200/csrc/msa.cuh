@@ -531,68 +531,107 @@ TSQ_HD void msa_rows_phase(const MsaRows& p, uint32_t r, int tid, int nt) {
   }
 }
 
+// phase 3 by ONE WARP (the device's walk-back).  The serial walk above is a chain of round trips consumed one code at a
+// time by one thread: a third of a merge's time once the sweep was tiled.  Here lane q fetches the direction codes of
+// the cells q and q + 32 steps ahead along the current run (down the diagonal, or along the gap run), a ballot finds
+// where the run ends, and all lanes before that point write their path entries at once.  Same state machine, same
+// path, entry for entry.  The pieces below are per-lane or warp-uniform functions of plain values, so that the CPU
+// emulation (tests/msa_emul.cpp) runs the same code with the ballots done by a loop over 32 lanes and compares the
+// path with the serial walk's; msa_walk_warp is the device's glue around them.
+struct MsaWalk {
+  int i, j, state;       // current cell, 0 = on the diagonal run, 1 = gap in X (moving along j), 2 = gap in Y
+  uint32_t k;            // path entries written
+};
+
+// lane q: codes of the cells q and q + 32 steps ahead along the current run (valid = the cell is on the matrix)
+TSQ_HD void msa_walk_fetch(const MsaTask& t, const uint16_t* codes4, const MsaWalk& w, int lane, uint32_t (&code)[2], bool (&valid)[2]) {
+  const int n = (int)t.Ly;
+  const size_t ld = (size_t)(t.Lx < t.Ly ? t.Lx : t.Ly) + 1;
+  const int di = w.state == 1 ? 0 : 1, dj = w.state == 2 ? 0 : 1;
+  for (int h = 0; h < 2; ++h) {
+    const int q = lane + 32 * h;
+    const int ii = w.i - q * di, jj = w.j - q * dj;
+    valid[h] = ii > 0 && jj > 0;
+    code[h] = valid[h] ? msa_read_code(codes4, t.dir, ii, jj, n, ld) : 0u;
+  }
+}
+
+// a cell on the matrix ends the run by a TURN: (state 0) it opens a gap run; (gap states) its flag says the run was
+// opened here -- that cell still belongs to the run
+TSQ_HD bool msa_walk_turn(int state, uint32_t code) {
+  return state == 0 ? (code & 3u) != 0u : state == 1 ? (code & 4u) != 0u : (code & 8u) != 0u;
+}
+
+// from the two ballots of a half (stops: off the matrix or a turn; turns): the first stopping lane s (32: none), whether
+// it is a turn, and how many path entries the half yields
+TSQ_HD int msa_walk_count(int state, uint32_t stops, uint32_t turns, int* s_out, bool* s_turn_out) {
+  int s = 32;
+  if (stops) {
+    s = 0;
+    while (!((stops >> s) & 1u)) ++s;
+  }
+  const bool s_turn = s < 32 && ((turns >> s) & 1u);
+  *s_out = s;
+  *s_turn_out = s_turn;
+  return (state != 0 && s_turn) ? s + 1 : s;
+}
+
+// lane < count writes the path entry of its cell of the half (i, j: the half's first cell)
+TSQ_HD void msa_walk_store(const MsaTask& t, const MsaWalk& w, int lane, int count) {
+  if (lane >= count) return;
+  const int di = w.state == 1 ? 0 : 1, dj = w.state == 2 ? 0 : 1;
+  const int ii = w.i - lane * di, jj = w.j - lane * dj;
+  t.path[2 * (w.k + (uint32_t)lane)] = w.state == 1 ? -1 : ii - 1;
+  t.path[2 * (w.k + (uint32_t)lane) + 1] = w.state == 2 ? -1 : jj - 1;
+}
+
+// after a half: move on; returns whether the run went through all 32 cells (the second half may follow)
+TSQ_HD bool msa_walk_advance(MsaWalk& w, int s, bool s_turn, int count, uint32_t code_at_s) {
+  const int di = w.state == 1 ? 0 : 1, dj = w.state == 2 ? 0 : 1;
+  w.k += (uint32_t)count;
+  w.i -= count * di;
+  w.j -= count * dj;
+  if (s >= 32) return true;
+  if (s_turn) w.state = w.state == 0 ? (int)(code_at_s & 3u) : 0;   // (off the matrix: i or j is 0 now, the walk's loop ends)
+  return false;
+}
+
+// the rest of the longer side faces gaps: lane's share of the two tails; then the totals
+TSQ_HD void msa_walk_tails(const MsaTask& t, const MsaWalk& w, int lane) {
+  for (int q = lane; q < w.j; q += 32) { t.path[2 * (w.k + (uint32_t)q)] = -1; t.path[2 * (w.k + (uint32_t)q) + 1] = w.j - 1 - q; }
+  const uint32_t k2 = w.k + (uint32_t)(w.j > 0 ? w.j : 0);
+  for (int q = lane; q < w.i; q += 32) { t.path[2 * (k2 + (uint32_t)q)] = w.i - 1 - q; t.path[2 * (k2 + (uint32_t)q) + 1] = -1; }
+}
+TSQ_HD void msa_walk_finish(const MsaTask& t, const MsaWalk& w, long long score) {
+  t.res->len = w.k + (uint32_t)(w.j > 0 ? w.j : 0) + (uint32_t)(w.i > 0 ? w.i : 0);
+  t.res->pad = 0;
+  t.res->score = score;
+}
+
 #ifdef TSQ_DEVICE_IMPL
-// phase 3 on the device: msa_walk_phase's walk by ONE WARP.  The serial walk is a chain of L2 round trips (16
-// direction bytes per trip, consumed one by one by one thread): a third of a merge's time once the sweep was tiled.
-// Here lane q fetches the direction bytes of the cells q and q + 32 steps ahead along the current run (down the
-// diagonal, or along the gap run), a ballot finds where the run ends, and all lanes before that point write their
-// path entries at once.  Same state machine, same path, entry for entry (GPU tests against the oracle; the CPU
-// emulation keeps running the serial statement above).
 __device__ __forceinline__ void msa_walk_warp(const MsaTask& t, long long score, int lane, const uint16_t* codes4) {
-  const int m = (int)t.Lx, n = (int)t.Ly;
-  const size_t ld = (size_t)(m < n ? m : n) + 1;
-  int i = m, j = n, state = 0;
-  uint32_t k = 0;
-  while (i > 0 && j > 0) {
-    const int di = state == 1 ? 0 : 1, dj = state == 2 ? 0 : 1;
+  MsaWalk w{(int)t.Lx, (int)t.Ly, 0, 0u};
+  while (w.i > 0 && w.j > 0) {
     uint32_t code[2];
     bool valid[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int q = lane + 32 * h;
-      const int ii = i - q * di, jj = j - q * dj;
-      valid[h] = ii > 0 && jj > 0;
-      uint32_t c = 0;
-      if (valid[h]) c = msa_read_code(codes4, t.dir, ii, jj, n, ld);
-      code[h] = c;
-    }
-    bool more = true;   // warp-uniform: the run went through all 32 cells of the half
+    msa_walk_fetch(t, codes4, w, lane, code, valid);
+    bool more = true;   // warp-uniform
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       if (!more) break;
-      const int ii = i - lane * di, jj = j - lane * dj;   // this lane's cell of the half (i, j have moved past the first half)
-      // a lane stops the run: off the matrix, or (state 0) a cell that opens a gap run, or (gap states) the cell
-      // whose flag says the run was opened here -- that cell still belongs to the run
-      const bool off = !valid[h];
-      const bool turn = !off && (state == 0 ? (code[h] & 3u) != 0u : state == 1 ? (code[h] & 4u) != 0u : (code[h] & 8u) != 0u);
-      const uint32_t stops = __ballot_sync(0xffffffffu, off || turn);
-      const int s = stops ? __ffs((int)stops) - 1 : 32;             // first stopping lane
-      const bool s_turn = s < 32 && ((__ballot_sync(0xffffffffu, turn) >> s) & 1u);
-      const int count = (state != 0 && s_turn) ? s + 1 : s;         // path entries of this half
-      if (lane < count) {
-        t.path[2 * (k + (uint32_t)lane)] = state == 1 ? -1 : ii - 1;
-        t.path[2 * (k + (uint32_t)lane) + 1] = state == 2 ? -1 : jj - 1;
-      }
-      k += (uint32_t)count;
-      i -= count * di;
-      j -= count * dj;
-      if (s < 32) {
-        more = false;
-        if (s_turn) state = state == 0 ? (int)(__shfl_sync(0xffffffffu, code[h], s) & 3u) : 0;
-        // (off the matrix: i or j is 0 now, the loop ends)
-      }
+      const bool turn = valid[h] && msa_walk_turn(w.state, code[h]);
+      const uint32_t stops = __ballot_sync(0xffffffffu, !valid[h] || turn);
+      const uint32_t turns = __ballot_sync(0xffffffffu, turn);
+      int s;
+      bool s_turn;
+      const int count = msa_walk_count(w.state, stops, turns, &s, &s_turn);
+      msa_walk_store(t, w, lane, count);
+      const uint32_t code_at_s = __shfl_sync(0xffffffffu, code[h], s & 31);
+      more = msa_walk_advance(w, s, s_turn, count, code_at_s);
     }
   }
-  // the rest of the longer side faces gaps
-  for (int q = lane; q < j; q += 32) { t.path[2 * (k + (uint32_t)q)] = -1; t.path[2 * (k + (uint32_t)q) + 1] = j - 1 - q; }
-  k += (uint32_t)(j > 0 ? j : 0);
-  for (int q = lane; q < i; q += 32) { t.path[2 * (k + (uint32_t)q)] = i - 1 - q; t.path[2 * (k + (uint32_t)q) + 1] = -1; }
-  k += (uint32_t)(i > 0 ? i : 0);
-  if (lane == 0) {
-    t.res->len = k;
-    t.res->pad = 0;
-    t.res->score = score;
-  }
+  msa_walk_tails(t, w, lane);
+  if (lane == 0) msa_walk_finish(t, w, score);
 }
 
 __global__ void __launch_bounds__(128) msa_leaf_kernel(const MsaLeaf* leaves, uint32_t n, uint32_t nsym) {
