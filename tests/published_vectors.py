@@ -1,0 +1,40 @@
+"""Global alignments whose optimal score is PUBLISHED: the only anchors of the Gotoh arithmetic that lie outside this
+repository (the reference holds no alignment code or vectors: DESIGN.md section 3).  Both use linear gaps, i.e. gap
+open 0 in the spec's cost go + k * ge.
+
+1. R. Durbin, S. Eddy, A. Krogh, G. Mitchison, "Biological sequence analysis" (1998), section 2.3, figure 2.5: HEAGAWGHEE
+   against PAWHEAE, BLOSUM50, gap penalty d = 8 per residue: the global dynamic-programming matrix ends in F = 1.
+   (The BLOSUM50 entries below are the ones of the book's figure 2.2 for the letters involved.)
+2. The worked example of the Needleman-Wunsch algorithm's encyclopedia entry: GATTACA against GCATGCU, match +1,
+   mismatch -1, indel -1: best score 0.
+"""
+import numpy as np
+
+PROTEIN_ORDER = "ARNDCQEGHILKMFPSTWYVBZX"
+
+_B50 = {("A", "A"): 5, ("A", "E"): -1, ("A", "G"): 0, ("A", "H"): -2, ("A", "P"): -1, ("A", "W"): -3,
+        ("E", "E"): 6, ("E", "G"): -3, ("E", "H"): 0, ("E", "P"): -1, ("E", "W"): -3,
+        ("G", "G"): 8, ("G", "H"): -2, ("G", "P"): -2, ("G", "W"): -3,
+        ("H", "H"): 10, ("H", "P"): -2, ("H", "W"): -3, ("P", "P"): 10, ("P", "W"): -4, ("W", "W"): 15}
+
+
+def blosum50_subset() -> np.ndarray:
+    """23 x 23 in the library's symbol order; only the entries among A, E, G, H, P, W are BLOSUM50, the rest 0."""
+    m = np.zeros((23, 23), dtype=np.int8)
+    for (a, b), v in _B50.items():
+        i, j = PROTEIN_ORDER.index(a), PROTEIN_ORDER.index(b)
+        m[i, j] = m[j, i] = v
+    return m
+
+
+def unit_nucleotide() -> np.ndarray:
+    m = np.full((5, 5), -1, dtype=np.int8)
+    np.fill_diagonal(m, 1)
+    return m
+
+
+# (name, alphabet, sequence a, sequence b, matrix, gap open, gap extend, published score)
+VECTORS = [
+    ("Durbin et al. 1998, fig. 2.5", 0, "HEAGAWGHEE", "PAWHEAE", blosum50_subset(), 0, 8, 1),
+    ("Needleman-Wunsch worked example", 1, "GATTACA", "GCATGCU", unit_nucleotide(), 0, 1, 0),
+]

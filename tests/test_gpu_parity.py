@@ -549,3 +549,27 @@ def test_backend_object_identity_tree_and_consensus(tmp_path):
     assert open(tmp_path / "g.dnd").read().strip().endswith(";")
     rows = [x[:200].ljust(200, "-") for x in seqs]
     assert tool.consensus(rows) == o.consensus(rows)
+
+
+# ---- published optima (tests/published_vectors.py): the anchors outside this repository, through the library ----------
+def test_published_alignment_scores_on_the_gpu():
+    """Durbin et al. 1998 fig. 2.5 (BLOSUM50, linear gap 8: score 1) and the Needleman-Wunsch worked example (+1/-1/-1:
+    score 0), as custom matrices through the C ABI; both argument orders, and in the same job as unrelated filler so that
+    the pairs sit in full 32-subject chunks of the packed kernel."""
+    from published_vectors import VECTORS
+    rng = np.random.default_rng(77)
+    for name, alphabet, a, b, mat, go, ge, published in VECTORS:
+        letters = "AEGHPW" if alphabet == 0 else "ACGT"
+        filler = ["".join(rng.choice(list(letters), int(l))) for l in rng.integers(1, 40, 70)]
+        seqs = [a, b] + filler + [b, a]
+        with t.Context(alphabet=alphabet, matrix=mat, gap_open=go, gap_extend=ge, flags=t.FLAG_NO_DISTANCES) as ctx:
+            ctx.set_sequences(seqs)
+            ctx.run()
+            s = ctx.scores()
+        n = len(seqs)
+        assert s[t.pair_index(0, 1, n)] == published, name
+        assert s[t.pair_index(n - 2, n - 1, n)] == published, name
+        assert s[t.pair_index(0, n - 2, n)] == published and s[t.pair_index(1, n - 1, n)] == published, name   # (a, b) again, across the job
+        enc = [o.encode(x, alphabet) for x in seqs]
+        ref, _ = o.all_pairs(enc, mat, go, ge, nthreads=4)
+        assert (s == ref).all()

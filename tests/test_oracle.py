@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from np_gotoh import gotoh_np, gotoh_py
+from published_vectors import VECTORS
 from oracle import pyoracle as o
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -223,3 +224,16 @@ def test_simd_cpu_baseline_kernel_is_bit_identical_to_the_scalar_oracle():
     a, _ = o.all_pairs(encl, mat, 11, 1, nthreads=2)
     b, _ = o.rows_simd(encl, mat, 11, 1, nthreads=2)
     assert (a == b).all() and a[0] == 11 * 3100
+
+
+@pytest.mark.parametrize("name,alphabet,a,b,mat,go,ge,published", VECTORS, ids=[v[0] for v in VECTORS])
+def test_published_alignment_scores(name, alphabet, a, b, mat, go, ge, published):
+    """The anchors outside this repository (tests/published_vectors.py): the scalar oracle, its SIMD kernel, the
+    independent numpy and pure-Python statements all give the published optimum, in both argument orders."""
+    ea, eb = o.encode(a, alphabet), o.encode(b, alphabet)
+    assert o.gotoh(ea, eb, mat, go, ge) == published
+    assert o.gotoh(eb, ea, mat, go, ge) == published
+    assert gotoh_np(ea, eb, mat, go, ge) == published
+    assert gotoh_py(ea, eb, mat, go, ge) == published
+    simd, _ = o.rows_simd([ea, eb], mat, go, ge, nthreads=1)
+    assert simd.tolist() == [published]
