@@ -7,6 +7,9 @@ open 0 in the spec's cost go + k * ge.
    (The BLOSUM50 entries below are the ones of the book's figure 2.2 for the letters involved.)
 2. The worked example of the Needleman-Wunsch algorithm's encyclopedia entry: GATTACA against GCATGCU, match +1,
    mismatch -1, indel -1: best score 0.
+3. An AFFINE gap with end gaps penalised: the Biopython Tutorial's pairwise2 example
+   globalms("ACCGT", "ACG", 2, -1, -.5, -.1) -> score 5 (match 2, mismatch -1, a gap of k residues costs
+   0.5 + 0.1 (k - 1)).  Scaled by 10 to integers: match 20, mismatch -10, gap of k residues 4 + k, i.e. go 4, ge 1: 50.
 """
 import numpy as np
 
@@ -27,9 +30,9 @@ def blosum50_subset() -> np.ndarray:
     return m
 
 
-def unit_nucleotide() -> np.ndarray:
-    m = np.full((5, 5), -1, dtype=np.int8)
-    np.fill_diagonal(m, 1)
+def unit_nucleotide(match: int = 1, mismatch: int = -1) -> np.ndarray:
+    m = np.full((5, 5), mismatch, dtype=np.int8)
+    np.fill_diagonal(m, match)
     return m
 
 
@@ -37,4 +40,5 @@ def unit_nucleotide() -> np.ndarray:
 VECTORS = [
     ("Durbin et al. 1998, fig. 2.5", 0, "HEAGAWGHEE", "PAWHEAE", blosum50_subset(), 0, 8, 1),
     ("Needleman-Wunsch worked example", 1, "GATTACA", "GCATGCU", unit_nucleotide(), 0, 1, 0),
+    ("Biopython tutorial globalms, x10", 1, "ACCGT", "ACG", unit_nucleotide(20, -10), 4, 1, 50),
 ]
