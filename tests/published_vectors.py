@@ -10,6 +10,13 @@ open 0 in the spec's cost go + k * ge.
 3. An AFFINE gap with end gaps penalised: the Biopython Tutorial's pairwise2 example
    globalms("ACCGT", "ACG", 2, -1, -.5, -.1) -> score 5 (match 2, mismatch -1, a gap of k residues costs
    0.5 + 0.1 (k - 1)).  Scaled by 10 to integers: match 20, mismatch -10, gap of k residues 4 + k, i.e. go 4, ge 1: 50.
+4. Rosalind problem GLOB ("Global Alignment with Scoring Matrix"), sample dataset: PLEASANTLY against MEANLY, BLOSUM62,
+   linear gap penalty 5: maximum alignment score 8.
+5. Rosalind problem GAFF ("Global Alignment with Scoring Matrix and Affine Gap Penalty"), sample dataset: PRTEINS against
+   PRTWPSEIN, BLOSUM62, gap opening 11 and extension 1 (a gap of k residues costs 11 + (k - 1), i.e. go 10, ge 1 here):
+   maximum alignment score 8 (PRT---EINS / PRTWPSEIN-: a three-residue gap and a penalised end gap).
+4 and 5 use the library's DEFAULT protein matrix (matrix None below): they anchor the BLOSUM62 table of
+Consensus.cpp:34-59 as the library holds it, too.
 """
 import numpy as np
 
@@ -36,9 +43,11 @@ def unit_nucleotide(match: int = 1, mismatch: int = -1) -> np.ndarray:
     return m
 
 
-# (name, alphabet, sequence a, sequence b, matrix, gap open, gap extend, published score)
+# (name, alphabet, sequence a, sequence b, matrix or None = the library's default, gap open, gap extend, published score)
 VECTORS = [
     ("Durbin et al. 1998, fig. 2.5", 0, "HEAGAWGHEE", "PAWHEAE", blosum50_subset(), 0, 8, 1),
     ("Needleman-Wunsch worked example", 1, "GATTACA", "GCATGCU", unit_nucleotide(), 0, 1, 0),
     ("Biopython tutorial globalms, x10", 1, "ACCGT", "ACG", unit_nucleotide(20, -10), 4, 1, 50),
+    ("Rosalind GLOB sample", 0, "PLEASANTLY", "MEANLY", None, 0, 5, 8),
+    ("Rosalind GAFF sample", 0, "PRTEINS", "PRTWPSEIN", None, 10, 1, 8),
 ]

@@ -559,7 +559,7 @@ def test_published_alignment_scores_on_the_gpu():
     from published_vectors import VECTORS
     rng = np.random.default_rng(77)
     for name, alphabet, a, b, mat, go, ge, published in VECTORS:
-        letters = "AEGHPW" if alphabet == 0 else "ACGT"
+        letters = ("AEGHPW" if mat is not None else "ARNDCQEGHILKMFPSTWYV") if alphabet == 0 else "ACGT"
         filler = ["".join(rng.choice(list(letters), int(l))) for l in rng.integers(1, 40, 70)]
         seqs = [a, b] + filler + [b, a]
         with t.Context(alphabet=alphabet, matrix=mat, gap_open=go, gap_extend=ge, flags=t.FLAG_NO_DISTANCES) as ctx:
@@ -571,5 +571,5 @@ def test_published_alignment_scores_on_the_gpu():
         assert s[t.pair_index(n - 2, n - 1, n)] == published, name
         assert s[t.pair_index(0, n - 2, n)] == published and s[t.pair_index(1, n - 1, n)] == published, name   # (a, b) again, across the job
         enc = [o.encode(x, alphabet) for x in seqs]
-        ref, _ = o.all_pairs(enc, mat, go, ge, nthreads=4)
+        ref, _ = o.all_pairs(enc, o.matrix(alphabet) if mat is None else mat, go, ge, nthreads=4)
         assert (s == ref).all()

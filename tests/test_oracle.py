@@ -231,6 +231,7 @@ def test_published_alignment_scores(name, alphabet, a, b, mat, go, ge, published
     """The anchors outside this repository (tests/published_vectors.py): the scalar oracle, its SIMD kernel, the
     independent numpy and pure-Python statements all give the published optimum, in both argument orders."""
     ea, eb = o.encode(a, alphabet), o.encode(b, alphabet)
+    mat = o.matrix(alphabet) if mat is None else mat
     assert o.gotoh(ea, eb, mat, go, ge) == published
     assert o.gotoh(eb, ea, mat, go, ge) == published
     assert gotoh_np(ea, eb, mat, go, ge) == published
