@@ -3,9 +3,9 @@
  *
  * TEST INFRASTRUCTURE ONLY (see gotoh_oracle.h).  PARITY UNPINNED by the reference: there is
  * no alignment arithmetic in groundstate/tweakseq to restate; the spec
- * implemented here is the one frozen in SURVEY.md section 8c.  What anchors it outside this repository are five
+ * implemented here is the one frozen in SURVEY.md section 8c.  What anchors it outside this repository are seven
  * published optima (tests/published_vectors.py: Durbin et al. 1998 fig. 2.5, the Needleman-Wunsch worked example,
- * the Biopython tutorial's affine example, the sample datasets of Rosalind's GLOB and GAFF on BLOSUM62);
+ * the Biopython tutorial's affine example, the sample datasets of Rosalind's GLOB, GAFF, GCON on BLOSUM62 and EDIT);
  * everything else that pins it is listed in DESIGN.md section 3.2.
  *
  * What follows the reference:

@@ -15,7 +15,11 @@ open 0 in the spec's cost go + k * ge.
 5. Rosalind problem GAFF ("Global Alignment with Scoring Matrix and Affine Gap Penalty"), sample dataset: PRTEINS against
    PRTWPSEIN, BLOSUM62, gap opening 11 and extension 1 (a gap of k residues costs 11 + (k - 1), i.e. go 10, ge 1 here):
    maximum alignment score 8 (PRT---EINS / PRTWPSEIN-: a three-residue gap and a penalised end gap).
-4 and 5 use the library's DEFAULT protein matrix (matrix None below): they anchor the BLOSUM62 table of
+6. Rosalind problem GCON ("Global Alignment with Constant Gap Penalty"), sample dataset: PLEASANTLY against MEANLY,
+   BLOSUM62, every gap costs 5 whatever its length (go 5, ge 0): 13.
+7. Rosalind problem EDIT, sample dataset: the edit distance of PLEASANTLY and MEANLY is 5 -- as an alignment with match 0,
+   mismatch -1 and indel -1 the optimum is -5.
+4, 5 and 6 use the library's DEFAULT protein matrix (matrix None below): they anchor the BLOSUM62 table of
 Consensus.cpp:34-59 as the library holds it, too.
 """
 import numpy as np
@@ -37,6 +41,12 @@ def blosum50_subset() -> np.ndarray:
     return m
 
 
+def edit_distance_matrix() -> np.ndarray:
+    m = np.full((23, 23), -1, dtype=np.int8)
+    np.fill_diagonal(m, 0)
+    return m
+
+
 def unit_nucleotide(match: int = 1, mismatch: int = -1) -> np.ndarray:
     m = np.full((5, 5), mismatch, dtype=np.int8)
     np.fill_diagonal(m, match)
@@ -50,4 +60,6 @@ VECTORS = [
     ("Biopython tutorial globalms, x10", 1, "ACCGT", "ACG", unit_nucleotide(20, -10), 4, 1, 50),
     ("Rosalind GLOB sample", 0, "PLEASANTLY", "MEANLY", None, 0, 5, 8),
     ("Rosalind GAFF sample", 0, "PRTEINS", "PRTWPSEIN", None, 10, 1, 8),
+    ("Rosalind GCON sample", 0, "PLEASANTLY", "MEANLY", None, 5, 0, 13),
+    ("Rosalind EDIT sample", 0, "PLEASANTLY", "MEANLY", edit_distance_matrix(), 0, 1, -5),
 ]
